@@ -1,0 +1,177 @@
+/*
+ * magcache_b200 — C ABI of the B200-native MagCache hot path (libmagcache_b200.so).
+ *
+ * Every entry point takes plain pointers and sizes (no torch types). Device pointers are raw CUDA device
+ * addresses (tensor.data_ptr()); `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ * All functions return 0 on success and a negative MC_ERR_* code on failure; mc_last_error() returns a
+ * thread-local, human-readable description of the last failure. Nothing here falls back to the CPU:
+ * device entry points fail with MC_ERR_CUDA if no sm_100 device/driver is usable.
+ *
+ * Each declaration cites the reference statement(s) it replaces (paths relative to the Zehong-Ma/MagCache tree).
+ */
+#ifndef MAGCACHE_B200_H_
+#define MAGCACHE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_OK 0
+#define MC_ERR_INVALID (-1) /* bad argument (null pointer, bad dtype, shape/alignment not supported) */
+#define MC_ERR_CUDA (-2)    /* CUDA runtime/driver error (message carries cudaGetErrorString) */
+#define MC_ERR_STATE (-3)   /* controller asked to re-use a residual that was never stored, cnt out of range, ... */
+
+/* element types of device buffers */
+#define MC_F32 0
+#define MC_BF16 1
+
+const char* mc_last_error(void);
+int32_t mc_abi_version(void); /* bumped whenever a signature in this header changes */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host logic (float64 / int, bit-exact with the reference's Python/numpy arithmetic)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* nearest_interp(src_array, target_length)          MagCache4Wan2.1/magcache_generate.py:27-34
+ * (identical copies: MagCache4FLUX/magcache_flux.py:12-19, MagCache4HunyuanVideo/magcache_sample_video.py:20-27).
+ * idx = round_half_even(arange(T) * (L-1)/(T-1)); T == 1 -> src[L-1]. `dst` has T entries. */
+int32_t mc_nearest_interp(const double* src, int32_t L, double* dst, int32_t T);
+
+/* Per-CFG-branch form used by Wan (magcache_generate.py:915-919): de-interleave [0::2]/[1::2], interpolate each
+ * to `steps`, re-interleave. src has 2*L_half entries, dst 2*steps entries. */
+int32_t mc_nearest_interp_cfg(const double* src, int32_t L_total, double* dst, int32_t steps);
+
+/* Controller variants. */
+#define MC_CMP_LT 0            /* err <  thresh : Wan2.1 magcache_generate.py:286 */
+#define MC_CMP_LE 1            /* err <= thresh : FLUX magcache_flux.py:332, Hunyuan magcache_sample_video.py:96 */
+#define MC_RETAIN_FLOOR 0      /* cnt >= int(num_steps*R)       Wan :279, Hunyuan :90 */
+#define MC_RETAIN_HALF_UP 1    /* cnt >= int(R*num_steps + 0.5) FLUX :327 */
+#define MC_RETAIN_CEIL 2       /* cnt >= ceil(R*num_steps)      OmniGen2 magcache_utils.py:343 */
+
+typedef struct mc_ctrl_config {
+  int32_t num_steps;       /* forward calls per video: 2*sample_steps for CFG models (Wan :899), steps otherwise */
+  int32_t branches;        /* 1 = scalar state (FLUX/Hunyuan), 2 = state per CFG branch, branch = cnt % 2 (Wan :281-288) */
+  int32_t K;               /* max consecutive skips (accumulated_steps <= K) */
+  int32_t cmp;             /* MC_CMP_* */
+  int32_t retention_mode;  /* MC_RETAIN_* */
+  int32_t veto_index;      /* -1 = none. FLUX :332: never skip when round_half_even(cnt*((veto_base-1)/(num_steps-1))) == veto_index */
+  int32_t veto_base;       /* 28 for FLUX */
+  int32_t reserved;
+  double thresh;           /* magcache_thresh */
+  double retention_ratio;
+  const double* mag_ratios; /* [num_steps], already interpolated; borrowed for the duration of the call / handle */
+} mc_ctrl_config;
+
+typedef struct mc_ctrl_state { /* mirrors the reference's class attributes (magcache_generate.py:897-906) */
+  int32_t cnt;
+  int32_t accumulated_steps[2];
+  int32_t pad;
+  double accumulated_ratio[2];
+  double accumulated_err[2];
+} mc_ctrl_state;
+
+/* One controller decision = the `if self.cnt >= int(self.num_steps*self.retention_ratio):` statement,
+ * magcache_generate.py:279-292 (FLUX :327-338, Hunyuan :90-102). Updates `st` in place, writes 1/0 to *skip.
+ * Does NOT advance cnt (see mc_ctrl_advance). */
+int32_t mc_ctrl_decide(const mc_ctrl_config* cfg, mc_ctrl_state* st, int32_t* skip);
+/* `self.cnt += 1; if self.cnt >= self.num_steps: reset`   magcache_generate.py:306-311. */
+int32_t mc_ctrl_advance(const mc_ctrl_config* cfg, mc_ctrl_state* st);
+/* Whole schedule: run `calls` decisions from a fresh state, mask[i] in {0,1}. */
+int32_t mc_ctrl_mask(const mc_ctrl_config* cfg, int32_t calls, uint8_t* mask);
+/* Reject configurations the reference would crash on (Appendix A quirk 4: cnt 0 eligible with an empty cache). */
+int32_t mc_ctrl_validate(const mc_ctrl_config* cfg);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Residual-cache kernels (HBM-bound)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* cache-hit branch  `x = x + residual_x`            magcache_generate.py:295 (FLUX :340, Hunyuan :104).
+ * out[i] = x[i] + r[i], computed in fp32, rounded to out_dtype (torch type promotion: bf16+fp32->fp32, bf16+bf16->bf16).
+ * out must not overlap x or r (inputs are streamed through the non-coherent path). n = element count. */
+int32_t mc_cache_hit_add(const void* x, int32_t x_dtype, const void* r, int32_t r_dtype, void* out, int32_t out_dtype,
+                         int64_t n, void* stream);
+
+/* cache-miss epilogue `residual_x = x - ori_x`      magcache_generate.py:299 (FLUX :426, Hunyuan :140). */
+int32_t mc_residual_sub(const void* x_out, int32_t xo_dtype, const void* x_in, int32_t xi_dtype, void* r, int32_t r_dtype,
+                        int64_t n, void* stream);
+
+/* calibration statistics                              magcache_generate.py:167-169 (one pass instead of ~7 + 3 syncs).
+ * r_cur, r_prev: [rows, cols]. stats (device, 4 doubles, overwritten): sum(ratio), sum(ratio^2), sum(1-cos), rows
+ * with ratio = ||r_cur[i]||2 / (||r_prev[i]||2 + denom_eps)  (denom_eps = 0 Wan :167; 1e-8 eval variant wan_magcache.py:652)
+ * and cos with eps 1e-8 as F.cosine_similarity. Host side: mean = s0/n, std = sqrt((s1 - s0^2/n)/(n-1)), cos_dis = s2/n. */
+int32_t mc_residual_stats(const void* r_cur, int32_t cur_dtype, const void* r_prev, int32_t prev_dtype, int64_t rows,
+                          int32_t cols, double denom_eps, double* stats_dev, void* stream);
+
+/* Fused miss epilogue for calibration runs: r = x_out - x_in, and the statistics of r against r_prev in the same pass. */
+int32_t mc_residual_sub_stats(const void* x_out, int32_t xo_dtype, const void* x_in, int32_t xi_dtype, void* r,
+                              const void* r_prev, int64_t rows, int32_t cols, double denom_eps, double* stats_dev,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * DiT block-stack kernels (cache-miss branch `for block in self.blocks: x = block(x, **kwargs)`,
+ * magcache_generate.py:297-298; block arithmetic per upstream Wan2.1 wan/modules/model.py)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* patch_embedding input side (magcache_generate.py:237): latent fp32 [C, F, H, W] -> token-major im2col
+ * bf16 [F*(H/2)*(W/2), C*4] (column = c*4 + dh*2 + dw, the Conv3d weight's flattened (c, kt=1, kh, kw) order). */
+int32_t mc_patchify(const float* latent, int32_t C, int32_t F, int32_t H, int32_t W, void* tokens_bf16, void* stream);
+
+/* AdaLN-modulated LayerNorm: y = LN(x) * (a) + b, eps, no affine inside LN; per-row fp32 statistics.
+ *   mode 0: a = 1 + (mod[scale_idx] + e[scale_idx]),  b = mod[shift_idx] + e[shift_idx]   (block norm1/norm2, head)
+ *   mode 1: a = w, b = bias                                                             (norm3, elementwise affine)
+ * x: [rows, cols] (x_dtype fp32 or bf16); round_ln_to_bf16 != 0 reproduces `.type_as(x)` for a bf16 stream (block 0).
+ * out: [rows, cols], out_dtype bf16 (GEMM operand) or fp32. */
+int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t cols, float eps, int32_t mode,
+                       const float* a_or_mod, const float* b_or_e, int32_t scale_idx, int32_t shift_idx,
+                       int32_t round_ln_to_bf16, void* out, int32_t out_dtype, void* stream);
+
+/* WanRMSNorm over the full model dim followed by 3-axis RoPE (rope_apply), in place on bf16 [rows, cols]:
+ *   y = bf16(rope(float(bf16(x * rsqrt(mean(x^2)+eps))) * w)).  cos_sin == NULL -> no RoPE (cross-attention q/k).
+ * cos_sin: fp32 [rows, head_dim] interleaved (cos, sin) per complex pair, i.e. [rows, head_dim/2, 2]; row = token. */
+int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, const float* w, float eps,
+                        const float* cos_sin, int32_t head_dim, void* stream);
+
+/* bf16 GEMM on tcgen05/TMEM, TMA-fed:  acc[m,n] = sum_k A[m,k] * B[n,k]   (A: [M,K] row-major, B: [N,K] row-major).
+ * lda/ldb/ldo in elements; K % 8 == 0, lda % 8 == 0, ldb % 8 == 0, 16-byte aligned bases. */
+#define MC_EPI_BIAS_BF16 0        /* out_bf16[m,n] = bf16(acc + bias[n])                              nn.Linear under autocast */
+#define MC_EPI_BIAS_GELU_BF16 1   /* out_bf16 = bf16(gelu_tanh(float(bf16(acc + bias[n]))))            ffn[0] + GELU(tanh) */
+#define MC_EPI_BIAS_GATE_RESID 2  /* resid_f32[m,n] += float(bf16(acc + bias[n])) * gate[n] (gate NULL -> 1) `x = x + y * e[2]` */
+#define MC_EPI_ROWBIAS_BF16 3     /* out_bf16[m,n] = bf16(acc + bias[m])                               V^T = Wv * h^T + bv */
+#define MC_EPI_BIAS_F32 4         /* out_f32[m,n] = acc + bias[n]                                                           */
+int32_t mc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
+                     const float* bias, int32_t epilogue, void* out, int64_t ldo, const float* gate, void* stream);
+
+/* Non-causal attention forward on tcgen05: out[i, h*128:(h+1)*128] = softmax(q_h k_h^T * scale) v_h, head_dim = 128.
+ * q: [Lq, heads*128] bf16 (ldq), k: [Lk, heads*128] bf16 (ldk), vt: V transposed [heads*128, Lk] bf16 (ldvt >= Lk, %8),
+ * out: [Lq, heads*128] bf16 (ldo). */
+int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out,
+                    int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* stream);
+
+/* Small fp32 linear for the time-embedding path (autocast-disabled region, magcache_generate.py:249-254):
+ * y[m, n] = act(sum_k x[m,k] * W[n,k] + b[n]), M <= 8. act: 0 none, 1 SiLU applied to the INPUT x first (time_projection),
+ * 2 SiLU applied to the output. */
+int32_t mc_linear_f32_small(const float* x, int32_t M, int32_t K, const float* W, const float* b, int32_t N, int32_t act,
+                            float* y, void* stream);
+
+/* Head + unpatchify (magcache_generate.py:304-305): out[c, f, 2h+p, 2w+q] = Linear_fp32(LN(x)*(1+e1)+e0)[token, (p,q,c)].
+ * x: [rows = F*Hp*Wp, cols] (fp32, or the un-materialised hit sum x0_bf16 + r_f32 when r != NULL: fused cache-hit path).
+ * head_mod: [2, cols] modulation parameter, e: [cols] time embedding, Wt: head.weight TRANSPOSED [cols, 64] fp32, b: [64];
+ * out fp32 [C, F, 2Hp, 2Wp]. */
+int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int32_t cols, int32_t F, int32_t Hp,
+                           int32_t Wp, int32_t C_out, const float* head_mod, const float* e, const float* Wt, const float* b,
+                           float eps, float* out, void* stream);
+
+/* sinusoidal_embedding_1d(freq_dim, t) in float64, cos half first (magcache_generate.py:250-251): pos_dev [n_pos] f64 ->
+ * out fp32 [n_pos, dim]. */
+int32_t mc_time_sinusoid(const double* pos_dev, int32_t n_pos, int32_t dim, float* out, void* stream);
+
+/* elementwise helpers */
+int32_t mc_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+int32_t mc_gelu_tanh_bf16(void* x_bf16, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGCACHE_B200_H_ */

@@ -1,0 +1,84 @@
+"""ctypes binding of libmagcache_b200.so (the C ABI declared in include/magcache_b200.h).
+
+There is no fallback: if the shared library has not been built (`python -m magcache_b200.build`) importing
+this module raises, and every device entry point raises `MagCacheError` when CUDA reports a failure.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_uint8, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmagcache_b200.so")
+
+MC_OK = 0
+MC_ERR_INVALID, MC_ERR_CUDA, MC_ERR_STATE = -1, -2, -3
+MC_F32, MC_BF16 = 0, 1
+MC_CMP_LT, MC_CMP_LE = 0, 1
+MC_RETAIN_FLOOR, MC_RETAIN_HALF_UP, MC_RETAIN_CEIL = 0, 1, 2
+MC_EPI_BIAS_BF16, MC_EPI_BIAS_GELU_BF16, MC_EPI_BIAS_GATE_RESID, MC_EPI_ROWBIAS_BF16, MC_EPI_BIAS_F32 = 0, 1, 2, 3, 4
+
+
+class MagCacheError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmagcache_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CtrlConfig(Structure):
+    _fields_ = [("num_steps", c_int32), ("branches", c_int32), ("K", c_int32), ("cmp", c_int32), ("retention_mode", c_int32),
+                ("veto_index", c_int32), ("veto_base", c_int32), ("reserved", c_int32), ("thresh", c_double),
+                ("retention_ratio", c_double), ("mag_ratios", POINTER(c_double))]
+
+
+class CtrlState(Structure):
+    _fields_ = [("cnt", c_int32), ("accumulated_steps", c_int32 * 2), ("pad", c_int32), ("accumulated_ratio", c_double * 2),
+                ("accumulated_err", c_double * 2)]
+
+
+# name -> argtypes ; every function returns int32 except mc_last_error. Kept in one table so the CPU test-suite can check
+# that the library exports exactly what the header declares.
+SIGNATURES = {
+    "mc_abi_version": [],
+    "mc_nearest_interp": [POINTER(c_double), c_int32, POINTER(c_double), c_int32],
+    "mc_nearest_interp_cfg": [POINTER(c_double), c_int32, POINTER(c_double), c_int32],
+    "mc_ctrl_decide": [POINTER(CtrlConfig), POINTER(CtrlState), POINTER(c_int32)],
+    "mc_ctrl_advance": [POINTER(CtrlConfig), POINTER(CtrlState)],
+    "mc_ctrl_mask": [POINTER(CtrlConfig), c_int32, POINTER(c_uint8)],
+    "mc_ctrl_validate": [POINTER(CtrlConfig)],
+    "mc_cache_hit_add": [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
+    "mc_residual_sub": [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
+    "mc_residual_stats": [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_double, c_void_p, c_void_p],
+    "mc_residual_sub_stats": [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p, c_void_p],
+    "mc_patchify": [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p],
+    "mc_ln_modulate": [c_void_p, c_int32, c_int64, c_int32, c_float, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                       c_int32, c_void_p],
+    "mc_rmsnorm_rope": [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_float, c_void_p, c_int32, c_void_p],
+    "mc_gemm_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p,
+                     c_void_p],
+    "mc_attn_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
+                    c_void_p],
+    "mc_linear_f32_small": [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p],
+    "mc_head_unpatchify": [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_float, c_void_p, c_void_p],
+    "mc_time_sinusoid": [c_void_p, c_int32, c_int32, c_void_p, c_void_p],
+    "mc_cast": [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
+    "mc_gelu_tanh_bf16": [c_void_p, c_int64, c_void_p],
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: the CUDA extension has not been built. Run `python -m magcache_b200.build` "
+        "(needs nvcc; cross-compiles for sm_100a without a GPU). There is no CPU/eager fallback by design.")
+
+lib = ctypes.CDLL(LIB_PATH)
+lib.mc_last_error.restype = c_char_p
+lib.mc_last_error.argtypes = []
+for _name, _args in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = c_int32
+    _fn.argtypes = _args
+
+
+def check(rc):
+    if rc != MC_OK:
+        raise MagCacheError(rc, lib.mc_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,297 @@
+// Non-causal flash-attention forward on tcgen05/TMEM, head_dim 128 — the self-/cross-attention of the Wan DiT block
+// (reference call chain MagCache4Wan2.1/magcache_generate.py:297-298 -> WanSelfAttention.forward ->
+// flash_attention / SDPA, upstream wan/modules/{model,attention}.py).
+//
+// One CTA = one 128-row query tile of one head; KV is streamed in 64-row tiles. Two CTAs are co-resident per SM
+// (256 TMEM columns and ~112 KB smem each), so one CTA's softmax overlaps the other's MMAs.
+//   warps 0-3  softmax    : thread = query row (TMEM lane). tcgen05.ld S, online softmax in the exp2 domain with lazy
+//                           rescaling of O (only when the running max grows by > 8), P -> bf16 -> swizzled smem
+//   warp 4     TMA        : Q once; K tile (2 boxes) and V^T tile (1 box) per iteration into 2-stage rings
+//   warp 5     MMA issuer : S_j = Q K_j^T (M128 N64 K128, double-buffered in TMEM), O += P_j V_j (M128 N128 K64)
+// V is consumed transposed (V^T [heads*128, Lk], produced directly by the V-projection GEMM) so that both MMAs see
+// K-major operands — the same smem/UMMA descriptor path the GEMM kernel uses.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace mc {
+
+constexpr int kBQ = 128, kBKV = 64, kHD = 128;
+constexpr int kQBytes = kBQ * kHD * 2;     // 32 KB (two 64-column boxes of 16 KB)
+constexpr int kKBytes = kBKV * kHD * 2;    // 16 KB (two boxes of 8 KB)
+constexpr int kVBytes = kHD * kBKV * 2;    // 16 KB (one box: 128 d-rows x 64 kv)
+constexpr int kPBytes = kBQ * kBKV * 2;    // 16 KB
+constexpr int kKVStages = 2;
+constexpr int kOffQ = 0;
+constexpr int kOffK = kOffQ + kQBytes;
+constexpr int kOffV = kOffK + kKVStages * kKBytes;
+constexpr int kOffP = kOffV + kKVStages * kVBytes;
+constexpr int kOffBar = kOffP + kPBytes;  // 112 KB
+constexpr int kAttnSmem = kOffBar + 256;
+constexpr int kAttnThreads = 192;
+constexpr int kTmemCols = 256;  // S0 [0,64) S1 [64,128) O [128,256)
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+struct AttnParams {
+  int Lq, Lk, heads;
+  float scale_log2;  // softmax scale * log2(e)
+  __nv_bfloat16* out;
+  int64_t ldo;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+    attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;   // [2]
+  uint64_t* s_free = bars + 11;  // [2]
+  uint64_t* p_full = bars + 13;
+  uint64_t* pv_done = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int head = blockIdx.y;
+  const int n_tiles = (p.Lk + kBKV - 1) / kBKV;
+
+  if (threadIdx.x == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) {
+      printf("attn_fwd_kernel: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_k);
+    ptx::prefetch_tmap(&tmap_vt);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&k_full[s], 1);
+      ptx::mbar_init(&k_empty[s], 1);
+      ptx::mbar_init(&v_full[s], 1);
+      ptx::mbar_init(&v_empty[s], 1);
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&s_free[s], 128);
+    }
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(pv_done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 5) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 4) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      ptx::mbar_expect_tx(q_full, kQBytes);
+      ptx::tma_load_2d(smem + kOffQ, &tmap_q, q_full, head * kHD, q0);
+      ptx::tma_load_2d(smem + kOffQ + kQBytes / 2, &tmap_q, q_full, head * kHD + 64, q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        ptx::mbar_wait(&k_empty[s], ph ^ 1);
+        ptx::mbar_expect_tx(&k_full[s], kKBytes);
+        ptx::tma_load_2d(smem + kOffK + s * kKBytes, &tmap_k, &k_full[s], head * kHD, j * kBKV);
+        ptx::tma_load_2d(smem + kOffK + s * kKBytes + kKBytes / 2, &tmap_k, &k_full[s], head * kHD + 64, j * kBKV);
+        ptx::mbar_wait(&v_empty[s], ph ^ 1);
+        ptx::mbar_expect_tx(&v_full[s], kVBytes);
+        ptx::tma_load_2d(smem + kOffV + s * kVBytes, &tmap_vt, &v_full[s], j * kBKV, head * kHD);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(kBQ, kBKV);  // 128 x 64
+      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32(kBQ, kHD);   // 128 x 128
+      const uint32_t q_addr = ptx::smem_u32(smem + kOffQ);
+      const uint32_t p_addr = ptx::smem_u32(smem + kOffP);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        const uint32_t k_addr = ptx::smem_u32(smem + kOffK + s * kKBytes);
+        const uint32_t tmem_s = tmem_base + s * kBKV;
+#pragma unroll
+        for (int kk = 0; kk < kHD / 16; ++kk) {
+          const uint64_t da = ptx::umma_desc_sw128_kmajor(q_addr + (kk >> 2) * (kQBytes / 2)) + 2 * (kk & 3);
+          const uint64_t db = ptx::umma_desc_sw128_kmajor(k_addr + (kk >> 2) * (kKBytes / 2)) + 2 * (kk & 3);
+          ptx::umma_ss(tmem_s, da, db, idesc_s, kk != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&k_empty[s]);
+        ptx::umma_commit(&s_full[s]);
+      };
+      ptx::mbar_wait(q_full, 0);
+      ptx::mbar_wait(&k_full[0], 0);
+      ptx::tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) {
+          const int t = j + 1;
+          ptx::mbar_wait(&k_full[t & 1], (t >> 1) & 1);
+          if (t >= 2) ptx::mbar_wait(&s_free[t & 1], ((t - 2) >> 1) & 1);  // softmax of tile t-2 has drained this S buffer
+          ptx::tc_fence_after();
+          issue_s(t);
+        }
+        ptx::mbar_wait(p_full, j & 1);
+        ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t v_addr = ptx::smem_u32(smem + kOffV + (j & 1) * kVBytes);
+#pragma unroll
+        for (int kk = 0; kk < kBKV / 16; ++kk) {
+          const uint64_t da = ptx::umma_desc_sw128_kmajor(p_addr) + 2 * kk;
+          const uint64_t db = ptx::umma_desc_sw128_kmajor(v_addr) + 2 * kk;
+          ptx::umma_ss(tmem_o, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&v_empty[j & 1]);
+        ptx::umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ------------------------------------------------ softmax warps -----------------------------------------------
+    const int r = warp * 32 + lane;  // row inside the Q tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    uint8_t* p_row = smem + kOffP + (r >> 3) * 1024 + (r & 7) * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int b = j & 1;
+      ptx::mbar_wait(&s_full[b], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t sreg[2][32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV, sreg[0]);
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV + 32, sreg[1]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s_free[b]);
+
+      const int valid = p.Lk - j * kBKV;  // columns >= valid are padding (only on the last tile)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float s = __uint_as_float(sreg[h][c]);
+          if (h * 32 + c >= valid) s = -INFINITY;
+          sreg[h][c] = __float_as_uint(s);
+          mx = fmaxf(mx, s);
+        }
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      bool waited = false;
+      if (j == 0) {
+        m = m_new;
+      } else {
+        const bool need = m_new > m + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // O must be quiescent: PV(j-1) complete
+          ptx::mbar_wait(pv_done, (j - 1) & 1);
+          ptx::tc_fence_after();
+          waited = true;
+          const float factor = need ? ptx::ex2_approx(m - m_new) : 1.0f;
+          if (need) {
+            l *= factor;
+            m = m_new;
+          }
+#pragma unroll 1
+          for (int c = 0; c < kHD / 32; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld_32x32b_x32(tmem_o + lane_sel + c * 32, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            ptx::tmem_st_32x32b_x32(tmem_o + lane_sel + c * 32, o);
+          }
+          ptx::tmem_st_wait();
+        }
+      }
+      // P = 2^(s*scale - m), row sum in fp32 before the bf16 rounding (as flash-attention does)
+      float psum = 0.f;
+      uint32_t packed[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[h][c]), p.scale_log2, -m));
+          const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[h][c + 1]), p.scale_log2, -m));
+          psum += p0 + p1;
+          packed[h * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
+        }
+      l += psum;
+      if (j > 0 && !waited) {
+        ptx::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) has finished reading the P buffer
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {  // 8 x 16-byte chunks per 128-byte row, XOR-swizzled with (row % 8)
+        uint4 w = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
+        *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) = w;
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global
+    ptx::mbar_wait(pv_done, (n_tiles - 1) & 1);
+    ptx::tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int row = q0 + r;
+#pragma unroll 1
+    for (int c = 0; c < kHD / 32; ++c) {
+      uint32_t o[32];
+      ptx::tmem_ld_32x32b_x32(tmem_o + lane_sel + c * 32, o);
+      ptx::tmem_ld_wait();
+      if (row < p.Lq) {
+        __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + i) = w;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace mc
+
+extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out,
+                               int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* stream) {
+  MC_CHECK_ARG(q && k && vt && out, "mc_attn_fwd: null pointer");
+  MC_CHECK_ARG(Lq >= 1 && Lk >= 1 && heads >= 1, "mc_attn_fwd: Lq=%d Lk=%d heads=%d", Lq, Lk, heads);
+  const int64_t width = static_cast<int64_t>(heads) * mc::kHD;
+  MC_CHECK_ARG(ldq >= width && ldk >= width && ldo >= width && ldvt >= Lk, "mc_attn_fwd: leading dimensions too small");
+  MC_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && ldo % 8 == 0, "mc_attn_fwd: leading dimensions must be multiples of 8");
+  MC_CHECK_ARG(mc::aligned16(q) && mc::aligned16(k) && mc::aligned16(vt) && mc::aligned16(out), "mc_attn_fwd: pointers must be 16-byte aligned");
+  CUtensorMap tq, tk, tv;
+  int32_t rc = mc::make_tmap_bf16_2d(&tq, q, static_cast<uint64_t>(Lq), static_cast<uint64_t>(width), static_cast<uint64_t>(ldq), mc::kBQ, 64);
+  if (rc) return rc;
+  rc = mc::make_tmap_bf16_2d(&tk, k, static_cast<uint64_t>(Lk), static_cast<uint64_t>(width), static_cast<uint64_t>(ldk), mc::kBKV, 64);
+  if (rc) return rc;
+  rc = mc::make_tmap_bf16_2d(&tv, vt, static_cast<uint64_t>(width), static_cast<uint64_t>(Lk), static_cast<uint64_t>(ldvt), mc::kHD, mc::kBKV);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mc::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    if (e != cudaSuccess) return mc::cuda_fail(e, "cudaFuncSetAttribute(attn smem)");
+    attr_set = true;
+  }
+  mc::AttnParams p{Lq, Lk, heads, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo};
+  dim3 grid((Lq + mc::kBQ - 1) / mc::kBQ, heads);
+  mc::attn_fwd_kernel<<<grid, mc::kAttnThreads, mc::kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  MC_CHECK_LAUNCH("attn_fwd_kernel launch");
+  return MC_OK;
+}

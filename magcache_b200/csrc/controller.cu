@@ -1,0 +1,185 @@
+// Host-side MagCache logic: error plumbing, nearest_interp, and the skip controller.
+// float64 / int arithmetic in exactly the reference's operation order so the skip mask is bit-exact.
+//   controller   MagCache4Wan2.1/magcache_generate.py:277-292, :306-311
+//                MagCache4FLUX/magcache_flux.py:326-338, :431-436
+//                MagCache4HunyuanVideo/magcache_sample_video.py:88-102, :149-154
+//   interp       MagCache4Wan2.1/magcache_generate.py:27-34, :915-919
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+// first call index that is allowed to skip
+static int32_t retention_start(const mc_ctrl_config* c) {
+  const double n = static_cast<double>(c->num_steps);
+  switch (c->retention_mode) {
+    case MC_RETAIN_HALF_UP:
+      return static_cast<int32_t>(c->retention_ratio * n + 0.5);  // int(R*n + 0.5)
+    case MC_RETAIN_CEIL:
+      return static_cast<int32_t>(std::ceil(c->retention_ratio * n));
+    default:
+      return static_cast<int32_t>(n * c->retention_ratio);  // int(n*R): truncation
+  }
+}
+
+static int32_t check_cfg(const mc_ctrl_config* c) {
+  MC_CHECK_ARG(c != nullptr, "mc_ctrl: null config");
+  MC_CHECK_ARG(c->num_steps >= 1, "mc_ctrl: num_steps=%d must be >= 1", c->num_steps);
+  MC_CHECK_ARG(c->branches == 1 || c->branches == 2, "mc_ctrl: branches=%d must be 1 or 2", c->branches);
+  MC_CHECK_ARG(c->mag_ratios != nullptr, "mc_ctrl: mag_ratios is null (reference: AttributeError, no table matched ckpt_dir)");
+  MC_CHECK_ARG(c->cmp == MC_CMP_LT || c->cmp == MC_CMP_LE, "mc_ctrl: bad cmp %d", c->cmp);
+  MC_CHECK_ARG(c->retention_mode >= 0 && c->retention_mode <= 2, "mc_ctrl: bad retention_mode %d", c->retention_mode);
+  MC_CHECK_ARG(c->veto_index < 0 || c->num_steps >= 2, "mc_ctrl: step veto needs num_steps >= 2 (reference divides by num_steps-1)");
+  return MC_OK;
+}
+
+static inline void reset_branch(mc_ctrl_state* st, int i) {
+  st->accumulated_err[i] = 0.0;
+  st->accumulated_steps[i] = 0;
+  st->accumulated_ratio[i] = 1.0;
+}
+
+static int32_t decide(const mc_ctrl_config* c, mc_ctrl_state* st) {
+  if (st->cnt < retention_start(c)) return 0;
+  const int i = (c->branches == 2) ? (st->cnt % 2) : 0;
+  const double cur = c->mag_ratios[st->cnt];
+  st->accumulated_ratio[i] = st->accumulated_ratio[i] * cur;
+  st->accumulated_steps[i] += 1;
+  const double skip_err = std::fabs(1.0 - st->accumulated_ratio[i]);
+  st->accumulated_err[i] += skip_err;
+  bool ok = (c->cmp == MC_CMP_LE) ? (st->accumulated_err[i] <= c->thresh) : (st->accumulated_err[i] < c->thresh);
+  ok = ok && (st->accumulated_steps[i] <= c->K);
+  if (c->veto_index >= 0) {
+    // np.round(cnt * ((base-1)/(num_steps-1))).astype(int) != veto_index ; nearbyint = round-half-even
+    const double scale = static_cast<double>(c->veto_base - 1) / static_cast<double>(c->num_steps - 1);
+    const long mapped = static_cast<long>(std::nearbyint(static_cast<double>(st->cnt) * scale));
+    ok = ok && (mapped != c->veto_index);
+  }
+  if (ok) return 1;
+  reset_branch(st, i);
+  return 0;
+}
+
+static void advance(const mc_ctrl_config* c, mc_ctrl_state* st) {
+  st->cnt += 1;
+  if (st->cnt >= c->num_steps) {
+    st->cnt = 0;
+    reset_branch(st, 0);
+    reset_branch(st, 1);
+  }
+}
+
+}  // namespace mc
+
+extern "C" {
+
+const char* mc_last_error(void) { return mc::g_err; }
+int32_t mc_abi_version(void) { return 1; }
+
+int32_t mc_nearest_interp(const double* src, int32_t L, double* dst, int32_t T) {
+  MC_CHECK_ARG(src && dst, "mc_nearest_interp: null pointer");
+  MC_CHECK_ARG(L >= 1 && T >= 1, "mc_nearest_interp: L=%d T=%d must be >= 1", L, T);
+  if (T == 1) {
+    dst[0] = src[L - 1];
+    return MC_OK;
+  }
+  const double scale = static_cast<double>(L - 1) / static_cast<double>(T - 1);
+  for (int32_t i = 0; i < T; ++i) {
+    const long idx = static_cast<long>(std::nearbyint(static_cast<double>(i) * scale));  // np.round: half to even
+    MC_CHECK_ARG(idx >= 0 && idx < L, "mc_nearest_interp: index %ld out of range", idx);
+    dst[i] = src[idx];
+  }
+  return MC_OK;
+}
+
+int32_t mc_nearest_interp_cfg(const double* src, int32_t L_total, double* dst, int32_t steps) {
+  MC_CHECK_ARG(src && dst, "mc_nearest_interp_cfg: null pointer");
+  MC_CHECK_ARG(L_total >= 2 && L_total % 2 == 0 && steps >= 1, "mc_nearest_interp_cfg: L_total=%d steps=%d", L_total, steps);
+  const int32_t L = L_total / 2;
+  std::vector<double> a(L), b(L), oa(steps), ob(steps);
+  for (int32_t i = 0; i < L; ++i) {
+    a[i] = src[2 * i];
+    b[i] = src[2 * i + 1];
+  }
+  int32_t rc = mc_nearest_interp(a.data(), L, oa.data(), steps);
+  if (rc) return rc;
+  rc = mc_nearest_interp(b.data(), L, ob.data(), steps);
+  if (rc) return rc;
+  for (int32_t i = 0; i < steps; ++i) {
+    dst[2 * i] = oa[i];
+    dst[2 * i + 1] = ob[i];
+  }
+  return MC_OK;
+}
+
+int32_t mc_ctrl_decide(const mc_ctrl_config* cfg, mc_ctrl_state* st, int32_t* skip) {
+  int32_t rc = mc::check_cfg(cfg);
+  if (rc) return rc;
+  MC_CHECK_ARG(st && skip, "mc_ctrl_decide: null pointer");
+  if (st->cnt < 0 || st->cnt >= cfg->num_steps) {
+    mc::set_error("mc_ctrl_decide: cnt=%d outside [0, %d)", st->cnt, cfg->num_steps);
+    return MC_ERR_STATE;
+  }
+  *skip = mc::decide(cfg, st);
+  return MC_OK;
+}
+
+int32_t mc_ctrl_advance(const mc_ctrl_config* cfg, mc_ctrl_state* st) {
+  MC_CHECK_ARG(cfg && st, "mc_ctrl_advance: null pointer");
+  mc::advance(cfg, st);
+  return MC_OK;
+}
+
+int32_t mc_ctrl_mask(const mc_ctrl_config* cfg, int32_t calls, uint8_t* mask) {
+  int32_t rc = mc::check_cfg(cfg);
+  if (rc) return rc;
+  MC_CHECK_ARG(mask && calls >= 0, "mc_ctrl_mask: bad arguments");
+  mc_ctrl_state st;
+  std::memset(&st, 0, sizeof(st));
+  st.accumulated_ratio[0] = st.accumulated_ratio[1] = 1.0;
+  for (int32_t i = 0; i < calls; ++i) {
+    mask[i] = static_cast<uint8_t>(mc::decide(cfg, &st));
+    mc::advance(cfg, &st);
+  }
+  return MC_OK;
+}
+
+int32_t mc_ctrl_validate(const mc_ctrl_config* cfg) {
+  int32_t rc = mc::check_cfg(cfg);
+  if (rc) return rc;
+  const int32_t start = mc::retention_start(cfg);
+  if (start < cfg->branches) {
+    mc::set_error(
+        "mc_ctrl_validate: first skip-eligible call is %d but %d residual slot(s) must be filled first "
+        "(reference: `x + None` TypeError; raise retention_ratio or num_steps)",
+        start, cfg->branches);
+    return MC_ERR_STATE;
+  }
+  return MC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,491 @@
+// Row-wise (token-local) kernels of the cache-miss branch — all HBM-bound, fp32 statistics, 128-bit accesses.
+// Arithmetic follows upstream Wan2.1 wan/modules/model.py as restated in SURVEY.md Appendix B.1; call sites in the
+// reference: MagCache4Wan2.1/magcache_generate.py:237 (patch_embedding), :249-254 (time embedding),
+// :297-298 (block stack), :304-305 (head, unpatchify).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mc {
+
+// A "team" of TPR threads owns one row; each thread keeps up to MAXG groups of 8 elements in registers.
+constexpr int kMaxG = 4;
+
+template <int TPR>
+__device__ __forceinline__ float team_sum(float v, float* scratch /* [rows_per_block][TPR/32] */, int team, int lane_in_team) {
+  v = warp_sum(v);
+  if (TPR == 32) return v;
+  constexpr int W = TPR / 32;
+  const int w = lane_in_team >> 5;
+  __syncthreads();  // protect scratch reuse between consecutive reductions
+  if ((lane_in_team & 31) == 0) scratch[team * W + w] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < W; ++i) t += scratch[team * W + i];
+  return t;
+}
+
+__device__ __forceinline__ void load_row_group(const void* x, int dtype_bf16, int64_t off, float (&f)[8]) {
+  if (dtype_bf16) {
+    uint4 v = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x) + off);
+    unpack_bf16x8(v, f);
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(x) + off);
+    float4 a = p[0], b = p[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+}
+
+// ---- K7: LayerNorm (no affine) + modulation / affine, optional bf16 rounding of the LN output -----------------
+template <int TPR>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const void* __restrict__ x, int x_bf16, int64_t rows, int cols, float eps,
+                                                          int mode, const float* __restrict__ a_or_mod,
+                                                          const float* __restrict__ b_or_e, int scale_idx, int shift_idx,
+                                                          int round_ln, void* __restrict__ out, int out_bf16) {
+  constexpr int RPB = 256 / TPR;  // rows per block
+  __shared__ float scratch[RPB * (TPR / 32 > 0 ? TPR / 32 : 1)];
+  const int team = threadIdx.x / TPR, lt = threadIdx.x % TPR;
+  const int groups = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  for (int64_t row0 = static_cast<int64_t>(blockIdx.x) * RPB; row0 < rows; row0 += static_cast<int64_t>(gridDim.x) * RPB) {
+    const int64_t row = row0 + team;
+    const bool live = row < rows;
+    float v[kMaxG][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxG; ++i) {
+      const int g = lt + i * TPR;
+      if (live && g < groups) {
+        load_row_group(x, x_bf16, row * cols + g * 8, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+    }
+    const float mean = team_sum<TPR>(s, scratch, team, lt) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxG; ++i) {
+      const int g = lt + i * TPR;
+      if (live && g < groups) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    }
+    const float var = team_sum<TPR>(q, scratch, team, lt) * inv_n;
+    const float rstd = rsqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxG; ++i) {
+      const int g = lt + i * TPR;
+      if (live && g < groups) {
+        const int c0 = g * 8;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = (v[i][j] - mean) * rstd;
+          if (round_ln) y = round_bf16(y);
+          float a, b;
+          if (mode == 0) {
+            const float sc = a_or_mod[scale_idx * cols + c0 + j] + b_or_e[scale_idx * cols + c0 + j];
+            a = 1.0f + sc;
+            b = a_or_mod[shift_idx * cols + c0 + j] + b_or_e[shift_idx * cols + c0 + j];
+          } else {
+            a = a_or_mod[c0 + j];
+            b = b_or_e[c0 + j];
+          }
+          o[j] = __fadd_rn(__fmul_rn(y, a), b);  // torch eager: separate mul and add, no FMA contraction
+        }
+        if (out_bf16) {
+          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + row * cols + c0) = pack_bf16x8(o);
+        } else {
+          float4* p = reinterpret_cast<float4*>(static_cast<float*>(out) + row * cols + c0);
+          p[0] = make_float4(o[0], o[1], o[2], o[3]);
+          p[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+}
+
+// ---- WanRMSNorm over the model dim (+ optional 3-axis RoPE), in place on bf16 ---------------------------------
+template <int TPR>
+__global__ void __launch_bounds__(256) rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int64_t rows, int cols,
+                                                           const float* __restrict__ w, float eps,
+                                                           const float* __restrict__ cos_sin, int head_dim) {
+  constexpr int RPB = 256 / TPR;
+  __shared__ float scratch[RPB * (TPR / 32 > 0 ? TPR / 32 : 1)];
+  const int team = threadIdx.x / TPR, lt = threadIdx.x % TPR;
+  const int groups = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  for (int64_t row0 = static_cast<int64_t>(blockIdx.x) * RPB; row0 < rows; row0 += static_cast<int64_t>(gridDim.x) * RPB) {
+    const int64_t row = row0 + team;
+    const bool live = row < rows;
+    float v[kMaxG][8];
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxG; ++i) {
+      const int g = lt + i * TPR;
+      if (live && g < groups) {
+        load_row_group(x, 1, row * ld + g * 8, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q = fmaf(v[i][j], v[i][j], q);
+      }
+    }
+    const float ms = team_sum<TPR>(q, scratch, team, lt) * inv_n;
+    const float r = rsqrtf(ms + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxG; ++i) {
+      const int g = lt + i * TPR;
+      if (live && g < groups) {
+        const int c0 = g * 8;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = round_bf16(v[i][j] * r) * w[c0 + j];  // _norm(x.float()).type_as(x) * weight
+        if (cos_sin != nullptr) {
+          const int d0 = c0 % head_dim;  // position inside the head; 8 elements = 4 complex pairs
+          const float4* cs = reinterpret_cast<const float4*>(cos_sin + row * head_dim + d0);
+          const float4 cs0 = cs[0], cs1 = cs[1];
+          const float c[4] = {cs0.x, cs0.z, cs1.x, cs1.z}, sn[4] = {cs0.y, cs0.w, cs1.y, cs1.w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float re = o[2 * p], im = o[2 * p + 1];
+            o[2 * p] = __fsub_rn(__fmul_rn(re, c[p]), __fmul_rn(im, sn[p]));
+            o[2 * p + 1] = __fadd_rn(__fmul_rn(re, sn[p]), __fmul_rn(im, c[p]));
+          }
+        }
+        *reinterpret_cast<uint4*>(x + row * ld + c0) = pack_bf16x8(o);
+      }
+    }
+  }
+}
+
+// ---- patchify: latent fp32 [C,F,H,W] -> tokens bf16 [F*Hp*Wp, C*4] ----------------------------------------------
+__global__ void patchify_kernel(const float* __restrict__ lat, int C, int F, int H, int W, __nv_bfloat16* __restrict__ tok) {
+  const int Hp = H >> 1, Wp = W >> 1;
+  const int64_t total = static_cast<int64_t>(F) * Hp * Wp * C;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    int64_t t = i / C;
+    const int wp = static_cast<int>(t % Wp);
+    t /= Wp;
+    const int hp = static_cast<int>(t % Hp);
+    const int f = static_cast<int>(t / Hp);
+    const float* src = lat + ((static_cast<int64_t>(c) * F + f) * H + hp * 2) * W + wp * 2;
+    const float2 r0 = *reinterpret_cast<const float2*>(src);
+    const float2 r1 = *reinterpret_cast<const float2*>(src + W);
+    uint2 o;
+    o.x = pack_bf16x2(r0.x, r0.y);
+    o.y = pack_bf16x2(r1.x, r1.y);
+    *reinterpret_cast<uint2*>(tok + i * 4) = o;
+  }
+}
+
+// ---- small fp32 linear (M <= 8): one warp per output feature -------------------------------------------------
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+template <int M>
+__global__ void __launch_bounds__(256) linear_f32_small_kernel(const float* __restrict__ x, int K, const float* __restrict__ Wt,
+                                                               const float* __restrict__ b, int N, int act, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m] = 0.f;
+  const float4* wrow = reinterpret_cast<const float4*>(Wt + static_cast<int64_t>(n) * K);
+  for (int k4 = lane; k4 < (K >> 2); k4 += 32) {
+    const float4 wv = wrow[k4];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float4 xv = reinterpret_cast<const float4*>(x + static_cast<int64_t>(m) * K)[k4];
+      if (act == 1) {
+        xv.x = silu(xv.x); xv.y = silu(xv.y); xv.z = silu(xv.z); xv.w = silu(xv.w);
+      }
+      acc[m] = fmaf(xv.x, wv.x, acc[m]);
+      acc[m] = fmaf(xv.y, wv.y, acc[m]);
+      acc[m] = fmaf(xv.z, wv.z, acc[m]);
+      acc[m] = fmaf(xv.w, wv.w, acc[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    float t = warp_sum(acc[m]);
+    if (lane == 0) {
+      t += (b != nullptr) ? b[n] : 0.f;
+      if (act == 2) t = silu(t);
+      y[static_cast<int64_t>(m) * N + n] = t;
+    }
+  }
+}
+
+// ---- head: LN + modulate + fp32 Linear(cols -> 64) + unpatchify ------------------------------------------------
+// Block = 128 threads, 32 rows x 64 outputs; each thread owns a 4x4 micro-tile. Phase 1: row statistics (one warp per
+// 8 rows). Phase 2: K-chunks of 32 columns staged in smem (x normalised+modulated on the way in; Wt chunk as is).
+constexpr int kHeadRows = 32, kHeadKC = 32, kHeadOut = 64;
+
+template <bool FUSED_HIT>
+__device__ __forceinline__ float head_load(const void* x, int x_bf16, const float* r, int64_t idx) {
+  float v = x_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(x)[idx]) : static_cast<const float*>(x)[idx];
+  if (FUSED_HIT) v = v + r[idx];  // `x + residual_x` (magcache_generate.py:295) never materialised
+  return v;
+}
+
+template <bool FUSED_HIT>
+__global__ void __launch_bounds__(128) head_unpatchify_kernel(const void* __restrict__ x, int x_bf16, const float* __restrict__ r,
+                                                              int64_t rows, int cols, int F, int Hp, int Wp, int C_out,
+                                                              const float* __restrict__ head_mod, const float* __restrict__ e,
+                                                              const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                              float eps, float* __restrict__ out) {
+  __shared__ float s_mean[kHeadRows], s_rstd[kHeadRows];
+  __shared__ __align__(16) float xs[kHeadKC][kHeadRows + 4];
+  __shared__ __align__(16) float ws[kHeadKC][kHeadOut];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row_base = static_cast<int64_t>(blockIdx.x) * kHeadRows;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+
+  // phase 1: statistics, two-pass (second pass re-reads the row from L1/L2)
+  for (int rr = warp; rr < kHeadRows; rr += 4) {
+    const int64_t row = row_base + rr;
+    float mean = 0.f, rstd = 0.f;
+    if (row < rows) {
+      float s = 0.f;
+      for (int c = lane; c < cols; c += 32) s += head_load<FUSED_HIT>(x, x_bf16, r, row * cols + c);
+      mean = warp_sum(s) * inv_n;
+      float q = 0.f;
+      for (int c = lane; c < cols; c += 32) {
+        const float d = head_load<FUSED_HIT>(x, x_bf16, r, row * cols + c) - mean;
+        q = fmaf(d, d, q);
+      }
+      rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+    }
+    if (lane == 0) {
+      s_mean[rr] = mean;
+      s_rstd[rr] = rstd;
+    }
+  }
+  __syncthreads();
+
+  const int tr = (tid >> 4) * 4;  // row offset of the micro-tile: 8 thread-rows x 4
+  const int tc = (tid & 15) * 4;  // col offset: 16 thread-cols x 4
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < cols; k0 += kHeadKC) {
+    // stage x chunk: 32 rows x 32 cols; thread -> (row = tid/4 ... ) coalesced along cols
+    for (int i = tid; i < kHeadRows * kHeadKC; i += 128) {
+      const int rr = i / kHeadKC, cc = i % kHeadKC;
+      const int64_t row = row_base + rr;
+      float val = 0.f;
+      if (row < rows) {
+        const int c = k0 + cc;
+        const float y = (head_load<FUSED_HIT>(x, x_bf16, r, row * cols + c) - s_mean[rr]) * s_rstd[rr];
+        const float a = 1.0f + (head_mod[cols + c] + e[c]);  // e[1] = modulation[1] + e
+        const float b = head_mod[c] + e[c];                  // e[0] = modulation[0] + e
+        val = __fadd_rn(__fmul_rn(y, a), b);
+      }
+      xs[cc][rr] = val;
+    }
+    for (int i = tid; i < kHeadKC * kHeadOut; i += 128) {
+      const int cc = i / kHeadOut, j = i % kHeadOut;
+      ws[cc][j] = Wt[static_cast<int64_t>(k0 + cc) * kHeadOut + j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < kHeadKC; ++cc) {
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[cc][tr]);
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[cc][tc]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], wa[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // epilogue: bias + unpatchify scatter. output feature j = (q*2 + rr)*C_out + c  ->  out[c, f, 2*hp+q, 2*wp+rr]
+  const int H2 = Hp * 2, W2 = Wp * 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = row_base + tr + i;
+    if (row >= rows) continue;
+    const int wp = static_cast<int>(row % Wp);
+    const int hp = static_cast<int>((row / Wp) % Hp);
+    const int f = static_cast<int>(row / (static_cast<int64_t>(Wp) * Hp));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = tc + j;
+      const int c = o % C_out, pq = o / C_out;
+      const int q = pq >> 1, rr = pq & 1;
+      out[((static_cast<int64_t>(c) * F + f) * H2 + hp * 2 + q) * W2 + wp * 2 + rr] = acc[i][j] + bias[o];
+    }
+  }
+}
+
+// ---- elementwise --------------------------------------------------------------------------------------------
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    d[i] = __bfloat162float(s[i]);
+}
+__global__ void gelu_tanh_bf16_kernel(__nv_bfloat16* __restrict__ x, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    x[i] = __float2bfloat16_rn(gelu_tanh(__bfloat162float(x[i])));
+}
+// sinusoidal_embedding_1d(dim, position) in float64, cos first (Appendix B.1); out fp32 [n_pos, dim]
+__global__ void time_sinusoid_kernel(const double* __restrict__ pos, int n_pos, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pos * half) return;
+  const int p = i / half, k = i % half;
+  const double freq = pow(10000.0, -static_cast<double>(k) / static_cast<double>(half));
+  const double s = pos[p] * freq;
+  out[static_cast<int64_t>(p) * dim + k] = static_cast<float>(cos(s));
+  out[static_cast<int64_t>(p) * dim + half + k] = static_cast<float>(sin(s));
+}
+
+static int grid_for(int64_t work_items, int per_block) {
+  int64_t want = (work_items + per_block - 1) / per_block;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (want < 1) want = 1;
+  return static_cast<int>(want < cap ? want : cap);
+}
+
+}  // namespace mc
+
+extern "C" {
+
+int32_t mc_patchify(const float* latent, int32_t C, int32_t F, int32_t H, int32_t W, void* tokens_bf16, void* stream) {
+  MC_CHECK_ARG(latent && tokens_bf16, "mc_patchify: null pointer");
+  MC_CHECK_ARG(C >= 1 && F >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "mc_patchify: bad shape C=%d F=%d H=%d W=%d", C, F, H, W);
+  MC_CHECK_ARG((reinterpret_cast<uintptr_t>(latent) & 7u) == 0 && (reinterpret_cast<uintptr_t>(tokens_bf16) & 7u) == 0,
+               "mc_patchify: pointers must be 8-byte aligned");
+  const int64_t total = static_cast<int64_t>(F) * (H / 2) * (W / 2) * C;
+  mc::patchify_kernel<<<mc::grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      latent, C, F, H, W, static_cast<__nv_bfloat16*>(tokens_bf16));
+  MC_CHECK_LAUNCH("patchify_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t cols, float eps, int32_t mode, const float* a_or_mod,
+                       const float* b_or_e, int32_t scale_idx, int32_t shift_idx, int32_t round_ln_to_bf16, void* out,
+                       int32_t out_dtype, void* stream) {
+  MC_CHECK_ARG(x && a_or_mod && b_or_e && out, "mc_ln_modulate: null pointer");
+  MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0 && cols <= 256 * 8 * mc::kMaxG, "mc_ln_modulate: cols=%d unsupported", cols);
+  MC_CHECK_ARG((x_dtype == MC_F32 || x_dtype == MC_BF16) && (out_dtype == MC_F32 || out_dtype == MC_BF16), "mc_ln_modulate: bad dtype");
+  MC_CHECK_ARG(mc::aligned16(x) && mc::aligned16(out), "mc_ln_modulate: x/out must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int groups = cols / 8;
+#define MC_LN(TPR)                                                                                                             \
+  mc::ln_modulate_kernel<TPR><<<mc::grid_for(rows, 256 / TPR), 256, 0, s>>>(x, x_dtype == MC_BF16, rows, cols, eps, mode,       \
+                                                                            a_or_mod, b_or_e, scale_idx, shift_idx,            \
+                                                                            round_ln_to_bf16, out, out_dtype == MC_BF16)
+  if (groups <= 32 * mc::kMaxG) MC_LN(32);
+  else if (groups <= 64 * mc::kMaxG) MC_LN(64);
+  else if (groups <= 128 * mc::kMaxG) MC_LN(128);
+  else MC_LN(256);
+#undef MC_LN
+  MC_CHECK_LAUNCH("ln_modulate_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, const float* w, float eps, const float* cos_sin,
+                        int32_t head_dim, void* stream) {
+  MC_CHECK_ARG(x_bf16 && w, "mc_rmsnorm_rope: null pointer");
+  MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0 && cols <= 256 * 8 * mc::kMaxG && ld >= cols && ld % 8 == 0,
+               "mc_rmsnorm_rope: cols=%d ld=%lld unsupported", cols, static_cast<long long>(ld));
+  MC_CHECK_ARG(mc::aligned16(x_bf16), "mc_rmsnorm_rope: x must be 16-byte aligned");
+  MC_CHECK_ARG(cos_sin == nullptr || (head_dim >= 8 && head_dim % 8 == 0 && cols % head_dim == 0 && mc::aligned16(cos_sin)),
+               "mc_rmsnorm_rope: bad head_dim %d", head_dim);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int groups = cols / 8;
+  __nv_bfloat16* xp = static_cast<__nv_bfloat16*>(x_bf16);
+#define MC_RMS(TPR) mc::rmsnorm_rope_kernel<TPR><<<mc::grid_for(rows, 256 / TPR), 256, 0, s>>>(xp, ld, rows, cols, w, eps, cos_sin, head_dim)
+  if (groups <= 32 * mc::kMaxG) MC_RMS(32);
+  else if (groups <= 64 * mc::kMaxG) MC_RMS(64);
+  else if (groups <= 128 * mc::kMaxG) MC_RMS(128);
+  else MC_RMS(256);
+#undef MC_RMS
+  MC_CHECK_LAUNCH("rmsnorm_rope_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_linear_f32_small(const float* x, int32_t M, int32_t K, const float* W, const float* b, int32_t N, int32_t act, float* y,
+                            void* stream) {
+  MC_CHECK_ARG(x && W && y, "mc_linear_f32_small: null pointer");
+  MC_CHECK_ARG(M >= 1 && M <= 8 && K >= 4 && K % 4 == 0 && N >= 1, "mc_linear_f32_small: M=%d K=%d N=%d unsupported", M, K, N);
+  MC_CHECK_ARG(mc::aligned16(x) && mc::aligned16(W), "mc_linear_f32_small: x/W must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = (N + 7) / 8;
+  switch (M) {
+#define MC_LS(MM) case MM: mc::linear_f32_small_kernel<MM><<<grid, 256, 0, s>>>(x, K, W, b, N, act, y); break;
+    MC_LS(1) MC_LS(2) MC_LS(3) MC_LS(4) MC_LS(5) MC_LS(6) MC_LS(7) MC_LS(8)
+#undef MC_LS
+  }
+  MC_CHECK_LAUNCH("linear_f32_small_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int32_t cols, int32_t F, int32_t Hp, int32_t Wp,
+                           int32_t C_out, const float* head_mod, const float* e, const float* Wt, const float* b, float eps,
+                           float* out, void* stream) {
+  MC_CHECK_ARG(x && head_mod && e && Wt && b && out, "mc_head_unpatchify: null pointer");
+  MC_CHECK_ARG(cols >= mc::kHeadKC && cols % mc::kHeadKC == 0, "mc_head_unpatchify: cols=%d must be a multiple of %d", cols, mc::kHeadKC);
+  MC_CHECK_ARG(C_out * 4 == mc::kHeadOut, "mc_head_unpatchify: only patch (1,2,2) x C_out=16 (64 output features) is built, got C_out=%d", C_out);
+  MC_CHECK_ARG(F >= 1 && Hp >= 1 && Wp >= 1, "mc_head_unpatchify: bad grid");
+  const int64_t rows = static_cast<int64_t>(F) * Hp * Wp;
+  const int grid = static_cast<int>((rows + mc::kHeadRows - 1) / mc::kHeadRows);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (r_or_null)
+    mc::head_unpatchify_kernel<true><<<grid, 128, 0, s>>>(x, x_dtype == MC_BF16, r_or_null, rows, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, out);
+  else
+    mc::head_unpatchify_kernel<false><<<grid, 128, 0, s>>>(x, x_dtype == MC_BF16, nullptr, rows, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, out);
+  MC_CHECK_LAUNCH("head_unpatchify_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
+  MC_CHECK_ARG(src && dst && n >= 0, "mc_cast: bad arguments");
+  if (n == 0) return MC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (src_dtype == MC_F32 && dst_dtype == MC_BF16)
+    mc::cast_f32_to_bf16_kernel<<<mc::grid_for(n, 256), 256, 0, s>>>(static_cast<const float*>(src), static_cast<__nv_bfloat16*>(dst), n);
+  else if (src_dtype == MC_BF16 && dst_dtype == MC_F32)
+    mc::cast_bf16_to_f32_kernel<<<mc::grid_for(n, 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src), static_cast<float*>(dst), n);
+  else {
+    mc::set_error("mc_cast: unsupported %d -> %d", src_dtype, dst_dtype);
+    return MC_ERR_INVALID;
+  }
+  MC_CHECK_LAUNCH("cast kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_gelu_tanh_bf16(void* x_bf16, int64_t n, void* stream) {
+  MC_CHECK_ARG(x_bf16 && n >= 0, "mc_gelu_tanh_bf16: bad arguments");
+  if (n == 0) return MC_OK;
+  mc::gelu_tanh_bf16_kernel<<<mc::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(x_bf16), n);
+  MC_CHECK_LAUNCH("gelu kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_time_sinusoid(const double* pos_dev, int32_t n_pos, int32_t dim, float* out, void* stream) {
+  MC_CHECK_ARG(pos_dev && out && n_pos >= 1 && dim >= 2 && dim % 2 == 0, "mc_time_sinusoid: bad arguments");
+  const int total = n_pos * (dim / 2);
+  mc::time_sinusoid_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(pos_dev, n_pos, dim, out);
+  MC_CHECK_LAUNCH("time_sinusoid_kernel launch");
+  return MC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+"""PyTorch-tensor front end of the C ABI: tensors in, tensors out, kernels on the current CUDA stream.
+
+PyTorch is used for device memory and streams only; every function below lands in exactly one hand-written
+sm_100a kernel of libmagcache_b200.so (see include/magcache_b200.h for the reference statement each one replaces).
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import MC_BF16, MC_F32, check, lib
+
+LAUNCHES = 0  # number of libmagcache_b200 kernel-launching calls made by this process (bench.py reports the delta)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return MC_F32
+    if t.dtype == torch.bfloat16:
+        return MC_BF16
+    raise TypeError(f"unsupported dtype {t.dtype} (fp32 / bf16 only)")
+
+
+def _dev(t, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: magcache_b200 has no CPU path")
+    return t
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _promote(a, b):
+    return torch.promote_types(a.dtype, b.dtype)
+
+
+def cache_hit_add(x, r, out=None):
+    """`x + residual_x` (MagCache4Wan2.1/magcache_generate.py:295) with torch's type promotion."""
+    _dev(x, "x"), _dev(r, "r")
+    assert x.shape == r.shape and x.is_contiguous() and r.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=_promote(x, r), device=x.device)
+    check(lib.mc_cache_hit_add(x.data_ptr(), _dt(x), r.data_ptr(), _dt(r), out.data_ptr(), _dt(out), x.numel(), _stream()))
+    _count()
+    return out
+
+
+def residual_sub(x_out, x_in, out=None):
+    """`residual_x = x - ori_x` (MagCache4Wan2.1/magcache_generate.py:299)."""
+    _dev(x_out, "x_out"), _dev(x_in, "x_in")
+    assert x_out.shape == x_in.shape and x_out.is_contiguous() and x_in.is_contiguous()
+    if out is None:
+        out = torch.empty(x_out.shape, dtype=_promote(x_out, x_in), device=x_out.device)
+    check(lib.mc_residual_sub(x_out.data_ptr(), _dt(x_out), x_in.data_ptr(), _dt(x_in), out.data_ptr(), _dt(out), x_out.numel(), _stream()))
+    _count()
+    return out
+
+
+def _finish_stats(stats_dev):
+    s0, s1, s2, n = stats_dev.tolist()  # the single host sync of the calibration path
+    mean = s0 / n
+    var = (s1 - s0 * s0 / n) / (n - 1) if n > 1 else float("nan")
+    return mean, math.sqrt(max(var, 0.0)), s2 / n
+
+
+def residual_stats(r_cur, r_prev, denom_eps=0.0):
+    """(norm_ratio, norm_std, cos_dis) of MagCache4Wan2.1/magcache_generate.py:167-169 in one pass + one sync."""
+    _dev(r_cur), _dev(r_prev)
+    assert r_cur.shape == r_prev.shape and r_cur.is_contiguous() and r_prev.is_contiguous()
+    cols = r_cur.shape[-1]
+    rows = r_cur.numel() // cols
+    stats = torch.empty(4, dtype=torch.float64, device=r_cur.device)
+    check(lib.mc_residual_stats(r_cur.data_ptr(), _dt(r_cur), r_prev.data_ptr(), _dt(r_prev), rows, cols, float(denom_eps),
+                                stats.data_ptr(), _stream()))
+    _count(2)
+    return _finish_stats(stats)
+
+
+def residual_sub_stats(x_out, x_in, r_prev, denom_eps=0.0):
+    """Fused `x - ori_x` + statistics against the previous residual (calibration miss epilogue)."""
+    _dev(x_out), _dev(x_in), _dev(r_prev)
+    assert x_out.dtype == torch.float32 and x_in.dtype == torch.bfloat16 and r_prev.dtype == torch.float32
+    cols = x_out.shape[-1]
+    rows = x_out.numel() // cols
+    r = torch.empty_like(x_out)
+    stats = torch.empty(4, dtype=torch.float64, device=x_out.device)
+    check(lib.mc_residual_sub_stats(x_out.data_ptr(), MC_F32, x_in.data_ptr(), MC_BF16, r.data_ptr(), r_prev.data_ptr(), rows, cols,
+                                    float(denom_eps), stats.data_ptr(), _stream()))
+    _count(2)
+    return r, _finish_stats(stats)
+
+
+def patchify(latent):
+    """latent fp32 [C,F,H,W] -> bf16 [F*(H/2)*(W/2), C*4] (im2col of the (1,2,2) patch embedding)."""
+    _dev(latent)
+    assert latent.dtype == torch.float32 and latent.dim() == 4 and latent.is_contiguous()
+    C, F, H, W = latent.shape
+    out = torch.empty(F * (H // 2) * (W // 2), C * 4, dtype=torch.bfloat16, device=latent.device)
+    check(lib.mc_patchify(latent.data_ptr(), C, F, H, W, out.data_ptr(), _stream()))
+    _count()
+    return out
+
+
+def ln_modulate(x, mod, e, scale_idx, shift_idx, eps=1e-6, round_ln_to_bf16=False, out_dtype=torch.bfloat16, out=None):
+    """bf16/fp32( LN(x) * (1 + mod[scale]+e[scale]) + (mod[shift]+e[shift]) ) ; x [rows, cols], mod/e fp32 [k, cols]."""
+    _dev(x)
+    rows, cols = x.shape
+    assert x.is_contiguous() and mod.dtype == torch.float32 and e.dtype == torch.float32 and mod.is_contiguous() and e.is_contiguous()
+    if out is None:
+        out = torch.empty(rows, cols, dtype=out_dtype, device=x.device)
+    check(lib.mc_ln_modulate(x.data_ptr(), _dt(x), rows, cols, eps, 0, mod.data_ptr(), e.data_ptr(), scale_idx, shift_idx,
+                             int(round_ln_to_bf16), out.data_ptr(), _dt(out), _stream()))
+    _count()
+    return out
+
+
+def ln_affine(x, weight, bias, eps=1e-6, out_dtype=torch.bfloat16, out=None):
+    """LayerNorm with elementwise affine (norm3 of the Wan block)."""
+    _dev(x)
+    rows, cols = x.shape
+    assert x.is_contiguous() and weight.dtype == torch.float32 and bias.dtype == torch.float32
+    if out is None:
+        out = torch.empty(rows, cols, dtype=out_dtype, device=x.device)
+    check(lib.mc_ln_modulate(x.data_ptr(), _dt(x), rows, cols, eps, 1, weight.data_ptr(), bias.data_ptr(), 0, 0, 0, out.data_ptr(),
+                             _dt(out), _stream()))
+    _count()
+    return out
+
+
+def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6):
+    """In-place WanRMSNorm (+ RoPE when cos_sin [rows, head_dim] is given) on a bf16 [rows, cols] view (row stride allowed)."""
+    _dev(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and weight.dtype == torch.float32
+    rows, cols = x.shape
+    if cos_sin is not None:
+        assert cos_sin.dtype == torch.float32 and cos_sin.is_contiguous() and cos_sin.shape == (rows, head_dim)
+    check(lib.mc_rmsnorm_rope(x.data_ptr(), x.stride(0), rows, cols, weight.data_ptr(), eps,
+                              cos_sin.data_ptr() if cos_sin is not None else None, head_dim, _stream()))
+    _count()
+    return x
+
+
+def gemm(a, b, bias=None, epilogue=_lib.MC_EPI_BIAS_BF16, out=None, gate=None):
+    """acc = a @ b.T on tcgen05 (a [M,K] bf16, b [N,K] bf16, row stride allowed) + fused epilogue (see MC_EPI_*)."""
+    _dev(a), _dev(b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N, K2 = b.shape
+    assert K == K2
+    if out is None:
+        assert epilogue != _lib.MC_EPI_BIAS_GATE_RESID, "the residual epilogue updates `out` in place; pass the fp32 stream"
+        out = torch.empty(M, N, dtype=torch.float32 if epilogue == _lib.MC_EPI_BIAS_F32 else torch.bfloat16, device=a.device)
+    want = torch.float32 if epilogue in (_lib.MC_EPI_BIAS_GATE_RESID, _lib.MC_EPI_BIAS_F32) else torch.bfloat16
+    assert out.dtype == want and out.stride(1) == 1 and out.shape == (M, N)
+    for v in (bias, gate):
+        assert v is None or (v.dtype == torch.float32 and v.is_contiguous())
+    check(lib.mc_gemm_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, bias.data_ptr() if bias is not None else None,
+                           epilogue, out.data_ptr(), out.stride(0), gate.data_ptr() if gate is not None else None, _stream()))
+    _count()
+    return out
+
+
+def attention(q, k, vt, heads, scale=None, out=None):
+    """softmax(q k^T * scale) v per head (head_dim 128). q [Lq, H*128], k [Lk, H*128], vt = V^T [H*128, Lk] (bf16)."""
+    _dev(q), _dev(k), _dev(vt)
+    assert q.dtype == k.dtype == vt.dtype == torch.bfloat16 and q.stride(1) == 1 and k.stride(1) == 1 and vt.stride(1) == 1
+    Lq, W = q.shape
+    Lk = k.shape[0]
+    assert W == heads * 128 and k.shape[1] == W and vt.shape == (W, Lk)
+    if scale is None:
+        scale = 1.0 / math.sqrt(128)
+    if out is None:
+        out = torch.empty(Lq, W, dtype=torch.bfloat16, device=q.device)
+    check(lib.mc_attn_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), vt.data_ptr(), vt.stride(0), out.data_ptr(),
+                          out.stride(0), Lq, Lk, heads, float(scale), _stream()))
+    _count()
+    return out
+
+
+def linear_f32_small(x, w, b=None, act=0):
+    """fp32 y = act(x @ w.T + b) for M <= 8 rows (time embedding path). act: 0 none, 1 SiLU on the input, 2 SiLU on the output."""
+    _dev(x), _dev(w)
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous()
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    check(lib.mc_linear_f32_small(x.data_ptr(), M, K, w.data_ptr(), b.data_ptr() if b is not None else None, N, act, y.data_ptr(), _stream()))
+    _count()
+    return y
+
+
+def time_sinusoid(t, dim):
+    """sinusoidal_embedding_1d(dim, t) computed in float64 on the device, returned as fp32 [len(t), dim]."""
+    _dev(t)
+    pos = t.to(torch.float64).contiguous()
+    out = torch.empty(pos.numel(), dim, dtype=torch.float32, device=t.device)
+    check(lib.mc_time_sinusoid(pos.data_ptr(), pos.numel(), dim, out.data_ptr(), _stream()))
+    _count()
+    return out
+
+
+def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6):
+    """head(x, e) + unpatchify (MagCache4Wan2.1/magcache_generate.py:304-305) -> fp32 [c_out, F, 2*Hp, 2*Wp].
+    With `residual` (fp32) the cache-hit sum x + residual is formed on the fly (fused hit path)."""
+    _dev(x)
+    F, Hp, Wp = grid
+    rows, cols = x.shape
+    assert rows == F * Hp * Wp and x.is_contiguous() and w_t.shape == (cols, 4 * c_out) and w_t.is_contiguous()
+    assert head_mod.shape[-2:] == (2, cols) and e.numel() == cols
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == x.shape
+    out = torch.empty(c_out, F, 2 * Hp, 2 * Wp, dtype=torch.float32, device=x.device)
+    check(lib.mc_head_unpatchify(x.data_ptr(), _dt(x), residual.data_ptr() if residual is not None else None, cols, F, Hp, Wp, c_out,
+                                 head_mod.data_ptr(), e.data_ptr(), w_t.data_ptr(), b.data_ptr(), eps, out.data_ptr(), _stream()))
+    _count()
+    return out
+
+
+def cast(src, dtype):
+    _dev(src)
+    assert src.is_contiguous()
+    dst = torch.empty(src.shape, dtype=dtype, device=src.device)
+    check(lib.mc_cast(src.data_ptr(), _dt(src), dst.data_ptr(), _dt(dst), src.numel(), _stream()))
+    _count()
+    return dst

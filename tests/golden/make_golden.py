@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by EXECUTING the reference's own code.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The MagCache scripts cannot be imported (`import wan` / `diffusers` / `hyvideo` are not installed),
+so this script parses them with `ast`, cuts out exactly the statements that make up the hot-path
+host logic and executes those statements, unmodified, against a stand-in `self`:
+
+* `nearest_interp`                    MagCache4Wan2.1/magcache_generate.py:27-34 (whole function)
+* the controller `if self.cnt>=...:`  MagCache4Wan2.1/magcache_generate.py:279-292
+                                      MagCache4FLUX/magcache_flux.py:327-338
+                                      MagCache4HunyuanVideo/magcache_sample_video.py:90-102
+* the counter/reset epilogue          :306-311 / :431-436 / :149-154
+* the calibration statistics block    MagCache4Wan2.1/magcache_generate.py:166-173
+* the calibrated `mag_ratios` literals (:910,:912,:1002,:1004,:1142,:1144; FLUX :459; Hunyuan :316,:318)
+
+Outputs (committed):  tables.json, nearest_interp.json, masks.json, calib_stats.json
+Nothing here is imported by the product; tests/ read the JSON files only.
+"""
+import ast
+import json
+import os
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+WAN = f"{REF}/MagCache4Wan2.1/magcache_generate.py"
+FLUX = f"{REF}/MagCache4FLUX/magcache_flux.py"
+HUN = f"{REF}/MagCache4HunyuanVideo/magcache_sample_video.py"
+
+
+def _tree(path):
+    with open(path) as f:
+        return ast.parse(f.read())
+
+
+def _func(tree, name):
+    for n in ast.walk(tree):
+        if isinstance(n, ast.FunctionDef) and n.name == name:
+            return n
+    raise KeyError(name)
+
+
+def _mentions(node, attr):
+    return any(isinstance(n, ast.Attribute) and n.attr == attr for n in ast.walk(node))
+
+
+def _compile(stmts):
+    mod = ast.Module(body=list(stmts), type_ignores=[])
+    ast.fix_missing_locations(mod)
+    return compile(mod, "<reference-extract>", "exec")
+
+
+# ----------------------------------------------------------------------------------------------
+# tables
+# ----------------------------------------------------------------------------------------------
+def extract_tables():
+    """Evaluate every `np.array([1.0]*k + [...])` literal assigned to `.mag_ratios` in the three scripts."""
+    out = {}
+
+    def grab(path, key_of):
+        tree = _tree(path)
+        for n in ast.walk(tree):
+            if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Attribute) \
+                    and n.targets[0].attr == "mag_ratios" and isinstance(n.value, ast.Call) \
+                    and isinstance(n.value.func, ast.Attribute) and n.value.func.attr == "array":
+                arr = eval(compile(ast.Expression(n.value), "<tbl>", "eval"), {"np": np})
+                key = key_of(n.lineno)
+                if key:
+                    out[key] = {"source": f"{os.path.relpath(path, REF)}:{n.lineno}", "values": [float(v) for v in arr]}
+
+    grab(WAN, lambda ln: {910: "wan2.1_t2v_14b", 912: "wan2.1_t2v_1.3b", 1002: "wan2.1_i2v_480p", 1004: "wan2.1_i2v_720p",
+                          1142: "wan2.1_vace_1.3b", 1144: "wan2.1_vace_14b"}.get(ln))
+    grab(FLUX, lambda ln: {459: "flux_dev"}.get(ln))
+    grab(HUN, lambda ln: {316: "hunyuan_720p", 318: "hunyuan_544p"}.get(ln))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# nearest_interp (the reference function itself)
+# ----------------------------------------------------------------------------------------------
+def reference_nearest_interp():
+    fn = _func(_tree(WAN), "nearest_interp")
+    env = {"np": np}
+    exec(_compile([fn]), env)
+    return env["nearest_interp"]
+
+
+# ----------------------------------------------------------------------------------------------
+# controller (the reference statements themselves, run against a stand-in `self`)
+# ----------------------------------------------------------------------------------------------
+class RefController:
+    """Runs the controller + counter statements cut out of a reference magcache_forward."""
+
+    def __init__(self, path, func="magcache_forward"):
+        fn = _func(_tree(path), func)
+        body = fn.body
+        ctrl = [s for s in body if isinstance(s, ast.If) and _mentions(s.test, "retention_ratio")]
+        assert len(ctrl) == 1, (path, len(ctrl))
+        self.ctrl = _compile(ctrl)
+        # `self.cnt += 1` and the following `if self.cnt >= self.num_steps:` reset
+        tail = []
+        for i, s in enumerate(body):
+            if isinstance(s, ast.AugAssign) and isinstance(s.target, ast.Attribute) and s.target.attr == "cnt":
+                tail = [s, body[i + 1]]
+                assert isinstance(body[i + 1], ast.If) and _mentions(body[i + 1].test, "num_steps")
+        assert tail, path
+        self.tail = _compile(tail)
+
+    def call(self, state):
+        env = {"self": state, "np": np, "skip_forward": False}
+        exec(self.ctrl, env)
+        skip = bool(env["skip_forward"])
+        exec(self.tail, env)
+        return skip
+
+
+def wan_state(table, steps, thresh, K, R, interp):
+    s = types.SimpleNamespace()
+    s.cnt = 0
+    s.num_steps = steps * 2
+    s.magcache_thresh = thresh
+    s.K = K
+    s.accumulated_err = [0.0, 0.0]
+    s.accumulated_steps = [0, 0]
+    s.accumulated_ratio = [1.0, 1.0]
+    s.retention_ratio = R
+    s.residual_cache = ["r0", "r1"]
+    mr = np.array(table)
+    if len(mr) != steps * 2:  # MagCache4Wan2.1/magcache_generate.py:915-919, executed literally
+        con = interp(mr[0::2], steps)
+        ucon = interp(mr[1::2], steps)
+        mr = np.concatenate([con.reshape(-1, 1), ucon.reshape(-1, 1)], axis=1).reshape(-1)
+    s.mag_ratios = mr
+    return s
+
+
+def scalar_state(table, steps, thresh, K, R, interp, cache_attr):
+    s = types.SimpleNamespace()
+    s.cnt = 0
+    s.num_steps = steps
+    s.magcache_thresh = thresh
+    s.K = K
+    s.accumulated_err = 0
+    s.accumulated_steps = 0
+    s.accumulated_ratio = 1
+    s.retention_ratio = R
+    setattr(s, cache_attr, "r")
+    mr = np.array(table)
+    if len(mr) != steps:
+        mr = interp(mr, steps)
+    s.mag_ratios = mr
+    return s
+
+
+def run_mask(ctrl, state, n_calls):
+    mask = []
+    for _ in range(n_calls):
+        mask.append(1 if ctrl.call(state) else 0)
+    return mask
+
+
+def final_state(s):
+    def f(v):
+        if isinstance(v, (list, tuple)):
+            return [float(x) for x in v]
+        return float(v)
+    return {"cnt": int(s.cnt), "accumulated_err": f(s.accumulated_err), "accumulated_steps": f(s.accumulated_steps),
+            "accumulated_ratio": f(s.accumulated_ratio)}
+
+
+# ----------------------------------------------------------------------------------------------
+# calibration statistics (reference statements, torch CPU)
+# ----------------------------------------------------------------------------------------------
+def calib_cases():
+    import torch
+    import torch.nn.functional as F
+
+    fn = _func(_tree(WAN), "magcache_calibration")
+    blk = [s for s in fn.body if isinstance(s, ast.If) and isinstance(s.test, ast.Compare)
+           and _mentions(s.test, "cnt") and not _mentions(s.test, "num_steps")
+           and any(_mentions(x, "norm_ratio") for x in s.body)]
+    assert len(blk) == 1
+    code = _compile(blk)
+    cases = []
+    for seed, (B, N, D), spread in [(0, (1, 64, 96), 0.02), (1, (1, 257, 128), 0.2), (2, (2, 33, 1536), 0.05), (3, (1, 1000, 64), 0.5)]:
+        g = torch.Generator().manual_seed(seed)
+        r_prev = torch.randn(B, N, D, generator=g) * 0.1
+        r_cur = r_prev * (0.97 + spread * torch.rand(B, N, 1, generator=g)) + 0.01 * torch.randn(B, N, D, generator=g)
+        st = types.SimpleNamespace(cnt=2, residual_cache=[r_prev, None], norm_ratio=[], norm_std=[], cos_dis=[])
+        env = {"self": st, "F": F, "torch": torch, "residual_x": r_cur, "round": round, "print": lambda *a, **k: None}
+        exec(code, env)
+        cases.append({"seed": seed, "shape": [B, N, D], "spread": spread,
+                      "norm_ratio": st.norm_ratio[0], "norm_std": st.norm_std[0], "cos_dis": st.cos_dis[0],
+                      "norm_ratio_raw": env["norm_ratio"], "norm_std_raw": env["norm_std"], "cos_dis_raw": env["cos_dis"]})
+    return cases
+
+
+def main():
+    tables = extract_tables()
+    with open(f"{OUT}/tables.json", "w") as f:
+        json.dump(tables, f, indent=0)
+    print("tables:", {k: len(v["values"]) for k, v in tables.items()})
+
+    interp = reference_nearest_interp()
+    ni = []
+    for key, targets in [("wan2.1_t2v_1.3b", [1, 2, 3, 10, 20, 25, 30, 40, 49, 50, 51, 60, 100]), ("flux_dev", [1, 2, 8, 20, 27, 28, 29, 50]),
+                         ("hunyuan_720p", [1, 30, 50, 64])]:
+        src = np.array(tables[key]["values"])
+        per_branch = key.startswith("wan")
+        srcs = [("cond", src[0::2]), ("uncond", src[1::2])] if per_branch else [("all", src)]
+        for tag, s in srcs:
+            for T in targets:
+                out = interp(s, T)
+                ni.append({"table": key, "slice": tag, "L": int(len(s)), "T": T, "out": [float(v) for v in out]})
+    # synthetic ties (round-half-to-even is visible when (L-1)/(T-1) lands on .5)
+    for L, T in [(5, 3), (9, 5), (3, 5), (4, 7), (51, 21), (101, 41), (2, 2), (7, 1)]:
+        s = np.arange(L, dtype=np.float64) * 1.5 + 0.25
+        ni.append({"table": None, "slice": f"arange{L}", "L": L, "T": T, "src": [float(v) for v in s], "out": [float(v) for v in interp(s, T)]})
+    with open(f"{OUT}/nearest_interp.json", "w") as f:
+        json.dump(ni, f)
+    print("nearest_interp cases:", len(ni))
+
+    masks = []
+    wan = RefController(WAN)
+    for key in ["wan2.1_t2v_1.3b", "wan2.1_t2v_14b", "wan2.1_i2v_480p", "wan2.1_i2v_720p", "wan2.1_vace_1.3b", "wan2.1_vace_14b"]:
+        for thresh, K, R in [(0.12, 2, 0.2), (0.12, 4, 0.2), (0.24, 6, 0.2), (0.02, 3, 0.2), (0.06, 1, 0.1), (0.5, 8, 0.3)]:
+            for steps in [50, 40, 30, 20]:
+                st = wan_state(tables[key]["values"], steps, thresh, K, R, interp)
+                n = 2 * steps * 2 + 7  # two whole videos and a bit: exercises the counter reset (:306-311)
+                m = run_mask(wan, st, n)
+                masks.append({"family": "wan2.1", "table": key, "steps": steps, "thresh": thresh, "K": K, "R": R,
+                              "calls": n, "mask": "".join(map(str, m)), "skipped_first_video": int(sum(m[:2 * steps])),
+                              "final": final_state(st)})
+    flux = RefController(FLUX)
+    for thresh, K, R in [(0.24, 5, 0.1), (0.12, 3, 0.1), (0.05, 4, 0.2), (0.4, 8, 0.05)]:
+        for steps in [28, 20, 50, 12]:
+            st = scalar_state(tables["flux_dev"]["values"], steps, thresh, K, R, interp, "previous_residual")
+            n = 2 * steps + 3
+            m = run_mask(flux, st, n)
+            masks.append({"family": "flux", "table": "flux_dev", "steps": steps, "thresh": thresh, "K": K, "R": R,
+                          "calls": n, "mask": "".join(map(str, m)), "skipped_first_video": int(sum(m[:steps])), "final": final_state(st)})
+    hun = RefController(HUN)
+    for key in ["hunyuan_720p", "hunyuan_544p"]:
+        for thresh, K, R in [(0.24, 6, 0.2), (0.12, 4, 0.2), (0.06, 2, 0.1)]:
+            for steps in [50, 30, 25]:
+                st = scalar_state(tables[key]["values"], steps, thresh, K, R, interp, "residual_cache")
+                n = 2 * steps + 3
+                m = run_mask(hun, st, n)
+                masks.append({"family": "hunyuan", "table": key, "steps": steps, "thresh": thresh, "K": K, "R": R,
+                              "calls": n, "mask": "".join(map(str, m)), "skipped_first_video": int(sum(m[:steps])), "final": final_state(st)})
+    with open(f"{OUT}/masks.json", "w") as f:
+        json.dump(masks, f, indent=0)
+    print("mask cases:", len(masks))
+    for c in masks:
+        if c["table"] == "wan2.1_t2v_1.3b" and c["steps"] == 50 and c["R"] == 0.2 and c["thresh"] in (0.12, 0.24):
+            print(c["thresh"], c["K"], c["skipped_first_video"], c["mask"][0:100:2])
+
+    cal = calib_cases()
+    with open(f"{OUT}/calib_stats.json", "w") as f:
+        json.dump(cal, f, indent=0)
+    print("calibration cases:", cal)
+
+
+if __name__ == "__main__":
+    main()

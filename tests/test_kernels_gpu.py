@@ -1,0 +1,334 @@
+"""GPU parity of every hand-written kernel against a plain PyTorch fp32 reference of the same op (called through the C ABI).
+
+Tolerances (stated per test): integer/bit-exact for the fp32 add/sub; <= 1 bf16 ulp for bf16 outputs whose fp32 pre-image is
+compared at rtol 1e-3 / atol 1e-4 (the north-star tolerance); statistics at 1e-5 absolute.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from magcache_b200 import ops
+    return ops
+
+
+def _lib():
+    from magcache_b200 import _lib
+    return _lib
+
+
+def bf16_ulp_close(got, ref_f32, extra_atol=0.0):
+    """got (bf16) must equal ref rounded to bf16 up to one bf16 ulp (2^-8 relative) — the rounding of an fp32 value that
+    itself carries rtol 1e-3/atol 1e-4 accumulation-order noise."""
+    g = got.float()
+    tol = ref_f32.abs() * (2.0 ** -7) + 1e-4 + extra_atol
+    bad = (g - ref_f32).abs() > tol
+    return int(bad.sum().item()), float((g - ref_f32).abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------- cache kernels
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 1000, 4096 * 3 + 5, 32760 * 1536])
+def test_cache_hit_add_wan_dtypes(n):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(n % 1000)
+    x = torch.randn(n, device=DEV, generator=g).bfloat16()
+    r = torch.randn(n, device=DEV, generator=g) * 0.1
+    out = ops.cache_hit_add(x, r)
+    ref = x + r  # torch promotes bf16 + fp32 -> fp32
+    assert out.dtype == torch.float32
+    assert torch.equal(out, ref)  # bit-exact
+
+
+@pytest.mark.parametrize("dx,dr", [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32), (torch.float32, torch.bfloat16)])
+def test_cache_hit_add_other_dtypes(dx, dr):
+    ops = _ops()
+    n = 4096 * 3072 + 3
+    x = torch.randn(n, device=DEV).to(dx)
+    r = (torch.randn(n, device=DEV) * 0.1).to(dr)
+    assert torch.equal(ops.cache_hit_add(x, r), x + r)
+    assert torch.equal(ops.residual_sub(x, r), x - r)
+
+
+def test_hit_then_sub_roundtrip_full_size():
+    """Size-independent property at the BASELINE config-2 size: (x + r) - x == r exactly when the add did not round,
+    and always |((x + r) - x) - r| <= ulp(x + r)."""
+    ops = _ops()
+    n = 32760 * 1536
+    x = torch.randn(n, device=DEV).bfloat16()
+    r = torch.randn(n, device=DEV) * 0.05
+    y = ops.cache_hit_add(x, r)
+    back = ops.residual_sub(y, x)
+    assert torch.equal(back, (x + r) - x)
+    err = (back - r).abs()
+    assert float(err.max()) <= float((y.abs().max() * 2 ** -23) * 2)
+
+
+def test_residual_sub_unaligned_and_ragged():
+    ops = _ops()
+    base_o = torch.randn(1024 + 3, device=DEV)
+    base_i = torch.randn(1024 + 3, device=DEV).bfloat16()
+    xo, xi = base_o[1:1001].contiguous(), base_i[:1000].contiguous()
+    assert torch.equal(ops.residual_sub(xo, xi), xo - xi)
+
+
+def _ref_stats(r, p, eps=0.0):
+    ratio = r.norm(dim=-1) / (p.norm(dim=-1) + eps)
+    return ratio.mean().item(), ratio.std().item(), (1 - torch.nn.functional.cosine_similarity(r, p, dim=-1, eps=1e-8)).mean().item()
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 96), (2, 33, 1536), (1, 32760, 1536)])
+def test_residual_stats(shape):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    p = torch.randn(*shape, device=DEV, generator=g) * 0.1
+    r = p * (0.97 + 0.05 * torch.rand(shape[0], shape[1], 1, device=DEV, generator=g)) + 0.01 * torch.randn(*shape, device=DEV, generator=g)
+    got = ops.residual_stats(r, p)
+    ref = _ref_stats(r.double(), p.double())
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 1e-5, (got, ref)
+
+
+def test_residual_sub_stats_fused():
+    ops = _ops()
+    rows, cols = 4095, 1536
+    xi = torch.randn(rows, cols, device=DEV).bfloat16()
+    p = torch.randn(rows, cols, device=DEV) * 0.1
+    xo = xi.float() + p * 1.02 + 0.003 * torch.randn(rows, cols, device=DEV)
+    r, st = ops.residual_sub_stats(xo, xi, p)
+    assert torch.equal(r, xo - xi)
+    ref = _ref_stats((xo - xi).double(), p.double())
+    for a, b in zip(st, ref):
+        assert abs(a - b) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- row-wise kernels
+def test_patchify_matches_conv3d_im2col():
+    ops = _ops()
+    lat = torch.randn(16, 3, 8, 12, device=DEV)
+    tok = ops.patchify(lat)
+    # reference: unfold the (1,2,2) patches in (c, kh, kw) order
+    C, F, H, W = lat.shape
+    ref = lat.view(C, F, H // 2, 2, W // 2, 2).permute(1, 2, 4, 0, 3, 5).reshape(F * (H // 2) * (W // 2), C * 4).bfloat16()
+    assert torch.equal(tok, ref)
+    # and against an actual Conv3d: tokens @ W.flatten(1).T == conv output
+    conv = torch.nn.Conv3d(16, 32, kernel_size=(1, 2, 2), stride=(1, 2, 2), device=DEV)
+    y = conv(lat.bfloat16().float().unsqueeze(0))[0].flatten(1).t()
+    y2 = tok.float() @ conv.weight.flatten(1).t() + conv.bias
+    assert torch.allclose(y, y2, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("rows,cols,xdt", [(37, 1536, torch.float32), (130, 5120, torch.float32), (64, 1536, torch.bfloat16), (5, 256, torch.float32)])
+def test_ln_modulate(rows, cols, xdt):
+    ops = _ops()
+    x = (torch.randn(rows, cols, device=DEV) * 3 + 0.5).to(xdt)
+    mod = torch.randn(6, cols, device=DEV) / math.sqrt(cols)
+    e = torch.randn(6, cols, device=DEV) * 0.2
+    round_ln = xdt == torch.bfloat16
+    out32 = ops.ln_modulate(x, mod, e, 1, 0, round_ln_to_bf16=round_ln, out_dtype=torch.float32)
+    ln = torch.nn.functional.layer_norm(x.float(), (cols,), eps=1e-6)
+    if round_ln:
+        ln = ln.to(xdt).float()
+    ee = mod + e
+    ref = ln * (1 + ee[1]) + ee[0]
+    # tolerance: rtol 1e-3 / atol 1e-4 (north star) -- fp32 LN statistics differ only by summation order; with round_ln the
+    # bf16 rounding of LN may flip by one ulp (2^-8 relative) on a handful of elements
+    if round_ln:
+        assert ((out32 - ref).abs() <= ref.abs() * 2 ** -7 + 1e-2).all()
+        assert ((out32 - ref).abs() > 1e-4 + 1e-3 * ref.abs()).float().mean() < 0.01
+    else:
+        assert torch.allclose(out32, ref, rtol=1e-3, atol=1e-4)
+    out16 = ops.ln_modulate(x, mod, e, 1, 0, round_ln_to_bf16=round_ln)
+    assert torch.equal(out16, out32.bfloat16())
+
+
+def test_ln_affine():
+    ops = _ops()
+    x = torch.randn(77, 1536, device=DEV) * 2
+    w = torch.randn(1536, device=DEV)
+    b = torch.randn(1536, device=DEV)
+    out = ops.ln_affine(x, w, b, out_dtype=torch.float32)
+    ref = torch.nn.functional.layer_norm(x, (1536,), w, b, eps=1e-6)
+    assert torch.allclose(out, ref, rtol=1e-3, atol=1e-4)
+
+
+def _rope_ref(x, cos_sin, heads):
+    rows, cols = x.shape
+    hd = cols // heads
+    xc = torch.view_as_complex(x.double().reshape(rows, heads, hd // 2, 2))
+    cs = cos_sin.double().reshape(rows, 1, hd // 2, 2)
+    fr = torch.complex(cs[..., 0], cs[..., 1])
+    return torch.view_as_real(xc * fr).reshape(rows, cols).float()
+
+
+@pytest.mark.parametrize("rows,cols,heads,rope", [(100, 1536, 12, True), (512, 1536, 12, False), (33, 5120, 40, True)])
+def test_rmsnorm_rope(rows, cols, heads, rope):
+    ops = _ops()
+    x = torch.randn(rows, 2 * cols, device=DEV).bfloat16()
+    view = x[:, cols:]  # strided view, like q/k inside a fused projection buffer
+    w = 1 + 0.1 * torch.randn(cols, device=DEV)
+    ang = torch.rand(rows, 64, device=DEV, dtype=torch.float64) * 6.28
+    cos_sin = torch.stack([ang.cos(), ang.sin()], -1).reshape(rows, 128).float() if rope else None
+    xf = view.float()
+    ref = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16().float() * w
+    if rope:
+        ref = _rope_ref(ref, cos_sin, heads)
+    keep = x[:, :cols].clone()
+    ops.rmsnorm_rope_(view, w, cos_sin, 128)
+    assert torch.equal(x[:, :cols], keep)  # the other half of the buffer is untouched
+    nbad, maxerr = bf16_ulp_close(view, ref)
+    assert nbad == 0, (nbad, maxerr)
+
+
+def test_linear_f32_small_and_time_path():
+    ops = _ops()
+    t = torch.tensor([999.0, 417.25], device=DEV)
+    sin = ops.time_sinusoid(t, 256)
+    half = 128
+    pos = t.double()
+    s = torch.outer(pos, torch.pow(10000, -torch.arange(half, device=DEV).double().div(half)))
+    ref = torch.cat([s.cos(), s.sin()], 1).float()
+    assert torch.allclose(sin, ref, rtol=0, atol=2e-7)
+    w = torch.randn(1536, 256, device=DEV) * 0.02
+    b = torch.randn(1536, device=DEV) * 0.1
+    y = ops.linear_f32_small(sin, w, b, act=2)
+    assert torch.allclose(y, torch.nn.functional.silu(sin @ w.t() + b), rtol=1e-3, atol=1e-4)
+    w2 = torch.randn(9216, 1536, device=DEV) * 0.02
+    y2 = ops.linear_f32_small(y, w2, None, act=1)
+    assert torch.allclose(y2, torch.nn.functional.silu(y) @ w2.t(), rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_head_unpatchify(fused):
+    ops = _ops()
+    F, Hp, Wp, D = 3, 5, 7, 1536
+    rows = F * Hp * Wp
+    head_mod = torch.randn(1, 2, D, device=DEV) / math.sqrt(D)
+    e = torch.randn(1, D, device=DEV) * 0.3
+    W = torch.randn(64, D, device=DEV) * 0.05
+    b = torch.randn(64, device=DEV) * 0.1
+    if fused:
+        x0 = torch.randn(rows, D, device=DEV).bfloat16()
+        r = torch.randn(rows, D, device=DEV) * 0.3
+        x = x0 + r
+        out = ops.head_unpatchify(x0, head_mod, e, W.t().contiguous(), b, (F, Hp, Wp), residual=r)
+    else:
+        x = torch.randn(rows, D, device=DEV) * 2
+        out = ops.head_unpatchify(x, head_mod, e, W.t().contiguous(), b, (F, Hp, Wp))
+    ee = head_mod + e.unsqueeze(1)
+    y = (torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + ee[0, 1]) + ee[0, 0]).double() @ W.double().t() + b.double()
+    ref = torch.einsum("fhwpqrc->cfphqwr", y.float().view(F, Hp, Wp, 1, 2, 2, 16)).reshape(16, F, Hp * 2, Wp * 2)
+    assert out.shape == ref.shape
+    assert torch.allclose(out, ref, rtol=1e-3, atol=1e-4), float((out - ref).abs().max())
+
+
+# ------------------------------------------------------------------------------------------- tcgen05 GEMM
+def _gemm_ref(a, b):
+    return a.double() @ b.double().t()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (256, 384, 1536), (300, 200, 512), (1000, 1536, 1536), (517, 8960, 1536),
+                                    (777, 1536, 8960), (64, 64, 64), (512, 1536, 4096), (333, 1536, 64)])
+def test_gemm_bias_bf16(M, N, K):
+    ops, L = _ops(), _lib()
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV).bfloat16().float()
+    out = ops.gemm(a, b, bias, L.MC_EPI_BIAS_BF16)
+    ref = (_gemm_ref(a, b) + bias.double()).float()
+    nbad, maxerr = bf16_ulp_close(out, ref)
+    assert nbad == 0, (nbad, maxerr)
+    # fp32 epilogue: the accumulator itself at rtol 1e-3 / atol 1e-4
+    out32 = ops.gemm(a, b, bias, L.MC_EPI_BIAS_F32)
+    assert torch.allclose(out32, ref, rtol=1e-3, atol=1e-4), float((out32 - ref).abs().max())
+
+
+def test_gemm_epilogues():
+    ops, L = _ops(), _lib()
+    M, N, K = 391, 640, 1536
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    b = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV).bfloat16().float()
+    acc = (_gemm_ref(a, b) + bias.double()).float()
+    # GELU(tanh) on the bf16-rounded Linear output
+    out = ops.gemm(a, b, bias, L.MC_EPI_BIAS_GELU_BF16)
+    ref = torch.nn.functional.gelu(acc.bfloat16().float(), approximate="tanh")
+    nbad, maxerr = bf16_ulp_close(out, ref, extra_atol=2e-3)  # a 1-ulp flip of the bf16 pre-activation moves GELU by <= ulp(x)
+    assert nbad == 0, (nbad, maxerr)
+    # gated residual, fp32 stream updated in place
+    x = torch.randn(M, N, device=DEV)
+    gate = torch.randn(N, device=DEV) * 0.5
+    x_ref = x + acc.bfloat16().float() * gate
+    ops.gemm(a, b, bias, L.MC_EPI_BIAS_GATE_RESID, out=x, gate=gate)
+    assert ((x - x_ref).abs() <= 1e-4 + gate.abs() * acc.abs() * 2 ** -7).all()
+    x2 = torch.randn(M, N, device=DEV)
+    x2_ref = x2 + acc.bfloat16().float()
+    ops.gemm(a, b, bias, L.MC_EPI_BIAS_GATE_RESID, out=x2, gate=None)
+    assert ((x2 - x2_ref).abs() <= 1e-4 + acc.abs() * 2 ** -7).all()
+    # row bias (V^T = Wv h^T + bv): A = weight [N, K], B = activations [M, K], padded leading dimension
+    rb = torch.randn(N, device=DEV).bfloat16().float()
+    buf = torch.zeros(N, M + 9, dtype=torch.bfloat16, device=DEV)
+    vt = ops.gemm(b, a, rb, L.MC_EPI_ROWBIAS_BF16, out=buf[:, :M])
+    ref_t = (_gemm_ref(b, a) + rb.double()[:, None]).float()
+    nbad, maxerr = bf16_ulp_close(vt, ref_t)
+    assert nbad == 0, (nbad, maxerr)
+    assert float(buf[:, M:].abs().max()) == 0.0  # nothing written past N columns
+
+
+def test_gemm_strided_operands():
+    ops, L = _ops(), _lib()
+    big = torch.randn(300, 2 * 512, device=DEV).bfloat16()
+    a = big[:, 512:]
+    b = (torch.randn(256, 512, device=DEV) / 22).bfloat16()
+    out = ops.gemm(a, b, None, L.MC_EPI_BIAS_F32)
+    assert torch.allclose(out, _gemm_ref(a, b).float(), rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- tcgen05 attention
+def _attn_ref(q, k, v, heads):
+    Lq, W = q.shape
+    qh = q.double().view(Lq, heads, 128).transpose(0, 1)
+    kh = k.double().view(-1, heads, 128).transpose(0, 1)
+    vh = v.double().view(-1, heads, 128).transpose(0, 1)
+    s = qh @ kh.transpose(1, 2) / math.sqrt(128)
+    return (torch.softmax(s, -1) @ vh).transpose(0, 1).reshape(Lq, W).float()
+
+
+@pytest.mark.parametrize("Lq,Lk,heads,qscale", [(128, 64, 1, 1.0), (128, 128, 1, 1.0), (256, 512, 2, 1.0), (300, 1000, 3, 1.0), (1000, 4095, 12, 1.0),
+                                                (200, 777, 2, 6.0), (130, 512, 12, 1.0)])
+def test_attention(Lq, Lk, heads, qscale):
+    ops = _ops()
+    W = heads * 128
+    q = (torch.randn(Lq, W, device=DEV) * qscale).bfloat16()
+    k = torch.randn(Lk, W, device=DEV).bfloat16()
+    v = torch.randn(Lk, W, device=DEV).bfloat16()
+    ld = (Lk + 7) // 8 * 8
+    vt_buf = torch.zeros(W, ld, dtype=torch.bfloat16, device=DEV)
+    vt_buf[:, :Lk] = v.t()
+    out = ops.attention(q, k, vt_buf[:, :Lk], heads)
+    ref = _attn_ref(q, k, v, heads)
+    # P is rounded to bf16 before the PV product (as in flash-attention): error ~ 2^-9 * sqrt(sum p^2) relative to |v|~1,
+    # plus the bf16 rounding of the output.
+    err = (out.float() - ref).abs()
+    assert float(err.max()) < 2e-2, float(err.max())
+    assert float(err.mean()) < 2e-3, float(err.mean())
+
+
+def test_attention_matches_sdpa_bf16_noise_level():
+    """Our error against the fp64 reference must be no worse than 2x torch SDPA's bf16 error on the same inputs."""
+    ops = _ops()
+    Lq, Lk, heads = 512, 2048, 4
+    W = heads * 128
+    q, k, v = (torch.randn(n, W, device=DEV).bfloat16() for n in (Lq, Lk, Lk))
+    out = ops.attention(q, k, v.t().contiguous(), heads)
+    ref = _attn_ref(q, k, v, heads)
+    sd = torch.nn.functional.scaled_dot_product_attention(q.view(Lq, heads, 128).transpose(0, 1)[None], k.view(Lk, heads, 128).transpose(0, 1)[None],
+                                                          v.view(Lk, heads, 128).transpose(0, 1)[None])[0].transpose(0, 1).reshape(Lq, W)
+    e_ours = (out.float() - ref).pow(2).mean().sqrt().item()
+    e_sdpa = (sd.float() - ref).pow(2).mean().sqrt().item()
+    assert e_ours <= 2.0 * e_sdpa + 1e-4, (e_ours, e_sdpa)
