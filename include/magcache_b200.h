@@ -118,13 +118,14 @@ int32_t mc_residual_sub_stats(const void* x_out, int32_t xo_dtype, const void* x
  * bf16 [F*(H/2)*(W/2), C*4] (column = c*4 + dh*2 + dw, the Conv3d weight's flattened (c, kt=1, kh, kw) order). */
 int32_t mc_patchify(const float* latent, int32_t C, int32_t F, int32_t H, int32_t W, void* tokens_bf16, void* stream);
 
-/* AdaLN-modulated LayerNorm: y = LN(x) * (a) + b, eps, no affine inside LN; per-row fp32 statistics.
- *   mode 0: a = 1 + (mod[scale_idx] + e[scale_idx]),  b = mod[shift_idx] + e[shift_idx]   (block norm1/norm2, head)
- *   mode 1: a = w, b = bias                                                             (norm3, elementwise affine)
- * x: [rows, cols] (x_dtype fp32 or bf16); round_ln_to_bf16 != 0 reproduces `.type_as(x)` for a bf16 stream (block 0).
- * out: [rows, cols], out_dtype bf16 (GEMM operand) or fp32. */
+/* AdaLN-modulated LayerNorm: y = LN(x) * a + b, eps inside the LN, no affine in the LN itself; per-row fp32 statistics.
+ *   mode 0: a = 1 + p0[scale_idx], b = p0[shift_idx]   p0 = e = modulation + e0, fp32 [k, cols]  (block norm1/norm2:
+ *           `norm1(x).float() * (1 + e[1]) + e[0]`, upstream WanAttentionBlock.forward); p1 unused
+ *   mode 1: a = p0, b = p1                             (norm3, elementwise affine weight / bias)
+ * x: [rows, cols] (fp32 or bf16); round_ln_to_bf16 != 0 reproduces `.type_as(x)` for a bf16 stream (block 0).
+ * out: [rows, cols] bf16 (GEMM operand) or fp32. x/out 32-byte aligned, cols % 8 == 0, cols <= 8192. */
 int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t cols, float eps, int32_t mode,
-                       const float* a_or_mod, const float* b_or_e, int32_t scale_idx, int32_t shift_idx,
+                       const float* p0, const float* p1, int32_t scale_idx, int32_t shift_idx,
                        int32_t round_ln_to_bf16, void* out, int32_t out_dtype, void* stream);
 
 /* WanRMSNorm over the full model dim followed by 3-axis RoPE (rope_apply), in place on bf16 [rows, cols]:

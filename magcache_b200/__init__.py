@@ -1,0 +1,12 @@
+"""magcache_b200 — B200-native (sm_100a) MagCache denoising hot path behind the reference's monkey-patch API.
+
+    from magcache_b200 import magcache_forward, magcache_calibration, init_magcache
+
+Importing this package loads libmagcache_b200.so (build it with `python -m magcache_b200.build`); there is no CPU fallback.
+"""
+from .config import PRESETS, MagCacheConfig, interp_cfg, nearest_interp, tables  # noqa: F401
+from .patch import (init_magcache, init_magcache_calibration, magcache_branch, magcache_calibration,  # noqa: F401
+                    magcache_forward)
+from .wan import WAN_CONFIGS, WanDims, WanEngine, WanModelHandle, WanWeights  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,95 @@
+"""Skip controller front end. The decision arithmetic lives in the C ABI (`mc_ctrl_decide` / `mc_ctrl_advance`, float64,
+bit-exact with the reference); this module only moves state between the reference's attribute names and the C structs."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import CtrlConfig, CtrlState, check, lib
+
+
+def make_ctrl_config(num_steps, thresh, K, retention_ratio, mag_ratios, branches, cmp, retention_mode, veto_index=-1, veto_base=0):
+    arr = np.ascontiguousarray(mag_ratios, dtype=np.float64)
+    if len(arr) < num_steps:
+        raise IndexError(f"mag_ratios has {len(arr)} entries but num_steps={num_steps} (interpolate first, magcache_generate.py:915-919)")
+    cfg = CtrlConfig()
+    cfg.num_steps, cfg.branches, cfg.K, cfg.cmp, cfg.retention_mode = int(num_steps), int(branches), int(K), int(cmp), int(retention_mode)
+    cfg.veto_index, cfg.veto_base = int(veto_index), int(veto_base)
+    cfg.thresh, cfg.retention_ratio = float(thresh), float(retention_ratio)
+    cfg.mag_ratios = arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    cfg._keepalive = arr
+    return cfg
+
+
+def schedule_mask(cfg, calls):
+    """Whole skip schedule (uint8 0/1 per forward call) from a fresh state."""
+    mask = np.zeros(calls, dtype=np.uint8)
+    check(lib.mc_ctrl_mask(ctypes.byref(cfg), calls, mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
+    return mask
+
+
+class AttrController:
+    """Runs the controller on state stored under the reference's attribute names of `owner` (a model instance whose class
+    carries `cnt`, `accumulated_ratio`, ... exactly as MagCache4Wan2.1/magcache_generate.py:897-906 installs them).
+    Scalar families (FLUX/Hunyuan) keep scalars, Wan keeps 2-element lists — whatever form the script wrote is preserved."""
+
+    def __init__(self, family_kwargs):
+        self.kw = family_kwargs
+        self._cfg = None
+        self._key = None
+
+    def _config(self, o):
+        mr = o.mag_ratios
+        key = (id(mr), len(mr), o.num_steps, float(o.magcache_thresh), int(o.K), float(o.retention_ratio))
+        if self._key != key:
+            self._cfg = make_ctrl_config(o.num_steps, o.magcache_thresh, o.K, o.retention_ratio, np.asarray(mr, dtype=np.float64), **self.kw)
+            self._key = key
+        return self._cfg
+
+    def _load(self, o):
+        st = CtrlState()
+        st.cnt = int(o.cnt)
+        if self.kw["branches"] == 2:
+            for i in range(2):
+                st.accumulated_ratio[i] = float(o.accumulated_ratio[i])
+                st.accumulated_err[i] = float(o.accumulated_err[i])
+                st.accumulated_steps[i] = int(o.accumulated_steps[i])
+        else:
+            st.accumulated_ratio[0] = float(o.accumulated_ratio)
+            st.accumulated_err[0] = float(o.accumulated_err)
+            st.accumulated_steps[0] = int(o.accumulated_steps)
+            st.accumulated_ratio[1] = 1.0
+        return st
+
+    def _store(self, o, st, with_cnt):
+        cls = type(o)
+        if self.kw["branches"] == 2:
+            # the reference mutates the class-level lists in place (self.accumulated_ratio[i] = ...)
+            for i in range(2):
+                o.accumulated_ratio[i] = st.accumulated_ratio[i]
+                o.accumulated_err[i] = st.accumulated_err[i]
+                o.accumulated_steps[i] = st.accumulated_steps[i]
+        else:
+            o.accumulated_ratio, o.accumulated_err, o.accumulated_steps = st.accumulated_ratio[0], st.accumulated_err[0], st.accumulated_steps[0]
+        if with_cnt:
+            o.cnt = st.cnt
+        del cls
+
+    def decide(self, o):
+        cfg = self._config(o)
+        st = self._load(o)
+        skip = ctypes.c_int32(0)
+        check(lib.mc_ctrl_decide(ctypes.byref(cfg), ctypes.byref(st), ctypes.byref(skip)))
+        self._store(o, st, with_cnt=False)
+        return bool(skip.value)
+
+    def advance(self, o):
+        cfg = self._config(o)
+        st = self._load(o)
+        check(lib.mc_ctrl_advance(ctypes.byref(cfg), ctypes.byref(st)))
+        if st.cnt == 0 and self.kw["branches"] == 2:
+            # end of video: the reference REBINDS fresh lists (magcache_generate.py:308-311)
+            o.accumulated_ratio, o.accumulated_err, o.accumulated_steps = [1.0, 1.0], [0.0, 0.0], [0, 0]
+            o.cnt = 0
+        else:
+            self._store(o, st, with_cnt=True)

@@ -15,19 +15,12 @@ struct Elem;
 template <>
 struct Elem<MC_F32> {
   static constexpr int kBytes = 4;
+  static constexpr int kAlign = 32;  // 8 fp32 move as ONE 256-bit access per lane
   __device__ static __forceinline__ void load8(const void* base, int64_t i, float (&f)[8]) {
-    const uint4* p = reinterpret_cast<const uint4*>(static_cast<const float*>(base) + i);
-    uint4 a = ptx::ld_nc_v4(p), b = ptx::ld_nc_v4(p + 1);
-    f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
-    f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+    ptx::ld_nc_v8_f32(static_cast<const float*>(base) + i, f);
   }
   __device__ static __forceinline__ void store8(void* base, int64_t i, const float (&f)[8]) {
-    uint4* p = reinterpret_cast<uint4*>(static_cast<float*>(base) + i);
-    uint4 a, b;
-    a.x = __float_as_uint(f[0]); a.y = __float_as_uint(f[1]); a.z = __float_as_uint(f[2]); a.w = __float_as_uint(f[3]);
-    b.x = __float_as_uint(f[4]); b.y = __float_as_uint(f[5]); b.z = __float_as_uint(f[6]); b.w = __float_as_uint(f[7]);
-    ptx::st_na_v4(p, a);
-    ptx::st_na_v4(p + 1, b);
+    ptx::st_na_v8_f32(static_cast<float*>(base) + i, f);
   }
   __device__ static __forceinline__ float load1(const void* base, int64_t i) { return static_cast<const float*>(base)[i]; }
   __device__ static __forceinline__ void store1(void* base, int64_t i, float v) { static_cast<float*>(base)[i] = v; }
@@ -35,6 +28,7 @@ struct Elem<MC_F32> {
 template <>
 struct Elem<MC_BF16> {
   static constexpr int kBytes = 2;
+  static constexpr int kAlign = 16;
   __device__ static __forceinline__ void load8(const void* base, int64_t i, float (&f)[8]) {
     uint4 a = ptx::ld_nc_v4(static_cast<const __nv_bfloat16*>(base) + i);
     unpack_bf16x8(a, f);
@@ -91,7 +85,8 @@ __global__ void axpb_scalar_kernel(const void* __restrict__ a, const void* __res
 template <int DA, int DB, int DO>
 static int32_t launch_axpb(const void* a, const void* b, void* out, int64_t n, float sign, cudaStream_t s) {
   constexpr int kUnroll = 4;
-  const bool vec_ok = aligned16(a) && aligned16(b) && aligned16(out);
+  auto al = [](const void* p, int a_) { return (reinterpret_cast<uintptr_t>(p) & static_cast<uintptr_t>(a_ - 1)) == 0; };
+  const bool vec_ok = al(a, Elem<DA>::kAlign) && al(b, Elem<DB>::kAlign) && al(out, Elem<DO>::kAlign);
   const int64_t n_groups = vec_ok ? n / 8 : 0;
   if (n_groups > 0) {
     const int threads = 256;
@@ -112,9 +107,9 @@ static int32_t launch_axpb(const void* a, const void* b, void* out, int64_t n, f
 
 static int32_t dispatch_axpb(const void* a, int da, const void* b, int db, void* out, int dout, int64_t n, float sign,
                              cudaStream_t s, const char* who) {
-  MC_CHECK_ARG(a && b && out, "%s: null pointer", who);
   MC_CHECK_ARG(n >= 0, "%s: negative element count", who);
-  if (n == 0) return MC_OK;
+  if (n == 0) return MC_OK;  // empty tensors have null data pointers
+  MC_CHECK_ARG(a && b && out, "%s: null pointer", who);
 #define MC_CASE(A, B, O) \
   if (da == A && db == B && dout == O) return launch_axpb<A, B, O>(a, b, out, n, sign, s);
   MC_CASE(MC_BF16, MC_F32, MC_F32)    // Wan hit: bf16 patch-embed output + fp32 residual
@@ -227,7 +222,8 @@ int32_t mc_residual_stats(const void* r_cur, int32_t cur_dtype, const void* r_pr
   MC_CHECK_ARG(r_cur && r_prev && stats_dev, "mc_residual_stats: null pointer");
   MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0, "mc_residual_stats: rows=%lld cols=%d (cols must be a multiple of 8)",
                static_cast<long long>(rows), cols);
-  MC_CHECK_ARG(mc::aligned16(r_cur) && mc::aligned16(r_prev), "mc_residual_stats: pointers must be 16-byte aligned");
+  MC_CHECK_ARG((reinterpret_cast<uintptr_t>(r_cur) & 31u) == 0 && (reinterpret_cast<uintptr_t>(r_prev) & 31u) == 0,
+               "mc_residual_stats: pointers must be 32-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cur_dtype == MC_F32 && prev_dtype == MC_F32)
     return mc::launch_stats<MC_F32, MC_F32, false>(r_cur, nullptr, nullptr, r_prev, rows, cols, denom_eps, stats_dev, s);
@@ -242,8 +238,9 @@ int32_t mc_residual_sub_stats(const void* x_out, int32_t xo_dtype, const void* x
   MC_CHECK_ARG(x_out && x_in && r && r_prev && stats_dev, "mc_residual_sub_stats: null pointer");
   MC_CHECK_ARG(xo_dtype == MC_F32 && xi_dtype == MC_BF16, "mc_residual_sub_stats: only fp32 - bf16 -> fp32 (the Wan stream) is built");
   MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0, "mc_residual_sub_stats: cols must be a multiple of 8");
-  MC_CHECK_ARG(mc::aligned16(x_out) && mc::aligned16(x_in) && mc::aligned16(r) && mc::aligned16(r_prev),
-               "mc_residual_sub_stats: pointers must be 16-byte aligned");
+  MC_CHECK_ARG((reinterpret_cast<uintptr_t>(x_out) & 31u) == 0 && mc::aligned16(x_in) && (reinterpret_cast<uintptr_t>(r) & 31u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(r_prev) & 31u) == 0,
+               "mc_residual_sub_stats: fp32 pointers must be 32-byte aligned, bf16 16-byte");
   return mc::launch_stats<MC_F32, MC_F32, true>(x_out, x_in, r, r_prev, rows, cols, denom_eps, stats_dev,
                                                 static_cast<cudaStream_t>(stream));
 }

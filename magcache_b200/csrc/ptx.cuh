@@ -188,4 +188,28 @@ __device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {  // streamin
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 256-bit global accesses (sm_100+): one instruction per lane moves 8 fp32, so a warp touches 1 KB contiguously and every
+// 32-byte sector is requested exactly once (two .v4 accesses per lane would request each sector twice from L2).
+__device__ __forceinline__ void ld_nc_v8_f32(const float* p, float (&f)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ld_v8_f32(const float* p, float (&f)[8]) {  // coherent variant (buffers written by this grid)
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st_na_v8_f32(float* p, const float (&f)[8]) {
+  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]),
+               "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_v8_f32(float* p, const float (&f)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]),
+               "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
+               : "memory");
+}
+
 }  // namespace ptx

@@ -7,8 +7,9 @@
 
 namespace mc {
 
-// A "team" of TPR threads owns one row; each thread keeps up to MAXG groups of 8 elements in registers.
-constexpr int kMaxG = 4;
+// A "team" of TPR threads owns one row; each thread keeps up to kMaxG groups of 8 elements in registers.
+// TPR = 32 (one warp per row, shuffle-only reductions) covers cols <= 2048; TPR = 128 covers cols <= 8192.
+constexpr int kMaxG = 8;
 
 template <int TPR>
 __device__ __forceinline__ float team_sum(float v, float* scratch /* [rows_per_block][TPR/32] */, int team, int lane_in_team) {
@@ -27,26 +28,32 @@ __device__ __forceinline__ float team_sum(float v, float* scratch /* [rows_per_b
 
 __device__ __forceinline__ void load_row_group(const void* x, int dtype_bf16, int64_t off, float (&f)[8]) {
   if (dtype_bf16) {
-    uint4 v = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x) + off);
+    uint4 v = ptx::ld_nc_v4(static_cast<const __nv_bfloat16*>(x) + off);
     unpack_bf16x8(v, f);
   } else {
-    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(x) + off);
-    float4 a = p[0], b = p[1];
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    ptx::ld_nc_v8_f32(static_cast<const float*>(x) + off, f);
   }
+}
+__device__ __forceinline__ void load_param8(const float* p, float (&f)[8]) {  // per-column parameters: L1-resident, reused by every row
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
 // ---- K7: LayerNorm (no affine) + modulation / affine, optional bf16 rounding of the LN output -----------------
+//   mode 0: y = LN(x) * (1 + p0[scale_idx]) + p0[shift_idx]   with p0 = e = modulation + e0, fp32 [k, cols]
+//   mode 1: y = LN(x) * p0 + p1                               (elementwise affine)
 template <int TPR>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const void* __restrict__ x, int x_bf16, int64_t rows, int cols, float eps,
-                                                          int mode, const float* __restrict__ a_or_mod,
-                                                          const float* __restrict__ b_or_e, int scale_idx, int shift_idx,
-                                                          int round_ln, void* __restrict__ out, int out_bf16) {
+                                                          int mode, const float* __restrict__ p0, const float* __restrict__ p1,
+                                                          int scale_idx, int shift_idx, int round_ln, void* __restrict__ out,
+                                                          int out_bf16) {
   constexpr int RPB = 256 / TPR;  // rows per block
   __shared__ float scratch[RPB * (TPR / 32 > 0 ? TPR / 32 : 1)];
   const int team = threadIdx.x / TPR, lt = threadIdx.x % TPR;
   const int groups = cols >> 3;
   const float inv_n = 1.0f / static_cast<float>(cols);
+  const float* pa = (mode == 0) ? p0 + static_cast<int64_t>(scale_idx) * cols : p0;
+  const float* pb = (mode == 0) ? p0 + static_cast<int64_t>(shift_idx) * cols : p1;
   for (int64_t row0 = static_cast<int64_t>(blockIdx.x) * RPB; row0 < rows; row0 += static_cast<int64_t>(gridDim.x) * RPB) {
     const int64_t row = row0 + team;
     const bool live = row < rows;
@@ -59,9 +66,6 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const void* __restrict
         load_row_group(x, x_bf16, row * cols + g * 8, v[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[i][j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
       }
     }
     const float mean = team_sum<TPR>(s, scratch, team, lt) * inv_n;
@@ -84,28 +88,20 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const void* __restrict
       const int g = lt + i * TPR;
       if (live && g < groups) {
         const int c0 = g * 8;
-        float o[8];
+        float a[8], b[8], o[8];
+        load_param8(pa + c0, a);
+        load_param8(pb + c0, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float y = (v[i][j] - mean) * rstd;
           if (round_ln) y = round_bf16(y);
-          float a, b;
-          if (mode == 0) {
-            const float sc = a_or_mod[scale_idx * cols + c0 + j] + b_or_e[scale_idx * cols + c0 + j];
-            a = 1.0f + sc;
-            b = a_or_mod[shift_idx * cols + c0 + j] + b_or_e[shift_idx * cols + c0 + j];
-          } else {
-            a = a_or_mod[c0 + j];
-            b = b_or_e[c0 + j];
-          }
-          o[j] = __fadd_rn(__fmul_rn(y, a), b);  // torch eager: separate mul and add, no FMA contraction
+          const float aa = (mode == 0) ? 1.0f + a[j] : a[j];
+          o[j] = __fadd_rn(__fmul_rn(y, aa), b[j]);  // torch eager: separate mul and add, no FMA contraction
         }
         if (out_bf16) {
-          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + row * cols + c0) = pack_bf16x8(o);
+          ptx::st_na_v4(static_cast<__nv_bfloat16*>(out) + row * cols + c0, pack_bf16x8(o));
         } else {
-          float4* p = reinterpret_cast<float4*>(static_cast<float*>(out) + row * cols + c0);
-          p[0] = make_float4(o[0], o[1], o[2], o[3]);
-          p[1] = make_float4(o[4], o[5], o[6], o[7]);
+          ptx::st_na_v8_f32(static_cast<float*>(out) + row * cols + c0, o);
         }
       }
     }
@@ -131,7 +127,8 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(__nv_bfloat16* __rest
     for (int i = 0; i < kMaxG; ++i) {
       const int g = lt + i * TPR;
       if (live && g < groups) {
-        load_row_group(x, 1, row * ld + g * 8, v[i]);
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + row * ld + g * 8);  // coherent: updated in place below
+        unpack_bf16x8(raw, v[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) q = fmaf(v[i][j], v[i][j], q);
       }
@@ -143,19 +140,19 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(__nv_bfloat16* __rest
       const int g = lt + i * TPR;
       if (live && g < groups) {
         const int c0 = g * 8;
-        float o[8];
+        float wv[8], o[8];
+        load_param8(w + c0, wv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = round_bf16(v[i][j] * r) * w[c0 + j];  // _norm(x.float()).type_as(x) * weight
+        for (int j = 0; j < 8; ++j) o[j] = round_bf16(v[i][j] * r) * wv[j];  // _norm(x.float()).type_as(x) * weight
         if (cos_sin != nullptr) {
           const int d0 = c0 % head_dim;  // position inside the head; 8 elements = 4 complex pairs
-          const float4* cs = reinterpret_cast<const float4*>(cos_sin + row * head_dim + d0);
-          const float4 cs0 = cs[0], cs1 = cs[1];
-          const float c[4] = {cs0.x, cs0.z, cs1.x, cs1.z}, sn[4] = {cs0.y, cs0.w, cs1.y, cs1.w};
+          float cs[8];
+          ptx::ld_nc_v8_f32(cos_sin + row * head_dim + d0, cs);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            const float re = o[2 * p], im = o[2 * p + 1];
-            o[2 * p] = __fsub_rn(__fmul_rn(re, c[p]), __fmul_rn(im, sn[p]));
-            o[2 * p + 1] = __fadd_rn(__fmul_rn(re, sn[p]), __fmul_rn(im, c[p]));
+            const float re = o[2 * p], im = o[2 * p + 1], c = cs[2 * p], sn = cs[2 * p + 1];
+            o[2 * p] = __fsub_rn(__fmul_rn(re, c), __fmul_rn(im, sn));
+            o[2 * p + 1] = __fadd_rn(__fmul_rn(re, sn), __fmul_rn(im, c));
           }
         }
         *reinterpret_cast<uint4*>(x + row * ld + c0) = pack_bf16x8(o);
@@ -379,23 +376,24 @@ int32_t mc_patchify(const float* latent, int32_t C, int32_t F, int32_t H, int32_
   return MC_OK;
 }
 
-int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t cols, float eps, int32_t mode, const float* a_or_mod,
-                       const float* b_or_e, int32_t scale_idx, int32_t shift_idx, int32_t round_ln_to_bf16, void* out,
+int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t cols, float eps, int32_t mode, const float* p0,
+                       const float* p1, int32_t scale_idx, int32_t shift_idx, int32_t round_ln_to_bf16, void* out,
                        int32_t out_dtype, void* stream) {
-  MC_CHECK_ARG(x && a_or_mod && b_or_e && out, "mc_ln_modulate: null pointer");
-  MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0 && cols <= 256 * 8 * mc::kMaxG, "mc_ln_modulate: cols=%d unsupported", cols);
+  MC_CHECK_ARG(x && p0 && out && (mode == 0 || p1), "mc_ln_modulate: null pointer");
+  MC_CHECK_ARG(mode == 0 || mode == 1, "mc_ln_modulate: bad mode %d", mode);
+  MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0 && cols <= 128 * 8 * mc::kMaxG, "mc_ln_modulate: cols=%d unsupported", cols);
+  MC_CHECK_ARG(mc::aligned16(p0) && (p1 == nullptr || mc::aligned16(p1)), "mc_ln_modulate: parameters must be 16-byte aligned");
   MC_CHECK_ARG((x_dtype == MC_F32 || x_dtype == MC_BF16) && (out_dtype == MC_F32 || out_dtype == MC_BF16), "mc_ln_modulate: bad dtype");
-  MC_CHECK_ARG(mc::aligned16(x) && mc::aligned16(out), "mc_ln_modulate: x/out must be 16-byte aligned");
+  MC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 31u) == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0,
+               "mc_ln_modulate: x/out must be 32-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = cols / 8;
 #define MC_LN(TPR)                                                                                                             \
   mc::ln_modulate_kernel<TPR><<<mc::grid_for(rows, 256 / TPR), 256, 0, s>>>(x, x_dtype == MC_BF16, rows, cols, eps, mode,       \
-                                                                            a_or_mod, b_or_e, scale_idx, shift_idx,            \
+                                                                            p0, p1, scale_idx, shift_idx,                      \
                                                                             round_ln_to_bf16, out, out_dtype == MC_BF16)
   if (groups <= 32 * mc::kMaxG) MC_LN(32);
-  else if (groups <= 64 * mc::kMaxG) MC_LN(64);
-  else if (groups <= 128 * mc::kMaxG) MC_LN(128);
-  else MC_LN(256);
+  else MC_LN(128);
 #undef MC_LN
   MC_CHECK_LAUNCH("ln_modulate_kernel launch");
   return MC_OK;
@@ -404,19 +402,18 @@ int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t col
 int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, const float* w, float eps, const float* cos_sin,
                         int32_t head_dim, void* stream) {
   MC_CHECK_ARG(x_bf16 && w, "mc_rmsnorm_rope: null pointer");
-  MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0 && cols <= 256 * 8 * mc::kMaxG && ld >= cols && ld % 8 == 0,
+  MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0 && cols <= 128 * 8 * mc::kMaxG && ld >= cols && ld % 8 == 0,
                "mc_rmsnorm_rope: cols=%d ld=%lld unsupported", cols, static_cast<long long>(ld));
   MC_CHECK_ARG(mc::aligned16(x_bf16), "mc_rmsnorm_rope: x must be 16-byte aligned");
-  MC_CHECK_ARG(cos_sin == nullptr || (head_dim >= 8 && head_dim % 8 == 0 && cols % head_dim == 0 && mc::aligned16(cos_sin)),
+  MC_CHECK_ARG(mc::aligned16(w), "mc_rmsnorm_rope: weight must be 16-byte aligned");
+  MC_CHECK_ARG(cos_sin == nullptr || (head_dim >= 8 && head_dim % 8 == 0 && cols % head_dim == 0 && (reinterpret_cast<uintptr_t>(cos_sin) & 31u) == 0),
                "mc_rmsnorm_rope: bad head_dim %d", head_dim);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = cols / 8;
   __nv_bfloat16* xp = static_cast<__nv_bfloat16*>(x_bf16);
 #define MC_RMS(TPR) mc::rmsnorm_rope_kernel<TPR><<<mc::grid_for(rows, 256 / TPR), 256, 0, s>>>(xp, ld, rows, cols, w, eps, cos_sin, head_dim)
   if (groups <= 32 * mc::kMaxG) MC_RMS(32);
-  else if (groups <= 64 * mc::kMaxG) MC_RMS(64);
-  else if (groups <= 128 * mc::kMaxG) MC_RMS(128);
-  else MC_RMS(256);
+  else MC_RMS(128);
 #undef MC_RMS
   MC_CHECK_LAUNCH("rmsnorm_rope_kernel launch");
   return MC_OK;

@@ -11,6 +11,25 @@ from . import _lib
 from ._lib import MC_BF16, MC_F32, check, lib
 
 LAUNCHES = 0  # number of libmagcache_b200 kernel-launching calls made by this process (bench.py reports the delta)
+PROFILE = None  # bench.py sets this to a dict: tag -> list of (start_event, end_event) recorded around tagged launches
+
+
+class _Timed:
+    """Records a CUDA-event pair on the launching stream around one tagged kernel launch (only when PROFILE is enabled)."""
+
+    def __init__(self, tag):
+        self.tag = tag if (PROFILE is not None and tag is not None) else None
+
+    def __enter__(self):
+        if self.tag is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.tag is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.setdefault(self.tag, []).append((self.e0, e1))
 
 
 def _dt(t):
@@ -40,13 +59,14 @@ def _promote(a, b):
     return torch.promote_types(a.dtype, b.dtype)
 
 
-def cache_hit_add(x, r, out=None):
+def cache_hit_add(x, r, out=None, tag=None):
     """`x + residual_x` (MagCache4Wan2.1/magcache_generate.py:295) with torch's type promotion."""
     _dev(x, "x"), _dev(r, "r")
     assert x.shape == r.shape and x.is_contiguous() and r.is_contiguous()
     if out is None:
         out = torch.empty(x.shape, dtype=_promote(x, r), device=x.device)
-    check(lib.mc_cache_hit_add(x.data_ptr(), _dt(x), r.data_ptr(), _dt(r), out.data_ptr(), _dt(out), x.numel(), _stream()))
+    with _Timed(tag):
+        check(lib.mc_cache_hit_add(x.data_ptr(), _dt(x), r.data_ptr(), _dt(r), out.data_ptr(), _dt(out), x.numel(), _stream()))
     _count()
     return out
 
@@ -107,14 +127,14 @@ def patchify(latent):
     return out
 
 
-def ln_modulate(x, mod, e, scale_idx, shift_idx, eps=1e-6, round_ln_to_bf16=False, out_dtype=torch.bfloat16, out=None):
-    """bf16/fp32( LN(x) * (1 + mod[scale]+e[scale]) + (mod[shift]+e[shift]) ) ; x [rows, cols], mod/e fp32 [k, cols]."""
+def ln_modulate(x, em, scale_idx, shift_idx, eps=1e-6, round_ln_to_bf16=False, out_dtype=torch.bfloat16, out=None):
+    """bf16/fp32( LN(x) * (1 + em[scale_idx]) + em[shift_idx] ) ; x [rows, cols], em = modulation + e0, fp32 [k, cols]."""
     _dev(x)
     rows, cols = x.shape
-    assert x.is_contiguous() and mod.dtype == torch.float32 and e.dtype == torch.float32 and mod.is_contiguous() and e.is_contiguous()
+    assert x.is_contiguous() and em.dtype == torch.float32 and em.is_contiguous() and em.shape[-1] == cols
     if out is None:
         out = torch.empty(rows, cols, dtype=out_dtype, device=x.device)
-    check(lib.mc_ln_modulate(x.data_ptr(), _dt(x), rows, cols, eps, 0, mod.data_ptr(), e.data_ptr(), scale_idx, shift_idx,
+    check(lib.mc_ln_modulate(x.data_ptr(), _dt(x), rows, cols, eps, 0, em.data_ptr(), None, scale_idx, shift_idx,
                              int(round_ln_to_bf16), out.data_ptr(), _dt(out), _stream()))
     _count()
     return out
@@ -146,7 +166,7 @@ def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6):
     return x
 
 
-def gemm(a, b, bias=None, epilogue=_lib.MC_EPI_BIAS_BF16, out=None, gate=None):
+def gemm(a, b, bias=None, epilogue=_lib.MC_EPI_BIAS_BF16, out=None, gate=None, tag=None):
     """acc = a @ b.T on tcgen05 (a [M,K] bf16, b [N,K] bf16, row stride allowed) + fused epilogue (see MC_EPI_*)."""
     _dev(a), _dev(b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
@@ -160,13 +180,14 @@ def gemm(a, b, bias=None, epilogue=_lib.MC_EPI_BIAS_BF16, out=None, gate=None):
     assert out.dtype == want and out.stride(1) == 1 and out.shape == (M, N)
     for v in (bias, gate):
         assert v is None or (v.dtype == torch.float32 and v.is_contiguous())
-    check(lib.mc_gemm_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, bias.data_ptr() if bias is not None else None,
-                           epilogue, out.data_ptr(), out.stride(0), gate.data_ptr() if gate is not None else None, _stream()))
+    with _Timed(tag):
+        check(lib.mc_gemm_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, bias.data_ptr() if bias is not None else None,
+                               epilogue, out.data_ptr(), out.stride(0), gate.data_ptr() if gate is not None else None, _stream()))
     _count()
     return out
 
 
-def attention(q, k, vt, heads, scale=None, out=None):
+def attention(q, k, vt, heads, scale=None, out=None, tag=None):
     """softmax(q k^T * scale) v per head (head_dim 128). q [Lq, H*128], k [Lk, H*128], vt = V^T [H*128, Lk] (bf16)."""
     _dev(q), _dev(k), _dev(vt)
     assert q.dtype == k.dtype == vt.dtype == torch.bfloat16 and q.stride(1) == 1 and k.stride(1) == 1 and vt.stride(1) == 1
@@ -177,8 +198,9 @@ def attention(q, k, vt, heads, scale=None, out=None):
         scale = 1.0 / math.sqrt(128)
     if out is None:
         out = torch.empty(Lq, W, dtype=torch.bfloat16, device=q.device)
-    check(lib.mc_attn_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), vt.data_ptr(), vt.stride(0), out.data_ptr(),
-                          out.stride(0), Lq, Lk, heads, float(scale), _stream()))
+    with _Timed(tag):
+        check(lib.mc_attn_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), vt.data_ptr(), vt.stride(0), out.data_ptr(),
+                              out.stride(0), Lq, Lk, heads, float(scale), _stream()))
     _count()
     return out
 
@@ -205,7 +227,7 @@ def time_sinusoid(t, dim):
     return out
 
 
-def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6):
+def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None):
     """head(x, e) + unpatchify (MagCache4Wan2.1/magcache_generate.py:304-305) -> fp32 [c_out, F, 2*Hp, 2*Wp].
     With `residual` (fp32) the cache-hit sum x + residual is formed on the fly (fused hit path)."""
     _dev(x)
@@ -216,8 +238,9 @@ def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == x.shape
     out = torch.empty(c_out, F, 2 * Hp, 2 * Wp, dtype=torch.float32, device=x.device)
-    check(lib.mc_head_unpatchify(x.data_ptr(), _dt(x), residual.data_ptr() if residual is not None else None, cols, F, Hp, Wp, c_out,
-                                 head_mod.data_ptr(), e.data_ptr(), w_t.data_ptr(), b.data_ptr(), eps, out.data_ptr(), _stream()))
+    with _Timed(tag):
+        check(lib.mc_head_unpatchify(x.data_ptr(), _dt(x), residual.data_ptr() if residual is not None else None, cols, F, Hp, Wp, c_out,
+                                     head_mod.data_ptr(), e.data_ptr(), w_t.data_ptr(), b.data_ptr(), eps, out.data_ptr(), _stream()))
     _count()
     return out
 
@@ -226,6 +249,15 @@ def cast(src, dtype):
     _dev(src)
     assert src.is_contiguous()
     dst = torch.empty(src.shape, dtype=dtype, device=src.device)
+    check(lib.mc_cast(src.data_ptr(), _dt(src), dst.data_ptr(), _dt(dst), src.numel(), _stream()))
+    _count()
+    return dst
+
+
+def cast_into(src, dst):
+    """dst[...] = src converted (bf16 <-> fp32), no allocation."""
+    _dev(src), _dev(dst)
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
     check(lib.mc_cast(src.data_ptr(), _dt(src), dst.data_ptr(), _dt(dst), src.numel(), _stream()))
     _count()
     return dst

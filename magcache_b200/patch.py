@@ -1,0 +1,181 @@
+"""Drop-in replacements for the reference's monkey-patched transformer forwards.
+
+Usage is the reference's own (MagCache4Wan2.1/magcache_generate.py:896-928): assign the function to the model class and set
+the class attributes it reads —
+
+    from magcache_b200 import magcache_forward, init_magcache
+    init_magcache(wan_t2v.model, sample_steps=50, thresh=0.12, K=4, retention_ratio=0.2, ckpt_dir=args.ckpt_dir)
+    # or, literally as the script does:  wan_t2v.model.__class__.forward = magcache_forward ; ...cnt = 0 ; ...
+
+Signatures, attribute names (`cnt, num_steps, magcache_thresh, K, retention_ratio, accumulated_ratio, accumulated_err,
+accumulated_steps, residual_cache, mag_ratios`; calibration: `norm_ratio, norm_std, cos_dis`) and error behaviour follow the
+reference. Everything between the Python call and the returned tensors runs on the CUDA kernels of libmagcache_b200.so;
+there is no eager/PyTorch fallback — a CPU tensor or a missing library raises.
+"""
+import torch
+
+from . import ops
+from .config import interp_cfg, table_for_ckpt_dir, tables
+from .controller import AttrController
+from .wan import WanEngine, WanWeights
+
+_WAN_CTRL = dict(branches=2, cmp=0, retention_mode=0, veto_index=-1, veto_base=0)  # `<`, int(n*R): magcache_generate.py:279-286
+
+
+def _engine(self):
+    eng = self.__dict__.get("_mc_engine")
+    if eng is None:
+        if hasattr(self, "patch_embedding"):
+            dev = self.patch_embedding.weight.device
+            if dev.type != "cuda":
+                raise RuntimeError("magcache_b200: the model must be on a CUDA device (no CPU path)")
+            weights = WanWeights.from_module(self, dev)
+        else:
+            raise TypeError("magcache_b200.magcache_forward expects a Wan2.1 WanModel (or an object carrying `_mc_engine`)")
+        eng = WanEngine(weights)
+        object.__setattr__(self, "_mc_engine", eng)
+    return eng
+
+
+def _controller(self):
+    c = self.__dict__.get("_mc_ctrl")
+    if c is None:
+        c = AttrController(_WAN_CTRL)
+        object.__setattr__(self, "_mc_ctrl", c)
+    return c
+
+
+def _prologue(self, x, t, context, seq_len, clip_fea, y):
+    if getattr(self, "model_type", "t2v") == "i2v" or clip_fea is not None or y is not None:
+        raise NotImplementedError("magcache_b200: only the t2v path is built (SURVEY §8f lists i2v/VACE as next)")
+    if len(x) != 1 or len(context) != 1:
+        raise NotImplementedError("magcache_b200: one sample per call (the reference's caller passes [latents], wan_magcache.py:296-299)")
+    eng = _engine(self)
+    lat = x[0]
+    if not lat.is_cuda:
+        raise RuntimeError("magcache_b200: latents must be CUDA tensors (no CPU path)")
+    n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
+    assert n_tok <= seq_len  # reference: assert seq_lens.max() <= seq_len
+    if n_tok != seq_len:
+        raise NotImplementedError("magcache_b200: seq_len padding (sequence-parallel upstream) is not built; pass seq_len == token count")
+    x0, e, e0, ctx, grid = eng.prologue(lat.float(), t, context[0])
+    return eng, x0, e, e0, ctx, grid
+
+
+def magcache_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
+    r"""MagCache4Wan2.1/magcache_generate.py:198-312 on the B200 kernels.
+
+    Args / returns as the reference: x List[Tensor[C_in, F, H, W]], t Tensor[B], context List[Tensor[L, C]], seq_len int
+    -> List[Tensor[C_out, F, H, W]] (float32).
+    """
+    eng, x0, e, e0, ctx, grid = _prologue(self, x, t, context, seq_len, clip_fea, y)
+    ctrl = _controller(self)
+    slot = self.cnt % 2
+    skip_forward = ctrl.decide(self)  # :279-292 (float64 state under the reference's attribute names)
+    if skip_forward:
+        residual_x = self.residual_cache[slot]
+        if residual_x is None:
+            raise TypeError("magcache_b200: cache hit with an empty residual_cache slot (reference: Tensor + NoneType)")
+        # `x = x + residual_x` feeds only the head: the sum is formed inside the head kernel (same fp32 arithmetic)
+        out = eng.head(x0, e, grid, residual=residual_x.view(x0.shape))
+    else:
+        xs = eng.run_blocks(x0, e0, ctx, grid)  # :297-298
+        prev = self.residual_cache[slot]
+        buf = prev.view(x0.shape) if (torch.is_tensor(prev) and prev.numel() == xs.numel() and prev.dtype == torch.float32
+                                      and prev.device == xs.device) else None
+        residual_x = ops.residual_sub(xs, x0, out=buf).view(1, *x0.shape)  # :299
+        out = eng.head(xs, e, grid)
+    self.residual_cache[slot] = residual_x  # :301
+    ctrl.advance(self)  # :306-311
+    return [out]
+
+
+def magcache_calibration(self, x, t, context, seq_len, clip_fea=None, y=None):
+    r"""MagCache4Wan2.1/magcache_generate.py:80-194: always runs the block stack and records, per forward, the token-mean
+    magnitude ratio, its std and the cosine distance to the previous residual of the same CFG branch (one fused pass)."""
+    eng, x0, e, e0, ctx, grid = _prologue(self, x, t, context, seq_len, clip_fea, y)
+    xs = eng.run_blocks(x0, e0, ctx, grid)
+    slot = self.cnt % 2
+    if self.cnt >= 2:
+        prev = self.residual_cache[slot].view(x0.shape)
+        residual_x, (norm_ratio, norm_std, cos_dis) = ops.residual_sub_stats(xs, x0, prev)
+        self.norm_ratio.append(round(norm_ratio, 5))
+        self.norm_std.append(round(norm_std, 5))
+        self.cos_dis.append(round(cos_dis, 5))
+        print(f"time: {self.cnt}, norm_ratio: {norm_ratio}, norm_std: {norm_std}, cos_dis: {cos_dis}")
+    else:
+        residual_x = ops.residual_sub(xs, x0)
+    self.residual_cache[slot] = residual_x.view(1, *x0.shape)
+    out = eng.head(xs, e, grid)
+    self.cnt += 1
+    if self.cnt >= self.num_steps:
+        self.cnt = 0
+        self.accumulated_ratio = [1.0, 1.0]
+        self.accumulated_err = [0.0, 0.0]
+        self.accumulated_steps = [0, 0]
+        print("norm ratio")
+        print(self.norm_ratio)
+        print("norm std")
+        print(self.norm_std)
+        print("cos_dis")
+        print(self.cos_dis)
+    return [out]
+
+
+def init_magcache(model, sample_steps, thresh=0.12, K=2, retention_ratio=0.2, mag_ratios=None, ckpt_dir=None, table=None):
+    """The installation block of magcache_generate.py:896-919 as a helper (same form as Wan2.2's `init_magcache`,
+    MagCache4Wan2.2/magcache_generate.py:340-362): patches the CLASS, like the reference."""
+    cls = model.__class__
+    cls.forward = magcache_forward
+    cls.cnt = 0
+    cls.num_steps = sample_steps * 2
+    cls.magcache_thresh = thresh
+    cls.K = K
+    cls.accumulated_err = [0.0, 0.0]
+    cls.accumulated_steps = [0, 0]
+    cls.accumulated_ratio = [1.0, 1.0]
+    cls.retention_ratio = retention_ratio
+    cls.residual_cache = [None, None]
+    if mag_ratios is None:
+        mag_ratios = tables()[table] if table is not None else table_for_ckpt_dir(ckpt_dir)
+    cls.mag_ratios = interp_cfg(mag_ratios, sample_steps)  # :915-919
+    return model
+
+
+def init_magcache_calibration(model, sample_steps):
+    """magcache_generate.py:921-928."""
+    cls = model.__class__
+    cls.forward = magcache_calibration
+    cls.cnt = 0
+    cls.num_steps = sample_steps * 2
+    cls.norm_ratio, cls.norm_std, cls.cos_dis = [], [], []
+    cls.residual_cache = [None, None]
+    return model
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Scalar-state families (FLUX, HunyuanVideo): controller + cache kernels around a caller-supplied block stack
+# ------------------------------------------------------------------------------------------------------------------
+_FLUX_CTRL = dict(branches=1, cmp=1, retention_mode=1, veto_index=11, veto_base=28)   # magcache_flux.py:327-332
+_HUNYUAN_CTRL = dict(branches=1, cmp=1, retention_mode=0, veto_index=-1, veto_base=0)  # magcache_sample_video.py:90-96
+
+
+def magcache_branch(self, hidden, run_blocks, family, cache_attr):
+    """The hit/miss branch of the FLUX / Hunyuan forwards (magcache_flux.py:326-427, magcache_sample_video.py:88-141):
+    decides with the family's controller, then either adds the cached residual (K1 kernel) or calls `run_blocks(hidden)`
+    (the model's own transformer stack) and stores `out - hidden` (K2 kernel) under `cache_attr`. Advances the counter."""
+    ctrls = self.__dict__.setdefault("_mc_ctrls", {})
+    if family not in ctrls:
+        ctrls[family] = AttrController(_FLUX_CTRL if family == "flux" else _HUNYUAN_CTRL)
+    ctrl = ctrls[family]
+    if ctrl.decide(self):
+        cur = getattr(self, cache_attr)
+        if cur is None:
+            raise TypeError("magcache_b200: cache hit with an empty residual cache (reference: Tensor + NoneType)")
+        out = ops.cache_hit_add(hidden.contiguous(), cur)
+    else:
+        out = run_blocks(hidden)
+        cur = ops.residual_sub(out.contiguous(), hidden.contiguous())
+    setattr(self, cache_attr, cur)
+    ctrl.advance(self)
+    return out

@@ -1,0 +1,299 @@
+"""Wan2.1 DiT engine: device-resident weights in the layout the sm_100a kernels want, plus the kernel sequence of one forward.
+
+This is the cache-miss branch of the reference (`for block in self.blocks: x = block(x, **kwargs)`,
+MagCache4Wan2.1/magcache_generate.py:297-298) and the prologue / epilogue around it (:229-275, :304-305), rebuilt on the
+C-ABI kernels. Block arithmetic follows upstream Wan2.1 `wan/modules/model.py` [EXT] as restated in SURVEY.md Appendix B.1.
+
+HBM layout per forward (N tokens, D model dim, F ffn dim; Wan2.1-1.3B at 832x480x81: N=32760, D=1536, F=8960):
+  x0   bf16 [N, D]     patch-embedding output (`ori_x`)            h    bf16 [N, D]    LN+modulate output (GEMM A operand)
+  xs   fp32 [N, D]     residual stream, updated in place           qk   bf16 [N, 2D]   fused q|k projection (RMSNorm+RoPE in place)
+  vt   bf16 [D, Npad]  V^T straight out of the V-projection GEMM   att  bf16 [N, D]    attention output
+  ffn  bf16 [N, F]     GELU(ffn[0]) output                         ctx  bf16 [512, D]  text embedding (+ per-layer k / v^T)
+All buffers are allocated once per engine and reused by every forward (no allocator traffic in the loop).
+"""
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+E = _lib
+
+
+@dataclass
+class WanDims:
+    dim: int = 1536
+    ffn_dim: int = 8960
+    num_heads: int = 12
+    num_layers: int = 30
+    in_dim: int = 16
+    out_dim: int = 16
+    freq_dim: int = 256
+    text_dim: int = 4096
+    text_len: int = 512
+    eps: float = 1e-6
+
+    @property
+    def head_dim(self):
+        return self.dim // self.num_heads
+
+
+WAN_CONFIGS = {
+    "t2v-1.3B": WanDims(1536, 8960, 12, 30),
+    "t2v-14B": WanDims(5120, 13824, 40, 40),
+}
+
+
+def _bf16(t, device):
+    return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _bias_autocast(t, device):
+    """Under bf16 autocast nn.Linear casts its bias to bf16 too; the epilogue adds it in fp32, so keep the rounded value as fp32."""
+    return t.detach().to(device=device, dtype=torch.bfloat16).float().contiguous()
+
+
+class WanWeights:
+    """Weights of one WanModel, repacked for the kernels. Build with `from_module` (any module exposing upstream Wan attribute
+    names: patch_embedding, text_embedding, time_embedding, time_projection, blocks[i].{norm3,self_attn,cross_attn,ffn,modulation},
+    head.{head,modulation}) or `random` (seeded synthetic weights created directly on the device)."""
+
+    def __init__(self, dims: WanDims, device):
+        self.dims, self.device = dims, device
+        self.blocks = []
+
+    @classmethod
+    def from_module(cls, m, device):
+        D = m.dim
+        dims = WanDims(dim=D, ffn_dim=m.ffn_dim, num_heads=m.num_heads, num_layers=len(m.blocks), in_dim=m.patch_embedding.in_channels,
+                       out_dim=m.out_dim, freq_dim=m.freq_dim, text_dim=m.text_embedding[0].in_features, text_len=m.text_len,
+                       eps=getattr(m, "eps", 1e-6))
+        if dims.head_dim != 128:
+            raise NotImplementedError(f"head_dim {dims.head_dim}: the attention kernel is built for head_dim 128 (Wan2.1 1.3B and 14B)")
+        assert tuple(m.patch_embedding.kernel_size) == (1, 2, 2), "patch size (1,2,2) only"
+        w = cls(dims, device)
+        pe = m.patch_embedding
+        w.patch_w = _bf16(pe.weight.flatten(1), device)            # [D, C*4] in (c, kt, kh, kw) order
+        w.patch_b = _bias_autocast(pe.bias, device)
+        te = m.text_embedding
+        w.text_w1, w.text_b1 = _bf16(te[0].weight, device), _bias_autocast(te[0].bias, device)
+        w.text_w2, w.text_b2 = _bf16(te[2].weight, device), _bias_autocast(te[2].bias, device)
+        tm = m.time_embedding
+        w.time_w1, w.time_b1 = _f32(tm[0].weight, device), _f32(tm[0].bias, device)
+        w.time_w2, w.time_b2 = _f32(tm[2].weight, device), _f32(tm[2].bias, device)
+        tp = m.time_projection[1]
+        w.tproj_w, w.tproj_b = _f32(tp.weight, device), _f32(tp.bias, device)
+        for blk in m.blocks:
+            sa, ca = blk.self_attn, blk.cross_attn
+            b = {
+                "mod": _f32(blk.modulation.reshape(6, D), device),
+                "w_qk": _bf16(torch.cat([sa.q.weight, sa.k.weight], 0), device),
+                "b_qk": _bias_autocast(torch.cat([sa.q.bias, sa.k.bias], 0), device),
+                "w_v": _bf16(sa.v.weight, device), "b_v": _bias_autocast(sa.v.bias, device),
+                "w_o": _bf16(sa.o.weight, device), "b_o": _bias_autocast(sa.o.bias, device),
+                "nq": _f32(sa.norm_q.weight, device), "nk": _f32(sa.norm_k.weight, device),
+                "n3_w": _f32(blk.norm3.weight, device), "n3_b": _f32(blk.norm3.bias, device),
+                "c_wq": _bf16(ca.q.weight, device), "c_bq": _bias_autocast(ca.q.bias, device),
+                "c_wk": _bf16(ca.k.weight, device), "c_bk": _bias_autocast(ca.k.bias, device),
+                "c_wv": _bf16(ca.v.weight, device), "c_bv": _bias_autocast(ca.v.bias, device),
+                "c_wo": _bf16(ca.o.weight, device), "c_bo": _bias_autocast(ca.o.bias, device),
+                "c_nq": _f32(ca.norm_q.weight, device), "c_nk": _f32(ca.norm_k.weight, device),
+                "w_f1": _bf16(blk.ffn[0].weight, device), "b_f1": _bias_autocast(blk.ffn[0].bias, device),
+                "w_f2": _bf16(blk.ffn[2].weight, device), "b_f2": _bias_autocast(blk.ffn[2].bias, device),
+            }
+            w.blocks.append(b)
+        w.head_mod = _f32(m.head.modulation.reshape(2, D), device)
+        w.head_wt = _f32(m.head.head.weight.t(), device)           # [D, 64]: transposed for the head kernel's K-chunk staging
+        w.head_b = _f32(m.head.head.bias, device)
+        return w
+
+    @classmethod
+    def random(cls, dims: WanDims, device, seed=0):
+        """Seeded synthetic weights with upstream's init scales (xavier-uniform Linears, N(0, 0.02) embeddings) but non-zero
+        biases / head so every term is exercised. Created on the device: a 1.3B model is 2.8 GB in bf16."""
+        g = torch.Generator(device=device).manual_seed(seed)
+        D, F = dims.dim, dims.ffn_dim
+        w = cls(dims, device)
+
+        def xav(o, i):
+            a = math.sqrt(6.0 / (i + o))
+            return ((torch.rand(o, i, device=device, generator=g) * 2 - 1) * a)
+
+        def small(*shape):
+            return 0.02 * torch.randn(*shape, device=device, generator=g)
+
+        def bias(n):
+            return small(n).bfloat16().float()
+
+        w.patch_w, w.patch_b = xav(D, dims.in_dim * 4).bfloat16(), bias(D)
+        w.text_w1, w.text_b1 = small(D, dims.text_dim).bfloat16(), bias(D)
+        w.text_w2, w.text_b2 = small(D, D).bfloat16(), bias(D)
+        w.time_w1, w.time_b1 = small(D, dims.freq_dim), small(D)
+        w.time_w2, w.time_b2 = small(D, D), small(D)
+        w.tproj_w, w.tproj_b = small(6 * D, D), small(6 * D)
+        for _ in range(dims.num_layers):
+            w.blocks.append({
+                "mod": torch.randn(6, D, device=device, generator=g) / math.sqrt(D),
+                "w_qk": torch.cat([xav(D, D), xav(D, D)], 0).bfloat16(), "b_qk": bias(2 * D),
+                "w_v": xav(D, D).bfloat16(), "b_v": bias(D), "w_o": xav(D, D).bfloat16(), "b_o": bias(D),
+                "nq": 1 + 0.1 * torch.randn(D, device=device, generator=g), "nk": 1 + 0.1 * torch.randn(D, device=device, generator=g),
+                "n3_w": 1 + 0.1 * torch.randn(D, device=device, generator=g), "n3_b": small(D),
+                "c_wq": xav(D, D).bfloat16(), "c_bq": bias(D), "c_wk": xav(D, D).bfloat16(), "c_bk": bias(D),
+                "c_wv": xav(D, D).bfloat16(), "c_bv": bias(D), "c_wo": xav(D, D).bfloat16(), "c_bo": bias(D),
+                "c_nq": 1 + 0.1 * torch.randn(D, device=device, generator=g), "c_nk": 1 + 0.1 * torch.randn(D, device=device, generator=g),
+                "w_f1": xav(F, D).bfloat16(), "b_f1": bias(F), "w_f2": xav(D, F).bfloat16(), "b_f2": bias(D),
+            })
+        w.head_mod = torch.randn(2, D, device=device, generator=g) / math.sqrt(D)
+        w.head_wt = small(D, 4 * dims.out_dim).contiguous()
+        w.head_b = small(4 * dims.out_dim)
+        return w
+
+
+def rope_table(grid, head_dim, device):
+    """cos/sin of the 3-axis rotary embedding for every token of an (f, h, w) grid, computed in float64 exactly as upstream
+    `rope_params` + `rope_apply` build them (theta 10000, split c-2(c//3) | c//3 | c//3 with c = head_dim/2), stored fp32
+    [f*h*w, head_dim] as interleaved (cos, sin) pairs."""
+    f, h, w = grid
+    c = head_dim // 2
+    split = [c - 2 * (c // 3), c // 3, c // 3]
+    dims = [head_dim - 4 * (head_dim // 6), 2 * (head_dim // 6), 2 * (head_dim // 6)]
+    angs = []
+    for n, d, s in zip((f, h, w), dims, split):
+        inv = 1.0 / np.power(10000.0, np.arange(0, d, 2, dtype=np.float64) / d)
+        assert len(inv) == s
+        angs.append(np.outer(np.arange(n, dtype=np.float64), inv))
+    ang = np.concatenate([np.broadcast_to(angs[0][:, None, None, :], (f, h, w, split[0])),
+                          np.broadcast_to(angs[1][None, :, None, :], (f, h, w, split[1])),
+                          np.broadcast_to(angs[2][None, None, :, :], (f, h, w, split[2]))], axis=-1).reshape(f * h * w, c)
+    cs = np.stack([np.cos(ang), np.sin(ang)], axis=-1).reshape(f * h * w, head_dim)
+    return torch.from_numpy(cs.astype(np.float32)).to(device)
+
+
+class WanEngine:
+    """Runs prologue / block stack / head of one Wan forward on the kernels. One engine per (weights, token count)."""
+
+    def __init__(self, weights: WanWeights):
+        self.w = weights
+        self.dims = weights.dims
+        self.device = weights.device
+        self._n = None
+        self._rope = {}
+
+    # ------------------------------------------------------------------------------------------ workspace
+    def _workspace(self, n):
+        if self._n == n:
+            return
+        d, dev = self.dims, self.device
+        D, F = d.dim, d.ffn_dim
+        self.npad = (n + 7) // 8 * 8
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.x0 = torch.empty(n, D, **bf)
+        self.xs = torch.empty(n, D, dtype=torch.float32, device=dev)
+        self.h = torch.empty(n, D, **bf)
+        self.qk = torch.empty(n, 2 * D, **bf)
+        self.vt = torch.zeros(D, self.npad, **bf)
+        self.att = torch.empty(n, D, **bf)
+        self.ffn = torch.empty(n, F, **bf)
+        self.cq = torch.empty(n, D, **bf)
+        self.ck = torch.empty(d.text_len, D, **bf)
+        self.cvt = torch.empty(D, d.text_len, **bf)
+        self.ctx_in = torch.zeros(d.text_len, d.text_dim, **bf)
+        self.ctx_h = torch.empty(d.text_len, D, **bf)
+        self.ctx = torch.empty(d.text_len, D, **bf)
+        self.em = torch.empty(6, D, dtype=torch.float32, device=dev)
+        self._n = n
+
+    def _rope_for(self, grid):
+        if grid not in self._rope:
+            self._rope[grid] = rope_table(grid, self.dims.head_dim, self.device)
+        return self._rope[grid]
+
+    # ------------------------------------------------------------------------------------------ prologue (:229-275)
+    def prologue(self, latent, t, context):
+        """latent fp32 [C, F, H, W]; t tensor [1]; context [L<=512, text_dim]. Returns (x0 bf16 [N, D], e fp32 [1, D], e0 fp32 [6, D],
+        ctx bf16 [512, D], grid)."""
+        d, w = self.dims, self.w
+        C, Fr, H, W = latent.shape
+        grid = (Fr, H // 2, W // 2)
+        n = grid[0] * grid[1] * grid[2]
+        self._workspace(n)
+        tok = ops.patchify(latent.contiguous())
+        ops.gemm(tok, w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
+        sin = ops.time_sinusoid(t.reshape(-1)[:1], d.freq_dim)
+        e = ops.linear_f32_small(ops.linear_f32_small(sin, w.time_w1, w.time_b1, act=2), w.time_w2, w.time_b2, act=0)
+        e0 = ops.linear_f32_small(e, w.tproj_w, w.tproj_b, act=1).view(6, d.dim)
+        L = context.shape[0]
+        assert L <= d.text_len and context.shape[1] == d.text_dim
+        self.ctx_in.zero_()
+        self.ctx_in[:L].copy_(context)  # pad to text_len with zeros; autocast casts the Linear input to bf16
+        ops.gemm(self.ctx_in, w.text_w1, w.text_b1, E.MC_EPI_BIAS_GELU_BF16, out=self.ctx_h)
+        ops.gemm(self.ctx_h, w.text_w2, w.text_b2, E.MC_EPI_BIAS_BF16, out=self.ctx)
+        return self.x0, e, e0, self.ctx, grid
+
+    # ------------------------------------------------------------------------------------------ block stack (:297-298)
+    def run_blocks(self, x0, e0, ctx, grid):
+        """30 (1.3B) / 40 (14B) WanAttentionBlocks. Returns the fp32 residual stream [N, D] (engine-owned buffer)."""
+        d, H = self.dims, self.dims.num_heads
+        D = d.dim
+        n = x0.shape[0]
+        xs = self.xs
+        ops.cast_into(x0, xs)  # block 0 sees the bf16 patch embedding; every later op works on the fp32 stream
+        rope = self._rope_for(grid)
+        q, k = self.qk[:, :D], self.qk[:, D:]
+        vt = self.vt[:, :n]
+        for li, b in enumerate(self.w.blocks):
+            ops.cache_hit_add(b["mod"], e0, out=self.em)  # e = modulation + e0 (fp32)
+            # --- self attention
+            ops.ln_modulate(xs, self.em, 1, 0, eps=d.eps, round_ln_to_bf16=(li == 0), out=self.h)
+            ops.gemm(self.h, b["w_qk"], b["b_qk"], E.MC_EPI_BIAS_BF16, out=self.qk, tag="gemm_qk")
+            ops.gemm(b["w_v"], self.h, b["b_v"], E.MC_EPI_ROWBIAS_BF16, out=vt)
+            ops.rmsnorm_rope_(q, b["nq"], rope, d.head_dim, eps=d.eps)
+            ops.rmsnorm_rope_(k, b["nk"], rope, d.head_dim, eps=d.eps)
+            ops.attention(q, k, vt, H, out=self.att, tag="attn_self")
+            ops.gemm(self.att, b["w_o"], b["b_o"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[2])
+            # --- cross attention (text)
+            ops.ln_affine(xs, b["n3_w"], b["n3_b"], eps=d.eps, out=self.h)
+            ops.gemm(self.h, b["c_wq"], b["c_bq"], E.MC_EPI_BIAS_BF16, out=self.cq)
+            ops.rmsnorm_rope_(self.cq, b["c_nq"], None, d.head_dim, eps=d.eps)
+            ops.gemm(ctx, b["c_wk"], b["c_bk"], E.MC_EPI_BIAS_BF16, out=self.ck)
+            ops.rmsnorm_rope_(self.ck, b["c_nk"], None, d.head_dim, eps=d.eps)
+            ops.gemm(b["c_wv"], ctx, b["c_bv"], E.MC_EPI_ROWBIAS_BF16, out=self.cvt)
+            ops.attention(self.cq, self.ck, self.cvt, H, out=self.att, tag="attn_cross")
+            ops.gemm(self.att, b["c_wo"], b["c_bo"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=None)
+            # --- FFN
+            ops.ln_modulate(xs, self.em, 4, 3, eps=d.eps, out=self.h)
+            ops.gemm(self.h, b["w_f1"], b["b_f1"], E.MC_EPI_BIAS_GELU_BF16, out=self.ffn, tag="gemm_ffn1")
+            ops.gemm(self.ffn, b["w_f2"], b["b_f2"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[5], tag="gemm_ffn2")
+        return xs
+
+    # ------------------------------------------------------------------------------------------ epilogue (:304-305)
+    def head(self, x, e, grid, residual=None):
+        w = self.w
+        return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps,
+                                   tag="head_hit_fused" if residual is not None else "head")
+
+
+class WanModelHandle:
+    """Minimal stand-in for `wan.modules.model.WanModel` when the weights do not come from an nn.Module (bench.py, tests):
+    carries the engine and receives the reference's class attributes (`cnt`, `mag_ratios`, ...) through `init_magcache`.
+    Each handle is its own class so two pipelines in one process do not share controller state (race note)."""
+
+    model_type = "t2v"
+
+    def __new__(cls, weights: WanWeights):
+        sub = type("WanModelHandle", (cls,), {})
+        self = object.__new__(sub)
+        return self
+
+    def __init__(self, weights: WanWeights):
+        self.dim, self.num_heads = weights.dims.dim, weights.dims.num_heads
+        self._mc_engine = WanEngine(weights)
+
+    def __call__(self, *args, **kwargs):
+        return self.forward(*args, **kwargs)

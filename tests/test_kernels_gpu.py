@@ -130,7 +130,9 @@ def test_ln_modulate(rows, cols, xdt):
     mod = torch.randn(6, cols, device=DEV) / math.sqrt(cols)
     e = torch.randn(6, cols, device=DEV) * 0.2
     round_ln = xdt == torch.bfloat16
-    out32 = ops.ln_modulate(x, mod, e, 1, 0, round_ln_to_bf16=round_ln, out_dtype=torch.float32)
+    em = ops.cache_hit_add(mod, e)  # e = modulation + e0 (fp32), as the engine forms it once per layer
+    assert torch.equal(em, mod + e)
+    out32 = ops.ln_modulate(x, em, 1, 0, round_ln_to_bf16=round_ln, out_dtype=torch.float32)
     ln = torch.nn.functional.layer_norm(x.float(), (cols,), eps=1e-6)
     if round_ln:
         ln = ln.to(xdt).float()
@@ -143,7 +145,7 @@ def test_ln_modulate(rows, cols, xdt):
         assert ((out32 - ref).abs() > 1e-4 + 1e-3 * ref.abs()).float().mean() < 0.01
     else:
         assert torch.allclose(out32, ref, rtol=1e-3, atol=1e-4)
-    out16 = ops.ln_modulate(x, mod, e, 1, 0, round_ln_to_bf16=round_ln)
+    out16 = ops.ln_modulate(x, em, 1, 0, round_ln_to_bf16=round_ln)
     assert torch.equal(out16, out32.bfloat16())
 
 

@@ -1,0 +1,175 @@
+"""End-to-end parity of the B200 path (called exactly as the reference calls it: `model.forward = magcache_forward` + class
+attributes) against the CPU oracle restatement of MagCache4Wan2.1/magcache_generate.py:198-312 on identical synthetic latents,
+timesteps, text embeddings and weights.
+
+Tolerances. The skip mask / controller state: bit-exact. Tensors: both implementations run bf16 GEMMs with fp32 accumulation
+but sum in different orders (MKL/oneDNN vs tcgen05), so individual bf16 roundings flip by one ulp and the difference grows
+with depth; an element-wise rtol 1e-3 is not meaningful for a bf16 pipeline. We therefore check (a) relative L2 error of our
+output against the oracle <= 2e-2, and (b) the north-star criterion in the only form that is well defined: our error against
+an fp64 evaluation of the same network is no larger than 1.5x the bf16 oracle's own error against it (+1e-4 absolute).
+"""
+import copy
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def build(cfg_name, seed=0):
+    from oracle import wan_ref
+    model = wan_ref.WanModel(**wan_ref.CONFIGS[cfg_name], text_dim=512, text_len=64).init_synthetic(seed)
+    return wan_ref, model
+
+
+def make_inputs(seed, grid=(3, 16, 24), text_dim=512, L=37):
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn(16, *grid, generator=g)
+    ctx = torch.randn(L, text_dim, generator=g)
+    ctx_null = torch.randn(L - 5, text_dim, generator=g)
+    return lat, ctx, ctx_null
+
+
+def install_ref(wan_ref, model, steps, **kw):
+    cls = type("RefWan", (model.__class__,), {})  # private subclass: class-level state does not leak between tests
+    model.__class__ = cls
+    from magcache_b200 import tables
+    wan_ref.install_magcache(cls, tables()["wan2.1_t2v_1.3b"], steps, **kw)
+    return model
+
+
+def install_ours(model_gpu, steps, **kw):
+    import magcache_b200 as mc
+    cls = type("OurWan", (model_gpu.__class__,), {})
+    model_gpu.__class__ = cls
+    mc.init_magcache(model_gpu, steps, table="wan2.1_t2v_1.3b", **kw)
+    return model_gpu
+
+
+@pytest.mark.parametrize("cfg_name", ["tiny", "small"])
+def test_single_forward_vs_oracle_and_fp64(cfg_name):
+    wan_ref, model = build(cfg_name)
+    lat, ctx, _ = make_inputs(1)
+    n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
+    t = torch.tensor([731.0])
+    ref_model = install_ref(wan_ref, copy.deepcopy(model), 10)
+    with torch.no_grad():
+        ref = ref_model([lat], t=t, context=[ctx], seq_len=n_tok)[0]
+        # fp64 evaluation of the same network (no bf16 rounding anywhere)
+        m64 = install_ref(wan_ref, copy.deepcopy(model).double(), 10)
+        with wan_ref.exact_fp64():
+            exact = m64([lat.double()], t=t, context=[ctx.double()], seq_len=n_tok)[0]
+    ours_model = install_ours(copy.deepcopy(model).to(DEV), 10)
+    out = ours_model([lat.to(DEV)], t=t.to(DEV), context=[ctx.to(DEV)], seq_len=n_tok)[0].cpu()
+    assert out.shape == ref.shape == (16, *lat.shape[1:]) and out.dtype == torch.float32
+    e_ours, e_ref, e_vs = rel_l2(out, exact), rel_l2(ref, exact), rel_l2(out, ref)
+    print(f"[{cfg_name}] rel-L2: ours vs fp64 {e_ours:.3e} | oracle(bf16) vs fp64 {e_ref:.3e} | ours vs oracle {e_vs:.3e}")
+    assert e_vs <= 2e-2
+    assert e_ours <= 1.5 * e_ref + 1e-4
+
+
+def test_magcache_loop_mask_cache_and_outputs():
+    """20 forward calls (10 steps x cond/uncond) through the patched forward on both sides, same inputs every call.
+    Checks: identical skip decisions (bit-exact), controller attributes, residual-cache contents, per-call outputs."""
+    wan_ref, model = build("tiny")
+    steps = 10
+    kw = dict(thresh=0.12, K=2, retention_ratio=0.2)
+    ref_model = install_ref(wan_ref, copy.deepcopy(model), steps, **kw)
+    ours_model = install_ours(copy.deepcopy(model).to(DEV), steps, **kw)
+    assert np.array_equal(type(ref_model).mag_ratios, type(ours_model).mag_ratios)
+    lat, ctx, ctx_null = make_inputs(2)
+    n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
+    sig = wan_ref.flow_sigmas(steps)
+    skips_ref, skips_ours = [], []
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for i in range(steps):
+            t = torch.tensor([float(sig[i] * 1000)])
+            x = lat + 0.1 * i * torch.randn(lat.shape, generator=g)  # a new latent every step, identical on both sides
+            for c in (ctx, ctx_null):
+                cnt_before = type(ours_model).cnt
+                ref = ref_model([x], t=t, context=[c], seq_len=n_tok)[0]
+                out = ours_model([x.to(DEV)], t=t.to(DEV), context=[c.to(DEV)], seq_len=n_tok)[0].cpu()
+                skips_ref.append(int(ref_model.last_skip))
+                slot = cnt_before % 2
+                r_ours = ours_model.residual_cache[slot]
+                r_ref = ref_model.residual_cache[slot]
+                assert r_ours.shape == r_ref.shape and r_ours.dtype == torch.float32
+                assert rel_l2(r_ours.cpu(), r_ref) <= 3e-2, (i, rel_l2(r_ours.cpu(), r_ref))
+                assert rel_l2(out, ref) <= 2e-2, (i, rel_l2(out, ref))
+                for attr in ("cnt", "accumulated_ratio", "accumulated_err", "accumulated_steps"):
+                    assert getattr(ours_model, attr) == getattr(ref_model, attr), attr  # float64 state, bit-exact
+    from magcache_b200.controller import make_ctrl_config, schedule_mask
+    from magcache_b200.config import MagCacheConfig
+    cfg = MagCacheConfig("wan2.1", sample_steps=steps, table="wan2.1_t2v_1.3b", **{"thresh": 0.12, "K": 2, "retention_ratio": 0.2})
+    mask = schedule_mask(make_ctrl_config(cfg.num_steps, cfg.thresh, cfg.K, cfg.retention_ratio, cfg.resolved_ratios(), **cfg.ctrl_kwargs()), 2 * steps)
+    assert mask.tolist() == skips_ref and sum(skips_ref) > 0
+    assert type(ours_model).cnt == 0  # wrapped around after num_steps calls
+
+
+def test_calibration_matches_oracle():
+    wan_ref, model = build("tiny")
+    steps = 3
+    ref_model = copy.deepcopy(model)
+    ref_cls = type("RefCal", (ref_model.__class__,), {})
+    ref_model.__class__ = ref_cls
+    wan_ref.install_magcache(ref_cls, None, steps, calibration=True)
+    import magcache_b200 as mc
+    ours = copy.deepcopy(model).to(DEV)
+    ours.__class__ = type("OurCal", (ours.__class__,), {})
+    mc.init_magcache_calibration(ours, steps)
+    lat, ctx, ctx_null = make_inputs(3)
+    n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
+    sig = wan_ref.flow_sigmas(steps)
+    with torch.no_grad():
+        for i in range(steps):
+            t = torch.tensor([float(sig[i] * 1000)])
+            x = lat * (1 - 0.2 * i)
+            for c in (ctx, ctx_null):
+                ref_model([x], t=t, context=[c], seq_len=n_tok)
+                ours([x.to(DEV)], t=t.to(DEV), context=[c.to(DEV)], seq_len=n_tok)
+    assert len(ours.norm_ratio) == len(ref_model.norm_ratio) == 2 * steps - 2
+    # the statistics are functions of two bf16-pipeline residuals: agreement to ~1e-2 relative is the noise floor
+    for a, b in zip(ours.norm_ratio, ref_model.norm_ratio):
+        assert abs(a - b) <= 2e-2 * abs(b), (ours.norm_ratio, ref_model.norm_ratio)
+    for a, b in zip(ours.cos_dis, ref_model.cos_dis):
+        assert abs(a - b) <= 2e-2 + 0.2 * abs(b), (ours.cos_dis, ref_model.cos_dis)
+
+
+def test_scalar_family_branch_flux_and_hunyuan():
+    """BASELINE config 1 plumbing (FLUX, scalar controller with the step-11 veto) and the Hunyuan variant: controller + K1/K2
+    kernels around a stand-in block stack, checked call by call against the oracle controller and torch arithmetic."""
+    import types as _t
+    from magcache_b200 import PRESETS, magcache_branch
+    from oracle.controller_ref import ControllerRef
+    for preset, fam, attr in [("flux-E024K5R01", "flux", "previous_residual"), ("hunyuan-720p-E024K6R02", "hunyuan", "residual_cache")]:
+        cfg = PRESETS[preset]
+        ratios = cfg.resolved_ratios()
+        cls = type("Fake", (), {})
+        m = cls()
+        cls.cnt, cls.num_steps, cls.magcache_thresh, cls.K, cls.retention_ratio = 0, cfg.num_steps, cfg.thresh, cfg.K, cfg.retention_ratio
+        cls.accumulated_ratio, cls.accumulated_err, cls.accumulated_steps, cls.mag_ratios = 1, 0, 0, ratios
+        setattr(cls, attr, None)
+        ref_ctl = ControllerRef(fam, ratios, cfg.num_steps, cfg.thresh, cfg.K, cfg.retention_ratio)
+        g = torch.Generator(device=DEV).manual_seed(0)
+        cache_ref = None
+        for i in range(cfg.num_steps + 3):
+            h = torch.randn(1, 4096, 3072 if fam == "flux" else 256, device=DEV, generator=g).bfloat16()
+            blocks = lambda z: (z.float() * 1.01 + 0.003 * (i + 1)).bfloat16()  # noqa: E731
+            out = magcache_branch(m, h, blocks, fam, attr)
+            skip = ref_ctl.step()
+            if skip:
+                exp = h + cache_ref
+            else:
+                exp = blocks(h)
+                cache_ref = exp - h
+            assert torch.equal(out, exp), (preset, i)
+            assert torch.equal(getattr(m, attr), cache_ref)
+            assert m.cnt == ref_ctl.cnt

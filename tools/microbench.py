@@ -65,7 +65,7 @@ if which in ("all", "rows"):
     xs = torch.randn(N_TOK, D, device=dev)
     mod, e = torch.randn(6, D, device=dev) * 0.03, torch.randn(6, D, device=dev) * 0.2
     h = torch.empty(N_TOK, D, dtype=torch.bfloat16, device=dev)
-    rec("ln_modulate", *timeit(lambda: ops.ln_modulate(xs, mod, e, 1, 0, out=h)), bytes_=n * 6)
+    rec("ln_modulate", *timeit(lambda: ops.ln_modulate(xs, mod, 1, 0, out=h)), bytes_=n * 6)
     qk = torch.randn(N_TOK, D, device=dev).bfloat16()
     w = torch.ones(D, device=dev)
     cs = torch.randn(N_TOK, 128, device=dev)
