@@ -3,23 +3,29 @@
 // (`for block in self.blocks: x = block(x, **kwargs)`, MagCache4Wan2.1/magcache_generate.py:297-298; patch_embedding :237;
 // text_embedding :257-262), with the reference's elementwise follow-ups fused into the epilogue.
 //
-// Tile: 128 (M) x 128 (N) x 64 (K) per pipeline stage, one output tile per CTA, two CTAs co-resident per SM so one CTA's
-// epilogue overlaps the other's main loop. Warp roles (192 threads):
-//   warp 0   TMA producer  : cp.async.bulk.tensor 2-D loads of A and B tiles (128-byte swizzle) into a 3-stage smem ring
-//   warp 1   MMA issuer    : one thread issues tcgen05.mma (M128 N128 K16) x4 per stage; tcgen05.commit frees the stage
-//   warps 2-5 epilogue     : tcgen05.ld the 128x128 fp32 accumulator (lane = row), apply the epilogue, store to global
+// Persistent kernel, one CTA per SM, tile 128 (M) x 256 (N) x 64 (K per stage):
+//   warp 0     TMA producer : A tile (128x64) + B tile (256x64) per stage, 128-byte swizzle, 4-stage smem ring (192 KB)
+//   warp 1     MMA issuer   : tcgen05.mma M128 N256 K16 x4 per stage into one of TWO 256-column TMEM accumulators
+//   warps 2-5  epilogue     : drain accumulator t&1 while the MMA warp fills the other one. tcgen05.ld (lane = row) ->
+//                             per-warp smem transpose -> lane = column, so every global access is a coalesced row segment
+// Tiles are walked in waves of gridDim.x consecutive tiles with N fastest: the CTAs of one wave share A row-panels in L2.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
 
 namespace mc {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3;
+constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 4;
 constexpr int kTileABytes = kBM * kBK * 2;  // 16 KB
-constexpr int kTileBBytes = kBN * kBK * 2;  // 16 KB
+constexpr int kTileBBytes = kBN * kBK * 2;  // 32 KB
 constexpr int kStageBytes = kTileABytes + kTileBBytes;
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 128 /* barriers */;
+constexpr int kStagePad = 33;                                 // floats per staged row (conflict-free transpose)
+constexpr int kStagingBytes = 4 * 32 * kStagePad * 4;         // one 32x32 fp32 patch per epilogue warp
+constexpr int kOffStaging = kStages * kStageBytes;            // 196608
+constexpr int kOffBars = kOffStaging + kStagingBytes;         // + 16896
+constexpr int kGemmSmem = kOffBars + 128;
 constexpr int kGemmThreads = 192;
+constexpr int kTmemCols = 512;  // 2 accumulators x 256 fp32 columns
 
 struct GemmParams {
   int M, N, K;
@@ -29,121 +35,114 @@ struct GemmParams {
   const float* gate;
 };
 
+// One 32-row x 32-column patch: `stage` holds acc[r][c] at stage[r*33 + c]; lane = column. All global accesses below
+// touch 128 (fp32) or 64 (bf16, two rows per instruction) contiguous bytes per row.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32]) {
-  // `row` is in range; columns col0 .. col0+31 may run past N.
-  const int ncols = min(32, p.N - col0);
-  if (ncols <= 0) return;
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+__device__ __forceinline__ void epilogue_patch(const GemmParams& p, const float* stage, int row0, int col0, int lane) {
+  const int rows = min(32, p.M - row0);
+  if (rows <= 0) return;
+  const int col = col0 + lane;
+  const bool col_ok = col < p.N;
 
-  if (EPI == MC_EPI_ROWBIAS_BF16) {
-    const float b = p.bias ? p.bias[row] : 0.f;
+  if (EPI == MC_EPI_BIAS_GATE_RESID) {
+    // x[m,n] = x[m,n] + float(bf16(acc + bias[n])) * gate[n]   (`x = x + y * e[2]`: y is the bf16 Linear output, fp32 stream)
+    const float b = (p.bias && col_ok) ? p.bias[col] : 0.f;
+    const float g = (p.gate && col_ok) ? p.gate[col] : 1.f;
+    float* xcol = static_cast<float*>(p.out) + static_cast<int64_t>(row0) * p.ldo + col;
+    float xv[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += b;
-  } else {
-    if (p.bias) {
-      if (ncols == 32) {
+    for (int r = 0; r < 32; ++r) xv[r] = (col_ok && r < rows) ? xcol[static_cast<int64_t>(r) * p.ldo] : 0.f;  // 32 loads in flight
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
-      } else {
-        for (int j = 0; j < ncols; ++j) v[j] += p.bias[col0 + j];
-      }
+    for (int r = 0; r < 32; ++r) {
+      const float y = round_bf16(stage[r * kStagePad + lane] + b);
+      xv[r] = __fadd_rn(xv[r], __fmul_rn(y, g));
     }
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+      if (col_ok && r < rows) xcol[static_cast<int64_t>(r) * p.ldo] = xv[r];
+    return;
   }
 
   if (EPI == MC_EPI_BIAS_F32) {
-    float* o = static_cast<float*>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
-    if (ncols == 32 && (p.ldo & 3) == 0) {
+    const float b = (p.bias && col_ok) ? p.bias[col] : 0.f;
+    float* ocol = static_cast<float*>(p.out) + static_cast<int64_t>(row0) * p.ldo + col;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-      for (int j = 0; j < ncols; ++j) o[j] = v[j];
-    }
+    for (int r = 0; r < 32; ++r)
+      if (col_ok && r < rows) ocol[static_cast<int64_t>(r) * p.ldo] = stage[r * kStagePad + lane] + b;
     return;
   }
 
-  if (EPI == MC_EPI_BIAS_GATE_RESID) {
-    // x[m,n] = x[m,n] + float(bf16(acc + bias)) * gate[n]     (`x = x + y * e[2]` in fp32, y is the bf16 Linear output)
-    float* o = static_cast<float*>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
-    if (ncols == 32 && (p.ldo & 3) == 0) {
+  // bf16 outputs: each instruction writes two rows x 16 column pairs (lane -> row parity = lane/16, column pair = lane%16)
+  const int half = lane >> 4, cp = (lane & 15) * 2;
+  const int c0 = col0 + cp;
+  float b0 = 0.f, b1 = 0.f;
+  if (EPI != MC_EPI_ROWBIAS_BF16 && p.bias) {
+    if (c0 < p.N) b0 = p.bias[c0];
+    if (c0 + 1 < p.N) b1 = p.bias[c0 + 1];
+  }
+  __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.out);
+  const bool pair_ok = (c0 + 1 < p.N) && ((p.ldo & 1) == 0);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 x = *reinterpret_cast<const float4*>(o + j);
-        float g0 = 1.f, g1 = 1.f, g2 = 1.f, g3 = 1.f;
-        if (p.gate) {
-          const float4 g = *reinterpret_cast<const float4*>(p.gate + col0 + j);
-          g0 = g.x; g1 = g.y; g2 = g.z; g3 = g.w;
-        }
-        x.x = __fadd_rn(x.x, __fmul_rn(round_bf16(v[j]), g0));
-        x.y = __fadd_rn(x.y, __fmul_rn(round_bf16(v[j + 1]), g1));
-        x.z = __fadd_rn(x.z, __fmul_rn(round_bf16(v[j + 2]), g2));
-        x.w = __fadd_rn(x.w, __fmul_rn(round_bf16(v[j + 3]), g3));
-        *reinterpret_cast<float4*>(o + j) = x;
-      }
+  for (int rr = 0; rr < 32; rr += 2) {
+    const int r = rr + half;
+    if (r >= rows) continue;
+    float v0 = stage[r * kStagePad + cp], v1 = stage[r * kStagePad + cp + 1];
+    if (EPI == MC_EPI_ROWBIAS_BF16) {
+      const float rb = p.bias ? p.bias[row0 + r] : 0.f;  // V^T = Wv h^T + bv: bias indexed by the output ROW
+      v0 += rb;
+      v1 += rb;
     } else {
-      for (int j = 0; j < ncols; ++j) {
-        const float g = p.gate ? p.gate[col0 + j] : 1.f;
-        o[j] = __fadd_rn(o[j], __fmul_rn(round_bf16(v[j]), g));
-      }
+      v0 += b0;
+      v1 += b1;
     }
-    return;
-  }
-
-  // bf16 outputs
-  if (EPI == MC_EPI_BIAS_GELU_BF16) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(round_bf16(v[j]));  // Linear output is bf16 before nn.GELU sees it
-  }
-  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row) * p.ldo + col0;
-  if (ncols == 32 && (p.ldo & 7) == 0) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 w;
-      w.x = pack_bf16x2(v[j], v[j + 1]);
-      w.y = pack_bf16x2(v[j + 2], v[j + 3]);
-      w.z = pack_bf16x2(v[j + 4], v[j + 5]);
-      w.w = pack_bf16x2(v[j + 6], v[j + 7]);
-      *reinterpret_cast<uint4*>(o + j) = w;
+    if (EPI == MC_EPI_BIAS_GELU_BF16) {  // the Linear output is bf16 before nn.GELU(tanh) sees it
+      v0 = gelu_tanh(round_bf16(v0));
+      v1 = gelu_tanh(round_bf16(v1));
     }
-  } else {
-    for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    __nv_bfloat16* o = obase + static_cast<int64_t>(row0 + r) * p.ldo + c0;
+    if (pair_ok) {
+      *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
+    } else {
+      if (c0 < p.N) o[0] = __float2bfloat16_rn(v0);
+      if (c0 + 1 < p.N) o[1] = __float2bfloat16_rn(v1);
+    }
   }
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 2)
+__global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // 128B-swizzled tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* staging = reinterpret_cast<float*>(smem + kOffStaging);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* acc_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* acc_full = empty_bar + kStages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // N tiles vary fastest so the CTAs that share an A row-panel run together (A panel stays in L2; B is small)
-  const int n_tiles = (p.N + kBN - 1) / kBN;
-  const int m0 = (blockIdx.x / n_tiles) * kBM;
-  const int n0 = (blockIdx.x % n_tiles) * kBN;
+  const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + kBN - 1) / kBN;
+  const int total_tiles = m_tiles * n_tiles;
   const int num_kb = (p.K + kBK - 1) / kBK;
 
-  if (warp == 0 && lane == 0) {
+  if (threadIdx.x == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) {
+      printf("gemm_bf16_kernel: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(acc_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full[a], 1);
+      ptx::mbar_init(&acc_empty[a], 128);
+    }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, kBN);  // 128 fp32 accumulator columns
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -151,54 +150,79 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * kStageBytes;
-        uint8_t* sb = sa + kTileABytes;
-        ptx::mbar_expect_tx(&full_bar[s], kStageBytes);
-        ptx::tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBK, m0);
-        ptx::tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kBK, n0);
+      uint32_t it = 0;  // running k-block counter across tiles -> smem stage / phase
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * kStageBytes;
+          ptx::mbar_expect_tx(&full_bar[s], kStageBytes);
+          ptx::tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBK, m0);
+          ptx::tma_load_2d(sa + kTileABytes, &tmap_b, &full_bar[s], kb * kBK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kBM, kBN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t & 1;
+        ptx::mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator (passes on first use)
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes);
-        const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
-        const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + kTileABytes);
+        const uint32_t tmem_d = tmem_base + acc * kBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes);
+          const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
+          const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + kTileABytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
-          ptx::umma_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
+            ptx::umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
         }
-        ptx::umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
+        ptx::umma_commit(&acc_full[acc]);  // accumulator complete
       }
-      ptx::umma_commit(acc_bar);  // accumulator complete
     }
   } else {
-    ptx::mbar_wait(acc_bar, 0);
-    ptx::tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
+    float* stage = staging + q * 32 * kStagePad;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
+      const uint32_t acc = t & 1;
+      ptx::mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * kBN + (static_cast<uint32_t>(q * 32) << 16);
+      const int row0 = m0 + q * 32;
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
-      uint32_t acc[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
-      ptx::tmem_ld_wait();
-      if (row < p.M) epilogue_chunk<EPI>(p, row, n0 + c * 32, acc);
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (c == kBN / 32 - 1) {  // last read of this accumulator: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&acc_empty[acc]);
+        }
+        __syncwarp();  // previous patch fully consumed before the staging rows are overwritten
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[lane * kStagePad + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        epilogue_patch<EPI>(p, stage, row0, n0 + c * 32, lane);
+      }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, kBN);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 template <int EPI>
@@ -210,7 +234,9 @@ static int32_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const G
     attr_set = true;
   }
   const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + kBN - 1) / kBN;
-  gemm_bf16_kernel<EPI><<<m_tiles * n_tiles, kGemmThreads, kGemmSmem, s>>>(ta, tb, p);
+  const int total = m_tiles * n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_bf16_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, p);
   MC_CHECK_LAUNCH("gemm_bf16_kernel launch");
   return MC_OK;
 }
@@ -224,8 +250,6 @@ extern "C" int32_t mc_gemm_bf16(const void* A, int64_t lda, const void* B, int64
   MC_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lda >= K && ldb >= K, "mc_gemm_bf16: K/lda/ldb must be multiples of 8 (16-byte TMA pitch)");
   MC_CHECK_ARG(mc::aligned16(A) && mc::aligned16(B) && mc::aligned16(out), "mc_gemm_bf16: A/B/out must be 16-byte aligned");
   MC_CHECK_ARG(ldo >= N, "mc_gemm_bf16: ldo=%lld < N=%d", static_cast<long long>(ldo), N);
-  MC_CHECK_ARG(bias == nullptr || mc::aligned16(bias), "mc_gemm_bf16: bias must be 16-byte aligned");
-  MC_CHECK_ARG(gate == nullptr || mc::aligned16(gate), "mc_gemm_bf16: gate must be 16-byte aligned");
   CUtensorMap ta, tb;
   int32_t rc = mc::make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), mc::kBM, mc::kBK);
   if (rc) return rc;

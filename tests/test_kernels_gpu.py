@@ -260,8 +260,9 @@ def test_gemm_epilogues():
     # GELU(tanh) on the bf16-rounded Linear output
     out = ops.gemm(a, b, bias, L.MC_EPI_BIAS_GELU_BF16)
     ref = torch.nn.functional.gelu(acc.bfloat16().float(), approximate="tanh")
-    nbad, maxerr = bf16_ulp_close(out, ref, extra_atol=2e-3)  # a 1-ulp flip of the bf16 pre-activation moves GELU by <= ulp(x)
-    assert nbad == 0, (nbad, maxerr)
+    # a 1-ulp flip of the bf16 pre-activation (2^-8 relative to |acc|) moves GELU by at most that much (|GELU'| <= 1.13)
+    tol = ref.abs() * 2.0 ** -7 + acc.abs() * 2.0 ** -7 + 1e-3
+    assert ((out.float() - ref).abs() <= tol).all(), float((out.float() - ref).abs().max())
     # gated residual, fp32 stream updated in place
     x = torch.randn(M, N, device=DEV)
     gate = torch.randn(N, device=DEV) * 0.5
