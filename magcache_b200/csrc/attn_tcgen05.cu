@@ -171,17 +171,23 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_free[b]);
 
-      const int valid = p.Lk - j * kBKV;  // columns >= valid are padding (only on the last tile)
-      float mx = -INFINITY;
+      const int valid = p.Lk - j * kBKV;  // columns >= valid are padding (only possible on the last tile)
+      if (valid < kBKV) {                  // warp-uniform, taken at most once per CTA
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (h * 32 + c >= valid) sreg[h][c] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains of 3-input max: 0.5 instruction per element
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          float s = __uint_as_float(sreg[h][c]);
-          if (h * 32 + c >= valid) s = -INFINITY;
-          sreg[h][c] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
+        for (int c = 0; c < 32; c += 4) {
+          mx0 = ptx::max3(mx0, __uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1]));
+          mx1 = ptx::max3(mx1, __uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3]));
         }
+      const float mx = fmaxf(mx0, mx1);
       const float m_new = fmaxf(m, mx * p.scale_log2);
       bool waited = false;
       if (j == 0) {
@@ -210,18 +216,32 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
           ptx::tmem_st_wait();
         }
       }
-      // P = 2^(s*scale - m), row sum in fp32 before the bf16 rounding (as flash-attention does)
-      float psum = 0.f;
+      // P = 2^(s*scale - m), row sum in fp32 before the bf16 rounding (as flash-attention does).
+      // Packed fp32x2 FMA / ADD: one FFMA2 + two MUFU.EX2 + one FADD2 + one bf16x2 pack per pair of elements.
+      const uint64_t scale2 = ptx::pack_f32x2(p.scale_log2, p.scale_log2);
+      const uint64_t negm2 = ptx::pack_f32x2(-m, -m);
+      uint64_t sum2a = 0ull, sum2b = 0ull;  // (+0.f, +0.f)
       uint32_t packed[32];
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[h][c]), p.scale_log2, -m));
-          const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[h][c + 1]), p.scale_log2, -m));
-          psum += p0 + p1;
-          packed[h * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
+        for (int c = 0; c < 32; c += 4) {
+          float a0, a1, b0, b1;
+          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1])), scale2, negm2), a0, a1);
+          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3])), scale2, negm2), b0, b1);
+          a0 = ptx::ex2_approx(a0);
+          a1 = ptx::ex2_approx(a1);
+          b0 = ptx::ex2_approx(b0);
+          b1 = ptx::ex2_approx(b1);
+          sum2a = ptx::add_f32x2(sum2a, ptx::pack_f32x2(a0, a1));
+          sum2b = ptx::add_f32x2(sum2b, ptx::pack_f32x2(b0, b1));
+          packed[h * 16 + (c >> 1)] = pack_bf16x2(a0, a1);
+          packed[h * 16 + (c >> 1) + 1] = pack_bf16x2(b0, b1);
         }
+      float s0, s1, s2, s3;
+      ptx::unpack_f32x2(sum2a, s0, s1);
+      ptx::unpack_f32x2(sum2b, s2, s3);
+      const float psum = (s0 + s1) + (s2 + s3);
       l += psum;
       if (j > 0 && !waited) {
         ptx::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) has finished reading the P buffer

@@ -71,8 +71,12 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float kBeta = 0.7978845608028654f;  // sqrt(2/pi)
   const float kKappa = 0.044715f;
   const float u = kBeta * (x + kKappa * x * x * x);
-  // 0.5*(1+tanh(u)) == 1/(1+exp(-2u)); __expf keeps the epilogue off the slow tanhf path (error << 1 bf16 ulp)
-  return x / (1.0f + __expf(-2.0f * u));
+  // one MUFU.TANH (tanh.approx.f32, |rel err| ~ 2^-11) instead of tanhf's ~20 instructions: the result is rounded to
+  // bf16 (2^-9 relative) by every caller, so the approximation is invisible after rounding except on exact ties
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -80,26 +80,53 @@ __device__ __forceinline__ void epilogue_patch(const GemmParams& p, const float*
     if (c0 < p.N) b0 = p.bias[c0];
     if (c0 + 1 < p.N) b1 = p.bias[c0 + 1];
   }
-  __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.out);
-  const bool pair_ok = (c0 + 1 < p.N) && ((p.ldo & 1) == 0);
+  __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row0 + half) * p.ldo + c0;
+  const float* sbase = stage + half * kStagePad + cp;
+  const float* rbias = (EPI == MC_EPI_ROWBIAS_BF16 && p.bias) ? p.bias + row0 + half : nullptr;
+
+  if (rows == 32 && col0 + 32 <= p.N && (p.ldo & 1) == 0) {
+    // interior patch: branch-free, 16 independent iterations for the scheduler to interleave
+    uint32_t w[16];
 #pragma unroll
-  for (int rr = 0; rr < 32; rr += 2) {
-    const int r = rr + half;
+    for (int i = 0; i < 16; ++i) {
+      float v0 = sbase[2 * i * kStagePad], v1 = sbase[2 * i * kStagePad + 1];
+      if (EPI == MC_EPI_ROWBIAS_BF16) {
+        const float rb = rbias ? rbias[2 * i] : 0.f;  // V^T = Wv h^T + bv: bias indexed by the output ROW
+        v0 += rb;
+        v1 += rb;
+      } else {
+        v0 += b0;
+        v1 += b1;
+      }
+      if (EPI == MC_EPI_BIAS_GELU_BF16) {  // the Linear output is bf16 before nn.GELU(tanh) sees it
+        v0 = gelu_tanh(round_bf16(v0));
+        v1 = gelu_tanh(round_bf16(v1));
+      }
+      w[i] = pack_bf16x2(v0, v1);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) *reinterpret_cast<uint32_t*>(obase + static_cast<int64_t>(2 * i) * p.ldo) = w[i];
+    return;
+  }
+
+  const bool pair_ok = (c0 + 1 < p.N) && ((p.ldo & 1) == 0);
+  for (int i = 0; i < 16; ++i) {
+    const int r = 2 * i + half;
     if (r >= rows) continue;
-    float v0 = stage[r * kStagePad + cp], v1 = stage[r * kStagePad + cp + 1];
+    float v0 = sbase[2 * i * kStagePad], v1 = sbase[2 * i * kStagePad + 1];
     if (EPI == MC_EPI_ROWBIAS_BF16) {
-      const float rb = p.bias ? p.bias[row0 + r] : 0.f;  // V^T = Wv h^T + bv: bias indexed by the output ROW
+      const float rb = rbias ? rbias[2 * i] : 0.f;
       v0 += rb;
       v1 += rb;
     } else {
       v0 += b0;
       v1 += b1;
     }
-    if (EPI == MC_EPI_BIAS_GELU_BF16) {  // the Linear output is bf16 before nn.GELU(tanh) sees it
+    if (EPI == MC_EPI_BIAS_GELU_BF16) {
       v0 = gelu_tanh(round_bf16(v0));
       v1 = gelu_tanh(round_bf16(v1));
     }
-    __nv_bfloat16* o = obase + static_cast<int64_t>(row0 + r) * p.ldo + c0;
+    __nv_bfloat16* o = obase + static_cast<int64_t>(2 * i) * p.ldo;
     if (pair_ok) {
       *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
     } else {

