@@ -95,6 +95,38 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle "port" of the reference path) — bounded sample, extrapolated; states exactly what was timed
 # ---------------------------------------------------------------------------------------------------------------------
+def host_cores():
+    """CPU threads this process may really use: affinity mask, clipped by the cgroup CPU quota when one is set."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(math.ceil(int(quota) / int(period)))))
+    except Exception:  # noqa: BLE001
+        pass
+    return n
+
+
+def pick_threads(state):
+    """torch-CPU scales badly past the physical cores the container really owns: try a few thread counts on one sample
+    each and keep the fastest ("all the host threads it can use", not more)."""
+    import torch
+    n = host_cores()
+    best, best_t = n, None
+    for c in sorted({min(n, v) for v in (8, 16, 32, 64, n)}):
+        torch.set_num_threads(c)
+        cpu_time_block(state)
+        t, _ = cpu_time_block(state)
+        if best_t is None or t < best_t:
+            best, best_t = c, t
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_sample_setup(n_frames=21, hp=15, wp=13):
     import torch
     from oracle import wan_ref
@@ -139,10 +171,9 @@ def run_reference_arm(args, rank):
     import torch
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     state = cpu_sample_setup()
     n_sample = state[-1]
+    cores = pick_threads(state)
     for _ in range(max(1, min(args.warmup, 2))):
         cpu_time_block(state)
     tb, ta = [], []
@@ -336,10 +367,8 @@ def bench_k1(dev, pk):
 
 def cpu_baseline_leg():
     import torch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     state = cpu_sample_setup()
-    cpu_time_block(state)
+    cores = pick_threads(state)
     tb, ta = [], []
     t0 = time.perf_counter()
     while len(tb) < 5 and time.perf_counter() - t0 < 25:
