@@ -10,6 +10,8 @@
 //   warp 5     MMA issuer : S_j = Q K_j^T (M128 N64 K128, double-buffered in TMEM), O += P_j V_j (M128 N128 K64)
 // V is consumed transposed (V^T [heads*128, Lk], produced directly by the V-projection GEMM) so that both MMAs see
 // K-major operands — the same smem/UMMA descriptor path the GEMM kernel uses.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
@@ -39,6 +41,10 @@ struct AttnParams {
   int64_t ldo;
 };
 
+// P_IN_TMEM: the bf16 probabilities are written back into the (already consumed) S columns of TMEM with tcgen05.st and the
+// PV MMA takes its A operand from TMEM — no smem round trip, no generic->async proxy fence, and P is double-buffered for free
+// (it lives in S buffer j&1), which removes the write-P -> PV -> pv_done -> write-next-P serialisation of the smem variant.
+template <bool P_IN_TMEM>
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
@@ -134,7 +140,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         if (j + 1 < n_tiles) {
           const int t = j + 1;
           ptx::mbar_wait(&k_full[t & 1], (t >> 1) & 1);
-          if (t >= 2) ptx::mbar_wait(&s_free[t & 1], ((t - 2) >> 1) & 1);  // softmax of tile t-2 has drained this S buffer
+          // S buffer t&1 was last used by tile t-2: its softmax must have drained it. With P in TMEM that is implied by
+          // p_full(t-2) (waited before PV(t-2) was issued) and the in-order execution of PV(t-2) before this MMA.
+          if (!P_IN_TMEM && t >= 2) ptx::mbar_wait(&s_free[t & 1], ((t - 2) >> 1) & 1);
           ptx::tc_fence_after();
           issue_s(t);
         }
@@ -144,9 +152,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         const uint32_t v_addr = ptx::smem_u32(smem + kOffV + (j & 1) * kVBytes);
 #pragma unroll
         for (int kk = 0; kk < kBKV / 16; ++kk) {
-          const uint64_t da = ptx::umma_desc_sw128_kmajor(p_addr) + 2 * kk;
           const uint64_t db = ptx::umma_desc_sw128_kmajor(v_addr) + 2 * kk;
-          ptx::umma_ss(tmem_o, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
+          if (P_IN_TMEM) {
+            ptx::umma_ts(tmem_o, tmem_base + (j & 1) * kBKV + kk * 8, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = ptx::umma_desc_sw128_kmajor(p_addr) + 2 * kk;
+            ptx::umma_ss(tmem_o, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
+          }
         }
         ptx::umma_commit(&v_empty[j & 1]);
         ptx::umma_commit(pv_done);
@@ -168,8 +180,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV, sreg[0]);
       ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV + 32, sreg[1]);
       ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&s_free[b]);
+      if (!P_IN_TMEM) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&s_free[b]);
+      }
 
       const int valid = p.Lk - j * kBKV;  // columns >= valid are padding (only possible on the last tile)
       if (valid < kBKV) {                  // warp-uniform, taken at most once per CTA
@@ -243,15 +257,22 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       ptx::unpack_f32x2(sum2b, s2, s3);
       const float psum = (s0 + s1) + (s2 + s3);
       l += psum;
-      if (j > 0 && !waited) {
-        ptx::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) has finished reading the P buffer
-      }
+      if (P_IN_TMEM) {
+        // P_j overwrites the first 32 columns of S buffer b (64 bf16 per row = 32 packed words); its reader PV(j) is ordered
+        // before S(j+2) by the tensor pipe, so nothing else has to be waited for here
+        ptx::tmem_st_32x32b_x32(tmem_base + lane_sel + b * kBKV, packed);
+        ptx::tmem_st_wait();
+      } else {
+        if (j > 0 && !waited) {
+          ptx::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) has finished reading the single smem P buffer
+        }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 8 x 16-byte chunks per 128-byte row, XOR-swizzled with (row % 8)
-        uint4 w = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
-        *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) = w;
+        for (int c = 0; c < 8; ++c) {  // 8 x 16-byte chunks per 128-byte row, XOR-swizzled with (row % 8)
+          uint4 w = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
+          *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) = w;
+        }
+        ptx::fence_proxy_async_smem();
       }
-      ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
     }
@@ -303,15 +324,23 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
   if (rc) return rc;
   rc = mc::make_tmap_bf16_2d(&tv, vt, static_cast<uint64_t>(width), static_cast<uint64_t>(Lk), static_cast<uint64_t>(ldvt), mc::kHD, mc::kBKV);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mc::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e != cudaSuccess) return mc::cuda_fail(e, "cudaFuncSetAttribute(attn smem)");
-    attr_set = true;
+  static int variant = -1;  // 1: P in TMEM (default), 0: P through shared memory (MC_ATTN_P_SMEM=1, kept for A/B measurements)
+  if (variant < 0) {
+    const char* ev = getenv("MC_ATTN_P_SMEM");
+    variant = (ev && ev[0] == '1') ? 0 : 1;
+    cudaError_t e = cudaFuncSetAttribute(mc::attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    if (e != cudaSuccess) {
+      variant = -1;
+      return mc::cuda_fail(e, "cudaFuncSetAttribute(attn smem)");
+    }
   }
   mc::AttnParams p{Lq, Lk, heads, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo};
   dim3 grid((Lq + mc::kBQ - 1) / mc::kBQ, heads);
-  mc::attn_fwd_kernel<<<grid, mc::kAttnThreads, mc::kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  if (variant == 1)
+    mc::attn_fwd_kernel<true><<<grid, mc::kAttnThreads, mc::kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  else
+    mc::attn_fwd_kernel<false><<<grid, mc::kAttnThreads, mc::kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   MC_CHECK_LAUNCH("attn_fwd_kernel launch");
   return MC_OK;
 }
