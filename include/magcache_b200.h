@@ -157,12 +157,16 @@ int32_t mc_linear_f32_small(const float* x, int32_t M, int32_t K, const float* W
                             float* y, void* stream);
 
 /* Head + unpatchify (magcache_generate.py:304-305): out[c, f, 2h+p, 2w+q] = Linear_fp32(LN(x)*(1+e1)+e0)[token, (p,q,c)].
- * x: [rows = F*Hp*Wp, cols] (fp32, or the un-materialised hit sum x0_bf16 + r_f32 when r != NULL: fused cache-hit path).
+ * x: [rows, cols] for the tokens row_offset .. row_offset+rows-1 of the F*Hp*Wp grid (rows = F*Hp*Wp, row_offset = 0 unless the
+ * token axis is sharded); fp32, or the un-materialised hit sum x0_bf16 + r_f32 when r != NULL (fused cache-hit path).
  * head_mod: [2, cols] modulation parameter, e: [cols] time embedding, Wt: head.weight TRANSPOSED [cols, 64] fp32, b: [64];
- * out fp32 [C, F, 2Hp, 2Wp]. */
-int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int32_t cols, int32_t F, int32_t Hp,
-                           int32_t Wp, int32_t C_out, const float* head_mod, const float* e, const float* Wt, const float* b,
-                           float eps, float* out, void* stream);
+ * out fp32 [C, F, 2Hp, 2Wp]: only the positions of the given tokens are written. */
+int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
+                           int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e,
+                           const float* Wt, const float* b, float eps, float* out, void* stream);
+
+/* bf16 transpose dst[c, r] = src[r, c] (token-sharded runs: all-gathered V [N, D] -> V^T [D, N] for mc_attn_fwd). */
+int32_t mc_transpose_bf16(const void* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldd, void* stream);
 
 /* sinusoidal_embedding_1d(freq_dim, t) in float64, cos half first (magcache_generate.py:250-251): pos_dev [n_pos] f64 ->
  * out fp32 [n_pos, dim]. */

@@ -2,10 +2,10 @@
 
     from magcache_b200 import magcache_forward, magcache_calibration, init_magcache
 
-Importing this package loads libmagcache_b200.so (build it with `python -m magcache_b200.build`); there is no CPU fallback.
+Importing this package loads libmagcache_b200.so (build it with `python magcache_b200/build.py`); there is no CPU fallback.
 """
 from .config import PRESETS, MagCacheConfig, interp_cfg, nearest_interp, tables  # noqa: F401
-from .patch import (init_magcache, init_magcache_calibration, magcache_branch, magcache_calibration,  # noqa: F401
+from .patch import (enable_token_shard, init_magcache, init_magcache_calibration, magcache_branch, magcache_calibration,  # noqa: F401
                     magcache_forward)
 from .wan import WAN_CONFIGS, WanDims, WanEngine, WanModelHandle, WanWeights  # noqa: F401
 

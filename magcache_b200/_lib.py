@@ -1,6 +1,6 @@
 """ctypes binding of libmagcache_b200.so (the C ABI declared in include/magcache_b200.h).
 
-There is no fallback: if the shared library has not been built (`python -m magcache_b200.build`) importing
+There is no fallback: if the shared library has not been built (`python magcache_b200/build.py`) importing
 this module raises, and every device entry point raises `MagCacheError` when CUDA reports a failure.
 """
 import ctypes
@@ -58,8 +58,9 @@ SIGNATURES = {
     "mc_attn_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
                     c_void_p],
     "mc_linear_f32_small": [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p],
-    "mc_head_unpatchify": [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                           c_void_p, c_float, c_void_p, c_void_p],
+    "mc_head_unpatchify": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_float, c_void_p, c_void_p],
+    "mc_transpose_bf16": [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p],
     "mc_time_sinusoid": [c_void_p, c_int32, c_int32, c_void_p, c_void_p],
     "mc_cast": [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
     "mc_gelu_tanh_bf16": [c_void_p, c_int64, c_void_p],
@@ -67,7 +68,7 @@ SIGNATURES = {
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"{LIB_PATH} is missing: the CUDA extension has not been built. Run `python -m magcache_b200.build` "
+        f"{LIB_PATH} is missing: the CUDA extension has not been built. Run `python magcache_b200/build.py` "
         "(needs nvcc; cross-compiles for sm_100a without a GPU). There is no CPU/eager fallback by design.")
 
 lib = ctypes.CDLL(LIB_PATH)

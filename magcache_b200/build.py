@@ -1,4 +1,4 @@
-"""Build libmagcache_b200.so (sm_100a only) in-tree with nvcc. `python -m magcache_b200.build [--force]`."""
+"""Build libmagcache_b200.so (sm_100a only) in-tree with nvcc. `python magcache_b200/build.py [--force]`."""
 import os
 import shutil
 import subprocess

@@ -235,7 +235,7 @@ __device__ __forceinline__ float head_load(const void* x, int x_bf16, const floa
 
 template <bool FUSED_HIT>
 __global__ void __launch_bounds__(128) head_unpatchify_kernel(const void* __restrict__ x, int x_bf16, const float* __restrict__ r,
-                                                              int64_t rows, int cols, int F, int Hp, int Wp, int C_out,
+                                                              int64_t rows, int64_t row_offset, int cols, int F, int Hp, int Wp, int C_out,
                                                               const float* __restrict__ head_mod, const float* __restrict__ e,
                                                               const float* __restrict__ Wt, const float* __restrict__ bias,
                                                               float eps, float* __restrict__ out) {
@@ -315,9 +315,10 @@ __global__ void __launch_bounds__(128) head_unpatchify_kernel(const void* __rest
   for (int i = 0; i < 4; ++i) {
     const int64_t row = row_base + tr + i;
     if (row >= rows) continue;
-    const int wp = static_cast<int>(row % Wp);
-    const int hp = static_cast<int>((row / Wp) % Hp);
-    const int f = static_cast<int>(row / (static_cast<int64_t>(Wp) * Hp));
+    const int64_t tok = row_offset + row;  // global token index (token-sharded runs own a contiguous token range)
+    const int wp = static_cast<int>(tok % Wp);
+    const int hp = static_cast<int>((tok / Wp) % Hp);
+    const int f = static_cast<int>(tok / (static_cast<int64_t>(Wp) * Hp));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int o = tc + j;
@@ -351,6 +352,31 @@ __global__ void time_sinusoid_kernel(const double* __restrict__ pos, int n_pos, 
   const double s = pos[p] * freq;
   out[static_cast<int64_t>(p) * dim + k] = static_cast<float>(cos(s));
   out[static_cast<int64_t>(p) * dim + half + k] = static_cast<float>(sin(s));
+}
+
+// ---- bf16 transpose [rows, cols] -> [cols, rows] through a padded smem tile (token-sharded runs: gathered V -> V^T) ----
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int64_t lds, int rows, int cols,
+                                                             __nv_bfloat16* __restrict__ dst, int64_t ldd) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + tx * 2 + h;  // two adjacent columns per lane
+      tile[i][tx * 2 + h] = (r < rows && c < cols) ? src[static_cast<int64_t>(r) * lds + c] : __float2bfloat16(0.f);
+    }
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i;  // output row
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = r0 + tx * 2 + h;  // output column
+      if (c < cols && r < rows) dst[static_cast<int64_t>(c) * ldd + r] = tile[tx * 2 + h][i];
+    }
+  }
 }
 
 static int grid_for(int64_t work_items, int per_block) {
@@ -435,21 +461,32 @@ int32_t mc_linear_f32_small(const float* x, int32_t M, int32_t K, const float* W
   return MC_OK;
 }
 
-int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int32_t cols, int32_t F, int32_t Hp, int32_t Wp,
-                           int32_t C_out, const float* head_mod, const float* e, const float* Wt, const float* b, float eps,
-                           float* out, void* stream) {
+int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
+                           int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e, const float* Wt,
+                           const float* b, float eps, float* out, void* stream) {
   MC_CHECK_ARG(x && head_mod && e && Wt && b && out, "mc_head_unpatchify: null pointer");
   MC_CHECK_ARG(cols >= mc::kHeadKC && cols % mc::kHeadKC == 0, "mc_head_unpatchify: cols=%d must be a multiple of %d", cols, mc::kHeadKC);
   MC_CHECK_ARG(C_out * 4 == mc::kHeadOut, "mc_head_unpatchify: only patch (1,2,2) x C_out=16 (64 output features) is built, got C_out=%d", C_out);
   MC_CHECK_ARG(F >= 1 && Hp >= 1 && Wp >= 1, "mc_head_unpatchify: bad grid");
-  const int64_t rows = static_cast<int64_t>(F) * Hp * Wp;
+  MC_CHECK_ARG(rows >= 1 && row_offset >= 0 && row_offset + rows <= static_cast<int64_t>(F) * Hp * Wp,
+               "mc_head_unpatchify: token range [%lld, %lld) outside the %d x %d x %d grid", static_cast<long long>(row_offset),
+               static_cast<long long>(row_offset + rows), F, Hp, Wp);
   const int grid = static_cast<int>((rows + mc::kHeadRows - 1) / mc::kHeadRows);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (r_or_null)
-    mc::head_unpatchify_kernel<true><<<grid, 128, 0, s>>>(x, x_dtype == MC_BF16, r_or_null, rows, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, out);
+    mc::head_unpatchify_kernel<true><<<grid, 128, 0, s>>>(x, x_dtype == MC_BF16, r_or_null, rows, row_offset, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, out);
   else
-    mc::head_unpatchify_kernel<false><<<grid, 128, 0, s>>>(x, x_dtype == MC_BF16, nullptr, rows, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, out);
+    mc::head_unpatchify_kernel<false><<<grid, 128, 0, s>>>(x, x_dtype == MC_BF16, nullptr, rows, row_offset, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, out);
   MC_CHECK_LAUNCH("head_unpatchify_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_transpose_bf16(const void* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldd, void* stream) {
+  MC_CHECK_ARG(src && dst && rows >= 1 && cols >= 1 && lds >= cols && ldd >= rows, "mc_transpose_bf16: bad arguments");
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+  mc::transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(src), lds, rows, cols,
+                                                                                static_cast<__nv_bfloat16*>(dst), ldd);
+  MC_CHECK_LAUNCH("transpose_bf16_kernel launch");
   return MC_OK;
 }
 

@@ -102,8 +102,9 @@ def residual_stats(r_cur, r_prev, denom_eps=0.0):
     return _finish_stats(stats)
 
 
-def residual_sub_stats(x_out, x_in, r_prev, denom_eps=0.0):
-    """Fused `x - ori_x` + statistics against the previous residual (calibration miss epilogue)."""
+def residual_sub_stats(x_out, x_in, r_prev, denom_eps=0.0, reduce=None):
+    """Fused `x - ori_x` + statistics against the previous residual (calibration miss epilogue). `reduce(stats_dev)` lets a
+    token-sharded caller all-reduce the four partial sums before they are finalised on the host."""
     _dev(x_out), _dev(x_in), _dev(r_prev)
     assert x_out.dtype == torch.float32 and x_in.dtype == torch.bfloat16 and r_prev.dtype == torch.float32
     cols = x_out.shape[-1]
@@ -113,6 +114,8 @@ def residual_sub_stats(x_out, x_in, r_prev, denom_eps=0.0):
     check(lib.mc_residual_sub_stats(x_out.data_ptr(), MC_F32, x_in.data_ptr(), MC_BF16, r.data_ptr(), r_prev.data_ptr(), rows, cols,
                                     float(denom_eps), stats.data_ptr(), _stream()))
     _count(2)
+    if reduce is not None:
+        stats = reduce(stats)
     return r, _finish_stats(stats)
 
 
@@ -227,20 +230,35 @@ def time_sinusoid(t, dim):
     return out
 
 
-def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None):
+def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None, row_offset=0, out=None):
     """head(x, e) + unpatchify (MagCache4Wan2.1/magcache_generate.py:304-305) -> fp32 [c_out, F, 2*Hp, 2*Wp].
-    With `residual` (fp32) the cache-hit sum x + residual is formed on the fly (fused hit path)."""
+    With `residual` (fp32) the cache-hit sum x + residual is formed on the fly (fused hit path). A token-sharded caller
+    passes its contiguous token range (`row_offset`, x.shape[0] rows) and a zero-initialised `out` to be summed over ranks."""
     _dev(x)
     F, Hp, Wp = grid
     rows, cols = x.shape
-    assert rows == F * Hp * Wp and x.is_contiguous() and w_t.shape == (cols, 4 * c_out) and w_t.is_contiguous()
+    assert row_offset + rows <= F * Hp * Wp and x.is_contiguous() and w_t.shape == (cols, 4 * c_out) and w_t.is_contiguous()
     assert head_mod.shape[-2:] == (2, cols) and e.numel() == cols
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == x.shape
-    out = torch.empty(c_out, F, 2 * Hp, 2 * Wp, dtype=torch.float32, device=x.device)
+    if out is None:
+        assert rows == F * Hp * Wp, "a partial token range needs a caller-provided (zeroed) output"
+        out = torch.empty(c_out, F, 2 * Hp, 2 * Wp, dtype=torch.float32, device=x.device)
     with _Timed(tag):
-        check(lib.mc_head_unpatchify(x.data_ptr(), _dt(x), residual.data_ptr() if residual is not None else None, cols, F, Hp, Wp, c_out,
-                                     head_mod.data_ptr(), e.data_ptr(), w_t.data_ptr(), b.data_ptr(), eps, out.data_ptr(), _stream()))
+        check(lib.mc_head_unpatchify(x.data_ptr(), _dt(x), residual.data_ptr() if residual is not None else None, rows, row_offset, cols,
+                                     F, Hp, Wp, c_out, head_mod.data_ptr(), e.data_ptr(), w_t.data_ptr(), b.data_ptr(), eps,
+                                     out.data_ptr(), _stream()))
+    _count()
+    return out
+
+
+def transpose(src, out):
+    """out[c, r] = src[r, c] for bf16 2-D views (row strides allowed)."""
+    _dev(src), _dev(out)
+    assert src.dtype == out.dtype == torch.bfloat16 and src.stride(1) == 1 and out.stride(1) == 1
+    rows, cols = src.shape
+    assert out.shape == (cols, rows)
+    check(lib.mc_transpose_bf16(src.data_ptr(), src.stride(0), rows, cols, out.data_ptr(), out.stride(0), _stream()))
     _count()
     return out
 

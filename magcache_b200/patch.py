@@ -32,9 +32,19 @@ def _engine(self):
             weights = WanWeights.from_module(self, dev)
         else:
             raise TypeError("magcache_b200.magcache_forward expects a Wan2.1 WanModel (or an object carrying `_mc_engine`)")
-        eng = WanEngine(weights)
+        eng = WanEngine(weights, **self.__dict__.get("_mc_shard_kw", {}))
         object.__setattr__(self, "_mc_engine", eng)
     return eng
+
+
+def enable_token_shard(model, rank, world, group=None):
+    """Shard the token axis of `model`'s forwards over `world` ranks of one node (call before the first forward; needs an
+    initialised torch.distributed NCCL group). Every rank must then make the same calls with the same inputs; outputs are
+    replicated, the residual cache stays sharded."""
+    if "_mc_engine" in model.__dict__:
+        raise RuntimeError("enable_token_shard must be called before the first forward")
+    object.__setattr__(model, "_mc_shard_kw", dict(shard_world=world, shard_rank=rank, shard_group=group))
+    return model
 
 
 def _controller(self):
@@ -98,7 +108,11 @@ def magcache_calibration(self, x, t, context, seq_len, clip_fea=None, y=None):
     slot = self.cnt % 2
     if self.cnt >= 2:
         prev = self.residual_cache[slot].view(x0.shape)
-        residual_x, (norm_ratio, norm_std, cos_dis) = ops.residual_sub_stats(xs, x0, prev)
+        reduce = None
+        if eng.shard is not None:  # the statistics are sums over tokens: add the partial sums of every token shard
+            from .shard import allreduce_stats
+            reduce = lambda st: allreduce_stats(st, eng.shard.group)  # noqa: E731
+        residual_x, (norm_ratio, norm_std, cos_dis) = ops.residual_sub_stats(xs, x0, prev, reduce=reduce)
         self.norm_ratio.append(round(norm_ratio, 5))
         self.norm_std.append(round(norm_std, 5))
         self.cos_dis.append(round(cos_dis, 5))

@@ -178,25 +178,41 @@ def rope_table(grid, head_dim, device):
 class WanEngine:
     """Runs prologue / block stack / head of one Wan forward on the kernels. One engine per (weights, token count)."""
 
-    def __init__(self, weights: WanWeights):
+    def __init__(self, weights: WanWeights, shard_world=1, shard_rank=0, shard_group=None):
         self.w = weights
         self.dims = weights.dims
         self.device = weights.device
         self._n = None
         self._rope = {}
+        # token-axis sharding (magcache_b200/shard.py): world 1 = single GPU
+        self.world, self.rank, self.group = shard_world, shard_rank, shard_group
+        self.shard = None
 
     # ------------------------------------------------------------------------------------------ workspace
-    def _workspace(self, n):
-        if self._n == n:
+    def _workspace(self, n_total):
+        if self._n == n_total:
             return
         d, dev = self.dims, self.device
         D, F = d.dim, d.ffn_dim
-        self.npad = (n + 7) // 8 * 8
+        self.npad = (n_total + 7) // 8 * 8
         bf = dict(dtype=torch.bfloat16, device=dev)
+        if self.world > 1:
+            from .shard import TokenShard
+            self.shard = TokenShard(self.rank, self.world, n_total, self.group)
+            n = self.shard.n_local
+            # gathered K / V rows of ALL tokens (every rank attends to every key), local q / k / v projections
+            self.k_all = torch.empty(n_total, D, **bf)
+            self.v_all = torch.empty(n_total, D, **bf)
+            self.q_loc = torch.empty(n, D, **bf)
+            self.k_loc = torch.empty(n, D, **bf)
+            self.v_loc = torch.empty(n, D, **bf)
+            self.out_full = None
+        else:
+            n = n_total
+            self.qk = torch.empty(n, 2 * D, **bf)
         self.x0 = torch.empty(n, D, **bf)
         self.xs = torch.empty(n, D, dtype=torch.float32, device=dev)
         self.h = torch.empty(n, D, **bf)
-        self.qk = torch.empty(n, 2 * D, **bf)
         self.vt = torch.zeros(D, self.npad, **bf)
         self.att = torch.empty(n, D, **bf)
         self.ffn = torch.empty(n, F, **bf)
@@ -207,7 +223,7 @@ class WanEngine:
         self.ctx_h = torch.empty(d.text_len, D, **bf)
         self.ctx = torch.empty(d.text_len, D, **bf)
         self.em = torch.empty(6, D, dtype=torch.float32, device=dev)
-        self._n = n
+        self._n = n_total
 
     def _rope_for(self, grid):
         if grid not in self._rope:
@@ -224,6 +240,8 @@ class WanEngine:
         n = grid[0] * grid[1] * grid[2]
         self._workspace(n)
         tok = ops.patchify(latent.contiguous())
+        if self.shard is not None:
+            tok = self.shard.rows(tok)  # this rank embeds only its own tokens
         ops.gemm(tok, w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
         sin = ops.time_sinusoid(t.reshape(-1)[:1], d.freq_dim)
         e = ops.linear_f32_small(ops.linear_f32_small(sin, w.time_w1, w.time_b1, act=2), w.time_w2, w.time_b2, act=0)
@@ -245,17 +263,37 @@ class WanEngine:
         xs = self.xs
         ops.cast_into(x0, xs)  # block 0 sees the bf16 patch embedding; every later op works on the fp32 stream
         rope = self._rope_for(grid)
-        q, k = self.qk[:, :D], self.qk[:, D:]
-        vt = self.vt[:, :n]
+        sh = self.shard
+        if sh is None:
+            q, k = self.qk[:, :D], self.qk[:, D:]
+            vt = self.vt[:, :n]
+        else:
+            rope = sh.rows(rope)  # RoPE uses the GLOBAL token index -> (f, h, w)
+            vt = self.vt[:, :sh.n_tokens]
         for li, b in enumerate(self.w.blocks):
             ops.cache_hit_add(b["mod"], e0, out=self.em)  # e = modulation + e0 (fp32)
             # --- self attention
             ops.ln_modulate(xs, self.em, 1, 0, eps=d.eps, round_ln_to_bf16=(li == 0), out=self.h)
-            ops.gemm(self.h, b["w_qk"], b["b_qk"], E.MC_EPI_BIAS_BF16, out=self.qk, tag="gemm_qk")
-            ops.gemm(b["w_v"], self.h, b["b_v"], E.MC_EPI_ROWBIAS_BF16, out=vt)
-            ops.rmsnorm_rope_(q, b["nq"], rope, d.head_dim, eps=d.eps)
-            ops.rmsnorm_rope_(k, b["nk"], rope, d.head_dim, eps=d.eps)
-            ops.attention(q, k, vt, H, out=self.att, tag="attn_self")
+            if sh is None:
+                ops.gemm(self.h, b["w_qk"], b["b_qk"], E.MC_EPI_BIAS_BF16, out=self.qk, tag="gemm_qk")
+                ops.gemm(b["w_v"], self.h, b["b_v"], E.MC_EPI_ROWBIAS_BF16, out=vt)
+                ops.rmsnorm_rope_(q, b["nq"], rope, d.head_dim, eps=d.eps)
+                ops.rmsnorm_rope_(k, b["nk"], rope, d.head_dim, eps=d.eps)
+                ops.attention(q, k, vt, H, out=self.att, tag="attn_self")
+            else:
+                from .shard import gather_rows
+                # K and V first so their all-gathers (NCCL, own stream) overlap the Q projection / RMSNorm / RoPE
+                ops.gemm(self.h, b["w_qk"][D:], b["b_qk"][D:], E.MC_EPI_BIAS_BF16, out=self.k_loc)
+                ops.rmsnorm_rope_(self.k_loc, b["nk"], rope, d.head_dim, eps=d.eps)
+                wk = gather_rows(self.k_loc, self.k_all, sh.group, async_op=True)
+                ops.gemm(self.h, b["w_v"], b["b_v"], E.MC_EPI_BIAS_BF16, out=self.v_loc)
+                wv = gather_rows(self.v_loc, self.v_all, sh.group, async_op=True)
+                ops.gemm(self.h, b["w_qk"][:D], b["b_qk"][:D], E.MC_EPI_BIAS_BF16, out=self.q_loc, tag="gemm_qk")
+                ops.rmsnorm_rope_(self.q_loc, b["nq"], rope, d.head_dim, eps=d.eps)
+                wk.wait()
+                wv.wait()
+                ops.transpose(self.v_all, vt)  # gathered V [N, D] -> V^T [D, N] for the PV MMA's K-major B operand
+                ops.attention(self.q_loc, self.k_all, vt, H, out=self.att, tag="attn_self")
             ops.gemm(self.att, b["w_o"], b["b_o"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[2])
             # --- cross attention (text)
             ops.ln_affine(xs, b["n3_w"], b["n3_b"], eps=d.eps, out=self.h)
@@ -275,8 +313,15 @@ class WanEngine:
     # ------------------------------------------------------------------------------------------ epilogue (:304-305)
     def head(self, x, e, grid, residual=None):
         w = self.w
-        return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps,
-                                   tag="head_hit_fused" if residual is not None else "head")
+        tag = "head_hit_fused" if residual is not None else "head"
+        if self.shard is None:
+            return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, c_out=self.dims.out_dim, residual=residual,
+                                       eps=self.dims.eps, tag=tag)
+        from .shard import sum_partial_outputs
+        out = torch.zeros(self.dims.out_dim, grid[0], 2 * grid[1], 2 * grid[2], dtype=torch.float32, device=self.device)
+        ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps,
+                            tag=tag, row_offset=self.shard.start, out=out)
+        return sum_partial_outputs(out, self.shard.group)  # every rank ends up with the full noise prediction
 
 
 class WanModelHandle:
@@ -286,14 +331,14 @@ class WanModelHandle:
 
     model_type = "t2v"
 
-    def __new__(cls, weights: WanWeights):
+    def __new__(cls, weights: WanWeights, **engine_kw):
         sub = type("WanModelHandle", (cls,), {})
         self = object.__new__(sub)
         return self
 
-    def __init__(self, weights: WanWeights):
+    def __init__(self, weights: WanWeights, **engine_kw):
         self.dim, self.num_heads = weights.dims.dim, weights.dims.num_heads
-        self._mc_engine = WanEngine(weights)
+        self._mc_engine = WanEngine(weights, **engine_kw)
 
     def __call__(self, *args, **kwargs):
         return self.forward(*args, **kwargs)
