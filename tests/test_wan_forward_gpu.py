@@ -173,3 +173,21 @@ def test_scalar_family_branch_flux_and_hunyuan():
             assert torch.equal(out, exp), (preset, i)
             assert torch.equal(getattr(m, attr), cache_ref)
             assert m.cnt == ref_ctl.cnt
+
+
+def test_wan14b_shaped_blocks_vs_oracle():
+    """BASELINE configs[4] shapes (dim 5120, 40 heads, ffn 13824) at reduced depth / token count: exercises the wide-row
+    LayerNorm / RMSNorm paths (cols > 2048), 40-head attention and the N = 13824 GEMM tiling against the oracle."""
+    from oracle import wan_ref
+    model = wan_ref.WanModel(dim=5120, ffn_dim=13824, num_heads=40, num_layers=1, text_dim=256, text_len=32).init_synthetic(1)
+    lat, ctx, _ = make_inputs(4, grid=(2, 8, 12), text_dim=256, L=19)
+    n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
+    t = torch.tensor([333.0])
+    ref_model = install_ref(wan_ref, copy.deepcopy(model), 10)
+    with torch.no_grad():
+        ref = ref_model([lat], t=t, context=[ctx], seq_len=n_tok)[0]
+    ours_model = install_ours(copy.deepcopy(model).to(DEV), 10)
+    out = ours_model([lat.to(DEV)], t=t.to(DEV), context=[ctx.to(DEV)], seq_len=n_tok)[0].cpu()
+    e = rel_l2(out, ref)
+    print("14B-shaped rel-L2 vs oracle", e)
+    assert e <= 2e-2
