@@ -55,7 +55,7 @@ def _controller(self):
     return c
 
 
-def _prologue(self, x, t, context, seq_len, clip_fea, y):
+def _stage(self, x, t, context, seq_len, clip_fea, y):
     if getattr(self, "model_type", "t2v") == "i2v" or clip_fea is not None or y is not None:
         raise NotImplementedError("magcache_b200: only the t2v path is built (SURVEY §8f lists i2v/VACE as next)")
     if len(x) != 1 or len(context) != 1:
@@ -68,8 +68,19 @@ def _prologue(self, x, t, context, seq_len, clip_fea, y):
     assert n_tok <= seq_len  # reference: assert seq_lens.max() <= seq_len
     if n_tok != seq_len:
         raise NotImplementedError("magcache_b200: seq_len padding (sequence-parallel upstream) is not built; pass seq_len == token count")
-    x0, e, e0, ctx, grid = eng.prologue(lat.float(), t, context[0])
-    return eng, x0, e, e0, ctx, grid
+    eng.stage_inputs(lat, t, context[0])
+    return eng
+
+
+def _sync_slot_in(self, eng, slot):
+    """The reference keeps the cached residual in `self.residual_cache[slot]`; the engine keeps it in a fixed buffer that the
+    attribute aliases. If a caller replaced the attribute (or cleared it), follow the attribute."""
+    cur = self.residual_cache[slot]
+    if cur is None:
+        eng.res_valid[slot] = False
+    elif torch.is_tensor(cur) and cur.data_ptr() != eng.res[slot].data_ptr():
+        eng.res[slot].copy_(cur.reshape(eng.res[slot].shape))
+        eng.res_valid[slot] = True
 
 
 def magcache_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
@@ -78,24 +89,15 @@ def magcache_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
     Args / returns as the reference: x List[Tensor[C_in, F, H, W]], t Tensor[B], context List[Tensor[L, C]], seq_len int
     -> List[Tensor[C_out, F, H, W]] (float32).
     """
-    eng, x0, e, e0, ctx, grid = _prologue(self, x, t, context, seq_len, clip_fea, y)
+    eng = _stage(self, x, t, context, seq_len, clip_fea, y)
     ctrl = _controller(self)
     slot = self.cnt % 2
     skip_forward = ctrl.decide(self)  # :279-292 (float64 state under the reference's attribute names)
-    if skip_forward:
-        residual_x = self.residual_cache[slot]
-        if residual_x is None:
-            raise TypeError("magcache_b200: cache hit with an empty residual_cache slot (reference: Tensor + NoneType)")
-        # `x = x + residual_x` feeds only the head: the sum is formed inside the head kernel (same fp32 arithmetic)
-        out = eng.head(x0, e, grid, residual=residual_x.view(x0.shape))
-    else:
-        xs = eng.run_blocks(x0, e0, ctx, grid)  # :297-298
-        prev = self.residual_cache[slot]
-        buf = prev.view(x0.shape) if (torch.is_tensor(prev) and prev.numel() == xs.numel() and prev.dtype == torch.float32
-                                      and prev.device == xs.device) else None
-        residual_x = ops.residual_sub(xs, x0, out=buf).view(1, *x0.shape)  # :299
-        out = eng.head(xs, e, grid)
-    self.residual_cache[slot] = residual_x  # :301
+    _sync_slot_in(self, eng, slot)
+    # hit : `x = x + residual_x` (:295) feeds only the head, so the sum is formed inside the head kernel (same fp32 arithmetic)
+    # miss: block stack (:297-298), `residual_x = x - ori_x` (:299) written into the slot's buffer
+    out = eng.forward("hit" if skip_forward else "miss", slot)
+    self.residual_cache[slot] = eng.res[slot].view(1, *eng.res[slot].shape)  # :301
     ctrl.advance(self)  # :306-311
     return [out]
 
@@ -103,8 +105,9 @@ def magcache_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
 def magcache_calibration(self, x, t, context, seq_len, clip_fea=None, y=None):
     r"""MagCache4Wan2.1/magcache_generate.py:80-194: always runs the block stack and records, per forward, the token-mean
     magnitude ratio, its std and the cosine distance to the previous residual of the same CFG branch (one fused pass)."""
-    eng, x0, e, e0, ctx, grid = _prologue(self, x, t, context, seq_len, clip_fea, y)
-    xs = eng.run_blocks(x0, e0, ctx, grid)
+    eng = _stage(self, x, t, context, seq_len, clip_fea, y)
+    x0, e, e0, ctx = eng.prologue()
+    xs = eng.run_blocks(x0, e0, ctx, eng.grid)
     slot = self.cnt % 2
     if self.cnt >= 2:
         prev = self.residual_cache[slot].view(x0.shape)
@@ -120,7 +123,7 @@ def magcache_calibration(self, x, t, context, seq_len, clip_fea=None, y=None):
     else:
         residual_x = ops.residual_sub(xs, x0)
     self.residual_cache[slot] = residual_x.view(1, *x0.shape)
-    out = eng.head(xs, e, grid)
+    out = eng.head(xs, e, eng.grid)
     self.cnt += 1
     if self.cnt >= self.num_steps:
         self.cnt = 0

@@ -12,6 +12,7 @@ HBM layout per forward (N tokens, D model dim, F ffn dim; Wan2.1-1.3B at 832x480
 All buffers are allocated once per engine and reused by every forward (no allocator traffic in the loop).
 """
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -187,6 +188,11 @@ class WanEngine:
         # token-axis sharding (magcache_b200/shard.py): world 1 = single GPU
         self.world, self.rank, self.group = shard_world, shard_rank, shard_group
         self.shard = None
+        # CUDA-graph replay of the whole forward (one graph per {miss, hit} x CFG slot). On by default for sharded runs, where
+        # ~650 launches per ~40 ms forward would otherwise leave the GPU waiting for the host; MC_GRAPHS=0/1 overrides.
+        env = os.environ.get("MC_GRAPHS")
+        self.use_graphs = (shard_world > 1) if env is None else (env == "1")
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------ workspace
     def _workspace(self, n_total):
@@ -223,6 +229,12 @@ class WanEngine:
         self.ctx_h = torch.empty(d.text_len, D, **bf)
         self.ctx = torch.empty(d.text_len, D, **bf)
         self.em = torch.empty(6, D, dtype=torch.float32, device=dev)
+        # engine-owned residual cache storage (one slot per CFG branch) and staged inputs: fixed addresses for graph replay
+        self.res = [torch.empty(n, D, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.res_valid = [False, False]
+        self.s_t = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.s_lat = None
+        self._graphs = {}
         self._n = n_total
 
     def _rope_for(self, grid):
@@ -231,28 +243,76 @@ class WanEngine:
         return self._rope[grid]
 
     # ------------------------------------------------------------------------------------------ prologue (:229-275)
-    def prologue(self, latent, t, context):
-        """latent fp32 [C, F, H, W]; t tensor [1]; context [L<=512, text_dim]. Returns (x0 bf16 [N, D], e fp32 [1, D], e0 fp32 [6, D],
-        ctx bf16 [512, D], grid)."""
-        d, w = self.dims, self.w
+    def stage_inputs(self, latent, t, context):
+        """Copy one call's inputs into the engine's fixed buffers (outside any captured graph): latent fp32 [C, F, H, W],
+        t tensor [1], context [L <= text_len, text_dim] (zero-padded to text_len, cast to bf16 as autocast would)."""
+        d = self.dims
         C, Fr, H, W = latent.shape
-        grid = (Fr, H // 2, W // 2)
-        n = grid[0] * grid[1] * grid[2]
-        self._workspace(n)
-        tok = ops.patchify(latent.contiguous())
-        if self.shard is not None:
-            tok = self.shard.rows(tok)  # this rank embeds only its own tokens
-        ops.gemm(tok, w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
-        sin = ops.time_sinusoid(t.reshape(-1)[:1], d.freq_dim)
-        e = ops.linear_f32_small(ops.linear_f32_small(sin, w.time_w1, w.time_b1, act=2), w.time_w2, w.time_b2, act=0)
-        e0 = ops.linear_f32_small(e, w.tproj_w, w.tproj_b, act=1).view(6, d.dim)
+        self.grid = (Fr, H // 2, W // 2)
+        self._workspace(self.grid[0] * self.grid[1] * self.grid[2])
+        if self.s_lat is None or self.s_lat.shape != latent.shape:
+            self.s_lat = torch.empty(latent.shape, dtype=torch.float32, device=self.device)
+            self._graphs = {}
+        self.s_lat.copy_(latent)
+        self.s_t.copy_(t.reshape(-1)[:1])
         L = context.shape[0]
         assert L <= d.text_len and context.shape[1] == d.text_dim
         self.ctx_in.zero_()
-        self.ctx_in[:L].copy_(context)  # pad to text_len with zeros; autocast casts the Linear input to bf16
+        self.ctx_in[:L].copy_(context)
+
+    def prologue(self):
+        """Embeddings from the staged inputs. Returns (x0 bf16 [N_local, D], e fp32 [1, D], e0 fp32 [6, D], ctx bf16 [text_len, D])."""
+        d, w = self.dims, self.w
+        tok = ops.patchify(self.s_lat)
+        if self.shard is not None:
+            tok = self.shard.rows(tok)  # this rank embeds only its own tokens
+        ops.gemm(tok, w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
+        sin = ops.time_sinusoid(self.s_t, d.freq_dim)
+        e = ops.linear_f32_small(ops.linear_f32_small(sin, w.time_w1, w.time_b1, act=2), w.time_w2, w.time_b2, act=0)
+        e0 = ops.linear_f32_small(e, w.tproj_w, w.tproj_b, act=1).view(6, d.dim)
         ops.gemm(self.ctx_in, w.text_w1, w.text_b1, E.MC_EPI_BIAS_GELU_BF16, out=self.ctx_h)
         ops.gemm(self.ctx_h, w.text_w2, w.text_b2, E.MC_EPI_BIAS_BF16, out=self.ctx)
-        return self.x0, e, e0, self.ctx, grid
+        return self.x0, e, e0, self.ctx
+
+    # ------------------------------------------------------------------------------------------ one patched forward
+    def _body(self, kind, slot):
+        """prologue -> {hit: head(x0 + residual) | miss: block stack, residual = x - x0, head(x)} on the staged inputs."""
+        x0, e, e0, ctx = self.prologue()
+        if kind == "hit":
+            return self.head(x0, e, self.grid, residual=self.res[slot])  # `x + residual_x` formed inside the head kernel
+        xs = self.run_blocks(x0, e0, ctx, self.grid)
+        ops.residual_sub(xs, x0, out=self.res[slot])  # magcache_generate.py:299, written into the slot's fixed buffer
+        return self.head(xs, e, self.grid)
+
+    def forward(self, kind, slot):
+        """Run (or replay) one forward of the given kind for CFG slot `slot`; returns a fresh fp32 [C, F, H, W] tensor."""
+        if kind == "hit" and not self.res_valid[slot]:
+            raise TypeError("magcache_b200: cache hit with an empty residual_cache slot (reference: Tensor + NoneType)")
+        if not self.use_graphs:
+            out = self._body(kind, slot)
+        else:
+            key = (kind, slot)
+            st = self._graphs.get(key)
+            if st is None:  # first use: eager (sets kernel attributes, sizes the allocator pools)
+                out = self._body(kind, slot)
+                self._graphs[key] = "warm"
+            else:
+                if st == "warm":
+                    prof, ops.PROFILE = ops.PROFILE, None  # event records are not capturable
+                    n0 = ops.LAUNCHES
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        gout = self._body(kind, slot)
+                    ops.PROFILE = prof
+                    st = self._graphs[key] = (g, gout, ops.LAUNCHES - n0)
+                    ops.LAUNCHES = n0
+                g, gout, n_launch = st
+                g.replay()
+                ops._count(n_launch)
+                out = gout.clone()  # callers keep outputs across calls (cond is alive while uncond runs)
+        if kind == "miss":
+            self.res_valid[slot] = True
+        return out
 
     # ------------------------------------------------------------------------------------------ block stack (:297-298)
     def run_blocks(self, x0, e0, ctx, grid):
