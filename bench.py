@@ -354,7 +354,37 @@ def run_ours(args, rank, world):
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        shutdown_distributed(model)
+
+
+def shutdown_distributed(model):
+    """Leave cleanly and in bounded time: captured CUDA graphs hold NCCL work, and tearing the process group down under them
+    can block forever — drop the graphs first, and never wait more than a few seconds for the communicator to go away."""
+    import gc
+
+    import torch
+    import torch.distributed as dist
+    eng = getattr(model, "_mc_engine", None)
+    if eng is not None:
+        eng._graphs.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    done = threading.Event()
+
+    def _destroy():
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+        done.set()
+
+    th = threading.Thread(target=_destroy, daemon=True)
+    th.start()
+    done.wait(timeout=15)
+    os._exit(0)
 
 
 def bench_k1(dev, pk):
