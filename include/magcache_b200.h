@@ -39,6 +39,10 @@ int32_t mc_abi_version(void); /* bumped whenever a signature in this header chan
  * idx = round_half_even(arange(T) * (L-1)/(T-1)); T == 1 -> src[L-1]. `dst` has T entries. */
 int32_t mc_nearest_interp(const double* src, int32_t L, double* dst, int32_t T);
 
+/* Qwen-Image's variant (MagCache4QwenImage/magcache_generate.py:14-21): idx = round_half_even(np.linspace(0, L-1, T));
+ * L == T returns a copy; T == 1 picks src[0] (the Wan form picks src[L-1]). */
+int32_t mc_nearest_interp_linspace(const double* src, int32_t L, double* dst, int32_t T);
+
 /* Per-CFG-branch form used by Wan (magcache_generate.py:915-919): de-interleave [0::2]/[1::2], interpolate each
  * to `steps`, re-interleave. src has 2*L_half entries, dst 2*steps entries. */
 int32_t mc_nearest_interp_cfg(const double* src, int32_t L_total, double* dst, int32_t steps);
@@ -49,6 +53,10 @@ int32_t mc_nearest_interp_cfg(const double* src, int32_t L_total, double* dst, i
 #define MC_RETAIN_FLOOR 0      /* cnt >= int(num_steps*R)       Wan :279, Hunyuan :90 */
 #define MC_RETAIN_HALF_UP 1    /* cnt >= int(R*num_steps + 0.5) FLUX :327 */
 #define MC_RETAIN_CEIL 2       /* cnt >= ceil(R*num_steps)      OmniGen2 magcache_utils.py:343 */
+/* Wan2.2 two-expert windows, MagCache4Wan2.2/magcache_generate.py:294-303 (split_step = 2*high_noise_steps, cnt spans both experts).
+ * The reference keeps cnt in an int64 torch tensor, so its `cnt <= python_float` comparison happens in float32: reproduced. */
+#define MC_RETAIN_WAN22_T2V 3  /* skip-disabled if cnt < int(split*R) or (split <= cnt <= (n-split)*R + split) */
+#define MC_RETAIN_WAN22_I2V 4  /* skip-disabled if cnt < int(split + (n-split)*R) */
 
 typedef struct mc_ctrl_config {
   int32_t num_steps;       /* forward calls per video: 2*sample_steps for CFG models (Wan :899), steps otherwise */
@@ -58,7 +66,7 @@ typedef struct mc_ctrl_config {
   int32_t retention_mode;  /* MC_RETAIN_* */
   int32_t veto_index;      /* -1 = none. FLUX :332: never skip when round_half_even(cnt*((veto_base-1)/(num_steps-1))) == veto_index */
   int32_t veto_base;       /* 28 for FLUX */
-  int32_t reserved;
+  int32_t split_step;      /* MC_RETAIN_WAN22_*: calls made to the high-noise expert per video (2*high_noise_steps); else unused */
   double thresh;           /* magcache_thresh */
   double retention_ratio;
   const double* mag_ratios; /* [num_steps], already interpolated; borrowed for the duration of the call / handle */

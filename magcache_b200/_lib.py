@@ -14,7 +14,7 @@ MC_OK = 0
 MC_ERR_INVALID, MC_ERR_CUDA, MC_ERR_STATE = -1, -2, -3
 MC_F32, MC_BF16 = 0, 1
 MC_CMP_LT, MC_CMP_LE = 0, 1
-MC_RETAIN_FLOOR, MC_RETAIN_HALF_UP, MC_RETAIN_CEIL = 0, 1, 2
+MC_RETAIN_FLOOR, MC_RETAIN_HALF_UP, MC_RETAIN_CEIL, MC_RETAIN_WAN22_T2V, MC_RETAIN_WAN22_I2V = 0, 1, 2, 3, 4
 MC_EPI_BIAS_BF16, MC_EPI_BIAS_GELU_BF16, MC_EPI_BIAS_GATE_RESID, MC_EPI_ROWBIAS_BF16, MC_EPI_BIAS_F32 = 0, 1, 2, 3, 4
 
 
@@ -26,7 +26,7 @@ class MagCacheError(RuntimeError):
 
 class CtrlConfig(Structure):
     _fields_ = [("num_steps", c_int32), ("branches", c_int32), ("K", c_int32), ("cmp", c_int32), ("retention_mode", c_int32),
-                ("veto_index", c_int32), ("veto_base", c_int32), ("reserved", c_int32), ("thresh", c_double),
+                ("veto_index", c_int32), ("veto_base", c_int32), ("split_step", c_int32), ("thresh", c_double),
                 ("retention_ratio", c_double), ("mag_ratios", POINTER(c_double))]
 
 
@@ -41,6 +41,7 @@ SIGNATURES = {
     "mc_abi_version": [],
     "mc_nearest_interp": [POINTER(c_double), c_int32, POINTER(c_double), c_int32],
     "mc_nearest_interp_cfg": [POINTER(c_double), c_int32, POINTER(c_double), c_int32],
+    "mc_nearest_interp_linspace": [POINTER(c_double), c_int32, POINTER(c_double), c_int32],
     "mc_ctrl_decide": [POINTER(CtrlConfig), POINTER(CtrlState), POINTER(c_int32)],
     "mc_ctrl_advance": [POINTER(CtrlConfig), POINTER(CtrlState)],
     "mc_ctrl_mask": [POINTER(CtrlConfig), c_int32, POINTER(c_uint8)],

@@ -8,13 +8,14 @@ from . import _lib
 from ._lib import CtrlConfig, CtrlState, check, lib
 
 
-def make_ctrl_config(num_steps, thresh, K, retention_ratio, mag_ratios, branches, cmp, retention_mode, veto_index=-1, veto_base=0):
+def make_ctrl_config(num_steps, thresh, K, retention_ratio, mag_ratios, branches, cmp, retention_mode, veto_index=-1, veto_base=0,
+                     split_step=0):
     arr = np.ascontiguousarray(mag_ratios, dtype=np.float64)
     if len(arr) < num_steps:
         raise IndexError(f"mag_ratios has {len(arr)} entries but num_steps={num_steps} (interpolate first, magcache_generate.py:915-919)")
     cfg = CtrlConfig()
     cfg.num_steps, cfg.branches, cfg.K, cfg.cmp, cfg.retention_mode = int(num_steps), int(branches), int(K), int(cmp), int(retention_mode)
-    cfg.veto_index, cfg.veto_base = int(veto_index), int(veto_base)
+    cfg.veto_index, cfg.veto_base, cfg.split_step = int(veto_index), int(veto_base), int(split_step)
     cfg.thresh, cfg.retention_ratio = float(thresh), float(retention_ratio)
     cfg.mag_ratios = arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
     cfg._keepalive = arr

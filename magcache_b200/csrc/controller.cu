@@ -33,7 +33,7 @@ int num_sms() {
   return cached;
 }
 
-// first call index that is allowed to skip
+// first call index that is allowed to skip (single-threshold modes)
 static int32_t retention_start(const mc_ctrl_config* c) {
   const double n = static_cast<double>(c->num_steps);
   switch (c->retention_mode) {
@@ -46,13 +46,32 @@ static int32_t retention_start(const mc_ctrl_config* c) {
   }
 }
 
+// `use_magcache` of the reference: may this call consult the controller at all?
+static bool eligible(const mc_ctrl_config* c, int32_t cnt) {
+  const double n = static_cast<double>(c->num_steps), sp = static_cast<double>(c->split_step), R = c->retention_ratio;
+  switch (c->retention_mode) {
+    case MC_RETAIN_WAN22_I2V:  // MagCache4Wan2.2/magcache_generate.py:295-297
+      return !(cnt < static_cast<int32_t>(sp + (n - sp) * R));
+    case MC_RETAIN_WAN22_T2V: {  // :298-300 ; `tensor(int64) <= python float` compares in float32
+      const bool early = cnt < static_cast<int32_t>(sp * R);
+      const float upper = static_cast<float>((n - sp) * R + sp);
+      const bool window = (static_cast<float>(cnt) <= upper) && (cnt >= c->split_step);
+      return !(early || window);
+    }
+    default:
+      return cnt >= retention_start(c);
+  }
+}
+
 static int32_t check_cfg(const mc_ctrl_config* c) {
   MC_CHECK_ARG(c != nullptr, "mc_ctrl: null config");
   MC_CHECK_ARG(c->num_steps >= 1, "mc_ctrl: num_steps=%d must be >= 1", c->num_steps);
   MC_CHECK_ARG(c->branches == 1 || c->branches == 2, "mc_ctrl: branches=%d must be 1 or 2", c->branches);
   MC_CHECK_ARG(c->mag_ratios != nullptr, "mc_ctrl: mag_ratios is null (reference: AttributeError, no table matched ckpt_dir)");
   MC_CHECK_ARG(c->cmp == MC_CMP_LT || c->cmp == MC_CMP_LE, "mc_ctrl: bad cmp %d", c->cmp);
-  MC_CHECK_ARG(c->retention_mode >= 0 && c->retention_mode <= 2, "mc_ctrl: bad retention_mode %d", c->retention_mode);
+  MC_CHECK_ARG(c->retention_mode >= 0 && c->retention_mode <= 4, "mc_ctrl: bad retention_mode %d", c->retention_mode);
+  MC_CHECK_ARG(c->retention_mode < MC_RETAIN_WAN22_T2V || (c->split_step >= 0 && c->split_step <= c->num_steps),
+               "mc_ctrl: split_step=%d outside [0, num_steps]", c->split_step);
   MC_CHECK_ARG(c->veto_index < 0 || c->num_steps >= 2, "mc_ctrl: step veto needs num_steps >= 2 (reference divides by num_steps-1)");
   return MC_OK;
 }
@@ -64,7 +83,7 @@ static inline void reset_branch(mc_ctrl_state* st, int i) {
 }
 
 static int32_t decide(const mc_ctrl_config* c, mc_ctrl_state* st) {
-  if (st->cnt < retention_start(c)) return 0;
+  if (!eligible(c, st->cnt)) return 0;
   const int i = (c->branches == 2) ? (st->cnt % 2) : 0;
   const double cur = c->mag_ratios[st->cnt];
   st->accumulated_ratio[i] = st->accumulated_ratio[i] * cur;
@@ -111,6 +130,25 @@ int32_t mc_nearest_interp(const double* src, int32_t L, double* dst, int32_t T) 
   for (int32_t i = 0; i < T; ++i) {
     const long idx = static_cast<long>(std::nearbyint(static_cast<double>(i) * scale));  // np.round: half to even
     MC_CHECK_ARG(idx >= 0 && idx < L, "mc_nearest_interp: index %ld out of range", idx);
+    dst[i] = src[idx];
+  }
+  return MC_OK;
+}
+
+int32_t mc_nearest_interp_linspace(const double* src, int32_t L, double* dst, int32_t T) {
+  MC_CHECK_ARG(src && dst, "mc_nearest_interp_linspace: null pointer");
+  MC_CHECK_ARG(L >= 1 && T >= 1, "mc_nearest_interp_linspace: L=%d T=%d must be >= 1", L, T);
+  if (L == T) {
+    for (int32_t i = 0; i < T; ++i) dst[i] = src[i];
+    return MC_OK;
+  }
+  // np.linspace(0, L-1, T): arange(T) * ((L-1)/(T-1)) + 0 with the last sample forced to L-1; T == 1 -> [0.]
+  const double step = (T > 1) ? static_cast<double>(L - 1) / static_cast<double>(T - 1) : 0.0;
+  for (int32_t i = 0; i < T; ++i) {
+    double pos = static_cast<double>(i) * step;
+    if (T > 1 && i == T - 1) pos = static_cast<double>(L - 1);
+    const long idx = static_cast<long>(std::nearbyint(pos));
+    MC_CHECK_ARG(idx >= 0 && idx < L, "mc_nearest_interp_linspace: index %ld out of range", idx);
     dst[i] = src[idx];
   }
   return MC_OK;
@@ -171,7 +209,8 @@ int32_t mc_ctrl_mask(const mc_ctrl_config* cfg, int32_t calls, uint8_t* mask) {
 int32_t mc_ctrl_validate(const mc_ctrl_config* cfg) {
   int32_t rc = mc::check_cfg(cfg);
   if (rc) return rc;
-  const int32_t start = mc::retention_start(cfg);
+  int32_t start = 0;
+  while (start < cfg->num_steps && !mc::eligible(cfg, start)) ++start;
   if (start < cfg->branches) {
     mc::set_error(
         "mc_ctrl_validate: first skip-eligible call is %d but %d residual slot(s) must be filled first "

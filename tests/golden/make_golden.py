@@ -33,6 +33,9 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 WAN = f"{REF}/MagCache4Wan2.1/magcache_generate.py"
 FLUX = f"{REF}/MagCache4FLUX/magcache_flux.py"
 HUN = f"{REF}/MagCache4HunyuanVideo/magcache_sample_video.py"
+WAN22 = f"{REF}/MagCache4Wan2.2/magcache_generate.py"
+QWEN = f"{REF}/MagCache4QwenImage/magcache_generate.py"
+OMNI = f"{REF}/MagCache4OmniGen2/magcache/magcache_utils.py"
 
 
 def _tree(path):
@@ -202,6 +205,122 @@ def calib_cases():
     return cases
 
 
+# ----------------------------------------------------------------------------------------------
+# "next" adapters: Wan2.2 expert windows, Qwen's linspace interpolation, OmniGen2's ceil/initial state
+# ----------------------------------------------------------------------------------------------
+def wan22_tables():
+    """The three `mag_ratios = [...]` list literals of MagCache4Wan2.2/magcache_generate.py (:695 t2v-A14B, :736/:738 ti2v-5B
+    (two resolutions), :771 i2v-A14B); the script prepends [1.0]*2 in init_magcache (:356)."""
+    out = {}
+    names = {695: "wan2.2_t2v_a14b", 736: "wan2.2_ti2v_5b_a", 738: "wan2.2_ti2v_5b_b", 771: "wan2.2_i2v_a14b"}
+    for n in ast.walk(_tree(WAN22)):
+        if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Name) and n.targets[0].id == "mag_ratios" \
+                and isinstance(n.value, ast.List) and n.lineno in names:
+            vals = eval(compile(ast.Expression(n.value), "<tbl>", "eval"))
+            out[names[n.lineno]] = {"source": f"MagCache4Wan2.2/magcache_generate.py:{n.lineno} (+ [1.0]*2 prefix, :356)",
+                                    "values": [1.0, 1.0] + [float(v) for v in vals]}
+    assert len(out) == 4, out.keys()
+    return out
+
+
+class RefControllerWan22:
+    """Statements :290-317 (use_magcache window + controller) and :328-334 (counter) of MagCache4Wan2.2 magcache_forward."""
+
+    def __init__(self):
+        body = _func(_tree(WAN22), "magcache_forward").body
+        i0 = next(i for i, s in enumerate(body) if isinstance(s, ast.Assign) and getattr(s.targets[0], "id", None) == "use_magcache")
+        i1 = next(i for i, s in enumerate(body) if isinstance(s, ast.If) and isinstance(s.test, ast.Name) and s.test.id == "use_magcache")
+        stmts = [s for s in body[i0:i1 + 1] if not (isinstance(s, ast.Assign) and getattr(s.targets[0], "id", None) == "ori_x")]
+        self.ctrl = _compile(stmts)
+        tail = []
+        for i, s in enumerate(body):
+            if isinstance(s, ast.AugAssign) and isinstance(s.target, ast.Attribute) and s.target.attr == "cnt":
+                tail = [s, body[i + 1]]
+        self.tail = _compile(tail)
+
+    def call(self, state):
+        env = {"self": state, "np": np}
+        exec(self.ctrl, env)
+        skip = bool(env["skip_forward"])
+        exec(self.tail, env)
+        return skip
+
+
+def wan22_state(table, steps, thresh, K, R, interp, split_steps, mode):
+    import torch
+    s = wan_state(table, steps, thresh, K, R, interp)
+    s.cnt = torch.tensor(0)  # as init_magcache does (:342): comparisons against Python floats then run in float32
+    s.split_step = None if split_steps is None else split_steps * 2
+    s.mode = mode
+    return s
+
+
+def qwen_nearest_interp():
+    fn = _func(_tree(QWEN), "nearest_interp")
+    env = {"np": np}
+    exec(_compile([fn]), env)
+    return env["nearest_interp"]
+
+
+class RefControllerOmni:
+    """OmniGen2 keeps the state in a `magcache_params` object; statements magcache_utils.py:342-354."""
+
+    def __init__(self):
+        fn = _func(_tree(OMNI), "magcache_forward")
+        ctrl = [s for s in ast.walk(fn) if isinstance(s, ast.If) and _mentions(s.test, "retention_ratio")]
+        assert len(ctrl) == 1
+        self.ctrl = _compile(ctrl)
+
+    def call(self, state):
+        import math
+        env = {"self": state, "np": np, "math": math, "skip_forward": False}
+        exec(self.ctrl, env)
+        return bool(env["skip_forward"])
+
+
+def extra_cases(tables, interp):
+    out = {"tables": wan22_tables(), "wan22_masks": [], "qwen_interp": [], "omnigen2_masks": []}
+    ref = RefControllerWan22()
+    for key, mode, has_split in [("wan2.2_t2v_a14b", "t2v", True), ("wan2.2_i2v_a14b", "i2v", True), ("wan2.2_ti2v_5b_a", "t2v", False)]:
+        tbl = out["tables"][key]["values"]
+        for steps in (len(tbl) // 2, 30, 25):
+            for hs in ((None,) if not has_split else (steps // 4, steps // 3, steps // 2, (2 * steps) // 3)):
+                for thresh, K, R in [(0.12, 2, 0.2), (0.06, 2, 0.2), (0.12, 4, 0.4), (0.24, 6, 0.1), (0.12, 2, 0.25), (0.12, 3, 1.0 / 3.0)]:
+                    st = wan22_state(tbl, steps, thresh, K, R, interp, hs, mode)
+                    n = 2 * steps * 2 + 5
+                    m = run_mask(ref, st, n)
+                    out["wan22_masks"].append({"table": key, "mode": mode if has_split else "ti2v", "steps": steps, "high_noise_steps": hs,
+                                               "thresh": thresh, "K": K, "R": R, "calls": n, "mask": "".join(map(str, m)),
+                                               "final": {"cnt": int(st.cnt), "accumulated_err": [float(v) for v in st.accumulated_err],
+                                                         "accumulated_ratio": [float(v) for v in st.accumulated_ratio],
+                                                         "accumulated_steps": [float(v) for v in st.accumulated_steps]}})
+    qi = qwen_nearest_interp()
+    for L, T in [(50, 50), (50, 40), (50, 1), (50, 2), (28, 20), (9, 5), (5, 3), (101, 41), (3, 7), (60, 50), (2, 2), (7, 1)]:
+        src = np.arange(L, dtype=np.float64) * 1.25 + 0.5
+        out["qwen_interp"].append({"L": L, "T": T, "src": [float(v) for v in src], "out": [float(v) for v in qi(src, T)]})
+    omni = RefControllerOmni()
+    import importlib.util  # MAG_RATIOS literal dict of magcache_utils.py:14-20
+    omni_tbls = {}
+    for n in ast.walk(_tree(OMNI)):
+        if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", None) == "MAG_RATIOS":
+            omni_tbls = {k: [float(v) for v in arr] for k, arr in eval(compile(ast.Expression(n.value), "<t>", "eval"), {"np": np}).items()}
+    out["tables"].update({f"omnigen2_{k}": {"source": "MagCache4OmniGen2/magcache/magcache_utils.py:14-20", "values": v} for k, v in omni_tbls.items()})
+    for key, tbl in omni_tbls.items():
+        for steps in (len(tbl), 30):
+            for thresh, K, R in [(0.06, 3, 0.2), (0.12, 3, 0.25), (0.04, 2, 0.33)]:
+                mr = np.array(tbl) if len(tbl) == steps else interp(np.array(tbl), steps)
+                params = types.SimpleNamespace(mag_ratios=mr, previous_residual="r", accumulated_ratio=1.0, accumulated_err=0.0,
+                                               accumulated_steps=3, cnt=0)  # dataclass defaults, magcache_utils.py:41-45
+                st = types.SimpleNamespace(magcache_params=params, retention_ratio=R, num_steps=steps, magcache_thresh=thresh, K=K)
+                mask = []
+                for c in range(steps):  # the sampler owns cnt (magcache_utils.py:435-513): advance it here
+                    params.cnt = c
+                    mask.append(1 if omni.call(st) else 0)
+                out["omnigen2_masks"].append({"table": f"omnigen2_{key}", "steps": steps, "thresh": thresh, "K": K, "R": R,
+                                              "initial_accumulated_steps": 3, "mask": "".join(map(str, mask))})
+    return out
+
+
 def main():
     tables = extract_tables()
     with open(f"{OUT}/tables.json", "w") as f:
@@ -261,6 +380,11 @@ def main():
     for c in masks:
         if c["table"] == "wan2.1_t2v_1.3b" and c["steps"] == 50 and c["R"] == 0.2 and c["thresh"] in (0.12, 0.24):
             print(c["thresh"], c["K"], c["skipped_first_video"], c["mask"][0:100:2])
+
+    extra = extra_cases(tables, interp)
+    with open(f"{OUT}/extra_adapters.json", "w") as f:
+        json.dump(extra, f, indent=0)
+    print("extra adapters:", {k: len(v) for k, v in extra.items()})
 
     cal = calib_cases()
     with open(f"{OUT}/calib_stats.json", "w") as f:
