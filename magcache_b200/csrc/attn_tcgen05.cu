@@ -36,6 +36,7 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct AttnParams {
   int Lq, Lk, heads;
+  int stagger_cycles, stagger_lo, stagger_hi;  // CTAs with linear id in [lo, hi) start their softmax this many cycles late
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* out;
   int64_t ldo;
@@ -44,10 +45,7 @@ struct AttnParams {
 // P_IN_TMEM: the bf16 probabilities are written back into the (already consumed) S columns of TMEM with tcgen05.st and the
 // PV MMA takes its A operand from TMEM — no smem round trip, no generic->async proxy fence, and P is double-buffered for free
 // (it lives in S buffer j&1), which removes the write-P -> PV -> pv_done -> write-next-P serialisation of the smem variant.
-// VARIANT 0: P through shared memory. 1: P in TMEM. 2: P in TMEM + speculative softmax: the exponentials of tile j are computed
-// against the running max of tiles < j while the tile's own max is still being reduced and the second half of S is still in
-// flight from TMEM; a tile whose max would have grown by more than the rescale threshold (rare after the first tiles) is redone.
-template <int VARIANT>
+template <bool P_IN_TMEM>
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
@@ -64,8 +62,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   uint64_t* pv_done = bars + 14;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
-  constexpr bool P_IN_TMEM = VARIANT >= 1;
-  constexpr bool SPECULATIVE = VARIANT == 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ;
   const int head = blockIdx.y;
@@ -176,123 +172,108 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     float m = -INFINITY, l = 0.f;
     uint8_t* p_row = smem + kOffP + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
+    // Two CTAs share each SM's MUFU and tensor pipes. Started together they stay in lock-step (both in their exp phase,
+    // then both in their load/max/store phase) and each unit idles half the time; the CTAs of the second residency slot
+    // (linear ids [#SM, 2*#SM) of the first wave) therefore start half a tile period late. Every later CTA inherits the
+    // offset because it starts when its predecessor on that slot retires.
+    {
+      const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+      if (lin >= p.stagger_lo && lin < p.stagger_hi && p.stagger_cycles > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.stagger_cycles) {
+        }
+      }
+    }
 
-    const uint64_t scale2 = ptx::pack_f32x2(p.scale_log2, p.scale_log2);
     for (int j = 0; j < n_tiles; ++j) {
       const int b = j & 1;
       ptx::mbar_wait(&s_full[b], (j >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t s_addr = tmem_base + lane_sel + b * kBKV;
-      const int valid = p.Lk - j * kBKV;  // columns >= valid are padding (only possible on the last tile)
       uint32_t sreg[2][32];
-      uint32_t packed[32];
-      uint64_t sum2a = 0ull, sum2b = 0ull;  // (+0.f, +0.f) pairs
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV, sreg[0]);
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV + 32, sreg[1]);
+      ptx::tmem_ld_wait();
+      if (!P_IN_TMEM) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&s_free[b]);
+      }
 
-      // P = 2^(s*scale - m) for 32 columns: one FFMA2 + two MUFU.EX2 + one FADD2 + one bf16x2 pack per pair of elements,
-      // row sum in fp32 before the bf16 rounding (as flash-attention does); optionally the 3-input running max alongside.
-      auto chunk = [&](const uint32_t (&sv)[32], uint32_t* pk, uint64_t negm2, bool with_max) {
+      const int valid = p.Lk - j * kBKV;  // columns >= valid are padding (only possible on the last tile)
+      if (valid < kBKV) {                  // warp-uniform, taken at most once per CTA
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (h * 32 + c >= valid) sreg[h][c] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains of 3-input max: 0.5 instruction per element
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          const float x0 = __uint_as_float(sv[c]), x1 = __uint_as_float(sv[c + 1]), x2 = __uint_as_float(sv[c + 2]), x3 = __uint_as_float(sv[c + 3]);
-          if (with_max) {
-            mx0 = ptx::max3(mx0, x0, x1);
-            mx1 = ptx::max3(mx1, x2, x3);
+          mx0 = ptx::max3(mx0, __uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1]));
+          mx1 = ptx::max3(mx1, __uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3]));
+        }
+      const float mx = fmaxf(mx0, mx1);
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      bool waited = false;
+      if (j == 0) {
+        m = m_new;
+      } else {
+        const bool need = m_new > m + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // O must be quiescent: PV(j-1) complete
+          ptx::mbar_wait(pv_done, (j - 1) & 1);
+          ptx::tc_fence_after();
+          waited = true;
+          const float factor = need ? ptx::ex2_approx(m - m_new) : 1.0f;
+          if (need) {
+            l *= factor;
+            m = m_new;
           }
+#pragma unroll 1
+          for (int c = 0; c < kHD / 32; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld_32x32b_x32(tmem_o + lane_sel + c * 32, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            ptx::tmem_st_32x32b_x32(tmem_o + lane_sel + c * 32, o);
+          }
+          ptx::tmem_st_wait();
+        }
+      }
+      // P = 2^(s*scale - m), row sum in fp32 before the bf16 rounding (as flash-attention does).
+      // Packed fp32x2 FMA / ADD: one FFMA2 + two MUFU.EX2 + one FADD2 + one bf16x2 pack per pair of elements.
+      const uint64_t scale2 = ptx::pack_f32x2(p.scale_log2, p.scale_log2);
+      const uint64_t negm2 = ptx::pack_f32x2(-m, -m);
+      uint64_t sum2a = 0ull, sum2b = 0ull;  // (+0.f, +0.f)
+      uint32_t packed[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
           float a0, a1, b0, b1;
-          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(x0, x1), scale2, negm2), a0, a1);
-          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(x2, x3), scale2, negm2), b0, b1);
+          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1])), scale2, negm2), a0, a1);
+          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3])), scale2, negm2), b0, b1);
           a0 = ptx::ex2_approx(a0);
           a1 = ptx::ex2_approx(a1);
           b0 = ptx::ex2_approx(b0);
           b1 = ptx::ex2_approx(b1);
           sum2a = ptx::add_f32x2(sum2a, ptx::pack_f32x2(a0, a1));
           sum2b = ptx::add_f32x2(sum2b, ptx::pack_f32x2(b0, b1));
-          pk[c >> 1] = pack_bf16x2(a0, a1);
-          pk[(c >> 1) + 1] = pack_bf16x2(b0, b1);
+          packed[h * 16 + (c >> 1)] = pack_bf16x2(a0, a1);
+          packed[h * 16 + (c >> 1) + 1] = pack_bf16x2(b0, b1);
         }
-      };
-      auto row_max_only = [&]() {
-        mx0 = mx1 = -INFINITY;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            mx0 = ptx::max3(mx0, __uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1]));
-            mx1 = ptx::max3(mx1, __uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3]));
-          }
-      };
-
-      bool exact_pass = true;  // compute max first, then the exponentials (always for tile 0, the padded tile and VARIANT < 2)
-      ptx::tmem_ld_32x32b_x32(s_addr, sreg[0]);
-      if (SPECULATIVE && j > 0 && valid >= kBKV) {
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x32(s_addr + 32, sreg[1]);  // second half in flight while the first is exponentiated
-        const uint64_t negm2 = ptx::pack_f32x2(-m, -m);
-        chunk(sreg[0], packed, negm2, true);
-        ptx::tmem_ld_wait();
-        chunk(sreg[1], packed + 16, negm2, true);
-        const float m_new = fmaxf(m, fmaxf(mx0, mx1) * p.scale_log2);
-        exact_pass = __any_sync(0xffffffffu, m_new > m + kRescaleThreshold);  // rare: redo this tile with the new max
-      } else {
-        ptx::tmem_ld_32x32b_x32(s_addr + 32, sreg[1]);
-        ptx::tmem_ld_wait();
-      }
-      if (!P_IN_TMEM) {
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&s_free[b]);
-      }
-
-      bool waited = false;
-      if (exact_pass) {
-        if (valid < kBKV) {  // warp-uniform, taken at most once per CTA
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (h * 32 + c >= valid) sreg[h][c] = 0xff800000u;  // -inf
-        }
-        row_max_only();
-        const float m_new = fmaxf(m, fmaxf(mx0, mx1) * p.scale_log2);
-        if (j == 0) {
-          m = m_new;
-        } else {
-          const bool need = m_new > m + kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {
-            // O must be quiescent: PV(j-1) complete
-            ptx::mbar_wait(pv_done, (j - 1) & 1);
-            ptx::tc_fence_after();
-            waited = true;
-            const float factor = need ? ptx::ex2_approx(m - m_new) : 1.0f;
-            if (need) {
-              l *= factor;
-              m = m_new;
-            }
-#pragma unroll 1
-            for (int c = 0; c < kHD / 32; ++c) {
-              uint32_t o[32];
-              ptx::tmem_ld_32x32b_x32(tmem_o + lane_sel + c * 32, o);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-              ptx::tmem_st_32x32b_x32(tmem_o + lane_sel + c * 32, o);
-            }
-            ptx::tmem_st_wait();
-          }
-        }
-        const uint64_t negm2 = ptx::pack_f32x2(-m, -m);
-        sum2a = sum2b = 0ull;
-        chunk(sreg[0], packed, negm2, false);
-        chunk(sreg[1], packed + 16, negm2, false);
-      }
       float s0, s1, s2, s3;
       ptx::unpack_f32x2(sum2a, s0, s1);
       ptx::unpack_f32x2(sum2b, s2, s3);
-      l += (s0 + s1) + (s2 + s3);
+      const float psum = (s0 + s1) + (s2 + s3);
+      l += psum;
       if (P_IN_TMEM) {
         // P_j overwrites the first 32 columns of S buffer b (64 bf16 per row = 32 packed words); its reader PV(j) is ordered
         // before S(j+2) by the tensor pipe, so nothing else has to be waited for here
-        ptx::tmem_st_32x32b_x32(s_addr, packed);
+        ptx::tmem_st_32x32b_x32(tmem_base + lane_sel + b * kBKV, packed);
         ptx::tmem_st_wait();
       } else {
         if (j > 0 && !waited) {
@@ -356,25 +337,28 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
   if (rc) return rc;
   rc = mc::make_tmap_bf16_2d(&tv, vt, static_cast<uint64_t>(width), static_cast<uint64_t>(Lk), static_cast<uint64_t>(ldvt), mc::kHD, mc::kBKV);
   if (rc) return rc;
-  static int variant = -1;  // MC_ATTN_VARIANT: 0 = P via smem, 1 = P in TMEM, 2 = P in TMEM + speculative softmax (default)
+  static int variant = -1;  // 1: P in TMEM (default), 0: P through shared memory (MC_ATTN_P_SMEM=1, kept for A/B measurements)
   if (variant < 0) {
-    const char* ev = getenv("MC_ATTN_VARIANT");
-    int v = (ev && ev[0] >= '0' && ev[0] <= '2') ? (ev[0] - '0') : 2;
-    cudaError_t e = cudaFuncSetAttribute(mc::attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e != cudaSuccess) return mc::cuda_fail(e, "cudaFuncSetAttribute(attn smem)");
-    variant = v;
+    const char* ev = getenv("MC_ATTN_P_SMEM");
+    variant = (ev && ev[0] == '1') ? 0 : 1;
+    cudaError_t e = cudaFuncSetAttribute(mc::attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    if (e != cudaSuccess) {
+      variant = -1;
+      return mc::cuda_fail(e, "cudaFuncSetAttribute(attn smem)");
+    }
   }
-  mc::AttnParams p{Lq, Lk, heads, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo};
+  static int stagger = -1;
+  if (stagger < 0) {
+    const char* ev = getenv("MC_ATTN_STAGGER");
+    stagger = ev ? atoi(ev) : 520;
+  }
+  mc::AttnParams p{Lq, Lk, heads, stagger, mc::num_sms(), 2 * mc::num_sms(), scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo};
   dim3 grid((Lq + mc::kBQ - 1) / mc::kBQ, heads);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (variant == 2)
-    mc::attn_fwd_kernel<2><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
-  else if (variant == 1)
-    mc::attn_fwd_kernel<1><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
+  if (variant == 1)
+    mc::attn_fwd_kernel<true><<<grid, mc::kAttnThreads, mc::kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   else
-    mc::attn_fwd_kernel<0><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
+    mc::attn_fwd_kernel<false><<<grid, mc::kAttnThreads, mc::kAttnSmem, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   MC_CHECK_LAUNCH("attn_fwd_kernel launch");
   return MC_OK;
 }
