@@ -44,9 +44,9 @@ struct AttnParams {
 // P_IN_TMEM: the bf16 probabilities are written back into the (already consumed) S columns of TMEM with tcgen05.st and the
 // PV MMA takes its A operand from TMEM — no smem round trip, no generic->async proxy fence, and P is double-buffered for free
 // (it lives in S buffer j&1), which removes the write-P -> PV -> pv_done -> write-next-P serialisation of the smem variant.
-// VARIANT 2 (default) additionally software-pipelines the softmax warps across tiles: while tile j is being exponentiated
-// (MUFU-bound), S of tile j+1 is fetched from TMEM and its row max is reduced in the shadow of the last exponentials, so
-// the latency chain wait -> tcgen05.ld -> max no longer sits between two exp phases.
+// VARIANT 0: P through shared memory (kept for A/B measurements); VARIANT 1 (default): P in TMEM.
+// Tried and dropped in round 1 (profiles/r01_attention_experiments.md): speculative exponentials against the running max,
+// cross-tile software pipelining of the softmax warps, staggered start of the second residency slot.
 template <int VARIANT>
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -175,136 +175,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     float m = -INFINITY, l = 0.f;
     uint8_t* p_row = smem + kOffP + (r >> 3) * 1024 + (r & 7) * 128;
     const int sw = r & 7;
-    if (VARIANT == 2) {
-      const uint64_t scale2 = ptx::pack_f32x2(p.scale_log2, p.scale_log2);
-      uint32_t sa[2][32], sb[2][32];
-      uint64_t sum2a, sum2b;
-      float mx0, mx1;
-      // exponentials of `n` columns (multiple of 4): FFMA2 + 2 MUFU.EX2 + FADD2 + bf16x2 pack per pair; optionally the
-      // 3-input max of 2n columns of the NEXT tile rides along (two FMNMX3 per four exponentials)
-      auto exps = [&](const uint32_t* sv, int n, uint32_t* pk, uint64_t negm2, const uint32_t* nx) {
-#pragma unroll
-        for (int c = 0; c < n; c += 4) {
-          if (nx != nullptr) {
-            mx0 = ptx::max3(mx0, __uint_as_float(nx[2 * c]), __uint_as_float(nx[2 * c + 1]));
-            mx1 = ptx::max3(mx1, __uint_as_float(nx[2 * c + 2]), __uint_as_float(nx[2 * c + 3]));
-            mx0 = ptx::max3(mx0, __uint_as_float(nx[2 * c + 4]), __uint_as_float(nx[2 * c + 5]));
-            mx1 = ptx::max3(mx1, __uint_as_float(nx[2 * c + 6]), __uint_as_float(nx[2 * c + 7]));
-          }
-          float a0, a1, b0, b1;
-          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), scale2, negm2), a0, a1);
-          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3])), scale2, negm2), b0, b1);
-          a0 = ptx::ex2_approx(a0);
-          a1 = ptx::ex2_approx(a1);
-          b0 = ptx::ex2_approx(b0);
-          b1 = ptx::ex2_approx(b1);
-          sum2a = ptx::add_f32x2(sum2a, ptx::pack_f32x2(a0, a1));
-          sum2b = ptx::add_f32x2(sum2b, ptx::pack_f32x2(b0, b1));
-          pk[c >> 1] = pack_bf16x2(a0, a1);
-          pk[(c >> 1) + 1] = pack_bf16x2(b0, b1);
-        }
-      };
-      auto mask_tail = [&](uint32_t (&t)[2][32], int valid) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (h * 32 + c >= valid) t[h][c] = 0xff800000u;  // -inf
-      };
-      // prologue: tile 0 -> sa, its max becomes the running max (nothing accumulated yet, no threshold)
-      ptx::mbar_wait(&s_full[0], 0);
-      ptx::tc_fence_after();
-      ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel, sa[0]);
-      ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + 32, sa[1]);
-      ptx::tmem_ld_wait();
-      if (p.Lk < kBKV) mask_tail(sa, p.Lk);
-      mx0 = mx1 = -INFINITY;
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          mx0 = ptx::max3(mx0, __uint_as_float(sa[h][c]), __uint_as_float(sa[h][c + 1]));
-          mx1 = ptx::max3(mx1, __uint_as_float(sa[h][c + 2]), __uint_as_float(sa[h][c + 3]));
-        }
-      m = fmaxf(mx0, mx1) * p.scale_log2;
-      float m_pend = m;   // max the CURRENT tile would like (decided while the previous tile was exponentiated)
-      bool pend = false;  // warp-uniform: some row of the current tile needs O rescaled before it can be accumulated
-
-      auto step = [&](uint32_t (&cur)[2][32], uint32_t (&nxt)[2][32], int j) {
-        const int b = j & 1;
-        const uint32_t s_addr = tmem_base + lane_sel + b * kBKV;
-        if (pend) {  // rare after the first tiles: rescale O (quiescent once PV(j-1) has completed) and adopt the new max
-          ptx::mbar_wait(pv_done, (j - 1) & 1);
-          ptx::tc_fence_after();
-          const bool need = m_pend > m + kRescaleThreshold;
-          const float factor = need ? ptx::ex2_approx(m - m_pend) : 1.0f;
-          if (need) {
-            l *= factor;
-            m = m_pend;
-          }
-#pragma unroll 1
-          for (int c = 0; c < kHD / 32; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld_32x32b_x32(tmem_o + lane_sel + c * 32, o);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            ptx::tmem_st_32x32b_x32(tmem_o + lane_sel + c * 32, o);
-          }
-          ptx::tmem_st_wait();
-        }
-        const uint64_t negm2 = ptx::pack_f32x2(-m, -m);
-        sum2a = sum2b = 0ull;
-        uint32_t pk[16];
-        exps(cur[0], 32, pk, negm2, nullptr);       // columns 0-31 of tile j
-        ptx::tmem_st_32x32b_x16(s_addr, pk);        // P_j words 0-15 over the (already consumed) S_j columns
-        exps(cur[1], 16, pk, negm2, nullptr);       // columns 32-47
-        const bool has_next = j + 1 < n_tiles;
-        if (has_next) {                             // S_{j+1} was issued right after PV(j-1): normally complete by now
-          ptx::mbar_wait(&s_full[b ^ 1], ((j + 1) >> 1) & 1);
-          ptx::tc_fence_after();
-          ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + (b ^ 1) * kBKV, nxt[0]);
-          ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + (b ^ 1) * kBKV + 32, nxt[1]);
-        }
-        exps(cur[1] + 16, 8, pk + 8, negm2, nullptr);  // columns 48-55 while the loads are in flight
-        mx0 = mx1 = -INFINITY;
-        if (has_next) {
-          ptx::tmem_ld_wait();
-          const int valid_next = p.Lk - (j + 1) * kBKV;
-          if (valid_next < kBKV) mask_tail(nxt, valid_next);
-          exps(cur[1] + 24, 4, pk + 12, negm2, nxt[0]);      // columns 56-59 + max of next columns 0-7 ... pattern: 8 next cols per 4 exps
-          exps(cur[1] + 28, 4, pk + 14, negm2, nxt[0] + 8);  // columns 60-63 + next columns 8-15
-#pragma unroll
-          for (int c = 16; c < 32; c += 4) {
-            mx0 = ptx::max3(mx0, __uint_as_float(nxt[0][c]), __uint_as_float(nxt[0][c + 1]));
-            mx1 = ptx::max3(mx1, __uint_as_float(nxt[0][c + 2]), __uint_as_float(nxt[0][c + 3]));
-          }
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            mx0 = ptx::max3(mx0, __uint_as_float(nxt[1][c]), __uint_as_float(nxt[1][c + 1]));
-            mx1 = ptx::max3(mx1, __uint_as_float(nxt[1][c + 2]), __uint_as_float(nxt[1][c + 3]));
-          }
-        } else {
-          exps(cur[1] + 24, 8, pk + 12, negm2, nullptr);
-        }
-        ptx::tmem_st_32x32b_x16(s_addr + 16, pk);   // P_j words 16-31
-        float s0, s1, s2, s3;
-        ptx::unpack_f32x2(sum2a, s0, s1);
-        ptx::unpack_f32x2(sum2b, s2, s3);
-        l += (s0 + s1) + (s2 + s3);
-        if (has_next) {
-          m_pend = fmaxf(m, fmaxf(mx0, mx1) * p.scale_log2);
-          pend = __any_sync(0xffffffffu, m_pend > m + kRescaleThreshold);
-        }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(p_full);
-      };
-      for (int j = 0; j < n_tiles; j += 2) {
-        step(sa, sb, j);
-        if (j + 1 < n_tiles) step(sb, sa, j + 1);
-      }
-    } else {
     for (int j = 0; j < n_tiles; ++j) {
       const int b = j & 1;
       ptx::mbar_wait(&s_full[b], (j >> 1) & 1);
@@ -459,22 +329,19 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
   if (rc) return rc;
   rc = mc::make_tmap_bf16_2d(&tv, vt, static_cast<uint64_t>(width), static_cast<uint64_t>(Lk), static_cast<uint64_t>(ldvt), mc::kHD, mc::kBKV);
   if (rc) return rc;
-  static int variant = -1;  // MC_ATTN_VARIANT: 0 = P via smem, 1 = P in TMEM, 2 = P in TMEM + cross-tile pipelined softmax (default)
+  static int variant = -1;  // MC_ATTN_VARIANT: 0 = P via smem, 1 = P in TMEM (default)
   if (variant < 0) {
     const char* ev = getenv("MC_ATTN_VARIANT");
-    const int v = (ev && ev[0] >= '0' && ev[0] <= '2') ? (ev[0] - '0') : 2;
+    const int v = (ev && ev[0] == '0') ? 0 : 1;
     cudaError_t e = cudaFuncSetAttribute(mc::attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
     if (e != cudaSuccess) return mc::cuda_fail(e, "cudaFuncSetAttribute(attn smem)");
     variant = v;
   }
   mc::AttnParams p{Lq, Lk, heads, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo};
   dim3 grid((Lq + mc::kBQ - 1) / mc::kBQ, heads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (variant == 2)
-    mc::attn_fwd_kernel<2><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
-  else if (variant == 1)
+  if (variant == 1)
     mc::attn_fwd_kernel<1><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
   else
     mc::attn_fwd_kernel<0><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
