@@ -280,8 +280,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       ptx::mbar_arrive(p_full);
     }
 
-    }
-
     // ---- epilogue: O / l -> bf16 -> global
     ptx::mbar_wait(pv_done, (n_tiles - 1) & 1);
     ptx::tc_fence_after();
