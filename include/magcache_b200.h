@@ -182,7 +182,6 @@ int32_t mc_time_sinusoid(const double* pos_dev, int32_t n_pos, int32_t dim, floa
 
 /* elementwise helpers */
 int32_t mc_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
-int32_t mc_gelu_tanh_bf16(void* x_bf16, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,6 @@ SIGNATURES = {
     "mc_transpose_bf16": [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p],
     "mc_time_sinusoid": [c_void_p, c_int32, c_int32, c_void_p, c_void_p],
     "mc_cast": [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
-    "mc_gelu_tanh_bf16": [c_void_p, c_int64, c_void_p],
 }
 
 if not os.path.exists(LIB_PATH):

@@ -338,10 +338,6 @@ __global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ s, flo
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     d[i] = __bfloat162float(s[i]);
 }
-__global__ void gelu_tanh_bf16_kernel(__nv_bfloat16* __restrict__ x, int64_t n) {
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    x[i] = __float2bfloat16_rn(gelu_tanh(__bfloat162float(x[i])));
-}
 // sinusoidal_embedding_1d(dim, position) in float64, cos first (Appendix B.1); out fp32 [n_pos, dim]
 __global__ void time_sinusoid_kernel(const double* __restrict__ pos, int n_pos, int dim, float* __restrict__ out) {
   const int half = dim / 2;
@@ -503,14 +499,6 @@ int32_t mc_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype
     return MC_ERR_INVALID;
   }
   MC_CHECK_LAUNCH("cast kernel launch");
-  return MC_OK;
-}
-
-int32_t mc_gelu_tanh_bf16(void* x_bf16, int64_t n, void* stream) {
-  MC_CHECK_ARG(x_bf16 && n >= 0, "mc_gelu_tanh_bf16: bad arguments");
-  if (n == 0) return MC_OK;
-  mc::gelu_tanh_bf16_kernel<<<mc::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(x_bf16), n);
-  MC_CHECK_LAUNCH("gelu kernel launch");
   return MC_OK;
 }
 
