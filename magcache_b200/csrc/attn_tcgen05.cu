@@ -312,6 +312,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 
 int32_t launch_attn_v3(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out, int64_t ldo,
                        int32_t Lq, int32_t Lk, int32_t heads, float scale, cudaStream_t stream);  // attn_tcgen05_v3.cu
+int32_t launch_attn_v4(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out, int64_t ldo,
+                       int32_t Lq, int32_t Lk, int32_t heads, float scale, cudaStream_t stream);  // attn_tcgen05_v4.cu
 
 }  // namespace mc
 
@@ -326,9 +328,10 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
   static int use_v3 = -1;  // MC_ATTN_VARIANT=3: 256-row CTAs with 128-wide KV tiles (attn_tcgen05_v3.cu)
   if (use_v3 < 0) {
     const char* ev = getenv("MC_ATTN_VARIANT");
-    use_v3 = (ev && ev[0] == '3') ? 1 : 0;
+    use_v3 = (ev && ev[0] == '3') ? 1 : ((ev && ev[0] == '4') ? 2 : 0);
   }
-  if (use_v3) return mc::launch_attn_v3(q, ldq, k, ldk, vt, ldvt, out, ldo, Lq, Lk, heads, scale, static_cast<cudaStream_t>(stream));
+  if (use_v3 == 2) return mc::launch_attn_v4(q, ldq, k, ldk, vt, ldvt, out, ldo, Lq, Lk, heads, scale, static_cast<cudaStream_t>(stream));
+  if (use_v3 == 1) return mc::launch_attn_v3(q, ldq, k, ldk, vt, ldvt, out, ldo, Lq, Lk, heads, scale, static_cast<cudaStream_t>(stream));
   CUtensorMap tq, tk, tv;
   int32_t rc = mc::make_tmap_bf16_2d(&tq, q, static_cast<uint64_t>(Lq), static_cast<uint64_t>(width), static_cast<uint64_t>(ldq), mc::kBQ, 64);
   if (rc) return rc;
