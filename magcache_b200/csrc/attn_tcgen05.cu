@@ -314,6 +314,8 @@ int32_t launch_attn_v3(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        int32_t Lq, int32_t Lk, int32_t heads, float scale, cudaStream_t stream);  // attn_tcgen05_v3.cu
 int32_t launch_attn_v4(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out, int64_t ldo,
                        int32_t Lq, int32_t Lk, int32_t heads, float scale, cudaStream_t stream);  // attn_tcgen05_v4.cu
+int32_t launch_attn_v5(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out, int64_t ldo,
+                       int32_t Lq, int32_t Lk, int32_t heads, float scale, cudaStream_t stream);  // attn_tcgen05_v5.cu
 
 }  // namespace mc
 
@@ -328,8 +330,9 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
   static int use_v3 = -1;  // MC_ATTN_VARIANT=3: 256-row CTAs with 128-wide KV tiles (attn_tcgen05_v3.cu)
   if (use_v3 < 0) {
     const char* ev = getenv("MC_ATTN_VARIANT");
-    use_v3 = (ev && ev[0] == '3') ? 1 : ((ev && ev[0] == '4') ? 2 : 0);
+    use_v3 = (ev && ev[0] == '3') ? 1 : ((ev && ev[0] == '4') ? 2 : ((ev && ev[0] == '5') ? 3 : 0));
   }
+  if (use_v3 == 3) return mc::launch_attn_v5(q, ldq, k, ldk, vt, ldvt, out, ldo, Lq, Lk, heads, scale, static_cast<cudaStream_t>(stream));
   if (use_v3 == 2) return mc::launch_attn_v4(q, ldq, k, ldk, vt, ldvt, out, ldo, Lq, Lk, heads, scale, static_cast<cudaStream_t>(stream));
   if (use_v3 == 1) return mc::launch_attn_v3(q, ldq, k, ldk, vt, ldvt, out, ldo, Lq, Lk, heads, scale, static_cast<cudaStream_t>(stream));
   CUtensorMap tq, tk, tv;
