@@ -45,8 +45,9 @@ struct AttnParams {
 // PV MMA takes its A operand from TMEM — no smem round trip, no generic->async proxy fence, and P is double-buffered for free
 // (it lives in S buffer j&1), which removes the write-P -> PV -> pv_done -> write-next-P serialisation of the smem variant.
 // VARIANT 0: P through shared memory (kept for A/B measurements); VARIANT 1 (default): P in TMEM.
-// Tried and dropped in round 1 (profiles/r01_attention_experiments.md): speculative exponentials against the running max,
-// cross-tile software pipelining of the softmax warps, staggered start of the second residency slot.
+// Tried, validated and dropped in round 1 because they were slower (profiles/r01_attention_experiments.md; sources in the git
+// history): speculative exponentials, cross-tile software pipelining, staggered CTA start, 256-row CTAs with 128-wide KV
+// tiles, split-row softmax with 8 softmax warps, 128-wide KV tiles with a single-buffered S.
 template <int VARIANT>
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -310,13 +311,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   if (warp == 5) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
-int32_t launch_attn_v3(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out, int64_t ldo,
-                       int32_t Lq, int32_t Lk, int32_t heads, float scale, cudaStream_t stream);  // attn_tcgen05_v3.cu
-int32_t launch_attn_v4(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out, int64_t ldo,
-                       int32_t Lq, int32_t Lk, int32_t heads, float scale, cudaStream_t stream);  // attn_tcgen05_v4.cu
-int32_t launch_attn_v5(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out, int64_t ldo,
-                       int32_t Lq, int32_t Lk, int32_t heads, float scale, cudaStream_t stream);  // attn_tcgen05_v5.cu
-
 }  // namespace mc
 
 extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out,
@@ -327,14 +321,6 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
   MC_CHECK_ARG(ldq >= width && ldk >= width && ldo >= width && ldvt >= Lk, "mc_attn_fwd: leading dimensions too small");
   MC_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && ldo % 8 == 0, "mc_attn_fwd: leading dimensions must be multiples of 8");
   MC_CHECK_ARG(mc::aligned16(q) && mc::aligned16(k) && mc::aligned16(vt) && mc::aligned16(out), "mc_attn_fwd: pointers must be 16-byte aligned");
-  static int use_v3 = -1;  // MC_ATTN_VARIANT=3: 256-row CTAs with 128-wide KV tiles (attn_tcgen05_v3.cu)
-  if (use_v3 < 0) {
-    const char* ev = getenv("MC_ATTN_VARIANT");
-    use_v3 = (ev && ev[0] == '3') ? 1 : ((ev && ev[0] == '4') ? 2 : ((ev && ev[0] == '5') ? 3 : 0));
-  }
-  if (use_v3 == 3) return mc::launch_attn_v5(q, ldq, k, ldk, vt, ldvt, out, ldo, Lq, Lk, heads, scale, static_cast<cudaStream_t>(stream));
-  if (use_v3 == 2) return mc::launch_attn_v4(q, ldq, k, ldk, vt, ldvt, out, ldo, Lq, Lk, heads, scale, static_cast<cudaStream_t>(stream));
-  if (use_v3 == 1) return mc::launch_attn_v3(q, ldq, k, ldk, vt, ldvt, out, ldo, Lq, Lk, heads, scale, static_cast<cudaStream_t>(stream));
   CUtensorMap tq, tk, tv;
   int32_t rc = mc::make_tmap_bf16_2d(&tq, q, static_cast<uint64_t>(Lq), static_cast<uint64_t>(width), static_cast<uint64_t>(ldq), mc::kBQ, 64);
   if (rc) return rc;
