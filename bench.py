@@ -323,10 +323,15 @@ def run_ours(args, rank, world):
         ts = [a.elapsed_time(b) for a, b in evs]
         kern[tag] = {"launches": len(ts), "ms_avg": sum(ts) / len(ts), "ms_total": sum(ts)}
     roof = None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_attn_traffic.json")
+    if world == 1 and os.path.exists(tp):  # dram__bytes_read + write of one full-shape launch, from the committed ncu capture
+        with open(tp) as f:
+            traffic = json.load(f)["traffic_bytes_per_launch"]
     if "attn_self" in kern:
         ach = (ATTN_SELF_FLOPS / world) / (kern["attn_self"]["ms_avg"] * 1e-3) / 1e12  # per GPU: N/world query rows x N keys
         roof = {"kernel": "attn_fwd_kernel (self-attention, 32760x32760x12 heads)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+                "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["src"] + " (sustained bf16)",
                 "share_of_step": (kern["attn_self"]["ms_total"] / ms) if not graphs else None, "flops_per_launch": ATTN_SELF_FLOPS / world,
                 "measured": roofline_source}
     # the HBM-bound cache-hit add, timed alone on rotating buffers (inputs 3 x 503 MB > L2)

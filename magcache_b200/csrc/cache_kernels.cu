@@ -138,22 +138,36 @@ __global__ void __launch_bounds__(256) stats_kernel(const void* __restrict__ cur
        row += static_cast<int64_t>(gridDim.x) * warps_per_block) {
     const int64_t base = row * cols;
     float cc = 0.f, pp = 0.f, cp = 0.f;
-    for (int g = lane; g < groups; g += 32) {
-      float c[8], p[8];
-      Elem<DCUR>::load8(cur_or_xo, base + g * 8, c);
-      if (FUSE_SUB) {
-        float xi[8];
-        Elem<MC_BF16>::load8(xi_bf16, base + g * 8, xi);
+    // kBatch groups per lane are loaded before any of them is reduced: 2 x kBatch independent 128/256-bit loads in flight
+    constexpr int kBatch = 3;
+    for (int g0 = lane; g0 < groups; g0 += 32 * kBatch) {
+      float c[kBatch][8], p[kBatch][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) c[j] = c[j] - xi[j];
-        Elem<MC_F32>::store8(r_out, base + g * 8, c);
+      for (int u = 0; u < kBatch; ++u) {
+        const int g = g0 + 32 * u;
+        if (g < groups) {
+          Elem<DCUR>::load8(cur_or_xo, base + g * 8, c[u]);
+          if (FUSE_SUB) {
+            float xi[8];
+            Elem<MC_BF16>::load8(xi_bf16, base + g * 8, xi);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[u][j] = c[u][j] - xi[j];
+          }
+          Elem<DPREV>::load8(prev, base + g * 8, p[u]);
+        }
       }
-      Elem<DPREV>::load8(prev, base + g * 8, p);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        cc = fmaf(c[j], c[j], cc);
-        pp = fmaf(p[j], p[j], pp);
-        cp = fmaf(c[j], p[j], cp);
+      for (int u = 0; u < kBatch; ++u) {
+        const int g = g0 + 32 * u;
+        if (g < groups) {
+          if (FUSE_SUB) Elem<MC_F32>::store8(r_out, base + g * 8, c[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            cc = fmaf(c[u][j], c[u][j], cc);
+            pp = fmaf(p[u][j], p[u][j], pp);
+            cp = fmaf(c[u][j], p[u][j], cp);
+          }
+        }
       }
     }
     cc = warp_sum(cc);
