@@ -1,0 +1,75 @@
+"""Run every kernel twice on identical inputs at the Wan2.1-1.3B shapes and compare bit for bit (race detector of last resort)."""
+import math
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from magcache_b200 import _lib, ops  # noqa: E402
+
+dev = "cuda"
+N, D, F, H = 32760, 1536, 8960, 12
+g = torch.Generator(device=dev).manual_seed(0)
+
+
+def rnd(*shape, scale=1.0, dtype=torch.bfloat16):
+    return (torch.randn(*shape, device=dev, generator=g) * scale).to(dtype)
+
+
+def check(name, fn, reps=3):
+    outs = [fn().clone() for _ in range(reps)]
+    torch.cuda.synchronize()
+    same = all(torch.equal(outs[0], o) for o in outs[1:])
+    nd = 0 if same else int((outs[0] != outs[1]).sum().item())
+    print(f"{name:34s} deterministic={same} differing_elems(run0 vs run1)={nd}", flush=True)
+    if not same:
+        idx = (outs[0] != outs[1]).nonzero()[:5].tolist()
+        print("    first diffs at", idx, [float(outs[0][tuple(i)]) for i in idx], [float(outs[1][tuple(i)]) for i in idx])
+    return same
+
+
+a = rnd(N, D)
+w_qk = rnd(2 * D, D, scale=1 / math.sqrt(D))
+w_f1 = rnd(F, D, scale=1 / math.sqrt(D))
+w_f2 = rnd(D, F, scale=1 / math.sqrt(F))
+bias = rnd(2 * D, dtype=torch.float32)
+check("gemm qk bias->bf16", lambda: ops.gemm(a, w_qk, bias, _lib.MC_EPI_BIAS_BF16))
+check("gemm ffn1 gelu", lambda: ops.gemm(a, w_f1, None, _lib.MC_EPI_BIAS_GELU_BF16))
+ff = rnd(N, F)
+x = rnd(N, D, dtype=torch.float32)
+gate = rnd(D, dtype=torch.float32)
+
+
+def resid():
+    xx = x.clone()
+    ops.gemm(ff, w_f2, bias[:D].contiguous(), _lib.MC_EPI_BIAS_GATE_RESID, out=xx, gate=gate)
+    return xx
+
+
+check("gemm ffn2 gate-resid", resid)
+vt_buf = torch.zeros(D, N, dtype=torch.bfloat16, device=dev)
+check("gemm V^T rowbias", lambda: ops.gemm(w_qk[:D], a, bias[:D].contiguous(), _lib.MC_EPI_ROWBIAS_BF16, out=vt_buf))
+q, k, vt = rnd(N, D), rnd(N, D), rnd(D, N)
+check("attention self 32760", lambda: ops.attention(q, k, vt, H))
+q6 = rnd(N, D, scale=4.0)
+check("attention self (large scores)", lambda: ops.attention(q6, k, vt, H))
+kc, vtc = rnd(512, D), rnd(D, 512)
+check("attention cross 512", lambda: ops.attention(q, kc, vtc, H))
+em = rnd(6, D, scale=0.1, dtype=torch.float32)
+check("ln_modulate", lambda: ops.ln_modulate(x, em, 1, 0))
+wn = rnd(D, dtype=torch.float32)
+cs = rnd(N, 128, dtype=torch.float32)
+
+
+def rms():
+    t = a.clone()
+    ops.rmsnorm_rope_(t, wn, cs, 128)
+    return t
+
+
+check("rmsnorm_rope", rms)
+hm, e = rnd(2, D, scale=0.03, dtype=torch.float32), rnd(1, D, dtype=torch.float32)
+wt, hb = rnd(D, 64, scale=0.03, dtype=torch.float32).contiguous(), rnd(64, dtype=torch.float32)
+check("head_unpatchify", lambda: ops.head_unpatchify(x, hm, e, wt, hb, (21, 30, 52)))
+lat = rnd(16, 21, 60, 104, dtype=torch.float32)
+check("patchify", lambda: ops.patchify(lat))
