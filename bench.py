@@ -234,9 +234,7 @@ def run_ours(args, rank, world):
     guide = 5.0
 
     def reset_controller():
-        cls = type(model)
-        cls.cnt = 0
-        cls.accumulated_err, cls.accumulated_steps, cls.accumulated_ratio = [0.0, 0.0], [0, 0], [1.0, 1.0]
+        mc.reset_magcache(model)
 
     def step_resident(i, x):
         t = t_dev[i % SAMPLE_STEPS]
@@ -268,7 +266,7 @@ def run_ours(args, rank, world):
         for i in range(args.warmup):  # warm-up: extra non-cached steps (cnt < retention window), then restart the schedule
             r = run_step(i, x) if run_step is step_resident else run_step(i)
             x = r if r is not None else x
-            if type(model).cnt >= 20:
+            if model.cnt >= 20:
                 reset_controller()
         reset_controller()
         x = lat_d.clone()

@@ -6,7 +6,7 @@ Importing this package loads libmagcache_b200.so (build it with `python magcache
 """
 from .config import PRESETS, MagCacheConfig, interp_cfg, nearest_interp, tables  # noqa: F401
 from .patch import (enable_token_shard, init_magcache, init_magcache_calibration, magcache_branch, magcache_calibration,  # noqa: F401
-                    magcache_forward)
+                    magcache_forward, reset_magcache)
 from .wan import WAN_CONFIGS, WanDims, WanEngine, WanModelHandle, WanWeights  # noqa: F401
 
 __version__ = "0.1.0"

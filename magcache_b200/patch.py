@@ -159,6 +159,21 @@ def init_magcache(model, sample_steps, thresh=0.12, K=2, retention_ratio=0.2, ma
     return model
 
 
+def reset_magcache(model):
+    """Start a new video: cnt = 0 and fresh accumulators (what `pipeline.transformer.__class__.cnt = 0` between prompts is
+    meant to do, MagCache4FLUX/magcache_flux.py:478). `self.cnt += 1` in the forward creates INSTANCE attributes that shadow
+    the class-level ones the scripts install, so both levels are reset here. The residual cache is kept, as in the reference."""
+    cls = model.__class__
+    for attr in ("cnt", "accumulated_err", "accumulated_steps", "accumulated_ratio"):
+        model.__dict__.pop(attr, None)
+    cls.cnt = 0
+    if isinstance(getattr(cls, "accumulated_err", None), list):
+        cls.accumulated_err, cls.accumulated_steps, cls.accumulated_ratio = [0.0, 0.0], [0, 0], [1.0, 1.0]
+    else:
+        cls.accumulated_err, cls.accumulated_steps, cls.accumulated_ratio = 0, 0, 1.0
+    return model
+
+
 def init_magcache_calibration(model, sample_steps):
     """magcache_generate.py:921-928."""
     cls = model.__class__

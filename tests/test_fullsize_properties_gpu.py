@@ -80,14 +80,13 @@ def test_full_shape_block_is_deterministic_and_finite():
     t = torch.tensor([777.0], device=DEV)
     outs = []
     for _ in range(2):
-        type(model).cnt = 0
-        type(model).accumulated_err, type(model).accumulated_steps, type(model).accumulated_ratio = [0.0, 0.0], [0, 0], [1.0, 1.0]
+        mc.reset_magcache(model)
         outs.append(model([lat], t=t, context=[ctx], seq_len=N)[0])
     assert torch.equal(outs[0], outs[1])
     assert torch.isfinite(outs[0]).all() and float(outs[0].abs().mean()) > 1e-3
     miss_uncond = model([lat], t=t, context=[ctx], seq_len=N)[0]   # cnt 1: miss (fills slot 1)
     hit = model([lat], t=t, context=[ctx], seq_len=N)[0]           # cnt 2: hit on slot 0 with the same inputs
-    assert type(model).cnt == 3
+    assert model.cnt == 3
     # same inputs => x0 + (x - x0) differs from x only by the fp32 rounding of the subtraction/addition pair
     rel = float((hit - outs[0]).norm() / outs[0].norm())
     assert rel < 1e-5, rel

@@ -94,7 +94,7 @@ def test_magcache_loop_mask_cache_and_outputs():
             t = torch.tensor([float(sig[i] * 1000)])
             x = lat + 0.1 * i * torch.randn(lat.shape, generator=g)  # a new latent every step, identical on both sides
             for c in (ctx, ctx_null):
-                cnt_before = type(ours_model).cnt
+                cnt_before = ours_model.cnt
                 ref = ref_model([x], t=t, context=[c], seq_len=n_tok)[0]
                 out = ours_model([x.to(DEV)], t=t.to(DEV), context=[c.to(DEV)], seq_len=n_tok)[0].cpu()
                 skips_ref.append(int(ref_model.last_skip))
@@ -111,7 +111,7 @@ def test_magcache_loop_mask_cache_and_outputs():
     cfg = MagCacheConfig("wan2.1", sample_steps=steps, table="wan2.1_t2v_1.3b", **{"thresh": 0.12, "K": 2, "retention_ratio": 0.2})
     mask = schedule_mask(make_ctrl_config(cfg.num_steps, cfg.thresh, cfg.K, cfg.retention_ratio, cfg.resolved_ratios(), **cfg.ctrl_kwargs()), 2 * steps)
     assert mask.tolist() == skips_ref and sum(skips_ref) > 0
-    assert type(ours_model).cnt == 0  # wrapped around after num_steps calls
+    assert ours_model.cnt == 0  # wrapped around after num_steps calls
 
 
 def test_calibration_matches_oracle():
