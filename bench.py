@@ -38,6 +38,22 @@ D, FFN, HEADS, LAYERS, TEXT_LEN, TEXT_DIM = 1536, 8960, 12, 30, 512, 4096
 ATTN_SELF_FLOPS = 4.0 * N_TOK * N_TOK * D  # QK^T + PV, 2 flop per MAC (6.594 TF per layer)
 LAYER_FLOPS = 9.433e12
 FWD_FLOPS = 283.0e12
+WORKLOAD = "Wan2.1-T2V-1.3B 832x480x81f"
+MODEL_KEY, TABLE = "t2v-1.3B", "wan2.1_t2v_1.3b"
+
+
+def select_workload(name):
+    """Default = BASELINE configs[1]. `wan14b` = configs[4]'s model and resolution (Wan2.1-T2V-14B, 1280x720x81f, E024K6R02):
+    not what the driver times, kept to show the 14B shapes run at full size (one GPU holds it: 28 GB of bf16 weights)."""
+    global GRID, LATENT, PRESET, N_TOK, D, FFN, HEADS, LAYERS, ATTN_SELF_FLOPS, FWD_FLOPS, WORKLOAD, MODEL_KEY, TABLE
+    if name == "wan14b":
+        GRID, LATENT = (21, 45, 80), (16, 21, 90, 160)
+        PRESET = dict(thresh=0.24, K=6, retention_ratio=0.2)
+        N_TOK = GRID[0] * GRID[1] * GRID[2]
+        D, FFN, HEADS, LAYERS = 5120, 13824, 40, 40
+        ATTN_SELF_FLOPS = 4.0 * N_TOK * N_TOK * D
+        FWD_FLOPS = 6523.0e12  # SURVEY §8d
+        WORKLOAD, MODEL_KEY, TABLE = "Wan2.1-T2V-14B 1280x720x81f", "t2v-14B", "wan2.1_t2v_14b"
 
 
 def peaks():
@@ -215,11 +231,11 @@ def run_ours(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    weights = mc.WanWeights.random(mc.WAN_CONFIGS["t2v-1.3B"], dev, seed=0)  # same seed on every rank: replicated weights
+    weights = mc.WanWeights.random(mc.WAN_CONFIGS[MODEL_KEY], dev, seed=0)  # same seed on every rank: replicated weights
     # N > 1: ONE video, token axis sharded over the ranks (K/V all-gather per layer), see magcache_b200/shard.py
     model = mc.WanModelHandle(weights, shard_world=world, shard_rank=rank) if world > 1 else mc.WanModelHandle(weights)
     thresh = 1e-9 if args.no_cache else PRESET["thresh"]  # --no-cache: the controller never skips (same code path, same shapes)
-    mc.init_magcache(model, SAMPLE_STEPS, thresh=thresh, K=PRESET["K"], retention_ratio=PRESET["retention_ratio"], table="wan2.1_t2v_1.3b")
+    mc.init_magcache(model, SAMPLE_STEPS, thresh=thresh, K=PRESET["K"], retention_ratio=PRESET["retention_ratio"], table=TABLE)
 
     g = torch.Generator().manual_seed(0)
     lat_h = torch.randn(*LATENT, generator=g).pin_memory()
@@ -240,8 +256,8 @@ def run_ours(args, rank, world):
         t = t_dev[i % SAMPLE_STEPS]
         cond = model([x], t=t, context=[ctx_d], seq_len=N_TOK)[0]
         uncond = model([x], t=t, context=[ctxn_d], seq_len=N_TOK)[0]
-        # CFG combine + Euler flow step: caller-side code (wan_magcache.py:301-310), outside the measured path's kernels
-        v = uncond + guide * (cond - uncond)
+        # caller-side code (wan_magcache.py:301-310): CFG combine (one kernel) + an Euler flow step standing in for FlowUniPC
+        v = ops.cfg_combine(cond, uncond, guide)
         return x + float(sig[(i % SAMPLE_STEPS) + 1] - sig[i % SAMPLE_STEPS]) * v
 
     def step_e2e(i):
@@ -310,7 +326,7 @@ def run_ours(args, rank, world):
 
     # skip schedule actually walked in the timed region
     from magcache_b200.controller import make_ctrl_config, schedule_mask
-    cfgm = mc.MagCacheConfig("wan2.1", thresh, PRESET["K"], PRESET["retention_ratio"], SAMPLE_STEPS, table="wan2.1_t2v_1.3b")
+    cfgm = mc.MagCacheConfig("wan2.1", thresh, PRESET["K"], PRESET["retention_ratio"], SAMPLE_STEPS, table=TABLE)
     mask = schedule_mask(make_ctrl_config(cfgm.num_steps, cfgm.thresh, cfgm.K, cfgm.retention_ratio, cfgm.resolved_ratios(), **cfgm.ctrl_kwargs()), 2 * SAMPLE_STEPS)
     walked = [int(mask[c % (2 * SAMPLE_STEPS)]) for c in range(2 * args.steps)]
     n_hit, n_miss = sum(walked), len(walked) - sum(walked)
@@ -323,17 +339,17 @@ def run_ours(args, rank, world):
     roof = None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r01_attn_traffic.json")
-    if world == 1 and os.path.exists(tp):  # dram__bytes_read + write of one full-shape launch, from the committed ncu capture
+    if world == 1 and MODEL_KEY == "t2v-1.3B" and os.path.exists(tp):  # dram__bytes_read + write of one full-shape launch, from the committed ncu capture
         with open(tp) as f:
             traffic = json.load(f)["traffic_bytes_per_launch"]
     if "attn_self" in kern:
         ach = (ATTN_SELF_FLOPS / world) / (kern["attn_self"]["ms_avg"] * 1e-3) / 1e12  # per GPU: N/world query rows x N keys
-        roof = {"kernel": "attn_fwd_kernel (self-attention, 32760x32760x12 heads)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"],
+        roof = {"kernel": f"attn_fwd_kernel (self-attention, {N_TOK}x{N_TOK}x{HEADS} heads)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"],
                 "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["src"] + " (sustained bf16)",
                 "share_of_step": (kern["attn_self"]["ms_total"] / ms) if not graphs else None, "flops_per_launch": ATTN_SELF_FLOPS / world,
                 "measured": roofline_source}
     # the HBM-bound cache-hit add, timed alone on rotating buffers (inputs 3 x 503 MB > L2)
-    k1 = bench_k1(dev, pk)
+    k1 = bench_k1(dev, pk) if MODEL_KEY == "t2v-1.3B" else None
 
     steps_per_s = args.steps / (ms * 1e-3)  # whole job: all ranks work on the same video
     e2e_v = args.steps / (ms_e2e * 1e-3)
@@ -342,7 +358,9 @@ def run_ours(args, rank, world):
     line = {"metric": "denoising_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Wan2.1-T2V-1.3B 832x480x81f, 50 steps, MagCache " + ("disabled (non-cached loop)" if args.no_cache else "E012K4R02") + " (BASELINE configs[1])",
+            "config": {"workload": WORKLOAD + ", 50 steps, MagCache " + ("disabled (non-cached loop)" if args.no_cache else
+                                    f"E{int(PRESET['thresh'] * 100):03d}K{PRESET['K']}R{int(PRESET['retention_ratio'] * 10):02d}") +
+                                    (" (BASELINE configs[1])" if MODEL_KEY == "t2v-1.3B" else " (BASELINE configs[4] model and shape, single GPU)"),
                        "tokens": N_TOK, "dim": D, "layers": LAYERS, "forwards_timed": {"miss": n_miss, "hit": n_hit},
                        "parallelism": "single GPU" if world == 1 else f"token-axis shard over {world} GPUs ({N_TOK // world} tokens each), NCCL all-gather of K and V per layer, replicated weights",
                        "cuda_graphs": bool(graphs),
@@ -353,7 +371,7 @@ def run_ours(args, rank, world):
             "model_flops_per_miss_forward": FWD_FLOPS,
             "achieved_tflops_miss_only_whole_job": (n_miss * FWD_FLOPS / 1e12) / (ms * 1e-3) if n_miss else None}
     if rank == 0:
-        if world == 1 and not args.skip_cpu:
+        if world == 1 and not args.skip_cpu and MODEL_KEY == "t2v-1.3B":
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -437,7 +455,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cache", action="store_true", help="time the non-cached DiT loop at identical shapes")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (debugging)")
+    ap.add_argument("--workload", default="wan1.3b", choices=["wan1.3b", "wan14b"], help="wan14b: BASELINE configs[4] model/shape (not the driver's metric)")
     args = ap.parse_args()
+    select_workload(args.workload)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -105,6 +105,11 @@ int32_t mc_cache_hit_add(const void* x, int32_t x_dtype, const void* r, int32_t 
 int32_t mc_residual_sub(const void* x_out, int32_t xo_dtype, const void* x_in, int32_t xi_dtype, void* r, int32_t r_dtype,
                         int64_t n, void* stream);
 
+/* classifier-free-guidance combine of the caller loop
+ * `noise_pred = noise_pred_uncond + guide_scale * (noise_pred_cond - noise_pred_uncond)`
+ * eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py:301-302 — one pass, fp32, each operation rounded like torch eager. */
+int32_t mc_cfg_combine(const float* cond, const float* uncond, float guide_scale, float* out, int64_t n, void* stream);
+
 /* calibration statistics                              magcache_generate.py:167-169 (one pass instead of ~7 + 3 syncs).
  * r_cur, r_prev: [rows, cols]. stats (device, 4 doubles, overwritten): sum(ratio), sum(ratio^2), sum(1-cos), rows
  * with ratio = ||r_cur[i]||2 / (||r_prev[i]||2 + denom_eps)  (denom_eps = 0 Wan :167; 1e-8 eval variant wan_magcache.py:652)

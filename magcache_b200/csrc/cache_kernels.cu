@@ -125,6 +125,25 @@ static int32_t dispatch_axpb(const void* a, int da, const void* b, int db, void*
   return MC_ERR_INVALID;
 }
 
+// ---- CFG combine of the caller loop: out = uncond + g * (cond - uncond), each op rounded separately like torch eager --------
+__global__ void __launch_bounds__(256) cfg_combine_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, float g,
+                                                          float* __restrict__ out, int64_t n_groups) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_groups; i += stride) {
+    float c[8], u[8];
+    Elem<MC_F32>::load8(cond, i * 8, c);
+    Elem<MC_F32>::load8(uncond, i * 8, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = __fadd_rn(u[j], __fmul_rn(g, __fsub_rn(c[j], u[j])));
+    Elem<MC_F32>::store8(out, i * 8, c);
+  }
+}
+__global__ void cfg_combine_tail_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, float g,
+                                        float* __restrict__ out, int64_t begin, int64_t n) {
+  const int64_t i = begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fadd_rn(uncond[i], __fmul_rn(g, __fsub_rn(cond[i], uncond[i])));
+}
+
 // ---- K3: per-row norms / cosine, single pass ---------------------------------------------------------------
 // One warp per row; lanes stride over 8-element groups. Optionally also forms cur = xo - xi on the fly and stores it.
 template <int DCUR, int DPREV, bool FUSE_SUB>
@@ -229,6 +248,27 @@ int32_t mc_residual_sub(const void* x_out, int32_t xo_dtype, const void* x_in, i
                         void* stream) {
   return mc::dispatch_axpb(x_out, xo_dtype, x_in, xi_dtype, r, r_dtype, n, -1.0f, static_cast<cudaStream_t>(stream),
                            "mc_residual_sub");
+}
+
+int32_t mc_cfg_combine(const float* cond, const float* uncond, float guide_scale, float* out, int64_t n, void* stream) {
+  MC_CHECK_ARG(n >= 0, "mc_cfg_combine: negative element count");
+  if (n == 0) return MC_OK;
+  MC_CHECK_ARG(cond && uncond && out, "mc_cfg_combine: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
+  const int64_t groups = (al32(cond) && al32(uncond) && al32(out)) ? n / 8 : 0;
+  if (groups > 0) {
+    int64_t want = (groups + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(mc::num_sms()) * 8;
+    mc::cfg_combine_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, s>>>(cond, uncond, guide_scale, out, groups);
+    MC_CHECK_LAUNCH("cfg_combine_kernel launch");
+  }
+  if (groups * 8 < n) {
+    const int64_t rem = n - groups * 8;
+    mc::cfg_combine_tail_kernel<<<static_cast<int>((rem + 255) / 256), 256, 0, s>>>(cond, uncond, guide_scale, out, groups * 8, n);
+    MC_CHECK_LAUNCH("cfg_combine_tail_kernel launch");
+  }
+  return MC_OK;
 }
 
 int32_t mc_residual_stats(const void* r_cur, int32_t cur_dtype, const void* r_prev, int32_t prev_dtype, int64_t rows, int32_t cols,

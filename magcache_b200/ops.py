@@ -82,6 +82,17 @@ def residual_sub(x_out, x_in, out=None):
     return out
 
 
+def cfg_combine(cond, uncond, guide_scale, out=None):
+    """`uncond + guide_scale * (cond - uncond)` (wan_magcache.py:301-302) in one pass, bit-identical to the torch expression."""
+    _dev(cond), _dev(uncond)
+    assert cond.dtype == uncond.dtype == torch.float32 and cond.shape == uncond.shape and cond.is_contiguous() and uncond.is_contiguous()
+    if out is None:
+        out = torch.empty_like(cond)
+    check(lib.mc_cfg_combine(cond.data_ptr(), uncond.data_ptr(), float(guide_scale), out.data_ptr(), cond.numel(), _stream()))
+    _count()
+    return out
+
+
 def _finish_stats(stats_dev):
     s0, s1, s2, n = stats_dev.tolist()  # the single host sync of the calibration path
     mean = s0 / n

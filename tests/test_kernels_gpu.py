@@ -77,6 +77,29 @@ def test_residual_sub_unaligned_and_ragged():
     assert torch.equal(ops.residual_sub(xo, xi), xo - xi)
 
 
+def test_cfg_combine_bit_exact():
+    """wan_magcache.py:301-302 on the full latent shape and on a ragged/unaligned one."""
+    ops = _ops()
+    for shape, off in [((16, 21, 60, 104), 0), ((1003,), 1)]:
+        n = int(torch.tensor(shape).prod()) + off
+        cond = torch.randn(n, device=DEV)[off:].contiguous() if off == 0 else torch.randn(n, device=DEV)[off:]
+        uncond = torch.randn(cond.shape, device=DEV)
+        cond = cond.contiguous()
+        for g in (5.0, 6.0, 1.0, 7.5):
+            assert torch.equal(ops.cfg_combine(cond, uncond, g), uncond + g * (cond - uncond))
+
+
+def test_cache_kernels_hunyuan_720p_shape():
+    """BASELINE configs[3] (HunyuanVideo 720p x 129 frames: [1, 118800, 3072], all bf16): hit add / residual sub bit-exact."""
+    ops = _ops()
+    n = 118800 * 3072
+    x = torch.randn(n, device=DEV).bfloat16()
+    r = (torch.randn(n, device=DEV) * 0.2).bfloat16()
+    y = ops.cache_hit_add(x, r)
+    assert y.dtype == torch.bfloat16 and torch.equal(y, x + r)
+    assert torch.equal(ops.residual_sub(y, x), y - x)
+
+
 def _ref_stats(r, p, eps=0.0):
     ratio = r.norm(dim=-1) / (p.norm(dim=-1) + eps)
     return ratio.mean().item(), ratio.std().item(), (1 - torch.nn.functional.cosine_similarity(r, p, dim=-1, eps=1e-8)).mean().item()
