@@ -216,6 +216,114 @@ __global__ void __launch_bounds__(256) stats_kernel(const void* __restrict__ cur
   }
 }
 
+// TMA-staged variant for fp32 residuals (the Wan stream): a producer thread keeps kStages x (4 rows of each tensor) in flight
+// with cp.async.bulk into a shared-memory ring, so the bytes in flight per SM (~150 KB) no longer depend on how many warps
+// happen to be in their load phase; four consumer warps (one row each) reduce out of shared memory with warp shuffles.
+// Same arithmetic as stats_kernel. FUSE_SUB additionally stages x_in (bf16) and writes r = x_out - x_in.
+constexpr int kStatRows = 4;  // rows per stage = consumer warps
+
+template <bool FUSE_SUB>
+__global__ void __launch_bounds__(160) stats_tma_kernel(const float* __restrict__ cur_or_xo, const __nv_bfloat16* __restrict__ xi,
+                                                        float* __restrict__ r_out, const float* __restrict__ prev, int64_t rows, int cols,
+                                                        int stages, double denom_eps, double* __restrict__ stats) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  const int row_f32 = cols * 4, row_bf16 = cols * 2;
+  const int stage_bytes = kStatRows * (2 * row_f32 + (FUSE_SUB ? row_bf16 : 0));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_dyn + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* empty = full + stages;
+  double* red = reinterpret_cast<double*>(empty + stages);  // [3][kStatRows]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_chunks = (rows + kStatRows - 1) / kStatRows;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], kStatRows);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kStatRows) {
+    // ---- producer warp (one thread): bulk copies of whole row groups, rows are contiguous in memory
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+        const int s = it % stages;
+        ptx::mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        const int64_t row0 = c * kStatRows;
+        const int64_t left = rows - row0;
+        const int nr = left < kStatRows ? static_cast<int>(left) : kStatRows;
+        uint8_t* base = smem_dyn + static_cast<size_t>(s) * stage_bytes;
+        const uint32_t bytes = static_cast<uint32_t>(nr) * (2 * row_f32 + (FUSE_SUB ? row_bf16 : 0));
+        ptx::mbar_expect_tx(&full[s], bytes);
+        ptx::bulk_load_1d(base, cur_or_xo + row0 * cols, nr * row_f32, &full[s]);
+        ptx::bulk_load_1d(base + kStatRows * row_f32, prev + row0 * cols, nr * row_f32, &full[s]);
+        if (FUSE_SUB) ptx::bulk_load_1d(base + 2 * kStatRows * row_f32, xi + row0 * cols, nr * row_bf16, &full[s]);
+      }
+    }
+  } else {
+    // ---- consumer warps: warp w owns row w of every stage
+    double acc_ratio = 0.0, acc_ratio2 = 0.0, acc_cos = 0.0;
+    const int groups = cols >> 3;
+    uint32_t it = 0;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+      const int s = it % stages;
+      ptx::mbar_wait(&full[s], (it / stages) & 1);
+      const int64_t row = c * kStatRows + warp;
+      if (row < rows) {
+        const uint8_t* base = smem_dyn + static_cast<size_t>(s) * stage_bytes;
+        const float4* cp4 = reinterpret_cast<const float4*>(base + warp * row_f32);
+        const float4* pp4 = reinterpret_cast<const float4*>(base + kStatRows * row_f32 + warp * row_f32);
+        const uint4* xp = reinterpret_cast<const uint4*>(base + 2 * kStatRows * row_f32 + warp * row_bf16);
+        float cc = 0.f, pp = 0.f, cp = 0.f;
+        for (int g = lane; g < groups; g += 32) {
+          float cv[8], pv[8];
+          const float4 c0 = cp4[2 * g], c1 = cp4[2 * g + 1], p0 = pp4[2 * g], p1 = pp4[2 * g + 1];
+          cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+          pv[0] = p0.x; pv[1] = p0.y; pv[2] = p0.z; pv[3] = p0.w; pv[4] = p1.x; pv[5] = p1.y; pv[6] = p1.z; pv[7] = p1.w;
+          if (FUSE_SUB) {
+            float xv[8];
+            unpack_bf16x8(xp[g], xv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cv[j] = cv[j] - xv[j];
+            Elem<MC_F32>::store8(r_out, row * cols + g * 8, cv);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            cc = fmaf(cv[j], cv[j], cc);
+            pp = fmaf(pv[j], pv[j], pp);
+            cp = fmaf(cv[j], pv[j], cp);
+          }
+        }
+        cc = warp_sum(cc);
+        pp = warp_sum(pp);
+        cp = warp_sum(cp);
+        if (lane == 0) {
+          const float n_cur = sqrtf(cc), n_prev = sqrtf(pp);
+          const float ratio = n_cur / (n_prev + static_cast<float>(denom_eps));
+          const float cosv = cp / (fmaxf(n_cur, 1e-8f) * fmaxf(n_prev, 1e-8f));
+          acc_ratio += static_cast<double>(ratio);
+          acc_ratio2 += static_cast<double>(ratio) * static_cast<double>(ratio);
+          acc_cos += static_cast<double>(1.0f - cosv);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty[s]);  // this warp is done reading the stage
+    }
+    if (lane == 0) {
+      red[0 * kStatRows + warp] = acc_ratio;
+      red[1 * kStatRows + warp] = acc_ratio2;
+      red[2 * kStatRows + warp] = acc_cos;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < kStatRows; ++w) t += red[threadIdx.x * kStatRows + w];
+    atomicAdd(&stats[threadIdx.x], t);
+  }
+}
+
 __global__ void stats_init_kernel(double* stats, double rows) {
   if (threadIdx.x < 3) stats[threadIdx.x] = 0.0;
   if (threadIdx.x == 3) stats[3] = rows;
@@ -226,6 +334,27 @@ static int32_t launch_stats(const void* cur, const void* xi, void* r_out, const 
                             double* stats, cudaStream_t s) {
   stats_init_kernel<<<1, 32, 0, s>>>(stats, static_cast<double>(rows));
   MC_CHECK_LAUNCH("stats_init_kernel launch");
+  if (DCUR == MC_F32 && DPREV == MC_F32) {
+    // TMA-staged path when at least two stages of 4 rows fit in shared memory (cols <= ~3000 for the plain statistics)
+    const int stage_bytes = kStatRows * (2 * cols * 4 + (FUSE ? cols * 2 : 0));
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages >= 2) {
+      const int smem = stages * stage_bytes + stages * 16 + 3 * kStatRows * 8 + 64;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(stats_tma_kernel<FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stats_tma smem)");
+        attr_set = true;
+      }
+      const int64_t n_chunks = (rows + kStatRows - 1) / kStatRows;
+      const int grid = static_cast<int>(n_chunks < num_sms() ? n_chunks : num_sms());
+      stats_tma_kernel<FUSE><<<grid, 160, smem, s>>>(static_cast<const float*>(cur), static_cast<const __nv_bfloat16*>(xi),
+                                                     static_cast<float*>(r_out), static_cast<const float*>(prev), rows, cols, stages, eps, stats);
+      MC_CHECK_LAUNCH("stats_tma_kernel launch");
+      return MC_OK;
+    }
+  }
   const int threads = 256, wpb = threads / 32;
   int64_t want = (rows + wpb - 1) / wpb;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
