@@ -56,7 +56,17 @@ if which in ("all", "cache"):
     rec("k2_residual_sub", *timeit(lambda: ops.residual_sub(xo, x, out=out), iters=20), bytes_=n * 10)
     rec("torch_copy_f32", *timeit(lambda: out.copy_(r), iters=20), bytes_=n * 8)
     r2, p2 = r.view(N_TOK, D), (r * 1.01).view(N_TOK, D)
-    rec("k3_stats", *timeit(lambda: ops.residual_stats(r2, p2), iters=10), bytes_=n * 8)
+    rec("k3_stats_with_host_sync", *timeit(lambda: ops.residual_stats(r2, p2), iters=10), bytes_=n * 8)
+    from magcache_b200._lib import check, lib
+    st = torch.empty(4, dtype=torch.float64, device=dev)
+    rec("k3_stats_kernels_only", *timeit(lambda: check(lib.mc_residual_stats(r2.data_ptr(), 0, p2.data_ptr(), 0, N_TOK, D, 0.0, st.data_ptr(),
+                                                                            torch.cuda.current_stream().cuda_stream)), iters=20), bytes_=n * 8)
+    xo2 = torch.randn(N_TOK, D, device=dev)
+    xi2 = torch.randn(N_TOK, D, device=dev).bfloat16()
+    ro = torch.empty(N_TOK, D, device=dev)
+    rec("k2k3_sub_stats_fused_kernels_only", *timeit(lambda: check(lib.mc_residual_sub_stats(xo2.data_ptr(), 0, xi2.data_ptr(), 1, ro.data_ptr(), p2.data_ptr(),
+                                                                                         N_TOK, D, 0.0, st.data_ptr(), torch.cuda.current_stream().cuda_stream)), iters=20),
+        bytes_=n * 14)
     xb = torch.randn(n, device=dev).bfloat16()
     ob = torch.empty_like(xb)
     rec("k1_hit_add_bf16_all", *timeit(lambda: ops.cache_hit_add(x, xb, out=ob), iters=20), bytes_=n * 6)
