@@ -264,10 +264,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       if (P_IN_TMEM) {
         // P_j overwrites the first 32 columns of S buffer b (64 bf16 per row = 32 packed words); its reader PV(j) is ordered
         // before S(j+2) by the tensor pipe.
-        // Measured on B200 (tools/diag_determinism.py): without this wait the kernel is not run-to-run deterministic on short
-        // sequences and whenever O is rescaled, although no TMEM region is shared between P_j (this buffer) and PV(j-1)
-        // (the other buffer + O). Keeping the softmax warps at most one PV behind the tensor pipe — the ordering the
-        // smem-P variant has by construction — makes every case bit-reproducible; PV(j-1) has normally long finished.
+        // An mbarrier parity wait can only tell the current phase from the one before it, so a waiter must never fall two
+        // phases behind. pv_done completes one phase per tile; a softmax thread that skipped it would reach the epilogue while
+        // PV(n-2) is still in flight, and its wait for PV(n-1) would then be satisfied by the parity of PV(n-3): O read early,
+        // run-to-run different results (caught by the full-shape determinism test, tools/diag_determinism.py). Observing
+        // PV(j-1) here every tile costs nothing measurable — it has normally completed long before — and keeps the phases aligned.
         if (j > 0 && !waited) ptx::mbar_wait(pv_done, (j - 1) & 1);
         ptx::tmem_st_32x32b_x32(tmem_base + lane_sel + b * kBKV, packed);
         ptx::tmem_st_wait();
