@@ -6,8 +6,11 @@
 // Persistent kernel, one CTA per SM, tile 128 (M) x 256 (N) x 64 (K per stage):
 //   warp 0     TMA producer : A tile (128x64) + B tile (256x64) per stage, 128-byte swizzle, 4-stage smem ring (192 KB)
 //   warp 1     MMA issuer   : tcgen05.mma M128 N256 K16 x4 per stage into one of TWO 256-column TMEM accumulators
-//   warps 2-5  epilogue     : drain accumulator t&1 while the MMA warp fills the other one. tcgen05.ld (lane = row) ->
-//                             per-warp smem transpose -> lane = column, so every global access is a coalesced row segment
+//   warps 2-9  epilogue     : drain accumulator t&1 while the MMA warp fills the other one; two warps per TMEM lane quarter,
+//                             each taking 128 of the 256 columns. tcgen05.ld (lane = row) -> per-warp smem transpose ->
+//                             lane = column, so every global access is a coalesced row segment. (With four epilogue warps
+//                             the K = 1536 GEMMs were epilogue-bound: ~12 us of dependent load/store per tile against a
+//                             6.4 us main loop.)
 // Tiles are walked in waves of gridDim.x consecutive tiles with N fastest: the CTAs of one wave share A row-panels in L2.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -20,11 +23,12 @@ constexpr int kTileABytes = kBM * kBK * 2;  // 16 KB
 constexpr int kTileBBytes = kBN * kBK * 2;  // 32 KB
 constexpr int kStageBytes = kTileABytes + kTileBBytes;
 constexpr int kStagePad = 33;                                 // floats per staged row (conflict-free transpose)
-constexpr int kStagingBytes = 4 * 32 * kStagePad * 4;         // one 32x32 fp32 patch per epilogue warp
+constexpr int kEpiWarps = 8;
+constexpr int kStagingBytes = kEpiWarps * 32 * kStagePad * 4;  // one 32x32 fp32 patch per epilogue warp
 constexpr int kOffStaging = kStages * kStageBytes;            // 196608
-constexpr int kOffBars = kOffStaging + kStagingBytes;         // + 16896
+constexpr int kOffBars = kOffStaging + kStagingBytes;         // + 33792
 constexpr int kGemmSmem = kOffBars + 128;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
 constexpr int kTmemCols = 512;  // 2 accumulators x 256 fp32 columns
 
 struct GemmParams {
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&acc_full[a], 1);
-      ptx::mbar_init(&acc_empty[a], 128);
+      ptx::mbar_init(&acc_empty[a], 32 * kEpiWarps);
     }
     ptx::fence_mbar_init();
   }
@@ -219,8 +223,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stage = staging + q * 32 * kStagePad;
+    const int q = warp & 3;           // TMEM lane quarter this warp may access (warps 2..9 -> 2,3,0,1,2,3,0,1)
+    const int chalf = (warp - 2) >> 2;  // which 128-column half of the tile this warp drains
+    float* stage = staging + (warp - 2) * 32 * kStagePad;
     uint32_t t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
@@ -230,11 +235,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const uint32_t taddr = tmem_base + acc * kBN + (static_cast<uint32_t>(q * 32) << 16);
       const int row0 = m0 + q * 32;
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
+      for (int c = chalf * (kBN / 64); c < (chalf + 1) * (kBN / 64); ++c) {
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
         ptx::tmem_ld_wait();
-        if (c == kBN / 32 - 1) {  // last read of this accumulator: hand it back to the MMA warp
+        if (c == (chalf + 1) * (kBN / 64) - 1) {  // this warp's last read of the accumulator: hand it back to the MMA warp
           ptx::tc_fence_before();
           ptx::mbar_arrive(&acc_empty[acc]);
         }

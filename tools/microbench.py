@@ -94,6 +94,10 @@ if which in ("all", "gemm"):
         o = torch.empty(N_TOK, N, dtype=torch.bfloat16, device=dev)
         rec(name, *timeit(lambda: ops.gemm(a, b, bias, epi, out=o)), flops=2.0 * N_TOK * N * K)
         rec(name + "_cublas", *timeit(lambda: torch.matmul(a, b.t())), flops=2.0 * N_TOK * N * K)
+    wo = (torch.randn(D, D, device=dev) / math.sqrt(D)).bfloat16()
+    xs0 = torch.randn(N_TOK, D, device=dev)
+    g0 = torch.randn(D, device=dev)
+    rec("gemm_oproj_1536x1536_gate_resid", *timeit(lambda: ops.gemm(a, wo, g0, _lib.MC_EPI_BIAS_GATE_RESID, out=xs0, gate=g0)), flops=2.0 * N_TOK * D * D)
     a2 = torch.randn(N_TOK, FFN, device=dev).bfloat16()
     b2 = (torch.randn(D, FFN, device=dev) / math.sqrt(FFN)).bfloat16()
     xs = torch.randn(N_TOK, D, device=dev)
