@@ -36,6 +36,9 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct AttnParams {
   int Lq, Lk, heads;
+  int splits;      // > 1: blockIdx.z owns a contiguous range of KV tiles and writes a partial result (split-KV)
+  float* part_o;   // [splits][Lq][heads*128] fp32, each split's output normalised by its own row sum
+  float2* part_ml; // [splits][Lq][heads]     (row max in the scaled log2 domain, row sum)
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* out;
   int64_t ldo;
@@ -69,7 +72,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ;
   const int head = blockIdx.y;
-  const int n_tiles = (p.Lk + kBKV - 1) / kBKV;
+  const int total_tiles = (p.Lk + kBKV - 1) / kBKV;
+  const int per_split = (total_tiles + p.splits - 1) / p.splits;
+  const int t0 = blockIdx.z * per_split;                       // first (global) KV tile of this CTA
+  const int n_tiles = min(per_split, total_tiles - t0);        // local tile count (>= 1, guaranteed by the host)
 
   if (threadIdx.x == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) {
@@ -110,11 +116,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         const uint32_t ph = (j >> 1) & 1;
         ptx::mbar_wait(&k_empty[s], ph ^ 1);
         ptx::mbar_expect_tx(&k_full[s], kKBytes);
-        ptx::tma_load_2d(smem + kOffK + s * kKBytes, &tmap_k, &k_full[s], head * kHD, j * kBKV);
-        ptx::tma_load_2d(smem + kOffK + s * kKBytes + kKBytes / 2, &tmap_k, &k_full[s], head * kHD + 64, j * kBKV);
+        ptx::tma_load_2d(smem + kOffK + s * kKBytes, &tmap_k, &k_full[s], head * kHD, (t0 + j) * kBKV);
+        ptx::tma_load_2d(smem + kOffK + s * kKBytes + kKBytes / 2, &tmap_k, &k_full[s], head * kHD + 64, (t0 + j) * kBKV);
         ptx::mbar_wait(&v_empty[s], ph ^ 1);
         ptx::mbar_expect_tx(&v_full[s], kVBytes);
-        ptx::tma_load_2d(smem + kOffV + s * kVBytes, &tmap_vt, &v_full[s], j * kBKV, head * kHD);
+        ptx::tma_load_2d(smem + kOffV + s * kVBytes, &tmap_vt, &v_full[s], (t0 + j) * kBKV, head * kHD);
       }
     }
   } else if (warp == 5) {
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         ptx::mbar_arrive(&s_free[b]);
       }
 
-      const int valid = p.Lk - j * kBKV;  // columns >= valid are padding (only possible on the last tile)
+      const int valid = p.Lk - (t0 + j) * kBKV;  // columns >= valid are padding (only possible on the last tile)
       if (valid < kBKV) {                  // warp-uniform, taken at most once per CTA
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -292,21 +298,31 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     ptx::tc_fence_after();
     const float inv_l = 1.0f / l;
     const int row = q0 + r;
+    if (p.splits > 1 && row < p.Lq)
+      p.part_ml[(static_cast<int64_t>(blockIdx.z) * p.Lq + row) * p.heads + head] = make_float2(m, l);
 #pragma unroll 1
     for (int c = 0; c < kHD / 32; ++c) {
       uint32_t o[32];
       ptx::tmem_ld_32x32b_x32(tmem_o + lane_sel + c * 32, o);
       ptx::tmem_ld_wait();
       if (row < p.Lq) {
-        __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD + c * 32;
+        if (p.splits > 1) {
+          float* dst = p.part_o + (static_cast<int64_t>(blockIdx.z) * p.Lq + row) * (static_cast<int64_t>(p.heads) * kHD) + head * kHD + c * 32;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-          w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-          w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-          w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + i) = w;
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
+                                                              __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        } else {
+          __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + i) = w;
+          }
         }
       }
     }
@@ -315,6 +331,54 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 5) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Merge of the split-KV partials: out = sum_s w_s O_s / sum_s w_s with w_s = l_s * 2^(m_s - max_s m_s).
+__global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, int splits,
+                                                           int Lq, int heads, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  const int groups_per_row = heads * (kHD / 8);
+  const int64_t total = static_cast<int64_t>(Lq) * groups_per_row;
+  const int64_t W = static_cast<int64_t>(heads) * kHD;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / groups_per_row), g = static_cast<int>(i % groups_per_row);
+    const int head = g / (kHD / 8);
+    float mmax = -INFINITY;
+    for (int s = 0; s < splits; ++s) mmax = fmaxf(mmax, part_ml[(static_cast<int64_t>(s) * Lq + row) * heads + head].x);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float wsum = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float2 ml = part_ml[(static_cast<int64_t>(s) * Lq + row) * heads + head];
+      const float w = ml.y * ptx::ex2_approx(ml.x - mmax);
+      wsum += w;
+      float v[8];
+      ptx::ld_nc_v8_f32(part_o + (static_cast<int64_t>(s) * Lq + row) * W + g * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+    }
+    const float inv = 1.0f / wsum;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo + g * 8) = pack_bf16x8(acc);
+  }
+}
+
+// scratch for the split-KV partials: grown on demand (first use happens in an eager call, before any graph capture)
+static float* g_part_o = nullptr;
+static float2* g_part_ml = nullptr;
+static size_t g_part_elems = 0;
+
+static int32_t ensure_split_scratch(int splits, int Lq, int heads) {
+  const size_t need = static_cast<size_t>(splits) * Lq * heads * kHD;
+  if (need <= g_part_elems) return MC_OK;
+  // the previous (smaller) buffers are deliberately not freed: captured CUDA graphs may still point at them
+  g_part_o = nullptr;
+  g_part_ml = nullptr;
+  g_part_elems = 0;
+  cudaError_t e = cudaMalloc(&g_part_o, need * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&g_part_ml, static_cast<size_t>(splits) * Lq * heads * sizeof(float2));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(split-KV scratch)");
+  g_part_elems = need;
+  return MC_OK;
 }
 
 }  // namespace mc
@@ -343,13 +407,52 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
     if (e != cudaSuccess) return mc::cuda_fail(e, "cudaFuncSetAttribute(attn smem)");
     variant = v;
   }
-  mc::AttnParams p{Lq, Lk, heads, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo};
-  dim3 grid((Lq + mc::kBQ - 1) / mc::kBQ, heads);
+  // Work split. One CTA = one 128-row query tile of one head; with fewer than two waves of CTAs (2 per SM) the last,
+  // partially filled wave dominates (token-sharded runs: 4095 rows x 12 heads = 384 CTAs on 296 slots), so the KV range is
+  // split across blockIdx.z until there are about three waves, and the partial softmaxes are merged by a second kernel.
+  const int q_tiles = (Lq + mc::kBQ - 1) / mc::kBQ;
+  const int total_tiles = (Lk + mc::kBKV - 1) / mc::kBKV;
+  const double waves = static_cast<double>(q_tiles) * heads / (2.0 * mc::num_sms());
+  // MC_ATTN_SPLITS=n forces n splits (1 = never split); unset/0 = choose by wave fill. Read per call (tools/bench_split.py).
+  const char* es = getenv("MC_ATTN_SPLITS");
+  int forced_splits = es ? atoi(es) : 0;
+  if (forced_splits < 0 || forced_splits > 16) forced_splits = 0;
+  int splits = 1;
+  if (forced_splits > 0) {
+    splits = forced_splits;
+  } else if (waves < 4.0 && total_tiles >= 16) {
+    // smallest split count whose last wave is at least 92 % full, else the fullest
+    double best = 0.0;
+    for (int sp = 1; sp <= 8 && sp * 8 <= total_tiles; ++sp) {
+      const double w = waves * sp, fill = w / static_cast<double>(static_cast<int64_t>(w + 0.999999));
+      if (fill > best + 1e-9) best = fill, splits = sp;
+      if (fill >= 0.92) break;
+    }
+  }
+  if (splits > total_tiles) splits = total_tiles;
+  if (splits > 1) {
+    const int per = (total_tiles + splits - 1) / splits;
+    splits = (total_tiles + per - 1) / per;  // no empty split
+  }
+  if (splits > 1) {
+    MC_CHECK_ARG(ldo % 8 == 0, "mc_attn_fwd: ldo must be a multiple of 8");
+    rc = mc::ensure_split_scratch(splits, Lq, heads);
+    if (rc) return rc;
+  }
+  mc::AttnParams p{Lq, Lk, heads, splits, mc::g_part_o, mc::g_part_ml, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo};
+  dim3 grid(q_tiles, heads, splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (variant == 1)
     mc::attn_fwd_kernel<1><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
   else
     mc::attn_fwd_kernel<0><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
   MC_CHECK_LAUNCH("attn_fwd_kernel launch");
+  if (splits > 1) {
+    const int64_t total = static_cast<int64_t>(Lq) * heads * (mc::kHD / 8);
+    const int64_t want = (total + 255) / 256, cap = static_cast<int64_t>(mc::num_sms()) * 8;
+    mc::attn_combine_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, st>>>(mc::g_part_o, mc::g_part_ml, splits, Lq, heads,
+                                                                                      static_cast<__nv_bfloat16*>(out), ldo);
+    MC_CHECK_LAUNCH("attn_combine_kernel launch");
+  }
   return MC_OK;
 }

@@ -364,6 +364,30 @@ def test_attention_matches_sdpa_bf16_noise_level():
     assert e_ours <= 2.0 * e_sdpa + 1e-4, (e_ours, e_sdpa)
 
 
+@pytest.mark.parametrize("Lq,Lk,heads,splits", [(1000, 4095, 12, 0), (300, 2000, 2, 3), (129, 1100, 1, 2), (512, 4100, 4, 8), (256, 700, 2, 5)])
+def test_attention_split_kv(Lq, Lk, heads, splits, monkeypatch):
+    """Split-KV path (small grids, e.g. the per-rank shape of an 8-way token shard): every split normalises its own partial
+    softmax and a second kernel merges them. Checked against the fp64 reference, against the unsplit kernel, and for
+    reproducibility; ragged cases where the last split has fewer KV tiles (and a partial tile)."""
+    ops = _ops()
+    W = heads * 128
+    q = (torch.randn(Lq, W, device=DEV) * 3.0).bfloat16()
+    k = torch.randn(Lk, W, device=DEV).bfloat16()
+    v = torch.randn(Lk, W, device=DEV).bfloat16()
+    ld = (Lk + 7) // 8 * 8
+    vt = torch.zeros(W, ld, dtype=torch.bfloat16, device=DEV)
+    vt[:, :Lk] = v.t()
+    monkeypatch.setenv("MC_ATTN_SPLITS", "1")
+    one = ops.attention(q, k, vt[:, :Lk], heads).clone()
+    monkeypatch.setenv("MC_ATTN_SPLITS", str(splits))
+    outs = [ops.attention(q, k, vt[:, :Lk], heads).clone() for _ in range(3)]
+    ref = _attn_ref(q, k, v, heads)
+    err = (outs[0].float() - ref).abs()
+    assert float(err.max()) < 2e-2 and float(err.mean()) < 2e-3, (float(err.max()), float(err.mean()))
+    assert float((outs[0].float() - one.float()).abs().max()) < 8e-3   # bf16 output rounding of two fp32 results a few ulp apart
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
 @pytest.mark.parametrize("Lq,Lk,heads,qscale", [(4096, 512, 12, 1.0), (2048, 4096, 4, 5.0), (1000, 777, 3, 8.0)])
 def test_attention_is_bit_reproducible(Lq, Lk, heads, qscale):
     """Same inputs -> same bits, including short KV sequences (cross-attention shape) and score ranges that force the
