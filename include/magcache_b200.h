@@ -57,6 +57,11 @@ int32_t mc_nearest_interp_cfg(const double* src, int32_t L_total, double* dst, i
  * The reference keeps cnt in an int64 torch tensor, so its `cnt <= python_float` comparison happens in float32: reproduced. */
 #define MC_RETAIN_WAN22_T2V 3  /* skip-disabled if cnt < int(split*R) or (split <= cnt <= (n-split)*R + split) */
 #define MC_RETAIN_WAN22_I2V 4  /* skip-disabled if cnt < int(split + (n-split)*R) */
+#define MC_RETAIN_EXPLICIT 5   /* cnt >= split_step: Open-Sora `self.t >= self.skip_time`, eval/magcache/experiments/opensora.py:297, :424 */
+/* mc_ctrl_config.flags */
+#define MC_CTRL_SIGNED_ERR 1     /* err += 1 - ratio (no abs): eval/magcache/experiments/opensora.py:301 */
+#define MC_CTRL_RESET_AT_ZERO 2  /* accumulators re-initialised whenever a call sees cnt == 0: MagCache4FramePack/magcache_demo_gradio.py:253-256 */
+#define MC_CTRL_RATIO_VETO 4     /* skip only while |1 - mag_ratios[.]| <= ratio_veto: magcache_demo_gradio.py:265 */
 
 typedef struct mc_ctrl_config {
   int32_t num_steps;       /* forward calls per video: 2*sample_steps for CFG models (Wan :899), steps otherwise */
@@ -66,10 +71,17 @@ typedef struct mc_ctrl_config {
   int32_t retention_mode;  /* MC_RETAIN_* */
   int32_t veto_index;      /* -1 = none. FLUX :332: never skip when round_half_even(cnt*((veto_base-1)/(num_steps-1))) == veto_index */
   int32_t veto_base;       /* 28 for FLUX */
-  int32_t split_step;      /* MC_RETAIN_WAN22_*: calls made to the high-noise expert per video (2*high_noise_steps); else unused */
+  int32_t split_step;      /* MC_RETAIN_WAN22_*: calls made to the high-noise expert per video (2*high_noise_steps);
+                              MC_RETAIN_EXPLICIT: first call allowed to skip; else unused */
+  int32_t table_offset;    /* the ratio of call cnt is mag_ratios[cnt - table_offset]: 0 everywhere except the paper-evaluation forwards
+                              (`self.ratio[self.t-10]` eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py:775; `ratio[t-1]` opensora.py:298) */
+  int32_t min_cnt;         /* additionally require cnt >= min_cnt (FramePack `and self.cnt>=1`, magcache_demo_gradio.py:259); 0 = off */
+  int32_t flags;           /* MC_CTRL_* bits */
+  int32_t reserved;        /* must be 0 */
   double thresh;           /* magcache_thresh */
   double retention_ratio;
-  const double* mag_ratios; /* [num_steps], already interpolated; borrowed for the duration of the call / handle */
+  double ratio_veto;       /* with MC_CTRL_RATIO_VETO (FramePack: 0.06); a zero-filled tail of this struct means "Wan2.1 behaviour" */
+  const double* mag_ratios; /* [num_steps - table_offset], already interpolated; borrowed for the duration of the call / handle */
 } mc_ctrl_config;
 
 typedef struct mc_ctrl_state { /* mirrors the reference's class attributes (magcache_generate.py:897-906) */

@@ -14,7 +14,9 @@ MC_OK = 0
 MC_ERR_INVALID, MC_ERR_CUDA, MC_ERR_STATE = -1, -2, -3
 MC_F32, MC_BF16 = 0, 1
 MC_CMP_LT, MC_CMP_LE = 0, 1
-MC_RETAIN_FLOOR, MC_RETAIN_HALF_UP, MC_RETAIN_CEIL, MC_RETAIN_WAN22_T2V, MC_RETAIN_WAN22_I2V = 0, 1, 2, 3, 4
+MC_RETAIN_FLOOR, MC_RETAIN_HALF_UP, MC_RETAIN_CEIL, MC_RETAIN_WAN22_T2V, MC_RETAIN_WAN22_I2V, MC_RETAIN_EXPLICIT = 0, 1, 2, 3, 4, 5
+MC_CTRL_SIGNED_ERR, MC_CTRL_RESET_AT_ZERO, MC_CTRL_RATIO_VETO = 1, 2, 4
+ABI_VERSION = 3
 MC_EPI_BIAS_BF16, MC_EPI_BIAS_GELU_BF16, MC_EPI_BIAS_GATE_RESID, MC_EPI_ROWBIAS_BF16, MC_EPI_BIAS_F32 = 0, 1, 2, 3, 4
 
 
@@ -26,8 +28,9 @@ class MagCacheError(RuntimeError):
 
 class CtrlConfig(Structure):
     _fields_ = [("num_steps", c_int32), ("branches", c_int32), ("K", c_int32), ("cmp", c_int32), ("retention_mode", c_int32),
-                ("veto_index", c_int32), ("veto_base", c_int32), ("split_step", c_int32), ("thresh", c_double),
-                ("retention_ratio", c_double), ("mag_ratios", POINTER(c_double))]
+                ("veto_index", c_int32), ("veto_base", c_int32), ("split_step", c_int32), ("table_offset", c_int32),
+                ("min_cnt", c_int32), ("flags", c_int32), ("reserved", c_int32), ("thresh", c_double), ("retention_ratio", c_double),
+                ("ratio_veto", c_double), ("mag_ratios", POINTER(c_double))]
 
 
 class CtrlState(Structure):
@@ -79,6 +82,11 @@ for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)
     _fn.restype = c_int32
     _fn.argtypes = _args
+
+
+if lib.mc_abi_version() != ABI_VERSION:
+    raise ImportError(f"{LIB_PATH} has ABI version {lib.mc_abi_version()}, this package needs {ABI_VERSION}: rebuild with "
+                      "`python magcache_b200/build.py`")
 
 
 def check(rc):

@@ -9,14 +9,18 @@ from ._lib import CtrlConfig, CtrlState, check, lib
 
 
 def make_ctrl_config(num_steps, thresh, K, retention_ratio, mag_ratios, branches, cmp, retention_mode, veto_index=-1, veto_base=0,
-                     split_step=0):
+                     split_step=0, table_offset=0, min_cnt=0, flags=0, ratio_veto=None):
     arr = np.ascontiguousarray(mag_ratios, dtype=np.float64)
-    if len(arr) < num_steps:
-        raise IndexError(f"mag_ratios has {len(arr)} entries but num_steps={num_steps} (interpolate first, magcache_generate.py:915-919)")
+    if len(arr) < num_steps - table_offset:
+        raise IndexError(f"mag_ratios has {len(arr)} entries but num_steps={num_steps}, table_offset={table_offset} "
+                         "(interpolate first, magcache_generate.py:915-919)")
     cfg = CtrlConfig()
     cfg.num_steps, cfg.branches, cfg.K, cfg.cmp, cfg.retention_mode = int(num_steps), int(branches), int(K), int(cmp), int(retention_mode)
     cfg.veto_index, cfg.veto_base, cfg.split_step = int(veto_index), int(veto_base), int(split_step)
-    cfg.thresh, cfg.retention_ratio = float(thresh), float(retention_ratio)
+    if ratio_veto is not None:
+        flags |= _lib.MC_CTRL_RATIO_VETO
+    cfg.table_offset, cfg.min_cnt, cfg.flags, cfg.reserved = int(table_offset), int(min_cnt), int(flags), 0
+    cfg.thresh, cfg.retention_ratio, cfg.ratio_veto = float(thresh), float(retention_ratio), float(ratio_veto or 0.0)
     cfg.mag_ratios = arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
     cfg._keepalive = arr
     return cfg
@@ -41,9 +45,14 @@ class AttrController:
 
     def _config(self, o):
         mr = o.mag_ratios
-        key = (id(mr), len(mr), o.num_steps, float(o.magcache_thresh), int(o.K), float(o.retention_ratio))
+        kw = self.kw
+        if kw["retention_mode"] in (_lib.MC_RETAIN_WAN22_T2V, _lib.MC_RETAIN_WAN22_I2V):
+            # MagCache4Wan2.2/magcache_generate.py:344 `split_step = split_steps*2`; None (TI2V-5B) falls back to int(n*R), :301-303
+            split = getattr(o, "split_step", None)
+            kw = dict(kw, split_step=int(split)) if split is not None else dict(kw, retention_mode=_lib.MC_RETAIN_FLOOR)
+        key = (id(mr), len(mr), o.num_steps, float(o.magcache_thresh), int(o.K), float(o.retention_ratio), kw.get("split_step"))
         if self._key != key:
-            self._cfg = make_ctrl_config(o.num_steps, o.magcache_thresh, o.K, o.retention_ratio, np.asarray(mr, dtype=np.float64), **self.kw)
+            self._cfg = make_ctrl_config(o.num_steps, o.magcache_thresh, o.K, o.retention_ratio, np.asarray(mr, dtype=np.float64), **kw)
             self._key = key
         return self._cfg
 

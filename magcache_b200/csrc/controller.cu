@@ -3,6 +3,8 @@
 //   controller   MagCache4Wan2.1/magcache_generate.py:277-292, :306-311
 //                MagCache4FLUX/magcache_flux.py:326-338, :431-436
 //                MagCache4HunyuanVideo/magcache_sample_video.py:88-102, :149-154
+//                MagCache4FramePack/magcache_demo_gradio.py:252-270 (ratio veto, cnt >= 1, re-initialisation at cnt == 0)
+//                eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py:770-786 (table offset 10), opensora.py:297-308 (signed error)
 //   interp       MagCache4Wan2.1/magcache_generate.py:27-34, :915-919
 #include <cmath>
 #include <cstring>
@@ -58,8 +60,10 @@ static bool eligible(const mc_ctrl_config* c, int32_t cnt) {
       const bool window = (static_cast<float>(cnt) <= upper) && (cnt >= c->split_step);
       return !(early || window);
     }
+    case MC_RETAIN_EXPLICIT:  // opensora.py:297 `self.t >= self.skip_time`
+      return cnt >= c->split_step && cnt >= c->min_cnt;
     default:
-      return cnt >= retention_start(c);
+      return cnt >= retention_start(c) && cnt >= c->min_cnt;
   }
 }
 
@@ -69,7 +73,11 @@ static int32_t check_cfg(const mc_ctrl_config* c) {
   MC_CHECK_ARG(c->branches == 1 || c->branches == 2, "mc_ctrl: branches=%d must be 1 or 2", c->branches);
   MC_CHECK_ARG(c->mag_ratios != nullptr, "mc_ctrl: mag_ratios is null (reference: AttributeError, no table matched ckpt_dir)");
   MC_CHECK_ARG(c->cmp == MC_CMP_LT || c->cmp == MC_CMP_LE, "mc_ctrl: bad cmp %d", c->cmp);
-  MC_CHECK_ARG(c->retention_mode >= 0 && c->retention_mode <= 4, "mc_ctrl: bad retention_mode %d", c->retention_mode);
+  MC_CHECK_ARG(c->retention_mode >= 0 && c->retention_mode <= 5, "mc_ctrl: bad retention_mode %d", c->retention_mode);
+  MC_CHECK_ARG(c->table_offset >= 0 && c->table_offset < c->num_steps, "mc_ctrl: table_offset=%d outside [0, num_steps)", c->table_offset);
+  MC_CHECK_ARG(c->min_cnt >= 0, "mc_ctrl: min_cnt=%d must be >= 0", c->min_cnt);
+  MC_CHECK_ARG((c->flags & ~(MC_CTRL_SIGNED_ERR | MC_CTRL_RESET_AT_ZERO | MC_CTRL_RATIO_VETO)) == 0 && c->reserved == 0, "mc_ctrl: unknown flag bits 0x%x", c->flags);
+  MC_CHECK_ARG(!(c->flags & MC_CTRL_RATIO_VETO) || c->ratio_veto >= 0.0, "mc_ctrl: ratio_veto must be >= 0");
   MC_CHECK_ARG(c->retention_mode < MC_RETAIN_WAN22_T2V || (c->split_step >= 0 && c->split_step <= c->num_steps),
                "mc_ctrl: split_step=%d outside [0, num_steps]", c->split_step);
   MC_CHECK_ARG(c->veto_index < 0 || c->num_steps >= 2, "mc_ctrl: step veto needs num_steps >= 2 (reference divides by num_steps-1)");
@@ -82,16 +90,28 @@ static inline void reset_branch(mc_ctrl_state* st, int i) {
   st->accumulated_ratio[i] = 1.0;
 }
 
+// returns 0/1, or a negative error code
 static int32_t decide(const mc_ctrl_config* c, mc_ctrl_state* st) {
+  if ((c->flags & MC_CTRL_RESET_AT_ZERO) && st->cnt == 0) {
+    reset_branch(st, 0);
+    reset_branch(st, 1);
+  }
   if (!eligible(c, st->cnt)) return 0;
+  if (st->cnt < c->table_offset) {
+    // the reference would read ratio[negative] = an entry counted from the END of the table; refuse instead of reproducing that
+    set_error("mc_ctrl_decide: call %d is skip-eligible but precedes table_offset=%d (retention window shorter than the table offset)", st->cnt,
+              c->table_offset);
+    return MC_ERR_STATE;
+  }
   const int i = (c->branches == 2) ? (st->cnt % 2) : 0;
-  const double cur = c->mag_ratios[st->cnt];
+  const double cur = c->mag_ratios[st->cnt - c->table_offset];
   st->accumulated_ratio[i] = st->accumulated_ratio[i] * cur;
   st->accumulated_steps[i] += 1;
-  const double skip_err = std::fabs(1.0 - st->accumulated_ratio[i]);
-  st->accumulated_err[i] += skip_err;
+  const double diff = 1.0 - st->accumulated_ratio[i];
+  st->accumulated_err[i] += (c->flags & MC_CTRL_SIGNED_ERR) ? diff : std::fabs(diff);
   bool ok = (c->cmp == MC_CMP_LE) ? (st->accumulated_err[i] <= c->thresh) : (st->accumulated_err[i] < c->thresh);
   ok = ok && (st->accumulated_steps[i] <= c->K);
+  if (c->flags & MC_CTRL_RATIO_VETO) ok = ok && (std::fabs(1.0 - cur) <= c->ratio_veto);
   if (c->veto_index >= 0) {
     // np.round(cnt * ((base-1)/(num_steps-1))).astype(int) != veto_index ; nearbyint = round-half-even
     const double scale = static_cast<double>(c->veto_base - 1) / static_cast<double>(c->num_steps - 1);
@@ -117,7 +137,7 @@ static void advance(const mc_ctrl_config* c, mc_ctrl_state* st) {
 extern "C" {
 
 const char* mc_last_error(void) { return mc::g_err; }
-int32_t mc_abi_version(void) { return 2; }
+int32_t mc_abi_version(void) { return 3; }
 
 int32_t mc_nearest_interp(const double* src, int32_t L, double* dst, int32_t T) {
   MC_CHECK_ARG(src && dst, "mc_nearest_interp: null pointer");
@@ -182,7 +202,9 @@ int32_t mc_ctrl_decide(const mc_ctrl_config* cfg, mc_ctrl_state* st, int32_t* sk
     mc::set_error("mc_ctrl_decide: cnt=%d outside [0, %d)", st->cnt, cfg->num_steps);
     return MC_ERR_STATE;
   }
-  *skip = mc::decide(cfg, st);
+  const int32_t d = mc::decide(cfg, st);
+  if (d < 0) return d;
+  *skip = d;
   return MC_OK;
 }
 
@@ -200,7 +222,9 @@ int32_t mc_ctrl_mask(const mc_ctrl_config* cfg, int32_t calls, uint8_t* mask) {
   std::memset(&st, 0, sizeof(st));
   st.accumulated_ratio[0] = st.accumulated_ratio[1] = 1.0;
   for (int32_t i = 0; i < calls; ++i) {
-    mask[i] = static_cast<uint8_t>(mc::decide(cfg, &st));
+    const int32_t d = mc::decide(cfg, &st);
+    if (d < 0) return d;
+    mask[i] = static_cast<uint8_t>(d);
     mc::advance(cfg, &st);
   }
   return MC_OK;
@@ -211,6 +235,11 @@ int32_t mc_ctrl_validate(const mc_ctrl_config* cfg) {
   if (rc) return rc;
   int32_t start = 0;
   while (start < cfg->num_steps && !mc::eligible(cfg, start)) ++start;
+  if (start < cfg->num_steps && start < cfg->table_offset) {
+    mc::set_error("mc_ctrl_validate: first skip-eligible call %d precedes table_offset=%d (the reference would index the table from its end)", start,
+                  cfg->table_offset);
+    return MC_ERR_STATE;
+  }
   if (start < cfg->branches) {
     mc::set_error(
         "mc_ctrl_validate: first skip-eligible call is %d but %d residual slot(s) must be filled first "

@@ -186,28 +186,33 @@ def init_magcache_calibration(model, sample_steps):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# Scalar-state families (FLUX, HunyuanVideo): controller + cache kernels around a caller-supplied block stack
+# Other adapters: controller + cache kernels around a caller-supplied block stack
 # ------------------------------------------------------------------------------------------------------------------
-_FLUX_CTRL = dict(branches=1, cmp=1, retention_mode=1, veto_index=11, veto_base=28)   # magcache_flux.py:327-332
-_HUNYUAN_CTRL = dict(branches=1, cmp=1, retention_mode=0, veto_index=-1, veto_base=0)  # magcache_sample_video.py:90-96
-
-
 def magcache_branch(self, hidden, run_blocks, family, cache_attr):
-    """The hit/miss branch of the FLUX / Hunyuan forwards (magcache_flux.py:326-427, magcache_sample_video.py:88-141):
-    decides with the family's controller, then either adds the cached residual (K1 kernel) or calls `run_blocks(hidden)`
-    (the model's own transformer stack) and stores `out - hidden` (K2 kernel) under `cache_attr`. Advances the counter."""
+    """The hit/miss branch of the other adapters' forwards — FLUX / Kontext (magcache_flux.py:326-427), HunyuanVideo
+    (magcache_sample_video.py:88-141), FramePack (magcache_demo_gradio.py:252-300), Wan2.2 / Qwen-Image
+    (MagCache4Wan2.2/magcache_generate.py:290-334): decides with the family's controller (`config.FAMILIES`), then either adds
+    the cached residual (K1 kernel) or calls `run_blocks(hidden)` (the model's own transformer stack) and stores `out - hidden`
+    (K2 kernel) under `cache_attr` — a tensor for scalar-state families, a 2-list indexed by `cnt % 2` for per-branch ones.
+    Advances the counter. Wan2.2's expert boundary is read from `self.split_step` like upstream (:344)."""
+    from .config import FAMILIES
     ctrls = self.__dict__.setdefault("_mc_ctrls", {})
     if family not in ctrls:
-        ctrls[family] = AttrController(_FLUX_CTRL if family == "flux" else _HUNYUAN_CTRL)
+        ctrls[family] = AttrController(FAMILIES[family])
     ctrl = ctrls[family]
+    per_branch = FAMILIES[family]["branches"] == 2
+    slot = int(self.cnt) % 2 if per_branch else None
     if ctrl.decide(self):
-        cur = getattr(self, cache_attr)
+        cur = getattr(self, cache_attr)[slot] if per_branch else getattr(self, cache_attr)
         if cur is None:
             raise TypeError("magcache_b200: cache hit with an empty residual cache (reference: Tensor + NoneType)")
         out = ops.cache_hit_add(hidden.contiguous(), cur)
     else:
         out = run_blocks(hidden)
         cur = ops.residual_sub(out.contiguous(), hidden.contiguous())
-    setattr(self, cache_attr, cur)
+    if per_branch:
+        getattr(self, cache_attr)[slot] = cur
+    else:
+        setattr(self, cache_attr, cur)
     ctrl.advance(self)
     return out

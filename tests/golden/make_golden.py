@@ -17,7 +17,7 @@ host logic and executes those statements, unmodified, against a stand-in `self`:
 * the calibration statistics block    MagCache4Wan2.1/magcache_generate.py:166-173
 * the calibrated `mag_ratios` literals (:910,:912,:1002,:1004,:1142,:1144; FLUX :459; Hunyuan :316,:318)
 
-Outputs (committed):  tables.json, nearest_interp.json, masks.json, calib_stats.json
+Outputs (committed):  tables.json, nearest_interp.json, masks.json, calib_stats.json, extra_adapters.json, paper_eval_adapters.json
 Nothing here is imported by the product; tests/ read the JSON files only.
 """
 import ast
@@ -36,6 +36,10 @@ HUN = f"{REF}/MagCache4HunyuanVideo/magcache_sample_video.py"
 WAN22 = f"{REF}/MagCache4Wan2.2/magcache_generate.py"
 QWEN = f"{REF}/MagCache4QwenImage/magcache_generate.py"
 OMNI = f"{REF}/MagCache4OmniGen2/magcache/magcache_utils.py"
+FRAMEPACK = f"{REF}/MagCache4FramePack/magcache_demo_gradio.py"
+FRAMEPACK_F1 = f"{REF}/MagCache4FramePack/magcache_demo_gradio_f1.py"
+EVAL_WAN = f"{REF}/eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py"
+OPENSORA = f"{REF}/eval/magcache/experiments/opensora.py"
 
 
 def _tree(path):
@@ -321,6 +325,175 @@ def extra_cases(tables, interp):
     return out
 
 
+# ----------------------------------------------------------------------------------------------
+# FramePack and the two paper-evaluation forwards (SURVEY Appendix A rows FramePack / Wan2.1 eval / Open-Sora)
+# ----------------------------------------------------------------------------------------------
+def _parent_bodies(tree):
+    for node in ast.walk(tree):
+        for field in ("body", "orelse", "finalbody"):
+            body = getattr(node, field, None)
+            if isinstance(body, list):
+                yield body
+
+
+def _counter_tail(fn, attr):
+    """`self.<attr> += 1` and the `if` that follows it, wherever they are nested."""
+    for body in _parent_bodies(fn):
+        for i, st in enumerate(body):
+            if isinstance(st, ast.AugAssign) and isinstance(st.target, ast.Attribute) and st.target.attr == attr:
+                assert isinstance(body[i + 1], ast.If)
+                return [st, body[i + 1]]
+    raise AssertionError(attr)
+
+
+def _class_attr_literal(path, attr):
+    """Value of the (un-commented) `<...>.__class__.<attr> = <expr>` assignment of a script, evaluated with numpy."""
+    for n in ast.walk(_tree(path)):
+        if isinstance(n, ast.Assign) and isinstance(n.targets[0], ast.Attribute) and n.targets[0].attr == attr:
+            return eval(compile(ast.Expression(n.value), "<t>", "eval"), {"np": np})
+    raise AssertionError((path, attr))
+
+
+class RefControllerFramePack:
+    """magcache_demo_gradio.py:252-270 (re-initialisation at cnt == 0, controller with the |1 - ratio| <= 0.06 veto and
+    `cnt >= 1`) and :298-300 (counter); `initialize_magcache` (:63-74) is executed whole, table literal and interpolation included."""
+
+    def __init__(self, path):
+        tree = _tree(path)
+        fn = _func(tree, "magcache_framepack_forward")
+        outer = [st for st in fn.body if isinstance(st, ast.If) and _mentions(st.test, "enable_magcache")]
+        assert len(outer) == 1
+        body = outer[0].body
+        head = []
+        for st in body:
+            head.append(st)
+            if isinstance(st, ast.If) and _mentions(st.test, "retention_ratio"):
+                break
+        assert len(head) == 3, [type(x).__name__ for x in head]  # if cnt == 0 / skip_forward = False / controller
+        self.ctrl = _compile(head)
+        self.tail = _compile(_counter_tail(outer[0], "cnt"))
+        env = {"np": np}
+        exec(_compile([_func(tree, "nearest_interp"), _func(tree, "initialize_magcache")]), env)
+        self.init = env["initialize_magcache"]
+
+    def state(self, steps, thresh, K, R):
+        s = types.SimpleNamespace()
+        self.init(s, True, steps, thresh, K, R)
+        return s
+
+    def call(self, state):
+        env = {"self": state, "np": np}
+        exec(self.ctrl, env)
+        skip = bool(env["skip_forward"])
+        exec(self.tail, env)
+        return skip
+
+
+class RefControllerEvalWan:
+    """eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py:770-786 (controller, `ratio[t-10]`) and :807-815 (counter)."""
+
+    def __init__(self):
+        fn = _func(_tree(EVAL_WAN), "magcache_forward")
+        i0 = next(i for i, st in enumerate(fn.body) if isinstance(st, ast.Assign) and getattr(st.targets[0], "id", None) == "skip_time")
+        ctrl = [fn.body[i0]] + [st for st in fn.body if isinstance(st, ast.If) and _mentions(st.test, "t") and isinstance(st.test, ast.Compare)
+                                and getattr(st.test.comparators[0], "id", None) == "skip_time"]
+        assert len(ctrl) == 2
+        self.ctrl = _compile(ctrl)
+        self.tail = _compile(_counter_tail(fn, "t"))
+        self.table = np.asarray(_class_attr_literal(EVAL_WAN, "ratio"), dtype=np.float64)
+
+    def state(self, steps, thresh, K, table=None):
+        s = types.SimpleNamespace(t=0, num_steps=2 * steps, magcache_thresh=thresh, magcache_K=K, accumulated_err=[0, 0], accumulated_sim=[1, 1],
+                                  accumulated_steps=[0, 0], skip_steps=0, residual_cache=np.zeros((2, 1, 1)),
+                                  ratio=self.table if table is None else table)  # attribute block :1131-1150
+        return s
+
+    def call(self, state):
+        env = {"self": state, "np": np, "skip_forward": False}
+        exec(self.ctrl, env)
+        skip = bool(env["skip_forward"])
+        exec(self.tail, env)
+        return skip
+
+
+class RefControllerOpenSora:
+    """eval/magcache/experiments/opensora.py:297-308 (controller: `ratio[t-1]`, error accumulated WITHOUT abs) and :348-354
+    (counter, video length 30 hard-coded)."""
+
+    def __init__(self):
+        fn = _func(_tree(OPENSORA), "magcache_forward")
+        ctrl = [st for st in ast.walk(fn) if isinstance(st, ast.If) and isinstance(st.test, ast.Compare) and _mentions(st.test, "skip_time")]
+        assert len(ctrl) == 1
+        self.ctrl = _compile(ctrl)
+        self.tail = _compile(_counter_tail(fn, "t"))
+        self.table = np.asarray(_class_attr_literal(OPENSORA, "ratio"), dtype=np.float64)
+
+    def state(self, thresh, K, skip_time):
+        return types.SimpleNamespace(t=0, magcache_thresh=thresh, K=K, skip_time=skip_time, accumulated_err=0, accumulated_sim=1,
+                                     accumulated_steps=0, skip_steps=0, residual_cache=np.zeros((1, 3)), ratio=self.table)  # :419-433
+
+    def call(self, state):
+        env = {"self": state, "np": np, "skip_forward": False}
+        exec(self.ctrl, env)
+        skip = bool(env["skip_forward"])
+        exec(self.tail, env)
+        return skip
+
+
+def remaining_tables():
+    """Table literals not covered above: Qwen-Image / Qwen-Image-Edit (`mag_ratios = [...]` + [1.0]*2 prefix, :76 / :79) and
+    FLUX-Kontext (magcache_flux_kontext.py:458)."""
+    out = {}
+    for key, path in (("qwen_image", QWEN), ("qwen_image_edit", f"{REF}/MagCache4QwenImageEdit/magcache_generate.py")):
+        found = [n for n in ast.walk(_tree(path)) if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Name)
+                 and n.targets[0].id == "mag_ratios" and isinstance(n.value, ast.List) and len(n.value.elts) > 10]
+        assert len(found) == 1, (path, len(found))
+        vals = eval(compile(ast.Expression(found[0].value), "<tbl>", "eval"))
+        out[key] = {"source": f"{os.path.relpath(path, REF)}:{found[0].lineno} (+ [1.0]*2 prefix in init_magcache)",
+                    "values": [1.0, 1.0] + [float(v) for v in vals]}
+    kpath = f"{REF}/MagCache4FLUX_Kontext/magcache_flux_kontext.py"
+    out["flux_kontext"] = {"source": "MagCache4FLUX_Kontext/magcache_flux_kontext.py:458",
+                           "values": [float(v) for v in _class_attr_literal(kpath, "mag_ratios")]}
+    return out
+
+
+def paper_eval_cases():
+    out = {"tables": {}, "framepack_masks": [], "eval_wan_masks": [], "opensora_masks": []}
+    for key, path in (("framepack", FRAMEPACK), ("framepack_f1", FRAMEPACK_F1)):
+        ref = RefControllerFramePack(path)
+        out["tables"][key] = {"source": f"{os.path.relpath(path, REF)}:70", "values": [float(v) for v in ref.state(25, 0.1, 3, 0.2).mag_ratios]}
+        for steps in (25, 20, 30, 50, 12):
+            for thresh, K, R in [(0.1, 3, 0.2), (0.1, 2, 0.2), (0.2, 5, 0.1), (0.3, 8, 0.0), (0.05, 3, 0.02), (0.6, 6, 0.3)]:
+                st = ref.state(steps, thresh, K, R)
+                n = 2 * steps + 3
+                m = run_mask(ref, st, n)
+                out["framepack_masks"].append({"table": key, "steps": steps, "thresh": thresh, "K": K, "R": R, "calls": n, "mask": "".join(map(str, m)),
+                                               "ratios": [float(v) for v in st.mag_ratios],
+                                               "final": {"cnt": int(st.cnt), "accumulated_err": float(st.accumulated_err),
+                                                         "accumulated_ratio": float(st.accumulated_ratio), "accumulated_steps": int(st.accumulated_steps)}})
+    ew = RefControllerEvalWan()
+    out["tables"]["wan2.1_eval"] = {"source": "eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py:1144", "values": [float(v) for v in ew.table]}
+    for thresh, K in [(0.12, 2), (0.12, 4), (0.24, 6), (0.06, 1), (0.03, 3), (0.5, 10)]:
+        st = ew.state(50, thresh, K)
+        n = 2 * 100 + 9
+        m = run_mask(ew, st, n)
+        out["eval_wan_masks"].append({"steps": 50, "thresh": thresh, "K": K, "calls": n, "mask": "".join(map(str, m)),
+                                      "skipped_first_video": int(sum(m[:100])),
+                                      "final": {"cnt": int(st.t), "accumulated_err": [float(v) for v in st.accumulated_err],
+                                                "accumulated_ratio": [float(v) for v in st.accumulated_sim],
+                                                "accumulated_steps": [int(v) for v in st.accumulated_steps]}})
+    os_ = RefControllerOpenSora()
+    out["tables"]["opensora_eval"] = {"source": "eval/magcache/experiments/opensora.py:433", "values": [float(v) for v in os_.table]}
+    for thresh, K, skip_time in [(0.12, 3, 6), (0.24, 5, 6), (0.06, 2, 6), (0.12, 3, 3), (0.4, 8, 1), (0.01, 3, 10), (0.005, 29, 1)]:
+        st = os_.state(thresh, K, skip_time)
+        n = 2 * 30 + 4
+        m = run_mask(os_, st, n)
+        out["opensora_masks"].append({"steps": 30, "thresh": thresh, "K": K, "skip_time": skip_time, "calls": n, "mask": "".join(map(str, m)),
+                                      "final": {"cnt": int(st.t), "accumulated_err": float(st.accumulated_err),
+                                                "accumulated_ratio": float(st.accumulated_sim), "accumulated_steps": int(st.accumulated_steps)}})
+    return out
+
+
 def main():
     tables = extract_tables()
     with open(f"{OUT}/tables.json", "w") as f:
@@ -385,6 +558,21 @@ def main():
     with open(f"{OUT}/extra_adapters.json", "w") as f:
         json.dump(extra, f, indent=0)
     print("extra adapters:", {k: len(v) for k, v in extra.items()})
+
+    pe = paper_eval_cases()
+    with open(f"{OUT}/paper_eval_adapters.json", "w") as f:
+        json.dump(pe, f, indent=0)
+    print("framepack / paper-eval adapters:", {k: len(v) for k, v in pe.items()})
+    # every calibrated table of the reference in one file (the package ships a copy: magcache_b200/tables.json)
+    every = dict(tables)
+    every.update(extra["tables"])
+    every.update(pe["tables"])
+    every.update(remaining_tables())
+    with open(f"{OUT}/tables_all.json", "w") as f:
+        json.dump(every, f, indent=0)
+    print("all tables:", {k: len(v["values"]) for k, v in every.items()})
+    for c in pe["eval_wan_masks"][:2] + pe["opensora_masks"][:2] + pe["framepack_masks"][:1]:
+        print({k: v for k, v in c.items() if k in ("thresh", "K", "mask", "skipped_first_video")})
 
     cal = calib_cases()
     with open(f"{OUT}/calib_stats.json", "w") as f:

@@ -34,8 +34,11 @@ def test_interp_cfg_matches_oracle(steps):
 def test_presets_resolve_and_validate():
     for name, cfg in mc.PRESETS.items():
         r = cfg.resolved_ratios()
-        assert len(r) == cfg.num_steps, name
-        assert cfg.branches == (2 if cfg.family == "wan2.1" else 1)
+        off = mc.config.FAMILIES[cfg.family].get("table_offset", 0)
+        assert len(r) == cfg.num_steps - off, name
+        assert cfg.branches == (2 if cfg.family.startswith(("wan", "qwen")) else 1)
+        m = cfg.schedule()
+        assert len(m) == cfg.num_steps and 0 < int(m.sum()) < cfg.num_steps and not m[:cfg.branches].any(), name
 
 
 def test_attr_controller_instance_vs_class_attributes():

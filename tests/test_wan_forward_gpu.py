@@ -175,6 +175,55 @@ def test_scalar_family_branch_flux_and_hunyuan():
             assert m.cnt == ref_ctl.cnt
 
 
+def test_branch_other_adapters_follow_their_preset_schedule():
+    """FramePack (ratio veto, cnt >= 1, scalar cache), Qwen-Image and Wan2.2 T2V-A14B (per-CFG-branch cache list, expert
+    window read from `split_step`): the branch taken on every call is the one `MagCacheConfig.schedule()` predicts — itself
+    pinned to the reference's statements by tests/test_paper_eval_adapters.py and tests/test_extra_adapters.py — and the K1/K2
+    arithmetic equals torch's."""
+    from magcache_b200 import PRESETS, magcache_branch
+    for preset, attr in [("framepack-E010K3R02", "previous_residual"), ("qwen-image-E006K2R02", "residual_cache"),
+                         ("wan2.2-t2v-a14b-E006K2R04", "residual_cache")]:
+        cfg = PRESETS[preset]
+        per_branch = cfg.branches == 2
+        n_calls = cfg.num_steps + 5
+        want = cfg.schedule(n_calls)
+        cls = type("Fake", (), {})
+        m = cls()
+        cls.cnt, cls.num_steps, cls.magcache_thresh, cls.K, cls.retention_ratio = 0, cfg.num_steps, cfg.thresh, cfg.K, cfg.retention_ratio
+        cls.mag_ratios = cfg.resolved_ratios()
+        if per_branch:
+            cls.accumulated_ratio, cls.accumulated_err, cls.accumulated_steps = [1.0, 1.0], [0.0, 0.0], [0, 0]
+            setattr(cls, attr, [None, None])
+            cls.split_step = None if cfg.high_noise_steps is None else 2 * cfg.high_noise_steps
+        else:
+            cls.accumulated_ratio, cls.accumulated_err, cls.accumulated_steps = 1.0, 0, 0
+            setattr(cls, attr, None)
+        g = torch.Generator(device=DEV).manual_seed(1)
+        cache_ref = [None, None]
+        ran = []
+        for i in range(n_calls):
+            slot = (m.cnt % 2) if per_branch else 0
+            h = torch.randn(1, 1024, 384, device=DEV, generator=g).bfloat16()
+
+            def blocks(z, i=i):
+                ran.append(i)
+                return (z.float() * 0.99 - 0.002 * (i + 1)).bfloat16()
+
+            before = len(ran)
+            out = magcache_branch(m, h, blocks, cfg.family, attr)
+            skipped = len(ran) == before
+            assert skipped == bool(want[i]), (preset, i)
+            if skipped:
+                exp = h + cache_ref[slot]
+            else:
+                exp = (h.float() * 0.99 - 0.002 * (i + 1)).bfloat16()
+                cache_ref[slot] = exp - h
+            assert torch.equal(out, exp), (preset, i)
+            cur = getattr(m, attr)[slot] if per_branch else getattr(m, attr)
+            assert torch.equal(cur, cache_ref[slot])
+        assert int(m.cnt) == n_calls % cfg.num_steps
+
+
 def test_wan14b_shaped_blocks_vs_oracle():
     """BASELINE configs[4] shapes (dim 5120, 40 heads, ffn 13824) at reduced depth / token count: exercises the wide-row
     LayerNorm / RMSNorm paths (cols > 2048), 40-head attention and the N = 13824 GEMM tiling against the oracle."""
