@@ -256,9 +256,8 @@ def run_ours(args, rank, world):
         t = t_dev[i % SAMPLE_STEPS]
         cond = model([x], t=t, context=[ctx_d], seq_len=N_TOK)[0]
         uncond = model([x], t=t, context=[ctxn_d], seq_len=N_TOK)[0]
-        # caller-side code (wan_magcache.py:301-310): CFG combine (one kernel) + an Euler flow step standing in for FlowUniPC
-        v = ops.cfg_combine(cond, uncond, guide)
-        return x + float(sig[(i % SAMPLE_STEPS) + 1] - sig[i % SAMPLE_STEPS]) * v
+        # caller-side code (wan_magcache.py:301-310): CFG combine + an Euler flow step standing in for FlowUniPC, one fused kernel
+        return ops.cfg_step(cond, uncond, guide, x, float(sig[(i % SAMPLE_STEPS) + 1] - sig[i % SAMPLE_STEPS]), out=x)
 
     def step_e2e(i):
         t = t_dev[i % SAMPLE_STEPS]

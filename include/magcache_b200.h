@@ -122,6 +122,18 @@ int32_t mc_residual_sub(const void* x_out, int32_t xo_dtype, const void* x_in, i
  * eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py:301-302 — one pass, fp32, each operation rounded like torch eager. */
 int32_t mc_cfg_combine(const float* cond, const float* uncond, float guide_scale, float* out, int64_t n, void* stream);
 
+/* CFG combine + the scheduler's latent update in ONE pass (caller loop wan_magcache.py:301-310:
+ * `noise_pred = ...; temp_x0 = sample_scheduler.step(noise_pred, t, latents)`). The flow-matching solvers the reference uses
+ * (FlowUniPC, FlowDPM++ — upstream, not in the reference tree — and plain Euler) all compute
+ *     v   = uncond + guide_scale * (cond - uncond)
+ *     out = coef_x * x + coef_v * v + sum_{i < n_hist} coef_h[i] * hist[i]        (Euler: coef_x = 1, coef_v = sigma_next - sigma)
+ *     x0  = x - sigma * v                         (written when x0_out != NULL: the x0-prediction the multistep solvers store)
+ * with scalar coefficients computed on the host. fp32; every product / sum rounded separately in the order written (bit-equal
+ * to the torch eager chain). out may alias x (in-place update); hist: device pointers, n_hist <= 4. */
+int32_t mc_cfg_step(const float* cond, const float* uncond, float guide_scale, const float* x, float coef_x, float coef_v,
+                    const float* const* hist, const float* coef_h, int32_t n_hist, float sigma, float* out, float* x0_out, int64_t n,
+                    void* stream);
+
 /* calibration statistics                              magcache_generate.py:167-169 (one pass instead of ~7 + 3 syncs).
  * r_cur, r_prev: [rows, cols]. stats (device, 4 doubles, overwritten): sum(ratio), sum(ratio^2), sum(1-cos), rows
  * with ratio = ||r_cur[i]||2 / (||r_prev[i]||2 + denom_eps)  (denom_eps = 0 Wan :167; 1e-8 eval variant wan_magcache.py:652)

@@ -52,6 +52,8 @@ SIGNATURES = {
     "mc_cache_hit_add": [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
     "mc_residual_sub": [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
     "mc_cfg_combine": [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p],
+    "mc_cfg_step": [c_void_p, c_void_p, c_float, c_void_p, c_float, c_float, POINTER(c_void_p), POINTER(c_float), c_int32, c_float, c_void_p,
+                    c_void_p, c_int64, c_void_p],
     "mc_residual_stats": [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_double, c_void_p, c_void_p],
     "mc_residual_sub_stats": [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p, c_void_p],
     "mc_patchify": [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p],

@@ -144,6 +144,84 @@ __global__ void cfg_combine_tail_kernel(const float* __restrict__ cond, const fl
   if (i < n) out[i] = __fadd_rn(uncond[i], __fmul_rn(g, __fsub_rn(cond[i], uncond[i])));
 }
 
+// ---- CFG combine + scheduler update of the caller loop in one pass ------------------------------------
+// Flow-matching samplers (Euler, FlowUniPC, FlowDPM++) all update the latent by a linear combination of the current sample,
+// the guided model output and a few stored tensors with host-computed scalar coefficients:
+//   v   = uncond + g * (cond - uncond)
+//   out = coef_x * x + coef_v * v + sum_i coef_h[i] * hist[i]            (Euler: coef_x = 1, coef_v = sigma_next - sigma)
+//   x0  = x - sigma * v                                                  (optional: the x0-prediction multistep solvers keep)
+// Every product and sum is rounded separately, in this order, like the chain of torch eager kernels it replaces.
+struct CfgStepArgs {
+  const float* cond;
+  const float* uncond;
+  const float* x;
+  const float* hist[4];
+  float coef_h[4];
+  float* out;
+  float* x0_out;
+  float g, coef_x, coef_v, sigma;
+  int n_hist;
+};
+
+template <int NH>
+__device__ __forceinline__ float cfg_step_one(const CfgStepArgs& a, float c, float u, float x, const float (&h)[4], float* x0) {
+  const float v = __fadd_rn(u, __fmul_rn(a.g, __fsub_rn(c, u)));
+  float acc = __fadd_rn(__fmul_rn(a.coef_x, x), __fmul_rn(a.coef_v, v));
+#pragma unroll
+  for (int k = 0; k < NH; ++k) acc = __fadd_rn(acc, __fmul_rn(a.coef_h[k], h[k]));
+  *x0 = __fsub_rn(x, __fmul_rn(a.sigma, v));
+  return acc;
+}
+
+template <int NH>
+__global__ void __launch_bounds__(256) cfg_step_kernel(const CfgStepArgs a, int64_t n_groups) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_groups; i += stride) {
+    float c[8], u[8], x[8], h[NH > 0 ? NH : 1][8], o[8], x0[8];
+    Elem<MC_F32>::load8(a.cond, i * 8, c);
+    Elem<MC_F32>::load8(a.uncond, i * 8, u);
+    ptx::ld_v8_f32(a.x + i * 8, x);  // x may alias out: coherent load
+#pragma unroll
+    for (int k = 0; k < NH; ++k) ptx::ld_v8_f32(a.hist[k] + i * 8, h[k]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float hj[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < NH; ++k) hj[k] = h[k][j];
+      o[j] = cfg_step_one<NH>(a, c[j], u[j], x[j], hj, &x0[j]);
+    }
+    Elem<MC_F32>::store8(a.out, i * 8, o);
+    if (a.x0_out) Elem<MC_F32>::store8(a.x0_out, i * 8, x0);
+  }
+}
+template <int NH>
+__global__ void cfg_step_tail_kernel(const CfgStepArgs a, int64_t begin, int64_t n) {
+  const int64_t i = begin + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float hj[4] = {0.f, 0.f, 0.f, 0.f}, x0;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) hj[k] = a.hist[k][i];
+    const float o = cfg_step_one<NH>(a, a.cond[i], a.uncond[i], a.x[i], hj, &x0);
+    a.out[i] = o;
+    if (a.x0_out) a.x0_out[i] = x0;
+  }
+}
+
+template <int NH>
+static int32_t launch_cfg_step(const CfgStepArgs& a, int64_t groups, int64_t n, cudaStream_t s) {
+  if (groups > 0) {
+    const int64_t want = (groups + 255) / 256, cap = static_cast<int64_t>(num_sms()) * 8;
+    cfg_step_kernel<NH><<<static_cast<int>(want < cap ? want : cap), 256, 0, s>>>(a, groups);
+    MC_CHECK_LAUNCH("cfg_step_kernel launch");
+  }
+  if (groups * 8 < n) {
+    const int64_t rem = n - groups * 8;
+    cfg_step_tail_kernel<NH><<<static_cast<int>((rem + 255) / 256), 256, 0, s>>>(a, groups * 8, n);
+    MC_CHECK_LAUNCH("cfg_step_tail_kernel launch");
+  }
+  return MC_OK;
+}
+
 // ---- K3: per-row norms / cosine, single pass ---------------------------------------------------------------
 // One warp per row; lanes stride over 8-element groups. Optionally also forms cur = xo - xi on the fly and stores it.
 template <int DCUR, int DPREV, bool FUSE_SUB>
@@ -398,6 +476,37 @@ int32_t mc_cfg_combine(const float* cond, const float* uncond, float guide_scale
     MC_CHECK_LAUNCH("cfg_combine_tail_kernel launch");
   }
   return MC_OK;
+}
+
+int32_t mc_cfg_step(const float* cond, const float* uncond, float guide_scale, const float* x, float coef_x, float coef_v,
+                    const float* const* hist, const float* coef_h, int32_t n_hist, float sigma, float* out, float* x0_out, int64_t n,
+                    void* stream) {
+  MC_CHECK_ARG(n >= 0, "mc_cfg_step: negative element count");
+  MC_CHECK_ARG(n_hist >= 0 && n_hist <= 4, "mc_cfg_step: n_hist=%d outside [0, 4]", n_hist);
+  if (n == 0) return MC_OK;
+  MC_CHECK_ARG(cond && uncond && x && out, "mc_cfg_step: null pointer");
+  MC_CHECK_ARG(n_hist == 0 || (hist && coef_h), "mc_cfg_step: null history arrays");
+  MC_CHECK_ARG(out != cond && out != uncond && x0_out != cond && x0_out != uncond && (x0_out == nullptr || (x0_out != out && x0_out != x)),
+               "mc_cfg_step: out may alias x only; x0_out must be a separate buffer");
+  mc::CfgStepArgs a{};
+  a.cond = cond, a.uncond = uncond, a.x = x, a.out = out, a.x0_out = x0_out;
+  a.g = guide_scale, a.coef_x = coef_x, a.coef_v = coef_v, a.sigma = sigma, a.n_hist = n_hist;
+  auto al32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
+  bool aligned = al32(cond) && al32(uncond) && al32(x) && al32(out) && (x0_out == nullptr || al32(x0_out));
+  for (int k = 0; k < n_hist; ++k) {
+    MC_CHECK_ARG(hist[k] != nullptr && hist[k] != out && hist[k] != x0_out, "mc_cfg_step: hist[%d] is null or aliases an output", k);
+    a.hist[k] = hist[k], a.coef_h[k] = coef_h[k];
+    aligned = aligned && al32(hist[k]);
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t groups = aligned ? n / 8 : 0;
+  switch (n_hist) {
+    case 0: return mc::launch_cfg_step<0>(a, groups, n, s);
+    case 1: return mc::launch_cfg_step<1>(a, groups, n, s);
+    case 2: return mc::launch_cfg_step<2>(a, groups, n, s);
+    case 3: return mc::launch_cfg_step<3>(a, groups, n, s);
+    default: return mc::launch_cfg_step<4>(a, groups, n, s);
+  }
 }
 
 int32_t mc_residual_stats(const void* r_cur, int32_t cur_dtype, const void* r_prev, int32_t prev_dtype, int64_t rows, int32_t cols,

@@ -227,6 +227,12 @@ __device__ __forceinline__ void ld_nc_v8_f32(const float* p, float (&f)[8]) {
                : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
                : "l"(p));
 }
+__device__ __forceinline__ void ld_v8_f32(const float* p, float (&f)[8]) {  // coherent form: the buffer may be written by this kernel
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "l"(p)
+               : "memory");
+}
 __device__ __forceinline__ void st_na_v8_f32(float* p, const float (&f)[8]) {
   asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]),
                "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])

@@ -93,6 +93,27 @@ def cfg_combine(cond, uncond, guide_scale, out=None):
     return out
 
 
+def cfg_step(cond, uncond, guide_scale, x, coef_v, coef_x=1.0, hist=(), coef_h=(), sigma=0.0, out=None, x0_out=None):
+    """CFG combine + scheduler update in one kernel (`mc_cfg_step`): `out = coef_x*x + coef_v*v + sum coef_h[i]*hist[i]` with
+    `v = uncond + guide_scale*(cond - uncond)` (wan_magcache.py:301-310); `out` may be `x` itself. Euler flow step:
+    `cfg_step(cond, uncond, g, x, sigma_next - sigma)` — bit-identical to `x + (sigma_next - sigma) * (uncond + g*(cond - uncond))`.
+    With `x0_out` the x0-prediction `x - sigma*v` is written as well."""
+    import ctypes
+    tensors = [cond, uncond, x, *hist] + ([out] if out is not None else []) + ([x0_out] if x0_out is not None else [])
+    for t in tensors:
+        _dev(t)
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == cond.numel()
+    assert len(hist) == len(coef_h) <= 4
+    if out is None:
+        out = torch.empty_like(x)
+    hp = (ctypes.c_void_p * max(len(hist), 1))(*[h.data_ptr() for h in hist])
+    hc = (ctypes.c_float * max(len(hist), 1))(*[float(c) for c in coef_h])
+    check(lib.mc_cfg_step(cond.data_ptr(), uncond.data_ptr(), float(guide_scale), x.data_ptr(), float(coef_x), float(coef_v), hp, hc, len(hist),
+                          float(sigma), out.data_ptr(), x0_out.data_ptr() if x0_out is not None else None, cond.numel(), _stream()))
+    _count()
+    return out
+
+
 def _finish_stats(stats_dev):
     s0, s1, s2, n = stats_dev.tolist()  # the single host sync of the calibration path
     mean = s0 / n

@@ -89,6 +89,81 @@ def test_cfg_combine_bit_exact():
             assert torch.equal(ops.cfg_combine(cond, uncond, g), uncond + g * (cond - uncond))
 
 
+def _cfg_step_torch(cond, uncond, g, x, coef_v, coef_x=1.0, hist=(), coef_h=(), sigma=0.0):
+    f = lambda a: torch.tensor(a, dtype=torch.float32, device=x.device)  # noqa: E731
+    v = uncond + f(g) * (cond - uncond)
+    acc = f(coef_x) * x + f(coef_v) * v
+    for h, c in zip(hist, coef_h):
+        acc = acc + f(c) * h
+    return acc, x - f(sigma) * v
+
+
+@pytest.mark.parametrize("n,off", [(16 * 21 * 60 * 104, 0), (1003, 0), (4099, 3), (7, 0)])
+def test_cfg_step_bit_exact(n, off):
+    """`mc_cfg_step` (CFG combine + scheduler update, wan_magcache.py:301-310) against the chain of torch eager kernels it
+    replaces — same rounding order, so bit-equal: Euler form, in-place update, 1..4 history terms, x0 output, ragged and
+    unaligned sizes (the unaligned views take the scalar tail kernel)."""
+    ops = _ops()
+    mk = lambda: torch.randn(n + off, device=DEV)[off:] if off else torch.randn(n, device=DEV)  # noqa: E731
+    cond, uncond, x = mk().contiguous(), mk().contiguous(), mk().contiguous()
+    if off:  # keep the storage offset (mis-aligned pointers) — .contiguous() above is a no-op for a 1-D slice
+        assert cond.data_ptr() % 32 != 0
+    d = -0.0123
+    want, _ = _cfg_step_torch(cond, uncond, 5.0, x, d)
+    assert torch.equal(want, x + d * (uncond + 5.0 * (cond - uncond)))  # the literal caller expression
+    assert torch.equal(ops.cfg_step(cond, uncond, 5.0, x, d), want)
+    xin = x.clone()
+    assert ops.cfg_step(cond, uncond, 5.0, xin, d, out=xin) is xin and torch.equal(xin, want)
+    hist = [mk().contiguous() for _ in range(4)]
+    coefs = [0.37, -1.9, 0.004, 2.5]
+    for k in range(1, 5):
+        x0 = torch.empty_like(x)
+        got = ops.cfg_step(cond, uncond, 6.5, x, -0.7, coef_x=0.93, hist=hist[:k], coef_h=coefs[:k], sigma=0.81, x0_out=x0)
+        want, want0 = _cfg_step_torch(cond, uncond, 6.5, x, -0.7, 0.93, hist[:k], coefs[:k], 0.81)
+        assert torch.equal(got, want) and torch.equal(x0, want0), k
+    # no-guidance form used by the sampler's predictor launch: cond = uncond = m, g = 0  ->  v = m exactly
+    got = ops.cfg_step(x, x, 0.0, cond, 0.25, coef_x=0.5)
+    assert torch.equal(got, torch.tensor(0.5, device=DEV) * cond + torch.tensor(0.25, device=DEV) * x)
+
+
+def test_cfg_step_rejects_aliasing_and_bad_history():
+    ops = _ops()
+    from magcache_b200._lib import MagCacheError
+    a, b, x = (torch.randn(64, device=DEV) for _ in range(3))
+    with pytest.raises(MagCacheError):
+        ops.cfg_step(a, b, 1.0, x, 0.1, out=a)  # out may alias x only
+    with pytest.raises(MagCacheError):
+        ops.cfg_step(a, b, 1.0, x, 0.1, x0_out=x)
+    with pytest.raises(AssertionError):
+        ops.cfg_step(a, b, 1.0, x, 0.1, hist=[a] * 5, coef_h=[1.0] * 5)
+
+
+def test_unipc_sampler_on_the_kernel_matches_the_oracle():
+    """magcache_b200/sampler.py on the real kernel: 20 UniPC steps (two launches each) and 20 Euler steps of a synthetic
+    two-branch flow model against oracle/sampler_ref.py in float64."""
+    from magcache_b200 import sampler as S
+    from oracle import sampler_ref as R
+    ops = _ops()
+
+    def model_v(z, sigma, branch):
+        c = 0.7 if branch == 0 else -0.2
+        return torch.tanh(1.3 * z + c) * (0.5 + float(sigma)) - 0.8 * z * float(sigma)
+
+    sig = S.sampling_sigmas(20, 5.0)
+    sig[0] = 0.9999
+    x0 = torch.randn(16, 21, 60, 104, device=DEV)
+    for name, smp, ref in [("unipc", S.FlowUniPCSampler(sig), R.UniPCRef(torch.tensor(sig, dtype=torch.float64))),
+                           ("euler", S.FlowEulerSampler(sig), R.EulerRef(torch.tensor(sig, dtype=torch.float64)))]:
+        x, xr = x0.clone(), x0.double()
+        launches0 = ops.LAUNCHES
+        for i in range(20):
+            x = smp.step(model_v(x, sig[i], 0), model_v(x, sig[i], 1), 5.0, x)
+            xr = ref.step(R.cfg(model_v(xr, sig[i], 0), model_v(xr, sig[i], 1), 5.0), xr)
+            err = float((x.double() - xr).abs().max()) / max(1.0, float(xr.abs().max()))
+            assert err < 5e-5, (name, i, err)
+        assert ops.LAUNCHES - launches0 == (40 if name == "unipc" else 20)
+
+
 def test_cache_kernels_hunyuan_720p_shape():
     """BASELINE configs[3] (HunyuanVideo 720p x 129 frames: [1, 118800, 3072], all bf16): hit add / residual sub bit-exact."""
     ops = _ops()
