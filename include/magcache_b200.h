@@ -178,6 +178,7 @@ int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, co
 #define MC_EPI_BIAS_GATE_RESID 2  /* resid_f32[m,n] += float(bf16(acc + bias[n])) * gate[n] (gate NULL -> 1) `x = x + y * e[2]` */
 #define MC_EPI_ROWBIAS_BF16 3     /* out_bf16[m,n] = bf16(acc + bias[m])                               V^T = Wv * h^T + bv */
 #define MC_EPI_BIAS_F32 4         /* out_f32[m,n] = acc + bias[n]                                                           */
+#define MC_EPI_BIAS_GELU_ERF_BF16 5 /* out_bf16 = bf16(gelu_erf(float(bf16(acc + bias[n]))))          img_emb Linear + nn.GELU() (i2v) */
 int32_t mc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
                      const float* bias, int32_t epilogue, void* out, int64_t ldo, const float* gate, void* stream);
 

@@ -66,6 +66,9 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
 }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// torch.nn.GELU() (exact, erf form) in fp32: 0.5*x*(1+erf(x/sqrt(2))) — `img_emb` of the i2v models
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
 // torch.nn.GELU(approximate='tanh') in fp32: 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float kBeta = 0.7978845608028654f;  // sqrt(2/pi)

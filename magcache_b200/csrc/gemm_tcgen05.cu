@@ -106,6 +106,10 @@ __device__ __forceinline__ void epilogue_patch(const GemmParams& p, const float*
         v0 = gelu_tanh(round_bf16(v0));
         v1 = gelu_tanh(round_bf16(v1));
       }
+      if (EPI == MC_EPI_BIAS_GELU_ERF_BF16) {
+        v0 = gelu_erf(round_bf16(v0));
+        v1 = gelu_erf(round_bf16(v1));
+      }
       w[i] = pack_bf16x2(v0, v1);
     }
 #pragma unroll
@@ -129,6 +133,10 @@ __device__ __forceinline__ void epilogue_patch(const GemmParams& p, const float*
     if (EPI == MC_EPI_BIAS_GELU_BF16) {
       v0 = gelu_tanh(round_bf16(v0));
       v1 = gelu_tanh(round_bf16(v1));
+    }
+    if (EPI == MC_EPI_BIAS_GELU_ERF_BF16) {
+      v0 = gelu_erf(round_bf16(v0));
+      v1 = gelu_erf(round_bf16(v1));
     }
     __nv_bfloat16* o = obase + static_cast<int64_t>(2 * i) * p.ldo;
     if (pair_ok) {
@@ -295,6 +303,7 @@ extern "C" int32_t mc_gemm_bf16(const void* A, int64_t lda, const void* B, int64
     case MC_EPI_BIAS_GATE_RESID: return mc::launch_gemm<MC_EPI_BIAS_GATE_RESID>(ta, tb, p, s);
     case MC_EPI_ROWBIAS_BF16: return mc::launch_gemm<MC_EPI_ROWBIAS_BF16>(ta, tb, p, s);
     case MC_EPI_BIAS_F32: return mc::launch_gemm<MC_EPI_BIAS_F32>(ta, tb, p, s);
+    case MC_EPI_BIAS_GELU_ERF_BF16: return mc::launch_gemm<MC_EPI_BIAS_GELU_ERF_BF16>(ta, tb, p, s);
     default:
       mc::set_error("mc_gemm_bf16: unknown epilogue %d", epilogue);
       return MC_ERR_INVALID;

@@ -56,9 +56,9 @@ def _controller(self):
 
 
 def _stage(self, x, t, context, seq_len, clip_fea, y):
-    if getattr(self, "model_type", "t2v") == "i2v" or clip_fea is not None or y is not None:
-        raise NotImplementedError("magcache_b200: only the t2v path is built (SURVEY §8f lists i2v/VACE as next)")
-    if len(x) != 1 or len(context) != 1:
+    if getattr(self, "model_type", "t2v") == "i2v":
+        assert clip_fea is not None and y is not None  # magcache_generate.py:226-227
+    if len(x) != 1 or len(context) != 1 or (y is not None and len(y) != 1):
         raise NotImplementedError("magcache_b200: one sample per call (the reference's caller passes [latents], wan_magcache.py:296-299)")
     eng = _engine(self)
     lat = x[0]
@@ -68,7 +68,7 @@ def _stage(self, x, t, context, seq_len, clip_fea, y):
     assert n_tok <= seq_len  # reference: assert seq_lens.max() <= seq_len
     if n_tok != seq_len:
         raise NotImplementedError("magcache_b200: seq_len padding (sequence-parallel upstream) is not built; pass seq_len == token count")
-    eng.stage_inputs(lat, t, context[0])
+    eng.stage_inputs(lat, t, context[0], clip_fea=clip_fea, y=None if y is None else y[0])
     return eng
 
 

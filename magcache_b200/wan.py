@@ -35,6 +35,9 @@ class WanDims:
     text_dim: int = 4096
     text_len: int = 512
     eps: float = 1e-6
+    model_type: str = "t2v"   # "i2v": in_dim 36 (noise | mask + first-frame latents), CLIP image tokens through `img_emb`
+    clip_dim: int = 1280
+    clip_len: int = 257
 
     @property
     def head_dim(self):
@@ -44,6 +47,7 @@ class WanDims:
 WAN_CONFIGS = {
     "t2v-1.3B": WanDims(1536, 8960, 12, 30),
     "t2v-14B": WanDims(5120, 13824, 40, 40),
+    "i2v-14B": WanDims(5120, 13824, 40, 40, in_dim=36, model_type="i2v"),
 }
 
 
@@ -74,7 +78,9 @@ class WanWeights:
         D = m.dim
         dims = WanDims(dim=D, ffn_dim=m.ffn_dim, num_heads=m.num_heads, num_layers=len(m.blocks), in_dim=m.patch_embedding.in_channels,
                        out_dim=m.out_dim, freq_dim=m.freq_dim, text_dim=m.text_embedding[0].in_features, text_len=m.text_len,
-                       eps=getattr(m, "eps", 1e-6))
+                       eps=getattr(m, "eps", 1e-6), model_type=getattr(m, "model_type", "t2v"))
+        if dims.model_type not in ("t2v", "i2v"):
+            raise NotImplementedError(f"model_type {dims.model_type!r}: t2v and i2v forwards are built")
         if dims.head_dim != 128:
             raise NotImplementedError(f"head_dim {dims.head_dim}: the attention kernel is built for head_dim 128 (Wan2.1 1.3B and 14B)")
         assert tuple(m.patch_embedding.kernel_size) == (1, 2, 2), "patch size (1,2,2) only"
@@ -108,7 +114,18 @@ class WanWeights:
                 "w_f1": _bf16(blk.ffn[0].weight, device), "b_f1": _bias_autocast(blk.ffn[0].bias, device),
                 "w_f2": _bf16(blk.ffn[2].weight, device), "b_f2": _bias_autocast(blk.ffn[2].bias, device),
             }
+            if dims.model_type == "i2v":  # WanI2VCrossAttention: own k / v projections and key norm for the CLIP tokens
+                b.update({"c_wk_img": _bf16(ca.k_img.weight, device), "c_bk_img": _bias_autocast(ca.k_img.bias, device),
+                          "c_wv_img": _bf16(ca.v_img.weight, device), "c_bv_img": _bias_autocast(ca.v_img.bias, device),
+                          "c_nk_img": _f32(ca.norm_k_img.weight, device)})
             w.blocks.append(b)
+        if dims.model_type == "i2v":
+            pj = m.img_emb.proj  # MLPProj: LayerNorm, Linear, GELU(erf), Linear, LayerNorm
+            dims.clip_dim = pj[1].in_features
+            w.img_ln1_w, w.img_ln1_b, w.img_ln1_eps = _f32(pj[0].weight, device), _f32(pj[0].bias, device), pj[0].eps
+            w.img_w1, w.img_b1 = _bf16(pj[1].weight, device), _bias_autocast(pj[1].bias, device)
+            w.img_w2, w.img_b2 = _bf16(pj[3].weight, device), _bias_autocast(pj[3].bias, device)
+            w.img_ln2_w, w.img_ln2_b, w.img_ln2_eps = _f32(pj[4].weight, device), _f32(pj[4].bias, device), pj[4].eps
         w.head_mod = _f32(m.head.modulation.reshape(2, D), device)
         w.head_wt = _f32(m.head.head.weight.t(), device)           # [D, 64]: transposed for the head kernel's K-chunk staging
         w.head_b = _f32(m.head.head.bias, device)
@@ -150,6 +167,15 @@ class WanWeights:
                 "c_nq": 1 + 0.1 * torch.randn(D, device=device, generator=g), "c_nk": 1 + 0.1 * torch.randn(D, device=device, generator=g),
                 "w_f1": xav(F, D).bfloat16(), "b_f1": bias(F), "w_f2": xav(D, F).bfloat16(), "b_f2": bias(D),
             })
+            if dims.model_type == "i2v":
+                w.blocks[-1].update({"c_wk_img": xav(D, D).bfloat16(), "c_bk_img": bias(D), "c_wv_img": xav(D, D).bfloat16(), "c_bv_img": bias(D),
+                                     "c_nk_img": 1 + 0.1 * torch.randn(D, device=device, generator=g)})
+        if dims.model_type == "i2v":
+            Cd = dims.clip_dim
+            w.img_ln1_w, w.img_ln1_b, w.img_ln1_eps = 1 + 0.1 * torch.randn(Cd, device=device, generator=g), small(Cd), 1e-5
+            w.img_w1, w.img_b1 = small(Cd, Cd).bfloat16(), bias(Cd)
+            w.img_w2, w.img_b2 = small(D, Cd).bfloat16(), bias(D)
+            w.img_ln2_w, w.img_ln2_b, w.img_ln2_eps = 1 + 0.1 * torch.randn(D, device=device, generator=g), small(D), 1e-5
         w.head_mod = torch.randn(2, D, device=device, generator=g) / math.sqrt(D)
         w.head_wt = small(D, 4 * dims.out_dim).contiguous()
         w.head_b = small(4 * dims.out_dim)
@@ -229,6 +255,16 @@ class WanEngine:
         self.ctx_h = torch.empty(d.text_len, D, **bf)
         self.ctx = torch.empty(d.text_len, D, **bf)
         self.em = torch.empty(6, D, dtype=torch.float32, device=dev)
+        if d.model_type == "i2v":
+            cl = d.clip_len
+            self.clip_in = torch.zeros(cl, d.clip_dim, dtype=torch.float32, device=dev)
+            self.clip_h1 = torch.empty(cl, d.clip_dim, **bf)
+            self.clip_h2 = torch.empty(cl, d.clip_dim, **bf)
+            self.clip_h3 = torch.empty(cl, D, **bf)
+            self.ctx_img = torch.empty(cl, D, **bf)
+            self.ck_img = torch.empty(cl, D, **bf)
+            self.cvt_img = torch.zeros(D, (cl + 7) // 8 * 8, **bf)  # V^T of the image tokens; row pitch padded to 16 bytes
+            self.att_img = torch.empty(n, D, **bf)
         # engine-owned residual cache storage (one slot per CFG branch) and staged inputs: fixed addresses for graph replay
         self.res = [torch.empty(n, D, dtype=torch.float32, device=dev) for _ in range(2)]
         self.res_valid = [False, False]
@@ -243,17 +279,30 @@ class WanEngine:
         return self._rope[grid]
 
     # ------------------------------------------------------------------------------------------ prologue (:229-275)
-    def stage_inputs(self, latent, t, context):
+    def stage_inputs(self, latent, t, context, clip_fea=None, y=None):
         """Copy one call's inputs into the engine's fixed buffers (outside any captured graph): latent fp32 [C, F, H, W],
-        t tensor [1], context [L <= text_len, text_dim] (zero-padded to text_len, cast to bf16 as autocast would)."""
+        t tensor [1], context [L <= text_len, text_dim] (zero-padded to text_len, cast to bf16 as autocast would); i2v also
+        y [C_y, F, H, W] (concatenated under the latent channels, magcache_generate.py:233-234) and clip_fea [1, 257, clip_dim]."""
         d = self.dims
         C, Fr, H, W = latent.shape
+        if d.model_type == "i2v":
+            assert clip_fea is not None and y is not None  # :226-227
+        c_y = 0 if y is None else y.shape[0]
+        if C + c_y != d.in_dim:
+            raise ValueError(f"magcache_b200: {C}+{c_y} input channels, the patch embedding takes {d.in_dim}")
         self.grid = (Fr, H // 2, W // 2)
         self._workspace(self.grid[0] * self.grid[1] * self.grid[2])
-        if self.s_lat is None or self.s_lat.shape != latent.shape:
-            self.s_lat = torch.empty(latent.shape, dtype=torch.float32, device=self.device)
+        shape = (C + c_y, Fr, H, W)
+        if self.s_lat is None or tuple(self.s_lat.shape) != shape:
+            self.s_lat = torch.empty(shape, dtype=torch.float32, device=self.device)
             self._graphs = {}
-        self.s_lat.copy_(latent)
+        self.s_lat[:C].copy_(latent)
+        if y is not None:
+            assert tuple(y.shape[1:]) == (Fr, H, W)
+            self.s_lat[C:].copy_(y)
+        if clip_fea is not None:
+            assert tuple(clip_fea.shape[-2:]) == (d.clip_len, d.clip_dim) and clip_fea.numel() == d.clip_len * d.clip_dim, "one sample per call"
+            self.clip_in.copy_(clip_fea.reshape(d.clip_len, d.clip_dim))
         self.s_t.copy_(t.reshape(-1)[:1])
         L = context.shape[0]
         assert L <= d.text_len and context.shape[1] == d.text_dim
@@ -272,6 +321,13 @@ class WanEngine:
         e0 = ops.linear_f32_small(e, w.tproj_w, w.tproj_b, act=1).view(6, d.dim)
         ops.gemm(self.ctx_in, w.text_w1, w.text_b1, E.MC_EPI_BIAS_GELU_BF16, out=self.ctx_h)
         ops.gemm(self.ctx_h, w.text_w2, w.text_b2, E.MC_EPI_BIAS_BF16, out=self.ctx)
+        if d.model_type == "i2v":
+            # context_clip = self.img_emb(clip_fea) (:264-266): LN(fp32) - Linear - GELU(erf) - Linear - LN(fp32). The block's k_img /
+            # v_img Linears cast their input to bf16, so the last LN writes bf16 directly (same value as fp32 -> autocast cast).
+            ops.ln_affine(self.clip_in, w.img_ln1_w, w.img_ln1_b, eps=w.img_ln1_eps, out=self.clip_h1)
+            ops.gemm(self.clip_h1, w.img_w1, w.img_b1, E.MC_EPI_BIAS_GELU_ERF_BF16, out=self.clip_h2)
+            ops.gemm(self.clip_h2, w.img_w2, w.img_b2, E.MC_EPI_BIAS_BF16, out=self.clip_h3)
+            ops.ln_affine(self.clip_h3, w.img_ln2_w, w.img_ln2_b, eps=w.img_ln2_eps, out=self.ctx_img)
         return self.x0, e, e0, self.ctx
 
     # ------------------------------------------------------------------------------------------ one patched forward
@@ -363,7 +419,15 @@ class WanEngine:
             ops.rmsnorm_rope_(self.ck, b["c_nk"], None, d.head_dim, eps=d.eps)
             ops.gemm(b["c_wv"], ctx, b["c_bv"], E.MC_EPI_ROWBIAS_BF16, out=self.cvt)
             ops.attention(self.cq, self.ck, self.cvt, H, out=self.att, tag="attn_cross")
-            ops.gemm(self.att, b["c_wo"], b["c_bo"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=None)
+            att = self.att
+            if d.model_type == "i2v":  # WanI2VCrossAttention: x = attn(q, k, v) + attn(q, k_img, v_img), summed in bf16
+                cvt_img = self.cvt_img[:, :d.clip_len]
+                ops.gemm(self.ctx_img, b["c_wk_img"], b["c_bk_img"], E.MC_EPI_BIAS_BF16, out=self.ck_img)
+                ops.rmsnorm_rope_(self.ck_img, b["c_nk_img"], None, d.head_dim, eps=d.eps)
+                ops.gemm(b["c_wv_img"], self.ctx_img, b["c_bv_img"], E.MC_EPI_ROWBIAS_BF16, out=cvt_img)
+                ops.attention(self.cq, self.ck_img, cvt_img, H, out=self.att_img, tag="attn_cross_img")
+                att = ops.cache_hit_add(self.att, self.att_img, out=self.h)  # h (norm3 output) is dead once cq is projected
+            ops.gemm(att, b["c_wo"], b["c_bo"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=None)
             # --- FFN
             ops.ln_modulate(xs, self.em, 4, 3, eps=d.eps, out=self.h)
             ops.gemm(self.h, b["w_f1"], b["b_f1"], E.MC_EPI_BIAS_GELU_BF16, out=self.ffn, tag="gemm_ffn1")

@@ -365,6 +365,17 @@ def test_gemm_epilogues():
     # a 1-ulp flip of the bf16 pre-activation (2^-8 relative to |acc|) moves GELU by at most that much (|GELU'| <= 1.13)
     tol = ref.abs() * 2.0 ** -7 + acc.abs() * 2.0 ** -7 + 1e-3
     assert ((out.float() - ref).abs() <= tol).all(), float((out.float() - ref).abs().max())
+    # exact (erf) GELU of the i2v `img_emb` MLP, same bf16 pre-activation rule
+    out = ops.gemm(a, b, bias, L.MC_EPI_BIAS_GELU_ERF_BF16)
+    ref = torch.nn.functional.gelu(acc.bfloat16().float())
+    assert ((out.float() - ref).abs() <= tol).all(), float((out.float() - ref).abs().max())
+    # 257 CLIP tokens x K = 1280: ragged M and N, K not a multiple of the 64-wide K block count the block GEMMs use
+    a2 = torch.randn(257, 1280, device=DEV).bfloat16()
+    b2 = (torch.randn(1280, 1280, device=DEV) / math.sqrt(1280)).bfloat16()
+    out2 = ops.gemm(a2, b2, None, L.MC_EPI_BIAS_GELU_ERF_BF16)
+    acc2 = _gemm_ref(a2, b2).float()
+    ref2 = torch.nn.functional.gelu(acc2.bfloat16().float())
+    assert ((out2.float() - ref2).abs() <= ref2.abs() * 2.0 ** -7 + acc2.abs() * 2.0 ** -7 + 1e-3).all()
     # gated residual, fp32 stream updated in place
     x = torch.randn(M, N, device=DEV)
     gate = torch.randn(N, device=DEV) * 0.5
@@ -459,7 +470,12 @@ def test_attention_split_kv(Lq, Lk, heads, splits, monkeypatch):
     ref = _attn_ref(q, k, v, heads)
     err = (outs[0].float() - ref).abs()
     assert float(err.max()) < 2e-2 and float(err.mean()) < 2e-3, (float(err.max()), float(err.mean()))
-    assert float((outs[0].float() - one.float()).abs().max()) < 8e-3   # bf16 output rounding of two fp32 results a few ulp apart
+    # P is rounded to bf16 relative to each CTA's own running max, so split and unsplit results differ at the level of that
+    # rounding (not just by the output's bf16 ulp): the split result must be as close to the fp64 reference as the unsplit one
+    err_one = (one.float() - ref).abs()
+    assert float(err.mean()) <= 1.25 * float(err_one.mean()) + 1e-5, (float(err.mean()), float(err_one.mean()))
+    assert float(err.max()) <= 2.0 * float(err_one.max()) + 1e-3, (float(err.max()), float(err_one.max()))
+    assert float((outs[0].float() - one.float()).abs().max()) < 2e-2
     assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 

@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import wan_ref
@@ -69,6 +70,36 @@ def test_oracle_bf16_close_to_fp64_evaluation():
             yb = b([lat.double()], t=torch.tensor([400.0]), context=[ctx.double()], seq_len=32)[0]
     assert yb.dtype == torch.float64
     rel = float((ya.double() - yb).norm() / yb.norm())
+    assert 0 < rel < 2e-2, rel
+
+
+def test_oracle_i2v_branch_uses_image_tokens_and_y():
+    """i2v restatement (magcache_generate.py:226-227, :233-234, :264-266 + upstream WanI2VCrossAttention / MLPProj): the output
+    depends on `y` and on `clip_fea`, the bf16 emulation stays close to the fp64 evaluation, and the reference's assert fires
+    when the extra inputs are missing."""
+    m = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, in_dim=36, text_dim=128, text_len=32, model_type="i2v",
+                         clip_dim=64).init_synthetic(0)
+    m.__class__ = type("I", (m.__class__,), {})
+    wan_ref.install_magcache(m.__class__, [1.0] * 8, 4)
+    b = copy.deepcopy(m).double()
+    b.__class__ = type("I64", (b.__class__,), {})
+    wan_ref.install_magcache(b.__class__, [1.0] * 8, 4)
+    g = torch.Generator().manual_seed(0)
+    lat, y, ctx, clip = torch.randn(16, 2, 8, 8, generator=g), torch.randn(20, 2, 8, 8, generator=g), torch.randn(9, 128, generator=g), torch.randn(1, 257, 64, generator=g)
+    t = torch.tensor([400.0])
+    with torch.no_grad():
+        base = m([lat], t=t, context=[ctx], seq_len=32, clip_fea=clip, y=[y])[0]
+        m.cnt = 0
+        other_y = m([lat], t=t, context=[ctx], seq_len=32, clip_fea=clip, y=[y * 0.5])[0]
+        m.cnt = 0
+        other_clip = m([lat], t=t, context=[ctx], seq_len=32, clip_fea=clip.flip(1), y=[y])[0]
+        with wan_ref.exact_fp64():
+            exact = b([lat.double()], t=t, context=[ctx.double()], seq_len=32, clip_fea=clip.double(), y=[y.double()])[0]
+        with pytest.raises(AssertionError):
+            m([lat], t=t, context=[ctx], seq_len=32)
+    assert base.shape == (16, 2, 8, 8) and base.dtype == torch.float32
+    assert float((base - other_y).abs().max()) > 1e-3 and float((base - other_clip).abs().max()) > 1e-4
+    rel = float((base.double() - exact).norm() / exact.norm())
     assert 0 < rel < 2e-2, rel
 
 

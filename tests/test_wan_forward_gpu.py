@@ -75,6 +75,54 @@ def test_single_forward_vs_oracle_and_fp64(cfg_name):
     assert e_ours <= 1.5 * e_ref + 1e-4
 
 
+def test_i2v_forward_vs_oracle_and_fp64():
+    """The same patched forward on an i2v model (magcache_generate.py:226-227, :233-234, :264-266; installed at :989-1018 with
+    the 480P / 720P tables): `y` concatenated under the latent channels (in_dim 36), CLIP tokens through `img_emb`
+    (LayerNorm - Linear - GELU(erf) - Linear - LayerNorm) and the image cross-attention branch summed with the text one.
+    miss, miss, then the hit path on both CFG slots, against the oracle; first call also against the fp64 evaluation."""
+    from oracle import wan_ref
+    import magcache_b200 as mc
+    model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, in_dim=36, text_dim=512, text_len=64, model_type="i2v",
+                             clip_dim=192).init_synthetic(3)
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(16, 3, 16, 24, generator=g)
+    y = torch.randn(20, 3, 16, 24, generator=g)
+    ctx, ctx_null = torch.randn(37, 512, generator=g), torch.randn(30, 512, generator=g)
+    clip = torch.randn(1, 257, 192, generator=g)
+    n_tok = 3 * 8 * 12
+    t = torch.tensor([640.0])
+    steps = 4
+    table = mc.tables()["wan2.1_i2v_480p"]
+
+    def ref_install(m):
+        cls = type("RefWanI2V", (m.__class__,), {})
+        m.__class__ = cls
+        wan_ref.install_magcache(cls, table, steps, thresh=10.0, K=3, retention_ratio=0.25)  # eligible from call 2: hit, hit
+        return m
+
+    ref_model = ref_install(copy.deepcopy(model))
+    ours = copy.deepcopy(model).to(DEV)
+    ours.__class__ = type("OurWanI2V", (ours.__class__,), {})
+    mc.init_magcache(ours, steps, thresh=10.0, K=3, retention_ratio=0.25, mag_ratios=table)
+    with torch.no_grad():
+        m64 = ref_install(copy.deepcopy(model).double())
+        with wan_ref.exact_fp64():
+            exact = m64([lat.double()], t=t, context=[ctx.double()], seq_len=n_tok, clip_fea=clip.double(), y=[y.double()])[0]
+        for i, c in enumerate((ctx, ctx_null, ctx, ctx_null)):
+            ref = ref_model([lat], t=t, context=[c], seq_len=n_tok, clip_fea=clip, y=[y])[0]
+            out = ours([lat.to(DEV)], t=t.to(DEV), context=[c.to(DEV)], seq_len=n_tok, clip_fea=clip.to(DEV), y=[y.to(DEV)])[0].cpu()
+            assert out.shape == ref.shape == (16, 3, 16, 24)
+            assert bool(ref_model.last_skip) == (i >= 2)
+            assert rel_l2(out, ref) <= 2e-2, (i, rel_l2(out, ref))
+            if i == 0:
+                e_ours, e_ref = rel_l2(out, exact), rel_l2(ref, exact)
+                print(f"[i2v] rel-L2: ours vs fp64 {e_ours:.3e} | oracle(bf16) vs fp64 {e_ref:.3e}")
+                assert e_ours <= 1.5 * e_ref + 1e-4
+            assert ours.cnt == ref_model.cnt and ours.accumulated_err == ref_model.accumulated_err
+    with pytest.raises(AssertionError):  # :226-227
+        ours([lat.to(DEV)], t=t.to(DEV), context=[ctx.to(DEV)], seq_len=n_tok)
+
+
 def test_magcache_loop_mask_cache_and_outputs():
     """20 forward calls (10 steps x cond/uncond) through the patched forward on both sides, same inputs every call.
     Checks: identical skip decisions (bit-exact), controller attributes, residual-cache contents, per-call outputs."""
