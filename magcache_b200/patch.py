@@ -55,7 +55,7 @@ def _controller(self):
     return c
 
 
-def _stage(self, x, t, context, seq_len, clip_fea, y):
+def _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=True):
     if getattr(self, "model_type", "t2v") == "i2v":
         assert clip_fea is not None and y is not None  # magcache_generate.py:226-227
     if len(x) != 1 or len(context) != 1 or (y is not None and len(y) != 1):
@@ -65,9 +65,14 @@ def _stage(self, x, t, context, seq_len, clip_fea, y):
     if not lat.is_cuda:
         raise RuntimeError("magcache_b200: latents must be CUDA tensors (no CPU path)")
     n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
-    assert n_tok <= seq_len  # reference: assert seq_lens.max() <= seq_len
-    if n_tok != seq_len:
-        raise NotImplementedError("magcache_b200: seq_len padding (sequence-parallel upstream) is not built; pass seq_len == token count")
+    assert n_tok <= seq_len  # reference: assert seq_lens.max() <= seq_len (:242)
+    # seq_len > n_tok (upstream rounds seq_len up to a multiple of the sequence-parallel size): the reference appends zero rows
+    # (:243-246) that never reach a real token — keys are masked by k_lens = seq_lens, every other op is per token, unpatchify
+    # reads the first n_tok rows — so they are simply not computed here. The only visible difference: residual_cache[i] has
+    # n_tok rows instead of seq_len. The calibration statistics DO average over the padded rows upstream, hence the check there.
+    if n_tok != seq_len and pad_ok is False:
+        raise NotImplementedError("magcache_b200: calibration with seq_len > token count (the reference averages the ratios over the "
+                                  "zero-padded rows too); pass seq_len == token count")
     eng.stage_inputs(lat, t, context[0], clip_fea=clip_fea, y=None if y is None else y[0])
     return eng
 
@@ -105,7 +110,7 @@ def magcache_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
 def magcache_calibration(self, x, t, context, seq_len, clip_fea=None, y=None):
     r"""MagCache4Wan2.1/magcache_generate.py:80-194: always runs the block stack and records, per forward, the token-mean
     magnitude ratio, its std and the cosine distance to the previous residual of the same CFG branch (one fused pass)."""
-    eng = _stage(self, x, t, context, seq_len, clip_fea, y)
+    eng = _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=False)
     x0, e, e0, ctx = eng.prologue()
     xs = eng.run_blocks(x0, e0, ctx, eng.grid)
     slot = self.cnt % 2

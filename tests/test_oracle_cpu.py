@@ -103,6 +103,25 @@ def test_oracle_i2v_branch_uses_image_tokens_and_y():
     assert 0 < rel < 2e-2, rel
 
 
+def test_oracle_seq_len_padding_reaches_no_real_token():
+    """magcache_generate.py:242-246 pads the token axis with zero rows up to `seq_len`; with the key mask of upstream's
+    flash_attention(k_lens=seq_lens) the real tokens' outputs do not change (what lets the CUDA path skip the padded rows), while the
+    cached residual gains seq_len - n rows."""
+    m = _tiny()
+    lat, ctx = torch.randn(16, 2, 8, 8), torch.randn(9, 128)
+    outs, caches = [], []
+    for seq_len in (32, 37):
+        a = copy.deepcopy(m)
+        a.__class__ = type("P", (a.__class__,), {})
+        wan_ref.install_magcache(a.__class__, [1.0] * 8, 4)
+        with torch.no_grad():
+            outs.append(a([lat], t=torch.tensor([400.0]), context=[ctx], seq_len=seq_len)[0])
+        caches.append(a.residual_cache[0])
+    assert caches[0].shape[1] == 32 and caches[1].shape[1] == 37
+    assert float((outs[0] - outs[1]).abs().max()) <= 1e-5 * float(outs[0].abs().max())  # SDPA picks another kernel with a mask
+    assert float((caches[0][0] - caches[1][0, :32]).abs().max()) <= 2e-2 * float(caches[0].abs().max())
+
+
 def test_denoise_loop_calls_cond_then_uncond():
     m = _tiny()
     m.__class__ = type("L", (m.__class__,), {})

@@ -75,6 +75,25 @@ def test_single_forward_vs_oracle_and_fp64(cfg_name):
     assert e_ours <= 1.5 * e_ref + 1e-4
 
 
+def test_seq_len_padding_is_accepted():
+    """seq_len > token count (upstream rounds it up to the sequence-parallel size, magcache_generate.py:242-246): same output as the
+    oracle run WITH the padded rows; our residual cache keeps token-count rows."""
+    wan_ref, model = build("tiny")
+    lat, ctx, _ = make_inputs(4)
+    n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
+    t = torch.tensor([512.0])
+    ref_model = install_ref(wan_ref, copy.deepcopy(model), 10)
+    ours_model = install_ours(copy.deepcopy(model).to(DEV), 10)
+    with torch.no_grad():
+        ref = ref_model([lat], t=t, context=[ctx], seq_len=n_tok + 7)[0]
+    out = ours_model([lat.to(DEV)], t=t.to(DEV), context=[ctx.to(DEV)], seq_len=n_tok + 7)[0].cpu()
+    assert rel_l2(out, ref) <= 2e-2
+    assert ref_model.residual_cache[0].shape[1] == n_tok + 7 and ours_model.residual_cache[0].shape[1] == n_tok
+    assert rel_l2(ours_model.residual_cache[0].cpu()[0], ref_model.residual_cache[0][0, :n_tok]) <= 3e-2
+    with pytest.raises(AssertionError):  # :242
+        ours_model([lat.to(DEV)], t=t.to(DEV), context=[ctx.to(DEV)], seq_len=n_tok - 1)
+
+
 def test_i2v_forward_vs_oracle_and_fp64():
     """The same patched forward on an i2v model (magcache_generate.py:226-227, :233-234, :264-266; installed at :989-1018 with
     the 480P / 720P tables): `y` concatenated under the latent channels (in_dim 36), CLIP tokens through `img_emb`
