@@ -55,7 +55,7 @@ def _controller(self):
     return c
 
 
-def _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=True):
+def _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=True, vace_context=None, vace_scale=1.0):
     if getattr(self, "model_type", "t2v") == "i2v":
         assert clip_fea is not None and y is not None  # magcache_generate.py:226-227
     if len(x) != 1 or len(context) != 1 or (y is not None and len(y) != 1):
@@ -73,7 +73,10 @@ def _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=True):
     if n_tok != seq_len and pad_ok is False:
         raise NotImplementedError("magcache_b200: calibration with seq_len > token count (the reference averages the ratios over the "
                                   "zero-padded rows too); pass seq_len == token count")
-    eng.stage_inputs(lat, t, context[0], clip_fea=clip_fea, y=None if y is None else y[0])
+    if vace_context is not None and len(vace_context) != 1:
+        raise NotImplementedError("magcache_b200: one sample per call")
+    eng.stage_inputs(lat, t, context[0], clip_fea=clip_fea, y=None if y is None else y[0],
+                     vace_context=None if vace_context is None else vace_context[0], vace_scale=vace_scale)
     return eng
 
 
@@ -107,10 +110,37 @@ def magcache_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
     return [out]
 
 
+def magcache_vace_forward(self, x, t, vace_context, context, seq_len, vace_context_scale=1.0, clip_fea=None, y=None):
+    r"""MagCache4Wan2.1/magcache_generate.py:439-560 (installed at :1126-1150 with the VACE tables): the T2V forward plus the
+    control branch. `vace_context`: List[Tensor[96, F, H, W]]. On a miss the control blocks run first (`forward_vace`, :541) and
+    every second main block adds its hint; on a hit nothing of the control branch is computed, as in the reference. `clip_fea` and
+    `y` are accepted and ignored (the reference has those lines commented out, :471-476, :505-507)."""
+    eng = _stage(self, x, t, context, seq_len, None, None, vace_context=vace_context, vace_scale=vace_context_scale)
+    ctrl = _controller(self)
+    slot = self.cnt % 2
+    skip_forward = ctrl.decide(self)  # :517-531
+    _sync_slot_in(self, eng, slot)
+    if skip_forward:
+        print("skip: ", self.cnt)  # :527
+    out = eng.forward("hit" if skip_forward else "miss", slot)
+    self.residual_cache[slot] = eng.res[slot].view(1, *eng.res[slot].shape)  # :549
+    ctrl.advance(self)  # :554-559
+    return [out]
+
+
+def magcache_vace_calibration(self, x, t, vace_context, context, seq_len, vace_context_scale=1.0, clip_fea=None, y=None):
+    r"""MagCache4Wan2.1/magcache_generate.py:314-436: `magcache_calibration` with the control branch."""
+    return _calibrate(self, _stage(self, x, t, context, seq_len, None, None, pad_ok=False, vace_context=vace_context,
+                                   vace_scale=vace_context_scale))
+
+
 def magcache_calibration(self, x, t, context, seq_len, clip_fea=None, y=None):
     r"""MagCache4Wan2.1/magcache_generate.py:80-194: always runs the block stack and records, per forward, the token-mean
     magnitude ratio, its std and the cosine distance to the previous residual of the same CFG branch (one fused pass)."""
-    eng = _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=False)
+    return _calibrate(self, _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=False))
+
+
+def _calibrate(self, eng):
     x0, e, e0, ctx = eng.prologue()
     xs = eng.run_blocks(x0, e0, ctx, eng.grid)
     slot = self.cnt % 2
@@ -145,10 +175,11 @@ def magcache_calibration(self, x, t, context, seq_len, clip_fea=None, y=None):
 
 
 def init_magcache(model, sample_steps, thresh=0.12, K=2, retention_ratio=0.2, mag_ratios=None, ckpt_dir=None, table=None):
-    """The installation block of magcache_generate.py:896-919 as a helper (same form as Wan2.2's `init_magcache`,
-    MagCache4Wan2.2/magcache_generate.py:340-362): patches the CLASS, like the reference."""
+    """The installation block of magcache_generate.py:896-919 (i2v :989-1010, VACE :1126-1150) as a helper (same form as Wan2.2's
+    `init_magcache`, MagCache4Wan2.2/magcache_generate.py:340-362): patches the CLASS, like the reference. VACE models
+    (`model_type == "vace"`) get `magcache_vace_forward`."""
     cls = model.__class__
-    cls.forward = magcache_forward
+    cls.forward = magcache_vace_forward if getattr(model, "model_type", "t2v") == "vace" else magcache_forward
     cls.cnt = 0
     cls.num_steps = sample_steps * 2
     cls.magcache_thresh = thresh
@@ -182,7 +213,7 @@ def reset_magcache(model):
 def init_magcache_calibration(model, sample_steps):
     """magcache_generate.py:921-928."""
     cls = model.__class__
-    cls.forward = magcache_calibration
+    cls.forward = magcache_vace_calibration if getattr(model, "model_type", "t2v") == "vace" else magcache_calibration
     cls.cnt = 0
     cls.num_steps = sample_steps * 2
     cls.norm_ratio, cls.norm_std, cls.cos_dis = [], [], []

@@ -38,6 +38,8 @@ class WanDims:
     model_type: str = "t2v"   # "i2v": in_dim 36 (noise | mask + first-frame latents), CLIP image tokens through `img_emb`
     clip_dim: int = 1280
     clip_len: int = 257
+    vace_layers: tuple = ()   # "vace": main-block indices that receive a hint (upstream default: every second block)
+    vace_in_dim: int = 96
 
     @property
     def head_dim(self):
@@ -48,6 +50,8 @@ WAN_CONFIGS = {
     "t2v-1.3B": WanDims(1536, 8960, 12, 30),
     "t2v-14B": WanDims(5120, 13824, 40, 40),
     "i2v-14B": WanDims(5120, 13824, 40, 40, in_dim=36, model_type="i2v"),
+    "vace-1.3B": WanDims(1536, 8960, 12, 30, model_type="vace", vace_layers=tuple(range(0, 30, 2))),
+    "vace-14B": WanDims(5120, 13824, 40, 40, model_type="vace", vace_layers=tuple(range(0, 40, 5))),
 }
 
 
@@ -79,8 +83,8 @@ class WanWeights:
         dims = WanDims(dim=D, ffn_dim=m.ffn_dim, num_heads=m.num_heads, num_layers=len(m.blocks), in_dim=m.patch_embedding.in_channels,
                        out_dim=m.out_dim, freq_dim=m.freq_dim, text_dim=m.text_embedding[0].in_features, text_len=m.text_len,
                        eps=getattr(m, "eps", 1e-6), model_type=getattr(m, "model_type", "t2v"))
-        if dims.model_type not in ("t2v", "i2v"):
-            raise NotImplementedError(f"model_type {dims.model_type!r}: t2v and i2v forwards are built")
+        if dims.model_type not in ("t2v", "i2v", "vace"):
+            raise NotImplementedError(f"model_type {dims.model_type!r}: t2v, i2v and vace forwards are built")
         if dims.head_dim != 128:
             raise NotImplementedError(f"head_dim {dims.head_dim}: the attention kernel is built for head_dim 128 (Wan2.1 1.3B and 14B)")
         assert tuple(m.patch_embedding.kernel_size) == (1, 2, 2), "patch size (1,2,2) only"
@@ -96,29 +100,18 @@ class WanWeights:
         w.time_w2, w.time_b2 = _f32(tm[2].weight, device), _f32(tm[2].bias, device)
         tp = m.time_projection[1]
         w.tproj_w, w.tproj_b = _f32(tp.weight, device), _f32(tp.bias, device)
-        for blk in m.blocks:
-            sa, ca = blk.self_attn, blk.cross_attn
-            b = {
-                "mod": _f32(blk.modulation.reshape(6, D), device),
-                "w_qk": _bf16(torch.cat([sa.q.weight, sa.k.weight], 0), device),
-                "b_qk": _bias_autocast(torch.cat([sa.q.bias, sa.k.bias], 0), device),
-                "w_v": _bf16(sa.v.weight, device), "b_v": _bias_autocast(sa.v.bias, device),
-                "w_o": _bf16(sa.o.weight, device), "b_o": _bias_autocast(sa.o.bias, device),
-                "nq": _f32(sa.norm_q.weight, device), "nk": _f32(sa.norm_k.weight, device),
-                "n3_w": _f32(blk.norm3.weight, device), "n3_b": _f32(blk.norm3.bias, device),
-                "c_wq": _bf16(ca.q.weight, device), "c_bq": _bias_autocast(ca.q.bias, device),
-                "c_wk": _bf16(ca.k.weight, device), "c_bk": _bias_autocast(ca.k.bias, device),
-                "c_wv": _bf16(ca.v.weight, device), "c_bv": _bias_autocast(ca.v.bias, device),
-                "c_wo": _bf16(ca.o.weight, device), "c_bo": _bias_autocast(ca.o.bias, device),
-                "c_nq": _f32(ca.norm_q.weight, device), "c_nk": _f32(ca.norm_k.weight, device),
-                "w_f1": _bf16(blk.ffn[0].weight, device), "b_f1": _bias_autocast(blk.ffn[0].bias, device),
-                "w_f2": _bf16(blk.ffn[2].weight, device), "b_f2": _bias_autocast(blk.ffn[2].bias, device),
-            }
-            if dims.model_type == "i2v":  # WanI2VCrossAttention: own k / v projections and key norm for the CLIP tokens
-                b.update({"c_wk_img": _bf16(ca.k_img.weight, device), "c_bk_img": _bias_autocast(ca.k_img.bias, device),
-                          "c_wv_img": _bf16(ca.v_img.weight, device), "c_bv_img": _bias_autocast(ca.v_img.bias, device),
-                          "c_nk_img": _f32(ca.norm_k_img.weight, device)})
-            w.blocks.append(b)
+        w.blocks = [cls._pack_block(blk, dims, device) for blk in m.blocks]
+        if dims.model_type == "vace":  # VaceWanModel: control-stream blocks with before/after projections, own patch embedding
+            dims.vace_layers, dims.vace_in_dim = tuple(m.vace_layers), m.vace_patch_embedding.in_channels
+            w.vace_patch_w = _bf16(m.vace_patch_embedding.weight.flatten(1), device)
+            w.vace_patch_b = _bias_autocast(m.vace_patch_embedding.bias, device)
+            w.vace_blocks = []
+            for j, vb in enumerate(m.vace_blocks):
+                b = cls._pack_block(vb, dims, device)
+                if j == 0:
+                    b["w_before"], b["b_before"] = _bf16(vb.before_proj.weight, device), _bias_autocast(vb.before_proj.bias, device)
+                b["w_after"], b["b_after"] = _bf16(vb.after_proj.weight, device), _bias_autocast(vb.after_proj.bias, device)
+                w.vace_blocks.append(b)
         if dims.model_type == "i2v":
             pj = m.img_emb.proj  # MLPProj: LayerNorm, Linear, GELU(erf), Linear, LayerNorm
             dims.clip_dim = pj[1].in_features
@@ -130,6 +123,32 @@ class WanWeights:
         w.head_wt = _f32(m.head.head.weight.t(), device)           # [D, 64]: transposed for the head kernel's K-chunk staging
         w.head_b = _f32(m.head.head.bias, device)
         return w
+
+    @staticmethod
+    def _pack_block(blk, dims, device):
+        D = dims.dim
+        sa, ca = blk.self_attn, blk.cross_attn
+        b = {
+            "mod": _f32(blk.modulation.reshape(6, D), device),
+            "w_qk": _bf16(torch.cat([sa.q.weight, sa.k.weight], 0), device),
+            "b_qk": _bias_autocast(torch.cat([sa.q.bias, sa.k.bias], 0), device),
+            "w_v": _bf16(sa.v.weight, device), "b_v": _bias_autocast(sa.v.bias, device),
+            "w_o": _bf16(sa.o.weight, device), "b_o": _bias_autocast(sa.o.bias, device),
+            "nq": _f32(sa.norm_q.weight, device), "nk": _f32(sa.norm_k.weight, device),
+            "n3_w": _f32(blk.norm3.weight, device), "n3_b": _f32(blk.norm3.bias, device),
+            "c_wq": _bf16(ca.q.weight, device), "c_bq": _bias_autocast(ca.q.bias, device),
+            "c_wk": _bf16(ca.k.weight, device), "c_bk": _bias_autocast(ca.k.bias, device),
+            "c_wv": _bf16(ca.v.weight, device), "c_bv": _bias_autocast(ca.v.bias, device),
+            "c_wo": _bf16(ca.o.weight, device), "c_bo": _bias_autocast(ca.o.bias, device),
+            "c_nq": _f32(ca.norm_q.weight, device), "c_nk": _f32(ca.norm_k.weight, device),
+            "w_f1": _bf16(blk.ffn[0].weight, device), "b_f1": _bias_autocast(blk.ffn[0].bias, device),
+            "w_f2": _bf16(blk.ffn[2].weight, device), "b_f2": _bias_autocast(blk.ffn[2].bias, device),
+        }
+        if dims.model_type == "i2v":  # WanI2VCrossAttention: own k / v projections and key norm for the CLIP tokens
+            b.update({"c_wk_img": _bf16(ca.k_img.weight, device), "c_bk_img": _bias_autocast(ca.k_img.bias, device),
+                      "c_wv_img": _bf16(ca.v_img.weight, device), "c_bv_img": _bias_autocast(ca.v_img.bias, device),
+                      "c_nk_img": _f32(ca.norm_k_img.weight, device)})
+        return b
 
     @classmethod
     def random(cls, dims: WanDims, device, seed=0):
@@ -155,8 +174,8 @@ class WanWeights:
         w.time_w1, w.time_b1 = small(D, dims.freq_dim), small(D)
         w.time_w2, w.time_b2 = small(D, D), small(D)
         w.tproj_w, w.tproj_b = small(6 * D, D), small(6 * D)
-        for _ in range(dims.num_layers):
-            w.blocks.append({
+        def rand_block():
+            blk = {
                 "mod": torch.randn(6, D, device=device, generator=g) / math.sqrt(D),
                 "w_qk": torch.cat([xav(D, D), xav(D, D)], 0).bfloat16(), "b_qk": bias(2 * D),
                 "w_v": xav(D, D).bfloat16(), "b_v": bias(D), "w_o": xav(D, D).bfloat16(), "b_o": bias(D),
@@ -166,10 +185,24 @@ class WanWeights:
                 "c_wv": xav(D, D).bfloat16(), "c_bv": bias(D), "c_wo": xav(D, D).bfloat16(), "c_bo": bias(D),
                 "c_nq": 1 + 0.1 * torch.randn(D, device=device, generator=g), "c_nk": 1 + 0.1 * torch.randn(D, device=device, generator=g),
                 "w_f1": xav(F, D).bfloat16(), "b_f1": bias(F), "w_f2": xav(D, F).bfloat16(), "b_f2": bias(D),
-            })
+            }
             if dims.model_type == "i2v":
-                w.blocks[-1].update({"c_wk_img": xav(D, D).bfloat16(), "c_bk_img": bias(D), "c_wv_img": xav(D, D).bfloat16(), "c_bv_img": bias(D),
-                                     "c_nk_img": 1 + 0.1 * torch.randn(D, device=device, generator=g)})
+                blk.update({"c_wk_img": xav(D, D).bfloat16(), "c_bk_img": bias(D), "c_wv_img": xav(D, D).bfloat16(), "c_bv_img": bias(D),
+                            "c_nk_img": 1 + 0.1 * torch.randn(D, device=device, generator=g)})
+            return blk
+
+        for _ in range(dims.num_layers):
+            w.blocks.append(rand_block())
+        if dims.model_type == "vace":
+            assert dims.vace_layers and dims.vace_layers[0] == 0
+            w.vace_patch_w, w.vace_patch_b = xav(D, dims.vace_in_dim * 4).bfloat16(), bias(D)
+            w.vace_blocks = []
+            for j in range(len(dims.vace_layers)):
+                blk = rand_block()
+                if j == 0:
+                    blk["w_before"], blk["b_before"] = (0.3 * xav(D, D)).bfloat16(), bias(D)
+                blk["w_after"], blk["b_after"] = (0.3 * xav(D, D)).bfloat16(), bias(D)
+                w.vace_blocks.append(blk)
         if dims.model_type == "i2v":
             Cd = dims.clip_dim
             w.img_ln1_w, w.img_ln1_b, w.img_ln1_eps = 1 + 0.1 * torch.randn(Cd, device=device, generator=g), small(Cd), 1e-5
@@ -255,6 +288,11 @@ class WanEngine:
         self.ctx_h = torch.empty(d.text_len, D, **bf)
         self.ctx = torch.empty(d.text_len, D, **bf)
         self.em = torch.empty(6, D, dtype=torch.float32, device=dev)
+        if d.model_type == "vace":
+            self.cs = torch.empty(n, D, dtype=torch.float32, device=dev)             # control stream (fp32 like the main one)
+            self.cbf = torch.empty(len(d.vace_layers), n, D, **bf)                   # bf16 copies = A operands of the after_proj GEMMs
+            self.vgate = torch.ones(D, dtype=torch.float32, device=dev)              # vace_context_scale, broadcast over features
+            self.s_vace = None
         if d.model_type == "i2v":
             cl = d.clip_len
             self.clip_in = torch.zeros(cl, d.clip_dim, dtype=torch.float32, device=dev)
@@ -279,7 +317,7 @@ class WanEngine:
         return self._rope[grid]
 
     # ------------------------------------------------------------------------------------------ prologue (:229-275)
-    def stage_inputs(self, latent, t, context, clip_fea=None, y=None):
+    def stage_inputs(self, latent, t, context, clip_fea=None, y=None, vace_context=None, vace_scale=1.0):
         """Copy one call's inputs into the engine's fixed buffers (outside any captured graph): latent fp32 [C, F, H, W],
         t tensor [1], context [L <= text_len, text_dim] (zero-padded to text_len, cast to bf16 as autocast would); i2v also
         y [C_y, F, H, W] (concatenated under the latent channels, magcache_generate.py:233-234) and clip_fea [1, 257, clip_dim]."""
@@ -300,6 +338,15 @@ class WanEngine:
         if y is not None:
             assert tuple(y.shape[1:]) == (Fr, H, W)
             self.s_lat[C:].copy_(y)
+        if d.model_type == "vace":
+            if vace_context is None:
+                raise TypeError("magcache_b200: a VACE model needs vace_context (magcache_generate.py:439-449)")
+            assert tuple(vace_context.shape) == (d.vace_in_dim, Fr, H, W), tuple(vace_context.shape)
+            if self.s_vace is None or self.s_vace.shape != vace_context.shape:
+                self.s_vace = torch.empty(vace_context.shape, dtype=torch.float32, device=self.device)
+                self._graphs = {}
+            self.s_vace.copy_(vace_context)
+            self.vgate.fill_(float(vace_scale))
         if clip_fea is not None:
             assert tuple(clip_fea.shape[-2:]) == (d.clip_len, d.clip_dim) and clip_fea.numel() == d.clip_len * d.clip_dim, "one sample per call"
             self.clip_in.copy_(clip_fea.reshape(d.clip_len, d.clip_dim))
@@ -372,67 +419,100 @@ class WanEngine:
 
     # ------------------------------------------------------------------------------------------ block stack (:297-298)
     def run_blocks(self, x0, e0, ctx, grid):
-        """30 (1.3B) / 40 (14B) WanAttentionBlocks. Returns the fp32 residual stream [N, D] (engine-owned buffer)."""
-        d, H = self.dims, self.dims.num_heads
-        D = d.dim
-        n = x0.shape[0]
+        """30 (1.3B) / 40 (14B) WanAttentionBlocks (VACE models: the control-stream pass first, then the main blocks with their
+        hints). Returns the fp32 residual stream [N, D] (engine-owned buffer)."""
+        d = self.dims
+        rope = self._rope_for(grid)
+        if self.shard is not None:
+            rope = self.shard.rows(rope)  # RoPE uses the GLOBAL token index -> (f, h, w)
+        if d.model_type == "vace":
+            self._vace_pass(x0, e0, ctx, rope)
         xs = self.xs
         ops.cast_into(x0, xs)  # block 0 sees the bf16 patch embedding; every later op works on the fp32 stream
-        rope = self._rope_for(grid)
+        for li, b in enumerate(self.w.blocks):
+            self._block(b, xs, e0, ctx, rope, first=(li == 0))
+            if li in d.vace_layers:
+                # BaseWanAttentionBlock: x = x + hints[j] * context_scale, hints[j] = after_proj(c_j). The projection runs HERE, its
+                # epilogue adding bf16(acc + bias) * scale straight into the fp32 stream (no hint tensors, no separate add pass).
+                j = d.vace_layers.index(li)
+                vb = self.w.vace_blocks[j]
+                ops.gemm(self.cbf[j], vb["w_after"], vb["b_after"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.vgate, tag="gemm_vace_after")
+        return xs
+
+    def _vace_pass(self, x0, e0, ctx, rope):
+        """`forward_vace` (upstream VaceWanModel, called at magcache_generate.py:541): patch-embed the control video, mix it with the
+        main stream's input in the first control block (`c = before_proj(c) + x`), run the control blocks and keep a bf16 copy of the
+        stream after each one (what `after_proj` — a Linear under autocast — reads)."""
+        w = self.w
+        tok = ops.patchify(self.s_vace)
+        if self.shard is not None:
+            tok = self.shard.rows(tok)
+        ops.gemm(tok, w.vace_patch_w, w.vace_patch_b, E.MC_EPI_BIAS_BF16, out=self.att)
+        vb0 = w.vace_blocks[0]
+        ops.gemm(self.att, vb0["w_before"], vb0["b_before"], E.MC_EPI_BIAS_BF16, out=self.cq)
+        ops.cache_hit_add(self.cq, x0, out=self.h)  # bf16 + bf16 -> bf16
+        ops.cast_into(self.h, self.cs)
+        for j, vb in enumerate(w.vace_blocks):
+            self._block(vb, self.cs, e0, ctx, rope, first=(j == 0))
+            ops.cast_into(self.cs, self.cbf[j])
+
+    def _block(self, b, xs, e0, ctx, rope, first):
+        """One WanAttentionBlock on the fp32 stream `xs` (updated in place). `first`: the stream still holds bf16 values (block 0
+        input), so the LayerNorm output is rounded to bf16 before the modulation like upstream's `.type_as(x)`."""
+        d, H = self.dims, self.dims.num_heads
+        D = d.dim
+        n = xs.shape[0]
         sh = self.shard
         if sh is None:
             q, k = self.qk[:, :D], self.qk[:, D:]
             vt = self.vt[:, :n]
         else:
-            rope = sh.rows(rope)  # RoPE uses the GLOBAL token index -> (f, h, w)
             vt = self.vt[:, :sh.n_tokens]
-        for li, b in enumerate(self.w.blocks):
-            ops.cache_hit_add(b["mod"], e0, out=self.em)  # e = modulation + e0 (fp32)
-            # --- self attention
-            ops.ln_modulate(xs, self.em, 1, 0, eps=d.eps, round_ln_to_bf16=(li == 0), out=self.h)
-            if sh is None:
-                ops.gemm(self.h, b["w_qk"], b["b_qk"], E.MC_EPI_BIAS_BF16, out=self.qk, tag="gemm_qk")
-                ops.gemm(b["w_v"], self.h, b["b_v"], E.MC_EPI_ROWBIAS_BF16, out=vt)
-                ops.rmsnorm_rope_(q, b["nq"], rope, d.head_dim, eps=d.eps)
-                ops.rmsnorm_rope_(k, b["nk"], rope, d.head_dim, eps=d.eps)
-                ops.attention(q, k, vt, H, out=self.att, tag="attn_self")
-            else:
-                from .shard import gather_rows
-                # K and V first so their all-gathers (NCCL, own stream) overlap the Q projection / RMSNorm / RoPE
-                ops.gemm(self.h, b["w_qk"][D:], b["b_qk"][D:], E.MC_EPI_BIAS_BF16, out=self.k_loc)
-                ops.rmsnorm_rope_(self.k_loc, b["nk"], rope, d.head_dim, eps=d.eps)
-                wk = gather_rows(self.k_loc, self.k_all, sh.group, async_op=True)
-                ops.gemm(self.h, b["w_v"], b["b_v"], E.MC_EPI_BIAS_BF16, out=self.v_loc)
-                wv = gather_rows(self.v_loc, self.v_all, sh.group, async_op=True)
-                ops.gemm(self.h, b["w_qk"][:D], b["b_qk"][:D], E.MC_EPI_BIAS_BF16, out=self.q_loc, tag="gemm_qk")
-                ops.rmsnorm_rope_(self.q_loc, b["nq"], rope, d.head_dim, eps=d.eps)
-                wk.wait()
-                wv.wait()
-                ops.transpose(self.v_all, vt)  # gathered V [N, D] -> V^T [D, N] for the PV MMA's K-major B operand
-                ops.attention(self.q_loc, self.k_all, vt, H, out=self.att, tag="attn_self")
-            ops.gemm(self.att, b["w_o"], b["b_o"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[2])
-            # --- cross attention (text)
-            ops.ln_affine(xs, b["n3_w"], b["n3_b"], eps=d.eps, out=self.h)
-            ops.gemm(self.h, b["c_wq"], b["c_bq"], E.MC_EPI_BIAS_BF16, out=self.cq)
-            ops.rmsnorm_rope_(self.cq, b["c_nq"], None, d.head_dim, eps=d.eps)
-            ops.gemm(ctx, b["c_wk"], b["c_bk"], E.MC_EPI_BIAS_BF16, out=self.ck)
-            ops.rmsnorm_rope_(self.ck, b["c_nk"], None, d.head_dim, eps=d.eps)
-            ops.gemm(b["c_wv"], ctx, b["c_bv"], E.MC_EPI_ROWBIAS_BF16, out=self.cvt)
-            ops.attention(self.cq, self.ck, self.cvt, H, out=self.att, tag="attn_cross")
-            att = self.att
-            if d.model_type == "i2v":  # WanI2VCrossAttention: x = attn(q, k, v) + attn(q, k_img, v_img), summed in bf16
-                cvt_img = self.cvt_img[:, :d.clip_len]
-                ops.gemm(self.ctx_img, b["c_wk_img"], b["c_bk_img"], E.MC_EPI_BIAS_BF16, out=self.ck_img)
-                ops.rmsnorm_rope_(self.ck_img, b["c_nk_img"], None, d.head_dim, eps=d.eps)
-                ops.gemm(b["c_wv_img"], self.ctx_img, b["c_bv_img"], E.MC_EPI_ROWBIAS_BF16, out=cvt_img)
-                ops.attention(self.cq, self.ck_img, cvt_img, H, out=self.att_img, tag="attn_cross_img")
-                att = ops.cache_hit_add(self.att, self.att_img, out=self.h)  # h (norm3 output) is dead once cq is projected
-            ops.gemm(att, b["c_wo"], b["c_bo"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=None)
-            # --- FFN
-            ops.ln_modulate(xs, self.em, 4, 3, eps=d.eps, out=self.h)
-            ops.gemm(self.h, b["w_f1"], b["b_f1"], E.MC_EPI_BIAS_GELU_BF16, out=self.ffn, tag="gemm_ffn1")
-            ops.gemm(self.ffn, b["w_f2"], b["b_f2"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[5], tag="gemm_ffn2")
-        return xs
+        ops.cache_hit_add(b["mod"], e0, out=self.em)  # e = modulation + e0 (fp32)
+        # --- self attention
+        ops.ln_modulate(xs, self.em, 1, 0, eps=d.eps, round_ln_to_bf16=first, out=self.h)
+        if sh is None:
+            ops.gemm(self.h, b["w_qk"], b["b_qk"], E.MC_EPI_BIAS_BF16, out=self.qk, tag="gemm_qk")
+            ops.gemm(b["w_v"], self.h, b["b_v"], E.MC_EPI_ROWBIAS_BF16, out=vt)
+            ops.rmsnorm_rope_(q, b["nq"], rope, d.head_dim, eps=d.eps)
+            ops.rmsnorm_rope_(k, b["nk"], rope, d.head_dim, eps=d.eps)
+            ops.attention(q, k, vt, H, out=self.att, tag="attn_self")
+        else:
+            from .shard import gather_rows
+            # K and V first so their all-gathers (NCCL, own stream) overlap the Q projection / RMSNorm / RoPE
+            ops.gemm(self.h, b["w_qk"][D:], b["b_qk"][D:], E.MC_EPI_BIAS_BF16, out=self.k_loc)
+            ops.rmsnorm_rope_(self.k_loc, b["nk"], rope, d.head_dim, eps=d.eps)
+            wk = gather_rows(self.k_loc, self.k_all, sh.group, async_op=True)
+            ops.gemm(self.h, b["w_v"], b["b_v"], E.MC_EPI_BIAS_BF16, out=self.v_loc)
+            wv = gather_rows(self.v_loc, self.v_all, sh.group, async_op=True)
+            ops.gemm(self.h, b["w_qk"][:D], b["b_qk"][:D], E.MC_EPI_BIAS_BF16, out=self.q_loc, tag="gemm_qk")
+            ops.rmsnorm_rope_(self.q_loc, b["nq"], rope, d.head_dim, eps=d.eps)
+            wk.wait()
+            wv.wait()
+            ops.transpose(self.v_all, vt)  # gathered V [N, D] -> V^T [D, N] for the PV MMA's K-major B operand
+            ops.attention(self.q_loc, self.k_all, vt, H, out=self.att, tag="attn_self")
+        ops.gemm(self.att, b["w_o"], b["b_o"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[2])
+        # --- cross attention (text)
+        ops.ln_affine(xs, b["n3_w"], b["n3_b"], eps=d.eps, out=self.h)
+        ops.gemm(self.h, b["c_wq"], b["c_bq"], E.MC_EPI_BIAS_BF16, out=self.cq)
+        ops.rmsnorm_rope_(self.cq, b["c_nq"], None, d.head_dim, eps=d.eps)
+        ops.gemm(ctx, b["c_wk"], b["c_bk"], E.MC_EPI_BIAS_BF16, out=self.ck)
+        ops.rmsnorm_rope_(self.ck, b["c_nk"], None, d.head_dim, eps=d.eps)
+        ops.gemm(b["c_wv"], ctx, b["c_bv"], E.MC_EPI_ROWBIAS_BF16, out=self.cvt)
+        ops.attention(self.cq, self.ck, self.cvt, H, out=self.att, tag="attn_cross")
+        att = self.att
+        if d.model_type == "i2v":  # WanI2VCrossAttention: x = attn(q, k, v) + attn(q, k_img, v_img), summed in bf16
+            cvt_img = self.cvt_img[:, :d.clip_len]
+            ops.gemm(self.ctx_img, b["c_wk_img"], b["c_bk_img"], E.MC_EPI_BIAS_BF16, out=self.ck_img)
+            ops.rmsnorm_rope_(self.ck_img, b["c_nk_img"], None, d.head_dim, eps=d.eps)
+            ops.gemm(b["c_wv_img"], self.ctx_img, b["c_bv_img"], E.MC_EPI_ROWBIAS_BF16, out=cvt_img)
+            ops.attention(self.cq, self.ck_img, cvt_img, H, out=self.att_img, tag="attn_cross_img")
+            att = ops.cache_hit_add(self.att, self.att_img, out=self.h)  # h (norm3 output) is dead once cq is projected
+        ops.gemm(att, b["c_wo"], b["c_bo"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=None)
+        # --- FFN
+        ops.ln_modulate(xs, self.em, 4, 3, eps=d.eps, out=self.h)
+        ops.gemm(self.h, b["w_f1"], b["b_f1"], E.MC_EPI_BIAS_GELU_BF16, out=self.ffn, tag="gemm_ffn1")
+        ops.gemm(self.ffn, b["w_f2"], b["b_f2"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[5], tag="gemm_ffn2")
 
     # ------------------------------------------------------------------------------------------ epilogue (:304-305)
     def head(self, x, e, grid, residual=None):

@@ -103,6 +103,40 @@ def test_oracle_i2v_branch_uses_image_tokens_and_y():
     assert 0 < rel < 2e-2, rel
 
 
+def test_oracle_vace_branch():
+    """VACE restatement (magcache_generate.py:439-560 + upstream VaceWanModel): hints only on a miss, output depends on the control
+    video and on vace_context_scale, scale 0 equals running the main blocks without hints, bf16 emulation close to fp64."""
+    m = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=4, text_dim=128, text_len=32, model_type="vace", vace_in_dim=24).init_synthetic(0)
+    assert m.vace_layers == [0, 2] and [getattr(b, "block_id", None) for b in m.blocks] == [0, None, 1, None]
+    assert hasattr(m.vace_blocks[0], "before_proj") and not hasattr(m.vace_blocks[1], "before_proj")
+    m.__class__ = type("V", (m.__class__,), {})
+    wan_ref.install_magcache(m.__class__, [1.0] * 8, 4, vace=True)
+    g = torch.Generator().manual_seed(0)
+    lat, vc, ctx = torch.randn(16, 2, 8, 8, generator=g), torch.randn(24, 2, 8, 8, generator=g), torch.randn(9, 128, generator=g)
+    t = torch.tensor([300.0])
+
+    def run(model, scale=1.0, vcx=vc, dt=torch.float32):
+        model.cnt = 0
+        return model([lat.to(dt)], t=t, vace_context=[vcx.to(dt)], context=[ctx.to(dt)], seq_len=32, vace_context_scale=scale)[0]
+
+    with torch.no_grad():
+        a, b, c0 = run(m), run(m, vcx=vc * 0.3), run(m, scale=0.0)
+        plain = copy.deepcopy(m)
+        plain.__class__ = type("P", (plain.__class__,), {})
+        wan_ref.install_magcache(plain.__class__, [1.0] * 8, 4)  # the T2V forward on the same weights: no hints at all
+        plain.cnt = 0
+        p = plain([lat], t=t, context=[ctx], seq_len=32)[0]
+        m64 = copy.deepcopy(m).double()
+        m64.__class__ = type("V64", (m64.__class__,), {})
+        wan_ref.install_magcache(m64.__class__, [1.0] * 8, 4, vace=True)
+        with wan_ref.exact_fp64():
+            exact = run(m64, dt=torch.float64)
+    assert float((a - b).abs().max()) > 1e-2 and float((a - c0).abs().max()) > 1e-2
+    assert torch.equal(c0, p)
+    rel = float((a.double() - exact).norm() / exact.norm())
+    assert 0 < rel < 2e-2, rel
+
+
 def test_oracle_seq_len_padding_reaches_no_real_token():
     """magcache_generate.py:242-246 pads the token axis with zero rows up to `seq_len`; with the key mask of upstream's
     flash_attention(k_lens=seq_lens) the real tokens' outputs do not change (what lets the CUDA path skip the padded rows), while the

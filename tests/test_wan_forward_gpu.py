@@ -142,6 +142,56 @@ def test_i2v_forward_vs_oracle_and_fp64():
         ours([lat.to(DEV)], t=t.to(DEV), context=[ctx.to(DEV)], seq_len=n_tok)
 
 
+def test_vace_forward_vs_oracle_and_fp64():
+    """`magcache_vace_forward` (magcache_generate.py:439-560, installed at :1126-1150): control video -> vace_patch_embedding ->
+    control blocks (before_proj mixing with the main input, after_proj hints) -> every second main block adds its hint.
+    miss, miss, hit, hit against the oracle, the first call also against fp64; then a non-default vace_context_scale."""
+    from oracle import wan_ref
+    import magcache_b200 as mc
+    model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=4, text_dim=512, text_len=64, model_type="vace",
+                             vace_in_dim=24).init_synthetic(7)
+    g = torch.Generator().manual_seed(6)
+    lat, vc = torch.randn(16, 3, 16, 24, generator=g), torch.randn(24, 3, 16, 24, generator=g)
+    ctx, ctx_null = torch.randn(37, 512, generator=g), torch.randn(30, 512, generator=g)
+    n_tok, t, steps = 3 * 8 * 12, torch.tensor([777.0]), 4
+    table = mc.tables()["wan2.1_vace_1.3b"]
+
+    def ref_install(m):
+        cls = type("RefWanVace", (m.__class__,), {})
+        m.__class__ = cls
+        wan_ref.install_magcache(cls, table, steps, thresh=10.0, K=3, retention_ratio=0.25, vace=True)
+        return m
+
+    ref_model = ref_install(copy.deepcopy(model))
+    ours = copy.deepcopy(model).to(DEV)
+    ours.__class__ = type("OurWanVace", (ours.__class__,), {})
+    mc.init_magcache(ours, steps, thresh=10.0, K=3, retention_ratio=0.25, mag_ratios=table)
+    assert type(ours).forward is mc.magcache_vace_forward
+    with torch.no_grad():
+        m64 = ref_install(copy.deepcopy(model).double())
+        with wan_ref.exact_fp64():
+            exact = m64([lat.double()], t=t, vace_context=[vc.double()], context=[ctx.double()], seq_len=n_tok)[0]
+        for i, c in enumerate((ctx, ctx_null, ctx, ctx_null)):
+            ref = ref_model([lat], t=t, vace_context=[vc], context=[c], seq_len=n_tok)[0]
+            out = ours([lat.to(DEV)], t=t.to(DEV), vace_context=[vc.to(DEV)], context=[c.to(DEV)], seq_len=n_tok)[0].cpu()
+            assert bool(ref_model.last_skip) == (i >= 2)
+            assert rel_l2(out, ref) <= 2e-2, (i, rel_l2(out, ref))
+            if i == 0:
+                e_ours, e_ref = rel_l2(out, exact), rel_l2(ref, exact)
+                print(f"[vace] rel-L2: ours vs fp64 {e_ours:.3e} | oracle(bf16) vs fp64 {e_ref:.3e}")
+                assert e_ours <= 1.5 * e_ref + 1e-4
+            assert ours.cnt == ref_model.cnt and ours.accumulated_err == ref_model.accumulated_err
+        # the control branch matters, and a scaled hint follows the oracle too
+        mc.reset_magcache(ours)
+        ref_model.cnt = 0
+        ref_s = ref_model([lat], t=t, vace_context=[vc], context=[ctx], seq_len=n_tok, vace_context_scale=0.5)[0]
+        out_s = ours([lat.to(DEV)], t=t.to(DEV), vace_context=[vc.to(DEV)], context=[ctx.to(DEV)], seq_len=n_tok, vace_context_scale=0.5)[0].cpu()
+        assert rel_l2(out_s, ref_s) <= 2e-2
+        assert rel_l2(out_s, ref) > 1e-2  # != the scale-1 result
+    with pytest.raises(TypeError):
+        mc.magcache_forward(ours, [lat.to(DEV)], t.to(DEV), [ctx.to(DEV)], n_tok)  # a VACE model without its control video
+
+
 def test_magcache_loop_mask_cache_and_outputs():
     """20 forward calls (10 steps x cond/uncond) through the patched forward on both sides, same inputs every call.
     Checks: identical skip decisions (bit-exact), controller attributes, residual-cache contents, per-call outputs."""
