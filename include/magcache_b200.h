@@ -147,6 +147,35 @@ int32_t mc_residual_sub_stats(const void* x_out, int32_t xo_dtype, const void* x
                               void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * TeaCache comparator (the baseline every published MagCache table is compared against)
+ * eval/magcache/experiments/Wan2.1_EVAL/wan_teacache.py:533-564 (controller), :566-582 (same hit / miss branches), :899-928 (setup)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct mc_tea_config {
+  int32_t num_steps;     /* forward calls per video (2*sample_steps) */
+  int32_t ret_steps;     /* calls [0, ret_steps) always compute        (:538; 1*2 or 10*2, :919/:927) */
+  int32_t cutoff_steps;  /* calls [cutoff_steps, num_steps) always compute (:921/:928) */
+  int32_t n_coef;        /* polynomial degree + 1, <= 8 */
+  double thresh;         /* teacache_thresh */
+  double coef[8];        /* np.poly1d order: highest power first (:915-926) */
+} mc_tea_config;
+
+typedef struct mc_tea_state {
+  int32_t cnt;
+  int32_t pad;
+  double accumulated[2]; /* accumulated_rel_l1_distance_even / _odd */
+} mc_tea_state;
+
+/* *needs = 1 when the call at st->cnt consults the distance (retention / cutoff calls do not: no reduction, no host sync). */
+int32_t mc_tea_needs_distance(const mc_tea_config* cfg, const mc_tea_state* st, int32_t* needs);
+/* One decision (:535-564): *calc = 1 -> run the block stack, 0 -> reuse the cached residual. rel_l1 = mean|e - e_prev| / mean|e_prev|
+ * of this CFG branch (ignored on retention / cutoff calls). Does not advance cnt. */
+int32_t mc_tea_decide(const mc_tea_config* cfg, mc_tea_state* st, double rel_l1, int32_t* calc);
+/* cnt += 1, wrapping at num_steps (:587-589; the accumulators are NOT reset at the wrap, as in the reference). */
+int32_t mc_tea_advance(const mc_tea_config* cfg, mc_tea_state* st);
+/* sums_dev (device, 2 doubles, overwritten) = { sum |cur - prev|, sum |prev| } over n fp32 elements — the two means of :543. */
+int32_t mc_rel_l1(const float* cur, const float* prev, int64_t n, double* sums_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * DiT block-stack kernels (cache-miss branch `for block in self.blocks: x = block(x, **kwargs)`,
  * magcache_generate.py:297-298; block arithmetic per upstream Wan2.1 wan/modules/model.py)
  * ---------------------------------------------------------------------------------------------------------- */

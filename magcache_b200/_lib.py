@@ -33,6 +33,15 @@ class CtrlConfig(Structure):
                 ("ratio_veto", c_double), ("mag_ratios", POINTER(c_double))]
 
 
+class TeaConfig(Structure):
+    _fields_ = [("num_steps", c_int32), ("ret_steps", c_int32), ("cutoff_steps", c_int32), ("n_coef", c_int32), ("thresh", c_double),
+                ("coef", c_double * 8)]
+
+
+class TeaState(Structure):
+    _fields_ = [("cnt", c_int32), ("pad", c_int32), ("accumulated", c_double * 2)]
+
+
 class CtrlState(Structure):
     _fields_ = [("cnt", c_int32), ("accumulated_steps", c_int32 * 2), ("pad", c_int32), ("accumulated_ratio", c_double * 2),
                 ("accumulated_err", c_double * 2)]
@@ -49,6 +58,10 @@ SIGNATURES = {
     "mc_ctrl_advance": [POINTER(CtrlConfig), POINTER(CtrlState)],
     "mc_ctrl_mask": [POINTER(CtrlConfig), c_int32, POINTER(c_uint8)],
     "mc_ctrl_validate": [POINTER(CtrlConfig)],
+    "mc_tea_needs_distance": [POINTER(TeaConfig), POINTER(TeaState), POINTER(c_int32)],
+    "mc_tea_decide": [POINTER(TeaConfig), POINTER(TeaState), c_double, POINTER(c_int32)],
+    "mc_tea_advance": [POINTER(TeaConfig), POINTER(TeaState)],
+    "mc_rel_l1": [c_void_p, c_void_p, c_int64, c_void_p, c_void_p],
     "mc_cache_hit_add": [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
     "mc_residual_sub": [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
     "mc_cfg_combine": [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p],

@@ -222,6 +222,30 @@ static int32_t launch_cfg_step(const CfgStepArgs& a, int64_t groups, int64_t n, 
   return MC_OK;
 }
 
+// ---- TeaCache distance: sum |cur - prev| and sum |prev| of the (tiny) modulated time embedding, one CTA --------------------
+__global__ void __launch_bounds__(256) rel_l1_kernel(const float* __restrict__ cur, const float* __restrict__ prev, int64_t n,
+                                                     double* __restrict__ sums) {
+  __shared__ double s_d[8], s_p[8];
+  double d = 0.0, p = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float c = cur[i], q = prev[i];
+    d += static_cast<double>(fabsf(c - q));  // the difference is rounded to fp32 like torch's `modulated_inp - previous`
+    p += static_cast<double>(fabsf(q));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+    p += __shfl_xor_sync(0xffffffffu, p, o);
+  }
+  if ((threadIdx.x & 31) == 0) s_d[threadIdx.x >> 5] = d, s_p[threadIdx.x >> 5] = p;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double td = 0.0, tp = 0.0;
+    for (int w = 0; w < 8; ++w) td += s_d[w], tp += s_p[w];
+    sums[0] = td;
+    sums[1] = tp;
+  }
+}
+
 // ---- K3: per-row norms / cosine, single pass ---------------------------------------------------------------
 // One warp per row; lanes stride over 8-element groups. Optionally also forms cur = xo - xi on the fly and stores it.
 template <int DCUR, int DPREV, bool FUSE_SUB>
@@ -475,6 +499,13 @@ int32_t mc_cfg_combine(const float* cond, const float* uncond, float guide_scale
     mc::cfg_combine_tail_kernel<<<static_cast<int>((rem + 255) / 256), 256, 0, s>>>(cond, uncond, guide_scale, out, groups * 8, n);
     MC_CHECK_LAUNCH("cfg_combine_tail_kernel launch");
   }
+  return MC_OK;
+}
+
+int32_t mc_rel_l1(const float* cur, const float* prev, int64_t n, double* sums_dev, void* stream) {
+  MC_CHECK_ARG(cur && prev && sums_dev && n >= 1, "mc_rel_l1: bad arguments");
+  mc::rel_l1_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(cur, prev, n, sums_dev);
+  MC_CHECK_LAUNCH("rel_l1_kernel launch");
   return MC_OK;
 }
 

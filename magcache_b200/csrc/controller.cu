@@ -230,6 +230,54 @@ int32_t mc_ctrl_mask(const mc_ctrl_config* cfg, int32_t calls, uint8_t* mask) {
   return MC_OK;
 }
 
+// ---- TeaCache comparator: eval/magcache/experiments/Wan2.1_EVAL/wan_teacache.py:535-564 ------------------------------------
+static int32_t tea_check(const mc_tea_config* c, const mc_tea_state* st) {
+  MC_CHECK_ARG(c && st, "mc_tea: null pointer");
+  MC_CHECK_ARG(c->num_steps >= 1 && c->n_coef >= 1 && c->n_coef <= 8, "mc_tea: num_steps=%d n_coef=%d", c->num_steps, c->n_coef);
+  if (st->cnt < 0 || st->cnt >= c->num_steps) {
+    mc::set_error("mc_tea: cnt=%d outside [0, %d)", st->cnt, c->num_steps);
+    return MC_ERR_STATE;
+  }
+  return MC_OK;
+}
+
+int32_t mc_tea_needs_distance(const mc_tea_config* cfg, const mc_tea_state* st, int32_t* needs) {
+  int32_t rc = tea_check(cfg, st);
+  if (rc) return rc;
+  MC_CHECK_ARG(needs, "mc_tea_needs_distance: null pointer");
+  *needs = !(st->cnt < cfg->ret_steps || st->cnt >= cfg->cutoff_steps);
+  return MC_OK;
+}
+
+int32_t mc_tea_decide(const mc_tea_config* cfg, mc_tea_state* st, double rel_l1, int32_t* calc) {
+  int32_t rc = tea_check(cfg, st);
+  if (rc) return rc;
+  MC_CHECK_ARG(calc, "mc_tea_decide: null pointer");
+  const int i = st->cnt % 2;  // even -> condition, odd -> uncondition
+  if (st->cnt < cfg->ret_steps || st->cnt >= cfg->cutoff_steps) {
+    *calc = 1;
+    st->accumulated[i] = 0.0;
+    return MC_OK;
+  }
+  double y = 0.0;  // np.poly1d(coefficients)(x): Horner, highest power first
+  for (int k = 0; k < cfg->n_coef; ++k) y = y * rel_l1 + cfg->coef[k];
+  st->accumulated[i] += y;
+  if (st->accumulated[i] < cfg->thresh) {
+    *calc = 0;
+  } else {
+    *calc = 1;
+    st->accumulated[i] = 0.0;
+  }
+  return MC_OK;
+}
+
+int32_t mc_tea_advance(const mc_tea_config* cfg, mc_tea_state* st) {
+  MC_CHECK_ARG(cfg && st, "mc_tea_advance: null pointer");
+  st->cnt += 1;
+  if (st->cnt >= cfg->num_steps) st->cnt = 0;
+  return MC_OK;
+}
+
 int32_t mc_ctrl_validate(const mc_ctrl_config* cfg) {
   int32_t rc = mc::check_cfg(cfg);
   if (rc) return rc;

@@ -114,6 +114,20 @@ def cfg_step(cond, uncond, guide_scale, x, coef_v, coef_x=1.0, hist=(), coef_h=(
     return out
 
 
+def rel_l1(cur, prev):
+    """`((cur - prev).abs().mean() / prev.abs().mean()).cpu().item()` (wan_teacache.py:543): one tiny reduction kernel and the one
+    host sync the reference has too. The two means and the quotient are rounded to fp32 like the torch scalars."""
+    import numpy as np
+    _dev(cur), _dev(prev)
+    assert cur.dtype == prev.dtype == torch.float32 and cur.is_contiguous() and prev.is_contiguous() and cur.numel() == prev.numel()
+    sums = torch.empty(2, dtype=torch.float64, device=cur.device)
+    check(lib.mc_rel_l1(cur.data_ptr(), prev.data_ptr(), cur.numel(), sums.data_ptr(), _stream()))
+    _count()
+    d, p = sums.tolist()
+    n = cur.numel()
+    return float(np.float32(d / n) / np.float32(p / n))
+
+
 def _finish_stats(stats_dev):
     s0, s1, s2, n = stats_dev.tolist()  # the single host sync of the calibration path
     mean = s0 / n

@@ -252,3 +252,93 @@ def magcache_branch(self, hidden, run_blocks, family, cache_attr):
         setattr(self, cache_attr, cur)
     ctrl.advance(self)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# TeaCache comparator (the baseline of every published MagCache table) on the same engine
+# ------------------------------------------------------------------------------------------------------------------
+# coefficients of eval/magcache/experiments/Wan2.1_EVAL/wan_teacache.py:913-926 (t2v) — keyed by (use_ret_steps, model size)
+TEACACHE_COEFFICIENTS = {
+    (True, "1.3B"): [-5.21862437e+04, 9.23041404e+03, -5.28275948e+02, 1.36987616e+01, -4.99875664e-02],
+    (True, "14B"): [-3.03318725e+05, 4.90537029e+04, -2.65530556e+03, 5.87365115e+01, -3.15583525e-01],
+    (False, "1.3B"): [2.39676752e+03, -1.31110545e+03, 2.01331979e+02, -8.29855975e+00, 1.37887774e-01],
+    (False, "14B"): [-5784.54975374, 5449.50911966, -1811.16591783, 256.27178429, -13.02252404],
+}
+
+
+def _tea_structs(self):
+    import ctypes
+
+    from . import _lib
+    coef = [float(c) for c in self.coefficients]
+    cfg = _lib.TeaConfig()
+    cfg.num_steps, cfg.ret_steps, cfg.cutoff_steps, cfg.n_coef, cfg.thresh = int(self.num_steps), int(self.ret_steps), int(self.cutoff_steps), len(coef), float(self.teacache_thresh)
+    for i, c in enumerate(coef):
+        cfg.coef[i] = c
+    st = _lib.TeaState()
+    st.cnt = int(self.cnt)
+    st.accumulated[0], st.accumulated[1] = float(self.accumulated_rel_l1_distance_even), float(self.accumulated_rel_l1_distance_odd)
+    return ctypes, _lib, cfg, st
+
+
+def teacache_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
+    r"""eval/magcache/experiments/Wan2.1_EVAL/wan_teacache.py:457-590 on the B200 kernels, state under the reference's attribute
+    names (`cnt, num_steps, teacache_thresh, accumulated_rel_l1_distance_even/odd, previous_e0_even/odd,
+    previous_residual_even/odd, use_ref_steps, ret_steps, cutoff_steps, coefficients, enable_teacache`). The decision reads the
+    relative L1 change of the modulated time embedding (one tiny reduction + the `.item()` sync the reference has), the hit /
+    miss branches are the MagCache ones (`x += previous_residual` | block stack, residual = x - ori_x)."""
+    eng = _stage(self, x, t, context, seq_len, clip_fea, y)
+    if not self.enable_teacache:  # :584-586: plain forward (the counter still advances, :587-589)
+        out = eng.forward("miss", self.cnt % 2)
+        self.cnt = 0 if self.cnt + 1 >= self.num_steps else self.cnt + 1
+        return [out]
+    ctypes, _lib, cfg, st = _tea_structs(self)
+    slot = self.cnt % 2
+    suffix = "even" if slot == 0 else "odd"
+    e, e0 = eng.time_embedding()
+    modulated = (e0 if self.use_ref_steps else e).reshape(-1)  # :534
+    needs = ctypes.c_int32()
+    _lib.check(_lib.lib.mc_tea_needs_distance(ctypes.byref(cfg), ctypes.byref(st), ctypes.byref(needs)))
+    dist = ops.rel_l1(modulated, getattr(self, "previous_e0_" + suffix).reshape(-1)) if needs.value else 0.0
+    calc = ctypes.c_int32()
+    _lib.check(_lib.lib.mc_tea_decide(ctypes.byref(cfg), ctypes.byref(st), dist, ctypes.byref(calc)))
+    self.accumulated_rel_l1_distance_even, self.accumulated_rel_l1_distance_odd = st.accumulated[0], st.accumulated[1]
+    setattr(self, "previous_e0_" + suffix, modulated.clone().view((e0 if self.use_ref_steps else e).shape))  # :549 / :564
+    cur = getattr(self, "previous_residual_" + suffix)
+    if cur is None:
+        eng.res_valid[slot] = False
+    elif torch.is_tensor(cur) and cur.data_ptr() != eng.res[slot].data_ptr():
+        eng.res[slot].copy_(cur.reshape(eng.res[slot].shape))
+        eng.res_valid[slot] = True
+    out = eng.forward("miss" if calc.value else "hit", slot)
+    setattr(self, "previous_residual_" + suffix, eng.res[slot].view(1, *eng.res[slot].shape))
+    _lib.check(_lib.lib.mc_tea_advance(ctypes.byref(cfg), ctypes.byref(st)))
+    self.cnt = st.cnt  # :587-589
+    return [out]
+
+
+def init_teacache(model, sample_steps, teacache_thresh=0.2, use_ret_steps=False, ckpt_dir=None, coefficients=None):
+    """The installation block of wan_teacache.py:899-928 as a helper: patches the CLASS. Coefficients are chosen by the '1.3B' /
+    '14B' substring of `ckpt_dir` like the reference, or passed explicitly."""
+    cls = model.__class__
+    cls.enable_teacache = True
+    cls.forward = teacache_forward
+    cls.cnt = 0
+    cls.num_steps = sample_steps * 2
+    cls.teacache_thresh = teacache_thresh
+    cls.accumulated_rel_l1_distance_even = 0
+    cls.accumulated_rel_l1_distance_odd = 0
+    cls.previous_e0_even = cls.previous_e0_odd = None
+    cls.previous_residual_even = cls.previous_residual_odd = None
+    cls.use_ref_steps = use_ret_steps
+    if coefficients is None:
+        size = "1.3B" if "1.3B" in (ckpt_dir or "") else ("14B" if "14B" in (ckpt_dir or "") else None)
+        if size is None:
+            raise KeyError(f"no TeaCache coefficients match ckpt_dir={ckpt_dir!r} (the reference would hit AttributeError later)")
+        coefficients = TEACACHE_COEFFICIENTS[(bool(use_ret_steps), size)]
+    cls.coefficients = list(coefficients)
+    if use_ret_steps:
+        cls.ret_steps, cls.cutoff_steps = 10 * 2, sample_steps * 2
+    else:
+        cls.ret_steps, cls.cutoff_steps = 1 * 2, sample_steps * 2 - 2
+    return model

@@ -356,6 +356,15 @@ class WanEngine:
         self.ctx_in.zero_()
         self.ctx_in[:L].copy_(context)
 
+    def time_embedding(self):
+        """`e = time_embedding(sinusoid(t))`, `e0 = time_projection(e)` (fp32 region, magcache_generate.py:249-254) from the staged t:
+        e fp32 [1, D], e0 fp32 [6, D]. Also what the TeaCache comparator measures between steps (wan_teacache.py:534)."""
+        d, w = self.dims, self.w
+        sin = ops.time_sinusoid(self.s_t, d.freq_dim)
+        e = ops.linear_f32_small(ops.linear_f32_small(sin, w.time_w1, w.time_b1, act=2), w.time_w2, w.time_b2, act=0)
+        e0 = ops.linear_f32_small(e, w.tproj_w, w.tproj_b, act=1).view(6, d.dim)
+        return e, e0
+
     def prologue(self):
         """Embeddings from the staged inputs. Returns (x0 bf16 [N_local, D], e fp32 [1, D], e0 fp32 [6, D], ctx bf16 [text_len, D])."""
         d, w = self.dims, self.w
@@ -363,9 +372,7 @@ class WanEngine:
         if self.shard is not None:
             tok = self.shard.rows(tok)  # this rank embeds only its own tokens
         ops.gemm(tok, w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
-        sin = ops.time_sinusoid(self.s_t, d.freq_dim)
-        e = ops.linear_f32_small(ops.linear_f32_small(sin, w.time_w1, w.time_b1, act=2), w.time_w2, w.time_b2, act=0)
-        e0 = ops.linear_f32_small(e, w.tproj_w, w.tproj_b, act=1).view(6, d.dim)
+        e, e0 = self.time_embedding()
         ops.gemm(self.ctx_in, w.text_w1, w.text_b1, E.MC_EPI_BIAS_GELU_BF16, out=self.ctx_h)
         ops.gemm(self.ctx_h, w.text_w2, w.text_b2, E.MC_EPI_BIAS_BF16, out=self.ctx)
         if d.model_type == "i2v":

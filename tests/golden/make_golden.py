@@ -440,6 +440,91 @@ class RefControllerOpenSora:
         return skip
 
 
+TEACACHE = f"{REF}/eval/magcache/experiments/Wan2.1_EVAL/wan_teacache.py"
+
+
+class RefTeaCache:
+    """The controller statements of teacache_forward (wan_teacache.py:533-564: the first `if self.enable_teacache:` block) and the
+    counter (:587-589), executed on stand-in tensors; the coefficient literals of the t2v installation block (:913-926)."""
+
+    def __init__(self):
+        fn = _func(_tree(TEACACHE), "teacache_forward")
+        blocks = [st for st in fn.body if isinstance(st, ast.If) and _mentions(st.test, "enable_teacache")]
+        assert len(blocks) == 2  # controller, then the hit/miss branches
+        self.ctrl = _compile([blocks[0]])
+        self.tail = _compile(_counter_tail(fn, "cnt"))
+        # coefficient literals: assignments `wan_t2v.model.__class__.coefficients = [...]` in order of appearance
+        lits = []
+        for n in ast.walk(_tree(TEACACHE)):
+            if isinstance(n, ast.Assign) and isinstance(n.targets[0], ast.Attribute) and n.targets[0].attr == "coefficients":
+                base = n.targets[0]
+                while isinstance(base, ast.Attribute):
+                    base = base.value
+                if getattr(base, "id", "") == "wan_t2v":
+                    lits.append((n.lineno, [float(v) for v in eval(compile(ast.Expression(n.value), "<c>", "eval"))]))
+        lits.sort()
+        assert len(lits) == 4, lits
+        self.coefficients = {"ret_1.3B": lits[0][1], "ret_14B": lits[1][1], "noret_1.3B": lits[2][1], "noret_14B": lits[3][1]}
+
+    def state(self, steps, thresh, key):
+        use_ret = key.startswith("ret")
+        return types.SimpleNamespace(enable_teacache=True, cnt=0, num_steps=2 * steps, teacache_thresh=thresh, accumulated_rel_l1_distance_even=0,
+                                     accumulated_rel_l1_distance_odd=0, previous_e0_even=None, previous_e0_odd=None, use_ref_steps=use_ret,
+                                     coefficients=self.coefficients[key], ret_steps=(10 * 2 if use_ret else 1 * 2),
+                                     cutoff_steps=(2 * steps if use_ret else 2 * steps - 2))  # :901-928
+
+    def call(self, state, e, e0):
+        env = {"self": state, "np": np, "e": e, "e0": e0}
+        exec(self.ctrl, env)
+        calc = env["should_calc_even"] if state.is_even else env["should_calc_odd"]
+        exec(self.tail, env)
+        return bool(calc)
+
+
+def teacache_cases():
+    """Synthetic but realistic modulated inputs: sinusoidal timestep embedding (freq_dim 256) through a seeded 2-layer SiLU MLP and
+    the 6-way projection, at the shift-5 flow timesteps; the cond and uncond calls of a step see the same t (wan_magcache.py:296-299)."""
+    import torch
+    ref = RefTeaCache()
+    g = torch.Generator().manual_seed(0)
+    D, fd = 192, 256
+    W1, W2, W3 = torch.randn(D, fd, generator=g) * 0.05, torch.randn(D, D, generator=g) * 0.08, torch.randn(6 * D, D, generator=g) * 0.08
+    b2, b3 = torch.randn(D, generator=g), torch.randn(6 * D, generator=g)  # trained models: the embedding moves a few % per step
+
+    def embed(tval, amp):
+        half = fd // 2
+        pos = torch.tensor([tval], dtype=torch.float64)
+        s_ = torch.outer(pos, torch.pow(10000, -torch.arange(half, dtype=torch.float64).div(half)))
+        x = torch.cat([torch.cos(s_), torch.sin(s_)], dim=1).float()
+        x[:, :64] = 0.0
+        x[:, half:half + 64] = 0.0  # keep the slow frequencies only: neighbouring timesteps stay correlated
+        e = amp * torch.nn.functional.silu(x @ W1.t()) @ W2.t() + b2
+        e0 = (amp * torch.nn.functional.silu(e) @ W3.t() + b3).unflatten(1, (6, D))
+        return e, e0
+
+    out = {"coefficients": ref.coefficients, "cases": []}
+    for key in ref.coefficients:
+        for steps, amp in ((50, 0.6), (50, 2.0), (50, 6.0), (30, 2.0)):
+            for thresh in (0.05, 0.1, 0.2, 0.3):
+                st = ref.state(steps, thresh, key)
+                s_lin = np.linspace(1.0, 1.0 / steps, steps)
+                sig = 5.0 * s_lin / (1 + 4.0 * s_lin)
+                dists, mask = [], []
+                n_calls = 2 * steps * 2 + 3  # two videos and a bit: the accumulators are not reset at the wrap
+                for c in range(n_calls):
+                    e, e0 = embed(float(sig[(c // 2) % steps] * 1000.0), amp)
+                    mod = e0 if st.use_ref_steps else e
+                    prev = st.previous_e0_even if st.cnt % 2 == 0 else st.previous_e0_odd
+                    consulted = not (st.cnt < st.ret_steps or st.cnt >= st.cutoff_steps)
+                    dists.append(((mod - prev).abs().mean() / prev.abs().mean()).cpu().item() if consulted else None)
+                    mask.append(1 if ref.call(st, e, e0) else 0)
+                out["cases"].append({"key": key, "steps": steps, "amp": amp, "thresh": thresh, "ret_steps": st.ret_steps, "cutoff_steps": st.cutoff_steps,
+                                     "rel_l1": dists, "calc": "".join(map(str, mask)), "computed_first_video": int(sum(mask[:2 * steps])),
+                                     "final": {"cnt": int(st.cnt), "even": float(st.accumulated_rel_l1_distance_even),
+                                               "odd": float(st.accumulated_rel_l1_distance_odd)}})
+    return out
+
+
 def remaining_tables():
     """Table literals not covered above: Qwen-Image / Qwen-Image-Edit (`mag_ratios = [...]` + [1.0]*2 prefix, :76 / :79) and
     FLUX-Kontext (magcache_flux_kontext.py:458)."""
@@ -573,6 +658,11 @@ def main():
     print("all tables:", {k: len(v["values"]) for k, v in every.items()})
     for c in pe["eval_wan_masks"][:2] + pe["opensora_masks"][:2] + pe["framepack_masks"][:1]:
         print({k: v for k, v in c.items() if k in ("thresh", "K", "mask", "skipped_first_video")})
+
+    tea = teacache_cases()
+    with open(f"{OUT}/teacache.json", "w") as f:
+        json.dump(tea, f, indent=0)
+    print("teacache cases:", len(tea["cases"]), [(c["key"], c["thresh"], c["computed_first_video"]) for c in tea["cases"] if c["steps"] == 50][:8])
 
     cal = calib_cases()
     with open(f"{OUT}/calib_stats.json", "w") as f:

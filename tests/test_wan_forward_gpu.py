@@ -192,6 +192,45 @@ def test_vace_forward_vs_oracle_and_fp64():
         mc.magcache_forward(ours, [lat.to(DEV)], t.to(DEV), [ctx.to(DEV)], n_tok)  # a VACE model without its control video
 
 
+def test_teacache_comparator_loop_vs_oracle():
+    """`teacache_forward` (eval/magcache/experiments/Wan2.1_EVAL/wan_teacache.py:457-590) on the same engine: 8 steps x cond/uncond,
+    the timestep embedding drifting as in a real schedule; same compute/skip decisions as the oracle on every call (the distance is
+    measured on each side's own embedding), same accumulators to 1e-4, outputs and cached residuals within the usual tolerance."""
+    import magcache_b200 as mc
+    wan_ref, model = build("tiny")
+    steps = 8
+    coef = [0.02, 0.04, 0.0]  # rescale polynomial sized for this random-weight model (rel. L1 between steps ~0.9): mixes hits and misses
+    ref_model = copy.deepcopy(model)
+    ref_model.__class__ = type("RefTea", (ref_model.__class__,), {})
+    wan_ref.install_teacache(type(ref_model), steps, 0.08, coef)
+    ours = copy.deepcopy(model).to(DEV)
+    ours.__class__ = type("OurTea", (ours.__class__,), {})
+    mc.init_teacache(ours, steps, teacache_thresh=0.08, coefficients=coef)
+    assert type(ours).ret_steps == 2 and type(ours).cutoff_steps == 2 * steps - 2
+    lat, ctx, ctx_null = make_inputs(3)
+    n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
+    sig = wan_ref.flow_sigmas(steps)
+    skips = []
+    with torch.no_grad():
+        for i in range(steps):
+            t = torch.tensor([float(sig[i] * 1000)])
+            for c in (ctx, ctx_null):
+                ref = ref_model([lat], t=t, context=[c], seq_len=n_tok)[0]
+                out = ours([lat.to(DEV)], t=t.to(DEV), context=[c.to(DEV)], seq_len=n_tok)[0].cpu()
+                skips.append(int(ref_model.last_skip))
+                assert rel_l2(out, ref) <= 2e-2, (i, rel_l2(out, ref))
+                assert ours.cnt == ref_model.cnt
+                for sfx in ("even", "odd"):
+                    a, b = getattr(ours, "accumulated_rel_l1_distance_" + sfx), getattr(ref_model, "accumulated_rel_l1_distance_" + sfx)
+                    assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (i, sfx, a, b)
+                    ro, rr = getattr(ours, "previous_residual_" + sfx), getattr(ref_model, "previous_residual_" + sfx)
+                    assert (ro is None) == (rr is None)
+                    if rr is not None:
+                        assert rel_l2(ro.cpu(), rr) <= 3e-2
+    assert 0 < sum(skips) < len(skips) - 4, skips  # the run exercised both branches beyond the forced first / last steps
+    print("teacache skips:", "".join(map(str, skips)))
+
+
 def test_magcache_loop_mask_cache_and_outputs():
     """20 forward calls (10 steps x cond/uncond) through the patched forward on both sides, same inputs every call.
     Checks: identical skip decisions (bit-exact), controller attributes, residual-cache contents, per-call outputs."""
