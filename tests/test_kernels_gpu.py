@@ -164,6 +164,19 @@ def test_unipc_sampler_on_the_kernel_matches_the_oracle():
         assert ops.LAUNCHES - launches0 == (40 if name == "unipc" else 20)
 
 
+@pytest.mark.parametrize("n", [1536, 6 * 1536, 6 * 5120, 7])
+def test_rel_l1_matches_the_reference_expression(n):
+    """`((cur - prev).abs().mean() / prev.abs().mean()).cpu().item()` (wan_teacache.py:543) to fp32 precision."""
+    ops = _ops()
+    prev = torch.randn(n, device=DEV)
+    cur = prev + 0.05 * torch.randn(n, device=DEV)
+    want = ((cur - prev).abs().mean() / prev.abs().mean()).cpu().item()
+    got = ops.rel_l1(cur, prev)
+    exact = float((cur.double() - prev.double()).abs().mean() / prev.double().abs().mean())
+    assert abs(got - exact) <= 2e-7 * exact + abs(want - exact), (got, want, exact)  # at least as close to exact as torch's fp32 value
+    assert abs(got - want) <= 1e-6 * want
+
+
 def test_cache_kernels_hunyuan_720p_shape():
     """BASELINE configs[3] (HunyuanVideo 720p x 129 frames: [1, 118800, 3072], all bf16): hit add / residual sub bit-exact."""
     ops = _ops()
