@@ -42,6 +42,25 @@ def table_for_ckpt_dir(ckpt_dir: str, task: str = "t2v"):
     raise KeyError(f"no calibrated mag_ratios table matches ckpt_dir={ckpt_dir!r} (the reference would hit AttributeError later)")
 
 
+def save_json(filename, obj_list):
+    """MagCache4Wan2.1/magcache_generate.py:36-38 (appends ".json" like the reference)."""
+    with open(str(filename) + ".json", "w") as f:
+        json.dump(obj_list, f)
+
+
+def table_from_calibration(ratios, branches=2):
+    """A `mag_ratios` table from a calibration run: the reference prints / dumps `norm_ratio` (one entry per forward from the
+    third call on, :165-175) and its authors paste it behind `[1.0]*2` (`np.array([1.0]*2+[...])`, :910-912; `[1.0]+[...]` for the
+    scalar-state families, magcache_flux.py:459). `ratios`: the list itself or the path of `wan2_1_mag_ratio.json`."""
+    if isinstance(ratios, (str, os.PathLike)):
+        with open(ratios) as f:
+            ratios = json.load(f)
+    arr = np.asarray(ratios, dtype=np.float64)
+    if arr.ndim != 1 or len(arr) == 0 or not np.all(np.isfinite(arr)):
+        raise ValueError("calibration ratios must be a non-empty 1-D list of finite numbers")
+    return np.concatenate([np.ones(branches), arr])
+
+
 def nearest_interp(src, target_length):
     """C-ABI `mc_nearest_interp` (MagCache4Wan2.1/magcache_generate.py:27-34)."""
     import ctypes

@@ -12,6 +12,8 @@ accumulated_steps, residual_cache, mag_ratios`; calibration: `norm_ratio, norm_s
 reference. Everything between the Python call and the returned tensors runs on the CUDA kernels of libmagcache_b200.so;
 there is no eager/PyTorch fallback — a CPU tensor or a missing library raises.
 """
+import os
+
 import torch
 
 from . import ops
@@ -171,6 +173,14 @@ def _calibrate(self, eng):
         print(self.norm_std)
         print("cos_dis")
         print(self.cos_dis)
+        # :191-193 `save_json("wan2_1_mag_ratio", self.norm_ratio)` ...: same file names, in `calibration_dir` (default: the
+        # working directory, like the reference). `config.table_from_calibration` turns the first file into a `mag_ratios` table.
+        out_dir = getattr(self, "calibration_dir", ".")
+        if out_dir is not None:
+            from .config import save_json
+            save_json(os.path.join(out_dir, "wan2_1_mag_ratio"), self.norm_ratio)
+            save_json(os.path.join(out_dir, "wan2_1_mag_std"), self.norm_std)
+            save_json(os.path.join(out_dir, "wan2_1_cos_dis"), self.cos_dis)
     return [out]
 
 
@@ -189,6 +199,9 @@ def init_magcache(model, sample_steps, thresh=0.12, K=2, retention_ratio=0.2, ma
     cls.accumulated_ratio = [1.0, 1.0]
     cls.retention_ratio = retention_ratio
     cls.residual_cache = [None, None]
+    if isinstance(mag_ratios, (str, os.PathLike)):  # a calibration dump (`wan2_1_mag_ratio.json`) instead of a pasted literal
+        from .config import table_from_calibration
+        mag_ratios = table_from_calibration(mag_ratios)
     if mag_ratios is None:
         mag_ratios = tables()[table] if table is not None else table_for_ckpt_dir(ckpt_dir)
     cls.mag_ratios = interp_cfg(mag_ratios, sample_steps)  # :915-919

@@ -79,3 +79,25 @@ def test_handle_classes_do_not_share_state():
     assert type(a) is not type(b) and issubclass(type(a), mc.WanModelHandle)
     type(a).cnt = 5
     assert not hasattr(type(b), "cnt") or type(b).cnt != 5
+
+
+def test_calibration_dump_round_trips_into_a_table(tmp_path):
+    """magcache_generate.py:36-38 / :191-193 file format and the `[1.0]*2 + [...]` table convention (:910-912)."""
+    import json
+
+    from magcache_b200.config import save_json, table_from_calibration
+    ratios = [1.0124, 1.02213, 1.00166, 1.0041, 0.99791, 1.00061]
+    save_json(tmp_path / "wan2_1_mag_ratio", ratios)
+    with open(tmp_path / "wan2_1_mag_ratio.json") as f:
+        assert json.load(f) == ratios
+    t = table_from_calibration(tmp_path / "wan2_1_mag_ratio.json")
+    assert t.tolist() == [1.0, 1.0] + ratios
+    assert table_from_calibration(ratios, branches=1).tolist() == [1.0] + ratios
+    # the shipped 1.3B table is exactly such a dump behind [1.0]*2
+    full = mc.tables()["wan2.1_t2v_1.3b"]
+    assert table_from_calibration(full[2:].tolist()).tolist() == full.tolist()
+    import pytest
+    with pytest.raises(ValueError):
+        table_from_calibration([])
+    with pytest.raises(ValueError):
+        table_from_calibration([1.0, float("nan")])

@@ -270,7 +270,7 @@ def test_magcache_loop_mask_cache_and_outputs():
     assert ours_model.cnt == 0  # wrapped around after num_steps calls
 
 
-def test_calibration_matches_oracle():
+def test_calibration_matches_oracle(tmp_path):
     wan_ref, model = build("tiny")
     steps = 3
     ref_model = copy.deepcopy(model)
@@ -281,6 +281,7 @@ def test_calibration_matches_oracle():
     ours = copy.deepcopy(model).to(DEV)
     ours.__class__ = type("OurCal", (ours.__class__,), {})
     mc.init_magcache_calibration(ours, steps)
+    type(ours).calibration_dir = str(tmp_path)  # where the end-of-video dump goes (reference: the working directory, :191-193)
     lat, ctx, ctx_null = make_inputs(3)
     n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
     sig = wan_ref.flow_sigmas(steps)
@@ -297,6 +298,13 @@ def test_calibration_matches_oracle():
         assert abs(a - b) <= 2e-2 * abs(b), (ours.norm_ratio, ref_model.norm_ratio)
     for a, b in zip(ours.cos_dis, ref_model.cos_dis):
         assert abs(a - b) <= 2e-2 + 0.2 * abs(b), (ours.cos_dis, ref_model.cos_dis)
+    # the dump is the reference's (`save_json("wan2_1_mag_ratio", self.norm_ratio)`) and feeds straight back as a table
+    import json
+    with open(tmp_path / "wan2_1_mag_ratio.json") as f:
+        assert json.load(f) == ours.norm_ratio
+    assert (tmp_path / "wan2_1_mag_std.json").exists() and (tmp_path / "wan2_1_cos_dis.json").exists()
+    mc.init_magcache(ours, steps, thresh=0.12, K=2, retention_ratio=0.34, mag_ratios=str(tmp_path / "wan2_1_mag_ratio.json"))
+    assert type(ours).mag_ratios.tolist() == [1.0, 1.0] + ours.norm_ratio and type(ours).forward is mc.magcache_forward
 
 
 def test_scalar_family_branch_flux_and_hunyuan():
