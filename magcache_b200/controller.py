@@ -65,9 +65,11 @@ class AttrController:
                 st.accumulated_err[i] = float(o.accumulated_err[i])
                 st.accumulated_steps[i] = int(o.accumulated_steps[i])
         else:
-            st.accumulated_ratio[0] = float(o.accumulated_ratio)
-            st.accumulated_err[0] = float(o.accumulated_err)
-            st.accumulated_steps[0] = int(o.accumulated_steps)
+            # FramePack's `initialize_magcache` does not create the accumulators; its forward does at cnt == 0
+            # (magcache_demo_gradio.py:63-74, :253-256) — absent attributes are the fresh state
+            st.accumulated_ratio[0] = float(getattr(o, "accumulated_ratio", 1.0))
+            st.accumulated_err[0] = float(getattr(o, "accumulated_err", 0.0))
+            st.accumulated_steps[0] = int(getattr(o, "accumulated_steps", 0))
             st.accumulated_ratio[1] = 1.0
         return st
 

@@ -101,3 +101,19 @@ def test_calibration_dump_round_trips_into_a_table(tmp_path):
         table_from_calibration([])
     with pytest.raises(ValueError):
         table_from_calibration([1.0, float("nan")])
+
+
+def test_attr_controller_framepack_state_created_on_first_call():
+    """FramePack's `initialize_magcache` (magcache_demo_gradio.py:63-74) sets cnt / num_steps / thresh / K / retention / mag_ratios only;
+    the accumulators appear when the forward first sees cnt == 0 (:253-256). The attribute shim must start from that state."""
+    from magcache_b200.controller import AttrController
+    cfg = mc.PRESETS["framepack-E010K3R02"]
+    o = type("FP", (), {})()
+    o.cnt, o.num_steps, o.magcache_thresh, o.K, o.retention_ratio, o.mag_ratios = 0, cfg.num_steps, cfg.thresh, cfg.K, cfg.retention_ratio, cfg.resolved_ratios()
+    ctrl = AttrController(mc.FAMILIES["framepack"])
+    got = []
+    for _ in range(cfg.num_steps):
+        got.append(int(ctrl.decide(o)))
+        ctrl.advance(o)
+    assert got == cfg.schedule().tolist() and o.cnt == 0
+    assert hasattr(o, "accumulated_ratio") and hasattr(o, "accumulated_err") and hasattr(o, "accumulated_steps")

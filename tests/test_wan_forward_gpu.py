@@ -270,6 +270,34 @@ def test_magcache_loop_mask_cache_and_outputs():
     assert ours_model.cnt == 0  # wrapped around after num_steps calls
 
 
+def test_cuda_graph_replay_equals_eager_with_split_attention(monkeypatch):
+    """Graph mode (default for token-sharded runs, `MC_GRAPHS=1` here) on one GPU: eager warm-up, capture, replay — bit-equal to
+    the eager engine over miss, miss, hit, hit, miss, miss on a 1024-token grid, where the small attention grid takes the split-KV
+    path (its scratch is allocated in the eager call, never during capture)."""
+    import magcache_b200 as mc
+    dims = mc.WanDims(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128, text_len=32)
+    g = torch.Generator().manual_seed(11)
+    lat = torch.randn(16, 4, 32, 32, generator=g).to(DEV)
+    ctxs = [torch.randn(20, 128, generator=g).to(DEV), torch.randn(17, 128, generator=g).to(DEV)]
+    n_tok = 4 * 16 * 16
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MC_GRAPHS", mode)
+        model = mc.WanModelHandle(mc.WanWeights.random(dims, torch.device(DEV), seed=4))
+        assert model._mc_engine.use_graphs == (mode == "1")
+        mc.init_magcache(model, 3, thresh=10.0, K=1, retention_ratio=0.34, mag_ratios=[1.0] * 6)  # miss miss | hit hit | miss miss
+        res = []
+        for video in range(2):
+            for i in range(6):
+                t = torch.tensor([900.0 - 100.0 * (i // 2)], device=DEV)
+                res.append(model([lat * (1.0 + 0.05 * i)], t=t, context=[ctxs[i % 2]], seq_len=n_tok)[0].clone())
+        outs[mode] = res
+        if mode == "1":
+            assert all(isinstance(v, tuple) for v in model._mc_engine._graphs.values()) and len(model._mc_engine._graphs) == 4
+    for a, b in zip(outs["0"], outs["1"]):
+        assert torch.equal(a, b)
+
+
 def test_calibration_matches_oracle(tmp_path):
     wan_ref, model = build("tiny")
     steps = 3
