@@ -268,6 +268,71 @@ def magcache_branch(self, hidden, run_blocks, family, cache_attr):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# The paper-evaluation variant of the Wan forward (the code behind the published Wan2.1 numbers)
+# ------------------------------------------------------------------------------------------------------------------
+def magcache_eval_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
+    r"""eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py:682-817 on the B200 kernels, state under THAT script's attribute
+    names (`t, num_steps, magcache_thresh, magcache_K, ratio, accumulated_sim, accumulated_err, accumulated_steps, residual_cache,
+    skip_steps, pre_con`). Differences from `magcache_forward`, all reproduced: `<=` threshold compare, table indexed `ratio[t-10]`,
+    retention fixed at `int(num_steps*0.2)`, residuals kept from call 10 on (`cache_time`) in a `[2, B, N, D, 1]` tensor — the
+    depth-1 `push_tensor_roll` FIFO (:67-85, :796-799) is the engine's two residual slots viewed in place, no roll, no copy —
+    and the conditional output of each step remembered in `pre_con` (:804-805)."""
+    import ctypes
+
+    from . import _lib
+    from .config import FAMILIES
+    from .controller import make_ctrl_config
+    eng = _stage(self, x, t, context, seq_len, clip_fea, y)
+    cache_time = 10                                  # :771
+    ratio = self.ratio
+    cc = self.__dict__.get("_mc_eval_cfg")
+    key = (id(ratio), len(ratio), self.num_steps, float(self.magcache_thresh), int(self.magcache_K))
+    if cc is None or cc[0] != key:
+        cc = (key, make_ctrl_config(self.num_steps, self.magcache_thresh, self.magcache_K, 0.2, ratio, **FAMILIES["wan2.1-eval"]))
+        object.__setattr__(self, "_mc_eval_cfg", cc)
+    cfg = cc[1]
+    st = _lib.CtrlState()
+    st.cnt = int(self.t)
+    for i in range(2):
+        st.accumulated_ratio[i], st.accumulated_err[i], st.accumulated_steps[i] = float(self.accumulated_sim[i]), float(self.accumulated_err[i]), int(self.accumulated_steps[i])
+    skip = ctypes.c_int32()
+    _lib.check(_lib.lib.mc_ctrl_decide(ctypes.byref(cfg), ctypes.byref(st), ctypes.byref(skip)))  # :774-786
+    for i in range(2):  # the reference mutates the lists in place
+        self.accumulated_sim[i], self.accumulated_err[i], self.accumulated_steps[i] = st.accumulated_ratio[i], st.accumulated_err[i], st.accumulated_steps[i]
+    slot = self.t % 2
+    if skip.value:
+        self.skip_steps += 1
+        print(f"skip time {self.t}, cur_scale: {ratio[self.t - 10]}, acc_sim: {self.accumulated_sim[slot]}, total_steps: {self.skip_steps}")  # :790
+    out = eng.forward("hit" if skip.value else "miss", slot)
+    if self.t >= cache_time:                         # :796-799
+        self.residual_cache = eng.res_buf.view(2, 1, *eng.res_buf.shape[1:], 1)
+    if self.t % 2 == 0:
+        self.pre_con = [out]                         # :804-805
+    self.t += 1                                      # :807-815
+    if self.t >= self.num_steps:
+        self.t = 0
+        self.skip_steps = 0
+        self.accumulated_sim = [1.0, 1.0]
+        self.accumulated_steps = [0, 0]
+        self.accumulated_err = [0, 0]
+    return [out]
+
+
+def init_magcache_eval(model, sample_steps, thresh=0.12, K=2, ratio=None):
+    """The installation block of wan_magcache.py:1129-1150 as a helper ("slow" = 0.12/K2, "fast" = 0.12/K4, wan_eval.sh:30-31,66-67)."""
+    import numpy as np
+    cls = model.__class__
+    cls.forward = magcache_eval_forward
+    cls.magcache_thresh, cls.magcache_K = thresh, K
+    cls.t, cls.accumulated_err, cls.skip_steps, cls.pre_con = 0, [0, 0], 0, None
+    cls.num_steps = sample_steps * 2
+    cls.ratio = np.asarray(tables()["wan2.1_eval"] if ratio is None else ratio, dtype=np.float64)
+    cls.residual_cache = None
+    cls.accumulated_sim, cls.accumulated_steps = [1, 1], [0, 0]
+    return model
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # TeaCache comparator (the baseline of every published MagCache table) on the same engine
 # ------------------------------------------------------------------------------------------------------------------
 # coefficients of eval/magcache/experiments/Wan2.1_EVAL/wan_teacache.py:913-926 (t2v) — keyed by (use_ret_steps, model size)

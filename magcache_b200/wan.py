@@ -304,7 +304,8 @@ class WanEngine:
             self.cvt_img = torch.zeros(D, (cl + 7) // 8 * 8, **bf)  # V^T of the image tokens; row pitch padded to 16 bytes
             self.att_img = torch.empty(n, D, **bf)
         # engine-owned residual cache storage (one slot per CFG branch) and staged inputs: fixed addresses for graph replay
-        self.res = [torch.empty(n, D, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.res_buf = torch.empty(2, n, D, dtype=torch.float32, device=dev)  # one buffer: the paper-eval forward exposes it whole
+        self.res = [self.res_buf[0], self.res_buf[1]]
         self.res_valid = [False, False]
         self.s_t = torch.zeros(1, dtype=torch.float64, device=dev)
         self.s_lat = None

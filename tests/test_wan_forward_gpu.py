@@ -270,6 +270,44 @@ def test_magcache_loop_mask_cache_and_outputs():
     assert ours_model.cnt == 0  # wrapped around after num_steps calls
 
 
+def test_eval_variant_loop_vs_oracle():
+    """`magcache_eval_forward` (eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py:682-817, the code behind the paper's Wan2.1
+    rows) for one whole 50-step video: identical hit/miss sequence (62 of 100 skipped at 0.12 / K4), float64 accumulators bit-equal,
+    outputs and the `[2, B, N, D, 1]` residual tensor within the usual tolerance of the oracle's rolled FIFO."""
+    import magcache_b200 as mc
+    wan_ref, model = build("tiny")
+    steps = 50
+    ref_model = copy.deepcopy(model)
+    ref_model.__class__ = type("RefEval", (ref_model.__class__,), {})
+    wan_ref.install_magcache_eval(type(ref_model), mc.tables()["wan2.1_eval"], steps, 0.12, 4)
+    ours = copy.deepcopy(model).to(DEV)
+    ours.__class__ = type("OurEval", (ours.__class__,), {})
+    mc.init_magcache_eval(ours, steps, thresh=0.12, K=4)
+    lat, ctx, ctx_null = make_inputs(8, grid=(2, 8, 12))
+    n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
+    sig = wan_ref.flow_sigmas(steps)
+    skips = 0
+    with torch.no_grad():
+        for i in range(steps):
+            t = torch.tensor([float(sig[i] * 1000)])
+            for c in (ctx, ctx_null):
+                t_before = ours.t
+                ref = ref_model([lat], t=t, context=[c], seq_len=n_tok)[0]
+                out = ours([lat.to(DEV)], t=t.to(DEV), context=[c.to(DEV)], seq_len=n_tok)[0].cpu()
+                skips += int(ref_model.last_skip)
+                assert rel_l2(out, ref) <= 2e-2, (i, rel_l2(out, ref))
+                assert ours.t == ref_model.t and ours.skip_steps == ref_model.skip_steps
+                for attr in ("accumulated_sim", "accumulated_err", "accumulated_steps"):
+                    assert [float(v) for v in getattr(ours, attr)] == [float(v) for v in getattr(ref_model, attr)], (i, attr)
+                if t_before >= 10:
+                    slot = t_before % 2
+                    assert tuple(ours.residual_cache.shape) == tuple(ref_model.residual_cache.shape) == (2, 1, n_tok, 256, 1)
+                    assert rel_l2(ours.residual_cache[slot][..., -1].cpu(), ref_model.residual_cache[slot][..., -1]) <= 3e-2
+                else:
+                    assert ours.residual_cache is None and ref_model.residual_cache is None
+    assert skips == 62 and ours.t == 0
+
+
 def test_cuda_graph_replay_equals_eager_with_split_attention(monkeypatch):
     """Graph mode (default for token-sharded runs, `MC_GRAPHS=1` here) on one GPU: eager warm-up, capture, replay — bit-equal to
     the eager engine over miss, miss, hit, hit, miss, miss on a 1024-token grid, where the small attention grid takes the split-KV
