@@ -180,7 +180,8 @@ class MagCacheConfig:
         import ctypes
 
         from .controller import make_ctrl_config
-        cfg = make_ctrl_config(self.num_steps, self.thresh, self.K, self.retention_ratio, self.resolved_ratios(), **self.ctrl_kwargs())
+        R = 0.2 if self.family == "wan2.1-eval" else self.retention_ratio  # hard-coded upstream: `skip_time = int(self.num_steps*0.2)`, :772
+        cfg = make_ctrl_config(self.num_steps, self.thresh, self.K, R, self.resolved_ratios(), **self.ctrl_kwargs())
         calls = self.num_steps if calls is None else calls
         st = _lib.CtrlState()
         st.accumulated_ratio[0] = st.accumulated_ratio[1] = 1.0
