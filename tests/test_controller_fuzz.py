@@ -155,3 +155,53 @@ def test_magcacheconfig_schedule_equals_restatement_for_every_preset():
             want = ref.mask(cfg.num_steps)
         assert cfg.schedule().tolist() == want, name
     assert isinstance(MagCacheConfig("hunyuan", table="hunyuan_544p").schedule(), np.ndarray)
+
+
+# ---------------------------------------------------------------------------------------------- nearest_interp / TeaCache fuzz
+@settings(max_examples=300, deadline=None)
+@given(L_=hs.integers(1, 200), T_=hs.integers(1, 200), seed=hs.integers(0, 2 ** 31 - 1))
+def test_nearest_interp_equals_numpy_expression(L_, T_, seed):
+    """`np.round(np.arange(T) * (L-1)/(T-1)).astype(int)` (round half to even) for every (L, T), incl. the linspace form of Qwen-Image."""
+    from oracle.controller_ref import nearest_interp as ref_interp
+    src = np.random.default_rng(seed).standard_normal(L_)
+    assert nearest_interp(src, T_).tolist() == ref_interp(src, T_).tolist()
+    out = np.empty(T_)
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.check(L.lib.mc_nearest_interp_linspace(np.ascontiguousarray(src).ctypes.data_as(dp), L_, out.ctypes.data_as(dp), T_))
+    want = src if L_ == T_ else src[np.round(np.linspace(0, L_ - 1, T_)).astype(int)]  # MagCache4QwenImage/magcache_generate.py:14-21
+    assert out.tolist() == np.asarray(want).tolist()
+
+
+@settings(max_examples=300, deadline=None)
+@given(steps=hs.integers(3, 40), seed=hs.integers(0, 2 ** 31 - 1), thresh=hs.sampled_from([0.02, 0.08, 0.2, 0.5]), ret=hs.integers(0, 10),
+       cut=hs.integers(0, 6), ncoef=hs.integers(1, 8))
+def test_teacache_controller_equals_numpy_poly1d_restatement(steps, seed, thresh, ret, cut, ncoef):
+    """wan_teacache.py:535-564 restated with np.poly1d on random coefficients / distances."""
+    rng = np.random.default_rng(seed)
+    n = 2 * steps
+    coef = (rng.standard_normal(ncoef) * np.logspace(ncoef - 1, 0, ncoef)).tolist()
+    cfg = L.TeaConfig()
+    cfg.num_steps, cfg.ret_steps, cfg.cutoff_steps, cfg.n_coef, cfg.thresh = n, ret, n - cut, ncoef, thresh
+    for i, c in enumerate(coef):
+        cfg.coef[i] = c
+    st = L.TeaState()
+    calc = ctypes.c_int32()
+    acc, cnt = [0, 0], 0
+    poly = np.poly1d(coef)
+    for _ in range(2 * n + 3):
+        d = float(abs(rng.standard_normal()) * 0.1)
+        i = cnt % 2
+        if cnt < ret or cnt >= n - cut:
+            want, acc[i] = True, 0
+        else:
+            acc[i] += poly(d)
+            if acc[i] < thresh:
+                want = False
+            else:
+                want, acc[i] = True, 0
+        L.check(L.lib.mc_tea_decide(ctypes.byref(cfg), ctypes.byref(st), d, ctypes.byref(calc)))
+        assert bool(calc.value) == want
+        assert [st.accumulated[0], st.accumulated[1]] == [float(acc[0]), float(acc[1])]
+        L.check(L.lib.mc_tea_advance(ctypes.byref(cfg), ctypes.byref(st)))
+        cnt = 0 if cnt + 1 >= n else cnt + 1
+        assert st.cnt == cnt
