@@ -103,6 +103,20 @@ int32_t mc_ctrl_mask(const mc_ctrl_config* cfg, int32_t calls, uint8_t* mask);
 /* Reject configurations the reference would crash on (Appendix A quirk 4: cnt 0 eligible with an empty cache). */
 int32_t mc_ctrl_validate(const mc_ctrl_config* cfg);
 
+/* Handle form of the same controller (create / step / reset / destroy) for hosts that prefer an opaque object to the
+ * two structs: the handle owns a COPY of the config and of the table and the state of one model instance.
+ *   mc_ctrl_create  validates (mc_ctrl_validate) and returns NULL + mc_last_error() on a bad configuration;
+ *   mc_ctrl_step    = decide + advance for the call the handle's own counter points at (magcache_generate.py:277-292 + :306-311);
+ *                     *cnt_out (optional) receives the counter AFTER the call;
+ *   mc_ctrl_reset   = what `__class__.cnt = 0` between prompts intends (magcache_flux.py:478): cnt 0, fresh accumulators;
+ *   mc_ctrl_state_of exposes the state struct (borrowed pointer, valid until destroy). */
+typedef struct mc_ctrl mc_ctrl;
+mc_ctrl* mc_ctrl_create(const mc_ctrl_config* cfg, int32_t initial_accumulated_steps);
+int32_t mc_ctrl_step(mc_ctrl* h, int32_t* skip, int32_t* cnt_out);
+int32_t mc_ctrl_reset(mc_ctrl* h);
+const mc_ctrl_state* mc_ctrl_state_of(const mc_ctrl* h);
+void mc_ctrl_destroy(mc_ctrl* h);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Residual-cache kernels (HBM-bound)
  * ---------------------------------------------------------------------------------------------------------- */

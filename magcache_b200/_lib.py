@@ -58,6 +58,8 @@ SIGNATURES = {
     "mc_ctrl_advance": [POINTER(CtrlConfig), POINTER(CtrlState)],
     "mc_ctrl_mask": [POINTER(CtrlConfig), c_int32, POINTER(c_uint8)],
     "mc_ctrl_validate": [POINTER(CtrlConfig)],
+    "mc_ctrl_step": [c_void_p, POINTER(c_int32), POINTER(c_int32)],
+    "mc_ctrl_reset": [c_void_p],
     "mc_tea_needs_distance": [POINTER(TeaConfig), POINTER(TeaState), POINTER(c_int32)],
     "mc_tea_decide": [POINTER(TeaConfig), POINTER(TeaState), c_double, POINTER(c_int32)],
     "mc_tea_advance": [POINTER(TeaConfig), POINTER(TeaState)],
@@ -98,6 +100,12 @@ for _name, _args in SIGNATURES.items():
     _fn.restype = c_int32
     _fn.argtypes = _args
 
+
+# entry points that do not return an int32 status
+lib.mc_ctrl_create.restype, lib.mc_ctrl_create.argtypes = c_void_p, [POINTER(CtrlConfig), c_int32]
+lib.mc_ctrl_state_of.restype, lib.mc_ctrl_state_of.argtypes = POINTER(CtrlState), [c_void_p]
+lib.mc_ctrl_destroy.restype, lib.mc_ctrl_destroy.argtypes = None, [c_void_p]
+OTHER_EXPORTS = ("mc_last_error", "mc_ctrl_create", "mc_ctrl_state_of", "mc_ctrl_destroy")
 
 if lib.mc_abi_version() != ABI_VERSION:
     raise ImportError(f"{LIB_PATH} has ABI version {lib.mc_abi_version()}, this package needs {ABI_VERSION}: rebuild with "

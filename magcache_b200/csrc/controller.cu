@@ -230,6 +230,55 @@ int32_t mc_ctrl_mask(const mc_ctrl_config* cfg, int32_t calls, uint8_t* mask) {
   return MC_OK;
 }
 
+// ---- handle form -----------------------------------------------------------------------------------------------
+struct mc_ctrl {
+  mc_ctrl_config cfg;
+  std::vector<double> table;
+  mc_ctrl_state st;
+  int32_t initial_steps;
+};
+
+static void ctrl_fresh(mc_ctrl* h) {
+  std::memset(&h->st, 0, sizeof(h->st));
+  h->st.accumulated_ratio[0] = h->st.accumulated_ratio[1] = 1.0;
+  h->st.accumulated_steps[0] = h->st.accumulated_steps[1] = h->initial_steps;  // OmniGen2: 3 (magcache_utils.py:44)
+}
+
+mc_ctrl* mc_ctrl_create(const mc_ctrl_config* cfg, int32_t initial_accumulated_steps) {
+  if (mc_ctrl_validate(cfg) != MC_OK) return nullptr;
+  if (initial_accumulated_steps < 0) {
+    mc::set_error("mc_ctrl_create: initial_accumulated_steps=%d must be >= 0", initial_accumulated_steps);
+    return nullptr;
+  }
+  mc_ctrl* h = new mc_ctrl();
+  h->cfg = *cfg;
+  h->table.assign(cfg->mag_ratios, cfg->mag_ratios + (cfg->num_steps - cfg->table_offset));
+  h->cfg.mag_ratios = h->table.data();
+  h->initial_steps = initial_accumulated_steps;
+  ctrl_fresh(h);
+  return h;
+}
+
+int32_t mc_ctrl_step(mc_ctrl* h, int32_t* skip, int32_t* cnt_out) {
+  MC_CHECK_ARG(h && skip, "mc_ctrl_step: null pointer");
+  const int32_t d = mc::decide(&h->cfg, &h->st);
+  if (d < 0) return d;
+  *skip = d;
+  mc::advance(&h->cfg, &h->st);
+  if (cnt_out) *cnt_out = h->st.cnt;
+  return MC_OK;
+}
+
+int32_t mc_ctrl_reset(mc_ctrl* h) {
+  MC_CHECK_ARG(h, "mc_ctrl_reset: null handle");
+  ctrl_fresh(h);
+  return MC_OK;
+}
+
+const mc_ctrl_state* mc_ctrl_state_of(const mc_ctrl* h) { return h ? &h->st : nullptr; }
+
+void mc_ctrl_destroy(mc_ctrl* h) { delete h; }
+
 // ---- TeaCache comparator: eval/magcache/experiments/Wan2.1_EVAL/wan_teacache.py:535-564 ------------------------------------
 static int32_t tea_check(const mc_tea_config* c, const mc_tea_state* st) {
   MC_CHECK_ARG(c && st, "mc_tea: null pointer");

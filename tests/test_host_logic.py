@@ -161,3 +161,40 @@ def test_oracle_c_restatement_matches(L):
         mask = (ctypes.c_uint8 * case["calls"])()
         ref.ref_ctrl_mask(fam[case["family"]], arr, n, ctypes.c_double(case["thresh"]), case["K"], ctypes.c_double(case["R"]), case["calls"], mask)
         assert "".join(str(int(v)) for v in mask) == case["mask"]
+
+
+def test_handle_form_equals_the_struct_form(L):
+    """mc_ctrl_create / step / reset / destroy against the golden schedules, plus table ownership and reset."""
+    for case in [m for m in MASKS if m["steps"] in (50, 28)][:24]:
+        t = TABLES[case["table"]]["values"]
+        steps = case["steps"]
+        if case["family"] == "wan2.1":
+            n = steps * 2
+            from magcache_b200.config import interp_cfg
+            ratios = list(interp_cfg(np.array(t), steps))
+        else:
+            n = steps
+            ratios = list(t)
+        cfg = _cfg(L, case["family"], ratios, n, case["thresh"], case["K"], case["R"])
+        h = L.lib.mc_ctrl_create(ctypes.byref(cfg), 0)
+        assert h
+        cfg.mag_ratios = None  # the handle owns a copy of the table
+        skip, cnt = ctypes.c_int32(), ctypes.c_int32()
+        got = []
+        for _ in range(case["calls"]):
+            L.check(L.lib.mc_ctrl_step(h, ctypes.byref(skip), ctypes.byref(cnt)))
+            got.append(str(skip.value))
+        assert "".join(got) == case["mask"]
+        st = L.lib.mc_ctrl_state_of(h).contents
+        assert st.cnt == cnt.value == case["final"]["cnt"]
+        L.check(L.lib.mc_ctrl_reset(h))
+        assert L.lib.mc_ctrl_state_of(h).contents.cnt == 0 and L.lib.mc_ctrl_state_of(h).contents.accumulated_ratio[0] == 1.0
+        again = []
+        for _ in range(n):
+            L.check(L.lib.mc_ctrl_step(h, ctypes.byref(skip), None))
+            again.append(str(skip.value))
+        assert "".join(again) == case["mask"][:n]
+        L.lib.mc_ctrl_destroy(h)
+    bad = _cfg(L, "wan2.1", [1.0] * 4, 4, 0.1, 2, 0.0)  # retention 0: the first call would hit an empty cache
+    assert not L.lib.mc_ctrl_create(ctypes.byref(bad), 0) and b"mc_ctrl_validate" in L.lib.mc_last_error()
+    L.lib.mc_ctrl_destroy(None)
