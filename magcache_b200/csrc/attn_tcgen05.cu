@@ -51,7 +51,9 @@ struct AttnParams {
 // Tried, validated and dropped in round 1 because they were slower (profiles/r01_attention_experiments.md; sources in the git
 // history): speculative exponentials, cross-tile software pipelining, staggered CTA start, 256-row CTAs with 128-wide KV
 // tiles, split-row softmax with 8 softmax warps, 128-wide KV tiles with a single-buffered S.
-template <int VARIANT>
+constexpr int kDefaultPoly = 0;  // see profiles/r01_attention_experiments.md ("exponentials on the FMA pipe")
+
+template <int VARIANT, int POLY>
 __global__ void __launch_bounds__(kAttnThreads, 2)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
@@ -253,10 +255,21 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
           float a0, a1, b0, b1;
           ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1])), scale2, negm2), a0, a1);
           ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3])), scale2, negm2), b0, b1);
-          a0 = ptx::ex2_approx(a0);
-          a1 = ptx::ex2_approx(a1);
-          b0 = ptx::ex2_approx(b0);
-          b1 = ptx::ex2_approx(b1);
+          // POLY / 4 of the exponentials are evaluated on the FMA pipe (ptx::ex2_emul_pair) to take them off the MUFU, which
+          // this loop otherwise keeps as busy as the tensor pipe (profiles/r01_ncu_attn.md): 1 = every other (b0, b1) pair,
+          // 2 = every (b0, b1) pair, 3 = those plus every other (a0, a1) pair.
+          if (POLY >= 3 && (c & 4)) {
+            ptx::ex2_emul_pair(a0, a1);
+          } else {
+            a0 = ptx::ex2_approx(a0);
+            a1 = ptx::ex2_approx(a1);
+          }
+          if (POLY >= 2 || (POLY == 1 && (c & 4))) {
+            ptx::ex2_emul_pair(b0, b1);
+          } else {
+            b0 = ptx::ex2_approx(b0);
+            b1 = ptx::ex2_approx(b1);
+          }
           sum2a = ptx::add_f32x2(sum2a, ptx::pack_f32x2(a0, a1));
           sum2b = ptx::add_f32x2(sum2b, ptx::pack_f32x2(b0, b1));
           packed[h * 16 + (c >> 1)] = pack_bf16x2(a0, a1);
@@ -402,8 +415,11 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
   if (variant < 0) {
     const char* ev = getenv("MC_ATTN_VARIANT");
     const int v = (ev && ev[0] == '0') ? 0 : 1;
-    cudaError_t e = cudaFuncSetAttribute(mc::attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    cudaError_t e = cudaFuncSetAttribute(mc::attn_fwd_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
     if (e != cudaSuccess) return mc::cuda_fail(e, "cudaFuncSetAttribute(attn smem)");
     variant = v;
   }
@@ -413,6 +429,10 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
   const int q_tiles = (Lq + mc::kBQ - 1) / mc::kBQ;
   const int total_tiles = (Lk + mc::kBKV - 1) / mc::kBKV;
   const double waves = static_cast<double>(q_tiles) * heads / (2.0 * mc::num_sms());
+  // MC_ATTN_POLY=k (0..3): k/4 of the softmax exponentials on the FMA pipe instead of the MUFU. Read per call (tools/bench_poly.py).
+  const char* ep = getenv("MC_ATTN_POLY");
+  int poly = ep ? atoi(ep) : mc::kDefaultPoly;
+  if (poly < 0 || poly > 3) poly = mc::kDefaultPoly;
   // MC_ATTN_SPLITS=n forces n splits (1 = never split); unset/0 = choose by wave fill. Read per call (tools/bench_split.py).
   const char* es = getenv("MC_ATTN_SPLITS");
   int forced_splits = es ? atoi(es) : 0;
@@ -443,9 +463,14 @@ extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_
   dim3 grid(q_tiles, heads, splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (variant == 1)
-    mc::attn_fwd_kernel<1><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
+    switch (poly) {
+      case 1: mc::attn_fwd_kernel<1, 1><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p); break;
+      case 2: mc::attn_fwd_kernel<1, 2><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p); break;
+      case 3: mc::attn_fwd_kernel<1, 3><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p); break;
+      default: mc::attn_fwd_kernel<1, 0><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p); break;
+    }
   else
-    mc::attn_fwd_kernel<0><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
+    mc::attn_fwd_kernel<0, 0><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
   MC_CHECK_LAUNCH("attn_fwd_kernel launch");
   if (splits > 1) {
     const int64_t total = static_cast<int64_t>(Lq) * heads * (mc::kHD / 8);
