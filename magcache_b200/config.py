@@ -2,7 +2,7 @@
 (SURVEY.md Appendix A), the calibrated `mag_ratios` tables, and the presets the reference's READMEs quote."""
 import json
 import os
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Sequence
 
 import numpy as np

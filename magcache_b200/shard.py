@@ -13,7 +13,6 @@ CUDA tensors with NCCL in the engine).
 """
 from dataclasses import dataclass
 
-import torch
 import torch.distributed as dist
 
 

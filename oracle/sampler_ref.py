@@ -10,7 +10,6 @@ is not pinned by the reference (README: "clone the repo"). What follows restates
 on the flow-matching parameterisation alpha_t = 1 - sigma_t the Wan schedulers use; the reference's own call site fixes only
 the call order (cond, uncond, combine, step) and the solver names.
 """
-import math
 
 import torch
 
