@@ -91,7 +91,7 @@ def _worker(rank, world, initfile, results):
 
 def test_sharded_self_attention_gather_and_reductions_world2():
     with tempfile.TemporaryDirectory() as d:
-        mgr = mp.Manager()
+        mgr = mp.get_context("spawn").Manager()  # fork() from a multi-threaded pytest process can deadlock
         results = mgr.dict()
         mp.spawn(_worker, args=(2, os.path.join(d, "init"), results), nprocs=2, join=True)
         assert set(results.keys()) == {0, 1}
