@@ -214,6 +214,15 @@ int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t col
 int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, const float* w, float eps,
                         const float* cos_sin, int32_t head_dim, void* stream);
 
+/* MMDiT (FLUX) attention front end [EXT diffusers FluxAttnProcessor2_0, called from MagCache4FLUX/magcache_flux.py:361-366, :413-418]:
+ * per-HEAD RMSNorm (head_dim 128; y = bf16(bf16(x * rsqrt(mean x^2 + eps)) * w), w fp32 copies of the bf16 weights [128]) followed
+ * by `apply_rotary_emb` on consecutive (real, imag) pairs, in place on x bf16 [rows, heads*128] (row stride ld).
+ * cos_sin: fp32 [rows, 128] interleaved (cos, sin) per pair, or NULL. */
+int32_t mc_rmsnorm_head_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t heads, const float* w, float eps, const float* cos_sin,
+                             void* stream);
+/* y = silu(x), bf16 -> bf16 (fp32 inside): `self.silu(emb)` of AdaLayerNormZero / ...Single / ...Continuous. */
+int32_t mc_silu_bf16(const void* x, void* y, int64_t n, void* stream);
+
 /* bf16 GEMM on tcgen05/TMEM, TMA-fed:  acc[m,n] = sum_k A[m,k] * B[n,k]   (A: [M,K] row-major, B: [N,K] row-major).
  * lda/ldb/ldo in elements; K % 8 == 0, lda % 8 == 0, ldb % 8 == 0, 16-byte aligned bases. */
 #define MC_EPI_BIAS_BF16 0        /* out_bf16[m,n] = bf16(acc + bias[n])                              nn.Linear under autocast */
@@ -222,6 +231,9 @@ int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, co
 #define MC_EPI_ROWBIAS_BF16 3     /* out_bf16[m,n] = bf16(acc + bias[m])                               V^T = Wv * h^T + bv */
 #define MC_EPI_BIAS_F32 4         /* out_f32[m,n] = acc + bias[n]                                                           */
 #define MC_EPI_BIAS_GELU_ERF_BF16 5 /* out_bf16 = bf16(gelu_erf(float(bf16(acc + bias[n]))))          img_emb Linear + nn.GELU() (i2v) */
+#define MC_EPI_BIAS_GATE_RESID_BF16 6 /* x_bf16[m,n] = bf16(x + bf16(gate[n] * bf16(acc + bias[n])))  all-bf16 streams (FLUX MMDiT:
+                                         `hidden_states = hidden_states + gate.unsqueeze(1) * attn_output`), in place on `out` */
+#define MC_EPI_BIAS_SILU_BF16 7   /* out_bf16 = bf16(silu(float(bf16(acc + bias[n]))))                 TimestepEmbedding linear_1 + SiLU */
 int32_t mc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
                      const float* bias, int32_t epilogue, void* out, int64_t ldo, const float* gate, void* stream);
 

@@ -66,6 +66,10 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
 }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }  // nn.SiLU in fp32
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
 // torch.nn.GELU() (exact, erf form) in fp32: 0.5*x*(1+erf(x/sqrt(2))) — `img_emb` of the i2v models
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

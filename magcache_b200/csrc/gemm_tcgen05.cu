@@ -84,6 +84,11 @@ __device__ __forceinline__ void epilogue_patch(const GemmParams& p, const float*
     if (c0 < p.N) b0 = p.bias[c0];
     if (c0 + 1 < p.N) b1 = p.bias[c0 + 1];
   }
+  float g0 = 1.f, g1 = 1.f;
+  if (EPI == MC_EPI_BIAS_GATE_RESID_BF16 && p.gate) {
+    if (c0 < p.N) g0 = p.gate[c0];
+    if (c0 + 1 < p.N) g1 = p.gate[c0 + 1];
+  }
   __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(row0 + half) * p.ldo + c0;
   const float* sbase = stage + half * kStagePad + cp;
   const float* rbias = (EPI == MC_EPI_ROWBIAS_BF16 && p.bias) ? p.bias + row0 + half : nullptr;
@@ -109,6 +114,15 @@ __device__ __forceinline__ void epilogue_patch(const GemmParams& p, const float*
       if (EPI == MC_EPI_BIAS_GELU_ERF_BF16) {
         v0 = gelu_erf(round_bf16(v0));
         v1 = gelu_erf(round_bf16(v1));
+      }
+      if (EPI == MC_EPI_BIAS_SILU_BF16) {
+        v0 = silu_f(round_bf16(v0));
+        v1 = silu_f(round_bf16(v1));
+      }
+      if (EPI == MC_EPI_BIAS_GATE_RESID_BF16) {  // x = x + g * y with every tensor bf16 (MMDiT streams): three roundings
+        const uint32_t old = *reinterpret_cast<const uint32_t*>(obase + static_cast<int64_t>(2 * i) * p.ldo);
+        v0 = bf16_lo(old) + round_bf16(g0 * round_bf16(v0));
+        v1 = bf16_hi(old) + round_bf16(g1 * round_bf16(v1));
       }
       w[i] = pack_bf16x2(v0, v1);
     }
@@ -138,7 +152,15 @@ __device__ __forceinline__ void epilogue_patch(const GemmParams& p, const float*
       v0 = gelu_erf(round_bf16(v0));
       v1 = gelu_erf(round_bf16(v1));
     }
+    if (EPI == MC_EPI_BIAS_SILU_BF16) {
+      v0 = silu_f(round_bf16(v0));
+      v1 = silu_f(round_bf16(v1));
+    }
     __nv_bfloat16* o = obase + static_cast<int64_t>(2 * i) * p.ldo;
+    if (EPI == MC_EPI_BIAS_GATE_RESID_BF16) {
+      if (c0 < p.N) v0 = __bfloat162float(o[0]) + round_bf16(g0 * round_bf16(v0));
+      if (c0 + 1 < p.N) v1 = __bfloat162float(o[1]) + round_bf16(g1 * round_bf16(v1));
+    }
     if (pair_ok) {
       *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
     } else {
@@ -304,6 +326,8 @@ extern "C" int32_t mc_gemm_bf16(const void* A, int64_t lda, const void* B, int64
     case MC_EPI_ROWBIAS_BF16: return mc::launch_gemm<MC_EPI_ROWBIAS_BF16>(ta, tb, p, s);
     case MC_EPI_BIAS_F32: return mc::launch_gemm<MC_EPI_BIAS_F32>(ta, tb, p, s);
     case MC_EPI_BIAS_GELU_ERF_BF16: return mc::launch_gemm<MC_EPI_BIAS_GELU_ERF_BF16>(ta, tb, p, s);
+    case MC_EPI_BIAS_GATE_RESID_BF16: return mc::launch_gemm<MC_EPI_BIAS_GATE_RESID_BF16>(ta, tb, p, s);
+    case MC_EPI_BIAS_SILU_BF16: return mc::launch_gemm<MC_EPI_BIAS_SILU_BF16>(ta, tb, p, s);
     default:
       mc::set_error("mc_gemm_bf16: unknown epilogue %d", epilogue);
       return MC_ERR_INVALID;

@@ -161,6 +161,59 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(__nv_bfloat16* __rest
   }
 }
 
+// ---- per-HEAD RMSNorm (head_dim 128, bf16 weight semantics) + RoPE, in place on bf16: the q / k normalisation of the MMDiT
+// attention (diffusers `RMSNorm(head_dim)` on [B, H, L, 128] followed by `apply_rotary_emb`, upstream of
+// MagCache4FLUX/magcache_flux.py:361-366). 16 threads per (token, head), 8 elements each.
+//   y = bf16( bf16(x * rsqrt(mean(x^2) + eps)) * w )      (variance in fp32; the product is cast to the bf16 weight dtype first)
+//   RoPE in fp32 on consecutive (real, imag) pairs, result rounded to bf16
+__global__ void __launch_bounds__(256) rmsnorm_head_rope_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int64_t rows, int heads,
+                                                                const float* __restrict__ w, float eps,
+                                                                const float* __restrict__ cos_sin) {
+  const int sub = threadIdx.x & 15;
+  const int64_t n_items = rows * heads;
+  // a warp handles two items per trip; the trip count is the same for all 32 lanes (full-mask shuffles below)
+  const int64_t warps_total = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t item0 = ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * 2; item0 < n_items; item0 += warps_total * 2) {
+    const int64_t item = item0 + ((threadIdx.x >> 4) & 1);
+    const bool live = item < n_items;  // all 16 lanes of a segment share `item`
+    const int64_t row = live ? item / heads : 0;
+    const int head = live ? static_cast<int>(item % heads) : 0;
+    __nv_bfloat16* px = x + row * ld + head * 128 + sub * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) unpack_bf16x8(*reinterpret_cast<const uint4*>(px), v);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q = fmaf(v[j], v[j], q);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);  // stays inside the 16-lane segment
+    if (!live) continue;
+    const float r = rsqrtf(q * (1.0f / 128.0f) + eps);
+    float wv[8], o[8];
+    load_param8(w + sub * 8, wv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = round_bf16(round_bf16(v[j] * r) * wv[j]);
+    if (cos_sin != nullptr) {
+      float cs[8];
+      ptx::ld_nc_v8_f32(cos_sin + row * 128 + sub * 8, cs);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float re = o[2 * p], im = o[2 * p + 1], c = cs[2 * p], sn = cs[2 * p + 1];
+        o[2 * p] = __fsub_rn(__fmul_rn(re, c), __fmul_rn(im, sn));
+        o[2 * p + 1] = __fadd_rn(__fmul_rn(im, c), __fmul_rn(re, sn));
+      }
+    }
+    *reinterpret_cast<uint4*>(px) = pack_bf16x8(o);
+  }
+}
+
+// ---- y = silu(x) on a bf16 vector (the `self.silu(emb)` in front of every AdaLayerNorm linear) ------------------------------
+__global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = __bfloat162float(x[i]);
+    y[i] = __float2bfloat16_rn(v / (1.0f + expf(-v)));
+  }
+}
+
 // ---- patchify: latent fp32 [C,F,H,W] -> tokens bf16 [F*Hp*Wp, C*4] ----------------------------------------------
 __global__ void patchify_kernel(const float* __restrict__ lat, int C, int F, int H, int W, __nv_bfloat16* __restrict__ tok) {
   const int Hp = H >> 1, Wp = W >> 1;
@@ -438,6 +491,30 @@ int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, co
   else MC_RMS(128);
 #undef MC_RMS
   MC_CHECK_LAUNCH("rmsnorm_rope_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_rmsnorm_head_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t heads, const float* w, float eps, const float* cos_sin,
+                             void* stream) {
+  MC_CHECK_ARG(x_bf16 && w, "mc_rmsnorm_head_rope: null pointer");
+  MC_CHECK_ARG(rows >= 1 && heads >= 1 && ld >= static_cast<int64_t>(heads) * 128 && ld % 8 == 0, "mc_rmsnorm_head_rope: rows=%lld heads=%d ld=%lld",
+               static_cast<long long>(rows), heads, static_cast<long long>(ld));
+  MC_CHECK_ARG(mc::aligned16(x_bf16) && (cos_sin == nullptr || (reinterpret_cast<uintptr_t>(cos_sin) & 31u) == 0),
+               "mc_rmsnorm_head_rope: x must be 16-byte and cos_sin 32-byte aligned");
+  const int64_t items = rows * heads;
+  const int64_t want = (items + 15) / 16, cap = static_cast<int64_t>(mc::num_sms()) * 8;
+  mc::rmsnorm_head_rope_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(x_bf16), ld, rows, heads, w, eps, cos_sin);
+  MC_CHECK_LAUNCH("rmsnorm_head_rope_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_silu_bf16(const void* x, void* y, int64_t n, void* stream) {
+  MC_CHECK_ARG(x && y && n >= 1, "mc_silu_bf16: bad arguments");
+  const int64_t want = (n + 255) / 256, cap = static_cast<int64_t>(mc::num_sms()) * 8;
+  mc::silu_bf16_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n);
+  MC_CHECK_LAUNCH("silu_bf16_kernel launch");
   return MC_OK;
 }
 

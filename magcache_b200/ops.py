@@ -215,6 +215,32 @@ def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6):
     return x
 
 
+def rmsnorm_head_rope_(x, weight, heads, cos_sin=None, eps=1e-6):
+    """In-place per-head RMSNorm (head_dim 128) + optional RoPE on a bf16 [rows, heads*128] view (row stride allowed): the q / k
+    normalisation of the MMDiT attention. weight fp32 [128]; cos_sin fp32 [rows, 128] (interleaved cos, sin)."""
+    _dev(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] == heads * 128
+    assert weight.dtype == torch.float32 and weight.numel() == 128 and weight.is_contiguous()
+    rows = x.shape[0]
+    if cos_sin is not None:
+        assert cos_sin.dtype == torch.float32 and cos_sin.is_contiguous() and cos_sin.shape == (rows, 128)
+    check(lib.mc_rmsnorm_head_rope(x.data_ptr(), x.stride(0), rows, heads, weight.data_ptr(), eps,
+                                   cos_sin.data_ptr() if cos_sin is not None else None, _stream()))
+    _count()
+    return x
+
+
+def silu(x, out=None):
+    """bf16 silu(x) (fp32 inside)."""
+    _dev(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.mc_silu_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()))
+    _count()
+    return out
+
+
 def gemm(a, b, bias=None, epilogue=_lib.MC_EPI_BIAS_BF16, out=None, gate=None, tag=None):
     """acc = a @ b.T on tcgen05 (a [M,K] bf16, b [N,K] bf16, row stride allowed) + fused epilogue (see MC_EPI_*)."""
     _dev(a), _dev(b)
@@ -223,7 +249,7 @@ def gemm(a, b, bias=None, epilogue=_lib.MC_EPI_BIAS_BF16, out=None, gate=None, t
     N, K2 = b.shape
     assert K == K2
     if out is None:
-        assert epilogue != _lib.MC_EPI_BIAS_GATE_RESID, "the residual epilogue updates `out` in place; pass the fp32 stream"
+        assert epilogue not in (_lib.MC_EPI_BIAS_GATE_RESID, _lib.MC_EPI_BIAS_GATE_RESID_BF16), "the residual epilogues update `out` in place; pass the stream"
         out = torch.empty(M, N, dtype=torch.float32 if epilogue == _lib.MC_EPI_BIAS_F32 else torch.bfloat16, device=a.device)
     want = torch.float32 if epilogue in (_lib.MC_EPI_BIAS_GATE_RESID, _lib.MC_EPI_BIAS_F32) else torch.bfloat16
     assert out.dtype == want and out.stride(1) == 1 and out.shape == (M, N)

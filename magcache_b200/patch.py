@@ -268,6 +268,75 @@ def magcache_branch(self, hidden, run_blocks, family, cache_attr):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# FLUX: the whole patched forward on the MMDiT engine (magcache_b200/flux.py; opt-in until validated on a GPU, see its header)
+# ------------------------------------------------------------------------------------------------------------------
+class _Sample:
+    """Stand-in for diffusers' Transformer2DModelOutput (`.sample`), which is not importable here."""
+
+    def __init__(self, sample):
+        self.sample = sample
+
+
+def magcache_flux_forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
+                          txt_ids=None, guidance=None, joint_attention_kwargs=None, controlnet_block_samples=None,
+                          controlnet_single_block_samples=None, return_dict=True, controlnet_blocks_repeat=False):
+    r"""MagCache4FLUX/magcache_flux.py:234-440 on the B200 kernels: same signature, same state attributes (`cnt, num_steps,
+    magcache_thresh, K, retention_ratio, accumulated_ratio / _err / _steps, previous_residual, mag_ratios`), `(output,)` or an object
+    with `.sample`. LoRA scaling, ip-adapter and ControlNet residuals (:275-288, :321-324, :371-381, :410-420) are not built and raise."""
+    if joint_attention_kwargs or controlnet_block_samples is not None or controlnet_single_block_samples is not None:
+        raise NotImplementedError("magcache_b200: joint_attention_kwargs / ControlNet residuals are not built for the FLUX engine")
+    if not hidden_states.is_cuda:
+        raise RuntimeError("magcache_b200: hidden_states must be CUDA tensors (no CPU path)")
+    eng = self.__dict__.get("_mc_flux_engine")
+    if eng is None:
+        from .flux import FluxEngine, FluxWeights
+        eng = FluxEngine(FluxWeights.from_module(self, hidden_states.device))
+        object.__setattr__(self, "_mc_flux_engine", eng)
+    if txt_ids.ndim == 3:  # :305-316 (deprecated 3-D ids)
+        txt_ids = txt_ids[0]
+    if img_ids.ndim == 3:
+        img_ids = img_ids[0]
+    eng.stage_inputs(hidden_states, encoder_hidden_states, pooled_projections, timestep, guidance, img_ids, txt_ids)
+    ctrls = self.__dict__.setdefault("_mc_ctrls", {})
+    if "flux" not in ctrls:
+        from .config import FAMILIES
+        ctrls["flux"] = AttrController(FAMILIES["flux"])
+    ctrl = ctrls["flux"]
+    skip_forward = ctrl.decide(self)  # :326-338
+    cur = self.previous_residual
+    if cur is None:
+        eng.res_valid = False
+    elif torch.is_tensor(cur) and cur.data_ptr() != eng.res.data_ptr():
+        eng.res.copy_(cur.reshape(eng.res.shape))
+        eng.res_valid = True
+    out = eng.forward("hit" if skip_forward else "miss")
+    self.previous_residual = eng.res.view(1, *eng.res.shape)  # :427
+    ctrl.advance(self)  # :431-436
+    output = out.view(1, *out.shape)
+    if not return_dict:
+        return (output,)
+    return _Sample(output)
+
+
+def init_magcache_flux(transformer, num_inference_steps=28, thresh=0.24, K=5, retention_ratio=0.1, mag_ratios=None, table="flux_dev"):
+    """The installation statements of magcache_flux.py:446-471 (Kontext: magcache_flux_kontext.py:445-470 with table "flux_kontext",
+    thresh 0.05, K 4, retention 0.2): patches the CLASS."""
+    from .config import nearest_interp
+    import numpy as np
+    cls = transformer.__class__
+    cls.forward = magcache_flux_forward
+    cls.cnt, cls.num_steps = 0, num_inference_steps
+    mr = np.asarray(tables()[table] if mag_ratios is None else mag_ratios, dtype=np.float64)
+    if len(mr) != num_inference_steps:  # :461-463
+        mr = nearest_interp(mr, num_inference_steps)
+    cls.mag_ratios = mr
+    cls.K, cls.magcache_thresh, cls.retention_ratio = K, thresh, retention_ratio
+    cls.accumulated_ratio, cls.accumulated_err, cls.accumulated_steps = 1, 0, 0
+    cls.previous_residual = None
+    return transformer
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # The paper-evaluation variant of the Wan forward (the code behind the published Wan2.1 numbers)
 # ------------------------------------------------------------------------------------------------------------------
 def magcache_eval_forward(self, x, t, context, seq_len, clip_fea=None, y=None):

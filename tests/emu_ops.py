@@ -1,0 +1,203 @@
+"""Test infrastructure: a torch-CPU emulation of magcache_b200.ops with the rounding points the kernels document (bf16 where the
+kernel rounds to bf16, fp32 elsewhere). Monkeypatched over an engine module's `ops`, it lets the ORCHESTRATION of an engine — weight
+packing, buffer views, row / column ranges, modulation indices, gates, op order — be checked against the oracle on CPU. It proves
+nothing about the kernels themselves (tests/test_kernels_gpu.py and the *_gpu.py forward tests do that)."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from magcache_b200 import _lib as L
+
+BF, F32 = torch.bfloat16, torch.float32
+LAUNCHES = 0
+PROFILE = None
+
+
+def _rb(t):
+    return t.to(BF).to(F32)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def gemm(a, b, bias=None, epilogue=L.MC_EPI_BIAS_BF16, out=None, gate=None, tag=None):
+    assert a.dtype == BF and b.dtype == BF and a.shape[1] == b.shape[1]
+    acc = a.to(F32) @ b.to(F32).t()
+    M, N = acc.shape
+    if epilogue == L.MC_EPI_ROWBIAS_BF16:
+        r = (acc + (bias[:, None] if bias is not None else 0.0)).to(BF)
+    else:
+        acc = acc + (bias[None, :] if bias is not None else 0.0)
+        if epilogue == L.MC_EPI_BIAS_BF16:
+            r = acc.to(BF)
+        elif epilogue == L.MC_EPI_BIAS_GELU_BF16:
+            r = F.gelu(_rb(acc), approximate="tanh").to(BF)
+        elif epilogue == L.MC_EPI_BIAS_GELU_ERF_BF16:
+            r = F.gelu(_rb(acc)).to(BF)
+        elif epilogue == L.MC_EPI_BIAS_SILU_BF16:
+            r = F.silu(_rb(acc)).to(BF)
+        elif epilogue == L.MC_EPI_BIAS_F32:
+            r = acc
+        elif epilogue == L.MC_EPI_BIAS_GATE_RESID:
+            assert out is not None and out.dtype == F32
+            r = out + _rb(acc) * (gate[None, :] if gate is not None else 1.0)
+        elif epilogue == L.MC_EPI_BIAS_GATE_RESID_BF16:
+            assert out is not None and out.dtype == BF
+            g = gate[None, :] if gate is not None else 1.0
+            r = (out.to(F32) + _rb(g * _rb(acc))).to(BF)
+        else:
+            raise ValueError(epilogue)
+    if out is None:
+        out = torch.empty(M, N, dtype=r.dtype)
+    assert out.shape == (M, N) and out.dtype == r.dtype and out.stride(1) == 1
+    out.copy_(r)
+    _count()
+    return out
+
+
+def ln_modulate(x, em, scale_idx, shift_idx, eps=1e-6, round_ln_to_bf16=False, out_dtype=BF, out=None):
+    assert x.is_contiguous() and em.dtype == F32 and em.is_contiguous()
+    ln = F.layer_norm(x.to(F32), (x.shape[-1],), None, None, eps)
+    if round_ln_to_bf16:
+        ln = _rb(ln)
+    y = ln * (1.0 + em[scale_idx]) + em[shift_idx]
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype)
+    assert out.is_contiguous()
+    out.copy_(y)
+    _count()
+    return out
+
+
+def ln_affine(x, weight, bias, eps=1e-6, out_dtype=BF, out=None):
+    y = F.layer_norm(x.to(F32), (x.shape[-1],), weight, bias, eps)
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype)
+    out.copy_(y)
+    _count()
+    return out
+
+
+def rmsnorm_head_rope_(x, weight, heads, cos_sin=None, eps=1e-6):
+    assert x.dtype == BF and x.stride(1) == 1 and x.shape[1] == heads * 128 and weight.numel() == 128
+    rows = x.shape[0]
+    v = x.to(F32).view(rows, heads, 128)
+    r = torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)
+    o = _rb(_rb(v * r) * weight)
+    if cos_sin is not None:
+        cs = cos_sin.view(rows, 1, 64, 2)
+        re, im = o.view(rows, heads, 64, 2).unbind(-1)
+        c, s = cs[..., 0], cs[..., 1]
+        o = torch.stack([re * c - im * s, im * c + re * s], dim=-1).view(rows, heads, 128)
+    x.copy_(o.reshape(rows, heads * 128))
+    _count()
+    return x
+
+
+def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6):
+    rows, cols = x.shape
+    v = x.to(F32)
+    o = _rb(v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)) * weight
+    if cos_sin is not None:
+        H = cols // head_dim
+        cs = cos_sin.view(rows, 1, head_dim // 2, 2)
+        re, im = o.view(rows, H, head_dim // 2, 2).unbind(-1)
+        c, s = cs[..., 0], cs[..., 1]
+        o = torch.stack([re * c - im * s, re * s + im * c], dim=-1).view(rows, cols)
+    x.copy_(o)
+    _count()
+    return x
+
+
+def attention(q, k, vt, heads, scale=None, out=None, tag=None):
+    Lq, W = q.shape
+    Lk = k.shape[0]
+    qh = q.to(F32).view(Lq, heads, 128).transpose(0, 1)
+    kh = k.to(F32).reshape(Lk, heads, 128).transpose(0, 1)
+    vh = vt.to(F32).t().reshape(Lk, heads, 128).transpose(0, 1)
+    s = qh @ kh.transpose(1, 2) * (scale if scale is not None else 1.0 / math.sqrt(128))
+    o = (torch.softmax(s, -1) @ vh).transpose(0, 1).reshape(Lq, W)
+    if out is None:
+        out = torch.empty(Lq, W, dtype=BF)
+    out.copy_(o)
+    _count()
+    return out
+
+
+def _promote(a, b):
+    return F32 if F32 in (a.dtype, b.dtype) else BF
+
+
+def cache_hit_add(x, r, out=None, tag=None):
+    y = x.to(F32) + r.to(F32)
+    if out is None:
+        out = torch.empty(x.shape, dtype=_promote(x, r))
+    out.copy_(y)
+    _count()
+    return out
+
+
+def residual_sub(x_out, x_in, out=None):
+    y = x_out.to(F32) - x_in.to(F32)
+    if out is None:
+        out = torch.empty(x_out.shape, dtype=_promote(x_out, x_in))
+    out.copy_(y)
+    _count()
+    return out
+
+
+def cast_into(src, dst):
+    dst.copy_(src.reshape(dst.shape))
+    _count()
+    return dst
+
+
+def silu(x, out=None):
+    y = F.silu(x.to(F32)).to(BF)
+    if out is None:
+        return y
+    out.copy_(y)
+    return out
+
+
+def time_sinusoid(t, dim):
+    half = dim // 2
+    pos = t.to(torch.float64).reshape(-1)
+    s = torch.outer(pos, torch.pow(10000.0, -torch.arange(half, dtype=torch.float64) / half))
+    _count()
+    return torch.cat([torch.cos(s), torch.sin(s)], dim=1).to(F32)
+
+
+def transpose(src, dst):
+    dst.copy_(src.t())
+    _count()
+    return dst
+
+
+def patchify(latent):
+    C, Fr, H, W = latent.shape
+    x = latent.view(C, Fr, H // 2, 2, W // 2, 2).permute(1, 2, 4, 0, 3, 5).reshape(Fr * (H // 2) * (W // 2), C * 4)
+    _count()
+    return x.to(BF)
+
+
+def linear_f32_small(x, w, b=None, act=0):
+    xin = F.silu(x) if act == 1 else x
+    y = xin @ w.t() + (b if b is not None else 0.0)
+    _count()
+    return F.silu(y) if act == 2 else y
+
+
+def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None, row_offset=0, out=None):
+    xs = x.to(F32) + (residual if residual is not None else 0.0)
+    em = head_mod + e.reshape(1, -1)  # (modulation[1,2,D] + e.unsqueeze(1)).chunk(2): shift, scale
+    y = F.layer_norm(xs, (xs.shape[-1],), None, None, eps) * (1 + em[1]) + em[0]
+    o = y @ w_t + b  # [N, 4*c_out]
+    f, h, w = grid
+    u = o.view(f, h, w, 1, 2, 2, c_out)
+    u = torch.einsum("fhwpqrc->cfphqwr", u).reshape(c_out, f, 2 * h, 2 * w)
+    _count()
+    return u.contiguous()

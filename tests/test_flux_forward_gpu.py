@@ -1,0 +1,130 @@
+"""FLUX MMDiT engine on the GPU: the new kernels (per-head RMSNorm + RoPE, SiLU, the bf16 gated-residual and SiLU GEMM epilogues) against
+torch, and `magcache_flux_forward` against the oracle restatement of MagCache4FLUX/magcache_flux.py:234-440.
+
+OPT-IN: this engine was written after round 1's GPU budget was spent; its orchestration is verified on CPU through the kernel
+emulation (tests/test_flux_engine_emulated_cpu.py) but these tests have not run on a B200 yet. `MC_RUN_UNVALIDATED=1 pytest -m gpu`
+enables them; once green, drop the skip."""
+import copy
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MC_RUN_UNVALIDATED") != "1", reason="FLUX engine not yet validated on a GPU (set MC_RUN_UNVALIDATED=1)")]
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _ops():
+    from magcache_b200 import ops
+    return ops
+
+
+def test_rmsnorm_head_rope_vs_torch():
+    import emu_ops
+    ops = _ops()
+    for rows, heads, strided in [(300, 24, False), (77, 2, True), (4608, 24, True)]:
+        W = heads * 128
+        buf = torch.randn(rows, 2 * W, device=DEV).bfloat16()
+        x = buf[:, W:] if strided else buf[:, :W].contiguous()
+        w = (1 + 0.1 * torch.randn(128, device=DEV)).bfloat16().float()
+        ang = torch.rand(rows, 64, device=DEV, dtype=torch.float64) * 6.28
+        cs = torch.stack([ang.cos(), ang.sin()], dim=-1).reshape(rows, 128).float().contiguous()
+        for table in (cs, None):
+            want = x.clone().cpu()
+            emu_ops.rmsnorm_head_rope_(want, w.cpu(), heads, None if table is None else table.cpu())
+            got = x.clone()
+            ops.rmsnorm_head_rope_(got, w, heads, table)
+            d = (got.float().cpu() - want.float()).abs()
+            # rsqrtf vs torch.rsqrt can flip a bf16 rounding: allow one bf16 ulp on a few elements, nothing more
+            assert float((d > 2.0 ** -7 * want.float().abs().clamp_min(2.0 ** -6)).float().mean()) == 0.0
+            assert float((d > 0).float().mean()) < 0.02
+
+
+def test_silu_and_gemm_epilogues_6_7_vs_torch():
+    import emu_ops
+    from magcache_b200 import _lib as L
+    ops = _ops()
+    x = torch.randn(1, 3072, device=DEV).bfloat16()
+    assert torch.equal(ops.silu(x).cpu(), emu_ops.silu(x.cpu()))
+    for M, N, K in [(391, 640, 1536), (1, 768, 256), (4608, 3072, 15360 // 4)]:
+        a = torch.randn(M, K, device=DEV).bfloat16()
+        b = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device=DEV).bfloat16().float()
+        gate = (torch.randn(N, device=DEV) * 0.5).bfloat16().float()
+        out = ops.gemm(a, b, bias, L.MC_EPI_BIAS_SILU_BF16)
+        ref = emu_ops.gemm(a.cpu(), b.cpu(), bias.cpu(), L.MC_EPI_BIAS_SILU_BF16)
+        acc = (a.double() @ b.double().t() + bias.double()).float().cpu()
+        assert ((out.float().cpu() - ref.float()).abs() <= ref.float().abs() * 2.0 ** -7 + acc.abs() * 2.0 ** -7 + 1e-3).all()
+        stream = torch.randn(M, N, device=DEV).bfloat16()
+        want = emu_ops.gemm(a.cpu(), b.cpu(), bias.cpu(), L.MC_EPI_BIAS_GATE_RESID_BF16, out=stream.clone().cpu(), gate=gate.cpu())
+        got = ops.gemm(a, b, bias, L.MC_EPI_BIAS_GATE_RESID_BF16, out=stream.clone(), gate=gate)
+        tol = want.float().abs() * 2.0 ** -7 + (gate.cpu().abs() * acc.abs()) * 2.0 ** -6 + 1e-3
+        assert ((got.float().cpu() - want.float()).abs() <= tol).all()
+
+
+def _model(guidance=True, seed=0, layers=(2, 3)):
+    from oracle import flux_ref as fr
+    return fr.FluxTransformer2DModel(in_channels=64, num_layers=layers[0], num_single_layers=layers[1], num_attention_heads=2,
+                                     joint_attention_dim=96, pooled_projection_dim=48, guidance_embeds=guidance).init_synthetic(seed)
+
+
+def test_flux_forward_vs_oracle_and_fp64():
+    import magcache_b200 as mc
+    from oracle import flux_ref as fr
+    model = _model()
+    g = torch.Generator().manual_seed(0)
+    hs, enc, pooled = torch.randn(1, 16 * 12, 64, generator=g).bfloat16(), torch.randn(1, 37, 96, generator=g).bfloat16(), torch.randn(1, 48, generator=g).bfloat16()
+    img_ids, txt_ids = fr.make_ids(16, 12, 37)
+    t, gd = torch.tensor([0.731]), torch.tensor([3.5])
+    ref_m = copy.deepcopy(model)
+    ref_m.__class__ = type("RefFlux", (ref_m.__class__,), {})
+    fr.install_magcache(type(ref_m), mc.tables()["flux_dev"], 28)
+    m64 = copy.deepcopy(model).double()
+    m64.__class__ = type("RefFlux64", (m64.__class__,), {})
+    fr.install_magcache(type(m64), mc.tables()["flux_dev"], 28)
+    ours = copy.deepcopy(model).to(DEV)
+    ours.__class__ = type("OurFlux", (ours.__class__,), {})
+    mc.init_magcache_flux(ours, 28)
+    with torch.no_grad():
+        ref = ref_m(hs, enc, pooled, t, img_ids, txt_ids, gd, return_dict=False)[0]
+        with fr.exact():
+            exact = m64(hs.double(), enc.double(), pooled.double(), t.double(), img_ids, txt_ids, gd.double(), return_dict=False)[0]
+    out = ours(hs.to(DEV), enc.to(DEV), pooled.to(DEV), t.to(DEV), img_ids.to(DEV), txt_ids.to(DEV), gd.to(DEV)).sample.cpu()
+    e_ours, e_ref, e_vs = rel_l2(out, exact), rel_l2(ref, exact), rel_l2(out, ref)
+    print(f"[flux] ours vs fp64 {e_ours:.3e} | oracle(bf16) vs fp64 {e_ref:.3e} | ours vs oracle {e_vs:.3e}")
+    assert e_ours <= 1.5 * e_ref + 1e-3 and e_vs <= 2.0 * e_ref + 1e-3
+
+
+def test_flux_loop_vs_oracle():
+    import magcache_b200 as mc
+    from oracle import flux_ref as fr
+    model = _model(seed=1)
+    g = torch.Generator().manual_seed(1)
+    hs, enc, pooled = torch.randn(1, 8 * 8, 64, generator=g).bfloat16(), torch.randn(1, 19, 96, generator=g).bfloat16(), torch.randn(1, 48, generator=g).bfloat16()
+    img_ids, txt_ids = fr.make_ids(8, 8, 19)
+    steps = 12
+    ref_m = copy.deepcopy(model)
+    ref_m.__class__ = type("RefFluxL", (ref_m.__class__,), {})
+    fr.install_magcache(type(ref_m), mc.tables()["flux_dev"], steps)
+    ours = copy.deepcopy(model).to(DEV)
+    ours.__class__ = type("OurFluxL", (ours.__class__,), {})
+    mc.init_magcache_flux(ours, steps)
+    skips = []
+    with torch.no_grad():
+        for i in range(steps + 2):
+            t = torch.tensor([1.0 - (i % steps) / steps])
+            x = hs * (1.0 - 0.03 * i)
+            ref = ref_m(x, enc, pooled, t, img_ids, txt_ids, torch.tensor([3.5]), return_dict=False)[0]
+            out = ours(x.to(DEV), enc.to(DEV), pooled.to(DEV), t.to(DEV), img_ids.to(DEV), txt_ids.to(DEV), torch.tensor([3.5], device=DEV),
+                       return_dict=False)[0].cpu()
+            skips.append(int(ref_m.last_skip))
+            assert rel_l2(out, ref) <= 0.15, (i, rel_l2(out, ref))
+            for attr in ("cnt", "accumulated_ratio", "accumulated_err", "accumulated_steps"):
+                assert float(getattr(ours, attr)) == float(getattr(ref_m, attr)), (i, attr)
+    assert 0 < sum(skips[:steps]) < steps
