@@ -129,6 +129,10 @@ class FluxEngine:
         self.x0, self.res, self.hit = torch.empty(n_img, D, **bf), torch.empty(n_img, D, **bf), torch.empty(n_img, D, **bf)
         self.qk = torch.empty(S, 2 * D, **bf)
         self.vt = torch.zeros(D, (S + 7) // 8 * 8, **bf)
+        # V^T column ranges must start on 16 bytes for the GEMM to write them directly; otherwise (text length not a multiple of 8:
+        # never with the pipeline's padded 512 tokens) V goes to a row-major buffer and is transposed once per attention
+        self.v_direct = n_txt % 8 == 0
+        self.v = None if self.v_direct else torch.empty(S, D, **bf)
         self.cat = torch.empty(S, 5 * D, **bf)
         self.ada = torch.empty(1, self.w.ada_rows, **bf)
         self.adaf = torch.empty(self.w.ada_rows, dtype=torch.float32, device=dev)
@@ -191,10 +195,19 @@ class FluxEngine:
         """q | k and V^T projections of the token range `rows` (a slice) from its LN output, then per-head RMSNorm + RoPE in place."""
         D, H = self.w.dim, self.w.heads
         ops.gemm(h_rows, qk_w, qk_b, E.MC_EPI_BIAS_BF16, out=self.qk[rows])
-        ops.gemm(v_w, h_rows, v_b, E.MC_EPI_ROWBIAS_BF16, out=self.vt[:, rows])
+        if self.v_direct:
+            ops.gemm(v_w, h_rows, v_b, E.MC_EPI_ROWBIAS_BF16, out=self.vt[:, rows])
+        else:
+            ops.gemm(h_rows, v_w, v_b, E.MC_EPI_BIAS_BF16, out=self.v[rows])
         rope = self._rope[rows]
         ops.rmsnorm_head_rope_(self.qk[rows][:, :D], nq, H, rope)
         ops.rmsnorm_head_rope_(self.qk[rows][:, D:], nk, H, rope)
+
+    def _joint_attention(self, out):
+        D, S = self.w.dim, self.S
+        if not self.v_direct:
+            ops.transpose(self.v, self.vt[:, :S])
+        ops.attention(self.qk[:, :D], self.qk[:, D:], self.vt[:, :S], self.w.heads, out=out, tag="flux_attn")
 
     def run_blocks(self):
         """The double-stream and single-stream blocks (:343-424) on `hs`; returns the image rows of the stream."""
@@ -208,7 +221,7 @@ class FluxEngine:
             ops.ln_modulate(hs[txt], emc, 1, 0, round_ln_to_bf16=True, out=h[txt])
             self._attention(img, h[img], b["qk_w"], b["qk_b"], b["v_w"], b["v_b"], b["nq"], b["nk"])
             self._attention(txt, h[txt], b["cqk_w"], b["cqk_b"], b["cv_w"], b["cv_b"], b["cnq"], b["cnk"])
-            ops.attention(self.qk[:, :D], self.qk[:, D:], self.vt[:, :S], H, out=self.att, tag="flux_attn")
+            self._joint_attention(self.att)
             ops.gemm(self.att[img], b["o_w"], b["o_b"], E.MC_EPI_BIAS_GATE_RESID_BF16, out=hs[img], gate=em[2])
             ops.gemm(self.att[txt], b["co_w"], b["co_b"], E.MC_EPI_BIAS_GATE_RESID_BF16, out=hs[txt], gate=emc[2])
             for rows, e, f1w, f1b, f2w, f2b in ((img, em, b["ff1_w"], b["ff1_b"], b["ff2_w"], b["ff2_b"]),
@@ -223,7 +236,7 @@ class FluxEngine:
             ops.ln_modulate(hs, em, 1, 0, round_ln_to_bf16=True, out=h)
             ops.gemm(h, b["mlp_w"], b["mlp_b"], E.MC_EPI_BIAS_GELU_BF16, out=self.cat[:, D:])
             self._attention(allr, h, b["qk_w"], b["qk_b"], b["v_w"], b["v_b"], b["nq"], b["nk"])
-            ops.attention(self.qk[:, :D], self.qk[:, D:], self.vt[:, :S], H, out=self.cat[:, :D], tag="flux_attn")
+            self._joint_attention(self.cat[:, :D])
             ops.gemm(self.cat, b["out_w"], b["out_b"], E.MC_EPI_BIAS_GATE_RESID_BF16, out=hs, gate=em[2])
         return hs[img]
 

@@ -41,10 +41,11 @@ def _inputs(seed=0, hw=(8, 6), n_txt=19):
     return hs, enc, pooled, img_ids, txt_ids
 
 
-@pytest.mark.parametrize("guidance", [True, False])
-def test_flux_engine_single_forward_matches_oracle(emulated, guidance):
+@pytest.mark.parametrize("guidance,n_txt", [(True, 19), (False, 19), (True, 24)])
+def test_flux_engine_single_forward_matches_oracle(emulated, guidance, n_txt):
+    """n_txt = 24: V^T written by the projection GEMM into its column range; 19: the row-major V + transpose fallback."""
     model = _model(guidance)
-    hs, enc, pooled, img_ids, txt_ids = _inputs()
+    hs, enc, pooled, img_ids, txt_ids = _inputs(n_txt=n_txt)
     t, gd = torch.tensor([0.731]), (torch.tensor([3.5]) if guidance else None)
     ref_m = copy.deepcopy(model)
     ref_m.__class__ = type("RefFlux", (ref_m.__class__,), {})
@@ -61,6 +62,7 @@ def test_flux_engine_single_forward_matches_oracle(emulated, guidance):
             exact = m64(hs.double(), enc.double(), pooled.double(), t.double(), img_ids, txt_ids, None if gd is None else gd.double(),
                         return_dict=False)[0]
         out = ours(hs, enc, pooled, t, img_ids, txt_ids, gd)
+    assert ours._mc_flux_engine.v_direct == (n_txt % 8 == 0)
     assert hasattr(out, "sample") and out.sample.shape == ref.shape == (1, 48, 64) and out.sample.dtype == torch.bfloat16
     e_ours, e_ref, e_vs = rel_l2(out.sample, exact), rel_l2(ref, exact), rel_l2(out.sample, ref)
     print(f"[flux emulated] ours vs fp64 {e_ours:.3e} | oracle(bf16) vs fp64 {e_ref:.3e} | ours vs oracle {e_vs:.3e}")

@@ -79,8 +79,8 @@ def test_flux_forward_vs_oracle_and_fp64():
     from oracle import flux_ref as fr
     model = _model()
     g = torch.Generator().manual_seed(0)
-    hs, enc, pooled = torch.randn(1, 16 * 12, 64, generator=g).bfloat16(), torch.randn(1, 37, 96, generator=g).bfloat16(), torch.randn(1, 48, generator=g).bfloat16()
-    img_ids, txt_ids = fr.make_ids(16, 12, 37)
+    hs, enc, pooled = torch.randn(1, 16 * 12, 64, generator=g).bfloat16(), torch.randn(1, 40, 96, generator=g).bfloat16(), torch.randn(1, 48, generator=g).bfloat16()
+    img_ids, txt_ids = fr.make_ids(16, 12, 40)
     t, gd = torch.tensor([0.731]), torch.tensor([3.5])
     ref_m = copy.deepcopy(model)
     ref_m.__class__ = type("RefFlux", (ref_m.__class__,), {})
