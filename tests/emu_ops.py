@@ -195,9 +195,16 @@ def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1
     xs = x.to(F32) + (residual if residual is not None else 0.0)
     em = head_mod + e.reshape(1, -1)  # (modulation[1,2,D] + e.unsqueeze(1)).chunk(2): shift, scale
     y = F.layer_norm(xs, (xs.shape[-1],), None, None, eps) * (1 + em[1]) + em[0]
-    o = y @ w_t + b  # [N, 4*c_out]
+    o = y @ w_t + b  # [rows, 4*c_out]
     f, h, w = grid
+    if o.shape[0] != f * h * w:  # token-sharded caller: only the positions of rows [row_offset, row_offset + rows) are written
+        full = torch.zeros(f * h * w, o.shape[1])
+        full[row_offset:row_offset + o.shape[0]] = o
+        o = full
     u = o.view(f, h, w, 1, 2, 2, c_out)
-    u = torch.einsum("fhwpqrc->cfphqwr", u).reshape(c_out, f, 2 * h, 2 * w)
+    u = torch.einsum("fhwpqrc->cfphqwr", u).reshape(c_out, f, 2 * h, 2 * w).contiguous()
     _count()
-    return u.contiguous()
+    if out is not None:
+        out.copy_(u)
+        return out
+    return u

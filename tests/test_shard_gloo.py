@@ -100,3 +100,57 @@ def test_sharded_self_attention_gather_and_reductions_world2():
             assert err < 3e-2, err      # bf16 pipeline; q/k RoPE in fp32 vs the oracle's fp64
             assert same                  # sum of partial outputs == full unpatchify, exactly
             assert stats == [3.0, 4.0, 6.0, float(N)]
+
+
+def _engine_worker(rank, world, initfile, results):
+    """The REAL engine code path of a token-sharded forward (WanEngine with shard_world=2: local projections, async K/V row
+    all-gathers, V transpose, attention over all keys, partial-output all-reduce in the head) with the kernels emulated on CPU
+    (tests/emu_ops.py) and gloo as the collective backend."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emu_ops
+    import magcache_b200 as mc
+    from magcache_b200 import patch as patch_mod
+    from magcache_b200 import wan as wan_mod
+    dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
+    try:
+        wan_mod.ops = emu_ops
+        patch_mod.ops = emu_ops
+        torch.Tensor.is_cuda = property(lambda self: True)
+        os.environ["MC_GRAPHS"] = "0"
+        model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=8).init_synthetic(3)
+        g = torch.Generator().manual_seed(7)
+        lat, ctx = torch.randn(16, *[GRID[0], 2 * GRID[1], 2 * GRID[2]], generator=g), torch.randn(5, 64, generator=g)
+        table = [1.0] * 8
+        outs = {}
+        for name, kw in (("single", {}), ("sharded", dict(shard_world=world, shard_rank=rank))):
+            m = type("M", (), {})()
+            m.model_type = "t2v"
+            object.__setattr__(m, "_mc_engine", mc.WanEngine(mc.WanWeights.from_module(model, torch.device("cpu")), **kw))
+            mc.init_magcache(m, 4, thresh=10.0, K=3, retention_ratio=0.25, mag_ratios=table)
+            seq = []
+            with torch.no_grad():
+                for i in range(4):  # miss, miss, hit, hit
+                    seq.append(m.forward([lat], torch.tensor([500.0]), [ctx], N)[0].clone())
+            outs[name] = (seq, m._mc_engine, m.residual_cache)
+        eng = outs["sharded"][1]
+        sh = eng.shard
+        errs = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(outs["sharded"][0], outs["single"][0])]
+        r_full = outs["single"][2][0][0]
+        r_loc = outs["sharded"][2][0][0]
+        cache_err = float((r_loc - r_full[sh.start:sh.stop]).abs().max() / r_full.abs().max())
+        results[rank] = (errs, cache_err, tuple(r_loc.shape), (sh.start, sh.stop))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_engine_equals_single_engine_world2():
+    with tempfile.TemporaryDirectory() as d:
+        mgr = mp.get_context("spawn").Manager()
+        results = mgr.dict()
+        mp.spawn(_engine_worker, args=(2, os.path.join(d, "init"), results), nprocs=2, join=True)
+        assert set(results.keys()) == {0, 1}
+        for r in (0, 1):
+            errs, cache_err, shape, rng = results[r]
+            assert len(errs) == 4 and max(errs) < 2e-3, errs       # same arithmetic on row subsets (CPU matmul blocking differs)
+            assert cache_err < 2e-3 and shape == (N // 2, 256) and rng == (r * N // 2, (r + 1) * N // 2)
