@@ -220,6 +220,9 @@ int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, co
  * cos_sin: fp32 [rows, 128] interleaved (cos, sin) per pair, or NULL. */
 int32_t mc_rmsnorm_head_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t heads, const float* w, float eps, const float* cos_sin,
                              void* stream);
+/* out[c] = bf16(bf16(sum_r x[r, c]) / rows): the mean over the valid text tokens that conditions HunyuanVideo's token refiner
+ * [EXT hyvideo SingleTokenRefiner.forward, called at MagCache4HunyuanVideo/magcache_sample_video.py:69]. x bf16 [rows, cols] (row stride ld). */
+int32_t mc_colmean_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols, void* out, void* stream);
 /* y = silu(x), bf16 -> bf16 (fp32 inside): `self.silu(emb)` of AdaLayerNormZero / ...Single / ...Continuous. */
 int32_t mc_silu_bf16(const void* x, void* y, int64_t n, void* stream);
 

@@ -77,6 +77,7 @@ SIGNATURES = {
                        c_int32, c_void_p],
     "mc_rmsnorm_rope": [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_float, c_void_p, c_int32, c_void_p],
     "mc_rmsnorm_head_rope": [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_float, c_void_p, c_void_p],
+    "mc_colmean_bf16": [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p],
     "mc_silu_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
     "mc_gemm_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p,
                      c_void_p],

@@ -206,6 +206,18 @@ __global__ void __launch_bounds__(256) rmsnorm_head_rope_kernel(__nv_bfloat16* _
   }
 }
 
+// ---- column mean of a bf16 matrix: the masked mean of the text states that conditions HunyuanVideo's token refiner
+// (`(x * mask).sum(dim=1) / mask.sum(dim=1)` over the valid tokens [EXT hyvideo SingleTokenRefiner], called at
+// MagCache4HunyuanVideo/magcache_sample_video.py:69). One thread per column (coalesced across a warp), fp32 accumulation.
+__global__ void colmean_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int rows, int cols, __nv_bfloat16* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += __bfloat162float(x[static_cast<int64_t>(r) * ld + c]);
+  // torch: the bf16 sum is rounded to bf16, then divided by the (bf16) count and rounded again
+  out[c] = __float2bfloat16_rn(round_bf16(s) / round_bf16(static_cast<float>(rows)));
+}
+
 // ---- y = silu(x) on a bf16 vector (the `self.silu(emb)` in front of every AdaLayerNorm linear) ------------------------------
 __global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -506,6 +518,14 @@ int32_t mc_rmsnorm_head_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t hea
   mc::rmsnorm_head_rope_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<__nv_bfloat16*>(x_bf16), ld, rows, heads, w, eps, cos_sin);
   MC_CHECK_LAUNCH("rmsnorm_head_rope_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_colmean_bf16(const void* x, int64_t ld, int32_t rows, int32_t cols, void* out, void* stream) {
+  MC_CHECK_ARG(x && out && rows >= 1 && cols >= 1 && ld >= cols, "mc_colmean_bf16: bad arguments");
+  mc::colmean_bf16_kernel<<<(cols + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, cols,
+                                                                                             static_cast<__nv_bfloat16*>(out));
+  MC_CHECK_LAUNCH("colmean_bf16_kernel launch");
   return MC_OK;
 }
 

@@ -230,6 +230,16 @@ def rmsnorm_head_rope_(x, weight, heads, cos_sin=None, eps=1e-6):
     return x
 
 
+def colmean(x):
+    """bf16 mean over the rows of a bf16 [rows, cols] view -> [1, cols] (torch semantics: bf16 sum, then bf16 division)."""
+    _dev(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty(1, x.shape[1], dtype=torch.bfloat16, device=x.device)
+    check(lib.mc_colmean_bf16(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), _stream()))
+    _count()
+    return out
+
+
 def silu(x, out=None):
     """bf16 silu(x) (fp32 inside)."""
     _dev(x)

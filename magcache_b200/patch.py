@@ -289,7 +289,7 @@ def magcache_flux_forward(self, hidden_states, encoder_hidden_states=None, poole
         raise RuntimeError("magcache_b200: hidden_states must be CUDA tensors (no CPU path)")
     eng = self.__dict__.get("_mc_flux_engine")
     if eng is None:
-        from .flux import FluxEngine, FluxWeights
+        from .mmdit import FluxEngine, FluxWeights
         eng = FluxEngine(FluxWeights.from_module(self, hidden_states.device))
         object.__setattr__(self, "_mc_flux_engine", eng)
     if txt_ids.ndim == 3:  # :305-316 (deprecated 3-D ids)
@@ -333,6 +333,61 @@ def init_magcache_flux(transformer, num_inference_steps=28, thresh=0.24, K=5, re
     cls.K, cls.magcache_thresh, cls.retention_ratio = K, thresh, retention_ratio
     cls.accumulated_ratio, cls.accumulated_err, cls.accumulated_steps = 1, 0, 0
     cls.previous_residual = None
+    return transformer
+
+
+def magcache_hunyuan_forward(self, x, t, text_states=None, text_mask=None, text_states_2=None, freqs_cos=None, freqs_sin=None,
+                             guidance=None, return_dict=True):
+    r"""MagCache4HunyuanVideo/magcache_sample_video.py:29-160 on the B200 kernels (MMDiT engine, magcache_b200/mmdit.py; opt-in until
+    validated on a GPU): same signature and state attributes (`cnt, num_steps, magcache_thresh, K, retention_ratio, accumulated_ratio /
+    _err / _steps, residual_cache, mag_ratios`), returns `{"x": img}` or the tensor. x [1, 16, T, H, W]; text_mask marks the valid
+    (right-padded) text tokens."""
+    if not x.is_cuda:
+        raise RuntimeError("magcache_b200: x must be a CUDA tensor (no CPU path)")
+    eng = self.__dict__.get("_mc_hunyuan_engine")
+    if eng is None:
+        from .mmdit import HunyuanEngine, HunyuanWeights
+        eng = HunyuanEngine(HunyuanWeights.from_module(self, x.device))
+        object.__setattr__(self, "_mc_hunyuan_engine", eng)
+    eng.stage_inputs(x, t, text_states, text_mask, text_states_2, freqs_cos, freqs_sin, guidance)
+    ctrls = self.__dict__.setdefault("_mc_ctrls", {})
+    if "hunyuan" not in ctrls:
+        from .config import FAMILIES
+        ctrls["hunyuan"] = AttrController(FAMILIES["hunyuan"])
+    ctrl = ctrls["hunyuan"]
+    skip_forward = ctrl.decide(self)  # :88-102
+    cur = self.residual_cache
+    if cur is None:
+        eng.res_valid = False
+    elif torch.is_tensor(cur) and cur.data_ptr() != eng.res.data_ptr():
+        eng.res.copy_(cur.reshape(eng.res.shape))
+        eng.res_valid = True
+    img = eng.forward("hit" if skip_forward else "miss")
+    self.residual_cache = eng.res.view(1, *eng.res.shape)  # :141
+    ctrl.advance(self)  # :149-154
+    if return_dict:
+        return {"x": img}
+    return img
+
+
+def init_magcache_hunyuan(transformer, infer_steps=50, thresh=0.24, K=6, retention_ratio=0.2, video_height=720, mag_ratios=None):
+    """The installation statements of magcache_sample_video.py:303-328 (table chosen by `args.video_size[0]` in {720, 544}, :315-318)."""
+    import numpy as np
+
+    from .config import nearest_interp
+    cls = transformer.__class__
+    cls.cnt, cls.num_steps, cls.magcache_thresh, cls.K = 0, infer_steps, thresh, K
+    cls.residual_cache = None
+    if mag_ratios is None:
+        if video_height not in (720, 544):
+            raise KeyError(f"no calibrated table for video height {video_height} (the reference would hit AttributeError later)")
+        mag_ratios = tables()["hunyuan_720p" if video_height == 720 else "hunyuan_544p"]
+    mr = np.asarray(mag_ratios, dtype=np.float64)
+    if len(mr) != infer_steps:
+        mr = nearest_interp(mr, infer_steps)
+    cls.mag_ratios, cls.retention_ratio = mr, retention_ratio
+    cls.forward = magcache_hunyuan_forward
+    cls.accumulated_ratio, cls.accumulated_err, cls.accumulated_steps = 1, 0, 0
     return transformer
 
 

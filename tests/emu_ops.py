@@ -155,6 +155,11 @@ def cast_into(src, dst):
     return dst
 
 
+def colmean(x):
+    _count()
+    return (x.to(F32).sum(0, keepdim=True).to(BF).to(F32) / torch.tensor(float(x.shape[0])).to(BF).to(F32)).to(BF)
+
+
 def silu(x, out=None):
     y = F.silu(x.to(F32)).to(BF)
     if out is None:

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import magcache_b200 as mc
-from magcache_b200 import flux as flux_mod
+from magcache_b200 import mmdit as flux_mod
 from magcache_b200 import patch as patch_mod
 from oracle import flux_ref as fr
 
