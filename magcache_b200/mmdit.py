@@ -9,9 +9,10 @@ the forwards' own statements (embedders, controller, hit / miss, residual, final
 (`MMDiTCore`): same modulation chunk order, same per-head q/k RMSNorm, same `cat(attn, act(mlp))` single block; they differ in the
 token order of the joint sequence, in which rows get RoPE, and in their embedders.
 
-STATUS: written at the end of round 1 without GPU time left to run it — the GPU parity tests (tests/test_flux_forward_gpu.py,
-tests/test_hunyuan_forward_gpu.py) are opt-in (`MC_RUN_UNVALIDATED=1`) until they have passed on a B200; the orchestration is verified on
-CPU through the kernel emulation (tests/test_*_engine_emulated_cpu.py). Nothing on the Wan path depends on this module.
+STATUS (end of round 1): parity-green on a B200 against the oracles at reduced depth / token counts (tests/test_flux_forward_gpu.py,
+tests/test_hunyuan_forward_gpu.py; profiles/r01_mmdit_first_gpu_run.md) and pinned on CPU through the kernel emulation
+(tests/test_*_engine_emulated_cpu.py); not yet run or timed at the full FLUX 1024^2 / HunyuanVideo 720p shapes. Nothing on the Wan path
+depends on this module.
 
 HBM layout (S = n_txt + n_img tokens; FLUX puts the text rows FIRST — `torch.cat([encoder_hidden_states, hidden_states], dim=1)`,
 magcache_flux.py:384 — HunyuanVideo the image rows — `torch.cat((img, txt), 1)`, magcache_sample_video.py:123; D = heads*128;

@@ -1,9 +1,10 @@
 """FLUX MMDiT engine on the GPU: the new kernels (per-head RMSNorm + RoPE, SiLU, the bf16 gated-residual and SiLU GEMM epilogues) against
 torch, and `magcache_flux_forward` against the oracle restatement of MagCache4FLUX/magcache_flux.py:234-440.
 
-OPT-IN: this engine was written after round 1's GPU budget was spent; its orchestration is verified on CPU through the kernel
-emulation (tests/test_flux_engine_emulated_cpu.py) but these tests have not run on a B200 yet. `MC_RUN_UNVALIDATED=1 pytest -m gpu`
-enables them; once green, drop the skip."""
+First B200 run (end of round 1, gpurun_out/unvalidated.log -> profiles/r01_mmdit_first_gpu_run.md): forward and loop tests green
+(ours vs oracle 4.8e-3 rel-L2, ours vs fp64 8.083e-2 against the bf16 oracle's own 8.081e-2), epilogue / SiLU tests green; the
+per-head RMSNorm + RoPE unit test tripped on its tolerance only (4e-6 of the elements beyond one output ulp where the rotation cancels);
+its bound is now the rigorous one and it stays opt-in (`MC_RUN_UNVALIDATED=1`) until it has been re-run."""
 import copy
 import math
 import os
@@ -11,8 +12,8 @@ import os
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MC_RUN_UNVALIDATED") != "1", reason="FLUX engine not yet validated on a GPU (set MC_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
+unvalidated = pytest.mark.skipif(os.environ.get("MC_RUN_UNVALIDATED") != "1", reason="tolerance changed after its only GPU run (set MC_RUN_UNVALIDATED=1)")
 DEV = "cuda"
 
 
@@ -25,6 +26,7 @@ def _ops():
     return ops
 
 
+@unvalidated
 def test_rmsnorm_head_rope_vs_torch():
     import emu_ops
     ops = _ops()
@@ -41,8 +43,11 @@ def test_rmsnorm_head_rope_vs_torch():
             got = x.clone()
             ops.rmsnorm_head_rope_(got, w, heads, table)
             d = (got.float().cpu() - want.float()).abs()
-            # rsqrtf vs torch.rsqrt can flip a bf16 rounding: allow one bf16 ulp on a few elements, nothing more
-            assert float((d > 2.0 ** -7 * want.float().abs().clamp_min(2.0 ** -6)).float().mean()) == 0.0
+            # rsqrtf vs torch.rsqrt can flip the bf16 rounding of a normalised value by one ulp (2^-8 relative); through the rotation
+            # that is at most 2^-8 (|re| + |im|) + the output rounding < 2^-7 * |(re, im)| — bounded by the PAIR norm, not by the
+            # (possibly cancelled) output element. Twice that as the hard limit, and such flips must stay rare.
+            pair = want.float().view(rows, heads, 64, 2).norm(dim=-1, keepdim=True).expand(rows, heads, 64, 2).reshape(rows, W)
+            assert bool((d <= 2.0 ** -6 * pair + 1e-6).all()), float((d / (pair + 1e-6)).max())
             assert float((d > 0).float().mean()) < 0.02
 
 
