@@ -500,3 +500,100 @@ class HunyuanEngine(MMDiTCore):
         c = w.out_channels
         o = o.view(1, t, hh, ww, c, 1, 2, 2)
         return torch.einsum("nthwcopq->nctohpwq", o).reshape(1, c, t, 2 * hh, 2 * ww)  # pure data movement
+
+
+# ======================================================================================================================
+# Synthetic weights created directly on the device (benchmarks: a FLUX.1-dev / HunyuanVideo-sized nn.Module does not fit a CPU box)
+# ======================================================================================================================
+def _rand_block_weights(D, dev, g, keys_prefix=("", "c")):
+    import math
+
+    def xav(o, i, s=1.0):
+        return ((torch.rand(o, i, device=dev, generator=g) * 2 - 1) * (s * math.sqrt(6.0 / (i + o)))).bfloat16()
+
+    def bias(n):
+        return (0.02 * torch.randn(n, device=dev, generator=g)).bfloat16().float()
+
+    def nw():
+        return (1 + 0.1 * torch.randn(128, device=dev, generator=g)).bfloat16().float()
+
+    d = {}
+    for k in keys_prefix:
+        d.update({f"{k}qk_w": xav(2 * D, D), f"{k}qk_b": bias(2 * D), f"{k}v_w": xav(D, D), f"{k}v_b": bias(D), f"{k}o_w": xav(D, D), f"{k}o_b": bias(D),
+                  f"{k}nq": nw(), f"{k}nk": nw(), f"{k}ff1_w": xav(4 * D, D), f"{k}ff1_b": bias(4 * D), f"{k}ff2_w": xav(D, 4 * D), f"{k}ff2_b": bias(D)})
+    return d, xav, bias, nw
+
+
+def _random_stack(w, D, n_double, n_single, dev, g):
+    """Double / single block weights + the stacked modulation matrix (rows: 12D per double block, 3D per single block, 2D final)."""
+    off = 0
+    for _ in range(n_double):
+        d, xav, bias, nw = _rand_block_weights(D, dev, g)
+        d["ada"], d["ada_c"] = off, off + 6 * D
+        off += 12 * D
+        w.double.append(d)
+    for _ in range(n_single):
+        _, xav, bias, nw = _rand_block_weights(D, dev, g, keys_prefix=())
+        w.single.append({"ada": off, "qk_w": xav(2 * D, D), "qk_b": bias(2 * D), "v_w": xav(D, D), "v_b": bias(D), "nq": nw(), "nk": nw(),
+                         "mlp_w": xav(4 * D, D), "mlp_b": bias(4 * D), "out_w": xav(D, 5 * D), "out_b": bias(D)})
+        off += 3 * D
+    w.ada_out = off
+    off += 2 * D
+    _, xav, bias, nw = _rand_block_weights(D, dev, g, keys_prefix=())
+    w.ada_w, w.ada_b, w.ada_rows = xav(off, D, 0.3), bias(off), off
+    return xav, bias, nw
+
+
+def random_flux_weights(dev, heads=24, num_layers=19, num_single_layers=38, in_channels=64, joint_dim=4096, pooled_dim=768, guidance=True, seed=0):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    w = FluxWeights()
+    w.heads, w.head_dim, w.dim = heads, 128, heads * 128
+    D = w.dim
+    w.in_channels, w.joint_dim, w.pooled_dim, w.guidance, w.device = in_channels, joint_dim, pooled_dim, guidance, dev
+    xav, bias, _ = _random_stack(w, D, num_layers, num_single_layers, dev, g)
+    w.x_w, w.x_b, w.ctx_w, w.ctx_b = xav(D, in_channels), bias(D), xav(D, joint_dim), bias(D)
+    w.t_mlp = (xav(D, 256), bias(D), xav(D, D), bias(D))
+    w.p_mlp = (xav(D, pooled_dim), bias(D), xav(D, D), bias(D))
+    w.g_mlp = (xav(D, 256), bias(D), xav(D, D), bias(D)) if guidance else None
+    w.out_w, w.out_b = xav(in_channels, D), bias(in_channels)
+    return w
+
+
+def random_hunyuan_weights(dev, heads=24, double_depth=20, single_depth=40, in_channels=16, text_dim=4096, pooled_dim=768, guidance=True, seed=0):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    w = HunyuanWeights()
+    w.heads, w.dim = heads, heads * 128
+    D = w.dim
+    w.in_channels, w.out_channels, w.guidance, w.text_dim, w.pooled_dim, w.device = in_channels, in_channels, guidance, text_dim, pooled_dim, dev
+    xav, bias, nw = _random_stack(w, D, double_depth, single_depth, dev, g)
+    w.patch_w, w.patch_b = xav(D, in_channels * 4), bias(D)
+    w.t_mlp = (xav(D, 256), bias(D), xav(D, D), bias(D))
+    w.p_mlp = (xav(D, pooled_dim), bias(D), xav(D, D), bias(D))
+    w.g_mlp = (xav(D, 256), bias(D), xav(D, D), bias(D)) if guidance else None
+    w.r_in_w, w.r_in_b = xav(D, text_dim), bias(D)
+    w.r_t_mlp = (xav(D, 256), bias(D), xav(D, D), bias(D))
+    w.r_c_mlp = (xav(D, text_dim), bias(D), xav(D, D), bias(D))
+    for _ in range(2):
+        w.refiner.append({"n1_w": nw().new_ones(D) + 0.1 * torch.randn(D, device=dev, generator=g), "n1_b": bias(D),
+                          "n2_w": nw().new_ones(D) + 0.1 * torch.randn(D, device=dev, generator=g), "n2_b": bias(D),
+                          "qk_w": xav(2 * D, D), "qk_b": bias(2 * D), "v_w": xav(D, D), "v_b": bias(D), "nq": nw(), "nk": nw(),
+                          "o_w": xav(D, D), "o_b": bias(D), "f1_w": xav(4 * D, D), "f1_b": bias(4 * D), "f2_w": xav(D, 4 * D), "f2_b": bias(D)})
+    w.r_ada_w, w.r_ada_b = xav(4 * D, D, 0.3), bias(4 * D)
+    w.out_w, w.out_b = xav(in_channels * 4, D), bias(in_channels * 4)
+    return w
+
+
+class MMDiTHandle:
+    """Stand-in for the pipeline's transformer object when the weights do not come from an nn.Module (benchmarks): carries the engine
+    and receives the reference's class attributes through `init_magcache_flux` / `init_magcache_hunyuan`."""
+
+    def __new__(cls, engine):
+        sub = type("MMDiTHandle", (cls,), {})
+        return object.__new__(sub)
+
+    def __init__(self, engine):
+        key = "_mc_flux_engine" if isinstance(engine, FluxEngine) else "_mc_hunyuan_engine"
+        object.__setattr__(self, key, engine)
+
+    def __call__(self, *a, **k):
+        return self.forward(*a, **k)
