@@ -59,10 +59,7 @@ def main():
 
     for i in range(3):  # warm-up inside the retention window, then restart the schedule
         step(i)
-    model.cnt = 0
-    type(model).accumulated_ratio, type(model).accumulated_err, type(model).accumulated_steps = 1, 0, 0
-    for a in ("accumulated_ratio", "accumulated_err", "accumulated_steps"):
-        model.__dict__.pop(a, None)
+    mc.reset_magcache(model)
     n0 = ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
