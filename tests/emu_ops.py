@@ -213,3 +213,32 @@ def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1
         out.copy_(u)
         return out
     return u
+
+
+def cfg_combine(cond, uncond, guide_scale, out=None):
+    r = uncond + torch.tensor(guide_scale, dtype=F32) * (cond - uncond)
+    _count()
+    if out is None:
+        return r
+    out.copy_(r)
+    return out
+
+
+def cfg_step(cond, uncond, guide_scale, x, coef_v, coef_x=1.0, hist=(), coef_h=(), sigma=0.0, out=None, x0_out=None):
+    f = lambda a: torch.tensor(a, dtype=F32)  # noqa: E731
+    v = uncond + f(guide_scale) * (cond - uncond)
+    acc = f(coef_x) * x + f(coef_v) * v
+    for h, c in zip(hist, coef_h):
+        acc = acc + f(c) * h
+    if x0_out is not None:
+        x0_out.copy_(x - f(sigma) * v)
+    _count()
+    if out is None:
+        return acc
+    out.copy_(acc)
+    return out
+
+
+def rel_l1(cur, prev):
+    _count()
+    return ((cur - prev).abs().mean() / prev.abs().mean()).item()
