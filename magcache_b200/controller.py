@@ -84,8 +84,19 @@ class AttrController:
         else:
             o.accumulated_ratio, o.accumulated_err, o.accumulated_steps = st.accumulated_ratio[0], st.accumulated_err[0], st.accumulated_steps[0]
         if with_cnt:
-            o.cnt = st.cnt
+            self._set_cnt(o, st.cnt)
         del cls
+
+    @staticmethod
+    def _set_cnt(o, value):
+        """`self.cnt += 1`. Wan2.2 / Qwen-Image install `cnt = torch.tensor(0)` on the CLASS (MagCache4Wan2.2/magcache_generate.py:342): the
+        in-place add mutates that one tensor, which is how the high-noise and the low-noise expert (two instances of one class) share a
+        counter. Keep that: a tensor counter is updated in place, anything else is rebound on the instance like a Python int."""
+        cur = getattr(type(o), "cnt", None)
+        if hasattr(cur, "fill_") and "cnt" not in o.__dict__:
+            cur.fill_(value)
+        else:
+            o.cnt = value
 
     def decide(self, o):
         cfg = self._config(o)
@@ -102,6 +113,6 @@ class AttrController:
         if st.cnt == 0 and self.kw["branches"] == 2:
             # end of video: the reference REBINDS fresh lists (magcache_generate.py:308-311)
             o.accumulated_ratio, o.accumulated_err, o.accumulated_steps = [1.0, 1.0], [0.0, 0.0], [0, 0]
-            o.cnt = 0
+            self._set_cnt(o, 0)
         else:
             self._store(o, st, with_cnt=True)

@@ -57,8 +57,8 @@ def _controller(self):
     return c
 
 
-def _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=True, vace_context=None, vace_scale=1.0):
-    if getattr(self, "model_type", "t2v") == "i2v":
+def _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=True, vace_context=None, vace_scale=1.0, require_clip=True):
+    if getattr(self, "model_type", "t2v") == "i2v" and require_clip:
         assert clip_fea is not None and y is not None  # magcache_generate.py:226-227
     if len(x) != 1 or len(context) != 1 or (y is not None and len(y) != 1):
         raise NotImplementedError("magcache_b200: one sample per call (the reference's caller passes [latents], wan_magcache.py:296-299)")
@@ -134,6 +134,54 @@ def magcache_vace_calibration(self, x, t, vace_context, context, seq_len, vace_c
     r"""MagCache4Wan2.1/magcache_generate.py:314-436: `magcache_calibration` with the control branch."""
     return _calibrate(self, _stage(self, x, t, context, seq_len, None, None, pad_ok=False, vace_context=vace_context,
                                    vace_scale=vace_context_scale))
+
+
+def magcache_wan22_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
+    r"""MagCache4Wan2.2/magcache_generate.py:209-336 for the A14B experts (T2V and I2V) on the Wan engine: the Wan2.1 forward with the
+    two-expert skip windows (`split_step`, `mode`, :294-303) and a counter shared by the high-noise and the low-noise model — two
+    instances of one class, one engine (weights) each, one controller state and one residual cache between them (:340-362).
+    Wan2.2 broadcasts `t` to every token (:263-264); only a uniform timestep is built, i.e. not TI2V-5B, whose first-frame tokens carry
+    t = 0 (per-token modulation)."""
+    if getattr(self, "model_type", "t2v") == "i2v":
+        assert y is not None  # :239-240
+    if t.dim() != 1:
+        if not bool((t == t.reshape(-1)[0]).all()):
+            raise NotImplementedError("magcache_b200: per-token timesteps (Wan2.2 TI2V-5B) are not built; A14B experts pass one t")
+        t = t.reshape(-1)[:1]
+    eng = _stage(self, x, t, context, seq_len, None, y, require_clip=False)
+    ctrls = self.__dict__.setdefault("_mc_ctrls", {})
+    fam = "wan2.2-i2v" if getattr(self, "mode", "t2v") == "i2v" else "wan2.2-t2v"
+    if fam not in ctrls:
+        from .config import FAMILIES
+        ctrls[fam] = AttrController(FAMILIES[fam])
+    ctrl = ctrls[fam]
+    slot = int(self.cnt) % 2
+    skip_forward = ctrl.decide(self)  # :290-317
+    _sync_slot_in(self, eng, slot)    # the other expert's residual arrives through the shared class-level list
+    out = eng.forward("hit" if skip_forward else "miss", slot)
+    self.residual_cache[slot] = eng.res[slot].view(1, *eng.res[slot].shape)  # :324
+    ctrl.advance(self)  # :328-334
+    return [out]
+
+
+def init_magcache_wan22(model, mag_ratios, sample_steps, thresh=0.06, K=2, retention_ratio=0.2, split_steps=None, mode="t2v"):
+    """`init_magcache(model, mag_ratios, args, split_steps, mode)` of MagCache4Wan2.2/magcache_generate.py:340-362: patches the CLASS the
+    two experts share. `mag_ratios`: the list without its `[1.0]*2` prefix like the script passes it, or a key of `tables()` (which
+    already carries the prefix)."""
+    import numpy as np
+    cls = model.__class__
+    cls.forward = magcache_wan22_forward
+    cls.cnt = torch.tensor(0)
+    cls.num_steps = sample_steps * 2
+    cls.split_step = split_steps * 2 if split_steps else None
+    cls.mode = mode
+    cls.magcache_thresh, cls.K = thresh, K
+    cls.accumulated_err, cls.accumulated_steps, cls.accumulated_ratio = [0.0, 0.0], [0, 0], [1.0, 1.0]
+    cls.retention_ratio = retention_ratio
+    cls.residual_cache = [None, None]
+    mr = tables()[mag_ratios] if isinstance(mag_ratios, str) else np.array([1.0] * 2 + list(mag_ratios))
+    cls.mag_ratios = interp_cfg(mr, sample_steps)  # :357-361
+    return model
 
 
 def magcache_calibration(self, x, t, context, seq_len, clip_fea=None, y=None):

@@ -83,6 +83,8 @@ class WanWeights:
         dims = WanDims(dim=D, ffn_dim=m.ffn_dim, num_heads=m.num_heads, num_layers=len(m.blocks), in_dim=m.patch_embedding.in_channels,
                        out_dim=m.out_dim, freq_dim=m.freq_dim, text_dim=m.text_embedding[0].in_features, text_len=m.text_len,
                        eps=getattr(m, "eps", 1e-6), model_type=getattr(m, "model_type", "t2v"))
+        if dims.model_type == "i2v" and not hasattr(m, "img_emb"):
+            dims.model_type = "t2v"  # Wan2.2 I2V-A14B: `y` under the latent channels (in_dim 36) but no CLIP tokens, plain text cross-attention
         if dims.model_type not in ("t2v", "i2v", "vace"):
             raise NotImplementedError(f"model_type {dims.model_type!r}: t2v, i2v and vace forwards are built")
         if dims.head_dim != 128:
