@@ -102,7 +102,7 @@ def test_sharded_self_attention_gather_and_reductions_world2():
             assert stats == [3.0, 4.0, 6.0, float(N)]
 
 
-def _engine_worker(rank, world, initfile, results):
+def _engine_worker(rank, world, initfile, results, kind="t2v"):
     """The REAL engine code path of a token-sharded forward (WanEngine with shard_world=2: local projections, async K/V row
     all-gathers, V transpose, attention over all keys, partial-output all-reduce in the head) with the kernels emulated on CPU
     (tests/emu_ops.py) and gloo as the collective backend."""
@@ -118,20 +118,30 @@ def _engine_worker(rank, world, initfile, results):
         patch_mod.ops = emu_ops
         torch.Tensor.is_cuda = property(lambda self: True)
         os.environ["MC_GRAPHS"] = "0"
-        model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=8).init_synthetic(3)
+        extra_model = {"i2v": dict(in_dim=36, model_type="i2v", clip_dim=64), "vace": dict(model_type="vace", vace_in_dim=24)}.get(kind, {})
+        model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=8, **extra_model).init_synthetic(3)
         g = torch.Generator().manual_seed(7)
-        lat, ctx = torch.randn(16, *[GRID[0], 2 * GRID[1], 2 * GRID[2]], generator=g), torch.randn(5, 64, generator=g)
+        shape = [GRID[0], 2 * GRID[1], 2 * GRID[2]]
+        lat, ctx = torch.randn(16, *shape, generator=g), torch.randn(5, 64, generator=g)
+        extra = {}
+        if kind == "i2v":
+            extra = dict(clip_fea=torch.randn(1, 257, 64, generator=g), y=[torch.randn(20, *shape, generator=g)])
+        if kind == "vace":
+            extra = dict(vace_context=[torch.randn(24, *shape, generator=g)])
         table = [1.0] * 8
         outs = {}
         for name, kw in (("single", {}), ("sharded", dict(shard_world=world, shard_rank=rank))):
             m = type("M", (), {})()
-            m.model_type = "t2v"
+            m.model_type = kind
             object.__setattr__(m, "_mc_engine", mc.WanEngine(mc.WanWeights.from_module(model, torch.device("cpu")), **kw))
             mc.init_magcache(m, 4, thresh=10.0, K=3, retention_ratio=0.25, mag_ratios=table)
             seq = []
             with torch.no_grad():
                 for i in range(4):  # miss, miss, hit, hit
-                    seq.append(m.forward([lat], torch.tensor([500.0]), [ctx], N)[0].clone())
+                    if kind == "vace":
+                        seq.append(m.forward([lat], torch.tensor([500.0]), extra["vace_context"], [ctx], N)[0].clone())
+                    else:
+                        seq.append(m.forward([lat], torch.tensor([500.0]), [ctx], N, **extra)[0].clone())
             outs[name] = (seq, m._mc_engine, m.residual_cache)
         eng = outs["sharded"][1]
         sh = eng.shard
@@ -144,11 +154,12 @@ def _engine_worker(rank, world, initfile, results):
         dist.destroy_process_group()
 
 
-def test_sharded_engine_equals_single_engine_world2():
+@pytest.mark.parametrize("kind", ["t2v", "i2v", "vace"])
+def test_sharded_engine_equals_single_engine_world2(kind):
     with tempfile.TemporaryDirectory() as d:
         mgr = mp.get_context("spawn").Manager()
         results = mgr.dict()
-        mp.spawn(_engine_worker, args=(2, os.path.join(d, "init"), results), nprocs=2, join=True)
+        mp.spawn(_engine_worker, args=(2, os.path.join(d, "init"), results, kind), nprocs=2, join=True)
         assert set(results.keys()) == {0, 1}
         for r in (0, 1):
             errs, cache_err, shape, rng = results[r]
