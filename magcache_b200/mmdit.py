@@ -241,6 +241,22 @@ class MMDiTCore:
         return self.head(x)
 
 
+    def calibrate(self):
+        """The calibration twin of `forward("miss")` (magcache_flux.py:21-231; magcache_sample_video.py:163-290): always runs the block
+        stack; returns (head output, (norm_ratio, norm_std, cos_dis) against the previous residual or None on the first call). The
+        statistics come from the fused fp32/fp64 reduction kernel — finer than the reference's bf16 tensor ops, which quantise them to
+        multiples of 2^-8 (the shipped FLUX table is visibly bf16-quantised)."""
+        x0 = self.prologue()
+        self.hs[self.img].copy_(x0)
+        x = self.run_blocks()
+        new = self.hit
+        ops.residual_sub(x.contiguous(), x0, out=new)
+        stats = ops.residual_stats(new, self.res) if self.res_valid else None
+        self.res, self.hit = new, self.res
+        self.res_valid = True
+        return self.head(x), stats
+
+
 class FluxEngine(MMDiTCore):
     txt_first = True
 

@@ -335,11 +335,7 @@ def magcache_flux_forward(self, hidden_states, encoder_hidden_states=None, poole
         raise NotImplementedError("magcache_b200: joint_attention_kwargs / ControlNet residuals are not built for the FLUX engine")
     if not hidden_states.is_cuda:
         raise RuntimeError("magcache_b200: hidden_states must be CUDA tensors (no CPU path)")
-    eng = self.__dict__.get("_mc_flux_engine")
-    if eng is None:
-        from .mmdit import FluxEngine, FluxWeights
-        eng = FluxEngine(FluxWeights.from_module(self, hidden_states.device))
-        object.__setattr__(self, "_mc_flux_engine", eng)
+    eng = _flux_engine(self, hidden_states)
     if txt_ids.ndim == 3:  # :305-316 (deprecated 3-D ids)
         txt_ids = txt_ids[0]
     if img_ids.ndim == 3:
@@ -364,6 +360,63 @@ def magcache_flux_forward(self, hidden_states, encoder_hidden_states=None, poole
     if not return_dict:
         return (output,)
     return _Sample(output)
+
+
+def _flux_engine(self, hidden_states):
+    eng = self.__dict__.get("_mc_flux_engine")
+    if eng is None:
+        from .mmdit import FluxEngine, FluxWeights
+        eng = FluxEngine(FluxWeights.from_module(self, hidden_states.device))
+        object.__setattr__(self, "_mc_flux_engine", eng)
+    return eng
+
+
+def magcache_flux_calibration(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
+                              txt_ids=None, guidance=None, joint_attention_kwargs=None, controlnet_block_samples=None,
+                              controlnet_single_block_samples=None, return_dict=True, controlnet_blocks_repeat=False):
+    r"""MagCache4FLUX/magcache_flux.py:21-231: every call runs the block stack and, from the second call on, records the token-mean
+    magnitude ratio, its std and the cosine distance to the previous residual (`norm_ratio / norm_std / cos_dis`, rounded to 5 places);
+    the lists are printed on the last call of a generation and cleared at the wrap (:207-221)."""
+    if joint_attention_kwargs or controlnet_block_samples is not None or controlnet_single_block_samples is not None:
+        raise NotImplementedError("magcache_b200: joint_attention_kwargs / ControlNet residuals are not built for the FLUX engine")
+    if not hidden_states.is_cuda:
+        raise RuntimeError("magcache_b200: hidden_states must be CUDA tensors (no CPU path)")
+    eng = _flux_engine(self, hidden_states)
+    eng.stage_inputs(hidden_states, encoder_hidden_states, pooled_projections, timestep, guidance,
+                     img_ids[0] if img_ids.ndim == 3 else img_ids, txt_ids[0] if txt_ids.ndim == 3 else txt_ids)
+    if self.cnt == 0:
+        eng.res_valid = False  # `if self.cnt>=1` (:199): the first call of a generation has nothing to compare with
+    out, stats = eng.calibrate()
+    if self.cnt >= 1 and stats is not None:
+        norm_ratio, norm_std, cos_dis = stats
+        self.norm_ratio.append(round(norm_ratio, 5))
+        self.norm_std.append(round(norm_std, 5))
+        self.cos_dis.append(round(cos_dis, 5))
+        print(f"time: {self.cnt}, norm_ratio: {norm_ratio}, norm_std: {norm_std}, cos_dis: {cos_dis}")
+    self.previous_residual = eng.res.view(1, *eng.res.shape)
+    if self.cnt >= self.num_steps - 1:
+        print("norm ratio")
+        print(self.norm_ratio)
+        print("norm std")
+        print(self.norm_std)
+        print("cos_dis")
+        print(self.cos_dis)
+    self.cnt += 1
+    if self.cnt >= self.num_steps:
+        self.cnt = 0
+        self.norm_ratio, self.norm_std, self.cos_dis = [], [], []
+    output = out.view(1, *out.shape)
+    return _Sample(output) if return_dict else (output,)
+
+
+def init_magcache_flux_calibration(transformer, num_inference_steps=28):
+    """magcache_flux.py:446-458 with `FluxTransformer2DModel.forward = magcache_calibration`."""
+    cls = transformer.__class__
+    cls.forward = magcache_flux_calibration
+    cls.cnt, cls.num_steps = 0, num_inference_steps
+    cls.norm_ratio, cls.norm_std, cls.cos_dis = [], [], []
+    cls.previous_residual = None
+    return transformer
 
 
 def init_magcache_flux(transformer, num_inference_steps=28, thresh=0.24, K=5, retention_ratio=0.1, mag_ratios=None, table="flux_dev"):
@@ -416,6 +469,49 @@ def magcache_hunyuan_forward(self, x, t, text_states=None, text_mask=None, text_
     if return_dict:
         return {"x": img}
     return img
+
+
+def magcache_hunyuan_calibration(self, x, t, text_states=None, text_mask=None, text_states_2=None, freqs_cos=None, freqs_sin=None,
+                                 guidance=None, return_dict=True):
+    r"""MagCache4HunyuanVideo/magcache_sample_video.py:163-290: the calibration twin (statistics from the second call on, lists printed
+    from call 49 on — hard-coded upstream, :266 — and a counter that is never wrapped, :281)."""
+    if not x.is_cuda:
+        raise RuntimeError("magcache_b200: x must be a CUDA tensor (no CPU path)")
+    eng = self.__dict__.get("_mc_hunyuan_engine")
+    if eng is None:
+        from .mmdit import HunyuanEngine, HunyuanWeights
+        eng = HunyuanEngine(HunyuanWeights.from_module(self, x.device))
+        object.__setattr__(self, "_mc_hunyuan_engine", eng)
+    eng.stage_inputs(x, t, text_states, text_mask, text_states_2, freqs_cos, freqs_sin, guidance)
+    if self.cnt == 0:
+        eng.res_valid = False
+    img, stats = eng.calibrate()
+    if self.cnt >= 1 and stats is not None:
+        norm_ratio, norm_std, cos_dis = stats
+        self.norm_ratio.append(round(norm_ratio, 5))
+        self.norm_std.append(round(norm_std, 5))
+        self.cos_dis.append(round(cos_dis, 5))
+        print(f"time: {self.cnt}, norm_ratio: {norm_ratio}, norm_std: {norm_std}, cos_dis: {cos_dis}")
+    self.residual_cache = eng.res.view(1, *eng.res.shape)
+    if self.cnt >= 49:
+        print("norm ratio")
+        print(self.norm_ratio)
+        print("norm std")
+        print(self.norm_std)
+        print("cos_dis")
+        print(self.cos_dis)
+    self.cnt += 1
+    return {"x": img} if return_dict else img
+
+
+def init_magcache_hunyuan_calibration(transformer, infer_steps=50):
+    """magcache_sample_video.py:307-314 with `forward = magcache_calibration` (:324)."""
+    cls = transformer.__class__
+    cls.forward = magcache_hunyuan_calibration
+    cls.cnt, cls.num_steps = 0, infer_steps
+    cls.norm_ratio, cls.norm_std, cls.cos_dis = [], [], []
+    cls.residual_cache = None
+    return transformer
 
 
 def init_magcache_hunyuan(transformer, infer_steps=50, thresh=0.24, K=6, retention_ratio=0.2, video_height=720, mag_ratios=None):

@@ -322,6 +322,41 @@ def magcache_forward(self, hidden_states, encoder_hidden_states=None, pooled_pro
     return types.SimpleNamespace(sample=output)
 
 
+def magcache_calibration(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None, txt_ids=None,
+                         guidance=None, joint_attention_kwargs=None, controlnet_block_samples=None, controlnet_single_block_samples=None,
+                         return_dict=True, controlnet_blocks_repeat=False):
+    """MagCache4FLUX/magcache_flux.py:21-231 (same omissions as magcache_forward); the statistics are bf16 tensor ops like upstream."""
+    hidden_states = self.x_embedder(hidden_states)
+    timestep = timestep.to(hidden_states.dtype) * 1000
+    guidance = guidance.to(hidden_states.dtype) * 1000 if guidance is not None else None
+    temb = self.time_text_embed(timestep, guidance, pooled_projections)
+    encoder_hidden_states = self.context_embedder(encoder_hidden_states)
+    image_rotary_emb = self.pos_embed(torch.cat((txt_ids, img_ids), dim=0))
+    ori_hidden_states = hidden_states
+    for block in self.transformer_blocks:
+        encoder_hidden_states, hidden_states = block(hidden_states=hidden_states, encoder_hidden_states=encoder_hidden_states, temb=temb,
+                                                     image_rotary_emb=image_rotary_emb)
+    hidden_states = torch.cat([encoder_hidden_states, hidden_states], dim=1)
+    for block in self.single_transformer_blocks:
+        hidden_states = block(hidden_states=hidden_states, temb=temb, image_rotary_emb=image_rotary_emb)
+    hidden_states = hidden_states[:, encoder_hidden_states.shape[1]:, ...]
+    cur_residual = hidden_states - ori_hidden_states                                   # :197
+    if self.cnt >= 1:                                                                  # :198-205
+        norm_ratio = ((cur_residual.norm(dim=-1) / self.previous_residual.norm(dim=-1)).mean()).item()
+        norm_std = (cur_residual.norm(dim=-1) / self.previous_residual.norm(dim=-1)).std().item()
+        cos_dis = (1 - F.cosine_similarity(cur_residual, self.previous_residual, dim=-1, eps=1e-8)).mean().item()
+        self.norm_ratio.append(round(norm_ratio, 5))
+        self.norm_std.append(round(norm_std, 5))
+        self.cos_dis.append(round(cos_dis, 5))
+    self.previous_residual = cur_residual
+    output = self.proj_out(self.norm_out(hidden_states, temb))
+    self.cnt += 1
+    if self.cnt >= self.num_steps:                                                     # :217-221
+        self.cnt = 0
+        self.norm_ratio, self.norm_std, self.cos_dis = [], [], []
+    return types.SimpleNamespace(sample=output) if return_dict else (output,)
+
+
 def install_magcache(model_cls, mag_ratios, num_steps, thresh=0.24, K=5, retention_ratio=0.1):
     """MagCache4FLUX/magcache_flux.py:446-471."""
     from .controller_ref import nearest_interp

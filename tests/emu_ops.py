@@ -242,3 +242,9 @@ def cfg_step(cond, uncond, guide_scale, x, coef_v, coef_x=1.0, hist=(), coef_h=(
 def rel_l1(cur, prev):
     _count()
     return ((cur - prev).abs().mean() / prev.abs().mean()).item()
+
+
+def residual_stats(r_cur, r_prev, denom_eps=0.0):
+    from oracle.controller_ref import calibration_stats
+    _count(2)
+    return calibration_stats(r_cur.to(F32)[None], r_prev.to(F32)[None], denom_eps)

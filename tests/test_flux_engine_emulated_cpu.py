@@ -109,3 +109,35 @@ def test_flux_forward_refuses_unbuilt_side_paths(emulated):
         ours(hs, enc, pooled, torch.tensor([0.5]), img_ids, txt_ids, torch.tensor([3.5]), controlnet_block_samples=[hs])
     with pytest.raises(ValueError):
         ours(hs, enc, pooled, torch.tensor([0.5]), img_ids, txt_ids, None)  # guidance-distilled model without guidance
+
+
+def test_flux_calibration_twin(emulated, capsys):
+    """`magcache_flux_calibration` (magcache_flux.py:21-231): same outputs as the oracle twin, statistics from the second call on (finer than
+    the reference's bf16-quantised ones: compared at 2e-2), lists printed on the last call and cleared at the wrap."""
+    model = _model(True, seed=2)
+    hs, enc, pooled, img_ids, txt_ids = _inputs(2)
+    steps = 4
+    ref_m = copy.deepcopy(model)
+    ref_m.__class__ = type("RefFluxC", (ref_m.__class__,), {})
+    type(ref_m).forward = fr.magcache_calibration
+    type(ref_m).cnt, type(ref_m).num_steps = 0, steps
+    type(ref_m).norm_ratio, type(ref_m).norm_std, type(ref_m).cos_dis, type(ref_m).previous_residual = [], [], [], None
+    ours = copy.deepcopy(model)
+    ours.__class__ = type("OurFluxC", (ours.__class__,), {})
+    mc.init_magcache_flux_calibration(ours, steps)
+    ratios_ref, ratios_ours = [], []
+    with torch.no_grad():
+        for i in range(steps):
+            t = torch.tensor([1.0 - i / steps])
+            x = hs * (1.0 - 0.1 * i)
+            a = ref_m(x, enc, pooled, t, img_ids, txt_ids, torch.tensor([3.5]), return_dict=False)[0]
+            if i < steps - 1:
+                ratios_ref = list(ref_m.norm_ratio)
+            b = ours(x, enc, pooled, t, img_ids, txt_ids, torch.tensor([3.5]), return_dict=False)[0]
+            if i < steps - 1:
+                ratios_ours = list(ours.norm_ratio)
+            assert rel_l2(b, a) <= 0.15
+    assert len(ratios_ref) == len(ratios_ours) == steps - 2
+    for a, b in zip(ratios_ours, ratios_ref):
+        assert abs(a - b) <= 2e-2 * abs(b), (ratios_ours, ratios_ref)
+    assert ours.cnt == 0 and ours.norm_ratio == [] and "norm ratio" in capsys.readouterr().out

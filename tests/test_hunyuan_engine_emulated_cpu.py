@@ -108,3 +108,32 @@ def test_hunyuan_forward_argument_checks(emulated):
         ours(x, torch.tensor([500.0]), txt, bad, pooled, cos, sin, torch.tensor([6000.0]))
     with pytest.raises(KeyError):
         mc.init_magcache_hunyuan(ours, 50, video_height=480)
+
+
+def test_hunyuan_calibration_twin(emulated, capsys):
+    """`magcache_hunyuan_calibration` (magcache_sample_video.py:163-290): always computes (outputs equal the cache-less forward), statistics
+    from the second call on against the reference expressions on the two residuals, counter never wrapped (:281)."""
+    from oracle.controller_ref import calibration_stats
+    model = _model(seed=3)
+    x, txt, mask, pooled, cos, sin = _inputs(3)
+    ref_m = copy.deepcopy(model)
+    ref_m.__class__ = type("RefHYC", (ref_m.__class__,), {})
+    hr.install_magcache(type(ref_m), [1.0] * 50, 50, thresh=-1.0)  # negative threshold: the oracle forward never skips
+    ours = copy.deepcopy(model)
+    ours.__class__ = type("OurHYC", (ours.__class__,), {})
+    mc.init_magcache_hunyuan_calibration(ours, 50)
+    prev = None
+    with torch.no_grad():
+        for i in range(4):
+            t = torch.tensor([900.0 - 100.0 * i])
+            xi = x * (1.0 - 0.1 * i)
+            a = ref_m(xi, t, txt, mask, pooled, cos, sin, torch.tensor([6000.0]))["x"]
+            b = ours(xi, t, txt, mask, pooled, cos, sin, torch.tensor([6000.0]))["x"]
+            assert rel_l2(b, a) <= 2e-2 and not ref_m.last_skip
+            cur = ref_m.residual_cache.float()
+            if prev is not None:
+                want = calibration_stats(cur, prev)[0]
+                assert abs(ours.norm_ratio[-1] - want) <= 2e-2 * abs(want), (i, ours.norm_ratio[-1], want)
+            prev = cur
+    assert ours.cnt == 4 and len(ours.norm_ratio) == len(ours.norm_std) == len(ours.cos_dis) == 3
+    assert "time: 1, norm_ratio" in capsys.readouterr().out
