@@ -124,22 +124,39 @@ class MMDiTCore:
     txt_first = True
 
     def _alloc_core(self, n_img, n_txt):
+        """Buffers for one (image tokens, text tokens) shape. Token-sharded (`self.world > 1`): the IMAGE rows are split over
+        the ranks, the (few) text rows are replicated — every rank carries all of them and computes the identical text stream — and per
+        attention the image K / V rows are all-gathered into the full-length K / V buffers (text rows copied in locally)."""
         D, dev = self.w.dim, self.device
-        S = n_img + n_txt
         bf = dict(dtype=torch.bfloat16, device=dev)
-        self.n_img, self.n_txt, self.S = n_img, n_txt, S
+        self.n_img_total, self.n_txt = n_img, n_txt
+        self.shard = None
+        if getattr(self, "world", 1) > 1:
+            from .shard import TokenShard
+            self.shard = TokenShard(self.rank, self.world, n_img, self.group)
+            n_img = self.shard.n_local
+        S = n_img + n_txt                      # rows this rank carries
+        Sg = self.n_img_total + n_txt          # keys every query attends to
+        self.n_img, self.S, self.S_keys = n_img, S, Sg
         if self.txt_first:
             self.txt, self.img = slice(0, n_txt), slice(n_txt, S)
+            self.txt_g, self.img_g = slice(0, n_txt), slice(n_txt, Sg)
         else:
             self.img, self.txt = slice(0, n_img), slice(n_img, S)
+            self.img_g, self.txt_g = slice(0, self.n_img_total), slice(self.n_img_total, Sg)
         self.hs, self.h, self.att = torch.empty(S, D, **bf), torch.empty(S, D, **bf), torch.empty(S, D, **bf)
         self.x0, self.res, self.hit = torch.empty(n_img, D, **bf), torch.empty(n_img, D, **bf), torch.empty(n_img, D, **bf)
-        self.qk = torch.empty(S, 2 * D, **bf)
-        self.vt = torch.zeros(D, (S + 7) // 8 * 8, **bf)
-        # V^T column ranges must start on 16 bytes for the GEMM to write them directly; otherwise (second segment starting at a row that is
-        # not a multiple of 8: never with FLUX's padded 512 text tokens) V goes to a row-major buffer and is transposed once per attention
-        self.v_direct = min(self.img.start, self.txt.start) == 0 and max(self.img.start, self.txt.start) % 8 == 0
-        self.v = None if self.v_direct else torch.empty(S, D, **bf)
+        self.vt = torch.zeros(D, (Sg + 7) // 8 * 8, **bf)
+        if self.shard is None:
+            self.qk = torch.empty(S, 2 * D, **bf)
+            # V^T column ranges must start on 16 bytes for the GEMM to write them directly; otherwise (second segment starting at a row that
+            # is not a multiple of 8: never with FLUX's padded 512 text tokens) V goes to a row-major buffer and is transposed per attention
+            self.v_direct = min(self.img.start, self.txt.start) == 0 and max(self.img.start, self.txt.start) % 8 == 0
+            self.v = None if self.v_direct else torch.empty(S, D, **bf)
+        else:
+            self.v_direct = False
+            self.q_loc, self.k_loc, self.v_loc = torch.empty(S, D, **bf), torch.empty(S, D, **bf), torch.empty(S, D, **bf)
+            self.k_all, self.v_all = torch.empty(Sg, D, **bf), torch.empty(Sg, D, **bf)
         self.cat = torch.empty(S, 5 * D, **bf)
         self.ada = torch.empty(1, self.w.ada_rows, **bf)
         self.adaf = torch.empty(self.w.ada_rows, dtype=torch.float32, device=dev)
@@ -162,7 +179,13 @@ class MMDiTCore:
 
     # ------------------------------------------------------------------------------------------ attention over the joint sequence
     def _project(self, rows, h_rows, qk_w, qk_b, v_w, v_b):
-        """q | k and V^T projections of the token range `rows` from its LN+modulate output."""
+        """q | k and V projections of the token range `rows` from its LN+modulate output."""
+        D = self.w.dim
+        if self.shard is not None:  # separate contiguous q / k / v buffers: k and v rows are sent to the other ranks
+            ops.gemm(h_rows, qk_w[:D], qk_b[:D], E.MC_EPI_BIAS_BF16, out=self.q_loc[rows])
+            ops.gemm(h_rows, qk_w[D:], qk_b[D:], E.MC_EPI_BIAS_BF16, out=self.k_loc[rows])
+            ops.gemm(h_rows, v_w, v_b, E.MC_EPI_BIAS_BF16, out=self.v_loc[rows])
+            return
         ops.gemm(h_rows, qk_w, qk_b, E.MC_EPI_BIAS_BF16, out=self.qk[rows])
         if self.v_direct:
             ops.gemm(v_w, h_rows, v_b, E.MC_EPI_ROWBIAS_BF16, out=self.vt[:, rows])
@@ -173,14 +196,36 @@ class MMDiTCore:
         """Per-head RMSNorm of q and k (+ RoPE where the family applies it), in place."""
         D, H = self.w.dim, self.w.heads
         rope = self._rope_for(rows)
-        ops.rmsnorm_head_rope_(self.qk[rows][:, :D], nq, H, rope)
-        ops.rmsnorm_head_rope_(self.qk[rows][:, D:], nk, H, rope)
+        q, k = (self.q_loc[rows], self.k_loc[rows]) if self.shard is not None else (self.qk[rows][:, :D], self.qk[rows][:, D:])
+        ops.rmsnorm_head_rope_(q, nq, H, rope)
+        ops.rmsnorm_head_rope_(k, nk, H, rope)
 
     def _joint_attention(self, out):
-        D, S = self.w.dim, self.S
+        D, H = self.w.dim, self.w.heads
+        if self.shard is not None:
+            from .shard import gather_rows
+            # image K / V rows of every rank -> the image block of the full-length buffers; the replicated text rows are copied in
+            wk = gather_rows(self.k_loc[self.img], self.k_all[self.img_g], self.shard.group, async_op=True)
+            wv = gather_rows(self.v_loc[self.img], self.v_all[self.img_g], self.shard.group, async_op=True)
+            self.k_all[self.txt_g].copy_(self.k_loc[self.txt])
+            self.v_all[self.txt_g].copy_(self.v_loc[self.txt])
+            wk.wait()
+            wv.wait()
+            ops.transpose(self.v_all, self.vt[:, :self.S_keys])
+            ops.attention(self.q_loc, self.k_all, self.vt[:, :self.S_keys], H, out=out, tag="mmdit_attn")
+            return
         if not self.v_direct:
-            ops.transpose(self.v, self.vt[:, :S])
-        ops.attention(self.qk[:, :D], self.qk[:, D:], self.vt[:, :S], self.w.heads, out=out, tag="mmdit_attn")
+            ops.transpose(self.v, self.vt[:, :self.S])
+        ops.attention(self.qk[:, :D], self.qk[:, D:], self.vt[:, :self.S], H, out=out, tag="mmdit_attn")
+
+    def _gather_output(self, o_local):
+        """Per-token head output of this rank's image rows -> all image rows, replicated (tiny: 64 features per token)."""
+        if self.shard is None:
+            return o_local
+        from .shard import gather_rows
+        full = torch.empty(self.n_img_total, o_local.shape[1], dtype=o_local.dtype, device=o_local.device)
+        gather_rows(o_local.contiguous(), full, self.shard.group)
+        return full
 
     def run_blocks(self):
         """Double-stream then single-stream blocks (magcache_flux.py:343-424; magcache_sample_video.py:108-139) on `hs`; the image rows of
@@ -246,6 +291,8 @@ class MMDiTCore:
         stack; returns (head output, (norm_ratio, norm_std, cos_dis) against the previous residual or None on the first call). The
         statistics come from the fused fp32/fp64 reduction kernel — finer than the reference's bf16 tensor ops, which quantise them to
         multiples of 2^-8 (the shipped FLUX table is visibly bf16-quantised)."""
+        if self.shard is not None:
+            raise NotImplementedError("magcache_b200: token-sharded calibration of the MMDiT engines is not built (run it on one GPU)")
         x0 = self.prologue()
         self.hs[self.img].copy_(x0)
         x = self.run_blocks()
@@ -260,8 +307,9 @@ class MMDiTCore:
 class FluxEngine(MMDiTCore):
     txt_first = True
 
-    def __init__(self, weights: FluxWeights):
+    def __init__(self, weights: FluxWeights, shard_world=1, shard_rank=0, shard_group=None):
         self.w, self.device = weights, weights.device
+        self.world, self.rank, self.group = shard_world, shard_rank, shard_group
         self._shape = None
         self._rope_key, self._rope = None, None
         self.res_valid = False
@@ -271,14 +319,20 @@ class FluxEngine(MMDiTCore):
             return
         bf = dict(dtype=torch.bfloat16, device=self.device)
         self._alloc_core(n_img, n_txt)
-        self.s_hidden = torch.empty(n_img, self.w.in_channels, **bf)
+        self.s_hidden = torch.empty(self.n_img, self.w.in_channels, **bf)  # this rank's image tokens
         self.s_enc = torch.empty(n_txt, self.w.joint_dim, **bf)
         self.s_pooled = torch.empty(1, self.w.pooled_dim, **bf)
         self.s_t = torch.zeros(2, dtype=torch.float64, device=self.device)  # timestep*1000, guidance*1000 (already rounded like the reference)
         self._shape = (n_img, n_txt)
 
     def _rope_for(self, rows):
-        return self._rope[rows]
+        if self.shard is None:
+            return self._rope[rows]
+        if rows == self.txt:
+            return self._rope[self.txt_g]
+        if rows == self.img:  # this rank's image rows sit at their GLOBAL positions in the table (text rows first)
+            return self._rope[self.n_txt + self.shard.start:self.n_txt + self.shard.stop]
+        return torch.cat([self._rope[self.txt_g], self._rope[self.n_txt + self.shard.start:self.n_txt + self.shard.stop]])
 
     # ------------------------------------------------------------------------------------------ inputs (:290-319)
     def stage_inputs(self, hidden_states, encoder_hidden_states, pooled, timestep, guidance, img_ids, txt_ids):
@@ -286,7 +340,7 @@ class FluxEngine(MMDiTCore):
         assert hidden_states.shape[0] == 1 and encoder_hidden_states.shape[0] == 1, "one sample per call"
         n_img, n_txt = hidden_states.shape[1], encoder_hidden_states.shape[1]
         self._workspace(n_img, n_txt)
-        self.s_hidden.copy_(hidden_states[0])
+        self.s_hidden.copy_(hidden_states[0] if self.shard is None else self.shard.rows(hidden_states[0]))
         self.s_enc.copy_(encoder_hidden_states[0])
         self.s_pooled.copy_(pooled.reshape(1, -1))
         if (w.guidance and guidance is None) or (not w.guidance and guidance is not None):
@@ -299,7 +353,7 @@ class FluxEngine(MMDiTCore):
         if self._rope_key != key:  # ids are constant over a generation
             self._rope = rope_table(torch.cat((txt_ids.reshape(-1, 3), img_ids.reshape(-1, 3)), dim=0), self.device)  # :318
             self._rope_key = key
-            assert self._rope.shape == (self.S, 128)
+            assert self._rope.shape == (self.S_keys, 128)
 
     def prologue(self):
         """x_embedder, time_text_embed, context_embedder (:290-303) and every AdaLayerNorm projection of the forward."""
@@ -318,7 +372,7 @@ class FluxEngine(MMDiTCore):
         w = self.w
         em = self._em(w.ada_out, 2)
         ops.ln_modulate(x_img, em, 0, 1, round_ln_to_bf16=True, out=self.h[self.img])
-        return ops.gemm(self.h[self.img], w.out_w, w.out_b, E.MC_EPI_BIAS_BF16)
+        return self._gather_output(ops.gemm(self.h[self.img], w.out_w, w.out_b, E.MC_EPI_BIAS_BF16))
 
 
 # ======================================================================================================================
@@ -411,8 +465,9 @@ class HunyuanEngine(MMDiTCore):
 
     txt_first = False
 
-    def __init__(self, weights: HunyuanWeights):
+    def __init__(self, weights: HunyuanWeights, shard_world=1, shard_rank=0, shard_group=None):
         self.w, self.device = weights, weights.device
+        self.world, self.rank, self.group = shard_world, shard_rank, shard_group
         self._shape = None
         self._rope_key, self._rope = None, None
         self._mask_key, self._valid = None, None
@@ -436,7 +491,9 @@ class HunyuanEngine(MMDiTCore):
         self._shape = (grid, n_txt)
 
     def _rope_for(self, rows):
-        return self._rope if rows == self.img else None  # the text tokens get no RoPE (magcache_sample_video.py:108-120 -> hyvideo blocks)
+        if rows != self.img or self._rope is None:
+            return None  # the text tokens get no RoPE (magcache_sample_video.py:108-120 -> hyvideo blocks)
+        return self._rope if self.shard is None else self._rope[self.shard.start:self.shard.stop]
 
     # ------------------------------------------------------------------------------------------ inputs (:42-86)
     def stage_inputs(self, x, t, text_states, text_mask, text_states_2, freqs_cos, freqs_sin, guidance):
@@ -461,10 +518,11 @@ class HunyuanEngine(MMDiTCore):
         gv = guidance.reshape(-1)[:1].double() if guidance is not None else torch.zeros(1, dtype=torch.float64, device=t.device)
         self.s_t.copy_(torch.cat([t.reshape(-1)[:1].double(), gv.to(t.device)]))
         if freqs_cos is not None:
-            key = (freqs_cos.data_ptr(), freqs_sin.data_ptr(), self.n_img)
+            key = (freqs_cos.data_ptr(), freqs_sin.data_ptr(), self.n_img_total)
             if self._rope_key != key:
-                assert tuple(freqs_cos.shape) == (self.n_img, 128) and tuple(freqs_sin.shape) == (self.n_img, 128)
-                cs = torch.stack([freqs_cos.float()[:, 0::2], freqs_sin.float()[:, 0::2]], dim=-1).reshape(self.n_img, 128)
+                n = self.n_img_total
+                assert tuple(freqs_cos.shape) == (n, 128) and tuple(freqs_sin.shape) == (n, 128)
+                cs = torch.stack([freqs_cos.float()[:, 0::2], freqs_sin.float()[:, 0::2]], dim=-1).reshape(n, 128)
                 self._rope, self._rope_key = cs.contiguous().to(self.device), key
         else:
             self._rope = None
@@ -480,11 +538,17 @@ class HunyuanEngine(MMDiTCore):
         ops.cast_into(self.rada.view(-1), self.radaf)
         x, h = self.hs[txt], self.h[txt]
         ops.gemm(self.s_txt, w.r_in_w, w.r_in_b, E.MC_EPI_BIAS_BF16, out=x)
-        q, k, vt = self.qk[txt][:, :D], self.qk[txt][:, D:], self.rvt[:, :n]
+        sharded = self.shard is not None
+        q, k = (self.q_loc[txt], self.k_loc[txt]) if sharded else (self.qk[txt][:, :D], self.qk[txt][:, D:])
+        vt = self.rvt[:, :n]
         for i, b in enumerate(w.refiner):
             g = self.radaf[i * 2 * D:(i + 1) * 2 * D].view(2, D)  # gate_msa, gate_mlp
             ops.ln_affine(x, b["n1_w"], b["n1_b"], eps=1e-6, out=h)
-            ops.gemm(h, b["qk_w"], b["qk_b"], E.MC_EPI_BIAS_BF16, out=self.qk[txt])
+            if sharded:
+                ops.gemm(h, b["qk_w"][:D], b["qk_b"][:D], E.MC_EPI_BIAS_BF16, out=q)
+                ops.gemm(h, b["qk_w"][D:], b["qk_b"][D:], E.MC_EPI_BIAS_BF16, out=k)
+            else:
+                ops.gemm(h, b["qk_w"], b["qk_b"], E.MC_EPI_BIAS_BF16, out=self.qk[txt])
             ops.gemm(b["v_w"], h, b["v_b"], E.MC_EPI_ROWBIAS_BF16, out=vt)
             ops.rmsnorm_head_rope_(q, b["nq"], H, None)
             ops.rmsnorm_head_rope_(k, b["nk"], H, None)
@@ -501,7 +565,8 @@ class HunyuanEngine(MMDiTCore):
         vec = ops.cache_hit_add(self._time_mlp(self._sinusoid(self.s_t[0:1]), w.t_mlp), self._time_mlp(self.s_pooled, w.p_mlp))
         if w.guidance:
             vec = ops.cache_hit_add(vec, self._time_mlp(self._sinusoid(self.s_t[1:2]), w.g_mlp))
-        ops.gemm(ops.patchify(self.s_lat), w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
+        tok = ops.patchify(self.s_lat)
+        ops.gemm(tok if self.shard is None else self.shard.rows(tok), w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
         self._refine_text()
         self._modulation_table(vec)
         return self.x0
@@ -511,7 +576,7 @@ class HunyuanEngine(MMDiTCore):
         w = self.w
         em = self._em(w.ada_out, 2)
         ops.ln_modulate(x_img, em, 1, 0, round_ln_to_bf16=True, out=self.h[self.img])
-        o = ops.gemm(self.h[self.img], w.out_w, w.out_b, E.MC_EPI_BIAS_BF16)  # [n_img, C*1*2*2], feature order (c, pt, ph, pw)
+        o = self._gather_output(ops.gemm(self.h[self.img], w.out_w, w.out_b, E.MC_EPI_BIAS_BF16))  # [n_img, C*1*2*2], (c, pt, ph, pw)
         t, hh, ww = self.grid
         c = w.out_channels
         o = o.view(1, t, hh, ww, c, 1, 2, 2)

@@ -42,8 +42,9 @@ def _engine(self):
 def enable_token_shard(model, rank, world, group=None):
     """Shard the token axis of `model`'s forwards over `world` ranks of one node (call before the first forward; needs an
     initialised torch.distributed NCCL group). Every rank must then make the same calls with the same inputs; outputs are
-    replicated, the residual cache stays sharded."""
-    if "_mc_engine" in model.__dict__:
+    replicated, the residual cache stays sharded. Wan engines shard all tokens; the FLUX / HunyuanVideo engines shard the image tokens and
+    replicate the text tokens."""
+    if any(k in model.__dict__ for k in ("_mc_engine", "_mc_flux_engine", "_mc_hunyuan_engine")):
         raise RuntimeError("enable_token_shard must be called before the first forward")
     object.__setattr__(model, "_mc_shard_kw", dict(shard_world=world, shard_rank=rank, shard_group=group))
     return model
@@ -366,7 +367,7 @@ def _flux_engine(self, hidden_states):
     eng = self.__dict__.get("_mc_flux_engine")
     if eng is None:
         from .mmdit import FluxEngine, FluxWeights
-        eng = FluxEngine(FluxWeights.from_module(self, hidden_states.device))
+        eng = FluxEngine(FluxWeights.from_module(self, hidden_states.device), **self.__dict__.get("_mc_shard_kw", {}))
         object.__setattr__(self, "_mc_flux_engine", eng)
     return eng
 
@@ -448,7 +449,7 @@ def magcache_hunyuan_forward(self, x, t, text_states=None, text_mask=None, text_
     eng = self.__dict__.get("_mc_hunyuan_engine")
     if eng is None:
         from .mmdit import HunyuanEngine, HunyuanWeights
-        eng = HunyuanEngine(HunyuanWeights.from_module(self, x.device))
+        eng = HunyuanEngine(HunyuanWeights.from_module(self, x.device), **self.__dict__.get("_mc_shard_kw", {}))
         object.__setattr__(self, "_mc_hunyuan_engine", eng)
     eng.stage_inputs(x, t, text_states, text_mask, text_states_2, freqs_cos, freqs_sin, guidance)
     ctrls = self.__dict__.setdefault("_mc_ctrls", {})
