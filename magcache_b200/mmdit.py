@@ -114,7 +114,7 @@ def rope_table(ids, device, axes_dim=(16, 56, 56), theta=10000.0):
     ang = [np.outer(pos[:, i], 1.0 / theta ** (np.arange(0, d, 2, dtype=np.float64) / d)) for i, d in enumerate(axes_dim)]
     ang = np.concatenate(ang, axis=1)  # [S, 64]
     cs = np.stack([np.cos(ang), np.sin(ang)], axis=-1).reshape(len(pos), 2 * ang.shape[1])
-    return torch.from_numpy(cs.astype(np.float32)).to(device)
+    return torch.tensor(cs.astype(np.float32)).to(device)  # torch-allocated (aligned) storage on every device
 
 
 class MMDiTCore:

@@ -14,6 +14,12 @@ LAUNCHES = 0
 PROFILE = None
 
 
+def _al(t, n=16):
+    """The kernels' pointer / pitch preconditions (mc_gemm_bf16, mc_attn_fwd, ... check them on the device side): CPU allocations are
+    64-byte aligned like CUDA ones are 256-byte aligned, so a misaligned VIEW offset shows up here exactly as it would on the GPU."""
+    return t.data_ptr() % n == 0
+
+
 def _rb(t):
     return t.to(BF).to(F32)
 
@@ -25,6 +31,8 @@ def _count(n=1):
 
 def gemm(a, b, bias=None, epilogue=L.MC_EPI_BIAS_BF16, out=None, gate=None, tag=None):
     assert a.dtype == BF and b.dtype == BF and a.shape[1] == b.shape[1]
+    assert a.stride(1) == 1 and b.stride(1) == 1 and a.shape[1] % 8 == 0 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0, "TMA operand pitch"
+    assert _al(a) and _al(b) and (out is None or _al(out)), "mc_gemm_bf16: A/B/out must be 16-byte aligned"
     acc = a.to(F32) @ b.to(F32).t()
     M, N = acc.shape
     if epilogue == L.MC_EPI_ROWBIAS_BF16:
@@ -83,6 +91,7 @@ def ln_affine(x, weight, bias, eps=1e-6, out_dtype=BF, out=None):
 
 def rmsnorm_head_rope_(x, weight, heads, cos_sin=None, eps=1e-6):
     assert x.dtype == BF and x.stride(1) == 1 and x.shape[1] == heads * 128 and weight.numel() == 128
+    assert x.stride(0) % 8 == 0 and _al(x) and (cos_sin is None or (cos_sin.is_contiguous() and _al(cos_sin, 32) and cos_sin.shape == (x.shape[0], 128)))
     rows = x.shape[0]
     v = x.to(F32).view(rows, heads, 128)
     r = torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)
@@ -115,7 +124,10 @@ def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6):
 def attention(q, k, vt, heads, scale=None, out=None, tag=None):
     Lq, W = q.shape
     Lk = k.shape[0]
-    qh = q.to(F32).view(Lq, heads, 128).transpose(0, 1)
+    assert q.stride(1) == 1 and k.stride(1) == 1 and vt.stride(1) == 1 and vt.shape == (W, Lk) and W == heads * 128
+    assert q.stride(0) % 8 == 0 and k.stride(0) % 8 == 0 and vt.stride(0) % 8 == 0 and _al(q) and _al(k) and _al(vt), "attention TMA operands"
+    assert out is None or (out.stride(1) == 1 and out.stride(0) % 8 == 0 and _al(out))
+    qh = q.to(F32).reshape(Lq, heads, 128).transpose(0, 1)
     kh = k.to(F32).reshape(Lk, heads, 128).transpose(0, 1)
     vh = vt.to(F32).t().reshape(Lk, heads, 128).transpose(0, 1)
     s = qh @ kh.transpose(1, 2) * (scale if scale is not None else 1.0 / math.sqrt(128))
@@ -132,6 +144,7 @@ def _promote(a, b):
 
 
 def cache_hit_add(x, r, out=None, tag=None):
+    assert x.shape == r.shape and x.is_contiguous() and r.is_contiguous() and (out is None or out.is_contiguous())
     y = x.to(F32) + r.to(F32)
     if out is None:
         out = torch.empty(x.shape, dtype=_promote(x, r))
@@ -141,6 +154,7 @@ def cache_hit_add(x, r, out=None, tag=None):
 
 
 def residual_sub(x_out, x_in, out=None):
+    assert x_out.shape == x_in.shape and x_out.is_contiguous() and x_in.is_contiguous() and (out is None or out.is_contiguous())
     y = x_out.to(F32) - x_in.to(F32)
     if out is None:
         out = torch.empty(x_out.shape, dtype=_promote(x_out, x_in))
@@ -150,6 +164,7 @@ def residual_sub(x_out, x_in, out=None):
 
 
 def cast_into(src, dst):
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
     dst.copy_(src.reshape(dst.shape))
     _count()
     return dst
@@ -177,6 +192,7 @@ def time_sinusoid(t, dim):
 
 
 def transpose(src, dst):
+    assert src.dtype == BF and dst.dtype == BF and src.stride(1) == 1 and dst.stride(1) == 1 and dst.shape == (src.shape[1], src.shape[0])
     dst.copy_(src.t())
     _count()
     return dst
