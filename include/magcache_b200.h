@@ -240,11 +240,26 @@ int32_t mc_silu_bf16(const void* x, void* y, int64_t n, void* stream);
 int32_t mc_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
                      const float* bias, int32_t epilogue, void* out, int64_t ldo, const float* gate, void* stream);
 
-/* Non-causal attention forward on tcgen05: out[i, h*128:(h+1)*128] = softmax(q_h k_h^T * scale) v_h, head_dim = 128.
- * q: [Lq, heads*128] bf16 (ldq), k: [Lk, heads*128] bf16 (ldk), vt: V transposed [heads*128, Lk] bf16 (ldvt >= Lk, %8),
- * out: [Lq, heads*128] bf16 (ldo). */
-int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out,
-                    int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* stream);
+/* Non-causal attention forward on tcgen05: out[i, h*128:(h+1)*128] = softmax(q_h k_h^T * scale) v_h, head_dim = 128
+ * (WanSelfAttention / WanT2VCrossAttention [EXT] behind MagCache4Wan2.1/magcache_generate.py:297-298; the joint attention of
+ * MagCache4FLUX/magcache_flux.py:343-425 and MagCache4HunyuanVideo/magcache_sample_video.py:108-140).
+ * q: [Lq, heads*128] bf16 (ldq), k: [Lk, heads*128] bf16 (ldk), v: [Lk, heads*128] bf16 (ldv) — all ROW-MAJOR views, so the three
+ * can be column slices of one fused q|k|v projection buffer; out: [Lq, heads*128] bf16 (ldo). Leading dimensions % 8 == 0,
+ * pointers 16-byte aligned.
+ * workspace: device scratch for the split-KV partials that small grids use (mc_attn_workspace_bytes tells how much a shape
+ * needs; 0 = the shape never splits, workspace may be NULL). The caller owns it: one per stream of concurrent use. */
+int32_t mc_attn_workspace_bytes(int32_t Lq, int32_t Lk, int32_t heads, int64_t* bytes_out);
+int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                    int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+/* Token-sharded form (the exchange of videosys/core/comm.py:272-292 overlapped with the attention itself): the key /
+ * value rows [first_key_row, ...) are the caller's own and already resident; the other ranks' rows arrive while the kernel runs.
+ * KV tiles are consumed in rotated order starting at the caller's own rows, and before a tile that touches source segment s
+ * (rows [s*seg_rows, (s+1)*seg_rows)) is loaded the kernel waits until seg_flags[s] (device memory, written by the sender
+ * after the segment's data) has reached seg_epoch. seg_flags == NULL: no waiting (plain rotation). */
+int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                       int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* workspace, int64_t workspace_bytes,
+                       int32_t first_key_row, const uint32_t* seg_flags, uint32_t seg_epoch, int32_t seg_rows, void* stream);
 
 /* Small fp32 linear for the time-embedding path (autocast-disabled region, magcache_generate.py:249-254):
  * y[m, n] = act(sum_k x[m,k] * W[n,k] + b[n]), M <= 8. act: 0 none, 1 SiLU applied to the INPUT x first (time_projection),
@@ -252,16 +267,28 @@ int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
 int32_t mc_linear_f32_small(const float* x, int32_t M, int32_t K, const float* W, const float* b, int32_t N, int32_t act,
                             float* y, void* stream);
 
-/* Head + unpatchify (magcache_generate.py:304-305): out[c, f, 2h+p, 2w+q] = Linear_fp32(LN(x)*(1+e1)+e0)[token, (p,q,c)].
+/* Head + unpatchify (magcache_generate.py:304-305), with the cache-hit sum `x + residual_x` (:295) formed on the fly:
+ * out[c, f, 2h+p, 2w+q] = Linear_fp32(LN(x)*(1+e1)+e0)[token, (p,q,c)], one pass over the rows (tcgen05, 3-pass bf16 split:
+ * fp32-class accuracy; see csrc/head_tcgen05.cu).
  * x: [rows, cols] for the tokens row_offset .. row_offset+rows-1 of the F*Hp*Wp grid (rows = F*Hp*Wp, row_offset = 0 unless the
- * token axis is sharded); fp32, or the un-materialised hit sum x0_bf16 + r_f32 when r != NULL (fused cache-hit path).
+ * token axis is sharded): fp32 with r == NULL (the residual stream), or bf16 together with r fp32 [rows, cols] — the
+ * un-materialised hit sum x0_bf16 + r_f32. cols % 64 == 0.
  * head_mod: [2, cols] modulation parameter, e: [cols] time embedding, Wt: head.weight TRANSPOSED [cols, 64] fp32, b: [64];
- * out fp32 [C, F, 2Hp, 2Wp]: only the positions of the given tokens are written. */
+ * out fp32 [C, F, 2Hp, 2Wp]: only the positions of the given tokens are written.
+ * workspace: mc_head_workspace_bytes(cols) bytes of device scratch, 1024-byte aligned (the modulated, split weight of this call).
+ * flags bit 0: round the hit sum to bf16 before the head (in-place `x += residual` on a bf16 tensor, wan_teacache.py:569/577).
+ * _ex: the same rows are written into n_out <= 8 output tensors (token-sharded runs: every peer's copy, P2P stores). */
+int32_t mc_head_workspace_bytes(int32_t cols, int64_t* bytes_out);
 int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
                            int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e,
-                           const float* Wt, const float* b, float eps, float* out, void* stream);
+                           const float* Wt, const float* b, float eps, float* out, void* workspace, int64_t workspace_bytes,
+                           int32_t flags, void* stream);
+int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
+                              int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e,
+                              const float* Wt, const float* b, float eps, float* const* outs, int32_t n_out, void* workspace,
+                              int64_t workspace_bytes, int32_t flags, void* stream);
 
-/* bf16 transpose dst[c, r] = src[r, c] (token-sharded runs: all-gathered V [N, D] -> V^T [D, N] for mc_attn_fwd). */
+/* bf16 transpose dst[c, r] = src[r, c]. */
 int32_t mc_transpose_bf16(const void* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldd, void* stream);
 
 /* sinusoidal_embedding_1d(freq_dim, t) in float64, cos half first (magcache_generate.py:250-251): pos_dev [n_pos] f64 ->

@@ -5,7 +5,7 @@ this module raises, and every device entry point raises `MagCacheError` when CUD
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_uint8, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_uint8, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmagcache_b200.so")
@@ -16,7 +16,7 @@ MC_F32, MC_BF16 = 0, 1
 MC_CMP_LT, MC_CMP_LE = 0, 1
 MC_RETAIN_FLOOR, MC_RETAIN_HALF_UP, MC_RETAIN_CEIL, MC_RETAIN_WAN22_T2V, MC_RETAIN_WAN22_I2V, MC_RETAIN_EXPLICIT = 0, 1, 2, 3, 4, 5
 MC_CTRL_SIGNED_ERR, MC_CTRL_RESET_AT_ZERO, MC_CTRL_RATIO_VETO = 1, 2, 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 MC_EPI_BIAS_BF16, MC_EPI_BIAS_GELU_BF16, MC_EPI_BIAS_GATE_RESID, MC_EPI_ROWBIAS_BF16, MC_EPI_BIAS_F32, MC_EPI_BIAS_GELU_ERF_BF16 = 0, 1, 2, 3, 4, 5
 MC_EPI_BIAS_GATE_RESID_BF16, MC_EPI_BIAS_SILU_BF16 = 6, 7
 
@@ -81,11 +81,17 @@ SIGNATURES = {
     "mc_silu_bf16": [c_void_p, c_void_p, c_int64, c_void_p],
     "mc_gemm_bf16": [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_void_p,
                      c_void_p],
+    "mc_attn_workspace_bytes": [c_int32, c_int32, c_int32, POINTER(c_int64)],
     "mc_attn_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
-                    c_void_p],
+                    c_void_p, c_int64, c_void_p],
+    "mc_attn_fwd_ex": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
+                       c_void_p, c_int64, c_int32, c_void_p, c_uint32, c_int32, c_void_p],
     "mc_linear_f32_small": [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p],
+    "mc_head_workspace_bytes": [c_int32, POINTER(c_int64)],
     "mc_head_unpatchify": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
-                           c_void_p, c_void_p, c_float, c_void_p, c_void_p],
+                           c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
+    "mc_head_unpatchify_ex": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_float, POINTER(c_void_p), c_int32, c_void_p, c_int64, c_int32, c_void_p],
     "mc_transpose_bf16": [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p],
     "mc_time_sinusoid": [c_void_p, c_int32, c_int32, c_void_p, c_void_p],
     "mc_cast": [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],

@@ -50,9 +50,12 @@ class AttrController:
             # MagCache4Wan2.2/magcache_generate.py:344 `split_step = split_steps*2`; None (TI2V-5B) falls back to int(n*R), :301-303
             split = getattr(o, "split_step", None)
             kw = dict(kw, split_step=int(split)) if split is not None else dict(kw, retention_mode=_lib.MC_RETAIN_FLOOR)
-        key = (id(mr), len(mr), o.num_steps, float(o.magcache_thresh), int(o.K), float(o.retention_ratio), kw.get("split_step"))
+        # keyed on the table's CONTENT (a few hundred bytes): an in-place edit of the installed table — the reference's suggested
+        # `**0.5` smoothing, say — keeps id() and len() but must reach the controller
+        arr = np.ascontiguousarray(np.asarray(mr, dtype=np.float64))
+        key = (hash(arr.tobytes()), len(arr), o.num_steps, float(o.magcache_thresh), int(o.K), float(o.retention_ratio), kw.get("split_step"))
         if self._key != key:
-            self._cfg = make_ctrl_config(o.num_steps, o.magcache_thresh, o.K, o.retention_ratio, np.asarray(mr, dtype=np.float64), **kw)
+            self._cfg = make_ctrl_config(o.num_steps, o.magcache_thresh, o.K, o.retention_ratio, arr, **kw)
             self._key = key
         return self._cfg
 

@@ -1,38 +1,40 @@
 // Non-causal flash-attention forward on tcgen05/TMEM, head_dim 128 — the self-/cross-attention of the Wan DiT block
 // (reference call chain MagCache4Wan2.1/magcache_generate.py:297-298 -> WanSelfAttention.forward ->
-// flash_attention / SDPA, upstream wan/modules/{model,attention}.py).
+// flash_attention / SDPA, upstream wan/modules/{model,attention}.py) and the joint attention of the MMDiT blocks
+// (MagCache4FLUX/magcache_flux.py:343-425, MagCache4HunyuanVideo/magcache_sample_video.py:108-140).
 //
-// One CTA = one 128-row query tile of one head; KV is streamed in 64-row tiles. Two CTAs are co-resident per SM
-// (256 TMEM columns and ~112 KB smem each), so one CTA's softmax overlaps the other's MMAs.
-//   warps 0-3  softmax    : thread = query row (TMEM lane). tcgen05.ld S, online softmax in the exp2 domain with lazy
-//                           rescaling of O (only when the running max grows by > 8), P -> bf16 -> swizzled smem
-//   warp 4     TMA        : Q once; K tile (2 boxes) and V^T tile (1 box) per iteration into 2-stage rings
-//   warp 5     MMA issuer : S_j = Q K_j^T (M128 N64 K128, double-buffered in TMEM), O += P_j V_j (M128 N128 K64)
-// V is consumed transposed (V^T [heads*128, Lk], produced directly by the V-projection GEMM) so that both MMAs see
-// K-major operands — the same smem/UMMA descriptor path the GEMM kernel uses.
+// q [Lq, H*128], k [Lk, H*128], v [Lk, H*128] are all ROW-MAJOR bf16 views (row pitch allowed: they are column slices of the
+// fused q|k|v projection buffer). K is the B operand of S = Q K^T in K-major form; V is the B operand of O += P V in MN-major
+// form (d contiguous) — the same [rows][64 bf16] 128-byte-swizzled TMA boxes for both, no transposed copy of V anywhere.
+//
+// Two kernels, one contract:
+//   attn_long_kernel  (Lk >= kLongMinLk): one CTA = TWO 128-row query tiles of one head (256 query rows), KV streamed in
+//     128-row tiles, one CTA per SM (192 KB smem, all 512 TMEM columns: S0 S1 O0 O1). Two softmax warpgroups, one per query
+//     tile; the MMA warp serves them alternately (PV0, S0', PV1, S1', ...), so while warpgroup 0 exponentiates tile j the
+//     tensor pipe runs PV1(j-1) and S1(j) — 1024 tensor cycles per window. The exponentials alone would fill that window
+//     (16 MUFU results per clock per SM against 4096 MACs per clock: one ex2 per 256 MACs), so a fixed fraction of them is
+//     evaluated on the FMA pipe (ptx::ex2_emul_pair); the S MMA runs at N = 128 (128 B of smem operands per clock, the
+//     UMMA fetch limit — at N = 64 it was 192 B/clk and fetch-bound) and every K / V tile is fetched once per 256 rows.
+//   attn_short_kernel (short key sequences: text / image cross-attention, refiner): one CTA = one 128-row query tile, 64-row
+//     KV tiles, two CTAs co-resident per SM so that one CTA's prologue / epilogue overlaps the other's main loop.
+// Both: thread = query row (TMEM lane) in the softmax warps, online softmax in the exp2 domain with lazy rescaling of O
+// (only when the running max grows by more than 2^8), P -> bf16 -> tcgen05.st over the consumed S columns, PV MMA with A
+// from TMEM. Small grids (token-sharded ranks) split the KV range over blockIdx.z and merge with attn_combine_kernel.
 #include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
 
+#ifndef MC_ATTN_EMU_DEFAULT
+#define MC_ATTN_EMU_DEFAULT 2  // eighths of the softmax exponentials on the FMA pipe (long kernel); MC_ATTN_EMU overrides per call
+#endif
+
 namespace mc {
 
-constexpr int kBQ = 128, kBKV = 64, kHD = 128;
-constexpr int kQBytes = kBQ * kHD * 2;     // 32 KB (two 64-column boxes of 16 KB)
-constexpr int kKBytes = kBKV * kHD * 2;    // 16 KB (two boxes of 8 KB)
-constexpr int kVBytes = kHD * kBKV * 2;    // 16 KB (one box: 128 d-rows x 64 kv)
-constexpr int kPBytes = kBQ * kBKV * 2;    // 16 KB
-constexpr int kKVStages = 2;
-constexpr int kOffQ = 0;
-constexpr int kOffK = kOffQ + kQBytes;
-constexpr int kOffV = kOffK + kKVStages * kKBytes;
-constexpr int kOffP = kOffV + kKVStages * kVBytes;
-constexpr int kOffBar = kOffP + kPBytes;  // 112 KB
-constexpr int kAttnSmem = kOffBar + 256;
-constexpr int kAttnThreads = 192;
-constexpr int kTmemCols = 256;  // S0 [0,64) S1 [64,128) O [128,256)
+constexpr int kHD = 128;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr int kLongMinLk = 1024;
 
 struct AttnParams {
   int Lq, Lk, heads;
@@ -42,21 +44,350 @@ struct AttnParams {
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* out;
   int64_t ldo;
+  uint32_t v_lbo, v_sbo;  // MN-major descriptor strides of the V tile (bytes): box stride, 8-row group stride
+  // KV tile order. Token-sharded runs consume the LOCAL keys first and the peers' keys in arrival order: tile j of this CTA is
+  // global tile (tile_rot + j) mod total. seg_flags != nullptr: before a tile that touches rows of source segment s
+  // (rows [s*seg_rows, (s+1)*seg_rows)) is loaded, seg_flags[s] must have reached seg_epoch (written by the peer copy).
+  int tile_rot;
+  const uint32_t* seg_flags;
+  uint32_t seg_epoch;
+  int seg_rows;
 };
 
-// P_IN_TMEM: the bf16 probabilities are written back into the (already consumed) S columns of TMEM with tcgen05.st and the
-// PV MMA takes its A operand from TMEM — no smem round trip, no generic->async proxy fence, and P is double-buffered for free
-// (it lives in S buffer j&1), which removes the write-P -> PV -> pv_done -> write-next-P serialisation of the smem variant.
-// VARIANT 0: P through shared memory (kept for A/B measurements); VARIANT 1 (default): P in TMEM.
-// Tried, validated and dropped in round 1 because they were slower (profiles/r01_attention_experiments.md; sources in the git
-// history): speculative exponentials, cross-tile software pipelining, staggered CTA start, 256-row CTAs with 128-wide KV
-// tiles, split-row softmax with 8 softmax warps, 128-wide KV tiles with a single-buffered S.
-constexpr int kDefaultPoly = 0;  // see profiles/r01_attention_experiments.md ("exponentials on the FMA pipe")
+// P = 2^x for four consecutive elements (two packed pairs): MUFU for a pair unless its bit in EMU_MASK is set, in which case the
+// pair goes through the FMA-pipe polynomial. `pair` is the running pair index (mod 8 selects the mask bit).
+template <uint32_t EMU_MASK>
+__device__ __forceinline__ void exp2_pair(float& a, float& b, int pair) {
+  if ((EMU_MASK >> (pair & 7)) & 1u) {
+    ptx::ex2_emul_pair(a, b);
+  } else {
+    a = ptx::ex2_approx(a);
+    b = ptx::ex2_approx(b);
+  }
+}
 
-template <int VARIANT, int POLY>
-__global__ void __launch_bounds__(kAttnThreads, 2)
-    attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
+// token-sharded runs: block until every source segment a KV tile touches has landed (flag written by the peer's copy stream
+// AFTER the segment's data, same stream). Called by the single TMA-issuing thread; the acquire load orders the flag before the
+// tile loads in the generic proxy, the proxy fence carries that order over to the async proxy the TMA reads through.
+__device__ __forceinline__ void wait_segments(const AttnParams& p, int row0, int rows) {
+  if (p.seg_flags == nullptr) return;
+  const int last = min(row0 + rows, p.Lk) - 1;
+  const int s0 = row0 / p.seg_rows, s1 = last / p.seg_rows;
+  for (int s = s0; s <= s1; ++s) {
+    const uint32_t* f = p.seg_flags + s;
+    const long long t0 = clock64();
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (static_cast<int32_t>(v - p.seg_epoch) >= 0) break;
+      __nanosleep(100);
+      if (clock64() - t0 > MC_MBAR_TIMEOUT_CYCLES) {
+        printf("attention: key segment %d never arrived (flag %u, epoch %u)\n", s, v, p.seg_epoch);
+        __trap();
+      }
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// =====================================================================================================================
+// long-sequence kernel: 256 query rows per CTA, 128-row KV tiles
+// =====================================================================================================================
+namespace lk {
+constexpr int kBQ = 128, kBKV = 128;
+constexpr int kQTileBytes = kBQ * kHD * 2;  // 32 KB per query tile (two 64-column boxes)
+constexpr int kKBytes = kBKV * kHD * 2;     // 32 KB (two boxes [128 kv x 64 hd])
+constexpr int kVBytes = kBKV * kHD * 2;     // 32 KB (two boxes [128 kv x 64 d])
+constexpr int kStages = 2;
+constexpr int kOffQ = 0;
+constexpr int kOffK = kOffQ + 2 * kQTileBytes;    // 64 KB
+constexpr int kOffV = kOffK + kStages * kKBytes;  // +64 KB
+constexpr int kOffBar = kOffV + kStages * kVBytes;  // 192 KB
+constexpr int kSmem = kOffBar + 256;
+constexpr int kThreads = 384;  // warps 0-3 softmax of query tile 0, 4-7 of query tile 1, warp 8 TMA, warp 9 MMA, 10-11 idle
+constexpr int kSoftmaxRegs = 216, kDataRegs = 56;  // setmaxnreg: the data-path warpgroup hands its registers to the softmax ones
+constexpr int kTmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_t (64 packed columns) overwrites S_t
+}  // namespace lk
+
+template <uint32_t EMU_MASK>
+__global__ void __launch_bounds__(lk::kThreads, 1)
+    attn_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using namespace lk;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2] per query tile
+  uint64_t* p_full = bars + 11;   // [2] per query tile, 128 arrivals
+  uint64_t* pv_done = bars + 13;  // [2] per query tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * kBQ);
+  const int head = blockIdx.y;
+  const int total_tiles = (p.Lk + kBKV - 1) / kBKV;
+  const int per_split = (total_tiles + p.splits - 1) / p.splits;
+  const int t0 = blockIdx.z * per_split;                 // first KV tile (in rotated order) of this CTA
+  const int n_tiles = min(per_split, total_tiles - t0);  // >= 1, guaranteed by the host
+  auto tile_of = [&](int j) {  // global KV tile index of this CTA's j-th tile
+    int t = p.tile_rot + t0 + j;
+    return t >= total_tiles ? t - total_tiles : t;
+  };
+
+  if (threadIdx.x == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) {
+      printf("attn_long_kernel: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_k);
+    ptx::prefetch_tmap(&tmap_v);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&k_full[s], 1);
+      ptx::mbar_init(&k_empty[s], 1);
+      ptx::mbar_init(&v_full[s], 1);
+      ptx::mbar_init(&v_empty[s], 1);
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&p_full[s], 128);
+      ptx::mbar_init(&pv_done[s], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 9) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 10) {
+    ptx::setmaxnreg_dec<kDataRegs>();  // idle warps of the data-path warpgroup
+  } else if (warp == 8) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    ptx::setmaxnreg_dec<kDataRegs>();
+    if (lane == 0) {
+      ptx::mbar_expect_tx(q_full, 2 * kQTileBytes);
+      for (int t = 0; t < 2; ++t) {
+        ptx::tma_load_2d(smem + kOffQ + t * kQTileBytes, &tmap_q, q_full, head * kHD, q0 + t * kBQ);
+        ptx::tma_load_2d(smem + kOffQ + t * kQTileBytes + kQTileBytes / 2, &tmap_q, q_full, head * kHD + 64, q0 + t * kBQ);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int kv0 = tile_of(j) * kBKV;
+        wait_segments(p, kv0, kBKV);
+        ptx::mbar_wait(&k_empty[s], ph ^ 1);
+        ptx::mbar_expect_tx(&k_full[s], kKBytes);
+        ptx::tma_load_2d(smem + kOffK + s * kKBytes, &tmap_k, &k_full[s], head * kHD, kv0);
+        ptx::tma_load_2d(smem + kOffK + s * kKBytes + kKBytes / 2, &tmap_k, &k_full[s], head * kHD + 64, kv0);
+        ptx::mbar_wait(&v_empty[s], ph ^ 1);
+        ptx::mbar_expect_tx(&v_full[s], kVBytes);
+        ptx::tma_load_2d(smem + kOffV + s * kVBytes, &tmap_v, &v_full[s], head * kHD, kv0);
+        ptx::tma_load_2d(smem + kOffV + s * kVBytes + kVBytes / 2, &tmap_v, &v_full[s], head * kHD + 64, kv0);
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    ptx::setmaxnreg_dec<kDataRegs>();
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(kBQ, kBKV);      // S: 128 x 128, both operands K-major
+      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32_bmn(kBQ, kHD);   // O: 128 x 128, B = V tile MN-major
+      auto issue_s = [&](int t, int j) {  // S_t(j) = Q_t K_j^T
+        const uint32_t q_addr = ptx::smem_u32(smem + kOffQ + t * kQTileBytes);
+        const uint32_t k_addr = ptx::smem_u32(smem + kOffK + (j & 1) * kKBytes);
+#pragma unroll
+        for (int kk = 0; kk < kHD / 16; ++kk) {
+          const uint64_t da = ptx::umma_desc_sw128_kmajor(q_addr + (kk >> 2) * (kQTileBytes / 2)) + 2 * (kk & 3);
+          const uint64_t db = ptx::umma_desc_sw128_kmajor(k_addr + (kk >> 2) * (kKBytes / 2)) + 2 * (kk & 3);
+          ptx::umma_ss(tmem_base + t * 128, da, db, idesc_s, kk != 0 ? 1u : 0u);
+        }
+      };
+      ptx::mbar_wait(q_full, 0);
+      ptx::mbar_wait(&k_full[0], 0);
+      ptx::tc_fence_after();
+      issue_s(0, 0);
+      ptx::umma_commit(&s_full[0]);
+      issue_s(1, 0);
+      ptx::umma_commit(&k_empty[0]);
+      ptx::umma_commit(&s_full[1]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t v_addr = ptx::smem_u32(smem + kOffV + (j & 1) * kVBytes);
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(&p_full[t], j & 1);
+          if (t == 0) ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < kBKV / 16; ++kk) {  // O_t += P_t(j) V_j : A from TMEM (8 packed columns per K16 step)
+            const uint64_t db = ptx::umma_desc_sw128_mnmajor(v_addr + kk * 2048, p.v_lbo, p.v_sbo);
+            ptx::umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
+          }
+          if (t == 1) ptx::umma_commit(&v_empty[j & 1]);
+          ptx::umma_commit(&pv_done[t]);
+          if (j + 1 < n_tiles) {
+            if (t == 0) {
+              ptx::mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+              ptx::tc_fence_after();
+            }
+            issue_s(t, j + 1);  // overwrites S_t / P_t(j): ordered behind PV_t(j) by the tensor pipe
+            if (t == 1) ptx::umma_commit(&k_empty[(j + 1) & 1]);
+            ptx::umma_commit(&s_full[t]);  // fires when S_t(j+1) AND everything before it (PV_t(j)) has completed
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------ softmax warpgroups ------------------------------------------
+    ptx::setmaxnreg_inc<kSoftmaxRegs>();
+    const int t = warp >> 2;                       // query tile of this warpgroup
+    const int r = (warp & 3) * 32 + lane;          // row inside the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tmem_s = tmem_base + t * 128 + lane_sel;
+    const uint32_t tmem_o = tmem_base + 256 + t * 128 + lane_sel;
+    const uint64_t scale2 = ptx::pack_f32x2(p.scale_log2, p.scale_log2);
+    float m = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      // s_full(j) also certifies that PV_t(j-1) has completed (commit semantics): O_t is quiescent until p_full(j) is signalled
+      ptx::mbar_wait(&s_full[t], j & 1);
+      ptx::tc_fence_after();
+      uint32_t sreg[4][32];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) ptx::tmem_ld_32x32b_x32(tmem_s + h * 32, sreg[h]);
+      ptx::tmem_ld_wait();
+      const int valid = p.Lk - tile_of(j) * kBKV;  // columns >= valid are padding (only the globally last tile)
+      if (valid < kBKV) {  // warp-uniform, at most once per CTA
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (h * 32 + c >= valid) sreg[h][c] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains of 3-input max: 0.5 instruction per element
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          mx0 = ptx::max3(mx0, __uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1]));
+          mx1 = ptx::max3(mx1, __uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3]));
+        }
+      const float m_new = fmaxf(m, fmaxf(mx0, mx1) * p.scale_log2);
+      if (j == 0) {
+        m = m_new;
+      } else {
+        const bool need = m_new > m + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          const float factor = need ? ptx::ex2_approx(m - m_new) : 1.0f;
+          if (need) {
+            l *= factor;
+            m = m_new;
+          }
+#pragma unroll 1
+          for (int c = 0; c < kHD / 32; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld_32x32b_x32(tmem_o + c * 32, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            ptx::tmem_st_32x32b_x32(tmem_o + c * 32, o);
+          }
+        }
+      }
+      // P = 2^(s*scale - m), row sum in fp32 before the bf16 rounding (as flash-attention does). Packed fp32x2 FMA / ADD;
+      // 32 columns -> 16 packed words, stored over the consumed S columns right away.
+      const uint64_t negm2 = ptx::pack_f32x2(-m, -m);
+      uint64_t sum2a = 0ull, sum2b = 0ull;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float a0, a1, b0, b1;
+          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1])), scale2, negm2), a0, a1);
+          ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3])), scale2, negm2), b0, b1);
+          exp2_pair<EMU_MASK>(a0, a1, (h * 32 + c) >> 1);
+          exp2_pair<EMU_MASK>(b0, b1, ((h * 32 + c) >> 1) + 1);
+          sum2a = ptx::add_f32x2(sum2a, ptx::pack_f32x2(a0, a1));
+          sum2b = ptx::add_f32x2(sum2b, ptx::pack_f32x2(b0, b1));
+          pk[c >> 1] = pack_bf16x2(a0, a1);
+          pk[(c >> 1) + 1] = pack_bf16x2(b0, b1);
+        }
+        ptx::tmem_st_32x32b_x16(tmem_s + h * 16, pk);
+      }
+      float s0, s1, s2, s3;
+      ptx::unpack_f32x2(sum2a, s0, s1);
+      ptx::unpack_f32x2(sum2b, s2, s3);
+      l += (s0 + s1) + (s2 + s3);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&p_full[t]);
+    }
+
+    // ---- epilogue: O_t / l -> bf16 -> global (or the normalised fp32 partial of this split)
+    ptx::mbar_wait(&pv_done[t], (n_tiles - 1) & 1);
+    ptx::tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int row = q0 + t * kBQ + r;
+    if (p.splits > 1 && row < p.Lq)
+      p.part_ml[(static_cast<int64_t>(blockIdx.z) * p.Lq + row) * p.heads + head] = make_float2(m, l);
+#pragma unroll 1
+    for (int c = 0; c < kHD / 32; ++c) {
+      uint32_t o[32];
+      ptx::tmem_ld_32x32b_x32(tmem_o + c * 32, o);
+      ptx::tmem_ld_wait();
+      if (row < p.Lq) {
+        if (p.splits > 1) {
+          float* dst = p.part_o + (static_cast<int64_t>(blockIdx.z) * p.Lq + row) * (static_cast<int64_t>(p.heads) * kHD) + head * kHD + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
+                                                              __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        } else {
+          __nv_bfloat16* dst = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + i) = w;
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
+// short-sequence kernel: 128 query rows per CTA, 64-row KV tiles, two CTAs per SM
+// =====================================================================================================================
+namespace sk {
+constexpr int kBQ = 128, kBKV = 64;
+constexpr int kQBytes = kBQ * kHD * 2;   // 32 KB (two 64-column boxes of 16 KB)
+constexpr int kKBytes = kBKV * kHD * 2;  // 16 KB (two boxes of 8 KB)
+constexpr int kVBytes = kBKV * kHD * 2;  // 16 KB (two boxes [64 kv x 64 d] of 8 KB)
+constexpr int kKVStages = 2;
+constexpr int kOffQ = 0;
+constexpr int kOffK = kOffQ + kQBytes;
+constexpr int kOffV = kOffK + kKVStages * kKBytes;
+constexpr int kOffBar = kOffV + kKVStages * kVBytes;  // 96 KB
+constexpr int kSmem = kOffBar + 256;
+constexpr int kThreads = 192;   // warps 0-3 softmax, warp 4 TMA, warp 5 MMA
+constexpr int kTmemCols = 256;  // S0 [0,64) S1 [64,128) O [128,256)
+}  // namespace sk
+
+__global__ void __launch_bounds__(sk::kThreads, 2)
+    attn_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                      const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using namespace sk;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars + 0;
@@ -65,28 +396,26 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
   uint64_t* v_full = bars + 5;   // [2]
   uint64_t* v_empty = bars + 7;  // [2]
   uint64_t* s_full = bars + 9;   // [2]
-  uint64_t* s_free = bars + 11;  // [2]
-  uint64_t* p_full = bars + 13;
-  uint64_t* pv_done = bars + 14;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_full = bars + 11;
+  uint64_t* pv_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
-  constexpr bool P_IN_TMEM = VARIANT >= 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ;
   const int head = blockIdx.y;
   const int total_tiles = (p.Lk + kBKV - 1) / kBKV;
   const int per_split = (total_tiles + p.splits - 1) / p.splits;
-  const int t0 = blockIdx.z * per_split;                       // first (global) KV tile of this CTA
-  const int n_tiles = min(per_split, total_tiles - t0);        // local tile count (>= 1, guaranteed by the host)
+  const int t0 = blockIdx.z * per_split;                 // first (global) KV tile of this CTA
+  const int n_tiles = min(per_split, total_tiles - t0);  // local tile count (>= 1, guaranteed by the host)
 
   if (threadIdx.x == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) {
-      printf("attn_fwd_kernel: dynamic smem base not 1024-aligned\n");
+      printf("attn_short_kernel: dynamic smem base not 1024-aligned\n");
       __trap();
     }
     ptx::prefetch_tmap(&tmap_q);
     ptx::prefetch_tmap(&tmap_k);
-    ptx::prefetch_tmap(&tmap_vt);
+    ptx::prefetch_tmap(&tmap_v);
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&k_full[s], 1);
@@ -94,7 +423,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       ptx::mbar_init(&v_full[s], 1);
       ptx::mbar_init(&v_empty[s], 1);
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&s_free[s], 128);
     }
     ptx::mbar_init(p_full, 128);
     ptx::mbar_init(pv_done, 1);
@@ -116,22 +444,23 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
+        const int kv0 = (t0 + j) * kBKV;
         ptx::mbar_wait(&k_empty[s], ph ^ 1);
         ptx::mbar_expect_tx(&k_full[s], kKBytes);
-        ptx::tma_load_2d(smem + kOffK + s * kKBytes, &tmap_k, &k_full[s], head * kHD, (t0 + j) * kBKV);
-        ptx::tma_load_2d(smem + kOffK + s * kKBytes + kKBytes / 2, &tmap_k, &k_full[s], head * kHD + 64, (t0 + j) * kBKV);
+        ptx::tma_load_2d(smem + kOffK + s * kKBytes, &tmap_k, &k_full[s], head * kHD, kv0);
+        ptx::tma_load_2d(smem + kOffK + s * kKBytes + kKBytes / 2, &tmap_k, &k_full[s], head * kHD + 64, kv0);
         ptx::mbar_wait(&v_empty[s], ph ^ 1);
         ptx::mbar_expect_tx(&v_full[s], kVBytes);
-        ptx::tma_load_2d(smem + kOffV + s * kVBytes, &tmap_vt, &v_full[s], (t0 + j) * kBKV, head * kHD);
+        ptx::tma_load_2d(smem + kOffV + s * kVBytes, &tmap_v, &v_full[s], head * kHD, kv0);
+        ptx::tma_load_2d(smem + kOffV + s * kVBytes + kVBytes / 2, &tmap_v, &v_full[s], head * kHD + 64, kv0);
       }
     }
   } else if (warp == 5) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(kBQ, kBKV);  // 128 x 64
-      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32(kBQ, kHD);   // 128 x 128
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(kBQ, kBKV);     // 128 x 64
+      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32_bmn(kBQ, kHD);  // 128 x 128, B = V tile MN-major
       const uint32_t q_addr = ptx::smem_u32(smem + kOffQ);
-      const uint32_t p_addr = ptx::smem_u32(smem + kOffP);
       auto issue_s = [&](int j) {
         const int s = j & 1;
         const uint32_t k_addr = ptx::smem_u32(smem + kOffK + s * kKBytes);
@@ -153,9 +482,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         if (j + 1 < n_tiles) {
           const int t = j + 1;
           ptx::mbar_wait(&k_full[t & 1], (t >> 1) & 1);
-          // S buffer t&1 was last used by tile t-2: its softmax must have drained it. With P in TMEM that is implied by
-          // p_full(t-2) (waited before PV(t-2) was issued) and the in-order execution of PV(t-2) before this MMA.
-          if (!P_IN_TMEM && t >= 2) ptx::mbar_wait(&s_free[t & 1], ((t - 2) >> 1) & 1);
+          // S buffer t&1 was last used by tile t-2: its softmax drained it before p_full(t-2), which was waited before PV(t-2)
+          // was issued, and PV(t-2) (the reader of P in that buffer) executes before this MMA on the in-order tensor pipe.
           ptx::tc_fence_after();
           issue_s(t);
         }
@@ -165,13 +493,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
         const uint32_t v_addr = ptx::smem_u32(smem + kOffV + (j & 1) * kVBytes);
 #pragma unroll
         for (int kk = 0; kk < kBKV / 16; ++kk) {
-          const uint64_t db = ptx::umma_desc_sw128_kmajor(v_addr) + 2 * kk;
-          if (P_IN_TMEM) {
-            ptx::umma_ts(tmem_o, tmem_base + (j & 1) * kBKV + kk * 8, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
-          } else {
-            const uint64_t da = ptx::umma_desc_sw128_kmajor(p_addr) + 2 * kk;
-            ptx::umma_ss(tmem_o, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
-          }
+          const uint64_t db = ptx::umma_desc_sw128_mnmajor(v_addr + kk * 2048, p.v_lbo, p.v_sbo);
+          ptx::umma_ts(tmem_o, tmem_base + (j & 1) * kBKV + kk * 8, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
         }
         ptx::umma_commit(&v_empty[j & 1]);
         ptx::umma_commit(pv_done);
@@ -182,8 +505,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
     const int r = warp * 32 + lane;  // row inside the Q tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
     float m = -INFINITY, l = 0.f;
-    uint8_t* p_row = smem + kOffP + (r >> 3) * 1024 + (r & 7) * 128;
-    const int sw = r & 7;
     for (int j = 0; j < n_tiles; ++j) {
       const int b = j & 1;
       ptx::mbar_wait(&s_full[b], (j >> 1) & 1);
@@ -192,10 +513,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV, sreg[0]);
       ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV + 32, sreg[1]);
       ptx::tmem_ld_wait();
-      if (!P_IN_TMEM) {
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&s_free[b]);
-      }
 
       const int valid = p.Lk - (t0 + j) * kBKV;  // columns >= valid are padding (only possible on the last tile)
       if (valid < kBKV) {                  // warp-uniform, taken at most once per CTA
@@ -205,7 +522,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
           for (int c = 0; c < 32; ++c)
             if (h * 32 + c >= valid) sreg[h][c] = 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains of 3-input max: 0.5 instruction per element
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -242,8 +559,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
           ptx::tmem_st_wait();
         }
       }
-      // P = 2^(s*scale - m), row sum in fp32 before the bf16 rounding (as flash-attention does).
-      // Packed fp32x2 FMA / ADD: one FFMA2 + two MUFU.EX2 + one FADD2 + one bf16x2 pack per pair of elements.
       const uint64_t scale2 = ptx::pack_f32x2(p.scale_log2, p.scale_log2);
       const uint64_t negm2 = ptx::pack_f32x2(-m, -m);
       uint64_t sum2a = 0ull, sum2b = 0ull;  // (+0.f, +0.f)
@@ -255,21 +570,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
           float a0, a1, b0, b1;
           ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1])), scale2, negm2), a0, a1);
           ptx::unpack_f32x2(ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3])), scale2, negm2), b0, b1);
-          // POLY / 4 of the exponentials are evaluated on the FMA pipe (ptx::ex2_emul_pair) to take them off the MUFU, which
-          // this loop otherwise keeps as busy as the tensor pipe (profiles/r01_ncu_attn.md): 1 = every other (b0, b1) pair,
-          // 2 = every (b0, b1) pair, 3 = those plus every other (a0, a1) pair.
-          if (POLY >= 3 && (c & 4)) {
-            ptx::ex2_emul_pair(a0, a1);
-          } else {
-            a0 = ptx::ex2_approx(a0);
-            a1 = ptx::ex2_approx(a1);
-          }
-          if (POLY >= 2 || (POLY == 1 && (c & 4))) {
-            ptx::ex2_emul_pair(b0, b1);
-          } else {
-            b0 = ptx::ex2_approx(b0);
-            b1 = ptx::ex2_approx(b1);
-          }
+          a0 = ptx::ex2_approx(a0);
+          a1 = ptx::ex2_approx(a1);
+          b0 = ptx::ex2_approx(b0);
+          b1 = ptx::ex2_approx(b1);
           sum2a = ptx::add_f32x2(sum2a, ptx::pack_f32x2(a0, a1));
           sum2b = ptx::add_f32x2(sum2b, ptx::pack_f32x2(b0, b1));
           packed[h * 16 + (c >> 1)] = pack_bf16x2(a0, a1);
@@ -278,30 +582,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
       float s0, s1, s2, s3;
       ptx::unpack_f32x2(sum2a, s0, s1);
       ptx::unpack_f32x2(sum2b, s2, s3);
-      const float psum = (s0 + s1) + (s2 + s3);
-      l += psum;
-      if (P_IN_TMEM) {
-        // P_j overwrites the first 32 columns of S buffer b (64 bf16 per row = 32 packed words); its reader PV(j) is ordered
-        // before S(j+2) by the tensor pipe.
-        // An mbarrier parity wait can only tell the current phase from the one before it, so a waiter must never fall two
-        // phases behind. pv_done completes one phase per tile; a softmax thread that skipped it would reach the epilogue while
-        // PV(n-2) is still in flight, and its wait for PV(n-1) would then be satisfied by the parity of PV(n-3): O read early,
-        // run-to-run different results (caught by the full-shape determinism test, tools/diag_determinism.py). Observing
-        // PV(j-1) here every tile costs nothing measurable — it has normally completed long before — and keeps the phases aligned.
-        if (j > 0 && !waited) ptx::mbar_wait(pv_done, (j - 1) & 1);
-        ptx::tmem_st_32x32b_x32(tmem_base + lane_sel + b * kBKV, packed);
-        ptx::tmem_st_wait();
-      } else {
-        if (j > 0 && !waited) {
-          ptx::mbar_wait(pv_done, (j - 1) & 1);  // PV(j-1) has finished reading the single smem P buffer
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {  // 8 x 16-byte chunks per 128-byte row, XOR-swizzled with (row % 8)
-          uint4 w = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
-          *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) = w;
-        }
-        ptx::fence_proxy_async_smem();
-      }
+      l += (s0 + s1) + (s2 + s3);
+      // P_j overwrites the first 32 columns of S buffer b (64 bf16 per row = 32 packed words); its reader PV(j) is ordered
+      // before S(j+2) by the tensor pipe.
+      // An mbarrier parity wait can only tell the current phase from the one before it, so a waiter must never fall two
+      // phases behind. pv_done completes one phase per tile; a softmax thread that skipped it would reach the epilogue while
+      // PV(n-2) is still in flight, and its wait for PV(n-1) would then be satisfied by the parity of PV(n-3): O read early,
+      // run-to-run different results (caught by the full-shape determinism test, tools/diag_determinism.py). Observing
+      // PV(j-1) here every tile costs nothing measurable — it has normally completed long before — and keeps the phases aligned.
+      if (j > 0 && !waited) ptx::mbar_wait(pv_done, (j - 1) & 1);
+      ptx::tmem_st_32x32b_x32(tmem_base + lane_sel + b * kBKV, packed);
+      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
     }
@@ -375,109 +666,148 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restri
   }
 }
 
-// scratch for the split-KV partials: grown on demand (first use happens in an eager call, before any graph capture)
-static float* g_part_o = nullptr;
-static float2* g_part_ml = nullptr;
-static size_t g_part_elems = 0;
+// ---- host side: work decomposition ----------------------------------------------------------------------------------
+struct AttnPlan {
+  bool long_kernel;
+  int q_blocks, kv_tile, total_tiles, splits;
+  size_t ws_bytes;  // workspace for the split partials (0 when unsplit)
+};
 
-static int32_t ensure_split_scratch(int splits, int Lq, int heads) {
-  const size_t need = static_cast<size_t>(splits) * Lq * heads * kHD;
-  if (need <= g_part_elems) return MC_OK;
-  // the previous (smaller) buffers are deliberately not freed: captured CUDA graphs may still point at them
-  g_part_o = nullptr;
-  g_part_ml = nullptr;
-  g_part_elems = 0;
-  cudaError_t e = cudaMalloc(&g_part_o, need * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&g_part_ml, static_cast<size_t>(splits) * Lq * heads * sizeof(float2));
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(split-KV scratch)");
-  g_part_elems = need;
-  return MC_OK;
+static int env_int(const char* name, int lo, int hi, int dflt) {
+  const char* e = getenv(name);
+  if (!e || !*e) return dflt;
+  const int v = atoi(e);
+  return (v < lo || v > hi) ? dflt : v;
 }
 
-}  // namespace mc
-
-extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* vt, int64_t ldvt, void* out,
-                               int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* stream) {
-  MC_CHECK_ARG(q && k && vt && out, "mc_attn_fwd: null pointer");
-  MC_CHECK_ARG(Lq >= 1 && Lk >= 1 && heads >= 1, "mc_attn_fwd: Lq=%d Lk=%d heads=%d", Lq, Lk, heads);
-  const int64_t width = static_cast<int64_t>(heads) * mc::kHD;
-  MC_CHECK_ARG(ldq >= width && ldk >= width && ldo >= width && ldvt >= Lk, "mc_attn_fwd: leading dimensions too small");
-  MC_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && ldo % 8 == 0, "mc_attn_fwd: leading dimensions must be multiples of 8");
-  MC_CHECK_ARG(mc::aligned16(q) && mc::aligned16(k) && mc::aligned16(vt) && mc::aligned16(out), "mc_attn_fwd: pointers must be 16-byte aligned");
-  CUtensorMap tq, tk, tv;
-  int32_t rc = mc::make_tmap_bf16_2d(&tq, q, static_cast<uint64_t>(Lq), static_cast<uint64_t>(width), static_cast<uint64_t>(ldq), mc::kBQ, 64);
-  if (rc) return rc;
-  rc = mc::make_tmap_bf16_2d(&tk, k, static_cast<uint64_t>(Lk), static_cast<uint64_t>(width), static_cast<uint64_t>(ldk), mc::kBKV, 64);
-  if (rc) return rc;
-  rc = mc::make_tmap_bf16_2d(&tv, vt, static_cast<uint64_t>(width), static_cast<uint64_t>(Lk), static_cast<uint64_t>(ldvt), mc::kHD, mc::kBKV);
-  if (rc) return rc;
-  static int variant = -1;  // MC_ATTN_VARIANT: 0 = P via smem, 1 = P in TMEM (default)
-  if (variant < 0) {
-    const char* ev = getenv("MC_ATTN_VARIANT");
-    const int v = (ev && ev[0] == '0') ? 0 : 1;
-    cudaError_t e = cudaFuncSetAttribute(mc::attn_fwd_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mc::attn_fwd_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mc::kAttnSmem);
-    if (e != cudaSuccess) return mc::cuda_fail(e, "cudaFuncSetAttribute(attn smem)");
-    variant = v;
-  }
-  // Work split. One CTA = one 128-row query tile of one head; with fewer than two waves of CTAs (2 per SM) the last,
-  // partially filled wave dominates (token-sharded runs: 4095 rows x 12 heads = 384 CTAs on 296 slots), so the KV range is
-  // split across blockIdx.z until there are about three waves, and the partial softmaxes are merged by a second kernel.
-  const int q_tiles = (Lq + mc::kBQ - 1) / mc::kBQ;
-  const int total_tiles = (Lk + mc::kBKV - 1) / mc::kBKV;
-  const double waves = static_cast<double>(q_tiles) * heads / (2.0 * mc::num_sms());
-  // MC_ATTN_POLY=k (0..3): k/4 of the softmax exponentials on the FMA pipe instead of the MUFU. Read per call (tools/bench_poly.py).
-  const char* ep = getenv("MC_ATTN_POLY");
-  int poly = ep ? atoi(ep) : mc::kDefaultPoly;
-  if (poly < 0 || poly > 3) poly = mc::kDefaultPoly;
-  // MC_ATTN_SPLITS=n forces n splits (1 = never split); unset/0 = choose by wave fill. Read per call (tools/bench_split.py).
-  const char* es = getenv("MC_ATTN_SPLITS");
-  int forced_splits = es ? atoi(es) : 0;
-  if (forced_splits < 0 || forced_splits > 16) forced_splits = 0;
+// One CTA = 256 (long kernel, 1 CTA/SM) or 128 (short kernel, 2 CTAs/SM) query rows of one head. With fewer than four waves of
+// CTAs the last, partially filled wave dominates (token-sharded runs: 4095 rows x 12 heads = 192 CTAs on 148 SMs), so the KV
+// range is split across blockIdx.z until the last wave is >= 92 % full, and the partial softmaxes are merged by a second kernel.
+static AttnPlan plan_attention(int Lq, int Lk, int heads) {
+  AttnPlan pl;
+  const int forced_splits = env_int("MC_ATTN_SPLITS", 1, 16, 0);  // MC_ATTN_SPLITS=n forces n splits (1 = never split)
+  const int kernel_sel = env_int("MC_ATTN_KERNEL", 0, 2, 0);  // 0 = by Lk, 1 = short, 2 = long (tests / A-B timing)
+  pl.long_kernel = kernel_sel == 2 || (kernel_sel == 0 && Lk >= kLongMinLk);
+  const int rows_per_cta = pl.long_kernel ? 2 * lk::kBQ : sk::kBQ;
+  pl.kv_tile = pl.long_kernel ? lk::kBKV : sk::kBKV;
+  pl.q_blocks = (Lq + rows_per_cta - 1) / rows_per_cta;
+  pl.total_tiles = (Lk + pl.kv_tile - 1) / pl.kv_tile;
+  const double slots = (pl.long_kernel ? 1.0 : 2.0) * num_sms();
+  const double waves = static_cast<double>(pl.q_blocks) * heads / slots;
+  const int min_tiles_per_split = pl.long_kernel ? 4 : 8;
   int splits = 1;
   if (forced_splits > 0) {
     splits = forced_splits;
-  } else if (waves < 4.0 && total_tiles >= 16) {
-    // smallest split count whose last wave is at least 92 % full, else the fullest
+  } else if (waves < 4.0 && pl.total_tiles >= 2 * min_tiles_per_split) {
     double best = 0.0;
-    for (int sp = 1; sp <= 8 && sp * 8 <= total_tiles; ++sp) {
+    for (int sp = 1; sp <= 8 && sp * min_tiles_per_split <= pl.total_tiles; ++sp) {
       const double w = waves * sp, fill = w / static_cast<double>(static_cast<int64_t>(w + 0.999999));
       if (fill > best + 1e-9) best = fill, splits = sp;
       if (fill >= 0.92) break;
     }
   }
-  if (splits > total_tiles) splits = total_tiles;
+  if (splits > pl.total_tiles) splits = pl.total_tiles;
   if (splits > 1) {
-    const int per = (total_tiles + splits - 1) / splits;
-    splits = (total_tiles + per - 1) / per;  // no empty split
+    const int per = (pl.total_tiles + splits - 1) / splits;
+    splits = (pl.total_tiles + per - 1) / per;  // no empty split
   }
-  if (splits > 1) {
-    MC_CHECK_ARG(ldo % 8 == 0, "mc_attn_fwd: ldo must be a multiple of 8");
-    rc = mc::ensure_split_scratch(splits, Lq, heads);
-    if (rc) return rc;
+  pl.splits = splits;
+  pl.ws_bytes = splits > 1 ? static_cast<size_t>(splits) * Lq * heads * (kHD * sizeof(float) + sizeof(float2)) : 0;
+  return pl;
+}
+
+}  // namespace mc
+
+extern "C" int32_t mc_attn_workspace_bytes(int32_t Lq, int32_t Lk, int32_t heads, int64_t* bytes_out) {
+  MC_CHECK_ARG(bytes_out != nullptr && Lq >= 1 && Lk >= 1 && heads >= 1, "mc_attn_workspace_bytes: bad arguments");
+  *bytes_out = static_cast<int64_t>(mc::plan_attention(Lq, Lk, heads).ws_bytes);
+  return MC_OK;
+}
+
+extern "C" int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                                  int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* workspace,
+                                  int64_t workspace_bytes, int32_t first_key_row, const uint32_t* seg_flags, uint32_t seg_epoch,
+                                  int32_t seg_rows, void* stream) {
+  MC_CHECK_ARG(q && k && v && out, "mc_attn_fwd: null pointer");
+  MC_CHECK_ARG(Lq >= 1 && Lk >= 1 && heads >= 1, "mc_attn_fwd: Lq=%d Lk=%d heads=%d", Lq, Lk, heads);
+  const int64_t width = static_cast<int64_t>(heads) * mc::kHD;
+  MC_CHECK_ARG(ldq >= width && ldk >= width && ldo >= width && ldv >= width, "mc_attn_fwd: leading dimensions too small");
+  MC_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "mc_attn_fwd: leading dimensions must be multiples of 8");
+  MC_CHECK_ARG(mc::aligned16(q) && mc::aligned16(k) && mc::aligned16(v) && mc::aligned16(out), "mc_attn_fwd: pointers must be 16-byte aligned");
+  MC_CHECK_ARG(first_key_row >= 0 && first_key_row < Lk, "mc_attn_fwd: first_key_row=%d outside [0, %d)", first_key_row, Lk);
+  MC_CHECK_ARG(seg_flags == nullptr || seg_rows >= 1, "mc_attn_fwd: seg_rows=%d", seg_rows);
+  const mc::AttnPlan pl = mc::plan_attention(Lq, Lk, heads);
+  MC_CHECK_ARG(pl.long_kernel || (first_key_row == 0 && seg_flags == nullptr),
+               "mc_attn_fwd: rotated / flag-gated key order needs the long-sequence kernel (Lk >= %d)", mc::kLongMinLk);
+  if (pl.splits > 1) {
+    MC_CHECK_ARG(workspace != nullptr && workspace_bytes >= static_cast<int64_t>(pl.ws_bytes) && (reinterpret_cast<uintptr_t>(workspace) & 31u) == 0,
+                 "mc_attn_fwd: split-KV needs a 32-byte aligned workspace of %lld bytes (mc_attn_workspace_bytes), got %lld",
+                 static_cast<long long>(pl.ws_bytes), static_cast<long long>(workspace_bytes));
   }
-  mc::AttnParams p{Lq, Lk, heads, splits, mc::g_part_o, mc::g_part_ml, scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo};
-  dim3 grid(q_tiles, heads, splits);
+  const int q_box = pl.long_kernel ? mc::lk::kBQ : mc::sk::kBQ;
+  CUtensorMap tq, tk, tv;
+  int32_t rc = mc::make_tmap_bf16_2d(&tq, q, static_cast<uint64_t>(Lq), static_cast<uint64_t>(width), static_cast<uint64_t>(ldq), q_box, 64);
+  if (rc) return rc;
+  rc = mc::make_tmap_bf16_2d(&tk, k, static_cast<uint64_t>(Lk), static_cast<uint64_t>(width), static_cast<uint64_t>(ldk), pl.kv_tile, 64);
+  if (rc) return rc;
+  rc = mc::make_tmap_bf16_2d(&tv, v, static_cast<uint64_t>(Lk), static_cast<uint64_t>(width), static_cast<uint64_t>(ldv), pl.kv_tile, 64);
+  if (rc) return rc;
+
+  float* part_o = static_cast<float*>(workspace);
+  float2* part_ml = pl.splits > 1 ? reinterpret_cast<float2*>(part_o + static_cast<size_t>(pl.splits) * Lq * heads * mc::kHD) : nullptr;
+  mc::AttnParams p{};
+  p.Lq = Lq, p.Lk = Lk, p.heads = heads, p.splits = pl.splits;
+  p.part_o = pl.splits > 1 ? part_o : nullptr, p.part_ml = part_ml;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = static_cast<__nv_bfloat16*>(out), p.ldo = ldo;
+  // MN-major V tile: two TMA boxes [kv_tile rows][64 d] -> box stride = kv_tile * 128 B, 8-row groups 1024 B apart.
+  // MC_ATTN_VDESC=1 swaps the two (descriptor bring-up aid, tools/diag_vdesc.py).
+  p.v_lbo = static_cast<uint32_t>(pl.kv_tile) * 128u, p.v_sbo = 1024u;
+  if (mc::env_int("MC_ATTN_VDESC", 0, 1, 0) == 1) p.v_lbo = 1024u, p.v_sbo = static_cast<uint32_t>(pl.kv_tile) * 128u;
+  // start with the first tile that lies entirely inside the caller's own (already resident) rows; the tile straddling the segment
+  // boundary before it comes last in the rotated order
+  p.tile_rot = ((first_key_row + pl.kv_tile - 1) / pl.kv_tile) % pl.total_tiles;
+  p.seg_flags = seg_flags, p.seg_epoch = seg_epoch, p.seg_rows = seg_rows > 0 ? seg_rows : Lk;
+
+  dim3 grid(pl.q_blocks, heads, pl.splits);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (variant == 1)
-    switch (poly) {
-      case 1: mc::attn_fwd_kernel<1, 1><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p); break;
-      case 2: mc::attn_fwd_kernel<1, 2><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p); break;
-      case 3: mc::attn_fwd_kernel<1, 3><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p); break;
-      default: mc::attn_fwd_kernel<1, 0><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p); break;
+  if (pl.long_kernel) {
+    static mc::PerDeviceOnce once[4];
+    // MC_ATTN_EMU = eighths of the exponentials evaluated on the FMA pipe: 0, 2 (25 %), 3 (37.5 %), 4 (50 %)
+    const int emu = mc::env_int("MC_ATTN_EMU", 0, 4, MC_ATTN_EMU_DEFAULT);
+#define MC_LAUNCH_LONG(MASK, IDX)                                                                                             \
+  do {                                                                                                                        \
+    rc = mc::set_max_smem_once(mc::attn_long_kernel<MASK>, mc::lk::kSmem, once[IDX], "cudaFuncSetAttribute(attn long smem)"); \
+    if (rc) return rc;                                                                                                        \
+    mc::attn_long_kernel<MASK><<<grid, mc::lk::kThreads, mc::lk::kSmem, st>>>(tq, tk, tv, p);                                 \
+  } while (0)
+    switch (emu) {
+      case 2: MC_LAUNCH_LONG(0x88u, 1); break;
+      case 3: MC_LAUNCH_LONG(0x92u, 2); break;
+      case 4: MC_LAUNCH_LONG(0xAAu, 3); break;
+      default: MC_LAUNCH_LONG(0x00u, 0); break;
     }
-  else
-    mc::attn_fwd_kernel<0, 0><<<grid, mc::kAttnThreads, mc::kAttnSmem, st>>>(tq, tk, tv, p);
-  MC_CHECK_LAUNCH("attn_fwd_kernel launch");
-  if (splits > 1) {
+#undef MC_LAUNCH_LONG
+    MC_CHECK_LAUNCH("attn_long_kernel launch");
+  } else {
+    static mc::PerDeviceOnce once;
+    rc = mc::set_max_smem_once(mc::attn_short_kernel, mc::sk::kSmem, once, "cudaFuncSetAttribute(attn short smem)");
+    if (rc) return rc;
+    mc::attn_short_kernel<<<grid, mc::sk::kThreads, mc::sk::kSmem, st>>>(tq, tk, tv, p);
+    MC_CHECK_LAUNCH("attn_short_kernel launch");
+  }
+  if (pl.splits > 1) {
     const int64_t total = static_cast<int64_t>(Lq) * heads * (mc::kHD / 8);
     const int64_t want = (total + 255) / 256, cap = static_cast<int64_t>(mc::num_sms()) * 8;
-    mc::attn_combine_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, st>>>(mc::g_part_o, mc::g_part_ml, splits, Lq, heads,
+    mc::attn_combine_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, st>>>(p.part_o, p.part_ml, pl.splits, Lq, heads,
                                                                                       static_cast<__nv_bfloat16*>(out), ldo);
     MC_CHECK_LAUNCH("attn_combine_kernel launch");
   }
   return MC_OK;
+}
+
+extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                               int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+  return mc_attn_fwd_ex(q, ldq, k, ldk, v, ldv, out, ldo, Lq, Lk, heads, scale, workspace, workspace_bytes, 0, nullptr, 0, 0, stream);
 }

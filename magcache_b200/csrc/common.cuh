@@ -33,7 +33,27 @@ inline int32_t cuda_fail(cudaError_t e, const char* what) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device (controller.cu)
+int num_sms();  // cudaDevAttrMultiProcessorCount of the current device, cached per device (controller.cu)
+
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel, device), not per process.
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+};
+template <typename Kernel>
+inline int32_t set_max_smem_once(Kernel kernel, int bytes, PerDeviceOnce& once, const char* what) {
+  const int d = current_device();
+  if (once.done[d]) return MC_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  once.done[d] = true;
+  return MC_OK;
+}
 
 // ---- device-side dtype helpers -----------------------------------------------------------------
 template <typename T>

@@ -24,15 +24,16 @@ void set_error(const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached[dev] = n;
     else
-      cached = 148;
+      cached[dev] = 148;
   }
-  return cached;
+  return cached[dev];
 }
 
 // first call index that is allowed to skip (single-threshold modes)
@@ -137,7 +138,7 @@ static void advance(const mc_ctrl_config* c, mc_ctrl_state* st) {
 extern "C" {
 
 const char* mc_last_error(void) { return mc::g_err; }
-int32_t mc_abi_version(void) { return 3; }
+int32_t mc_abi_version(void) { return 4; }
 
 int32_t mc_nearest_interp(const double* src, int32_t L, double* dst, int32_t T) {
   MC_CHECK_ARG(src && dst, "mc_nearest_interp: null pointer");

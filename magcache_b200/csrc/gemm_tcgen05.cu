@@ -18,6 +18,15 @@
 
 namespace mc {
 
+TmapCacheEntry* tmap_cache() {
+  static TmapCacheEntry table[kTmapCacheSize] = {};
+  return table;
+}
+std::mutex& tmap_cache_mutex() {
+  static std::mutex m;
+  return m;
+}
+
 constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 4;
 constexpr int kTileABytes = kBM * kBK * 2;  // 16 KB
 constexpr int kTileBBytes = kBN * kBK * 2;  // 32 KB
@@ -289,12 +298,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
 template <int EPI>
 static int32_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm smem)");
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  const int32_t rc = set_max_smem_once(gemm_bf16_kernel<EPI>, kGemmSmem, once, "cudaFuncSetAttribute(gemm smem)");
+  if (rc) return rc;
   const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + kBN - 1) / kBN;
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();

@@ -1,0 +1,427 @@
+// Head of the Wan forward — LayerNorm (no affine) + modulation + fp32 Linear(cols -> 64) + unpatchify — and the cache-hit branch
+// in front of it, as ONE streaming pass (MagCache4Wan2.1/magcache_generate.py:293-295 `x = x + residual_x`, :304-305 `head`,
+// `unpatchify`; `Head` itself is upstream wan/modules/model.py [EXT], restated in oracle/wan_ref.py::Head).
+//
+// The row statistics and the Linear commute:   with  s_k = 1 + e1_k,  t_k = e0_k,  W'_ck = s_k W_ck,
+//     y_c = sum_k ((x_k - mu) rstd s_k + t_k) W_ck + b_c = rstd * (sum_k x_k W'_ck - mu * sum_k W'_ck) + (sum_k t_k W_ck + b_c)
+// so every row is read exactly ONCE: while its 64-column chunks stream through registers the kernel (a) accumulates the row's
+// mean / M2 (Chan's pairwise update, fp32) and (b) feeds the raw values to the tensor cores as the A operand of a
+// [rows x cols] x [cols x 64] GEMM against W'. The reference runs this Linear in fp32 (`amp.autocast(dtype=torch.float32)`), so
+// the GEMM uses a 3-pass split: x = x_hi + x_lo, W' = W'_hi + W'_lo (bf16 pairs), acc = x_hi W'_hi + x_lo W'_hi + x_hi W'_lo in
+// fp32 TMEM accumulators — products carry ~2^-17 relative error instead of bf16's 2^-9. To keep `acc - mu * c1` from cancelling when
+// a row has a large common offset, every row is shifted by a pilot value p (the mean of its first 64 elements) before the split;
+// LayerNorm is shift invariant, so only mu changes to mu - p.
+//
+// HBM-bound: per row cols * 4 B (fp32 stream), or cols * (2 + 4) B on a cache hit (bf16 patch embedding + fp32 cached residual,
+// the sum never materialised), + 256 B out. Persistent CTAs, each owning a contiguous row range (balanced to one row), 16 converter
+// warps (4 threads per row, 256-bit loads, next chunk prefetched into registers), 1 TMA warp (W' chunks), 1 MMA warp.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace mc {
+namespace hd {
+constexpr int kRows = 128, kKC = 64, kOut = 64, kStages = 3;
+constexpr int kATile = kRows * kKC * 2;  // 16 KB: one bf16 operand tile (hi or lo), 128-byte rows, 128-byte swizzle
+constexpr int kWTile = kOut * kKC * 2;   // 8 KB
+constexpr int kStageBytes = 2 * kATile + 2 * kWTile;  // 48 KB
+constexpr int kOffStats = kStages * kStageBytes;      // 144 KB
+constexpr int kOffBars = kOffStats + kRows * 8;
+constexpr int kSmem = kOffBars + 128;
+constexpr int kConvWarps = 16;
+constexpr int kConvThreads = kConvWarps * 32;  // 512: 4 threads per row
+constexpr int kThreads = kConvThreads + 128;   // + one data-path warpgroup: TMA warp, MMA warp, two idle warps
+constexpr int kConvRegs = 112, kDataRegs = 40; // setmaxnreg: the data-path warpgroup hands its registers to the converters
+constexpr int kTmemCols = 64;
+constexpr int kMaxPeers = 8;
+}  // namespace hd
+
+struct HeadParams {
+  const void* x;       // [rows, cols] fp32, or bf16 when r != nullptr
+  const float* r;      // cached residual (cache-hit branch) or nullptr
+  int x_bf16, round_sum_bf16;
+  int64_t rows, row_offset;
+  int cols, F, Hp, Wp;
+  int rows_per_cta;
+  const float* c1;     // [64] sum_k W'_ck
+  const float* c0;     // [64] sum_k t_k W_ck + b_c
+  float eps;
+  float* out[hd::kMaxPeers];  // fp32 [16, F, 2Hp, 2Wp] — the caller's own and, token-sharded, every peer's (P2P stores)
+  int n_out;
+};
+
+// ---- per-forward preparation: W' = (1 + e1) * W split into bf16 hi / lo, K-major [64, cols]; c1, c0 ----------------------------
+__global__ void __launch_bounds__(256) head_prep_kernel(const float* __restrict__ head_mod, const float* __restrict__ e,
+                                                        const float* __restrict__ Wt, const float* __restrict__ bias, int cols,
+                                                        __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo,
+                                                        float* __restrict__ c1, float* __restrict__ c0) {
+  __shared__ double red[2][8];
+  const int c = blockIdx.x;
+  double s1 = 0.0, s0 = 0.0;
+  for (int k = threadIdx.x; k < cols; k += blockDim.x) {
+    const float sk = 1.0f + (head_mod[cols + k] + e[k]);  // e[1] = modulation[1] + e
+    const float tk = head_mod[k] + e[k];                  // e[0] = modulation[0] + e
+    const float w = Wt[static_cast<int64_t>(k) * hd::kOut + c];
+    const float wp = sk * w;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(wp);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(wp - __bfloat162float(hi));
+    w_hi[static_cast<int64_t>(c) * cols + k] = hi;
+    w_lo[static_cast<int64_t>(c) * cols + k] = lo;
+    s1 += static_cast<double>(__bfloat162float(hi)) + static_cast<double>(__bfloat162float(lo));  // what the MMA multiplies by
+    s0 += static_cast<double>(tk) * static_cast<double>(w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s1;
+    red[1][threadIdx.x >> 5] = s0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) a += red[0][i], b += red[1][i];
+    c1[c] = static_cast<float>(a);
+    c0[c] = static_cast<float>(b + static_cast<double>(bias[c]));
+  }
+}
+
+// 16 consecutive elements of one row chunk -> fp32 (the cache-hit sum formed in fp32 exactly like torch's promoted add)
+template <bool HIT>
+struct ChunkRegs {
+  float a[16];      // fp32 stream, or the fp32 residual on a hit
+  uint32_t b[8];    // bf16 patch embedding on a hit (unused otherwise)
+};
+
+template <bool HIT>
+__device__ __forceinline__ void load_chunk(const HeadParams& p, int64_t row, int k0, ChunkRegs<HIT>& c) {
+  if (HIT) {
+    const float* rp = p.r + row * p.cols + k0;
+    float t0[8], t1[8];
+    ptx::ld_nc_v8_f32(rp, t0);
+    ptx::ld_nc_v8_f32(rp + 8, t1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c.a[i] = t0[i], c.a[8 + i] = t1[i];
+    float tb[8];
+    ptx::ld_nc_v8_f32(reinterpret_cast<const float*>(static_cast<const __nv_bfloat16*>(p.x) + row * p.cols + k0), tb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c.b[i] = __float_as_uint(tb[i]);
+  } else {
+    const float* xp = static_cast<const float*>(p.x) + row * p.cols + k0;
+    float t0[8], t1[8];
+    ptx::ld_nc_v8_f32(xp, t0);
+    ptx::ld_nc_v8_f32(xp + 8, t1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c.a[i] = t0[i], c.a[8 + i] = t1[i];
+  }
+}
+
+template <bool HIT>
+__device__ __forceinline__ void chunk_values(const HeadParams& p, const ChunkRegs<HIT>& c, float (&v)[16]) {
+  if (HIT) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[2 * i] = bf16_lo(c.b[i]) + c.a[2 * i];          // `x + residual_x`: bf16 -> fp32 promotion, fp32 add
+      v[2 * i + 1] = bf16_hi(c.b[i]) + c.a[2 * i + 1];
+    }
+    if (p.round_sum_bf16) {  // in-place `x += residual` on a bf16 tensor (TeaCache comparator, wan_teacache.py:569/577)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = c.a[i];
+  }
+}
+
+template <bool HIT>
+__global__ void __launch_bounds__(hd::kThreads, 1)
+    head_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_constant__ CUtensorMap tmap_wlo, const HeadParams p) {
+  using namespace hd;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float2* stats = reinterpret_cast<float2*>(smem + kOffStats);  // (mean - pilot, rstd) per tile row
+  float* pilots = reinterpret_cast<float*>(stats + kRows);      // unused tail of the stats area is not needed: pilot folded into mean
+  (void)pilots;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t* a_full = bars + 0;               // [kStages] 16 arrivals (one per converter warp)
+  uint64_t* a_empty = bars + kStages;        // [kStages] tcgen05.commit
+  uint64_t* w_full = bars + 2 * kStages;     // [kStages] TMA
+  uint64_t* acc_full = bars + 3 * kStages;   // accumulator of the current row tile complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkc = p.cols / kKC;
+  const int64_t cta_row0 = static_cast<int64_t>(blockIdx.x) * p.rows_per_cta;
+  const int64_t cta_row1 = min(cta_row0 + p.rows_per_cta, p.rows);
+  const int n_sub = cta_row1 > cta_row0 ? static_cast<int>((cta_row1 - cta_row0 + kRows - 1) / kRows) : 0;
+
+  if (threadIdx.x == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) {
+      printf("head_tc_kernel: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    ptx::prefetch_tmap(&tmap_whi);
+    ptx::prefetch_tmap(&tmap_wlo);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&a_full[s], kConvWarps);
+      ptx::mbar_init(&a_empty[s], 1);
+      ptx::mbar_init(&w_full[s], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == kConvWarps + 1) ptx::tmem_alloc(tmem_slot, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp >= kConvWarps + 2) {
+    ptx::setmaxnreg_dec<kDataRegs>();  // idle warps of the data-path warpgroup
+  } else if (warp == kConvWarps) {
+    // ------------------------------------------------ TMA producer: W' hi / lo chunks ------------------------------------------
+    ptx::setmaxnreg_dec<kDataRegs>();
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int st = 0; st < n_sub; ++st)
+        for (int kc = 0; kc < nkc; ++kc, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          ptx::mbar_wait(&a_empty[s], ph ^ 1);  // the MMAs that read this stage (A and W') have completed
+          uint8_t* wdst = smem + s * kStageBytes + 2 * kATile;
+          ptx::mbar_expect_tx(&w_full[s], 2 * kWTile);
+          ptx::tma_load_2d(wdst, &tmap_whi, &w_full[s], kc * kKC, 0);
+          ptx::tma_load_2d(wdst + kWTile, &tmap_wlo, &w_full[s], kc * kKC, 0);
+        }
+    }
+  } else if (warp == kConvWarps + 1) {
+    // ------------------------------------------------ MMA issuer ----------------------------------------------------------------
+    ptx::setmaxnreg_dec<kDataRegs>();
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, kOut);  // 128 x 64, both operands K-major
+      uint32_t it = 0;
+      for (int st = 0; st < n_sub; ++st) {
+        for (int kc = 0; kc < nkc; ++kc, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          ptx::mbar_wait(&a_full[s], ph);
+          ptx::mbar_wait(&w_full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t base = ptx::smem_u32(smem + s * kStageBytes);
+          const uint64_t a_hi = ptx::umma_desc_sw128_kmajor(base), a_lo = ptx::umma_desc_sw128_kmajor(base + kATile);
+          const uint64_t w_hi = ptx::umma_desc_sw128_kmajor(base + 2 * kATile), w_lo = ptx::umma_desc_sw128_kmajor(base + 2 * kATile + kWTile);
+#pragma unroll
+          for (int k = 0; k < kKC / 16; ++k) {
+            ptx::umma_ss(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            ptx::umma_ss(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+            ptx::umma_ss(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+          }
+          ptx::umma_commit(&a_empty[s]);
+        }
+        ptx::umma_commit(acc_full);
+        // the next tile's first MMA overwrites the accumulator: it cannot be issued before a_full of its first chunk, which the
+        // epilogue warps only arrive on after they have drained the accumulator (program order in those warps)
+      }
+    }
+  } else {
+    // ------------------------------------------------ converter warps (+ epilogue) ---------------------------------------------
+    ptx::setmaxnreg_inc<kConvRegs>();
+    const int tid = threadIdx.x;
+    const int rt = tid >> 2, sub = tid & 3;  // tile row, 16-element slice of the 64-column chunk
+    const int sw = rt & 7;
+    uint32_t it = 0;
+    const float inv_cols = 1.0f / static_cast<float>(p.cols);
+    for (int st = 0; st < n_sub; ++st) {
+      const int64_t row = cta_row0 + static_cast<int64_t>(st) * kRows + rt;
+      const bool live = row < cta_row1;
+      ChunkRegs<HIT> cur, nxt;
+      if (live) load_chunk<HIT>(p, row, sub * 16, cur);
+      float pilot = 0.f, mean = 0.f, m2 = 0.f;  // running mean / M2 of the shifted values over the slices this thread has seen
+      for (int kc = 0; kc < nkc; ++kc, ++it) {
+        if (live && kc + 1 < nkc) load_chunk<HIT>(p, row, (kc + 1) * kKC + sub * 16, nxt);
+        float v[16];
+        if (live) {
+          chunk_values<HIT>(p, cur, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        if (kc == 0) {  // pilot = mean of the row's first 64 elements (4 adjacent lanes)
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s += v[i];
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          pilot = s * (1.0f / 64.0f);
+        }
+        float cs = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] -= pilot;
+          cs += v[i];
+        }
+        const float cm = cs * (1.0f / 16.0f);
+        float cq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float d = v[i] - cm;
+          cq = fmaf(d, d, cq);
+        }
+        // Chan: combine (n_a = 16*kc, mean, m2) with (16, cm, cq)
+        const float na = 16.0f * static_cast<float>(kc), n = na + 16.0f;
+        const float delta = cm - mean;
+        mean = fmaf(delta, 16.0f / n, mean);
+        m2 += cq + delta * delta * (na * 16.0f / n);
+
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          lo[i] = pack_bf16x2(v[2 * i] - bf16_lo(hi[i]), v[2 * i + 1] - bf16_hi(hi[i]));
+        }
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        ptx::mbar_wait(&a_empty[s], ph ^ 1);
+        uint8_t* arow = smem + s * kStageBytes + (rt >> 3) * 1024 + sw * 128;
+        const int ch0 = (2 * sub) ^ sw, ch1 = (2 * sub + 1) ^ sw;  // 16-byte chunk index XOR (row % 8): the 128-byte swizzle
+        *reinterpret_cast<uint4*>(arow + ch0 * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(arow + ch1 * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<uint4*>(arow + kATile + ch0 * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(arow + kATile + ch1 * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&a_full[s]);
+        if (kc + 1 < nkc) cur = nxt;
+      }
+      // row statistics: merge the four slices of the row (Chan again, equal counts), publish (mean_shifted, rstd)
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mean, o), oq = __shfl_xor_sync(0xffffffffu, m2, o);
+        const float cnt = static_cast<float>(p.cols) * (o == 1 ? 0.25f : 0.5f);  // elements behind each side
+        const float delta = om - mean;
+        mean = 0.5f * (mean + om);
+        m2 = m2 + oq + delta * delta * (cnt * 0.5f);
+      }
+      if (sub == 0) stats[rt] = make_float2(mean, rsqrtf(m2 * inv_cols + p.eps));
+      asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+      if (warp < 8) {
+        // ---- epilogue: y = rstd * (acc - mean_shifted * c1) + c0 -> unpatchify. Warp = (TMEM lane quarter, 32-column half);
+        // output feature j = (q*2 + rr)*16 + c -> out[c, f, 2*hp+q, 2*wp+rr]: columns [32q, 32q+32) hold rr = 0 | rr = 1 for the
+        // same 16 channels, so every store is one float2 and a warp writes 256 contiguous bytes per channel row.
+        const int qtr = warp & 3, qh = warp >> 2;
+        ptx::mbar_wait(acc_full, st & 1);
+        ptx::tc_fence_after();
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(qtr * 32) << 16) + qh * 32, acc);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        const int er = qtr * 32 + lane;
+        const int64_t erow = cta_row0 + static_cast<int64_t>(st) * kRows + er;
+        if (erow < cta_row1) {
+          const float2 ms = stats[er];
+          const int64_t tok = p.row_offset + erow;
+          const int wp = static_cast<int>(tok % p.Wp);
+          const int hp = static_cast<int>((tok / p.Wp) % p.Hp);
+          const int f = static_cast<int>(tok / (static_cast<int64_t>(p.Wp) * p.Hp));
+          const int H2 = p.Hp * 2, W2 = p.Wp * 2;
+          const int64_t plane = static_cast<int64_t>(p.F) * H2 * W2;
+          const int64_t off = (static_cast<int64_t>(f) * H2 + hp * 2 + qh) * W2 + wp * 2;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int j0 = qh * 32 + c, j1 = j0 + 16;
+            const float y0 = fmaf(ms.y, __uint_as_float(acc[c]) - ms.x * __ldg(p.c1 + j0), __ldg(p.c0 + j0));
+            const float y1 = fmaf(ms.y, __uint_as_float(acc[16 + c]) - ms.x * __ldg(p.c1 + j1), __ldg(p.c0 + j1));
+            for (int o = 0; o < p.n_out; ++o) *reinterpret_cast<float2*>(p.out[o] + c * plane + off) = make_float2(y0, y1);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == hd::kConvWarps + 1) ptx::tmem_dealloc(tmem_acc, hd::kTmemCols);
+}
+
+}  // namespace mc
+
+extern "C" {
+
+int32_t mc_head_workspace_bytes(int32_t cols, int64_t* bytes_out) {
+  MC_CHECK_ARG(bytes_out != nullptr && cols >= 64, "mc_head_workspace_bytes: bad arguments");
+  *bytes_out = static_cast<int64_t>(2) * 64 * cols * 2 + 1024;  // W'_hi, W'_lo [64, cols] bf16; c1, c0 [64] fp32
+  return MC_OK;
+}
+
+int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
+                              int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e, const float* Wt,
+                              const float* b, float eps, float* const* outs, int32_t n_out, void* workspace, int64_t workspace_bytes,
+                              int32_t flags, void* stream) {
+  using namespace mc;
+  MC_CHECK_ARG(x && head_mod && e && Wt && b && outs && workspace, "mc_head_unpatchify: null pointer");
+  MC_CHECK_ARG(n_out >= 1 && n_out <= hd::kMaxPeers, "mc_head_unpatchify: n_out=%d outside [1, %d]", n_out, hd::kMaxPeers);
+  MC_CHECK_ARG(cols >= hd::kKC && cols % hd::kKC == 0, "mc_head_unpatchify: cols=%d must be a multiple of %d", cols, hd::kKC);
+  MC_CHECK_ARG(C_out * 4 == hd::kOut, "mc_head_unpatchify: only patch (1,2,2) x C_out=16 (64 output features) is built, got C_out=%d", C_out);
+  MC_CHECK_ARG(F >= 1 && Hp >= 1 && Wp >= 1, "mc_head_unpatchify: bad grid");
+  MC_CHECK_ARG(rows >= 1 && row_offset >= 0 && row_offset + rows <= static_cast<int64_t>(F) * Hp * Wp,
+               "mc_head_unpatchify: token range [%lld, %lld) outside the %d x %d x %d grid", static_cast<long long>(row_offset),
+               static_cast<long long>(row_offset + rows), F, Hp, Wp);
+  MC_CHECK_ARG((x_dtype == MC_F32 && r_or_null == nullptr) || (x_dtype == MC_BF16 && r_or_null != nullptr),
+               "mc_head_unpatchify: x must be fp32 (stream) or bf16 together with an fp32 residual (cache hit)");
+  MC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 31u) == 0 && (r_or_null == nullptr || (reinterpret_cast<uintptr_t>(r_or_null) & 31u) == 0),
+               "mc_head_unpatchify: x / r must be 32-byte aligned");
+  int64_t need = 0;
+  mc_head_workspace_bytes(cols, &need);
+  MC_CHECK_ARG(workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 1023u) == 0,
+               "mc_head_unpatchify: workspace of %lld bytes, 1024-byte aligned, needed (mc_head_workspace_bytes)", static_cast<long long>(need));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* w_hi = static_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* w_lo = w_hi + static_cast<size_t>(64) * cols;
+  float* c1 = reinterpret_cast<float*>(w_lo + static_cast<size_t>(64) * cols);
+  float* c0 = c1 + 64;
+  head_prep_kernel<<<hd::kOut, 256, 0, s>>>(head_mod, e, Wt, b, cols, w_hi, w_lo, c1, c0);
+  MC_CHECK_LAUNCH("head_prep_kernel launch");
+
+  CUtensorMap thi, tlo;
+  int32_t rc = make_tmap_bf16_2d(&thi, w_hi, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tlo, w_lo, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
+  if (rc) return rc;
+  HeadParams p{};
+  p.x = x, p.r = r_or_null, p.x_bf16 = x_dtype == MC_BF16, p.round_sum_bf16 = (flags & 1) != 0;
+  p.rows = rows, p.row_offset = row_offset, p.cols = cols, p.F = F, p.Hp = Hp, p.Wp = Wp;
+  const int sms = num_sms();
+  p.rows_per_cta = static_cast<int>((rows + sms - 1) / sms);
+  if (p.rows_per_cta < 16) p.rows_per_cta = 16;
+  p.c1 = c1, p.c0 = c0, p.eps = eps;
+  for (int i = 0; i < n_out; ++i) {
+    MC_CHECK_ARG(outs[i] != nullptr && (reinterpret_cast<uintptr_t>(outs[i]) & 7u) == 0, "mc_head_unpatchify: out[%d] null or not 8-byte aligned", i);
+    p.out[i] = outs[i];
+  }
+  p.n_out = n_out;
+  const int grid = static_cast<int>((rows + p.rows_per_cta - 1) / p.rows_per_cta);
+  static PerDeviceOnce once_hit, once_stream;
+  if (r_or_null) {
+    rc = set_max_smem_once(head_tc_kernel<true>, hd::kSmem, once_hit, "cudaFuncSetAttribute(head smem)");
+    if (rc) return rc;
+    head_tc_kernel<true><<<grid, hd::kThreads, hd::kSmem, s>>>(thi, tlo, p);
+  } else {
+    rc = set_max_smem_once(head_tc_kernel<false>, hd::kSmem, once_stream, "cudaFuncSetAttribute(head smem)");
+    if (rc) return rc;
+    head_tc_kernel<false><<<grid, hd::kThreads, hd::kSmem, s>>>(thi, tlo, p);
+  }
+  MC_CHECK_LAUNCH("head_tc_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
+                           int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e, const float* Wt,
+                           const float* b, float eps, float* out, void* workspace, int64_t workspace_bytes, int32_t flags, void* stream) {
+  float* outs[1] = {out};
+  return mc_head_unpatchify_ex(x, x_dtype, r_or_null, rows, row_offset, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, outs, 1, workspace,
+                               workspace_bytes, flags, stream);
+}
+
+}  // extern "C"

@@ -286,114 +286,6 @@ __global__ void __launch_bounds__(256) linear_f32_small_kernel(const float* __re
   }
 }
 
-// ---- head: LN + modulate + fp32 Linear(cols -> 64) + unpatchify ------------------------------------------------
-// Block = 128 threads, 32 rows x 64 outputs; each thread owns a 4x4 micro-tile. Phase 1: row statistics (one warp per
-// 8 rows). Phase 2: K-chunks of 32 columns staged in smem (x normalised+modulated on the way in; Wt chunk as is).
-constexpr int kHeadRows = 32, kHeadKC = 32, kHeadOut = 64;
-
-template <bool FUSED_HIT>
-__device__ __forceinline__ float head_load(const void* x, int x_bf16, const float* r, int64_t idx) {
-  float v = x_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(x)[idx]) : static_cast<const float*>(x)[idx];
-  if (FUSED_HIT) v = v + r[idx];  // `x + residual_x` (magcache_generate.py:295) never materialised
-  return v;
-}
-
-template <bool FUSED_HIT>
-__global__ void __launch_bounds__(128) head_unpatchify_kernel(const void* __restrict__ x, int x_bf16, const float* __restrict__ r,
-                                                              int64_t rows, int64_t row_offset, int cols, int F, int Hp, int Wp, int C_out,
-                                                              const float* __restrict__ head_mod, const float* __restrict__ e,
-                                                              const float* __restrict__ Wt, const float* __restrict__ bias,
-                                                              float eps, float* __restrict__ out) {
-  __shared__ float s_mean[kHeadRows], s_rstd[kHeadRows];
-  __shared__ __align__(16) float xs[kHeadKC][kHeadRows + 4];
-  __shared__ __align__(16) float ws[kHeadKC][kHeadOut];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t row_base = static_cast<int64_t>(blockIdx.x) * kHeadRows;
-  const float inv_n = 1.0f / static_cast<float>(cols);
-
-  // phase 1: statistics, two-pass (second pass re-reads the row from L1/L2)
-  for (int rr = warp; rr < kHeadRows; rr += 4) {
-    const int64_t row = row_base + rr;
-    float mean = 0.f, rstd = 0.f;
-    if (row < rows) {
-      float s = 0.f;
-      for (int c = lane; c < cols; c += 32) s += head_load<FUSED_HIT>(x, x_bf16, r, row * cols + c);
-      mean = warp_sum(s) * inv_n;
-      float q = 0.f;
-      for (int c = lane; c < cols; c += 32) {
-        const float d = head_load<FUSED_HIT>(x, x_bf16, r, row * cols + c) - mean;
-        q = fmaf(d, d, q);
-      }
-      rstd = rsqrtf(warp_sum(q) * inv_n + eps);
-    }
-    if (lane == 0) {
-      s_mean[rr] = mean;
-      s_rstd[rr] = rstd;
-    }
-  }
-  __syncthreads();
-
-  const int tr = (tid >> 4) * 4;  // row offset of the micro-tile: 8 thread-rows x 4
-  const int tc = (tid & 15) * 4;  // col offset: 16 thread-cols x 4
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int k0 = 0; k0 < cols; k0 += kHeadKC) {
-    // stage x chunk: 32 rows x 32 cols; thread -> (row = tid/4 ... ) coalesced along cols
-    for (int i = tid; i < kHeadRows * kHeadKC; i += 128) {
-      const int rr = i / kHeadKC, cc = i % kHeadKC;
-      const int64_t row = row_base + rr;
-      float val = 0.f;
-      if (row < rows) {
-        const int c = k0 + cc;
-        const float y = (head_load<FUSED_HIT>(x, x_bf16, r, row * cols + c) - s_mean[rr]) * s_rstd[rr];
-        const float a = 1.0f + (head_mod[cols + c] + e[c]);  // e[1] = modulation[1] + e
-        const float b = head_mod[c] + e[c];                  // e[0] = modulation[0] + e
-        val = __fadd_rn(__fmul_rn(y, a), b);
-      }
-      xs[cc][rr] = val;
-    }
-    for (int i = tid; i < kHeadKC * kHeadOut; i += 128) {
-      const int cc = i / kHeadOut, j = i % kHeadOut;
-      ws[cc][j] = Wt[static_cast<int64_t>(k0 + cc) * kHeadOut + j];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int cc = 0; cc < kHeadKC; ++cc) {
-      const float4 xv = *reinterpret_cast<const float4*>(&xs[cc][tr]);
-      const float4 wv = *reinterpret_cast<const float4*>(&ws[cc][tc]);
-      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, wa[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], wa[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-
-  // epilogue: bias + unpatchify scatter. output feature j = (q*2 + rr)*C_out + c  ->  out[c, f, 2*hp+q, 2*wp+rr]
-  const int H2 = Hp * 2, W2 = Wp * 2;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t row = row_base + tr + i;
-    if (row >= rows) continue;
-    const int64_t tok = row_offset + row;  // global token index (token-sharded runs own a contiguous token range)
-    const int wp = static_cast<int>(tok % Wp);
-    const int hp = static_cast<int>((tok / Wp) % Hp);
-    const int f = static_cast<int>(tok / (static_cast<int64_t>(Wp) * Hp));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int o = tc + j;
-      const int c = o % C_out, pq = o / C_out;
-      const int q = pq >> 1, rr = pq & 1;
-      out[((static_cast<int64_t>(c) * F + f) * H2 + hp * 2 + q) * W2 + wp * 2 + rr] = acc[i][j] + bias[o];
-    }
-  }
-}
-
 // ---- elementwise --------------------------------------------------------------------------------------------
 __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, int64_t n) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -551,26 +443,6 @@ int32_t mc_linear_f32_small(const float* x, int32_t M, int32_t K, const float* W
 #undef MC_LS
   }
   MC_CHECK_LAUNCH("linear_f32_small_kernel launch");
-  return MC_OK;
-}
-
-int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
-                           int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e, const float* Wt,
-                           const float* b, float eps, float* out, void* stream) {
-  MC_CHECK_ARG(x && head_mod && e && Wt && b && out, "mc_head_unpatchify: null pointer");
-  MC_CHECK_ARG(cols >= mc::kHeadKC && cols % mc::kHeadKC == 0, "mc_head_unpatchify: cols=%d must be a multiple of %d", cols, mc::kHeadKC);
-  MC_CHECK_ARG(C_out * 4 == mc::kHeadOut, "mc_head_unpatchify: only patch (1,2,2) x C_out=16 (64 output features) is built, got C_out=%d", C_out);
-  MC_CHECK_ARG(F >= 1 && Hp >= 1 && Wp >= 1, "mc_head_unpatchify: bad grid");
-  MC_CHECK_ARG(rows >= 1 && row_offset >= 0 && row_offset + rows <= static_cast<int64_t>(F) * Hp * Wp,
-               "mc_head_unpatchify: token range [%lld, %lld) outside the %d x %d x %d grid", static_cast<long long>(row_offset),
-               static_cast<long long>(row_offset + rows), F, Hp, Wp);
-  const int grid = static_cast<int>((rows + mc::kHeadRows - 1) / mc::kHeadRows);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (r_or_null)
-    mc::head_unpatchify_kernel<true><<<grid, 128, 0, s>>>(x, x_dtype == MC_BF16, r_or_null, rows, row_offset, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, out);
-  else
-    mc::head_unpatchify_kernel<false><<<grid, 128, 0, s>>>(x, x_dtype == MC_BF16, nullptr, rows, row_offset, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, out);
-  MC_CHECK_LAUNCH("head_unpatchify_kernel launch");
   return MC_OK;
 }
 

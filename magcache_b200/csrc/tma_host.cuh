@@ -2,6 +2,7 @@
 // (cudaGetDriverEntryPoint) so the library has no link-time dependency on libcuda.
 #pragma once
 #include <cuda.h>
+#include <mutex>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -29,8 +30,57 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 // 2-D bf16 row-major tensor [rows, cols] with row pitch ld (elements); box = [box_rows, box_cols] with box_cols*2 == 128 B,
 // 128-byte swizzle. Out-of-bounds box elements are filled with zeros.
+// A tensor map is a pure function of (base, shape, pitch, box): the engines call the same few hundred (buffer, shape) pairs every
+// forward, so encoded maps are kept in a small direct-mapped cache instead of re-running the driver's encoder per launch.
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+  }
+};
+struct TmapCacheEntry {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+constexpr int kTmapCacheSize = 1024;
+TmapCacheEntry* tmap_cache();          // defined in gemm_tcgen05.cu (one table per process; entries are device-pointer keyed)
+std::mutex& tmap_cache_mutex();
+
+inline int32_t make_tmap_bf16_2d_uncached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                                          uint32_t box_cols);
+
 inline int32_t make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                                  uint32_t box_cols) {
+  const TmapKey key{base, rows, cols, ld, box_rows, box_cols};
+  uint64_t h = reinterpret_cast<uint64_t>(base) >> 4;
+  h ^= rows * 0x9E3779B97F4A7C15ull;
+  h ^= (cols << 20) ^ (ld << 40) ^ (static_cast<uint64_t>(box_rows) << 8) ^ box_cols;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  TmapCacheEntry& e = tmap_cache()[h % kTmapCacheSize];
+  {
+    std::lock_guard<std::mutex> g(tmap_cache_mutex());
+    if (e.valid && e.key == key) {
+      *map = e.map;
+      return MC_OK;
+    }
+  }
+  const int32_t rc = make_tmap_bf16_2d_uncached(map, base, rows, cols, ld, box_rows, box_cols);
+  if (rc == MC_OK) {
+    std::lock_guard<std::mutex> g(tmap_cache_mutex());
+    e.key = key;
+    e.map = *map;
+    e.valid = true;
+  }
+  return rc;
+}
+
+inline int32_t make_tmap_bf16_2d_uncached(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                                          uint32_t box_cols) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return MC_ERR_CUDA;
   cuuint64_t gdim[2] = {cols, rows};

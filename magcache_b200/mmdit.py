@@ -20,7 +20,7 @@ everything bf16 like the reference pipelines, which run without autocast):
   hs   [S, D]    both residual streams; the double-stream blocks work on the two row ranges, the single-stream blocks on all rows
   x0   [n_img, D] x_embedder output (`ori_hidden_states`)         res [n_img, D]  cached residual (`previous_residual`)
   h    [S, D]    LN+modulate output (GEMM A operand)              qk  [S, 2D]     q | k projections, per-head RMSNorm + RoPE in place
-  vt   [D, Spad] V^T straight out of the V-projection GEMMs       cat [S, 5D]     single blocks: attention output | GELU(proj_mlp);
+  v    [S, D]    row-major V (attention reads it as is)          cat [S, 5D]     single blocks: attention output | GELU(proj_mlp);
                                                                                   double blocks borrow cat[:, D:] as the FF hidden
   ada  [R]       ALL AdaLayerNorm projections of the forward from ONE GEMM over silu(temb) (they depend on temb only)
 """
@@ -146,15 +146,10 @@ class MMDiTCore:
             self.img_g, self.txt_g = slice(0, self.n_img_total), slice(self.n_img_total, Sg)
         self.hs, self.h, self.att = torch.empty(S, D, **bf), torch.empty(S, D, **bf), torch.empty(S, D, **bf)
         self.x0, self.res, self.hit = torch.empty(n_img, D, **bf), torch.empty(n_img, D, **bf), torch.empty(n_img, D, **bf)
-        self.vt = torch.zeros(D, (Sg + 7) // 8 * 8, **bf)
         if self.shard is None:
             self.qk = torch.empty(S, 2 * D, **bf)
-            # V^T column ranges must start on 16 bytes for the GEMM to write them directly; otherwise (second segment starting at a row that
-            # is not a multiple of 8: never with FLUX's padded 512 text tokens) V goes to a row-major buffer and is transposed per attention
-            self.v_direct = min(self.img.start, self.txt.start) == 0 and max(self.img.start, self.txt.start) % 8 == 0
-            self.v = None if self.v_direct else torch.empty(S, D, **bf)
+            self.v = torch.empty(S, D, **bf)   # row-major V: the attention kernel consumes it as is (MN-major B operand)
         else:
-            self.v_direct = False
             self.q_loc, self.k_loc, self.v_loc = torch.empty(S, D, **bf), torch.empty(S, D, **bf), torch.empty(S, D, **bf)
             self.k_all, self.v_all = torch.empty(Sg, D, **bf), torch.empty(Sg, D, **bf)
         self.cat = torch.empty(S, 5 * D, **bf)
@@ -187,10 +182,7 @@ class MMDiTCore:
             ops.gemm(h_rows, v_w, v_b, E.MC_EPI_BIAS_BF16, out=self.v_loc[rows])
             return
         ops.gemm(h_rows, qk_w, qk_b, E.MC_EPI_BIAS_BF16, out=self.qk[rows])
-        if self.v_direct:
-            ops.gemm(v_w, h_rows, v_b, E.MC_EPI_ROWBIAS_BF16, out=self.vt[:, rows])
-        else:
-            ops.gemm(h_rows, v_w, v_b, E.MC_EPI_BIAS_BF16, out=self.v[rows])
+        ops.gemm(h_rows, v_w, v_b, E.MC_EPI_BIAS_BF16, out=self.v[rows])
 
     def _qk_norm(self, rows, nq, nk):
         """Per-head RMSNorm of q and k (+ RoPE where the family applies it), in place."""
@@ -211,12 +203,9 @@ class MMDiTCore:
             self.v_all[self.txt_g].copy_(self.v_loc[self.txt])
             wk.wait()
             wv.wait()
-            ops.transpose(self.v_all, self.vt[:, :self.S_keys])
-            ops.attention(self.q_loc, self.k_all, self.vt[:, :self.S_keys], H, out=out, tag="mmdit_attn")
+            ops.attention(self.q_loc, self.k_all, self.v_all, H, out=out, tag="mmdit_attn")
             return
-        if not self.v_direct:
-            ops.transpose(self.v, self.vt[:, :self.S])
-        ops.attention(self.qk[:, :D], self.qk[:, D:], self.vt[:, :self.S], H, out=out, tag="mmdit_attn")
+        ops.attention(self.qk[:, :D], self.qk[:, D:], self.v, H, out=out, tag="mmdit_attn")
 
     def _gather_output(self, o_local):
         """Per-token head output of this rank's image rows -> all image rows, replicated (tiny: 64 features per token)."""
@@ -485,7 +474,7 @@ class HunyuanEngine(MMDiTCore):
         self.s_txt = torch.empty(n_txt, w.text_dim, **bf)
         self.s_pooled = torch.empty(1, w.pooled_dim, **bf)
         self.s_t = torch.zeros(2, dtype=torch.float64, device=dev)
-        self.rvt = torch.zeros(w.dim, (n_txt + 7) // 8 * 8, **bf)  # V^T of the token refiner's self-attention
+        self.rv = torch.empty(n_txt, w.dim, **bf)  # V of the token refiner's self-attention
         self.rada = torch.empty(1, w.r_ada_w.shape[0], **bf)
         self.radaf = torch.empty(w.r_ada_w.shape[0], dtype=torch.float32, device=dev)
         self._shape = (grid, n_txt)
@@ -540,7 +529,7 @@ class HunyuanEngine(MMDiTCore):
         ops.gemm(self.s_txt, w.r_in_w, w.r_in_b, E.MC_EPI_BIAS_BF16, out=x)
         sharded = self.shard is not None
         q, k = (self.q_loc[txt], self.k_loc[txt]) if sharded else (self.qk[txt][:, :D], self.qk[txt][:, D:])
-        vt = self.rvt[:, :n]
+        rv = self.rv[:n]
         for i, b in enumerate(w.refiner):
             g = self.radaf[i * 2 * D:(i + 1) * 2 * D].view(2, D)  # gate_msa, gate_mlp
             ops.ln_affine(x, b["n1_w"], b["n1_b"], eps=1e-6, out=h)
@@ -549,10 +538,10 @@ class HunyuanEngine(MMDiTCore):
                 ops.gemm(h, b["qk_w"][D:], b["qk_b"][D:], E.MC_EPI_BIAS_BF16, out=k)
             else:
                 ops.gemm(h, b["qk_w"], b["qk_b"], E.MC_EPI_BIAS_BF16, out=self.qk[txt])
-            ops.gemm(b["v_w"], h, b["v_b"], E.MC_EPI_ROWBIAS_BF16, out=vt)
+            ops.gemm(h, b["v_w"], b["v_b"], E.MC_EPI_BIAS_BF16, out=rv)
             ops.rmsnorm_head_rope_(q, b["nq"], H, None)
             ops.rmsnorm_head_rope_(k, b["nk"], H, None)
-            ops.attention(q, k, vt, H, out=self.att[txt], tag="refiner_attn")
+            ops.attention(q, k, rv, H, out=self.att[txt], tag="refiner_attn")
             ops.gemm(self.att[txt], b["o_w"], b["o_b"], E.MC_EPI_BIAS_GATE_RESID_BF16, out=x, gate=g[0])
             ops.ln_affine(x, b["n2_w"], b["n2_b"], eps=1e-6, out=h)
             ffh = self.cat[txt][:, D:]

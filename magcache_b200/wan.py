@@ -6,9 +6,10 @@ C-ABI kernels. Block arithmetic follows upstream Wan2.1 `wan/modules/model.py` [
 
 HBM layout per forward (N tokens, D model dim, F ffn dim; Wan2.1-1.3B at 832x480x81: N=32760, D=1536, F=8960):
   x0   bf16 [N, D]     patch-embedding output (`ori_x`)            h    bf16 [N, D]    LN+modulate output (GEMM A operand)
-  xs   fp32 [N, D]     residual stream, updated in place           qk   bf16 [N, 2D]   fused q|k projection (RMSNorm+RoPE in place)
-  vt   bf16 [D, Npad]  V^T straight out of the V-projection GEMM   att  bf16 [N, D]    attention output
-  ffn  bf16 [N, F]     GELU(ffn[0]) output                         ctx  bf16 [512, D]  text embedding (+ per-layer k / v^T)
+  xs   fp32 [N, D]     residual stream, updated in place           qkv  bf16 [N, 3D]   fused q|k|v projection (one GEMM; RMSNorm+RoPE in
+  att  bf16 [N, D]     attention output                                                place on the q and k column blocks)
+  ffn  bf16 [N, F]     GELU(ffn[0]) output                         ctx  bf16 [512, D]  text embedding; ckv bf16 [512, 2D] its per-layer k|v
+The attention kernel reads q, k and v as column slices of `qkv` (row pitch 3D): V stays row-major, nothing is transposed.
 All buffers are allocated once per engine and reused by every forward (no allocator traffic in the loop).
 """
 import math
@@ -132,23 +133,22 @@ class WanWeights:
         sa, ca = blk.self_attn, blk.cross_attn
         b = {
             "mod": _f32(blk.modulation.reshape(6, D), device),
-            "w_qk": _bf16(torch.cat([sa.q.weight, sa.k.weight], 0), device),
-            "b_qk": _bias_autocast(torch.cat([sa.q.bias, sa.k.bias], 0), device),
-            "w_v": _bf16(sa.v.weight, device), "b_v": _bias_autocast(sa.v.bias, device),
+            "w_qkv": _bf16(torch.cat([sa.q.weight, sa.k.weight, sa.v.weight], 0), device),   # one [3D, D] projection
+            "b_qkv": _bias_autocast(torch.cat([sa.q.bias, sa.k.bias, sa.v.bias], 0), device),
             "w_o": _bf16(sa.o.weight, device), "b_o": _bias_autocast(sa.o.bias, device),
             "nq": _f32(sa.norm_q.weight, device), "nk": _f32(sa.norm_k.weight, device),
             "n3_w": _f32(blk.norm3.weight, device), "n3_b": _f32(blk.norm3.bias, device),
             "c_wq": _bf16(ca.q.weight, device), "c_bq": _bias_autocast(ca.q.bias, device),
-            "c_wk": _bf16(ca.k.weight, device), "c_bk": _bias_autocast(ca.k.bias, device),
-            "c_wv": _bf16(ca.v.weight, device), "c_bv": _bias_autocast(ca.v.bias, device),
+            "c_wkv": _bf16(torch.cat([ca.k.weight, ca.v.weight], 0), device),                # text k|v: one [2D, D] projection
+            "c_bkv": _bias_autocast(torch.cat([ca.k.bias, ca.v.bias], 0), device),
             "c_wo": _bf16(ca.o.weight, device), "c_bo": _bias_autocast(ca.o.bias, device),
             "c_nq": _f32(ca.norm_q.weight, device), "c_nk": _f32(ca.norm_k.weight, device),
             "w_f1": _bf16(blk.ffn[0].weight, device), "b_f1": _bias_autocast(blk.ffn[0].bias, device),
             "w_f2": _bf16(blk.ffn[2].weight, device), "b_f2": _bias_autocast(blk.ffn[2].bias, device),
         }
         if dims.model_type == "i2v":  # WanI2VCrossAttention: own k / v projections and key norm for the CLIP tokens
-            b.update({"c_wk_img": _bf16(ca.k_img.weight, device), "c_bk_img": _bias_autocast(ca.k_img.bias, device),
-                      "c_wv_img": _bf16(ca.v_img.weight, device), "c_bv_img": _bias_autocast(ca.v_img.bias, device),
+            b.update({"c_wkv_img": _bf16(torch.cat([ca.k_img.weight, ca.v_img.weight], 0), device),
+                      "c_bkv_img": _bias_autocast(torch.cat([ca.k_img.bias, ca.v_img.bias], 0), device),
                       "c_nk_img": _f32(ca.norm_k_img.weight, device)})
         return b
 
@@ -179,17 +179,17 @@ class WanWeights:
         def rand_block():
             blk = {
                 "mod": torch.randn(6, D, device=device, generator=g) / math.sqrt(D),
-                "w_qk": torch.cat([xav(D, D), xav(D, D)], 0).bfloat16(), "b_qk": bias(2 * D),
-                "w_v": xav(D, D).bfloat16(), "b_v": bias(D), "w_o": xav(D, D).bfloat16(), "b_o": bias(D),
+                "w_qkv": torch.cat([xav(D, D), xav(D, D), xav(D, D)], 0).bfloat16(), "b_qkv": bias(3 * D),
+                "w_o": xav(D, D).bfloat16(), "b_o": bias(D),
                 "nq": 1 + 0.1 * torch.randn(D, device=device, generator=g), "nk": 1 + 0.1 * torch.randn(D, device=device, generator=g),
                 "n3_w": 1 + 0.1 * torch.randn(D, device=device, generator=g), "n3_b": small(D),
-                "c_wq": xav(D, D).bfloat16(), "c_bq": bias(D), "c_wk": xav(D, D).bfloat16(), "c_bk": bias(D),
-                "c_wv": xav(D, D).bfloat16(), "c_bv": bias(D), "c_wo": xav(D, D).bfloat16(), "c_bo": bias(D),
+                "c_wq": xav(D, D).bfloat16(), "c_bq": bias(D), "c_wkv": torch.cat([xav(D, D), xav(D, D)], 0).bfloat16(), "c_bkv": bias(2 * D),
+                "c_wo": xav(D, D).bfloat16(), "c_bo": bias(D),
                 "c_nq": 1 + 0.1 * torch.randn(D, device=device, generator=g), "c_nk": 1 + 0.1 * torch.randn(D, device=device, generator=g),
                 "w_f1": xav(F, D).bfloat16(), "b_f1": bias(F), "w_f2": xav(D, F).bfloat16(), "b_f2": bias(D),
             }
             if dims.model_type == "i2v":
-                blk.update({"c_wk_img": xav(D, D).bfloat16(), "c_bk_img": bias(D), "c_wv_img": xav(D, D).bfloat16(), "c_bv_img": bias(D),
+                blk.update({"c_wkv_img": torch.cat([xav(D, D), xav(D, D)], 0).bfloat16(), "c_bkv_img": bias(2 * D),
                             "c_nk_img": 1 + 0.1 * torch.randn(D, device=device, generator=g)})
             return blk
 
@@ -254,6 +254,7 @@ class WanEngine:
         env = os.environ.get("MC_GRAPHS")
         self.use_graphs = (shard_world > 1) if env is None else (env == "1")
         self._graphs = {}
+        self.hit_sum_bf16 = False  # TeaCache comparator: the hit sum is rounded to bf16 before the head (wan_teacache.py:569/577)
 
     # ------------------------------------------------------------------------------------------ workspace
     def _workspace(self, n_total):
@@ -267,25 +268,21 @@ class WanEngine:
             from .shard import TokenShard
             self.shard = TokenShard(self.rank, self.world, n_total, self.group)
             n = self.shard.n_local
-            # gathered K / V rows of ALL tokens (every rank attends to every key), local q / k / v projections
-            self.k_all = torch.empty(n_total, D, **bf)
-            self.v_all = torch.empty(n_total, D, **bf)
+            # local q and k | v projections; the k | v rows of every rank are gathered into kv_all (all tokens x [k | v])
             self.q_loc = torch.empty(n, D, **bf)
-            self.k_loc = torch.empty(n, D, **bf)
-            self.v_loc = torch.empty(n, D, **bf)
+            self.kv_loc = torch.empty(n, 2 * D, **bf)
+            self.kv_all = torch.empty(n_total, 2 * D, **bf)
             self.out_full = None
         else:
             n = n_total
-            self.qk = torch.empty(n, 2 * D, **bf)
+            self.qkv = torch.empty(n, 3 * D, **bf)
         self.x0 = torch.empty(n, D, **bf)
         self.xs = torch.empty(n, D, dtype=torch.float32, device=dev)
         self.h = torch.empty(n, D, **bf)
-        self.vt = torch.zeros(D, self.npad, **bf)
         self.att = torch.empty(n, D, **bf)
         self.ffn = torch.empty(n, F, **bf)
         self.cq = torch.empty(n, D, **bf)
-        self.ck = torch.empty(d.text_len, D, **bf)
-        self.cvt = torch.empty(D, d.text_len, **bf)
+        self.ckv = torch.empty(d.text_len, 2 * D, **bf)
         self.ctx_in = torch.zeros(d.text_len, d.text_dim, **bf)
         self.ctx_h = torch.empty(d.text_len, D, **bf)
         self.ctx = torch.empty(d.text_len, D, **bf)
@@ -302,8 +299,7 @@ class WanEngine:
             self.clip_h2 = torch.empty(cl, d.clip_dim, **bf)
             self.clip_h3 = torch.empty(cl, D, **bf)
             self.ctx_img = torch.empty(cl, D, **bf)
-            self.ck_img = torch.empty(cl, D, **bf)
-            self.cvt_img = torch.zeros(D, (cl + 7) // 8 * 8, **bf)  # V^T of the image tokens; row pitch padded to 16 bytes
+            self.ckv_img = torch.empty(cl, 2 * D, **bf)
             self.att_img = torch.empty(n, D, **bf)
         # engine-owned residual cache storage (one slot per CFG branch) and staged inputs: fixed addresses for graph replay
         self.res_buf = torch.empty(2, n, D, dtype=torch.float32, device=dev)  # one buffer: the paper-eval forward exposes it whole
@@ -368,14 +364,18 @@ class WanEngine:
         e0 = ops.linear_f32_small(e, w.tproj_w, w.tproj_b, act=1).view(6, d.dim)
         return e, e0
 
-    def prologue(self):
-        """Embeddings from the staged inputs. Returns (x0 bf16 [N_local, D], e fp32 [1, D], e0 fp32 [6, D], ctx bf16 [text_len, D])."""
+    def prologue(self, need_ctx=True):
+        """Embeddings from the staged inputs. Returns (x0 bf16 [N_local, D], e fp32 [1, D], e0 fp32 [6, D], ctx bf16 [text_len, D]).
+        `need_ctx=False` (cache hit): the text / image-token embeddings feed only the blocks, which a hit skips — the reference
+        computes them anyway (:255-266); leaving them out changes no output."""
         d, w = self.dims, self.w
         tok = ops.patchify(self.s_lat)
         if self.shard is not None:
             tok = self.shard.rows(tok)  # this rank embeds only its own tokens
         ops.gemm(tok, w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
         e, e0 = self.time_embedding()
+        if not need_ctx:
+            return self.x0, e, e0, None
         ops.gemm(self.ctx_in, w.text_w1, w.text_b1, E.MC_EPI_BIAS_GELU_BF16, out=self.ctx_h)
         ops.gemm(self.ctx_h, w.text_w2, w.text_b2, E.MC_EPI_BIAS_BF16, out=self.ctx)
         if d.model_type == "i2v":
@@ -390,9 +390,10 @@ class WanEngine:
     # ------------------------------------------------------------------------------------------ one patched forward
     def _body(self, kind, slot):
         """prologue -> {hit: head(x0 + residual) | miss: block stack, residual = x - x0, head(x)} on the staged inputs."""
-        x0, e, e0, ctx = self.prologue()
+        x0, e, e0, ctx = self.prologue(need_ctx=(kind != "hit"))
         if kind == "hit":
-            return self.head(x0, e, self.grid, residual=self.res[slot])  # `x + residual_x` formed inside the head kernel
+            # `x + residual_x` (:295) is formed inside the head kernel; TeaCache's in-place bf16 `x += residual` rounds the sum first
+            return self.head(x0, e, self.grid, residual=self.res[slot], round_sum_to_bf16=self.hit_sum_bf16)
         xs = self.run_blocks(x0, e0, ctx, self.grid)
         ops.residual_sub(xs, x0, out=self.res[slot])  # magcache_generate.py:299, written into the slot's fixed buffer
         return self.head(xs, e, self.grid)
@@ -404,7 +405,7 @@ class WanEngine:
         if not self.use_graphs:
             out = self._body(kind, slot)
         else:
-            key = (kind, slot)
+            key = (kind, slot, self.hit_sum_bf16)
             st = self._graphs.get(key)
             if st is None:  # first use: eager (sets kernel attributes, sizes the allocator pools)
                 out = self._body(kind, slot)
@@ -473,68 +474,55 @@ class WanEngine:
         D = d.dim
         n = xs.shape[0]
         sh = self.shard
-        if sh is None:
-            q, k = self.qk[:, :D], self.qk[:, D:]
-            vt = self.vt[:, :n]
-        else:
-            vt = self.vt[:, :sh.n_tokens]
         ops.cache_hit_add(b["mod"], e0, out=self.em)  # e = modulation + e0 (fp32)
         # --- self attention
         ops.ln_modulate(xs, self.em, 1, 0, eps=d.eps, round_ln_to_bf16=first, out=self.h)
         if sh is None:
-            ops.gemm(self.h, b["w_qk"], b["b_qk"], E.MC_EPI_BIAS_BF16, out=self.qk, tag="gemm_qk")
-            ops.gemm(b["w_v"], self.h, b["b_v"], E.MC_EPI_ROWBIAS_BF16, out=vt)
+            q, k, v = self.qkv[:, :D], self.qkv[:, D:2 * D], self.qkv[:, 2 * D:]
+            ops.gemm(self.h, b["w_qkv"], b["b_qkv"], E.MC_EPI_BIAS_BF16, out=self.qkv, tag="gemm_qkv")
             ops.rmsnorm_rope_(q, b["nq"], rope, d.head_dim, eps=d.eps)
             ops.rmsnorm_rope_(k, b["nk"], rope, d.head_dim, eps=d.eps)
-            ops.attention(q, k, vt, H, out=self.att, tag="attn_self")
+            ops.attention(q, k, v, H, out=self.att, tag="attn_self")
         else:
             from .shard import gather_rows
-            # K and V first so their all-gathers (NCCL, own stream) overlap the Q projection / RMSNorm / RoPE
-            ops.gemm(self.h, b["w_qk"][D:], b["b_qk"][D:], E.MC_EPI_BIAS_BF16, out=self.k_loc)
-            ops.rmsnorm_rope_(self.k_loc, b["nk"], rope, d.head_dim, eps=d.eps)
-            wk = gather_rows(self.k_loc, self.k_all, sh.group, async_op=True)
-            ops.gemm(self.h, b["w_v"], b["b_v"], E.MC_EPI_BIAS_BF16, out=self.v_loc)
-            wv = gather_rows(self.v_loc, self.v_all, sh.group, async_op=True)
-            ops.gemm(self.h, b["w_qk"][:D], b["b_qk"][:D], E.MC_EPI_BIAS_BF16, out=self.q_loc, tag="gemm_qk")
+            # k | v first so their all-gather (own stream) overlaps the q projection / RMSNorm / RoPE
+            ops.gemm(self.h, b["w_qkv"][D:], b["b_qkv"][D:], E.MC_EPI_BIAS_BF16, out=self.kv_loc, tag="gemm_qkv")
+            ops.rmsnorm_rope_(self.kv_loc[:, :D], b["nk"], rope, d.head_dim, eps=d.eps)
+            wkv = gather_rows(self.kv_loc, self.kv_all, sh.group, async_op=True)
+            ops.gemm(self.h, b["w_qkv"][:D], b["b_qkv"][:D], E.MC_EPI_BIAS_BF16, out=self.q_loc, tag="gemm_qkv")
             ops.rmsnorm_rope_(self.q_loc, b["nq"], rope, d.head_dim, eps=d.eps)
-            wk.wait()
-            wv.wait()
-            ops.transpose(self.v_all, vt)  # gathered V [N, D] -> V^T [D, N] for the PV MMA's K-major B operand
-            ops.attention(self.q_loc, self.k_all, vt, H, out=self.att, tag="attn_self")
-        ops.gemm(self.att, b["w_o"], b["b_o"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[2])
+            wkv.wait()
+            ops.attention(self.q_loc, self.kv_all[:, :D], self.kv_all[:, D:], H, out=self.att, tag="attn_self")
+        ops.gemm(self.att, b["w_o"], b["b_o"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[2], tag="gemm_o")
         # --- cross attention (text)
         ops.ln_affine(xs, b["n3_w"], b["n3_b"], eps=d.eps, out=self.h)
-        ops.gemm(self.h, b["c_wq"], b["c_bq"], E.MC_EPI_BIAS_BF16, out=self.cq)
+        ops.gemm(self.h, b["c_wq"], b["c_bq"], E.MC_EPI_BIAS_BF16, out=self.cq, tag="gemm_cq")
         ops.rmsnorm_rope_(self.cq, b["c_nq"], None, d.head_dim, eps=d.eps)
-        ops.gemm(ctx, b["c_wk"], b["c_bk"], E.MC_EPI_BIAS_BF16, out=self.ck)
-        ops.rmsnorm_rope_(self.ck, b["c_nk"], None, d.head_dim, eps=d.eps)
-        ops.gemm(b["c_wv"], ctx, b["c_bv"], E.MC_EPI_ROWBIAS_BF16, out=self.cvt)
-        ops.attention(self.cq, self.ck, self.cvt, H, out=self.att, tag="attn_cross")
+        ops.gemm(ctx, b["c_wkv"], b["c_bkv"], E.MC_EPI_BIAS_BF16, out=self.ckv, tag="gemm_ckv")
+        ops.rmsnorm_rope_(self.ckv[:, :D], b["c_nk"], None, d.head_dim, eps=d.eps)
+        ops.attention(self.cq, self.ckv[:, :D], self.ckv[:, D:], H, out=self.att, tag="attn_cross")
         att = self.att
         if d.model_type == "i2v":  # WanI2VCrossAttention: x = attn(q, k, v) + attn(q, k_img, v_img), summed in bf16
-            cvt_img = self.cvt_img[:, :d.clip_len]
-            ops.gemm(self.ctx_img, b["c_wk_img"], b["c_bk_img"], E.MC_EPI_BIAS_BF16, out=self.ck_img)
-            ops.rmsnorm_rope_(self.ck_img, b["c_nk_img"], None, d.head_dim, eps=d.eps)
-            ops.gemm(b["c_wv_img"], self.ctx_img, b["c_bv_img"], E.MC_EPI_ROWBIAS_BF16, out=cvt_img)
-            ops.attention(self.cq, self.ck_img, cvt_img, H, out=self.att_img, tag="attn_cross_img")
+            ops.gemm(self.ctx_img, b["c_wkv_img"], b["c_bkv_img"], E.MC_EPI_BIAS_BF16, out=self.ckv_img)
+            ops.rmsnorm_rope_(self.ckv_img[:, :D], b["c_nk_img"], None, d.head_dim, eps=d.eps)
+            ops.attention(self.cq, self.ckv_img[:, :D], self.ckv_img[:, D:], H, out=self.att_img, tag="attn_cross_img")
             att = ops.cache_hit_add(self.att, self.att_img, out=self.h)  # h (norm3 output) is dead once cq is projected
-        ops.gemm(att, b["c_wo"], b["c_bo"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=None)
+        ops.gemm(att, b["c_wo"], b["c_bo"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=None, tag="gemm_co")
         # --- FFN
         ops.ln_modulate(xs, self.em, 4, 3, eps=d.eps, out=self.h)
         ops.gemm(self.h, b["w_f1"], b["b_f1"], E.MC_EPI_BIAS_GELU_BF16, out=self.ffn, tag="gemm_ffn1")
         ops.gemm(self.ffn, b["w_f2"], b["b_f2"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[5], tag="gemm_ffn2")
 
     # ------------------------------------------------------------------------------------------ epilogue (:304-305)
-    def head(self, x, e, grid, residual=None):
+    def head(self, x, e, grid, residual=None, round_sum_to_bf16=False):
         w = self.w
         tag = "head_hit_fused" if residual is not None else "head"
+        kw = dict(c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps, tag=tag, round_sum_to_bf16=round_sum_to_bf16)
         if self.shard is None:
-            return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, c_out=self.dims.out_dim, residual=residual,
-                                       eps=self.dims.eps, tag=tag)
+            return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, **kw)
         from .shard import sum_partial_outputs
         out = torch.zeros(self.dims.out_dim, grid[0], 2 * grid[1], 2 * grid[2], dtype=torch.float32, device=self.device)
-        ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps,
-                            tag=tag, row_offset=self.shard.start, out=out)
+        ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, row_offset=self.shard.start, out=out, **kw)
         return sum_partial_outputs(out, self.shard.group)  # every rank ends up with the full noise prediction
 
 

@@ -121,15 +121,15 @@ def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6):
     return x
 
 
-def attention(q, k, vt, heads, scale=None, out=None, tag=None):
+def attention(q, k, v, heads, scale=None, out=None, tag=None, first_key_row=0, seg_flags=None, seg_epoch=0, seg_rows=0):
     Lq, W = q.shape
     Lk = k.shape[0]
-    assert q.stride(1) == 1 and k.stride(1) == 1 and vt.stride(1) == 1 and vt.shape == (W, Lk) and W == heads * 128
-    assert q.stride(0) % 8 == 0 and k.stride(0) % 8 == 0 and vt.stride(0) % 8 == 0 and _al(q) and _al(k) and _al(vt), "attention TMA operands"
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1 and v.shape == (Lk, W) and W == heads * 128
+    assert q.stride(0) % 8 == 0 and k.stride(0) % 8 == 0 and v.stride(0) % 8 == 0 and _al(q) and _al(k) and _al(v), "attention TMA operands"
     assert out is None or (out.stride(1) == 1 and out.stride(0) % 8 == 0 and _al(out))
     qh = q.to(F32).reshape(Lq, heads, 128).transpose(0, 1)
     kh = k.to(F32).reshape(Lk, heads, 128).transpose(0, 1)
-    vh = vt.to(F32).t().reshape(Lk, heads, 128).transpose(0, 1)
+    vh = v.to(F32).reshape(Lk, heads, 128).transpose(0, 1)
     s = qh @ kh.transpose(1, 2) * (scale if scale is not None else 1.0 / math.sqrt(128))
     o = (torch.softmax(s, -1) @ vh).transpose(0, 1).reshape(Lq, W)
     if out is None:
@@ -212,8 +212,13 @@ def linear_f32_small(x, w, b=None, act=0):
     return F.silu(y) if act == 2 else y
 
 
-def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None, row_offset=0, out=None):
+def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None, row_offset=0, out=None, round_sum_to_bf16=False,
+                    peer_outs=None):
+    assert (x.dtype == F32 and residual is None) or (x.dtype == BF and residual is not None), "fp32 stream, or bf16 + fp32 residual"
+    assert x.shape[1] % 64 == 0, "mc_head_unpatchify: cols % 64"
     xs = x.to(F32) + (residual if residual is not None else 0.0)
+    if round_sum_to_bf16:
+        xs = _rb(xs)
     em = head_mod + e.reshape(1, -1)  # (modulation[1,2,D] + e.unsqueeze(1)).chunk(2): shift, scale
     y = F.layer_norm(xs, (xs.shape[-1],), None, None, eps) * (1 + em[1]) + em[0]
     o = y @ w_t + b  # [rows, 4*c_out]

@@ -62,7 +62,6 @@ def test_flux_engine_single_forward_matches_oracle(emulated, guidance, n_txt):
             exact = m64(hs.double(), enc.double(), pooled.double(), t.double(), img_ids, txt_ids, None if gd is None else gd.double(),
                         return_dict=False)[0]
         out = ours(hs, enc, pooled, t, img_ids, txt_ids, gd)
-    assert ours._mc_flux_engine.v_direct == (n_txt % 8 == 0)
     assert hasattr(out, "sample") and out.sample.shape == ref.shape == (1, 48, 64) and out.sample.dtype == torch.bfloat16
     e_ours, e_ref, e_vs = rel_l2(out.sample, exact), rel_l2(ref, exact), rel_l2(out.sample, ref)
     print(f"[flux emulated] ours vs fp64 {e_ours:.3e} | oracle(bf16) vs fp64 {e_ref:.3e} | ours vs oracle {e_vs:.3e}")

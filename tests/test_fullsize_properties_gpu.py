@@ -36,14 +36,14 @@ def test_attention_convexity_full_sequence():
     q = torch.randn(N, D, device=DEV, generator=g).bfloat16()
     k = torch.randn(N, D, device=DEV, generator=g).bfloat16()
     const = torch.linspace(-2, 2, D, device=DEV).bfloat16()
-    vt = const[:, None].expand(D, N).contiguous()
-    out = ops.attention(q, k, vt, heads)
+    v = const[None, :].expand(N, D).contiguous()
+    out = ops.attention(q, k, v, heads)
     err = (out.float() - const.float()[None, :]).abs()
     assert float(err.max()) <= 2.0 ** -7 * 2 + 1e-3, float(err.max())
     # second invariant on a slice of queries: out depends on k only through q.k differences -> shifting every key by a vector
     # orthogonal to... is not exact in bf16; instead check the row-stochastic property with a one-hot V column block
-    onehot = torch.zeros(D, N, dtype=torch.bfloat16, device=DEV)
-    onehot[:, :N // 2] = 1.0
+    onehot = torch.zeros(N, D, dtype=torch.bfloat16, device=DEV)
+    onehot[:N // 2] = 1.0
     out2 = ops.attention(q[:1024], k, onehot, heads).float()
     assert float(out2.min()) >= -1e-3 and float(out2.max()) <= 1.0 + 2.0 ** -7  # a probability mass in [0, 1]
     assert abs(float(out2.mean()) - 0.5) < 0.05  # iid keys: about half the mass on the first half of the keys

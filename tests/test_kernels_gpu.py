@@ -320,6 +320,73 @@ def test_linear_f32_small_and_time_path():
     assert torch.allclose(y2, torch.nn.functional.silu(y) @ w2.t(), rtol=1e-3, atol=1e-4)
 
 
+@pytest.mark.parametrize("rows_grid,D", [((1, 1, 1), 256), ((2, 3, 5), 384), ((3, 16, 24), 1536), ((5, 30, 52), 1536)])
+@pytest.mark.parametrize("kind", ["plain", "offset", "outlier"])
+def test_head_unpatchify_shapes_and_offsets(rows_grid, D, kind):
+    """The single-pass tensor-core head (row statistics by Chan's update, 3-pass bf16 split GEMM against the modulated weight)
+    against an fp64 evaluation of `Head` + unpatchify: ragged row counts (CTA row ranges and partial 128-row tiles), rows with a
+    large common offset (the pilot shift) and rows with a few huge columns, both the fp32-stream and the fused cache-hit form.
+    Tolerance = the north-star's rtol 1e-3 / atol 1e-4 on fp32 outputs."""
+    ops = _ops()
+    F, Hp, Wp = rows_grid
+    rows = F * Hp * Wp
+    g = torch.Generator(device=DEV).manual_seed(rows + D)
+    head_mod = torch.randn(1, 2, D, device=DEV, generator=g) / math.sqrt(D)
+    e = torch.randn(1, D, device=DEV, generator=g) * 0.3
+    W = torch.randn(64, D, device=DEV, generator=g) * 0.05
+    b = torch.randn(64, device=DEV, generator=g) * 0.1
+    x = torch.randn(rows, D, device=DEV, generator=g) * 2
+    if kind == "offset":
+        x = x + torch.randn(rows, 1, device=DEV, generator=g) * 50.0
+    if kind == "outlier":
+        x[:, 0] *= 300.0
+        x[:, D // 2 + 3] += 500.0
+    ee = (head_mod + e.unsqueeze(1)).double()
+
+    def ref_of(xx):
+        y = torch.nn.functional.layer_norm(xx.double(), (D,), eps=1e-6) * (1 + ee[0, 1]) + ee[0, 0]
+        y = y @ W.double().t() + b.double()
+        return torch.einsum("fhwpqrc->cfphqwr", y.float().view(F, Hp, Wp, 1, 2, 2, 16)).reshape(16, F, Hp * 2, Wp * 2)
+
+    out = ops.head_unpatchify(x, head_mod, e, W.t().contiguous(), b, rows_grid)
+    ref = ref_of(x)
+    assert torch.allclose(out, ref, rtol=1e-3, atol=1e-4), (kind, float((out - ref).abs().max()), float(ref.abs().max()))
+    x0 = x.bfloat16()
+    r = torch.randn(rows, D, device=DEV, generator=g) * 0.3
+    out_h = ops.head_unpatchify(x0, head_mod, e, W.t().contiguous(), b, rows_grid, residual=r)
+    ref_h = ref_of(x0.float() + r)
+    assert torch.allclose(out_h, ref_h, rtol=1e-3, atol=1e-4), (kind, float((out_h - ref_h).abs().max()))
+    # the fused hit equals add-then-head bit for bit (same fp32 sum, same pipeline)
+    assert torch.equal(out_h, ops.head_unpatchify(ops.cache_hit_add(x0, r), head_mod, e, W.t().contiguous(), b, rows_grid))
+    # TeaCache form: sum rounded to bf16 first
+    out_t = ops.head_unpatchify(x0, head_mod, e, W.t().contiguous(), b, rows_grid, residual=r, round_sum_to_bf16=True)
+    ref_t = ref_of((x0.float() + r).bfloat16().float())
+    assert torch.allclose(out_t, ref_t, rtol=1e-3, atol=1e-4)
+
+
+def test_head_unpatchify_token_range():
+    """Token-sharded call: rows [row_offset, row_offset + n) of the grid written into a caller-provided output, other positions
+    untouched."""
+    ops = _ops()
+    F, Hp, Wp, D = 3, 8, 12, 384
+    rows = F * Hp * Wp
+    g = torch.Generator(device=DEV).manual_seed(7)
+    head_mod = torch.randn(1, 2, D, device=DEV, generator=g) / math.sqrt(D)
+    e = torch.randn(1, D, device=DEV, generator=g) * 0.3
+    Wt = (torch.randn(64, D, device=DEV, generator=g) * 0.05).t().contiguous()
+    b = torch.randn(64, device=DEV, generator=g) * 0.1
+    x = torch.randn(rows, D, device=DEV, generator=g)
+    full = ops.head_unpatchify(x, head_mod, e, Wt, b, (F, Hp, Wp))
+    out = torch.full_like(full, 777.0)
+    lo, hi = 100, 233
+    ops.head_unpatchify(x[lo:hi].contiguous(), head_mod, e, Wt, b, (F, Hp, Wp), row_offset=lo, out=out)
+    tok = torch.zeros(rows, dtype=torch.bool, device=DEV)
+    tok[lo:hi] = True
+    mask = tok.view(F, Hp, Wp)[:, :, None, :, None].expand(F, Hp, 2, Wp, 2).reshape(F, Hp * 2, Wp * 2)[None].expand(16, -1, -1, -1)
+    assert torch.equal(out[mask], full[mask])
+    assert bool((out[~mask] == 777.0).all())
+
+
 @pytest.mark.parametrize("fused", [False, True])
 def test_head_unpatchify(fused):
     ops = _ops()
@@ -436,10 +503,7 @@ def test_attention(Lq, Lk, heads, qscale):
     q = (torch.randn(Lq, W, device=DEV) * qscale).bfloat16()
     k = torch.randn(Lk, W, device=DEV).bfloat16()
     v = torch.randn(Lk, W, device=DEV).bfloat16()
-    ld = (Lk + 7) // 8 * 8
-    vt_buf = torch.zeros(W, ld, dtype=torch.bfloat16, device=DEV)
-    vt_buf[:, :Lk] = v.t()
-    out = ops.attention(q, k, vt_buf[:, :Lk], heads)
+    out = ops.attention(q, k, v, heads)
     ref = _attn_ref(q, k, v, heads)
     # P is rounded to bf16 before the PV product (as in flash-attention): error ~ 2^-9 * sqrt(sum p^2) relative to |v|~1,
     # plus the bf16 rounding of the output.
@@ -448,13 +512,55 @@ def test_attention(Lq, Lk, heads, qscale):
     assert float(err.mean()) < 2e-3, float(err.mean())
 
 
+@pytest.mark.parametrize("emu", [0, 2, 3, 4])
+@pytest.mark.parametrize("Lq,Lk,heads,qscale", [(128, 128, 1, 1.0), (256, 256, 1, 1.0), (300, 1000, 3, 1.0), (513, 1285, 2, 6.0), (1000, 4095, 12, 1.0),
+                                                (40, 130, 1, 3.0)])
+def test_attention_long_kernel(Lq, Lk, heads, qscale, emu, monkeypatch):
+    """The 256-row / 128-wide-KV kernel forced onto small and ragged shapes (second query tile empty or partial, one KV tile, ragged
+    last KV tile), for every exponential-emulation fraction it is built with: same bounds as the default path, and each variant
+    bit-reproducible."""
+    ops = _ops()
+    monkeypatch.setenv("MC_ATTN_KERNEL", "2")
+    monkeypatch.setenv("MC_ATTN_EMU", str(emu))
+    W = heads * 128
+    q = (torch.randn(Lq, W, device=DEV) * qscale).bfloat16()
+    k = torch.randn(Lk, W, device=DEV).bfloat16()
+    v = torch.randn(Lk, W, device=DEV).bfloat16()
+    out = ops.attention(q, k, v, heads)
+    ref = _attn_ref(q, k, v, heads)
+    err = (out.float() - ref).abs()
+    assert float(err.max()) < 2e-2, float(err.max())
+    assert float(err.mean()) < 2e-3, float(err.mean())
+    assert torch.equal(out, ops.attention(q, k, v, heads))
+
+
+def test_attention_strided_qkv_views_and_rotation(monkeypatch):
+    """q, k, v as column slices of one fused [L, 3W] buffer (row pitch 3W), and the rotated key order of the token-sharded form
+    (`first_key_row`): softmax is permutation invariant over keys, so the result matches the unrotated one to rounding."""
+    ops = _ops()
+    L, heads = 1500, 3
+    W = heads * 128
+    qkv = torch.randn(L, 3 * W, device=DEV).bfloat16()
+    q, k, v = qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:]
+    ref = _attn_ref(q.contiguous(), k.contiguous(), v.contiguous(), heads)
+    out = ops.attention(q, k, v, heads)
+    assert float((out.float() - ref).abs().max()) < 2e-2
+    for first in (0, 127, 128, 700, 1499):
+        rot = ops.attention(q, k, v, heads, first_key_row=first)
+        assert float((rot.float() - ref).abs().max()) < 2e-2, first
+        assert float((rot.float() - out.float()).abs().mean()) < 1e-3, first
+    monkeypatch.setenv("MC_ATTN_SPLITS", "3")
+    rot = ops.attention(q, k, v, heads, first_key_row=700)
+    assert float((rot.float() - ref).abs().max()) < 2e-2
+
+
 def test_attention_matches_sdpa_bf16_noise_level():
     """Our error against the fp64 reference must be no worse than 2x torch SDPA's bf16 error on the same inputs."""
     ops = _ops()
     Lq, Lk, heads = 512, 2048, 4
     W = heads * 128
     q, k, v = (torch.randn(n, W, device=DEV).bfloat16() for n in (Lq, Lk, Lk))
-    out = ops.attention(q, k, v.t().contiguous(), heads)
+    out = ops.attention(q, k, v, heads)
     ref = _attn_ref(q, k, v, heads)
     sd = torch.nn.functional.scaled_dot_product_attention(q.view(Lq, heads, 128).transpose(0, 1)[None], k.view(Lk, heads, 128).transpose(0, 1)[None],
                                                           v.view(Lk, heads, 128).transpose(0, 1)[None])[0].transpose(0, 1).reshape(Lq, W)
@@ -473,13 +579,13 @@ def test_attention_split_kv(Lq, Lk, heads, splits, monkeypatch):
     q = (torch.randn(Lq, W, device=DEV) * 3.0).bfloat16()
     k = torch.randn(Lk, W, device=DEV).bfloat16()
     v = torch.randn(Lk, W, device=DEV).bfloat16()
-    ld = (Lk + 7) // 8 * 8
-    vt = torch.zeros(W, ld, dtype=torch.bfloat16, device=DEV)
-    vt[:, :Lk] = v.t()
     monkeypatch.setenv("MC_ATTN_SPLITS", "1")
-    one = ops.attention(q, k, vt[:, :Lk], heads).clone()
-    monkeypatch.setenv("MC_ATTN_SPLITS", str(splits))
-    outs = [ops.attention(q, k, vt[:, :Lk], heads).clone() for _ in range(3)]
+    one = ops.attention(q, k, v, heads).clone()
+    if splits:
+        monkeypatch.setenv("MC_ATTN_SPLITS", str(splits))
+    else:
+        monkeypatch.delenv("MC_ATTN_SPLITS")
+    outs = [ops.attention(q, k, v, heads).clone() for _ in range(3)]
     ref = _attn_ref(q, k, v, heads)
     err = (outs[0].float() - ref).abs()
     assert float(err.max()) < 2e-2 and float(err.mean()) < 2e-3, (float(err.max()), float(err.mean()))
@@ -501,10 +607,8 @@ def test_attention_is_bit_reproducible(Lq, Lk, heads, qscale):
     W = heads * 128
     q = (torch.randn(Lq, W, device=DEV) * qscale).bfloat16()
     k = torch.randn(Lk, W, device=DEV).bfloat16()
-    ld = (Lk + 7) // 8 * 8
-    vt = torch.zeros(W, ld, dtype=torch.bfloat16, device=DEV)
-    vt[:, :Lk] = torch.randn(W, Lk, device=DEV).bfloat16()
-    outs = [ops.attention(q, k, vt[:, :Lk], heads).clone() for _ in range(4)]
+    v = torch.randn(Lk, W, device=DEV).bfloat16()
+    outs = [ops.attention(q, k, v, heads).clone() for _ in range(4)]
     assert torch.isfinite(outs[0].float()).all()
     for o in outs[1:]:
         assert torch.equal(outs[0], o)

@@ -47,13 +47,11 @@ def resid():
 
 
 check("gemm ffn2 gate-resid", resid)
-vt_buf = torch.zeros(D, N, dtype=torch.bfloat16, device=dev)
-check("gemm V^T rowbias", lambda: ops.gemm(w_qk[:D], a, bias[:D].contiguous(), _lib.MC_EPI_ROWBIAS_BF16, out=vt_buf))
-q, k, vt = rnd(N, D), rnd(N, D), rnd(D, N)
+q, k, vt = rnd(N, D), rnd(N, D), rnd(N, D)
 check("attention self 32760", lambda: ops.attention(q, k, vt, H))
 q6 = rnd(N, D, scale=4.0)
 check("attention self (large scores)", lambda: ops.attention(q6, k, vt, H))
-kc, vtc = rnd(512, D), rnd(D, 512)
+kc, vtc = rnd(512, D), rnd(512, D)
 check("attention cross 512", lambda: ops.attention(q, kc, vtc, H))
 em = rnd(6, D, scale=0.1, dtype=torch.float32)
 check("ln_modulate", lambda: ops.ln_modulate(x, em, 1, 0))

@@ -108,19 +108,19 @@ if which in ("all", "gemm"):
 if which in ("all", "attn"):
     q = torch.randn(N_TOK, D, device=dev).bfloat16()
     k = torch.randn(N_TOK, D, device=dev).bfloat16()
-    vt = torch.randn(D, N_TOK, device=dev).bfloat16()
+    vt = torch.randn(N_TOK, D, device=dev).bfloat16()
     o = torch.empty_like(q)
     rec("attn_self_32760", *timeit(lambda: ops.attention(q, k, vt, HEADS, out=o), iters=5, warmup=2), flops=4.0 * N_TOK * N_TOK * D)
     try:
         qh = q.view(1, N_TOK, HEADS, 128).transpose(1, 2)
         kh = k.view(1, N_TOK, HEADS, 128).transpose(1, 2)
-        vh = vt.t().contiguous().view(1, N_TOK, HEADS, 128).transpose(1, 2)
+        vh = vt.view(1, N_TOK, HEADS, 128).transpose(1, 2)
         rec("attn_self_sdpa_torch", *timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qh, kh, vh), iters=5, warmup=2),
             flops=4.0 * N_TOK * N_TOK * D)
     except Exception as ex:  # noqa: BLE001
         print("sdpa failed", ex)
     kc = torch.randn(512, D, device=dev).bfloat16()
-    vtc = torch.randn(D, 512, device=dev).bfloat16()
+    vtc = torch.randn(512, D, device=dev).bfloat16()
     rec("attn_cross_512", *timeit(lambda: ops.attention(q, kc, vtc, HEADS, out=o)), flops=4.0 * N_TOK * 512 * D)
 
 import os  # noqa: E402
