@@ -44,7 +44,6 @@ struct AttnParams {
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* out;
   int64_t ldo;
-  uint32_t v_lbo, v_sbo;  // MN-major descriptor strides of the V tile (bytes): box stride, 8-row group stride
   // KV tile order. Token-sharded runs consume the LOCAL keys first and the peers' keys in arrival order: tile j of this CTA is
   // global tile (tile_rot + j) mod total. seg_flags != nullptr: before a tile that touches rows of source segment s
   // (rows [s*seg_rows, (s+1)*seg_rows)) is loaded, seg_flags[s] must have reached seg_epoch (written by the peer copy).
@@ -64,6 +63,23 @@ __device__ __forceinline__ void exp2_pair(float& a, float& b, int pair) {
     a = ptx::ex2_approx(a);
     b = ptx::ex2_approx(b);
   }
+}
+
+// Ragged last KV tile: the score columns of keys past Lk are overwritten with -inf IN TMEM before the softmax reads the tile.
+// Kept out of line and on the TMEM side on purpose: as a register-level `if (col >= valid) s = -inf` the compiler if-converts
+// the test into a compare + select per element of EVERY tile (+40 % instructions in the softmax loop); this runs once per CTA.
+__device__ __noinline__ void mask_padding_columns(uint32_t tmem_row, int valid, int width) {
+  for (int h = 0; h < width; h += 32) {
+    if (h + 32 <= valid) continue;
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(tmem_row + h, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (h + c >= valid) v[c] = 0xff800000u;  // -inf
+    ptx::tmem_st_32x32b_x32(tmem_row + h, v);
+  }
+  ptx::tmem_st_wait();
 }
 
 // token-sharded runs: block until every source segment a KV tile touches has landed (flag written by the peer's copy stream
@@ -105,7 +121,7 @@ constexpr int kOffV = kOffK + kStages * kKBytes;  // +64 KB
 constexpr int kOffBar = kOffV + kStages * kVBytes;  // 192 KB
 constexpr int kSmem = kOffBar + 256;
 constexpr int kThreads = 384;  // warps 0-3 softmax of query tile 0, 4-7 of query tile 1, warp 8 TMA, warp 9 MMA, 10-11 idle
-constexpr int kSoftmaxRegs = 216, kDataRegs = 56;  // setmaxnreg: the data-path warpgroup hands its registers to the softmax ones
+constexpr int kSoftmaxRegs = 208, kDataRegs = 80;  // setmaxnreg: the data-path warpgroup hands its registers to the softmax ones
 constexpr int kTmemCols = 512;  // S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_t (64 packed columns) overwrites S_t
 }  // namespace lk
 
@@ -122,9 +138,10 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
   uint64_t* v_full = bars + 5;    // [2]
   uint64_t* v_empty = bars + 7;   // [2]
   uint64_t* s_full = bars + 9;    // [2] per query tile
-  uint64_t* p_full = bars + 11;   // [2] per query tile, 128 arrivals
-  uint64_t* pv_done = bars + 13;  // [2] per query tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_half0 = bars + 11;  // [2] per query tile, 128 arrivals: P columns of keys 0..63 of the tile are in TMEM
+  uint64_t* p_half1 = bars + 13;  // [2] per query tile, 128 arrivals: keys 64..127
+  uint64_t* pv_done = bars + 15;  // [2] per query tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * kBQ);
@@ -153,7 +170,8 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
       ptx::mbar_init(&v_full[s], 1);
       ptx::mbar_init(&v_empty[s], 1);
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&p_full[s], 128);
+      ptx::mbar_init(&p_half0[s], 128);
+      ptx::mbar_init(&p_half1[s], 128);
       ptx::mbar_init(&pv_done[s], 1);
     }
     ptx::fence_mbar_init();
@@ -168,74 +186,100 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
     ptx::setmaxnreg_dec<kDataRegs>();  // idle warps of the data-path warpgroup
   } else if (warp == 8) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
+    // (whole warp in uniform control flow, the copies issued by one elected lane: see ptx::elect_one)
     ptx::setmaxnreg_dec<kDataRegs>();
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(q_full, 2 * kQTileBytes);
       for (int t = 0; t < 2; ++t) {
         ptx::tma_load_2d(smem + kOffQ + t * kQTileBytes, &tmap_q, q_full, head * kHD, q0 + t * kBQ);
         ptx::tma_load_2d(smem + kOffQ + t * kQTileBytes + kQTileBytes / 2, &tmap_q, q_full, head * kHD + 64, q0 + t * kBQ);
       }
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int kv0 = tile_of(j) * kBKV;
-        wait_segments(p, kv0, kBKV);
-        ptx::mbar_wait(&k_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int kv0 = tile_of(j) * kBKV;
+      if (p.seg_flags != nullptr) {
+        if (lane == 0) wait_segments(p, kv0, kBKV);
+        __syncwarp();
+      }
+      ptx::mbar_wait(&k_empty[s], ph ^ 1);
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&k_full[s], kKBytes);
         ptx::tma_load_2d(smem + kOffK + s * kKBytes, &tmap_k, &k_full[s], head * kHD, kv0);
         ptx::tma_load_2d(smem + kOffK + s * kKBytes + kKBytes / 2, &tmap_k, &k_full[s], head * kHD + 64, kv0);
-        ptx::mbar_wait(&v_empty[s], ph ^ 1);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&v_empty[s], ph ^ 1);
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&v_full[s], kVBytes);
         ptx::tma_load_2d(smem + kOffV + s * kVBytes, &tmap_v, &v_full[s], head * kHD, kv0);
         ptx::tma_load_2d(smem + kOffV + s * kVBytes + kVBytes / 2, &tmap_v, &v_full[s], head * kHD + 64, kv0);
       }
+      __syncwarp();
     }
   } else if (warp == 9) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
+    // All 32 lanes walk the loop and wait on the barriers; the MMAs and commits are issued by the elected lane.
     ptx::setmaxnreg_dec<kDataRegs>();
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(kBQ, kBKV);      // S: 128 x 128, both operands K-major
-      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32_bmn(kBQ, kHD);   // O: 128 x 128, B = V tile MN-major
-      auto issue_s = [&](int t, int j) {  // S_t(j) = Q_t K_j^T
-        const uint32_t q_addr = ptx::smem_u32(smem + kOffQ + t * kQTileBytes);
-        const uint32_t k_addr = ptx::smem_u32(smem + kOffK + (j & 1) * kKBytes);
+    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(kBQ, kBKV);      // S: 128 x 128, both operands K-major
+    constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32_bmn(kBQ, kHD);   // O: 128 x 128, B = V tile MN-major
+    const uint32_t q_base = ptx::smem_u32(smem + kOffQ), k_base = ptx::smem_u32(smem + kOffK), v_base = ptx::smem_u32(smem + kOffV);
+    auto issue_s = [&](int t, int j) {  // S_t(j) = Q_t K_j^T   (elected lane only)
+      const uint64_t da0 = ptx::umma_desc_sw128_kmajor(q_base + t * kQTileBytes);
+      const uint64_t db0 = ptx::umma_desc_sw128_kmajor(k_base + (j & 1) * kKBytes);
 #pragma unroll
-        for (int kk = 0; kk < kHD / 16; ++kk) {
-          const uint64_t da = ptx::umma_desc_sw128_kmajor(q_addr + (kk >> 2) * (kQTileBytes / 2)) + 2 * (kk & 3);
-          const uint64_t db = ptx::umma_desc_sw128_kmajor(k_addr + (kk >> 2) * (kKBytes / 2)) + 2 * (kk & 3);
-          ptx::umma_ss(tmem_base + t * 128, da, db, idesc_s, kk != 0 ? 1u : 0u);
-        }
-      };
-      ptx::mbar_wait(q_full, 0);
-      ptx::mbar_wait(&k_full[0], 0);
-      ptx::tc_fence_after();
+      for (int kk = 0; kk < kHD / 16; ++kk) {
+        // 64-column half (kk >> 2) is a separate TMA box kQTileBytes / 2 further; inside a box one K-step is 32 B (+2 in the >>4 field)
+        const uint64_t off = static_cast<uint64_t>((kk >> 2) * (kQTileBytes / 2 / 16) + 2 * (kk & 3));
+        ptx::umma_ss(tmem_base + t * 128, da0 + off, db0 + off, idesc_s, kk != 0 ? 1u : 0u);
+      }
+    };
+    ptx::mbar_wait(q_full, 0);
+    ptx::mbar_wait(&k_full[0], 0);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
       issue_s(0, 0);
       ptx::umma_commit(&s_full[0]);
       issue_s(1, 0);
       ptx::umma_commit(&k_empty[0]);
       ptx::umma_commit(&s_full[1]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t v_addr = ptx::smem_u32(smem + kOffV + (j & 1) * kVBytes);
-        for (int t = 0; t < 2; ++t) {
-          ptx::mbar_wait(&p_full[t], j & 1);
-          if (t == 0) ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
-          ptx::tc_fence_after();
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint64_t dv0 = ptx::umma_desc_sw128_mnmajor(v_base + (j & 1) * kVBytes, kBKV * 128);  // LBO = one [128 kv x 64 d] box
+      for (int t = 0; t < 2; ++t) {
+        // O_t += P_t(j) V_j, A from TMEM (8 packed columns per K16 step), in two halves: the first 64 keys' probabilities are
+        // signalled as soon as they are written, so this half of the MMA runs while the softmax warps exponentiate the rest
 #pragma unroll
-          for (int kk = 0; kk < kBKV / 16; ++kk) {  // O_t += P_t(j) V_j : A from TMEM (8 packed columns per K16 step)
-            const uint64_t db = ptx::umma_desc_sw128_mnmajor(v_addr + kk * 2048, p.v_lbo, p.v_sbo);
-            ptx::umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
-          }
-          if (t == 1) ptx::umma_commit(&v_empty[j & 1]);
-          ptx::umma_commit(&pv_done[t]);
-          if (j + 1 < n_tiles) {
-            if (t == 0) {
-              ptx::mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-              ptx::tc_fence_after();
+        for (int half = 0; half < 2; ++half) {
+          ptx::mbar_wait(half == 0 ? &p_half0[t] : &p_half1[t], j & 1);
+          if (t == 0 && half == 0) ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int kk = half * 4; kk < half * 4 + 4; ++kk)  // one K-step = 16 kv rows = 2048 B of the MN-major tile
+              ptx::umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, dv0 + static_cast<uint64_t>(kk * (2048 / 16)), idesc_o,
+                           (j | kk) != 0 ? 1u : 0u);
+            if (half == 1) {
+              if (t == 1) ptx::umma_commit(&v_empty[j & 1]);
+              ptx::umma_commit(&pv_done[t]);
             }
+          }
+          __syncwarp();
+        }
+        if (j + 1 < n_tiles) {
+          if (t == 0) {
+            ptx::mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+            ptx::tc_fence_after();
+          }
+          if (ptx::elect_one()) {
             issue_s(t, j + 1);  // overwrites S_t / P_t(j): ordered behind PV_t(j) by the tensor pipe
             if (t == 1) ptx::umma_commit(&k_empty[(j + 1) & 1]);
             ptx::umma_commit(&s_full[t]);  // fires when S_t(j+1) AND everything before it (PV_t(j)) has completed
           }
+          __syncwarp();
         }
       }
     }
@@ -251,30 +295,29 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
     float m = -INFINITY, l = 0.f;
 
     for (int j = 0; j < n_tiles; ++j) {
-      // s_full(j) also certifies that PV_t(j-1) has completed (commit semantics): O_t is quiescent until p_full(j) is signalled
+      // s_full(j) also certifies that PV_t(j-1) has completed (commit semantics): O_t is quiescent until p_half0(j) is signalled
       ptx::mbar_wait(&s_full[t], j & 1);
       ptx::tc_fence_after();
+      const int valid = p.Lk - tile_of(j) * kBKV;  // columns >= valid are padding (only the globally last tile)
+      if (valid < kBKV) mask_padding_columns(tmem_s, valid, kBKV);  // warp-uniform, at most once per CTA
       uint32_t sreg[4][32];
 #pragma unroll
       for (int h = 0; h < 4; ++h) ptx::tmem_ld_32x32b_x32(tmem_s + h * 32, sreg[h]);
       ptx::tmem_ld_wait();
-      const int valid = p.Lk - tile_of(j) * kBKV;  // columns >= valid are padding (only the globally last tile)
-      if (valid < kBKV) {  // warp-uniform, at most once per CTA
+      // 3-input max, 0.5 instruction per element, in EIGHT independent chains (two per 32-column chunk): the exponentials cannot
+      // start before the row max is known, so the chain depth (8 dependent ops) is what this costs, not the instruction count
+      float mxa[4], mxb[4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (h * 32 + c >= valid) sreg[h][c] = 0xff800000u;  // -inf
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY;  // two chains of 3-input max: 0.5 instruction per element
-#pragma unroll
-      for (int h = 0; h < 4; ++h)
+      for (int h = 0; h < 4; ++h) {
+        mxa[h] = -INFINITY, mxb[h] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          mx0 = ptx::max3(mx0, __uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1]));
-          mx1 = ptx::max3(mx1, __uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3]));
+          mxa[h] = ptx::max3(mxa[h], __uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1]));
+          mxb[h] = ptx::max3(mxb[h], __uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3]));
         }
-      const float m_new = fmaxf(m, fmaxf(mx0, mx1) * p.scale_log2);
+      }
+      const float mx = fmaxf(ptx::max3(mxa[0], mxa[1], mxa[2]), fmaxf(mxa[3], fmaxf(ptx::max3(mxb[0], mxb[1], mxb[2]), mxb[3])));
+      const float m_new = fmaxf(m, mx * p.scale_log2);
       if (j == 0) {
         m = m_new;
       } else {
@@ -316,6 +359,11 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
           pk[(c >> 1) + 1] = pack_bf16x2(b0, b1);
         }
         ptx::tmem_st_32x32b_x16(tmem_s + h * 16, pk);
+        if (h == 1) {  // keys 0..63 of this tile are in place: let the first half of PV_t(j) go
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&p_half0[t]);
+        }
       }
       float s0, s1, s2, s3;
       ptx::unpack_f32x2(sum2a, s0, s1);
@@ -323,7 +371,7 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
       l += (s0 + s1) + (s2 + s3);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&p_full[t]);
+      ptx::mbar_arrive(&p_half1[t]);
     }
 
     // ---- epilogue: O_t / l -> bf16 -> global (or the normalised fp32 partial of this split)
@@ -437,68 +485,73 @@ __global__ void __launch_bounds__(sk::kThreads, 2)
 
   if (warp == 4) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(q_full, kQBytes);
       ptx::tma_load_2d(smem + kOffQ, &tmap_q, q_full, head * kHD, q0);
       ptx::tma_load_2d(smem + kOffQ + kQBytes / 2, &tmap_q, q_full, head * kHD + 64, q0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int kv0 = (t0 + j) * kBKV;
-        ptx::mbar_wait(&k_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int kv0 = (t0 + j) * kBKV;
+      ptx::mbar_wait(&k_empty[s], ph ^ 1);
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&k_full[s], kKBytes);
         ptx::tma_load_2d(smem + kOffK + s * kKBytes, &tmap_k, &k_full[s], head * kHD, kv0);
         ptx::tma_load_2d(smem + kOffK + s * kKBytes + kKBytes / 2, &tmap_k, &k_full[s], head * kHD + 64, kv0);
-        ptx::mbar_wait(&v_empty[s], ph ^ 1);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&v_empty[s], ph ^ 1);
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&v_full[s], kVBytes);
         ptx::tma_load_2d(smem + kOffV + s * kVBytes, &tmap_v, &v_full[s], head * kHD, kv0);
         ptx::tma_load_2d(smem + kOffV + s * kVBytes + kVBytes / 2, &tmap_v, &v_full[s], head * kHD + 64, kv0);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
-    // ------------------------------------------------ MMA issuer --------------------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(kBQ, kBKV);     // 128 x 64
-      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32_bmn(kBQ, kHD);  // 128 x 128, B = V tile MN-major
-      const uint32_t q_addr = ptx::smem_u32(smem + kOffQ);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        const uint32_t k_addr = ptx::smem_u32(smem + kOffK + s * kKBytes);
-        const uint32_t tmem_s = tmem_base + s * kBKV;
+    // ------------------------------------------------ MMA issuer (elected lane, uniform control flow) --------------
+    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(kBQ, kBKV);     // 128 x 64
+    constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32_bmn(kBQ, kHD);  // 128 x 128, B = V tile MN-major
+    const uint32_t q_base = ptx::smem_u32(smem + kOffQ), k_base = ptx::smem_u32(smem + kOffK), v_base = ptx::smem_u32(smem + kOffV);
+    auto issue_s = [&](int j) {  // elected lane only
+      const int s = j & 1;
+      const uint64_t da0 = ptx::umma_desc_sw128_kmajor(q_base), db0 = ptx::umma_desc_sw128_kmajor(k_base + s * kKBytes);
 #pragma unroll
-        for (int kk = 0; kk < kHD / 16; ++kk) {
-          const uint64_t da = ptx::umma_desc_sw128_kmajor(q_addr + (kk >> 2) * (kQBytes / 2)) + 2 * (kk & 3);
-          const uint64_t db = ptx::umma_desc_sw128_kmajor(k_addr + (kk >> 2) * (kKBytes / 2)) + 2 * (kk & 3);
-          ptx::umma_ss(tmem_s, da, db, idesc_s, kk != 0 ? 1u : 0u);
-        }
-        ptx::umma_commit(&k_empty[s]);
-        ptx::umma_commit(&s_full[s]);
-      };
-      ptx::mbar_wait(q_full, 0);
-      ptx::mbar_wait(&k_full[0], 0);
-      ptx::tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) {
-          const int t = j + 1;
-          ptx::mbar_wait(&k_full[t & 1], (t >> 1) & 1);
-          // S buffer t&1 was last used by tile t-2: its softmax drained it before p_full(t-2), which was waited before PV(t-2)
-          // was issued, and PV(t-2) (the reader of P in that buffer) executes before this MMA on the in-order tensor pipe.
-          ptx::tc_fence_after();
-          issue_s(t);
-        }
-        ptx::mbar_wait(p_full, j & 1);
-        ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+      for (int kk = 0; kk < kHD / 16; ++kk)
+        ptx::umma_ss(tmem_base + s * kBKV, da0 + static_cast<uint64_t>((kk >> 2) * (kQBytes / 2 / 16) + 2 * (kk & 3)),
+                     db0 + static_cast<uint64_t>((kk >> 2) * (kKBytes / 2 / 16) + 2 * (kk & 3)), idesc_s, kk != 0 ? 1u : 0u);
+      ptx::umma_commit(&k_empty[s]);
+      ptx::umma_commit(&s_full[s]);
+    };
+    ptx::mbar_wait(q_full, 0);
+    ptx::mbar_wait(&k_full[0], 0);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) issue_s(0);
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) {
+        const int t = j + 1;
+        ptx::mbar_wait(&k_full[t & 1], (t >> 1) & 1);
+        // S buffer t&1 was last used by tile t-2: its softmax drained it before p_full(t-2), which was waited before PV(t-2)
+        // was issued, and PV(t-2) (the reader of P in that buffer) executes before this MMA on the in-order tensor pipe.
         ptx::tc_fence_after();
-        const uint32_t v_addr = ptx::smem_u32(smem + kOffV + (j & 1) * kVBytes);
+        if (ptx::elect_one()) issue_s(t);
+        __syncwarp();
+      }
+      ptx::mbar_wait(p_full, j & 1);
+      ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint64_t dv0 = ptx::umma_desc_sw128_mnmajor(v_base + (j & 1) * kVBytes, kBKV * 128);  // LBO = one [64 kv x 64 d] box
 #pragma unroll
-        for (int kk = 0; kk < kBKV / 16; ++kk) {
-          const uint64_t db = ptx::umma_desc_sw128_mnmajor(v_addr + kk * 2048, p.v_lbo, p.v_sbo);
-          ptx::umma_ts(tmem_o, tmem_base + (j & 1) * kBKV + kk * 8, db, idesc_o, (j | kk) != 0 ? 1u : 0u);
-        }
+        for (int kk = 0; kk < kBKV / 16; ++kk)
+          ptx::umma_ts(tmem_o, tmem_base + (j & 1) * kBKV + kk * 8, dv0 + static_cast<uint64_t>(kk * (2048 / 16)), idesc_o, (j | kk) != 0 ? 1u : 0u);
         ptx::umma_commit(&v_empty[j & 1]);
         ptx::umma_commit(pv_done);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------ softmax warps -----------------------------------------------
@@ -509,19 +562,12 @@ __global__ void __launch_bounds__(sk::kThreads, 2)
       const int b = j & 1;
       ptx::mbar_wait(&s_full[b], (j >> 1) & 1);
       ptx::tc_fence_after();
+      const int valid = p.Lk - (t0 + j) * kBKV;  // columns >= valid are padding (only possible on the last tile)
+      if (valid < kBKV) mask_padding_columns(tmem_base + lane_sel + b * kBKV, valid, kBKV);  // warp-uniform, at most once per CTA
       uint32_t sreg[2][32];
       ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV, sreg[0]);
       ptx::tmem_ld_32x32b_x32(tmem_base + lane_sel + b * kBKV + 32, sreg[1]);
       ptx::tmem_ld_wait();
-
-      const int valid = p.Lk - (t0 + j) * kBKV;  // columns >= valid are padding (only possible on the last tile)
-      if (valid < kBKV) {                  // warp-uniform, taken at most once per CTA
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (h * 32 + c >= valid) sreg[h][c] = 0xff800000u;  // -inf
-      }
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int h = 0; h < 2; ++h)
@@ -760,10 +806,6 @@ extern "C" int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int
   p.part_o = pl.splits > 1 ? part_o : nullptr, p.part_ml = part_ml;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out), p.ldo = ldo;
-  // MN-major V tile: two TMA boxes [kv_tile rows][64 d] -> box stride = kv_tile * 128 B, 8-row groups 1024 B apart.
-  // MC_ATTN_VDESC=1 swaps the two (descriptor bring-up aid, tools/diag_vdesc.py).
-  p.v_lbo = static_cast<uint32_t>(pl.kv_tile) * 128u, p.v_sbo = 1024u;
-  if (mc::env_int("MC_ATTN_VDESC", 0, 1, 0) == 1) p.v_lbo = 1024u, p.v_sbo = static_cast<uint32_t>(pl.kv_tile) * 128u;
   // start with the first tile that lies entirely inside the caller's own (already resident) rows; the tile straddling the segment
   // boundary before it comes last in the rotated order
   p.tile_rot = ((first_key_row + pl.kv_tile - 1) / pl.kv_tile) % pl.total_tiles;

@@ -219,35 +219,38 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;  // running k-block counter across tiles -> smem stage / phase
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+    // TMA producer: the whole warp walks the loop in uniform control flow, one elected lane issues the copies (ptx::elect_one)
+    uint32_t it = 0;  // running k-block counter across tiles -> smem stage / phase
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * kBN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        if (ptx::elect_one()) {
           uint8_t* sa = smem + s * kStageBytes;
           ptx::mbar_expect_tx(&full_bar[s], kStageBytes);
           ptx::tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBK, m0);
           ptx::tma_load_2d(sa + kTileABytes, &tmap_b, &full_bar[s], kb * kBK, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kBM, kBN);
-      uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-        const uint32_t acc = t & 1;
-        ptx::mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator (passes on first use)
+    // MMA issuer: all lanes wait on the barriers, the elected lane issues the four K16 MMAs of a stage and the commits
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kBM, kBN);
+    uint32_t it = 0, t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const uint32_t acc = t & 1;
+      ptx::mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator (passes on first use)
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kBN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * kBN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          ptx::mbar_wait(&full_bar[s], ph);
-          ptx::tc_fence_after();
+        if (ptx::elect_one()) {
           const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes);
           const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
           const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + kTileABytes);
@@ -256,9 +259,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             // advance 16 bf16 = 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
             ptx::umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
+          ptx::umma_commit(&empty_bar[s]);                       // stage reusable once these MMAs have read it
+          if (kb == num_kb - 1) ptx::umma_commit(&acc_full[acc]);  // accumulator complete
         }
-        ptx::umma_commit(&acc_full[acc]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else {

@@ -31,7 +31,7 @@ constexpr int kSmem = kOffBars + 128;
 constexpr int kConvWarps = 16;
 constexpr int kConvThreads = kConvWarps * 32;  // 512: 4 threads per row
 constexpr int kThreads = kConvThreads + 128;   // + one data-path warpgroup: TMA warp, MMA warp, two idle warps
-constexpr int kConvRegs = 112, kDataRegs = 40; // setmaxnreg: the data-path warpgroup hands its registers to the converters
+constexpr int kConvRegs = 104, kDataRegs = 32; // setmaxnreg: the data-path warpgroup hands its registers to the converters
 constexpr int kTmemCols = 64;
 constexpr int kMaxPeers = 8;
 }  // namespace hd
@@ -183,33 +183,33 @@ __global__ void __launch_bounds__(hd::kThreads, 1)
   } else if (warp == kConvWarps) {
     // ------------------------------------------------ TMA producer: W' hi / lo chunks ------------------------------------------
     ptx::setmaxnreg_dec<kDataRegs>();
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int st = 0; st < n_sub; ++st)
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          ptx::mbar_wait(&a_empty[s], ph ^ 1);  // the MMAs that read this stage (A and W') have completed
-          uint8_t* wdst = smem + s * kStageBytes + 2 * kATile;
-          ptx::mbar_expect_tx(&w_full[s], 2 * kWTile);
-          ptx::tma_load_2d(wdst, &tmap_whi, &w_full[s], kc * kKC, 0);
-          ptx::tma_load_2d(wdst + kWTile, &tmap_wlo, &w_full[s], kc * kKC, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int st = 0; st < n_sub; ++st)
+      for (int kc = 0; kc < nkc; ++kc) {
+        ptx::mbar_wait(&a_empty[stage], phase ^ 1);  // the MMAs that read this stage (A and W') have completed
+        if (ptx::elect_one()) {
+          uint8_t* wdst = smem + stage * kStageBytes + 2 * kATile;
+          ptx::mbar_expect_tx(&w_full[stage], 2 * kWTile);
+          ptx::tma_load_2d(wdst, &tmap_whi, &w_full[stage], kc * kKC, 0);
+          ptx::tma_load_2d(wdst + kWTile, &tmap_wlo, &w_full[stage], kc * kKC, 0);
         }
-    }
+        __syncwarp();
+        if (++stage == kStages) stage = 0, phase ^= 1;
+      }
   } else if (warp == kConvWarps + 1) {
-    // ------------------------------------------------ MMA issuer ----------------------------------------------------------------
+    // ------------------------------------------------ MMA issuer (elected lane, uniform control flow) ---------------------------
     ptx::setmaxnreg_dec<kDataRegs>();
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, kOut);  // 128 x 64, both operands K-major
-      uint32_t it = 0;
-      for (int st = 0; st < n_sub; ++st) {
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          ptx::mbar_wait(&a_full[s], ph);
-          ptx::mbar_wait(&w_full[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t base = ptx::smem_u32(smem + s * kStageBytes);
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, kOut);  // 128 x 64, both operands K-major
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int st = 0; st < n_sub; ++st) {
+      for (int kc = 0; kc < nkc; ++kc) {
+        ptx::mbar_wait(&a_full[stage], phase);
+        ptx::mbar_wait(&w_full[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t base = ptx::smem_u32(smem + stage * kStageBytes);
           const uint64_t a_hi = ptx::umma_desc_sw128_kmajor(base), a_lo = ptx::umma_desc_sw128_kmajor(base + kATile);
           const uint64_t w_hi = ptx::umma_desc_sw128_kmajor(base + 2 * kATile), w_lo = ptx::umma_desc_sw128_kmajor(base + 2 * kATile + kWTile);
 #pragma unroll
@@ -218,11 +218,13 @@ __global__ void __launch_bounds__(hd::kThreads, 1)
             ptx::umma_ss(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
             ptx::umma_ss(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
           }
-          ptx::umma_commit(&a_empty[s]);
+          ptx::umma_commit(&a_empty[stage]);
+          // the next tile's first MMA overwrites the accumulator: it cannot be issued before a_full of its first chunk, which the
+          // epilogue warps only arrive on after they have drained the accumulator (program order in those warps)
+          if (kc == nkc - 1) ptx::umma_commit(acc_full);
         }
-        ptx::umma_commit(acc_full);
-        // the next tile's first MMA overwrites the accumulator: it cannot be issued before a_full of its first chunk, which the
-        // epilogue warps only arrive on after they have drained the accumulator (program order in those warps)
+        __syncwarp();
+        if (++stage == kStages) stage = 0, phase ^= 1;
       }
     }
   } else {
@@ -231,19 +233,21 @@ __global__ void __launch_bounds__(hd::kThreads, 1)
     const int tid = threadIdx.x;
     const int rt = tid >> 2, sub = tid & 3;  // tile row, 16-element slice of the 64-column chunk
     const int sw = rt & 7;
-    uint32_t it = 0;
+    const uint32_t row_off = static_cast<uint32_t>((rt >> 3) * 1024 + sw * 128);
+    const uint32_t ch0 = static_cast<uint32_t>(((2 * sub) ^ sw) * 16), ch1 = static_cast<uint32_t>(((2 * sub + 1) ^ sw) * 16);  // 128-byte swizzle
+    int stage = 0;
+    uint32_t phase = 0;
     const float inv_cols = 1.0f / static_cast<float>(p.cols);
     for (int st = 0; st < n_sub; ++st) {
       const int64_t row = cta_row0 + static_cast<int64_t>(st) * kRows + rt;
       const bool live = row < cta_row1;
-      ChunkRegs<HIT> cur, nxt;
-      if (live) load_chunk<HIT>(p, row, sub * 16, cur);
       float pilot = 0.f, mean = 0.f, m2 = 0.f;  // running mean / M2 of the shifted values over the slices this thread has seen
-      for (int kc = 0; kc < nkc; ++kc, ++it) {
-        if (live && kc + 1 < nkc) load_chunk<HIT>(p, row, (kc + 1) * kKC + sub * 16, nxt);
+
+      // one 64-column chunk of this thread's row slice: statistics, hi / lo split, swizzled store, hand-over to the MMA warp
+      auto process = [&](const ChunkRegs<HIT>& c, int kc) {
         float v[16];
         if (live) {
-          chunk_values<HIT>(p, cur, v);
+          chunk_values<HIT>(p, c, v);
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -270,30 +274,42 @@ __global__ void __launch_bounds__(hd::kThreads, 1)
           cq = fmaf(d, d, cq);
         }
         // Chan: combine (n_a = 16*kc, mean, m2) with (16, cm, cq)
-        const float na = 16.0f * static_cast<float>(kc), n = na + 16.0f;
+        const float na = 16.0f * static_cast<float>(kc), rn = 1.0f / (na + 16.0f);
         const float delta = cm - mean;
-        mean = fmaf(delta, 16.0f / n, mean);
-        m2 += cq + delta * delta * (na * 16.0f / n);
+        mean = fmaf(delta, 16.0f * rn, mean);
+        m2 += fmaf(delta * delta, na * 16.0f * rn, cq);
 
-        uint32_t hi[8], lo[8];
+        ptx::mbar_wait(&a_empty[stage], phase ^ 1);
+        uint8_t* arow = smem + stage * kStageBytes + row_off;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          hi[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-          lo[i] = pack_bf16x2(v[2 * i] - bf16_lo(hi[i]), v[2 * i + 1] - bf16_hi(hi[i]));
+        for (int hf = 0; hf < 2; ++hf) {  // 8 elements -> one 16-byte chunk of the hi tile and one of the lo tile
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = v[hf * 8 + 2 * i], b = v[hf * 8 + 2 * i + 1];
+            hi[i] = pack_bf16x2(a, b);
+            lo[i] = pack_bf16x2(a - bf16_lo(hi[i]), b - bf16_hi(hi[i]));
+          }
+          const uint32_t ch = hf == 0 ? ch0 : ch1;
+          *reinterpret_cast<uint4*>(arow + ch) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(arow + kATile + ch) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        ptx::mbar_wait(&a_empty[s], ph ^ 1);
-        uint8_t* arow = smem + s * kStageBytes + (rt >> 3) * 1024 + sw * 128;
-        const int ch0 = (2 * sub) ^ sw, ch1 = (2 * sub + 1) ^ sw;  // 16-byte chunk index XOR (row % 8): the 128-byte swizzle
-        *reinterpret_cast<uint4*>(arow + ch0 * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(arow + ch1 * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        *reinterpret_cast<uint4*>(arow + kATile + ch0 * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(arow + kATile + ch1 * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a_full[s]);
-        if (kc + 1 < nkc) cur = nxt;
+        if (lane == 0) ptx::mbar_arrive(&a_full[stage]);
+        if (++stage == kStages) stage = 0, phase ^= 1;
+      };
+
+      // two register buffers in ping-pong: the loads of chunk kc+1 are in flight while chunk kc is converted
+      ChunkRegs<HIT> bufa, bufb;
+      if (live) load_chunk<HIT>(p, row, sub * 16, bufa);
+      for (int kc = 0; kc < nkc; kc += 2) {
+        if (live && kc + 1 < nkc) load_chunk<HIT>(p, row, (kc + 1) * kKC + sub * 16, bufb);
+        process(bufa, kc);
+        if (kc + 1 < nkc) {
+          if (live && kc + 2 < nkc) load_chunk<HIT>(p, row, (kc + 2) * kKC + sub * 16, bufa);
+          process(bufb, kc + 1);
+        }
       }
       // row statistics: merge the four slices of the row (Chan again, equal counts), publish (mean_shifted, rstd)
 #pragma unroll

@@ -56,6 +56,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp. tcgen05.mma / commit and the TMA instructions take their operands from UNIFORM registers: under
+// a divergent `if (lane == 0)` ptxas has to wrap every one of them in a uniformisation loop (ELECT / PLOP3 / BRA.U.ANY, ~10
+// instructions and ~100 cycles per MMA — enough to make the single issuing thread the bottleneck of a kernel whose MMAs take 64
+// cycles each). Issued under elect.sync from warp-uniform control flow they are single instructions. The elected lane is the same on
+// every call (the lowest active one), which tcgen05.commit relies on.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // proxies / fences
 // ------------------------------------------------------------------------------------------------

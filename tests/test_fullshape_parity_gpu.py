@@ -84,16 +84,20 @@ def test_attention_full_key_sequence_vs_fp64(Lq, qscale):
     out = ops.attention_rowmajor_v(q, k, v, HEADS)
     ref = _attn_ref64(q, k, v, HEADS)
     err = (out.float() - ref).abs()
-    # with 32760 iid keys the output is a mean of ~N(0,1) rows: |out| ~ 1/sqrt(Neff); P is rounded to bf16 (rel 2^-9) before PV
-    # and the output to bf16. Same absolute bounds as the short-sequence test, plus an error RELATIVE to the output's own scale.
-    assert float(err.max()) < 2e-2, float(err.max())
-    assert float(err.mean()) < 2e-3, float(err.mean())
-    assert rel_l2(out.float(), ref) < 8e-3, rel_l2(out.float(), ref)
     sd = torch.nn.functional.scaled_dot_product_attention(q.view(Lq, HEADS, 128).transpose(0, 1)[None], k.view(N, HEADS, 128).transpose(0, 1)[None],
                                                           v.view(N, HEADS, 128).transpose(0, 1)[None])[0].transpose(0, 1).reshape(Lq, D)
+    err_sd = (sd.float() - ref).abs()
     e_ours, e_sdpa = rel_l2(out.float(), ref), rel_l2(sd.float(), ref)
-    print(f"Lq={Lq} qscale={qscale}: rel-L2 vs fp64 ours {e_ours:.3e}, torch SDPA {e_sdpa:.3e}")
+    print(f"Lq={Lq} qscale={qscale}: rel-L2 vs fp64 ours {e_ours:.3e}, torch SDPA {e_sdpa:.3e}; max abs err ours {float(err.max()):.3e}, "
+          f"SDPA {float(err_sd.max()):.3e}; |ref| max {float(ref.abs().max()):.2f}")
+    # P is rounded to bf16 (rel 2^-9) before PV and the output to bf16: with unit logits the output is a mean over ~32760 keys
+    # (|out| ~ 0.01), with 6-7x logits the softmax is peaked and |out| ~ 1, so the absolute error scales with the case. The
+    # yardstick is the library kernel on the same tensors: no worse than 2x torch SDPA's error against fp64, in rel-L2 and in the
+    # maximum; plus a fixed relative bound.
     assert e_ours <= 2.0 * e_sdpa + 1e-4, (e_ours, e_sdpa)
+    assert float(err.max()) <= 2.0 * float(err_sd.max()) + 1e-3, (float(err.max()), float(err_sd.max()))
+    assert e_ours < 8e-3, e_ours
+    assert float(err.mean()) < 2e-3, float(err.mean())
 
 
 def test_attention_full_square_slices_vs_fp64():
