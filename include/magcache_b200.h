@@ -256,10 +256,29 @@ int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
  * value rows [first_key_row, ...) are the caller's own and already resident; the other ranks' rows arrive while the kernel runs.
  * KV tiles are consumed in rotated order starting at the caller's own rows, and before a tile that touches source segment s
  * (rows [s*seg_rows, (s+1)*seg_rows)) is loaded the kernel waits until seg_flags[s] (device memory, written by the sender
- * after the segment's data) has reached seg_epoch. seg_flags == NULL: no waiting (plain rotation). */
+ * after the segment's data) has reached *seg_epoch (device memory, read when the kernel runs). seg_flags == NULL: no waiting
+ * (plain rotation). */
 int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                        int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* workspace, int64_t workspace_bytes,
-                       int32_t first_key_row, const uint32_t* seg_flags, uint32_t seg_epoch, int32_t seg_rows, void* stream);
+                       int32_t first_key_row, const uint32_t* seg_flags, const uint32_t* seg_epoch, int32_t seg_rows, void* stream);
+
+/* ---- peer-to-peer exchange of token-sharded runs (one node, NVLink / NVSwitch; csrc/p2p.cu) ------------------------------------
+ * The counterpart of the reference's sequence-parallel gather (videosys/core/comm.py:272-292): every rank owns a window that its
+ * peers map through CUDA IPC; K|V segments and flags are moved by the copy engines, consumers poll the flags in device memory.
+ * mc_p2p_alloc: cudaMalloc `bytes` (zero-filled) on the current device and return its IPC handle (64 bytes) for the peers.
+ * mc_p2p_open / close: map / unmap a peer's window in this process.  mc_p2p_free: release an own window.
+ * mc_p2p_bump: on `stream`, *epoch += 1 (and *own_flag = *epoch when given): starts a new exchange round.
+ * mc_p2p_push: on `stream`, for every destination i: copy `bytes` from src to dst_ptrs[i], then copy *epoch (4 bytes) to
+ *              flag_ptrs[i] — a peer that observes the flag observes the data. bytes == 0: flags only.
+ * mc_p2p_wait: on `stream`, a one-block kernel that returns once flags[0..n) have all reached *epoch. */
+int32_t mc_p2p_alloc(int64_t bytes, void** ptr_out, void* handle_out);
+int32_t mc_p2p_open(const void* handle, void** ptr_out);
+int32_t mc_p2p_close(void* ptr);
+int32_t mc_p2p_free(void* ptr);
+int32_t mc_p2p_bump(uint32_t* epoch, uint32_t* own_flag_or_null, void* stream);
+int32_t mc_p2p_push(const void* src, void* const* dst_ptrs, void* const* flag_ptrs, int32_t n_dst, int64_t bytes, const uint32_t* epoch,
+                    void* stream);
+int32_t mc_p2p_wait(const uint32_t* flags, int32_t n, const uint32_t* epoch, void* stream);
 
 /* Small fp32 linear for the time-embedding path (autocast-disabled region, magcache_generate.py:249-254):
  * y[m, n] = act(sum_k x[m,k] * W[n,k] + b[n]), M <= 8. act: 0 none, 1 SiLU applied to the INPUT x first (time_projection),

@@ -85,7 +85,14 @@ SIGNATURES = {
     "mc_attn_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
                     c_void_p, c_int64, c_void_p],
     "mc_attn_fwd_ex": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float,
-                       c_void_p, c_int64, c_int32, c_void_p, c_uint32, c_int32, c_void_p],
+                       c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p],
+    "mc_p2p_alloc": [c_int64, POINTER(c_void_p), c_void_p],
+    "mc_p2p_open": [c_void_p, POINTER(c_void_p)],
+    "mc_p2p_close": [c_void_p],
+    "mc_p2p_free": [c_void_p],
+    "mc_p2p_bump": [c_void_p, c_void_p, c_void_p],
+    "mc_p2p_push": [c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int32, c_int64, c_void_p, c_void_p],
+    "mc_p2p_wait": [c_void_p, c_int32, c_void_p, c_void_p],
     "mc_linear_f32_small": [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p],
     "mc_head_workspace_bytes": [c_int32, POINTER(c_int64)],
     "mc_head_unpatchify": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,

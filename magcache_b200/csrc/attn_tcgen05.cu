@@ -49,7 +49,7 @@ struct AttnParams {
   // (rows [s*seg_rows, (s+1)*seg_rows)) is loaded, seg_flags[s] must have reached seg_epoch (written by the peer copy).
   int tile_rot;
   const uint32_t* seg_flags;
-  uint32_t seg_epoch;
+  const uint32_t* seg_epoch;  // device memory: the epoch the flags must have reached (read at run time, so graph replays work)
   int seg_rows;
 };
 
@@ -87,6 +87,7 @@ __device__ __noinline__ void mask_padding_columns(uint32_t tmem_row, int valid, 
 // tile loads in the generic proxy, the proxy fence carries that order over to the async proxy the TMA reads through.
 __device__ __forceinline__ void wait_segments(const AttnParams& p, int row0, int rows) {
   if (p.seg_flags == nullptr) return;
+  const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(p.seg_epoch);
   const int last = min(row0 + rows, p.Lk) - 1;
   const int s0 = row0 / p.seg_rows, s1 = last / p.seg_rows;
   for (int s = s0; s <= s1; ++s) {
@@ -95,10 +96,10 @@ __device__ __forceinline__ void wait_segments(const AttnParams& p, int row0, int
     for (;;) {
       uint32_t v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      if (static_cast<int32_t>(v - p.seg_epoch) >= 0) break;
+      if (static_cast<int32_t>(v - want) >= 0) break;
       __nanosleep(100);
       if (clock64() - t0 > MC_MBAR_TIMEOUT_CYCLES) {
-        printf("attention: key segment %d never arrived (flag %u, epoch %u)\n", s, v, p.seg_epoch);
+        printf("attention: key segment %d never arrived (flag %u, epoch %u)\n", s, v, want);
         __trap();
       }
     }
@@ -729,11 +730,11 @@ static int env_int(const char* name, int lo, int hi, int dflt) {
 // One CTA = 256 (long kernel, 1 CTA/SM) or 128 (short kernel, 2 CTAs/SM) query rows of one head. With fewer than four waves of
 // CTAs the last, partially filled wave dominates (token-sharded runs: 4095 rows x 12 heads = 192 CTAs on 148 SMs), so the KV
 // range is split across blockIdx.z until the last wave is >= 92 % full, and the partial softmaxes are merged by a second kernel.
-static AttnPlan plan_attention(int Lq, int Lk, int heads) {
+static AttnPlan plan_attention(int Lq, int Lk, int heads, bool need_long = false) {
   AttnPlan pl;
   const int forced_splits = env_int("MC_ATTN_SPLITS", 1, 16, 0);  // MC_ATTN_SPLITS=n forces n splits (1 = never split)
   const int kernel_sel = env_int("MC_ATTN_KERNEL", 0, 2, 0);  // 0 = by Lk, 1 = short, 2 = long (tests / A-B timing)
-  pl.long_kernel = kernel_sel == 2 || (kernel_sel == 0 && Lk >= kLongMinLk);
+  pl.long_kernel = need_long || kernel_sel == 2 || (kernel_sel == 0 && Lk >= kLongMinLk);  // rotated / flag-gated key order: long kernel only
   const int rows_per_cta = pl.long_kernel ? 2 * lk::kBQ : sk::kBQ;
   pl.kv_tile = pl.long_kernel ? lk::kBKV : sk::kBKV;
   pl.q_blocks = (Lq + rows_per_cta - 1) / rows_per_cta;
@@ -766,13 +767,15 @@ static AttnPlan plan_attention(int Lq, int Lk, int heads) {
 
 extern "C" int32_t mc_attn_workspace_bytes(int32_t Lq, int32_t Lk, int32_t heads, int64_t* bytes_out) {
   MC_CHECK_ARG(bytes_out != nullptr && Lq >= 1 && Lk >= 1 && heads >= 1, "mc_attn_workspace_bytes: bad arguments");
-  *bytes_out = static_cast<int64_t>(mc::plan_attention(Lq, Lk, heads).ws_bytes);
+  // the larger of the two decompositions the launcher may pick (the rotated / flag-gated form always takes the long kernel)
+  const size_t a = mc::plan_attention(Lq, Lk, heads, false).ws_bytes, b = mc::plan_attention(Lq, Lk, heads, true).ws_bytes;
+  *bytes_out = static_cast<int64_t>(a > b ? a : b);
   return MC_OK;
 }
 
 extern "C" int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                                   int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* workspace,
-                                  int64_t workspace_bytes, int32_t first_key_row, const uint32_t* seg_flags, uint32_t seg_epoch,
+                                  int64_t workspace_bytes, int32_t first_key_row, const uint32_t* seg_flags, const uint32_t* seg_epoch,
                                   int32_t seg_rows, void* stream) {
   MC_CHECK_ARG(q && k && v && out, "mc_attn_fwd: null pointer");
   MC_CHECK_ARG(Lq >= 1 && Lk >= 1 && heads >= 1, "mc_attn_fwd: Lq=%d Lk=%d heads=%d", Lq, Lk, heads);
@@ -781,10 +784,8 @@ extern "C" int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int
   MC_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "mc_attn_fwd: leading dimensions must be multiples of 8");
   MC_CHECK_ARG(mc::aligned16(q) && mc::aligned16(k) && mc::aligned16(v) && mc::aligned16(out), "mc_attn_fwd: pointers must be 16-byte aligned");
   MC_CHECK_ARG(first_key_row >= 0 && first_key_row < Lk, "mc_attn_fwd: first_key_row=%d outside [0, %d)", first_key_row, Lk);
-  MC_CHECK_ARG(seg_flags == nullptr || seg_rows >= 1, "mc_attn_fwd: seg_rows=%d", seg_rows);
-  const mc::AttnPlan pl = mc::plan_attention(Lq, Lk, heads);
-  MC_CHECK_ARG(pl.long_kernel || (first_key_row == 0 && seg_flags == nullptr),
-               "mc_attn_fwd: rotated / flag-gated key order needs the long-sequence kernel (Lk >= %d)", mc::kLongMinLk);
+  MC_CHECK_ARG(seg_flags == nullptr || (seg_rows >= 1 && seg_epoch != nullptr), "mc_attn_fwd: seg_rows=%d / null epoch", seg_rows);
+  const mc::AttnPlan pl = mc::plan_attention(Lq, Lk, heads, first_key_row != 0 || seg_flags != nullptr);
   if (pl.splits > 1) {
     MC_CHECK_ARG(workspace != nullptr && workspace_bytes >= static_cast<int64_t>(pl.ws_bytes) && (reinterpret_cast<uintptr_t>(workspace) & 31u) == 0,
                  "mc_attn_fwd: split-KV needs a 32-byte aligned workspace of %lld bytes (mc_attn_workspace_bytes), got %lld",
@@ -851,5 +852,5 @@ extern "C" int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int
 extern "C" int32_t mc_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                                int64_t ldo, int32_t Lq, int32_t Lk, int32_t heads, float scale, void* workspace,
                                int64_t workspace_bytes, void* stream) {
-  return mc_attn_fwd_ex(q, ldq, k, ldk, v, ldv, out, ldo, Lq, Lk, heads, scale, workspace, workspace_bytes, 0, nullptr, 0, 0, stream);
+  return mc_attn_fwd_ex(q, ldq, k, ldk, v, ldv, out, ldo, Lq, Lk, heads, scale, workspace, workspace_bytes, 0, nullptr, nullptr, 0, stream);
 }

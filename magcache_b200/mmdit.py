@@ -134,6 +134,8 @@ class MMDiTCore:
         if getattr(self, "world", 1) > 1:
             from .shard import TokenShard
             self.shard = TokenShard(self.rank, self.world, n_img, self.group)
+            if self.shard.pad:
+                raise NotImplementedError(f"magcache_b200: {n_img} image tokens over {self.world} ranks needs the pad rule, built for the Wan engines only")
             n_img = self.shard.n_local
         S = n_img + n_txt                      # rows this rank carries
         Sg = self.n_img_total + n_txt          # keys every query attends to

@@ -302,7 +302,7 @@ def _workspace(kind, device, nbytes):
     return buf
 
 
-def attention(q, k, v, heads, scale=None, out=None, tag=None, first_key_row=0, seg_flags=None, seg_epoch=0, seg_rows=0):
+def attention(q, k, v, heads, scale=None, out=None, tag=None, first_key_row=0, seg_flags=None, seg_epoch=None, seg_rows=0):
     """softmax(q k^T * scale) v per head (head_dim 128). q [Lq, H*128], k [Lk, H*128], v [Lk, H*128]: row-major bf16 views (row
     stride allowed — column slices of one fused q|k|v buffer). `first_key_row` / `seg_*`: token-sharded key order, see
     mc_attn_fwd_ex in include/magcache_b200.h."""
@@ -323,7 +323,8 @@ def attention(q, k, v, heads, scale=None, out=None, tag=None, first_key_row=0, s
         check(lib.mc_attn_fwd_ex(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
                                  out.stride(0), Lq, Lk, heads, float(scale), ws.data_ptr() if ws is not None else None,
                                  ws.numel() if ws is not None else 0, int(first_key_row),
-                                 seg_flags.data_ptr() if seg_flags is not None else None, int(seg_epoch) & 0xFFFFFFFF, int(seg_rows), _stream()))
+                                 seg_flags.data_ptr() if seg_flags is not None else None,
+                                 seg_epoch.data_ptr() if seg_epoch is not None else None, int(seg_rows), _stream()))
     _count(2 if need.value > 0 else 1)
     return out
 

@@ -221,6 +221,7 @@ def _calibrate(self, eng):
     else:
         residual_x = ops.residual_sub(xs, x0)
     self.residual_cache[slot] = residual_x.view(1, *x0.shape)
+    eng._slot = slot
     out = eng.head(xs, e, eng.grid)
     self.cnt += 1
     if self.cnt >= self.num_steps:

@@ -254,6 +254,8 @@ class WanEngine:
         env = os.environ.get("MC_GRAPHS")
         self.use_graphs = (shard_world > 1) if env is None else (env == "1")
         self._graphs = {}
+        self.xch = None  # K|V exchange of a token-sharded engine (shard.py)
+        self._slot = 0   # CFG slot of the forward in flight (selects the output window of a sharded engine)
         self.hit_sum_bf16 = False  # TeaCache comparator: the hit sum is rounded to bf16 before the head (wan_teacache.py:569/577)
 
     # ------------------------------------------------------------------------------------------ workspace
@@ -265,14 +267,16 @@ class WanEngine:
         self.npad = (n_total + 7) // 8 * 8
         bf = dict(dtype=torch.bfloat16, device=dev)
         if self.world > 1:
-            from .shard import TokenShard
+            from .shard import TokenShard, make_exchange
             self.shard = TokenShard(self.rank, self.world, n_total, self.group)
             n = self.shard.n_local
-            # local q and k | v projections; the k | v rows of every rank are gathered into kv_all (all tokens x [k | v])
+            # local q projection; the k | v rows are written straight into this rank's segment of the gathered buffers, which the
+            # exchange (magcache_b200/shard.py) fills with every other rank's rows while the attention kernel already runs
             self.q_loc = torch.empty(n, D, **bf)
-            self.kv_loc = torch.empty(n, 2 * D, **bf)
-            self.kv_all = torch.empty(n_total, 2 * D, **bf)
-            self.out_full = None
+            if self.xch is not None:
+                self.xch.close()
+            self.xch = make_exchange(self.shard, 2 * D, (d.out_dim, self.grid[0], 2 * self.grid[1], 2 * self.grid[2]), dev)
+            self._xi = 0
         else:
             n = n_total
             self.qkv = torch.empty(n, 3 * D, **bf)
@@ -390,6 +394,7 @@ class WanEngine:
     # ------------------------------------------------------------------------------------------ one patched forward
     def _body(self, kind, slot):
         """prologue -> {hit: head(x0 + residual) | miss: block stack, residual = x - x0, head(x)} on the staged inputs."""
+        self._slot = slot
         x0, e, e0, ctx = self.prologue(need_ctx=(kind != "hit"))
         if kind == "hit":
             # `x + residual_x` (:295) is formed inside the head kernel; TeaCache's in-place bf16 `x += residual` rounds the sum first
@@ -484,15 +489,18 @@ class WanEngine:
             ops.rmsnorm_rope_(k, b["nk"], rope, d.head_dim, eps=d.eps)
             ops.attention(q, k, v, H, out=self.att, tag="attn_self")
         else:
-            from .shard import gather_rows
-            # k | v first so their all-gather (own stream) overlaps the q projection / RMSNorm / RoPE
-            ops.gemm(self.h, b["w_qkv"][D:], b["b_qkv"][D:], E.MC_EPI_BIAS_BF16, out=self.kv_loc, tag="gemm_qkv")
-            ops.rmsnorm_rope_(self.kv_loc[:, :D], b["nk"], rope, d.head_dim, eps=d.eps)
-            wkv = gather_rows(self.kv_loc, self.kv_all, sh.group, async_op=True)
+            # k | v first: their rows start travelling to the other ranks (copy engines, side stream) while this rank projects q;
+            # the attention kernel then begins on the local keys and picks the peers' segments up as they land
+            xi = self._xi
+            self._xi ^= 1
+            kv_own = self.xch.own_rows(xi)
+            ops.gemm(self.h, b["w_qkv"][D:], b["b_qkv"][D:], E.MC_EPI_BIAS_BF16, out=kv_own, tag="gemm_qkv")
+            ops.rmsnorm_rope_(kv_own[:, :D], b["nk"], rope, d.head_dim, eps=d.eps)
+            self.xch.begin(xi)
             ops.gemm(self.h, b["w_qkv"][:D], b["b_qkv"][:D], E.MC_EPI_BIAS_BF16, out=self.q_loc, tag="gemm_qkv")
             ops.rmsnorm_rope_(self.q_loc, b["nq"], rope, d.head_dim, eps=d.eps)
-            wkv.wait()
-            ops.attention(self.q_loc, self.kv_all[:, :D], self.kv_all[:, D:], H, out=self.att, tag="attn_self")
+            kv_all, kw = self.xch.keys_values(xi)
+            ops.attention(self.q_loc, kv_all[:, :D], kv_all[:, D:], H, out=self.att, tag="attn_self", **kw)
         ops.gemm(self.att, b["w_o"], b["b_o"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[2], tag="gemm_o")
         # --- cross attention (text)
         ops.ln_affine(xs, b["n3_w"], b["n3_b"], eps=d.eps, out=self.h)
@@ -520,10 +528,10 @@ class WanEngine:
         kw = dict(c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps, tag=tag, round_sum_to_bf16=round_sum_to_bf16)
         if self.shard is None:
             return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, **kw)
-        from .shard import sum_partial_outputs
-        out = torch.zeros(self.dims.out_dim, grid[0], 2 * grid[1], 2 * grid[2], dtype=torch.float32, device=self.device)
-        ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, row_offset=self.shard.start, out=out, **kw)
-        return sum_partial_outputs(out, self.shard.group)  # every rank ends up with the full noise prediction
+        self.xch.join()  # every push of this forward is ordered before its end (and inside a captured graph)
+        out, peer_outs = self.xch.head_output(self._slot)
+        ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, row_offset=self.shard.start, out=out, peer_outs=peer_outs, **kw)
+        return self.xch.finish_head(out, self._slot)  # every rank ends up with the full noise prediction
 
 
 class WanModelHandle:

@@ -121,7 +121,7 @@ def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6):
     return x
 
 
-def attention(q, k, v, heads, scale=None, out=None, tag=None, first_key_row=0, seg_flags=None, seg_epoch=0, seg_rows=0):
+def attention(q, k, v, heads, scale=None, out=None, tag=None, first_key_row=0, seg_flags=None, seg_epoch=None, seg_rows=0):
     Lq, W = q.shape
     Lk = k.shape[0]
     assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1 and v.shape == (Lk, W) and W == heads * 128

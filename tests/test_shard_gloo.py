@@ -24,8 +24,15 @@ def test_token_shard_partition():
     assert (s1.start, s1.stop, s1.n_local) == (7 * 4095, 32760, 4095)
     t = torch.arange(32760 * 2).view(32760, 2)
     assert torch.equal(torch.cat([TokenShard(r, 8, 32760).rows(t) for r in range(8)]), t)
-    with pytest.raises(ValueError):
-        TokenShard(0, 7, 32760 + 1)
+    # token counts that do not divide by the world size: the reference's pad rule (videosys/core/comm.py:373-381) — ceil(N / P) row
+    # slots per rank, the trailing slots of the last rank are pad
+    sh = [TokenShard(r, 8, 32761) for r in range(8)]
+    assert all(s.n_slots == 4096 and s.pad == 7 and s.n_padded == 32768 for s in sh)
+    assert [s.n_local for s in sh] == [4096] * 7 + [4096 - 7]
+    t = torch.arange(32761 * 2).view(32761, 2)
+    assert torch.equal(torch.cat([s.rows(t) for s in sh]), t)
+    with pytest.raises(ValueError):  # a rank without a single token
+        TokenShard(7, 8, 9)
 
 
 def test_rope_table_matches_oracle_rope_apply():
@@ -102,7 +109,7 @@ def test_sharded_self_attention_gather_and_reductions_world2():
             assert stats == [3.0, 4.0, 6.0, float(N)]
 
 
-def _engine_worker(rank, world, initfile, results, kind="t2v"):
+def _engine_worker(rank, world, initfile, results, kind="t2v", grid=GRID):
     """The REAL engine code path of a token-sharded forward (WanEngine with shard_world=2: local projections, async K/V row
     all-gathers, V transpose, attention over all keys, partial-output all-reduce in the head) with the kernels emulated on CPU
     (tests/emu_ops.py) and gloo as the collective backend."""
@@ -121,7 +128,8 @@ def _engine_worker(rank, world, initfile, results, kind="t2v"):
         extra_model = {"i2v": dict(in_dim=36, model_type="i2v", clip_dim=64), "vace": dict(model_type="vace", vace_in_dim=24)}.get(kind, {})
         model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=8, **extra_model).init_synthetic(3)
         g = torch.Generator().manual_seed(7)
-        shape = [GRID[0], 2 * GRID[1], 2 * GRID[2]]
+        shape = [grid[0], 2 * grid[1], 2 * grid[2]]
+        n_tok = grid[0] * grid[1] * grid[2]
         lat, ctx = torch.randn(16, *shape, generator=g), torch.randn(5, 64, generator=g)
         extra = {}
         if kind == "i2v":
@@ -139,9 +147,9 @@ def _engine_worker(rank, world, initfile, results, kind="t2v"):
             with torch.no_grad():
                 for i in range(4):  # miss, miss, hit, hit
                     if kind == "vace":
-                        seq.append(m.forward([lat], torch.tensor([500.0]), extra["vace_context"], [ctx], N)[0].clone())
+                        seq.append(m.forward([lat], torch.tensor([500.0]), extra["vace_context"], [ctx], n_tok)[0].clone())
                     else:
-                        seq.append(m.forward([lat], torch.tensor([500.0]), [ctx], N, **extra)[0].clone())
+                        seq.append(m.forward([lat], torch.tensor([500.0]), [ctx], n_tok, **extra)[0].clone())
             outs[name] = (seq, m._mc_engine, m.residual_cache)
         eng = outs["sharded"][1]
         sh = eng.shard
@@ -165,3 +173,17 @@ def test_sharded_engine_equals_single_engine_world2(kind):
             errs, cache_err, shape, rng = results[r]
             assert len(errs) == 4 and max(errs) < 2e-3, errs       # same arithmetic on row subsets (CPU matmul blocking differs)
             assert cache_err < 2e-3 and shape == (N // 2, 256) and rng == (r * N // 2, (r + 1) * N // 2)
+
+
+def test_sharded_engine_with_padded_token_count_world2():
+    """45 tokens over 2 ranks: 23 row slots each, rank 1 owns 22 tokens + 1 pad slot (the reference's pad rule,
+    videosys/core/comm.py:373-381); outputs and the sharded residual cache equal the single engine's."""
+    grid = (1, 5, 9)
+    with tempfile.TemporaryDirectory() as d:
+        mgr = mp.get_context("spawn").Manager()
+        results = mgr.dict()
+        mp.spawn(_engine_worker, args=(2, os.path.join(d, "init"), results, "t2v", grid), nprocs=2, join=True)
+        for r, (lo, hi) in enumerate(((0, 23), (23, 45))):
+            errs, cache_err, shape, rng = results[r]
+            assert len(errs) == 4 and max(errs) < 2e-3, errs
+            assert cache_err < 2e-3 and shape == (hi - lo, 256) and rng == (lo, hi)
