@@ -13,36 +13,45 @@
 // LayerNorm is shift invariant, so only mu changes to mu - p.
 //
 // HBM-bound: per row cols * 4 B (fp32 stream), or cols * (2 + 4) B on a cache hit (bf16 patch embedding + fp32 cached residual,
-// the sum never materialised), + 256 B out. Persistent CTAs, each owning a contiguous row range (balanced to one row), 16 converter
-// warps (4 threads per row, 256-bit loads, next chunk prefetched into registers), 1 TMA warp (W' chunks), 1 MMA warp.
+// the sum never materialised), + 256 B out. One CTA per SM, each owning a contiguous row range (balanced to one row). A TMA warp
+// streams the rows in [128 x 64] chunks into a shared-memory ring (96 KB in flight per SM, no registers tied up in loads) next to
+// the W' chunks; 16 converter warps (4 threads per row) read the staged values, update the statistics and write the hi / lo
+// operand tiles; 1 MMA warp. Warp-shuffle reductions merge the four threads of a row.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
 
 namespace mc {
 namespace hd {
-constexpr int kRows = 128, kKC = 64, kOut = 64, kStages = 3;
-constexpr int kATile = kRows * kKC * 2;  // 16 KB: one bf16 operand tile (hi or lo), 128-byte rows, 128-byte swizzle
-constexpr int kWTile = kOut * kKC * 2;   // 8 KB
-constexpr int kStageBytes = 2 * kATile + 2 * kWTile;  // 48 KB
-constexpr int kOffStats = kStages * kStageBytes;      // 144 KB
-constexpr int kOffBars = kOffStats + kRows * 8;
-constexpr int kSmem = kOffBars + 128;
+constexpr int kRows = 128, kKC = 64, kOut = 64;
+constexpr int kATile = kRows * kKC * 2;      // 16 KB: one bf16 operand tile (hi or lo), 128-byte rows, 128-byte swizzle
+constexpr int kWTile = kOut * kKC * 2;       // 8 KB
+constexpr int kOpStage = 2 * kATile + 2 * kWTile;  // 48 KB: A_hi, A_lo, W'_hi, W'_lo of one 64-column chunk
+constexpr int kOpStages = 2;
+constexpr int kRawF32 = kRows * kKC * 4;     // 32 KB: the fp32 chunk as two TMA boxes [128 rows x 32 fp32] (128-byte rows, swizzled)
+constexpr int kRawBf16 = kRows * kKC * 2;    // 16 KB: the bf16 chunk (cache hit: patch embedding), one box [128 x 64 bf16]
 constexpr int kConvWarps = 16;
 constexpr int kConvThreads = kConvWarps * 32;  // 512: 4 threads per row
 constexpr int kThreads = kConvThreads + 128;   // + one data-path warpgroup: TMA warp, MMA warp, two idle warps
 constexpr int kConvRegs = 104, kDataRegs = 32; // setmaxnreg: the data-path warpgroup hands its registers to the converters
 constexpr int kTmemCols = 64;
 constexpr int kMaxPeers = 8;
+template <bool HIT>
+struct Layout {
+  static constexpr int kRawStage = kRawF32 + (HIT ? kRawBf16 : 0);  // 48 KB on a hit, 32 KB otherwise
+  static constexpr int kRawStages = HIT ? 2 : 3;                    // 96 KB of loads in flight per SM either way
+  static constexpr int kOffRaw = kOpStages * kOpStage;              // 96 KB
+  static constexpr int kOffStats = kOffRaw + kRawStages * kRawStage;  // 192 KB
+  static constexpr int kOffBars = kOffStats + kRows * 8;
+  static constexpr int kSmem = kOffBars + 256;
+};
 }  // namespace hd
 
 struct HeadParams {
-  const void* x;       // [rows, cols] fp32, or bf16 when r != nullptr
-  const float* r;      // cached residual (cache-hit branch) or nullptr
-  int x_bf16, round_sum_bf16;
+  int round_sum_bf16;
   int64_t rows, row_offset;
   int cols, F, Hp, Wp;
-  int rows_per_cta;
+  int rows_per_cta, tail_rows;  // rows of the last 128-row tile of a CTA's range (its own TMA box height; 0: the range is a multiple of 128)
   const float* c1;     // [64] sum_k W'_ck
   const float* c0;     // [64] sum_k t_k W_ck + b_c
   float eps;
@@ -88,86 +97,68 @@ __global__ void __launch_bounds__(256) head_prep_kernel(const float* __restrict_
   }
 }
 
-// 16 consecutive elements of one row chunk -> fp32 (the cache-hit sum formed in fp32 exactly like torch's promoted add)
-template <bool HIT>
-struct ChunkRegs {
-  float a[16];      // fp32 stream, or the fp32 residual on a hit
-  uint32_t b[8];    // bf16 patch embedding on a hit (unused otherwise)
+// Host: 2-D fp32 tensor map [rows, cols], box [box_rows, 32 fp32] (128-byte rows), 128-byte swizzle, zero fill out of bounds.
+static int32_t make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return MC_ERR_CUDA;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(fp32) failed (CUresult %d): base=%p rows=%llu cols=%llu box_rows=%u", static_cast<int>(r), base,
+              static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols), box_rows);
+    return MC_ERR_CUDA;
+  }
+  return MC_OK;
+}
+
+// Tensor maps of one launch: the fp32 rows (residual stream, or the cached residual on a hit) and the bf16 rows (hit only), each with
+// a full-height (128-row) box and a tail box for the last tile of a CTA's row range — so no CTA fetches a row it does not own.
+struct HeadMaps {
+  CUtensorMap f32_full, f32_tail, bf16_full, bf16_tail, w_hi, w_lo;
 };
 
 template <bool HIT>
-__device__ __forceinline__ void load_chunk(const HeadParams& p, int64_t row, int k0, ChunkRegs<HIT>& c) {
-  if (HIT) {
-    const float* rp = p.r + row * p.cols + k0;
-    float t0[8], t1[8];
-    ptx::ld_nc_v8_f32(rp, t0);
-    ptx::ld_nc_v8_f32(rp + 8, t1);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) c.a[i] = t0[i], c.a[8 + i] = t1[i];
-    float tb[8];
-    ptx::ld_nc_v8_f32(reinterpret_cast<const float*>(static_cast<const __nv_bfloat16*>(p.x) + row * p.cols + k0), tb);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) c.b[i] = __float_as_uint(tb[i]);
-  } else {
-    const float* xp = static_cast<const float*>(p.x) + row * p.cols + k0;
-    float t0[8], t1[8];
-    ptx::ld_nc_v8_f32(xp, t0);
-    ptx::ld_nc_v8_f32(xp + 8, t1);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) c.a[i] = t0[i], c.a[8 + i] = t1[i];
-  }
-}
-
-template <bool HIT>
-__device__ __forceinline__ void chunk_values(const HeadParams& p, const ChunkRegs<HIT>& c, float (&v)[16]) {
-  if (HIT) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v[2 * i] = bf16_lo(c.b[i]) + c.a[2 * i];          // `x + residual_x`: bf16 -> fp32 promotion, fp32 add
-      v[2 * i + 1] = bf16_hi(c.b[i]) + c.a[2 * i + 1];
-    }
-    if (p.round_sum_bf16) {  // in-place `x += residual` on a bf16 tensor (TeaCache comparator, wan_teacache.py:569/577)
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = c.a[i];
-  }
-}
-
-template <bool HIT>
-__global__ void __launch_bounds__(hd::kThreads, 1)
-    head_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_constant__ CUtensorMap tmap_wlo, const HeadParams p) {
+__global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_constant__ HeadMaps maps, const HeadParams p) {
   using namespace hd;
+  using L = Layout<HIT>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  float2* stats = reinterpret_cast<float2*>(smem + kOffStats);  // (mean - pilot, rstd) per tile row
-  float* pilots = reinterpret_cast<float*>(stats + kRows);      // unused tail of the stats area is not needed: pilot folded into mean
-  (void)pilots;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint64_t* a_full = bars + 0;               // [kStages] 16 arrivals (one per converter warp)
-  uint64_t* a_empty = bars + kStages;        // [kStages] tcgen05.commit
-  uint64_t* w_full = bars + 2 * kStages;     // [kStages] TMA
-  uint64_t* acc_full = bars + 3 * kStages;   // accumulator of the current row tile complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+  float2* stats = reinterpret_cast<float2*>(smem + L::kOffStats);  // (mean - pilot, rstd) per tile row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
+  uint64_t* raw_full = bars + 0;    // [kRawStages] TMA
+  uint64_t* raw_empty = bars + 3;   // [kRawStages] 16 arrivals (one per converter warp): the raw chunk has been read into registers
+  uint64_t* a_full = bars + 6;      // [kOpStages] 16 arrivals: hi / lo operand tiles written
+  uint64_t* w_full = bars + 8;      // [kOpStages] TMA
+  uint64_t* op_empty = bars + 10;   // [kOpStages] tcgen05.commit: the MMAs that read A and W' of this stage have completed
+  uint64_t* acc_full = bars + 12;   // accumulator of the current row tile complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkc = p.cols / kKC;
   const int64_t cta_row0 = static_cast<int64_t>(blockIdx.x) * p.rows_per_cta;
   const int64_t cta_row1 = min(cta_row0 + p.rows_per_cta, p.rows);
   const int n_sub = cta_row1 > cta_row0 ? static_cast<int>((cta_row1 - cta_row0 + kRows - 1) / kRows) : 0;
+  const int n_sub_full = (p.rows_per_cta + kRows - 1) / kRows;  // tiles of a full range: the last of them uses the tail box
 
   if (threadIdx.x == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) {
       printf("head_tc_kernel: dynamic smem base not 1024-aligned\n");
       __trap();
     }
-    ptx::prefetch_tmap(&tmap_whi);
-    ptx::prefetch_tmap(&tmap_wlo);
-    for (int s = 0; s < kStages; ++s) {
+    ptx::prefetch_tmap(&maps.f32_full);
+    ptx::prefetch_tmap(&maps.w_hi);
+    ptx::prefetch_tmap(&maps.w_lo);
+    for (int s = 0; s < L::kRawStages; ++s) {
+      ptx::mbar_init(&raw_full[s], 1);
+      ptx::mbar_init(&raw_empty[s], kConvWarps);
+    }
+    for (int s = 0; s < kOpStages; ++s) {
       ptx::mbar_init(&a_full[s], kConvWarps);
-      ptx::mbar_init(&a_empty[s], 1);
       ptx::mbar_init(&w_full[s], 1);
+      ptx::mbar_init(&op_empty[s], 1);
     }
     ptx::mbar_init(acc_full, 1);
     ptx::fence_mbar_init();
@@ -181,35 +172,50 @@ __global__ void __launch_bounds__(hd::kThreads, 1)
   if (warp >= kConvWarps + 2) {
     ptx::setmaxnreg_dec<kDataRegs>();  // idle warps of the data-path warpgroup
   } else if (warp == kConvWarps) {
-    // ------------------------------------------------ TMA producer: W' hi / lo chunks ------------------------------------------
+    // ------------------------------------------------ TMA producer: raw row chunks and W' hi / lo chunks ------------------------
     ptx::setmaxnreg_dec<kDataRegs>();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int st = 0; st < n_sub; ++st)
+    int rs = 0, os = 0;
+    uint32_t rph = 0, oph = 0;
+    for (int st = 0; st < n_sub; ++st) {
+      const bool tail = p.tail_rows != 0 && st == n_sub_full - 1;
+      const int r0 = static_cast<int>(cta_row0) + st * kRows;
+      const uint32_t raw_bytes = static_cast<uint32_t>((tail ? p.tail_rows : kRows) * kKC * (HIT ? 6 : 4));
       for (int kc = 0; kc < nkc; ++kc) {
-        ptx::mbar_wait(&a_empty[stage], phase ^ 1);  // the MMAs that read this stage (A and W') have completed
+        ptx::mbar_wait(&raw_empty[rs], rph ^ 1);
         if (ptx::elect_one()) {
-          uint8_t* wdst = smem + stage * kStageBytes + 2 * kATile;
-          ptx::mbar_expect_tx(&w_full[stage], 2 * kWTile);
-          ptx::tma_load_2d(wdst, &tmap_whi, &w_full[stage], kc * kKC, 0);
-          ptx::tma_load_2d(wdst + kWTile, &tmap_wlo, &w_full[stage], kc * kKC, 0);
+          uint8_t* dst = smem + L::kOffRaw + rs * L::kRawStage;
+          ptx::mbar_expect_tx(&raw_full[rs], raw_bytes);
+          const CUtensorMap* mf = tail ? &maps.f32_tail : &maps.f32_full;
+          ptx::tma_load_2d(dst, mf, &raw_full[rs], kc * kKC, r0);
+          ptx::tma_load_2d(dst + kRawF32 / 2, mf, &raw_full[rs], kc * kKC + 32, r0);
+          if (HIT) ptx::tma_load_2d(dst + kRawF32, tail ? &maps.bf16_tail : &maps.bf16_full, &raw_full[rs], kc * kKC, r0);
         }
         __syncwarp();
-        if (++stage == kStages) stage = 0, phase ^= 1;
+        if (++rs == L::kRawStages) rs = 0, rph ^= 1;
+        ptx::mbar_wait(&op_empty[os], oph ^ 1);
+        if (ptx::elect_one()) {
+          uint8_t* wdst = smem + os * kOpStage + 2 * kATile;
+          ptx::mbar_expect_tx(&w_full[os], 2 * kWTile);
+          ptx::tma_load_2d(wdst, &maps.w_hi, &w_full[os], kc * kKC, 0);
+          ptx::tma_load_2d(wdst + kWTile, &maps.w_lo, &w_full[os], kc * kKC, 0);
+        }
+        __syncwarp();
+        if (++os == kOpStages) os = 0, oph ^= 1;
       }
+    }
   } else if (warp == kConvWarps + 1) {
     // ------------------------------------------------ MMA issuer (elected lane, uniform control flow) ---------------------------
     ptx::setmaxnreg_dec<kDataRegs>();
     constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, kOut);  // 128 x 64, both operands K-major
-    int stage = 0;
-    uint32_t phase = 0;
+    int os = 0;
+    uint32_t oph = 0;
     for (int st = 0; st < n_sub; ++st) {
       for (int kc = 0; kc < nkc; ++kc) {
-        ptx::mbar_wait(&a_full[stage], phase);
-        ptx::mbar_wait(&w_full[stage], phase);
+        ptx::mbar_wait(&a_full[os], oph);
+        ptx::mbar_wait(&w_full[os], oph);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t base = ptx::smem_u32(smem + stage * kStageBytes);
+          const uint32_t base = ptx::smem_u32(smem + os * kOpStage);
           const uint64_t a_hi = ptx::umma_desc_sw128_kmajor(base), a_lo = ptx::umma_desc_sw128_kmajor(base + kATile);
           const uint64_t w_hi = ptx::umma_desc_sw128_kmajor(base + 2 * kATile), w_lo = ptx::umma_desc_sw128_kmajor(base + 2 * kATile + kWTile);
 #pragma unroll
@@ -218,40 +224,61 @@ __global__ void __launch_bounds__(hd::kThreads, 1)
             ptx::umma_ss(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
             ptx::umma_ss(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
           }
-          ptx::umma_commit(&a_empty[stage]);
+          ptx::umma_commit(&op_empty[os]);
           // the next tile's first MMA overwrites the accumulator: it cannot be issued before a_full of its first chunk, which the
           // epilogue warps only arrive on after they have drained the accumulator (program order in those warps)
           if (kc == nkc - 1) ptx::umma_commit(acc_full);
         }
         __syncwarp();
-        if (++stage == kStages) stage = 0, phase ^= 1;
+        if (++os == kOpStages) os = 0, oph ^= 1;
       }
     }
   } else {
     // ------------------------------------------------ converter warps (+ epilogue) ---------------------------------------------
     ptx::setmaxnreg_inc<kConvRegs>();
     const int tid = threadIdx.x;
-    const int rt = tid >> 2, sub = tid & 3;  // tile row, 16-element slice of the 64-column chunk
+    const int rt = tid >> 2, sub = tid & 3;  // tile row; this thread owns columns [8 sub, 8 sub + 8) and [32 + 8 sub, 32 + 8 sub + 8) of a chunk
     const int sw = rt & 7;
     const uint32_t row_off = static_cast<uint32_t>((rt >> 3) * 1024 + sw * 128);
-    const uint32_t ch0 = static_cast<uint32_t>(((2 * sub) ^ sw) * 16), ch1 = static_cast<uint32_t>(((2 * sub + 1) ^ sw) * 16);  // 128-byte swizzle
-    int stage = 0;
-    uint32_t phase = 0;
+    // 16-byte chunk offsets inside a 128-byte swizzled row (chunk index XOR row % 8):
+    const uint32_t f0 = static_cast<uint32_t>(((2 * sub) ^ sw) * 16), f1 = static_cast<uint32_t>(((2 * sub + 1) ^ sw) * 16);  // fp32 box: 8 floats = 2 chunks
+    const uint32_t h0 = static_cast<uint32_t>((sub ^ sw) * 16), h1 = static_cast<uint32_t>(((4 + sub) ^ sw) * 16);            // bf16 rows: 8 elements = 1 chunk
+    int rs = 0, os = 0;
+    uint32_t rph = 0, oph = 0;
     const float inv_cols = 1.0f / static_cast<float>(p.cols);
     for (int st = 0; st < n_sub; ++st) {
       const int64_t row = cta_row0 + static_cast<int64_t>(st) * kRows + rt;
       const bool live = row < cta_row1;
       float pilot = 0.f, mean = 0.f, m2 = 0.f;  // running mean / M2 of the shifted values over the slices this thread has seen
-
-      // one 64-column chunk of this thread's row slice: statistics, hi / lo split, swizzled store, hand-over to the MMA warp
-      auto process = [&](const ChunkRegs<HIT>& c, int kc) {
+      for (int kc = 0; kc < nkc; ++kc) {
+        // ---- this thread's 16 values of the chunk, from the TMA-staged rows
         float v[16];
-        if (live) {
-          chunk_values<HIT>(p, c, v);
-        } else {
+        ptx::mbar_wait(&raw_full[rs], rph);
+        {
+          const uint8_t* raw = smem + L::kOffRaw + rs * L::kRawStage + row_off;
+          const float4 a0 = *reinterpret_cast<const float4*>(raw + f0), a1 = *reinterpret_cast<const float4*>(raw + f1);
+          const float4 b0 = *reinterpret_cast<const float4*>(raw + kRawF32 / 2 + f0), b1 = *reinterpret_cast<const float4*>(raw + kRawF32 / 2 + f1);
+          v[0] = a0.x, v[1] = a0.y, v[2] = a0.z, v[3] = a0.w, v[4] = a1.x, v[5] = a1.y, v[6] = a1.z, v[7] = a1.w;
+          v[8] = b0.x, v[9] = b0.y, v[10] = b0.z, v[11] = b0.w, v[12] = b1.x, v[13] = b1.y, v[14] = b1.z, v[15] = b1.w;
+          if (HIT) {
+            const uint4 x0 = *reinterpret_cast<const uint4*>(raw + kRawF32 + h0), x1 = *reinterpret_cast<const uint4*>(raw + kRawF32 + h1);
+            const uint32_t xb[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            for (int i = 0; i < 8; ++i) {  // `x + residual_x`: bf16 -> fp32 promotion, fp32 add (exactly torch's promoted add)
+              v[2 * i] = bf16_lo(xb[i]) + v[2 * i];
+              v[2 * i + 1] = bf16_hi(xb[i]) + v[2 * i + 1];
+            }
+            if (p.round_sum_bf16) {  // in-place `x += residual` on a bf16 tensor (TeaCache comparator, wan_teacache.py:569/577)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
+            }
+          }
         }
+        if (!live) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;  // rows past the range (tail box: not loaded; zero-filled or stale smem)
+        }
+        // ---- statistics
         if (kc == 0) {  // pilot = mean of the row's first 64 elements (4 adjacent lanes)
           float s = 0.f;
 #pragma unroll
@@ -266,6 +293,10 @@ __global__ void __launch_bounds__(hd::kThreads, 1)
           v[i] -= pilot;
           cs += v[i];
         }
+        // every staged value has been consumed by the sum above (the loads have completed, not merely issued): hand the stage back
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&raw_empty[rs]);
+        if (++rs == L::kRawStages) rs = 0, rph ^= 1;
         const float cm = cs * (1.0f / 16.0f);
         float cq = 0.f;
 #pragma unroll
@@ -279,10 +310,11 @@ __global__ void __launch_bounds__(hd::kThreads, 1)
         mean = fmaf(delta, 16.0f * rn, mean);
         m2 += fmaf(delta * delta, na * 16.0f * rn, cq);
 
-        ptx::mbar_wait(&a_empty[stage], phase ^ 1);
-        uint8_t* arow = smem + stage * kStageBytes + row_off;
+        // ---- hi / lo split into the swizzled operand tiles: columns [8 sub, +8) -> chunk sub, [32 + 8 sub, +8) -> chunk 4 + sub
+        ptx::mbar_wait(&op_empty[os], oph ^ 1);
+        uint8_t* arow = smem + os * kOpStage + row_off;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {  // 8 elements -> one 16-byte chunk of the hi tile and one of the lo tile
+        for (int hf = 0; hf < 2; ++hf) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -290,26 +322,14 @@ __global__ void __launch_bounds__(hd::kThreads, 1)
             hi[i] = pack_bf16x2(a, b);
             lo[i] = pack_bf16x2(a - bf16_lo(hi[i]), b - bf16_hi(hi[i]));
           }
-          const uint32_t ch = hf == 0 ? ch0 : ch1;
+          const uint32_t ch = hf == 0 ? h0 : h1;
           *reinterpret_cast<uint4*>(arow + ch) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(arow + kATile + ch) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a_full[stage]);
-        if (++stage == kStages) stage = 0, phase ^= 1;
-      };
-
-      // two register buffers in ping-pong: the loads of chunk kc+1 are in flight while chunk kc is converted
-      ChunkRegs<HIT> bufa, bufb;
-      if (live) load_chunk<HIT>(p, row, sub * 16, bufa);
-      for (int kc = 0; kc < nkc; kc += 2) {
-        if (live && kc + 1 < nkc) load_chunk<HIT>(p, row, (kc + 1) * kKC + sub * 16, bufb);
-        process(bufa, kc);
-        if (kc + 1 < nkc) {
-          if (live && kc + 2 < nkc) load_chunk<HIT>(p, row, (kc + 2) * kKC + sub * 16, bufa);
-          process(bufb, kc + 1);
-        }
+        if (lane == 0) ptx::mbar_arrive(&a_full[os]);
+        if (++os == kOpStages) os = 0, oph ^= 1;
       }
       // row statistics: merge the four slices of the row (Chan again, equal counts), publish (mean_shifted, rstd)
 #pragma unroll
@@ -400,33 +420,47 @@ int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_
   head_prep_kernel<<<hd::kOut, 256, 0, s>>>(head_mod, e, Wt, b, cols, w_hi, w_lo, c1, c0);
   MC_CHECK_LAUNCH("head_prep_kernel launch");
 
-  CUtensorMap thi, tlo;
-  int32_t rc = make_tmap_bf16_2d(&thi, w_hi, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
-  if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tlo, w_lo, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
-  if (rc) return rc;
   HeadParams p{};
-  p.x = x, p.r = r_or_null, p.x_bf16 = x_dtype == MC_BF16, p.round_sum_bf16 = (flags & 1) != 0;
+  p.round_sum_bf16 = (flags & 1) != 0;
   p.rows = rows, p.row_offset = row_offset, p.cols = cols, p.F = F, p.Hp = Hp, p.Wp = Wp;
   const int sms = num_sms();
-  p.rows_per_cta = static_cast<int>((rows + sms - 1) / sms);
+  p.rows_per_cta = static_cast<int>((rows + sms - 1) / sms);  // contiguous row range per CTA: HBM bytes balanced to one row
   if (p.rows_per_cta < 16) p.rows_per_cta = 16;
+  p.tail_rows = p.rows_per_cta % hd::kRows;
   p.c1 = c1, p.c0 = c0, p.eps = eps;
   for (int i = 0; i < n_out; ++i) {
     MC_CHECK_ARG(outs[i] != nullptr && (reinterpret_cast<uintptr_t>(outs[i]) & 7u) == 0, "mc_head_unpatchify: out[%d] null or not 8-byte aligned", i);
     p.out[i] = outs[i];
   }
   p.n_out = n_out;
+
+  HeadMaps maps{};
+  int32_t rc = make_tmap_bf16_2d(&maps.w_hi, w_hi, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&maps.w_lo, w_lo, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
+  if (rc) return rc;
+  const void* f32_rows = r_or_null ? static_cast<const void*>(r_or_null) : x;  // the fp32 operand: cached residual on a hit, else the stream
+  const uint32_t tail_box = p.tail_rows ? static_cast<uint32_t>(p.tail_rows) : hd::kRows;
+  rc = make_tmap_f32_2d(&maps.f32_full, f32_rows, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), hd::kRows);
+  if (rc) return rc;
+  rc = make_tmap_f32_2d(&maps.f32_tail, f32_rows, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), tail_box);
+  if (rc) return rc;
+  if (r_or_null) {
+    rc = make_tmap_bf16_2d(&maps.bf16_full, x, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kRows, hd::kKC);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&maps.bf16_tail, x, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), tail_box, hd::kKC);
+    if (rc) return rc;
+  }
   const int grid = static_cast<int>((rows + p.rows_per_cta - 1) / p.rows_per_cta);
   static PerDeviceOnce once_hit, once_stream;
   if (r_or_null) {
-    rc = set_max_smem_once(head_tc_kernel<true>, hd::kSmem, once_hit, "cudaFuncSetAttribute(head smem)");
+    rc = set_max_smem_once(head_tc_kernel<true>, hd::Layout<true>::kSmem, once_hit, "cudaFuncSetAttribute(head smem)");
     if (rc) return rc;
-    head_tc_kernel<true><<<grid, hd::kThreads, hd::kSmem, s>>>(thi, tlo, p);
+    head_tc_kernel<true><<<grid, hd::kThreads, hd::Layout<true>::kSmem, s>>>(maps, p);
   } else {
-    rc = set_max_smem_once(head_tc_kernel<false>, hd::kSmem, once_stream, "cudaFuncSetAttribute(head smem)");
+    rc = set_max_smem_once(head_tc_kernel<false>, hd::Layout<false>::kSmem, once_stream, "cudaFuncSetAttribute(head smem)");
     if (rc) return rc;
-    head_tc_kernel<false><<<grid, hd::kThreads, hd::kSmem, s>>>(thi, tlo, p);
+    head_tc_kernel<false><<<grid, hd::kThreads, hd::Layout<false>::kSmem, s>>>(maps, p);
   }
   MC_CHECK_LAUNCH("head_tc_kernel launch");
   return MC_OK;
