@@ -213,6 +213,10 @@ int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t col
  * cos_sin: fp32 [rows, head_dim] interleaved (cos, sin) per complex pair, i.e. [rows, head_dim/2, 2]; row = token. */
 int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, const float* w, float eps,
                         const float* cos_sin, int32_t head_dim, void* stream);
+/* the same over `segs` adjacent column blocks of `cols` columns per row (q | k of the fused q|k|v projection in ONE launch):
+ * x [rows, >= segs*cols] with row pitch ld, w [segs, cols]; RoPE (when cos_sin != NULL) is applied to every block. */
+int32_t mc_rmsnorm_rope_segs(void* x_bf16, int64_t ld, int64_t rows, int32_t segs, int32_t cols, const float* w, float eps,
+                             const float* cos_sin, int32_t head_dim, void* stream);
 
 /* MMDiT (FLUX) attention front end [EXT diffusers FluxAttnProcessor2_0, called from MagCache4FLUX/magcache_flux.py:361-366, :413-418]:
  * per-HEAD RMSNorm (head_dim 128; y = bf16(bf16(x * rsqrt(mean x^2 + eps)) * w), w fp32 copies of the bf16 weights [128]) followed

@@ -161,6 +161,161 @@ __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(__nv_bfloat16* __rest
   }
 }
 
+// ---- warp-per-row forms of the two kernels above with the NEXT row's loads in flight while the current row is reduced and
+// stored (two register buffers in ping-pong). The plain forms keep one row per warp in flight and spend half their time
+// in the reduce / store phase: ~3.4 TB/s on 32760 x 1536; with 2 rows x 16 warps per SM in flight the loads never drain.
+// G = 8-element groups per lane (cols <= 256 G); instantiated for the widths the engines use. (fp32 rows of G >= 6 groups need
+// 2 x 48+ registers for the two buffers: one block of 8 warps per SM, 96 KB of loads in flight.)
+template <int G>
+__global__ void __launch_bounds__(256, (G >= 6 ? 1 : 2)) ln_modulate_pipe_kernel(const void* __restrict__ x, int x_bf16, int64_t rows, int cols, float eps,
+                                                                  int mode, const float* __restrict__ p0, const float* __restrict__ p1,
+                                                                  int scale_idx, int shift_idx, int round_ln, void* __restrict__ out,
+                                                                  int out_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int groups = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  const float* pa = (mode == 0) ? p0 + static_cast<int64_t>(scale_idx) * cols : p0;
+  const float* pb = (mode == 0) ? p0 + static_cast<int64_t>(shift_idx) * cols : p1;
+  const int64_t stride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  auto load = [&](int64_t row, float (&v)[G][8]) {
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int g = lane + i * 32;
+      if (g < groups) load_row_group(x, x_bf16, row * cols + g * 8, v[i]);
+    }
+  };
+  auto process = [&](int64_t row, float (&v)[G][8]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+      if (lane + i * 32 < groups) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+    const float mean = warp_sum(s) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+      if (lane + i * 32 < groups) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int g = lane + i * 32;
+      if (g < groups) {
+        const int c0 = g * 8;
+        float a[8], b[8], o[8];
+        load_param8(pa + c0, a);
+        load_param8(pb + c0, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = (v[i][j] - mean) * rstd;
+          if (round_ln) y = round_bf16(y);
+          const float aa = (mode == 0) ? 1.0f + a[j] : a[j];
+          o[j] = __fadd_rn(__fmul_rn(y, aa), b[j]);  // torch eager: separate mul and add, no FMA contraction
+        }
+        if (out_bf16) {
+          ptx::st_na_v4(static_cast<__nv_bfloat16*>(out) + row * cols + c0, pack_bf16x8(o));
+        } else {
+          ptx::st_na_v8_f32(static_cast<float*>(out) + row * cols + c0, o);
+        }
+      }
+    }
+  };
+  float va[G][8], vb[G][8];
+  int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row < rows) load(row, va);
+  for (; row < rows; row += 2 * stride) {
+    const int64_t r1 = row + stride, r2 = row + 2 * stride;
+    if (r1 < rows) load(r1, vb);
+    process(row, va);
+    if (r1 < rows) {
+      if (r2 < rows) load(r2, va);
+      process(r1, vb);
+    }
+  }
+}
+
+// In-place WanRMSNorm (+ RoPE) over `segs` adjacent column blocks of `cols` columns per token (q | k of the fused projection in
+// one launch: weight [segs, cols]); one warp per (token, block), the next one's loads in flight.
+template <int G>
+__global__ void __launch_bounds__(256, 2) rmsnorm_rope_pipe_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int64_t rows, int segs, int cols,
+                                                                   const float* __restrict__ w, float eps,
+                                                                   const float* __restrict__ cos_sin, int head_dim) {
+  const int lane = threadIdx.x & 31;
+  const int groups = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  const int64_t items = rows * segs;
+  const int64_t stride = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  auto load = [&](int64_t it, uint4 (&v)[G]) {
+    const int64_t row = it / segs;
+    const int seg = static_cast<int>(it - row * segs);
+    const __nv_bfloat16* px = x + row * ld + static_cast<int64_t>(seg) * cols;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int g = lane + i * 32;
+      if (g < groups) v[i] = *reinterpret_cast<const uint4*>(px + g * 8);  // coherent: updated in place below
+    }
+  };
+  auto process = [&](int64_t it, uint4 (&raw)[G]) {
+    const int64_t row = it / segs;
+    const int seg = static_cast<int>(it - row * segs);
+    __nv_bfloat16* px = x + row * ld + static_cast<int64_t>(seg) * cols;
+    const float* ws = w + static_cast<int64_t>(seg) * cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+      if (lane + i * 32 < groups) {
+        float f[8];
+        unpack_bf16x8(raw[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q = fmaf(f[j], f[j], q);
+      }
+    const float r = rsqrtf(warp_sum(q) * inv_n + eps);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int g = lane + i * 32;
+      if (g < groups) {
+        const int c0 = g * 8;
+        float f[8], wv[8], o[8];
+        unpack_bf16x8(raw[i], f);
+        load_param8(ws + c0, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = round_bf16(f[j] * r) * wv[j];  // _norm(x.float()).type_as(x) * weight
+        if (cos_sin != nullptr) {
+          const int d0 = c0 % head_dim;  // position inside the head; 8 elements = 4 complex pairs
+          float cs[8];
+          ptx::ld_nc_v8_f32(cos_sin + row * head_dim + d0, cs);
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const float re = o[2 * pp], im = o[2 * pp + 1], c = cs[2 * pp], sn = cs[2 * pp + 1];
+            o[2 * pp] = __fsub_rn(__fmul_rn(re, c), __fmul_rn(im, sn));
+            o[2 * pp + 1] = __fadd_rn(__fmul_rn(re, sn), __fmul_rn(im, c));
+          }
+        }
+        *reinterpret_cast<uint4*>(px + c0) = pack_bf16x8(o);
+      }
+    }
+  };
+  uint4 va[G], vb[G];
+  int64_t it = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (it < items) load(it, va);
+  for (; it < items; it += 2 * stride) {
+    const int64_t i1 = it + stride, i2 = it + 2 * stride;
+    if (i1 < items) load(i1, vb);
+    process(it, va);
+    if (i1 < items) {
+      if (i2 < items) load(i2, va);
+      process(i1, vb);
+    }
+  }
+}
+
 // ---- per-HEAD RMSNorm (head_dim 128, bf16 weight semantics) + RoPE, in place on bf16: the q / k normalisation of the MMDiT
 // attention (diffusers `RMSNorm(head_dim)` on [B, H, L, 128] followed by `apply_rotary_emb`, upstream of
 // MagCache4FLUX/magcache_flux.py:361-366). 16 threads per (token, head), 8 elements each.
@@ -332,6 +487,12 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
   }
 }
 
+// warp-per-row pipelined kernels: 2 blocks of 8 warps per SM, every warp walks rows with a stride of the total warp count
+static int pipe_grid(int64_t rows, int blocks_per_sm = 2) {
+  const int64_t want = (rows + 7) / 8, cap = static_cast<int64_t>(num_sms()) * blocks_per_sm;
+  return static_cast<int>(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
 static int grid_for(int64_t work_items, int per_block) {
   int64_t want = (work_items + per_block - 1) / per_block;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
@@ -371,17 +532,33 @@ int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t col
   mc::ln_modulate_kernel<TPR><<<mc::grid_for(rows, 256 / TPR), 256, 0, s>>>(x, x_dtype == MC_BF16, rows, cols, eps, mode,       \
                                                                             p0, p1, scale_idx, shift_idx,                      \
                                                                             round_ln_to_bf16, out, out_dtype == MC_BF16)
-  if (groups <= 32 * mc::kMaxG) MC_LN(32);
+#define MC_LNP(G)                                                                                                              \
+  mc::ln_modulate_pipe_kernel<G><<<mc::pipe_grid(rows, (G) >= 6 ? 1 : 2), 256, 0, s>>>(x, x_dtype == MC_BF16, rows, cols, eps, mode, p0, p1,      \
+                                                                     scale_idx, shift_idx, round_ln_to_bf16, out, out_dtype == MC_BF16)
+  if (groups <= 32 * 2) MC_LNP(2);
+  else if (groups <= 32 * 4) MC_LNP(4);
+  else if (groups <= 32 * 6) MC_LNP(6);
+  else if (groups <= 32 * mc::kMaxG) MC_LNP(8);
   else MC_LN(128);
+#undef MC_LNP
 #undef MC_LN
   MC_CHECK_LAUNCH("ln_modulate_kernel launch");
   return MC_OK;
 }
 
+int32_t mc_rmsnorm_rope_segs(void* x_bf16, int64_t ld, int64_t rows, int32_t segs, int32_t cols, const float* w, float eps, const float* cos_sin,
+                             int32_t head_dim, void* stream);
+
 int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, const float* w, float eps, const float* cos_sin,
                         int32_t head_dim, void* stream) {
+  return mc_rmsnorm_rope_segs(x_bf16, ld, rows, 1, cols, w, eps, cos_sin, head_dim, stream);
+}
+
+int32_t mc_rmsnorm_rope_segs(void* x_bf16, int64_t ld, int64_t rows, int32_t segs, int32_t cols, const float* w, float eps, const float* cos_sin,
+                             int32_t head_dim, void* stream) {
   MC_CHECK_ARG(x_bf16 && w, "mc_rmsnorm_rope: null pointer");
-  MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0 && cols <= 128 * 8 * mc::kMaxG && ld >= cols && ld % 8 == 0,
+  MC_CHECK_ARG(segs >= 1 && segs <= 4, "mc_rmsnorm_rope: segs=%d outside [1, 4]", segs);
+  MC_CHECK_ARG(rows >= 1 && cols >= 8 && cols % 8 == 0 && cols <= 128 * 8 * mc::kMaxG && ld >= static_cast<int64_t>(segs) * cols && ld % 8 == 0,
                "mc_rmsnorm_rope: cols=%d ld=%lld unsupported", cols, static_cast<long long>(ld));
   MC_CHECK_ARG(mc::aligned16(x_bf16), "mc_rmsnorm_rope: x must be 16-byte aligned");
   MC_CHECK_ARG(mc::aligned16(w), "mc_rmsnorm_rope: weight must be 16-byte aligned");
@@ -390,10 +567,18 @@ int32_t mc_rmsnorm_rope(void* x_bf16, int64_t ld, int64_t rows, int32_t cols, co
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = cols / 8;
   __nv_bfloat16* xp = static_cast<__nv_bfloat16*>(x_bf16);
-#define MC_RMS(TPR) mc::rmsnorm_rope_kernel<TPR><<<mc::grid_for(rows, 256 / TPR), 256, 0, s>>>(xp, ld, rows, cols, w, eps, cos_sin, head_dim)
-  if (groups <= 32 * mc::kMaxG) MC_RMS(32);
-  else MC_RMS(128);
-#undef MC_RMS
+#define MC_RMSP(G) mc::rmsnorm_rope_pipe_kernel<G><<<mc::pipe_grid(rows * segs), 256, 0, s>>>(xp, ld, rows, segs, cols, w, eps, cos_sin, head_dim)
+  if (groups <= 32 * 2) MC_RMSP(2);
+  else if (groups <= 32 * 4) MC_RMSP(4);
+  else if (groups <= 32 * 6) MC_RMSP(6);
+  else if (groups <= 32 * mc::kMaxG) MC_RMSP(8);
+  else {
+    // wide rows (Wan-14B: 5120): four warps per row, one column block per launch
+    for (int sg = 0; sg < segs; ++sg)
+      mc::rmsnorm_rope_kernel<128><<<mc::grid_for(rows, 2), 256, 0, s>>>(xp + static_cast<int64_t>(sg) * cols, ld, rows, cols,
+                                                                        w + static_cast<int64_t>(sg) * cols, eps, cos_sin, head_dim);
+  }
+#undef MC_RMSP
   MC_CHECK_LAUNCH("rmsnorm_rope_kernel launch");
   return MC_OK;
 }

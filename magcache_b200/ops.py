@@ -227,6 +227,23 @@ def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6, tag=None):
     return x
 
 
+def rmsnorm_rope_segs_(x, weights, segs, cos_sin=None, head_dim=128, eps=1e-6, tag=None):
+    """`rmsnorm_rope_` over `segs` adjacent column blocks per row in ONE launch (q | k of the fused q|k|v projection): x bf16
+    [rows, >= segs*cols] view, weights fp32 [segs, cols]; RoPE applies to every block."""
+    _dev(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and weights.dtype == torch.float32 and weights.is_contiguous()
+    rows = x.shape[0]
+    cols = weights.shape[-1]
+    assert weights.numel() == segs * cols and x.shape[1] >= segs * cols
+    if cos_sin is not None:
+        assert cos_sin.dtype == torch.float32 and cos_sin.is_contiguous() and cos_sin.shape == (rows, head_dim)
+    with _Timed(tag, "rmsnorm_rope"):
+        check(lib.mc_rmsnorm_rope_segs(x.data_ptr(), x.stride(0), rows, segs, cols, weights.data_ptr(), eps,
+                                       cos_sin.data_ptr() if cos_sin is not None else None, head_dim, _stream()))
+    _count()
+    return x
+
+
 def rmsnorm_head_rope_(x, weight, heads, cos_sin=None, eps=1e-6, tag=None):
     """In-place per-head RMSNorm (head_dim 128) + optional RoPE on a bf16 [rows, heads*128] view (row stride allowed): the q / k
     normalisation of the MMDiT attention. weight fp32 [128]; cos_sin fp32 [rows, 128] (interleaved cos, sin)."""

@@ -136,7 +136,7 @@ class WanWeights:
             "w_qkv": _bf16(torch.cat([sa.q.weight, sa.k.weight, sa.v.weight], 0), device),   # one [3D, D] projection
             "b_qkv": _bias_autocast(torch.cat([sa.q.bias, sa.k.bias, sa.v.bias], 0), device),
             "w_o": _bf16(sa.o.weight, device), "b_o": _bias_autocast(sa.o.bias, device),
-            "nq": _f32(sa.norm_q.weight, device), "nk": _f32(sa.norm_k.weight, device),
+            "nqk": _f32(torch.stack([sa.norm_q.weight, sa.norm_k.weight]), device),   # [2, D]: q | k normalised in one launch
             "n3_w": _f32(blk.norm3.weight, device), "n3_b": _f32(blk.norm3.bias, device),
             "c_wq": _bf16(ca.q.weight, device), "c_bq": _bias_autocast(ca.q.bias, device),
             "c_wkv": _bf16(torch.cat([ca.k.weight, ca.v.weight], 0), device),                # text k|v: one [2D, D] projection
@@ -181,7 +181,7 @@ class WanWeights:
                 "mod": torch.randn(6, D, device=device, generator=g) / math.sqrt(D),
                 "w_qkv": torch.cat([xav(D, D), xav(D, D), xav(D, D)], 0).bfloat16(), "b_qkv": bias(3 * D),
                 "w_o": xav(D, D).bfloat16(), "b_o": bias(D),
-                "nq": 1 + 0.1 * torch.randn(D, device=device, generator=g), "nk": 1 + 0.1 * torch.randn(D, device=device, generator=g),
+                "nqk": 1 + 0.1 * torch.randn(2, D, device=device, generator=g),
                 "n3_w": 1 + 0.1 * torch.randn(D, device=device, generator=g), "n3_b": small(D),
                 "c_wq": xav(D, D).bfloat16(), "c_bq": bias(D), "c_wkv": torch.cat([xav(D, D), xav(D, D)], 0).bfloat16(), "c_bkv": bias(2 * D),
                 "c_wo": xav(D, D).bfloat16(), "c_bo": bias(D),
@@ -485,8 +485,7 @@ class WanEngine:
         if sh is None:
             q, k, v = self.qkv[:, :D], self.qkv[:, D:2 * D], self.qkv[:, 2 * D:]
             ops.gemm(self.h, b["w_qkv"], b["b_qkv"], E.MC_EPI_BIAS_BF16, out=self.qkv, tag="gemm_qkv")
-            ops.rmsnorm_rope_(q, b["nq"], rope, d.head_dim, eps=d.eps)
-            ops.rmsnorm_rope_(k, b["nk"], rope, d.head_dim, eps=d.eps)
+            ops.rmsnorm_rope_segs_(self.qkv, b["nqk"], 2, rope, d.head_dim, eps=d.eps)  # q and k column blocks, one launch
             ops.attention(q, k, v, H, out=self.att, tag="attn_self")
         else:
             # k | v first: their rows start travelling to the other ranks (copy engines, side stream) while this rank projects q;
@@ -495,10 +494,10 @@ class WanEngine:
             self._xi ^= 1
             kv_own = self.xch.own_rows(xi)
             ops.gemm(self.h, b["w_qkv"][D:], b["b_qkv"][D:], E.MC_EPI_BIAS_BF16, out=kv_own, tag="gemm_qkv")
-            ops.rmsnorm_rope_(kv_own[:, :D], b["nk"], rope, d.head_dim, eps=d.eps)
+            ops.rmsnorm_rope_(kv_own[:, :D], b["nqk"][1], rope, d.head_dim, eps=d.eps)
             self.xch.begin(xi)
             ops.gemm(self.h, b["w_qkv"][:D], b["b_qkv"][:D], E.MC_EPI_BIAS_BF16, out=self.q_loc, tag="gemm_qkv")
-            ops.rmsnorm_rope_(self.q_loc, b["nq"], rope, d.head_dim, eps=d.eps)
+            ops.rmsnorm_rope_(self.q_loc, b["nqk"][0], rope, d.head_dim, eps=d.eps)
             kv_all, kw = self.xch.keys_values(xi)
             ops.attention(self.q_loc, kv_all[:, :D], kv_all[:, D:], H, out=self.att, tag="attn_self", **kw)
         ops.gemm(self.att, b["w_o"], b["b_o"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[2], tag="gemm_o")

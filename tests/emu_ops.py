@@ -106,7 +106,17 @@ def rmsnorm_head_rope_(x, weight, heads, cos_sin=None, eps=1e-6):
     return x
 
 
-def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6):
+def rmsnorm_rope_segs_(x, weights, segs, cos_sin=None, head_dim=128, eps=1e-6, tag=None):
+    cols = weights.shape[-1]
+    assert weights.numel() == segs * cols and x.shape[1] >= segs * cols
+    for sg in range(segs):
+        rmsnorm_rope_(x[:, sg * cols:(sg + 1) * cols], weights.reshape(segs, cols)[sg], cos_sin, head_dim, eps)
+    global LAUNCHES
+    LAUNCHES -= segs - 1
+    return x
+
+
+def rmsnorm_rope_(x, weight, cos_sin=None, head_dim=128, eps=1e-6, tag=None):
     rows, cols = x.shape
     v = x.to(F32)
     o = _rb(v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps)) * weight

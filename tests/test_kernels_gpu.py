@@ -485,6 +485,24 @@ def test_gemm_strided_operands():
     assert torch.allclose(out, _gemm_ref(a, b).float(), rtol=1e-3, atol=1e-4)
 
 
+@pytest.mark.parametrize("rows,D", [(7, 256), (333, 384), (1000, 1536), (515, 2048)])
+def test_rmsnorm_rope_two_blocks_one_launch(rows, D):
+    """q | k of the fused q|k|v buffer normalised (+ RoPE) by ONE launch over two column blocks == two single-block launches, bit
+    for bit (same per-row arithmetic), on a row-strided view; the v block is untouched."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(rows)
+    qkv = torch.randn(rows, 3 * D, device=DEV, generator=g).bfloat16()
+    w = 1 + 0.1 * torch.randn(2, D, device=DEV, generator=g)
+    cs = torch.randn(rows, 128, device=DEV, generator=g)
+    a, b = qkv.clone(), qkv.clone()
+    ops.rmsnorm_rope_segs_(a, w, 2, cs, 128)
+    ops.rmsnorm_rope_(b[:, :D], w[0], cs, 128)
+    ops.rmsnorm_rope_(b[:, D:2 * D], w[1], cs, 128)
+    assert torch.equal(a, b)
+    assert torch.equal(a[:, 2 * D:], qkv[:, 2 * D:])
+    assert not torch.equal(a[:, :2 * D], qkv[:, :2 * D])
+
+
 # ------------------------------------------------------------------------------------------- tcgen05 attention
 def _attn_ref(q, k, v, heads):
     Lq, W = q.shape
