@@ -299,17 +299,21 @@ int32_t mc_linear_f32_small(const float* x, int32_t M, int32_t K, const float* W
  * head_mod: [2, cols] modulation parameter, e: [cols] time embedding, Wt: head.weight TRANSPOSED [cols, 64] fp32, b: [64];
  * out fp32 [C, F, 2Hp, 2Wp]: only the positions of the given tokens are written.
  * workspace: mc_head_workspace_bytes(cols) bytes of device scratch, 1024-byte aligned (the modulated, split weight of this call).
- * flags bit 0: round the hit sum to bf16 before the head (in-place `x += residual` on a bf16 tensor, wan_teacache.py:569/577).
- * _ex: the same rows are written into n_out <= 8 output tensors (token-sharded runs: every peer's copy, P2P stores). */
+ * flags bit 0: round the hit sum to bf16 before the head (in-place `x += residual` on a bf16 tensor, wan_teacache.py:569/577). */
 int32_t mc_head_workspace_bytes(int32_t cols, int64_t* bytes_out);
 int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
                            int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e,
                            const float* Wt, const float* b, float eps, float* out, void* workspace, int64_t workspace_bytes,
                            int32_t flags, void* stream);
+/* The two halves of mc_head_unpatchify, for callers that know the time embedding before the rows are ready (the engine prepares
+ * right after the time MLP): mc_head_prepare folds the modulation into the weight (W' = (1 + e1) * W as bf16 hi / lo, the two
+ * per-output constants) into `workspace`; mc_head_unpatchify_ex streams the rows against a prepared workspace and stores them into
+ * n_out <= 8 output tensors (token-sharded runs: every peer's copy, P2P stores). */
+int32_t mc_head_prepare(const float* head_mod, const float* e, const float* Wt, const float* b, int32_t cols, void* workspace,
+                        int64_t workspace_bytes, void* stream);
 int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
-                              int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e,
-                              const float* Wt, const float* b, float eps, float* const* outs, int32_t n_out, void* workspace,
-                              int64_t workspace_bytes, int32_t flags, void* stream);
+                              int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, float eps, float* const* outs, int32_t n_out,
+                              const void* prepared, int64_t prepared_bytes, int32_t flags, void* stream);
 
 /* bf16 transpose dst[c, r] = src[r, c]. */
 int32_t mc_transpose_bf16(const void* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldd, void* stream);

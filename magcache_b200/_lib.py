@@ -98,8 +98,9 @@ SIGNATURES = {
     "mc_head_workspace_bytes": [c_int32, POINTER(c_int64)],
     "mc_head_unpatchify": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
-    "mc_head_unpatchify_ex": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
-                              c_void_p, c_void_p, c_float, POINTER(c_void_p), c_int32, c_void_p, c_int64, c_int32, c_void_p],
+    "mc_head_prepare": [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p],
+    "mc_head_unpatchify_ex": [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
+                              POINTER(c_void_p), c_int32, c_void_p, c_int64, c_int32, c_void_p],
     "mc_transpose_bf16": [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p],
     "mc_time_sinusoid": [c_void_p, c_int32, c_int32, c_void_p, c_void_p],
     "mc_cast": [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],

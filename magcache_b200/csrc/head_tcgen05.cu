@@ -26,8 +26,9 @@ namespace hd {
 constexpr int kRows = 128, kKC = 64, kOut = 64;
 constexpr int kATile = kRows * kKC * 2;      // 16 KB: one bf16 operand tile (hi or lo), 128-byte rows, 128-byte swizzle
 constexpr int kWTile = kOut * kKC * 2;       // 8 KB
-constexpr int kOpStage = 2 * kATile + 2 * kWTile;  // 48 KB: A_hi, A_lo, W'_hi, W'_lo of one 64-column chunk
-constexpr int kOpStages = 2;
+constexpr int kATiles = 2 * kATile;          // 32 KB: A_hi | A_lo of one 64-column chunk (single-buffered: see Layout)
+constexpr int kWStage = 2 * kWTile;          // 16 KB: W'_hi | W'_lo of one chunk
+constexpr int kWStages = 2;
 constexpr int kRawF32 = kRows * kKC * 4;     // 32 KB: the fp32 chunk as two TMA boxes [128 rows x 32 fp32] (128-byte rows, swizzled)
 constexpr int kRawBf16 = kRows * kKC * 2;    // 16 KB: the bf16 chunk (cache hit: patch embedding), one box [128 x 64 bf16]
 constexpr int kConvWarps = 16;
@@ -36,12 +37,16 @@ constexpr int kThreads = kConvThreads + 128;   // + one data-path warpgroup: TMA
 constexpr int kConvRegs = 104, kDataRegs = 32; // setmaxnreg: the data-path warpgroup hands its registers to the converters
 constexpr int kTmemCols = 64;
 constexpr int kMaxPeers = 8;
+// Shared memory is spent on bytes in flight: the operand tiles the converters write are single-buffered (the MMAs of a chunk take
+// ~0.25 us, well inside the ~1.2 us a chunk's HBM bytes take), the W' chunks (L2 latency) double-buffered, and everything else is
+// the ring of TMA-staged rows: 3 x 48 KB on a hit, 4 x 32 KB otherwise.
 template <bool HIT>
 struct Layout {
-  static constexpr int kRawStage = kRawF32 + (HIT ? kRawBf16 : 0);  // 48 KB on a hit, 32 KB otherwise
-  static constexpr int kRawStages = HIT ? 2 : 3;                    // 96 KB of loads in flight per SM either way
-  static constexpr int kOffRaw = kOpStages * kOpStage;              // 96 KB
-  static constexpr int kOffStats = kOffRaw + kRawStages * kRawStage;  // 192 KB
+  static constexpr int kRawStage = kRawF32 + (HIT ? kRawBf16 : 0);
+  static constexpr int kRawStages = HIT ? 3 : 4;
+  static constexpr int kOffW = kATiles;                               // 32 KB
+  static constexpr int kOffRaw = kOffW + kWStages * kWStage;          // 64 KB
+  static constexpr int kOffStats = kOffRaw + kRawStages * kRawStage;  // 208 KB / 192 KB
   static constexpr int kOffBars = kOffStats + kRows * 8;
   static constexpr int kSmem = kOffBars + 256;
 };
@@ -128,13 +133,14 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem[];
   float2* stats = reinterpret_cast<float2*>(smem + L::kOffStats);  // (mean - pilot, rstd) per tile row
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
-  uint64_t* raw_full = bars + 0;    // [kRawStages] TMA
-  uint64_t* raw_empty = bars + 3;   // [kRawStages] 16 arrivals (one per converter warp): the raw chunk has been read into registers
-  uint64_t* a_full = bars + 6;      // [kOpStages] 16 arrivals: hi / lo operand tiles written
-  uint64_t* w_full = bars + 8;      // [kOpStages] TMA
-  uint64_t* op_empty = bars + 10;   // [kOpStages] tcgen05.commit: the MMAs that read A and W' of this stage have completed
-  uint64_t* acc_full = bars + 12;   // accumulator of the current row tile complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* raw_full = bars + 0;    // [kRawStages <= 4] TMA
+  uint64_t* raw_empty = bars + 4;   // [kRawStages] 16 arrivals (one per converter warp): the raw chunk has been consumed
+  uint64_t* a_full = bars + 8;      // 16 arrivals: hi / lo operand tiles written
+  uint64_t* a_empty = bars + 9;     // tcgen05.commit: the MMAs that read the operand tiles have completed
+  uint64_t* w_full = bars + 10;     // [kWStages] TMA
+  uint64_t* w_empty = bars + 12;    // [kWStages] tcgen05.commit
+  uint64_t* acc_full = bars + 14;   // accumulator of the current row tile complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkc = p.cols / kKC;
@@ -155,11 +161,12 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
       ptx::mbar_init(&raw_full[s], 1);
       ptx::mbar_init(&raw_empty[s], kConvWarps);
     }
-    for (int s = 0; s < kOpStages; ++s) {
-      ptx::mbar_init(&a_full[s], kConvWarps);
+    for (int s = 0; s < kWStages; ++s) {
       ptx::mbar_init(&w_full[s], 1);
-      ptx::mbar_init(&op_empty[s], 1);
+      ptx::mbar_init(&w_empty[s], 1);
     }
+    ptx::mbar_init(a_full, kConvWarps);
+    ptx::mbar_init(a_empty, 1);
     ptx::mbar_init(acc_full, 1);
     ptx::fence_mbar_init();
   }
@@ -174,8 +181,8 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
   } else if (warp == kConvWarps) {
     // ------------------------------------------------ TMA producer: raw row chunks and W' hi / lo chunks ------------------------
     ptx::setmaxnreg_dec<kDataRegs>();
-    int rs = 0, os = 0;
-    uint32_t rph = 0, oph = 0;
+    int rs = 0, ws = 0;
+    uint32_t rph = 0, wph = 0;
     for (int st = 0; st < n_sub; ++st) {
       const bool tail = p.tail_rows != 0 && st == n_sub_full - 1;
       const int r0 = static_cast<int>(cta_row0) + st * kRows;
@@ -192,45 +199,48 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
         }
         __syncwarp();
         if (++rs == L::kRawStages) rs = 0, rph ^= 1;
-        ptx::mbar_wait(&op_empty[os], oph ^ 1);
+        ptx::mbar_wait(&w_empty[ws], wph ^ 1);
         if (ptx::elect_one()) {
-          uint8_t* wdst = smem + os * kOpStage + 2 * kATile;
-          ptx::mbar_expect_tx(&w_full[os], 2 * kWTile);
-          ptx::tma_load_2d(wdst, &maps.w_hi, &w_full[os], kc * kKC, 0);
-          ptx::tma_load_2d(wdst + kWTile, &maps.w_lo, &w_full[os], kc * kKC, 0);
+          uint8_t* wdst = smem + L::kOffW + ws * kWStage;
+          ptx::mbar_expect_tx(&w_full[ws], kWStage);
+          ptx::tma_load_2d(wdst, &maps.w_hi, &w_full[ws], kc * kKC, 0);
+          ptx::tma_load_2d(wdst + kWTile, &maps.w_lo, &w_full[ws], kc * kKC, 0);
         }
         __syncwarp();
-        if (++os == kOpStages) os = 0, oph ^= 1;
+        if (++ws == kWStages) ws = 0, wph ^= 1;
       }
     }
   } else if (warp == kConvWarps + 1) {
     // ------------------------------------------------ MMA issuer (elected lane, uniform control flow) ---------------------------
     ptx::setmaxnreg_dec<kDataRegs>();
     constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, kOut);  // 128 x 64, both operands K-major
-    int os = 0;
-    uint32_t oph = 0;
+    int ws = 0;
+    uint32_t wph = 0, aph = 0;
+    const uint32_t a_base = ptx::smem_u32(smem);
+    const uint64_t a_hi = ptx::umma_desc_sw128_kmajor(a_base), a_lo = ptx::umma_desc_sw128_kmajor(a_base + kATile);
     for (int st = 0; st < n_sub; ++st) {
       for (int kc = 0; kc < nkc; ++kc) {
-        ptx::mbar_wait(&a_full[os], oph);
-        ptx::mbar_wait(&w_full[os], oph);
+        ptx::mbar_wait(a_full, aph);
+        ptx::mbar_wait(&w_full[ws], wph);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t base = ptx::smem_u32(smem + os * kOpStage);
-          const uint64_t a_hi = ptx::umma_desc_sw128_kmajor(base), a_lo = ptx::umma_desc_sw128_kmajor(base + kATile);
-          const uint64_t w_hi = ptx::umma_desc_sw128_kmajor(base + 2 * kATile), w_lo = ptx::umma_desc_sw128_kmajor(base + 2 * kATile + kWTile);
+          const uint32_t w_base = ptx::smem_u32(smem + L::kOffW + ws * kWStage);
+          const uint64_t w_hi = ptx::umma_desc_sw128_kmajor(w_base), w_lo = ptx::umma_desc_sw128_kmajor(w_base + kWTile);
 #pragma unroll
           for (int k = 0; k < kKC / 16; ++k) {
             ptx::umma_ss(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
             ptx::umma_ss(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
             ptx::umma_ss(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
           }
-          ptx::umma_commit(&op_empty[os]);
+          ptx::umma_commit(a_empty);
+          ptx::umma_commit(&w_empty[ws]);
           // the next tile's first MMA overwrites the accumulator: it cannot be issued before a_full of its first chunk, which the
           // epilogue warps only arrive on after they have drained the accumulator (program order in those warps)
           if (kc == nkc - 1) ptx::umma_commit(acc_full);
         }
         __syncwarp();
-        if (++os == kOpStages) os = 0, oph ^= 1;
+        aph ^= 1;
+        if (++ws == kWStages) ws = 0, wph ^= 1;
       }
     }
   } else {
@@ -243,8 +253,8 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
     // 16-byte chunk offsets inside a 128-byte swizzled row (chunk index XOR row % 8):
     const uint32_t f0 = static_cast<uint32_t>(((2 * sub) ^ sw) * 16), f1 = static_cast<uint32_t>(((2 * sub + 1) ^ sw) * 16);  // fp32 box: 8 floats = 2 chunks
     const uint32_t h0 = static_cast<uint32_t>((sub ^ sw) * 16), h1 = static_cast<uint32_t>(((4 + sub) ^ sw) * 16);            // bf16 rows: 8 elements = 1 chunk
-    int rs = 0, os = 0;
-    uint32_t rph = 0, oph = 0;
+    int rs = 0;
+    uint32_t rph = 0, aph = 0;
     const float inv_cols = 1.0f / static_cast<float>(p.cols);
     for (int st = 0; st < n_sub; ++st) {
       const int64_t row = cta_row0 + static_cast<int64_t>(st) * kRows + rt;
@@ -311,8 +321,8 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
         m2 += fmaf(delta * delta, na * 16.0f * rn, cq);
 
         // ---- hi / lo split into the swizzled operand tiles: columns [8 sub, +8) -> chunk sub, [32 + 8 sub, +8) -> chunk 4 + sub
-        ptx::mbar_wait(&op_empty[os], oph ^ 1);
-        uint8_t* arow = smem + os * kOpStage + row_off;
+        ptx::mbar_wait(a_empty, aph ^ 1);
+        uint8_t* arow = smem + row_off;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           uint32_t hi[4], lo[4];
@@ -328,8 +338,8 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a_full[os]);
-        if (++os == kOpStages) os = 0, oph ^= 1;
+        if (lane == 0) ptx::mbar_arrive(a_full);
+        aph ^= 1;
       }
       // row statistics: merge the four slices of the row (Chan again, equal counts), publish (mean_shifted, rstd)
 #pragma unroll
@@ -391,12 +401,38 @@ int32_t mc_head_workspace_bytes(int32_t cols, int64_t* bytes_out) {
   return MC_OK;
 }
 
-int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
-                              int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e, const float* Wt,
-                              const float* b, float eps, float* const* outs, int32_t n_out, void* workspace, int64_t workspace_bytes,
-                              int32_t flags, void* stream) {
+static int32_t head_workspace_split(void* workspace, int64_t workspace_bytes, int32_t cols, __nv_bfloat16** w_hi, __nv_bfloat16** w_lo, float** c1,
+                                    float** c0) {
+  int64_t need = 0;
+  mc_head_workspace_bytes(cols, &need);
+  MC_CHECK_ARG(workspace != nullptr && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 1023u) == 0,
+               "mc_head: workspace of %lld bytes, 1024-byte aligned, needed (mc_head_workspace_bytes)", static_cast<long long>(need));
+  *w_hi = static_cast<__nv_bfloat16*>(workspace);
+  *w_lo = *w_hi + static_cast<size_t>(64) * cols;
+  *c1 = reinterpret_cast<float*>(*w_lo + static_cast<size_t>(64) * cols);
+  *c0 = *c1 + 64;
+  return MC_OK;
+}
+
+int32_t mc_head_prepare(const float* head_mod, const float* e, const float* Wt, const float* b, int32_t cols, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
   using namespace mc;
-  MC_CHECK_ARG(x && head_mod && e && Wt && b && outs && workspace, "mc_head_unpatchify: null pointer");
+  MC_CHECK_ARG(head_mod && e && Wt && b, "mc_head_prepare: null pointer");
+  MC_CHECK_ARG(cols >= hd::kKC && cols % hd::kKC == 0, "mc_head_prepare: cols=%d must be a multiple of %d", cols, hd::kKC);
+  __nv_bfloat16 *w_hi, *w_lo;
+  float *c1, *c0;
+  const int32_t rc = head_workspace_split(workspace, workspace_bytes, cols, &w_hi, &w_lo, &c1, &c0);
+  if (rc) return rc;
+  head_prep_kernel<<<hd::kOut, 256, 0, static_cast<cudaStream_t>(stream)>>>(head_mod, e, Wt, b, cols, w_hi, w_lo, c1, c0);
+  MC_CHECK_LAUNCH("head_prep_kernel launch");
+  return MC_OK;
+}
+
+int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
+                              int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, float eps, float* const* outs, int32_t n_out,
+                              const void* prepared, int64_t prepared_bytes, int32_t flags, void* stream) {
+  using namespace mc;
+  MC_CHECK_ARG(x && outs && prepared, "mc_head_unpatchify: null pointer");
   MC_CHECK_ARG(n_out >= 1 && n_out <= hd::kMaxPeers, "mc_head_unpatchify: n_out=%d outside [1, %d]", n_out, hd::kMaxPeers);
   MC_CHECK_ARG(cols >= hd::kKC && cols % hd::kKC == 0, "mc_head_unpatchify: cols=%d must be a multiple of %d", cols, hd::kKC);
   MC_CHECK_ARG(C_out * 4 == hd::kOut, "mc_head_unpatchify: only patch (1,2,2) x C_out=16 (64 output features) is built, got C_out=%d", C_out);
@@ -406,19 +442,13 @@ int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_
                static_cast<long long>(row_offset + rows), F, Hp, Wp);
   MC_CHECK_ARG((x_dtype == MC_F32 && r_or_null == nullptr) || (x_dtype == MC_BF16 && r_or_null != nullptr),
                "mc_head_unpatchify: x must be fp32 (stream) or bf16 together with an fp32 residual (cache hit)");
-  MC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 31u) == 0 && (r_or_null == nullptr || (reinterpret_cast<uintptr_t>(r_or_null) & 31u) == 0),
-               "mc_head_unpatchify: x / r must be 32-byte aligned");
-  int64_t need = 0;
-  mc_head_workspace_bytes(cols, &need);
-  MC_CHECK_ARG(workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 1023u) == 0,
-               "mc_head_unpatchify: workspace of %lld bytes, 1024-byte aligned, needed (mc_head_workspace_bytes)", static_cast<long long>(need));
+  MC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (r_or_null == nullptr || (reinterpret_cast<uintptr_t>(r_or_null) & 15u) == 0),
+               "mc_head_unpatchify: x / r must be 16-byte aligned");
+  __nv_bfloat16 *w_hi, *w_lo;
+  float *c1, *c0;
+  int32_t rc = head_workspace_split(const_cast<void*>(prepared), prepared_bytes, cols, &w_hi, &w_lo, &c1, &c0);
+  if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  __nv_bfloat16* w_hi = static_cast<__nv_bfloat16*>(workspace);
-  __nv_bfloat16* w_lo = w_hi + static_cast<size_t>(64) * cols;
-  float* c1 = reinterpret_cast<float*>(w_lo + static_cast<size_t>(64) * cols);
-  float* c0 = c1 + 64;
-  head_prep_kernel<<<hd::kOut, 256, 0, s>>>(head_mod, e, Wt, b, cols, w_hi, w_lo, c1, c0);
-  MC_CHECK_LAUNCH("head_prep_kernel launch");
 
   HeadParams p{};
   p.round_sum_bf16 = (flags & 1) != 0;
@@ -435,7 +465,7 @@ int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_
   p.n_out = n_out;
 
   HeadMaps maps{};
-  int32_t rc = make_tmap_bf16_2d(&maps.w_hi, w_hi, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
+  rc = make_tmap_bf16_2d(&maps.w_hi, w_hi, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&maps.w_lo, w_lo, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
   if (rc) return rc;
@@ -469,9 +499,11 @@ int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_
 int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
                            int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, const float* head_mod, const float* e, const float* Wt,
                            const float* b, float eps, float* out, void* workspace, int64_t workspace_bytes, int32_t flags, void* stream) {
+  const int32_t rc = mc_head_prepare(head_mod, e, Wt, b, cols, workspace, workspace_bytes, stream);
+  if (rc) return rc;
   float* outs[1] = {out};
-  return mc_head_unpatchify_ex(x, x_dtype, r_or_null, rows, row_offset, cols, F, Hp, Wp, C_out, head_mod, e, Wt, b, eps, outs, 1, workspace,
-                               workspace_bytes, flags, stream);
+  return mc_head_unpatchify_ex(x, x_dtype, r_or_null, rows, row_offset, cols, F, Hp, Wp, C_out, eps, outs, 1, workspace, workspace_bytes, flags,
+                               stream);
 }
 
 }  // extern "C"

@@ -373,36 +373,58 @@ def time_sinusoid(t, dim, tag=None):
     return out
 
 
+class HeadPrep:
+    """The head's per-forward preparation (`mc_head_prepare`): the modulated weight split into bf16 hi / lo and the two per-output
+    constants, in a device workspace. Built right after the time embedding, consumed by `head_unpatchify(..., prep=...)`."""
+
+    def __init__(self, ptr, nbytes, cols, keep):
+        self.ptr, self.nbytes, self.cols, self._keep = ptr, nbytes, cols, keep
+
+
+def head_prepare(head_mod, e, w_t, b, tag=None):
+    """Fold (modulation + e) into head.weight for one forward: head_mod [2, cols] fp32, e [cols] fp32, w_t [cols, 64] fp32, b [64]."""
+    import ctypes
+    _dev(w_t)
+    cols = w_t.shape[0]
+    assert head_mod.shape[-2:] == (2, cols) and e.numel() == cols and w_t.shape == (cols, 64) and w_t.is_contiguous() and b.numel() == 64
+    need = ctypes.c_int64(0)
+    check(lib.mc_head_workspace_bytes(cols, ctypes.byref(need)))
+    ws = _workspace("head", w_t.device, need.value + 1024)
+    ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+    with _Timed(tag, "head_prepare"):
+        check(lib.mc_head_prepare(head_mod.data_ptr(), e.data_ptr(), w_t.data_ptr(), b.data_ptr(), cols, ptr, need.value, _stream()))
+    _count()
+    return HeadPrep(ptr, need.value, cols, ws)
+
+
 def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None, row_offset=0, out=None, round_sum_to_bf16=False,
-                    peer_outs=None):
+                    peer_outs=None, prep=None):
     """head(x, e) + unpatchify (MagCache4Wan2.1/magcache_generate.py:304-305) -> fp32 [c_out, F, 2*Hp, 2*Wp].
     x fp32 (the residual stream), or bf16 with `residual` (fp32): the cache-hit sum x + residual is formed on the fly (fused hit
-    path, :295). A token-sharded caller passes its contiguous token range (`row_offset`, x.shape[0] rows) and an `out` whose other
-    positions the peers fill; `peer_outs` (device pointers of the peers' outputs) makes the kernel store its rows there as well."""
+    path, :295). `prep`: a `head_prepare` result for this forward's time embedding (else it is computed here). A token-sharded
+    caller passes its contiguous token range (`row_offset`, x.shape[0] rows) and an `out` whose other positions the peers fill;
+    `peer_outs` (device pointers of the peers' outputs) makes the kernel store its rows there as well."""
     import ctypes
     _dev(x)
     F, Hp, Wp = grid
     rows, cols = x.shape
-    assert row_offset + rows <= F * Hp * Wp and x.is_contiguous() and w_t.shape == (cols, 4 * c_out) and w_t.is_contiguous()
-    assert head_mod.shape[-2:] == (2, cols) and e.numel() == cols
+    assert row_offset + rows <= F * Hp * Wp and x.is_contiguous()
     if residual is not None:
         assert x.dtype == torch.bfloat16 and residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == x.shape
     else:
         assert x.dtype == torch.float32, "head_unpatchify: fp32 stream, or bf16 patch embedding + fp32 residual"
+    if prep is None:
+        prep = head_prepare(head_mod, e, w_t, b)
+    assert prep.cols == cols
     if out is None:
         assert rows == F * Hp * Wp, "a partial token range needs a caller-provided output"
         out = torch.empty(c_out, F, 2 * Hp, 2 * Wp, dtype=torch.float32, device=x.device)
-    need = ctypes.c_int64(0)
-    check(lib.mc_head_workspace_bytes(cols, ctypes.byref(need)))
-    ws = _workspace("head", x.device, need.value + 1024)
-    ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
     ptrs = [out.data_ptr()] + [int(p) for p in (peer_outs or [])]
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
     with _Timed(tag, "head"):
         check(lib.mc_head_unpatchify_ex(x.data_ptr(), _dt(x), residual.data_ptr() if residual is not None else None, rows, row_offset, cols,
-                                        F, Hp, Wp, c_out, head_mod.data_ptr(), e.data_ptr(), w_t.data_ptr(), b.data_ptr(), eps,
-                                        arr, len(ptrs), ws_ptr, need.value, 1 if round_sum_to_bf16 else 0, _stream()))
-    _count(2)
+                                        F, Hp, Wp, c_out, eps, arr, len(ptrs), prep.ptr, prep.nbytes, 1 if round_sum_to_bf16 else 0, _stream()))
+    _count()
     return out
 
 

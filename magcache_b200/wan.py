@@ -378,6 +378,8 @@ class WanEngine:
             tok = self.shard.rows(tok)  # this rank embeds only its own tokens
         ops.gemm(tok, w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
         e, e0 = self.time_embedding()
+        # the head's modulated weight depends on the time embedding only: prepared here, off the tail of the forward
+        self._head_prep = ops.head_prepare(w.head_mod, e, w.head_wt, w.head_b)
         if not need_ctx:
             return self.x0, e, e0, None
         ops.gemm(self.ctx_in, w.text_w1, w.text_b1, E.MC_EPI_BIAS_GELU_BF16, out=self.ctx_h)
@@ -524,7 +526,7 @@ class WanEngine:
     def head(self, x, e, grid, residual=None, round_sum_to_bf16=False):
         w = self.w
         tag = "head_hit_fused" if residual is not None else "head"
-        kw = dict(c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps, tag=tag, round_sum_to_bf16=round_sum_to_bf16)
+        kw = dict(c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps, tag=tag, round_sum_to_bf16=round_sum_to_bf16, prep=self._head_prep)
         if self.shard is None:
             return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, **kw)
         self.xch.join()  # every push of this forward is ordered before its end (and inside a captured graph)

@@ -222,8 +222,13 @@ def linear_f32_small(x, w, b=None, act=0):
     return F.silu(y) if act == 2 else y
 
 
+def head_prepare(head_mod, e, w_t, b, tag=None):
+    _count()
+    return None
+
+
 def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None, row_offset=0, out=None, round_sum_to_bf16=False,
-                    peer_outs=None):
+                    peer_outs=None, prep=None):
     assert (x.dtype == F32 and residual is None) or (x.dtype == BF and residual is not None), "fp32 stream, or bf16 + fp32 residual"
     assert x.shape[1] % 64 == 0, "mc_head_unpatchify: cols % 64"
     xs = x.to(F32) + (residual if residual is not None else 0.0)
