@@ -26,9 +26,8 @@ namespace hd {
 constexpr int kRows = 128, kKC = 64, kOut = 64;
 constexpr int kATile = kRows * kKC * 2;      // 16 KB: one bf16 operand tile (hi or lo), 128-byte rows, 128-byte swizzle
 constexpr int kWTile = kOut * kKC * 2;       // 8 KB
-constexpr int kATiles = 2 * kATile;          // 32 KB: A_hi | A_lo of one 64-column chunk (single-buffered: see Layout)
-constexpr int kWStage = 2 * kWTile;          // 16 KB: W'_hi | W'_lo of one chunk
-constexpr int kWStages = 2;
+constexpr int kOpStage = 2 * kATile + 2 * kWTile;  // 48 KB: A_hi, A_lo, W'_hi, W'_lo of one 64-column chunk
+constexpr int kOpStages = 2;
 constexpr int kRawF32 = kRows * kKC * 4;     // 32 KB: the fp32 chunk as two TMA boxes [128 rows x 32 fp32] (128-byte rows, swizzled)
 constexpr int kRawBf16 = kRows * kKC * 2;    // 16 KB: the bf16 chunk (cache hit: patch embedding), one box [128 x 64 bf16]
 constexpr int kConvWarps = 16;
@@ -37,16 +36,12 @@ constexpr int kThreads = kConvThreads + 128;   // + one data-path warpgroup: TMA
 constexpr int kConvRegs = 104, kDataRegs = 32; // setmaxnreg: the data-path warpgroup hands its registers to the converters
 constexpr int kTmemCols = 64;
 constexpr int kMaxPeers = 8;
-// Shared memory is spent on bytes in flight: the operand tiles the converters write are single-buffered (the MMAs of a chunk take
-// ~0.25 us, well inside the ~1.2 us a chunk's HBM bytes take), the W' chunks (L2 latency) double-buffered, and everything else is
-// the ring of TMA-staged rows: 3 x 48 KB on a hit, 4 x 32 KB otherwise.
 template <bool HIT>
 struct Layout {
-  static constexpr int kRawStage = kRawF32 + (HIT ? kRawBf16 : 0);
-  static constexpr int kRawStages = HIT ? 3 : 4;
-  static constexpr int kOffW = kATiles;                               // 32 KB
-  static constexpr int kOffRaw = kOffW + kWStages * kWStage;          // 64 KB
-  static constexpr int kOffStats = kOffRaw + kRawStages * kRawStage;  // 208 KB / 192 KB
+  static constexpr int kRawStage = kRawF32 + (HIT ? kRawBf16 : 0);  // 48 KB on a hit, 32 KB otherwise
+  static constexpr int kRawStages = HIT ? 2 : 3;                    // 96 KB of loads in flight per SM either way
+  static constexpr int kOffRaw = kOpStages * kOpStage;              // 96 KB
+  static constexpr int kOffStats = kOffRaw + kRawStages * kRawStage;  // 192 KB
   static constexpr int kOffBars = kOffStats + kRows * 8;
   static constexpr int kSmem = kOffBars + 256;
 };
@@ -133,14 +128,13 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem[];
   float2* stats = reinterpret_cast<float2*>(smem + L::kOffStats);  // (mean - pilot, rstd) per tile row
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
-  uint64_t* raw_full = bars + 0;    // [kRawStages <= 4] TMA
-  uint64_t* raw_empty = bars + 4;   // [kRawStages] 16 arrivals (one per converter warp): the raw chunk has been consumed
-  uint64_t* a_full = bars + 8;      // 16 arrivals: hi / lo operand tiles written
-  uint64_t* a_empty = bars + 9;     // tcgen05.commit: the MMAs that read the operand tiles have completed
-  uint64_t* w_full = bars + 10;     // [kWStages] TMA
-  uint64_t* w_empty = bars + 12;    // [kWStages] tcgen05.commit
-  uint64_t* acc_full = bars + 14;   // accumulator of the current row tile complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* raw_full = bars + 0;    // [kRawStages] TMA
+  uint64_t* raw_empty = bars + 3;   // [kRawStages] 16 arrivals (one per converter warp): the raw chunk has been read into registers
+  uint64_t* a_full = bars + 6;      // [kOpStages] 16 arrivals: hi / lo operand tiles written
+  uint64_t* w_full = bars + 8;      // [kOpStages] TMA
+  uint64_t* op_empty = bars + 10;   // [kOpStages] tcgen05.commit: the MMAs that read A and W' of this stage have completed
+  uint64_t* acc_full = bars + 12;   // accumulator of the current row tile complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkc = p.cols / kKC;
@@ -161,12 +155,11 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
       ptx::mbar_init(&raw_full[s], 1);
       ptx::mbar_init(&raw_empty[s], kConvWarps);
     }
-    for (int s = 0; s < kWStages; ++s) {
+    for (int s = 0; s < kOpStages; ++s) {
+      ptx::mbar_init(&a_full[s], kConvWarps);
       ptx::mbar_init(&w_full[s], 1);
-      ptx::mbar_init(&w_empty[s], 1);
+      ptx::mbar_init(&op_empty[s], 1);
     }
-    ptx::mbar_init(a_full, kConvWarps);
-    ptx::mbar_init(a_empty, 1);
     ptx::mbar_init(acc_full, 1);
     ptx::fence_mbar_init();
   }
@@ -181,8 +174,8 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
   } else if (warp == kConvWarps) {
     // ------------------------------------------------ TMA producer: raw row chunks and W' hi / lo chunks ------------------------
     ptx::setmaxnreg_dec<kDataRegs>();
-    int rs = 0, ws = 0;
-    uint32_t rph = 0, wph = 0;
+    int rs = 0, os = 0;
+    uint32_t rph = 0, oph = 0;
     for (int st = 0; st < n_sub; ++st) {
       const bool tail = p.tail_rows != 0 && st == n_sub_full - 1;
       const int r0 = static_cast<int>(cta_row0) + st * kRows;
@@ -199,48 +192,45 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
         }
         __syncwarp();
         if (++rs == L::kRawStages) rs = 0, rph ^= 1;
-        ptx::mbar_wait(&w_empty[ws], wph ^ 1);
+        ptx::mbar_wait(&op_empty[os], oph ^ 1);
         if (ptx::elect_one()) {
-          uint8_t* wdst = smem + L::kOffW + ws * kWStage;
-          ptx::mbar_expect_tx(&w_full[ws], kWStage);
-          ptx::tma_load_2d(wdst, &maps.w_hi, &w_full[ws], kc * kKC, 0);
-          ptx::tma_load_2d(wdst + kWTile, &maps.w_lo, &w_full[ws], kc * kKC, 0);
+          uint8_t* wdst = smem + os * kOpStage + 2 * kATile;
+          ptx::mbar_expect_tx(&w_full[os], 2 * kWTile);
+          ptx::tma_load_2d(wdst, &maps.w_hi, &w_full[os], kc * kKC, 0);
+          ptx::tma_load_2d(wdst + kWTile, &maps.w_lo, &w_full[os], kc * kKC, 0);
         }
         __syncwarp();
-        if (++ws == kWStages) ws = 0, wph ^= 1;
+        if (++os == kOpStages) os = 0, oph ^= 1;
       }
     }
   } else if (warp == kConvWarps + 1) {
     // ------------------------------------------------ MMA issuer (elected lane, uniform control flow) ---------------------------
     ptx::setmaxnreg_dec<kDataRegs>();
     constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kRows, kOut);  // 128 x 64, both operands K-major
-    int ws = 0;
-    uint32_t wph = 0, aph = 0;
-    const uint32_t a_base = ptx::smem_u32(smem);
-    const uint64_t a_hi = ptx::umma_desc_sw128_kmajor(a_base), a_lo = ptx::umma_desc_sw128_kmajor(a_base + kATile);
+    int os = 0;
+    uint32_t oph = 0;
     for (int st = 0; st < n_sub; ++st) {
       for (int kc = 0; kc < nkc; ++kc) {
-        ptx::mbar_wait(a_full, aph);
-        ptx::mbar_wait(&w_full[ws], wph);
+        ptx::mbar_wait(&a_full[os], oph);
+        ptx::mbar_wait(&w_full[os], oph);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t w_base = ptx::smem_u32(smem + L::kOffW + ws * kWStage);
-          const uint64_t w_hi = ptx::umma_desc_sw128_kmajor(w_base), w_lo = ptx::umma_desc_sw128_kmajor(w_base + kWTile);
+          const uint32_t base = ptx::smem_u32(smem + os * kOpStage);
+          const uint64_t a_hi = ptx::umma_desc_sw128_kmajor(base), a_lo = ptx::umma_desc_sw128_kmajor(base + kATile);
+          const uint64_t w_hi = ptx::umma_desc_sw128_kmajor(base + 2 * kATile), w_lo = ptx::umma_desc_sw128_kmajor(base + 2 * kATile + kWTile);
 #pragma unroll
           for (int k = 0; k < kKC / 16; ++k) {
             ptx::umma_ss(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
             ptx::umma_ss(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
             ptx::umma_ss(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
           }
-          ptx::umma_commit(a_empty);
-          ptx::umma_commit(&w_empty[ws]);
+          ptx::umma_commit(&op_empty[os]);
           // the next tile's first MMA overwrites the accumulator: it cannot be issued before a_full of its first chunk, which the
           // epilogue warps only arrive on after they have drained the accumulator (program order in those warps)
           if (kc == nkc - 1) ptx::umma_commit(acc_full);
         }
         __syncwarp();
-        aph ^= 1;
-        if (++ws == kWStages) ws = 0, wph ^= 1;
+        if (++os == kOpStages) os = 0, oph ^= 1;
       }
     }
   } else {
@@ -253,8 +243,8 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
     // 16-byte chunk offsets inside a 128-byte swizzled row (chunk index XOR row % 8):
     const uint32_t f0 = static_cast<uint32_t>(((2 * sub) ^ sw) * 16), f1 = static_cast<uint32_t>(((2 * sub + 1) ^ sw) * 16);  // fp32 box: 8 floats = 2 chunks
     const uint32_t h0 = static_cast<uint32_t>((sub ^ sw) * 16), h1 = static_cast<uint32_t>(((4 + sub) ^ sw) * 16);            // bf16 rows: 8 elements = 1 chunk
-    int rs = 0;
-    uint32_t rph = 0, aph = 0;
+    int rs = 0, os = 0;
+    uint32_t rph = 0, oph = 0;
     const float inv_cols = 1.0f / static_cast<float>(p.cols);
     for (int st = 0; st < n_sub; ++st) {
       const int64_t row = cta_row0 + static_cast<int64_t>(st) * kRows + rt;
@@ -321,8 +311,8 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
         m2 += fmaf(delta * delta, na * 16.0f * rn, cq);
 
         // ---- hi / lo split into the swizzled operand tiles: columns [8 sub, +8) -> chunk sub, [32 + 8 sub, +8) -> chunk 4 + sub
-        ptx::mbar_wait(a_empty, aph ^ 1);
-        uint8_t* arow = smem + row_off;
+        ptx::mbar_wait(&op_empty[os], oph ^ 1);
+        uint8_t* arow = smem + os * kOpStage + row_off;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           uint32_t hi[4], lo[4];
@@ -338,8 +328,8 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(a_full);
-        aph ^= 1;
+        if (lane == 0) ptx::mbar_arrive(&a_full[os]);
+        if (++os == kOpStages) os = 0, oph ^= 1;
       }
       // row statistics: merge the four slices of the row (Chan again, equal counts), publish (mean_shifted, rstd)
 #pragma unroll
