@@ -478,6 +478,115 @@ def check_shard_parity(mc, model, weights, lat_d, ctx_d, t, rank, dev):
     return res
 
 
+def run_mmdit(args, rank, world):
+    """BASELINE configs[0] / configs[3] on the MMDiT engines (magcache_b200/mmdit.py): FLUX.1-dev 1024x1024 (4096 image + 512 text
+    tokens, 19 + 38 blocks, E024K5R01, 28 steps) and HunyuanVideo 720p x 129 frames (118 800 image + 256 text tokens, 20 + 40 blocks,
+    E024K6R02, 50 steps), synthetic device-side weights. One step = one patched-forward call (these pipelines use distilled guidance:
+    no CFG pair). Same JSON contract as the Wan workload; the roofline object is the joint-attention kernel."""
+    import torch
+
+    import magcache_b200 as mc
+    from magcache_b200 import mmdit, ops
+
+    if world != 1:
+        raise SystemExit("--workload flux / hunyuan720p: single GPU (token-sharded MMDiT runs are covered by tests/test_shard_gpu.py)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    flux = args.workload == "flux"
+    if flux:
+        total_steps, preset = 28, dict(thresh=0.24, K=5, retention_ratio=0.1)
+        model = mmdit.MMDiTHandle(mmdit.FluxEngine(mmdit.random_flux_weights(dev)))
+        mc.init_magcache_flux(model, total_steps, **preset)
+        n_img, n_txt, heads, layers = 4096, 512, 24, 19 + 38
+        hs_h = torch.randn(1, n_img, 64, generator=torch.Generator().manual_seed(0)).bfloat16().pin_memory()
+        enc_h = torch.randn(1, n_txt, 4096, generator=torch.Generator().manual_seed(1)).bfloat16().pin_memory()
+        hs, enc = hs_h.to(dev), enc_h.to(dev)
+        pooled = torch.randn(1, 768, device=dev, generator=g).bfloat16()
+        img_ids = torch.zeros(n_img, 3, device=dev)
+        img_ids[:, 1], img_ids[:, 2] = torch.arange(n_img, device=dev) // 64, torch.arange(n_img, device=dev) % 64
+        txt_ids = torch.zeros(n_txt, 3, device=dev)
+        gd = torch.tensor([3.5], device=dev)
+        ts = [torch.tensor([1.0 - i / total_steps], device=dev) for i in range(total_steps)]
+
+        def call(i, x, c):
+            return model(x, c, pooled, ts[i % total_steps], img_ids, txt_ids, gd, return_dict=False)[0]
+        workload = "FLUX.1-dev 1024x1024, 28 steps, MagCache E024K5R01 (BASELINE configs[0])"
+    else:
+        total_steps, preset = 50, dict(thresh=0.24, K=6, retention_ratio=0.2)
+        model = mmdit.MMDiTHandle(mmdit.HunyuanEngine(mmdit.random_hunyuan_weights(dev)))
+        mc.init_magcache_hunyuan(model, total_steps, **preset)
+        grid = (33, 45, 80)  # 129 frames -> 33 latent frames; 720 x 1280 -> 90 x 160 latent -> 45 x 80 patches
+        n_img, n_txt, heads, layers = grid[0] * grid[1] * grid[2], 256, 24, 20 + 40
+        hs_h = torch.randn(1, 16, grid[0], 2 * grid[1], 2 * grid[2], generator=torch.Generator().manual_seed(0)).bfloat16().pin_memory()
+        enc_h = torch.randn(1, n_txt, 4096, generator=torch.Generator().manual_seed(1)).bfloat16().pin_memory()
+        hs, enc = hs_h.to(dev), enc_h.to(dev)
+        mask = torch.zeros(1, n_txt, dtype=torch.long, device=dev)
+        mask[0, :48] = 1
+        pooled = torch.randn(1, 768, device=dev, generator=g).bfloat16()
+        ang = torch.rand(n_img, 64, device=dev, generator=g) * 6.28
+        cos, sin = ang.cos().repeat_interleave(2, dim=1), ang.sin().repeat_interleave(2, dim=1)
+        gd = torch.tensor([6000.0], device=dev)
+        ts = [torch.tensor([1000.0 * (1 - i / total_steps)], device=dev) for i in range(total_steps)]
+
+        def call(i, x, c):
+            return model(x, ts[i % total_steps], c, mask, pooled, cos, sin, gd, return_dict=False)
+        workload = "HunyuanVideo 720p x 129 frames, 50 steps, MagCache E024K6R02 (BASELINE configs[3])"
+    out_h = torch.empty_like(hs_h).pin_memory()
+    steps = args.steps
+
+    def timed(e2e, tags):
+        mc.reset_magcache(model)
+        for i in range(args.warmup):
+            call(i, hs, enc)
+        # warm the hit path too (first eligible call of the schedule) before the clock starts
+        model.cnt = total_steps // 2
+        call(total_steps // 2, hs, enc)
+        mc.reset_magcache(model)
+        ops.PROFILE = {} if tags else None
+        ops.PROFILE_TAGS = tags
+        n0 = ops.LAUNCHES
+        sampler = ClockSampler(0)
+        torch.cuda.synchronize()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            if e2e:
+                x, c = hs_h.to(dev, non_blocking=True), enc_h.to(dev, non_blocking=True)
+                o = call(i, x, c)
+                out_h.view(-1)[:o.numel()].copy_(o.reshape(-1), non_blocking=True)
+            else:
+                call(i, hs, enc)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        prof, ops.PROFILE, ops.PROFILE_TAGS = ops.PROFILE, None, None
+        return e0.elapsed_time(e1), ops.LAUNCHES - n0, clocks, prof
+
+    ms, launches, clocks, prof = timed(False, {"mmdit_attn"})
+    ms_e2e, _, _, _ = timed(True, None)
+    pk = peaks()
+    S = n_img + n_txt
+    attn_flops = 4.0 * S * S * heads * 128
+    kern = {t: {"launches": len(ev), "ms_avg": sum(a.elapsed_time(b) for a, b in ev) / len(ev), "ms_total": sum(a.elapsed_time(b) for a, b in ev)} for t, ev in (prof or {}).items()}
+    roof = None
+    if "mmdit_attn" in kern:
+        ach = attn_flops / (kern["mmdit_attn"]["ms_avg"] * 1e-3) / 1e12
+        roof = {"kernel": f"attn_long_kernel (joint attention, {S}x{S}x{heads} heads)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)", "share_of_step": kern["mmdit_attn"]["ms_total"] / ms,
+                "flops_per_launch": attn_flops, "measured": "CUDA events around every launch inside the timed region"}
+    line = {"metric": "denoising_steps_per_sec", "value": steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "image_tokens": n_img, "text_tokens": n_txt, "layers": layers, "parallelism": "single GPU",
+                       "schedule": f"the first {steps} calls of the {total_steps}-step schedule from cnt = 0"},
+            "sec_per_sample_if_linear": (ms * 1e-3) * total_steps / steps,
+            "e2e": {"value": steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": hs_h.numel() * 2 + enc_h.numel() * 2,
+                    "d2h_bytes_per_step": hs_h.numel() * 2, "ms_per_step": ms_e2e / steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern}
+    print(json.dumps(line), flush=True)
+
+
 def shutdown_distributed(model):
     """Leave cleanly and in bounded time: captured CUDA graphs hold NCCL work, and tearing the process group down under them
     can block forever — drop the graphs first, and never wait more than a few seconds for the communicator to go away."""
@@ -546,11 +655,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cache", action="store_true", help="time the non-cached DiT loop at identical shapes")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (debugging)")
-    ap.add_argument("--workload", default="wan1.3b", choices=["wan1.3b", "wan14b"], help="wan14b: BASELINE configs[4] model/shape (not the driver's metric)")
+    ap.add_argument("--workload", default="wan1.3b", choices=["wan1.3b", "wan14b", "flux", "hunyuan720p"],
+                    help="wan14b: BASELINE configs[4] model/shape; flux: configs[0] (FLUX.1-dev 1024x1024, 28 steps); hunyuan720p: configs[3] "
+                         "(720p x 129 frames, 50 steps) — none of these is the driver's metric")
     args = ap.parse_args()
     select_workload(args.workload)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.workload in ("flux", "hunyuan720p"):
+        run_mmdit(args, rank, world)
+        return
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return

@@ -62,6 +62,8 @@ int32_t mc_nearest_interp_cfg(const double* src, int32_t L_total, double* dst, i
 #define MC_CTRL_SIGNED_ERR 1     /* err += 1 - ratio (no abs): eval/magcache/experiments/opensora.py:301 */
 #define MC_CTRL_RESET_AT_ZERO 2  /* accumulators re-initialised whenever a call sees cnt == 0: MagCache4FramePack/magcache_demo_gradio.py:253-256 */
 #define MC_CTRL_RATIO_VETO 4     /* skip only while |1 - mag_ratios[.]| <= ratio_veto: magcache_demo_gradio.py:265 */
+#define MC_CTRL_WRAP_KEEPS_ACC 8 /* at cnt >= num_steps only the counter is reset, the accumulators carry over into the next sample:
+                                    MagCache4QwenImage/magcache_generate.py:243-244 (Wan2.1 :306-311, FLUX :432-436, ... reset all) */
 
 typedef struct mc_ctrl_config {
   int32_t num_steps;       /* forward calls per video: 2*sample_steps for CFG models (Wan :899), steps otherwise */

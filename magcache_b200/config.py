@@ -106,7 +106,8 @@ FAMILIES = {
     "wan2.2-i2v": dict(branches=2, cmp=_LT, retention_mode=_lib.MC_RETAIN_WAN22_I2V),
     "wan2.2-ti2v": dict(branches=2, cmp=_LT, retention_mode=_lib.MC_RETAIN_FLOOR),
     # MagCache4QwenImage/magcache_generate.py:205-219 (+ Edit): Wan2.1's controller, np.linspace interpolation (:14-21)
-    "qwen-image": dict(branches=2, cmp=_LT, retention_mode=_lib.MC_RETAIN_FLOOR),
+    # the wrap resets ONLY the counter (:243-244): the accumulators carry over into the next image of the same process
+    "qwen-image": dict(branches=2, cmp=_LT, retention_mode=_lib.MC_RETAIN_FLOOR, flags=_lib.MC_CTRL_WRAP_KEEPS_ACC),
     # MagCache4FLUX/magcache_flux.py:326-338 ; MagCache4FLUX_Kontext/magcache_flux_kontext.py:328-340 (same statements)
     "flux": dict(branches=1, cmp=_LE, retention_mode=_lib.MC_RETAIN_HALF_UP, veto_index=11, veto_base=28),
     "flux-kontext": dict(branches=1, cmp=_LE, retention_mode=_lib.MC_RETAIN_HALF_UP, veto_index=11, veto_base=28),

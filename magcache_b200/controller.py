@@ -113,7 +113,7 @@ class AttrController:
         cfg = self._config(o)
         st = self._load(o)
         check(lib.mc_ctrl_advance(ctypes.byref(cfg), ctypes.byref(st)))
-        if st.cnt == 0 and self.kw["branches"] == 2:
+        if st.cnt == 0 and self.kw["branches"] == 2 and not (self.kw.get("flags", 0) & _lib.MC_CTRL_WRAP_KEEPS_ACC):
             # end of video: the reference REBINDS fresh lists (magcache_generate.py:308-311)
             o.accumulated_ratio, o.accumulated_err, o.accumulated_steps = [1.0, 1.0], [0.0, 0.0], [0, 0]
             self._set_cnt(o, 0)

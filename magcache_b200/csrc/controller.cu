@@ -77,7 +77,7 @@ static int32_t check_cfg(const mc_ctrl_config* c) {
   MC_CHECK_ARG(c->retention_mode >= 0 && c->retention_mode <= 5, "mc_ctrl: bad retention_mode %d", c->retention_mode);
   MC_CHECK_ARG(c->table_offset >= 0 && c->table_offset < c->num_steps, "mc_ctrl: table_offset=%d outside [0, num_steps)", c->table_offset);
   MC_CHECK_ARG(c->min_cnt >= 0, "mc_ctrl: min_cnt=%d must be >= 0", c->min_cnt);
-  MC_CHECK_ARG((c->flags & ~(MC_CTRL_SIGNED_ERR | MC_CTRL_RESET_AT_ZERO | MC_CTRL_RATIO_VETO)) == 0 && c->reserved == 0, "mc_ctrl: unknown flag bits 0x%x", c->flags);
+  MC_CHECK_ARG((c->flags & ~(MC_CTRL_SIGNED_ERR | MC_CTRL_RESET_AT_ZERO | MC_CTRL_RATIO_VETO | MC_CTRL_WRAP_KEEPS_ACC)) == 0 && c->reserved == 0, "mc_ctrl: unknown flag bits 0x%x", c->flags);
   MC_CHECK_ARG(!(c->flags & MC_CTRL_RATIO_VETO) || c->ratio_veto >= 0.0, "mc_ctrl: ratio_veto must be >= 0");
   MC_CHECK_ARG(c->retention_mode < MC_RETAIN_WAN22_T2V || (c->split_step >= 0 && c->split_step <= c->num_steps),
                "mc_ctrl: split_step=%d outside [0, num_steps]", c->split_step);
@@ -128,8 +128,10 @@ static void advance(const mc_ctrl_config* c, mc_ctrl_state* st) {
   st->cnt += 1;
   if (st->cnt >= c->num_steps) {
     st->cnt = 0;
-    reset_branch(st, 0);
-    reset_branch(st, 1);
+    if (!(c->flags & MC_CTRL_WRAP_KEEPS_ACC)) {
+      reset_branch(st, 0);
+      reset_branch(st, 1);
+    }
   }
 }
 

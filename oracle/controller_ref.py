@@ -98,7 +98,7 @@ class AdapterControllerRef:
       wan2.2-t2v   MagCache4Wan2.2/magcache_generate.py:294-317 (mode t2v)      per branch, `<`,  two-expert window, float32 compare
       wan2.2-i2v   idem (mode i2v)                                               per branch, `<`,  int(split+(n-split)*R)
       wan2.2-ti2v  idem (split_step None)                                        per branch, `<`,  int(n*R)
-      qwen-image   MagCache4QwenImage/magcache_generate.py:205-219               = wan2.1
+      qwen-image   MagCache4QwenImage/magcache_generate.py:205-219, :243-244     = wan2.1, but the wrap resets only the counter
       flux         MagCache4FLUX/magcache_flux.py:326-338, :431-436              scalar, `<=`, int(R*n+0.5), step-11 veto
       flux-kontext MagCache4FLUX_Kontext/magcache_flux_kontext.py:328-340        = flux
       hunyuan      MagCache4HunyuanVideo/magcache_sample_video.py:88-102         scalar, `<=`, int(R*n)
@@ -166,7 +166,7 @@ class AdapterControllerRef:
             self.cnt += 1
             if self.cnt >= self.n:
                 self.cnt = 0
-                if f != "framepack":
+                if f not in ("framepack", "qwen-image"):  # those two reset only the counter (magcache_demo_gradio.py:299-300; Qwen :243-244)
                     self.ratio, self.err, self.steps = [1.0] * self.nb, [0.0] * self.nb, [0] * self.nb
         return skip
 

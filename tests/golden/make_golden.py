@@ -302,6 +302,20 @@ def extra_cases(tables, interp):
     for L, T in [(50, 50), (50, 40), (50, 1), (50, 2), (28, 20), (9, 5), (5, 3), (101, 41), (3, 7), (60, 50), (2, 2), (7, 1)]:
         src = np.arange(L, dtype=np.float64) * 1.25 + 0.5
         out["qwen_interp"].append({"L": L, "T": T, "src": [float(v) for v in src], "out": [float(v) for v in qi(src, T)]})
+    # Qwen-Image controller over MORE than one image per process: its wrap statement resets only the counter
+    # (MagCache4QwenImage/magcache_generate.py:243-244) — the accumulators of the last calls carry over into the next image.
+    qref = RefController(QWEN)
+    out["qwen_masks"] = []
+    for key, tbl in remaining_tables().items():
+        if not key.startswith("qwen"):
+            continue
+        for steps in (50, 40, 30):
+            for thresh, K, R in [(0.06, 2, 0.2), (0.12, 4, 0.2), (0.24, 6, 0.1), (0.5, 8, 0.0)]:
+                st = wan_state(tbl["values"], steps, thresh, K, R, qi)
+                n = 3 * steps * 2 + 5  # three images and a bit
+                m = run_mask(qref, st, n)
+                out["qwen_masks"].append({"table": key, "steps": steps, "thresh": thresh, "K": K, "R": R, "calls": n, "mask": "".join(map(str, m)),
+                                          "final": final_state(st)})
     omni = RefControllerOmni()
     import importlib.util  # MAG_RATIOS literal dict of magcache_utils.py:14-20
     omni_tbls = {}

@@ -16,6 +16,8 @@ from magcache_b200.controller import make_ctrl_config, schedule_mask
 
 with open(os.path.join(os.path.dirname(__file__), "golden", "extra_adapters.json")) as f:
     X = json.load(f)
+with open(os.path.join(os.path.dirname(__file__), "golden", "tables_all.json")) as f:
+    REMAINING = json.load(f)  # every table literal of the reference, incl. Qwen-Image(-Edit) with their [1.0]*2 prefix
 
 
 @pytest.mark.parametrize("case", X["wan22_masks"], ids=lambda c: f"{c['table']}-{c['mode']}-s{c['steps']}-h{c['high_noise_steps']}-E{c['thresh']}K{c['K']}R{c['R']:.3f}")
@@ -91,3 +93,58 @@ def test_omnigen2_ceil_retention_and_initial_state(case):
         L.check(L.lib.mc_ctrl_decide(ctypes.byref(cfg), ctypes.byref(st), ctypes.byref(skip)))
         got.append(str(skip.value))
     assert "".join(got) == case["mask"]
+
+
+@pytest.mark.parametrize("case", X["qwen_masks"], ids=lambda c: f"{c['table']}-s{c['steps']}-E{c['thresh']}K{c['K']}R{c['R']}")
+def test_qwen_image_over_several_images_keeps_accumulators_at_the_wrap(case):
+    """Three images and a bit through Qwen-Image's controller, whose wrap statement resets ONLY the counter
+    (MagCache4QwenImage/magcache_generate.py:243-244): C ABI (config flag MC_CTRL_WRAP_KEEPS_ACC from the family table), the
+    attribute-level shim and the independent Python restatement against the mask and final state the reference's own statements
+    produce; without the flag the schedule of the later images must differ for at least one preset (the flag is not a no-op)."""
+    from magcache_b200.config import FAMILIES
+    from magcache_b200.controller import AttrController
+    from oracle.controller_ref import AdapterControllerRef
+    tbl = np.array(REMAINING[case["table"]]["values"])
+    steps = case["steps"]
+    ratios = tbl
+    if len(tbl) != 2 * steps:
+        def qi(a, T):
+            out = np.empty(T)
+            dp = ctypes.POINTER(ctypes.c_double)
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            L.check(L.lib.mc_nearest_interp_linspace(a.ctypes.data_as(dp), len(a), out.ctypes.data_as(dp), T))
+            return out
+        ratios = np.stack([qi(tbl[0::2], steps), qi(tbl[1::2], steps)], axis=1).reshape(-1)
+    kw = FAMILIES["qwen-image"]
+    assert kw["flags"] & L.MC_CTRL_WRAP_KEEPS_ACC
+    cfg = make_ctrl_config(2 * steps, case["thresh"], case["K"], case["R"], ratios, **kw)
+    mask = "".join(map(str, schedule_mask(cfg, case["calls"]).tolist()))
+    assert mask == case["mask"]
+    ref = AdapterControllerRef("qwen-image", ratios, 2 * steps, case["thresh"], case["K"], case["R"])
+    assert "".join(map(str, ref.mask(case["calls"]))) == case["mask"]
+    # attribute-level shim (what the patched forward drives)
+    import types
+    o = types.SimpleNamespace(cnt=0, num_steps=2 * steps, magcache_thresh=case["thresh"], K=case["K"], retention_ratio=case["R"],
+                              accumulated_ratio=[1.0, 1.0], accumulated_err=[0.0, 0.0], accumulated_steps=[0, 0], mag_ratios=ratios)
+    ctrl = AttrController(kw)
+    got = []
+    for _ in range(case["calls"]):
+        got.append(int(ctrl.decide(o)))
+        ctrl.advance(o)
+    assert "".join(map(str, got)) == case["mask"]
+    assert o.cnt == case["final"]["cnt"] and list(map(float, o.accumulated_err)) == case["final"]["accumulated_err"]
+    assert list(map(float, o.accumulated_ratio)) == case["final"]["accumulated_ratio"] and list(map(float, o.accumulated_steps)) == case["final"]["accumulated_steps"]
+
+
+def test_qwen_wrap_flag_changes_some_schedule():
+    from magcache_b200.config import FAMILIES
+    kw = dict(FAMILIES["qwen-image"])
+    differs = 0
+    for case in X["qwen_masks"]:
+        tbl = np.array(REMAINING[case["table"]]["values"])
+        if len(tbl) != 2 * case["steps"]:
+            continue
+        with_flag = schedule_mask(make_ctrl_config(2 * case["steps"], case["thresh"], case["K"], case["R"], tbl, **kw), case["calls"])
+        without = schedule_mask(make_ctrl_config(2 * case["steps"], case["thresh"], case["K"], case["R"], tbl, **dict(kw, flags=0)), case["calls"])
+        differs += int(not np.array_equal(with_flag, without))
+    assert differs >= 1

@@ -1,19 +1,19 @@
 """FLUX MMDiT engine on the GPU: the new kernels (per-head RMSNorm + RoPE, SiLU, the bf16 gated-residual and SiLU GEMM epilogues) against
 torch, and `magcache_flux_forward` against the oracle restatement of MagCache4FLUX/magcache_flux.py:234-440.
 
-First B200 run (end of round 1, gpurun_out/unvalidated.log -> profiles/r01_mmdit_first_gpu_run.md): forward and loop tests green
-(ours vs oracle 4.8e-3 rel-L2, ours vs fp64 8.083e-2 against the bf16 oracle's own 8.081e-2), epilogue / SiLU tests green; the
-per-head RMSNorm + RoPE unit test tripped on its tolerance only (4e-6 of the elements beyond one output ulp where the rotation cancels);
-its bound is now the rigorous one and it stays opt-in (`MC_RUN_UNVALIDATED=1`) until it has been re-run."""
+Tolerances are tied to the oracle's own error: every comparison against the bf16 oracle is bounded by a small multiple of the oracle's
+distance from an fp64 evaluation of the same network on the same inputs (all-bf16 streams with synthetic weights amplify rounding to
+several percent, so a fixed number would be either meaningless or flaky)."""
 import copy
 import math
 import os
+import sys
 
 import pytest
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
-unvalidated = pytest.mark.skipif(os.environ.get("MC_RUN_UNVALIDATED") != "1", reason="tolerance changed after its only GPU run (set MC_RUN_UNVALIDATED=1)")
 DEV = "cuda"
 
 
@@ -26,7 +26,6 @@ def _ops():
     return ops
 
 
-@unvalidated
 def test_rmsnorm_head_rope_vs_torch():
     import emu_ops
     ops = _ops()
@@ -107,6 +106,8 @@ def test_flux_forward_vs_oracle_and_fp64():
 
 
 def test_flux_loop_vs_oracle():
+    """14 calls (hits and misses) through both patched forwards: controller state bit-equal on every call; tensors within twice the
+    bf16 oracle's own distance from an fp64 run of the same loop (+1e-3)."""
     import magcache_b200 as mc
     from oracle import flux_ref as fr
     model = _model(seed=1)
@@ -117,6 +118,9 @@ def test_flux_loop_vs_oracle():
     ref_m = copy.deepcopy(model)
     ref_m.__class__ = type("RefFluxL", (ref_m.__class__,), {})
     fr.install_magcache(type(ref_m), mc.tables()["flux_dev"], steps)
+    m64 = copy.deepcopy(model).double()
+    m64.__class__ = type("RefFluxL64", (m64.__class__,), {})
+    fr.install_magcache(type(m64), mc.tables()["flux_dev"], steps)
     ours = copy.deepcopy(model).to(DEV)
     ours.__class__ = type("OurFluxL", (ours.__class__,), {})
     mc.init_magcache_flux(ours, steps)
@@ -126,10 +130,52 @@ def test_flux_loop_vs_oracle():
             t = torch.tensor([1.0 - (i % steps) / steps])
             x = hs * (1.0 - 0.03 * i)
             ref = ref_m(x, enc, pooled, t, img_ids, txt_ids, torch.tensor([3.5]), return_dict=False)[0]
+            with fr.exact():
+                exact = m64(x.double(), enc.double(), pooled.double(), t.double(), img_ids, txt_ids, torch.tensor([3.5]).double(), return_dict=False)[0]
             out = ours(x.to(DEV), enc.to(DEV), pooled.to(DEV), t.to(DEV), img_ids.to(DEV), txt_ids.to(DEV), torch.tensor([3.5], device=DEV),
                        return_dict=False)[0].cpu()
             skips.append(int(ref_m.last_skip))
-            assert rel_l2(out, ref) <= 0.15, (i, rel_l2(out, ref))
+            e_ref, e_vs, e_ours = rel_l2(ref, exact), rel_l2(out, ref), rel_l2(out, exact)
+            assert e_vs <= 2.0 * e_ref + 1e-3, (i, e_vs, e_ref)
+            assert e_ours <= 1.5 * e_ref + 1e-3, (i, e_ours, e_ref)
             for attr in ("cnt", "accumulated_ratio", "accumulated_err", "accumulated_steps"):
                 assert float(getattr(ours, attr)) == float(getattr(ref_m, attr)), (i, attr)
     assert 0 < sum(skips[:steps]) < steps
+
+
+def test_flux_mid_size_forward_vs_oracle_and_fp64():
+    """A FLUX-shaped model at a mid size — hidden 1536 (12 heads x 128), 3 double + 5 single blocks, 32 x 32 = 1024 image tokens + 128
+    text tokens (the long attention kernel, multi-tile GEMMs, ragged last tiles) — miss then hit, against the bf16 oracle and the
+    fp64 evaluation."""
+    import magcache_b200 as mc
+    from oracle import flux_ref as fr
+    model = fr.FluxTransformer2DModel(in_channels=64, num_layers=3, num_single_layers=5, num_attention_heads=12, joint_attention_dim=256,
+                                      pooled_projection_dim=96, guidance_embeds=True).init_synthetic(4)
+    g = torch.Generator().manual_seed(4)
+    hs, enc, pooled = torch.randn(1, 1024, 64, generator=g).bfloat16(), torch.randn(1, 128, 256, generator=g).bfloat16(), torch.randn(1, 96, generator=g).bfloat16()
+    img_ids, txt_ids = fr.make_ids(32, 32, 128)
+    t, gd = torch.tensor([0.62]), torch.tensor([3.5])
+    steps = 4
+    table = [1.0] + [0.98] * 3
+    ref_m = copy.deepcopy(model)
+    ref_m.__class__ = type("RefFluxM", (ref_m.__class__,), {})
+    fr.install_magcache(type(ref_m), table, steps, thresh=10.0, K=3, retention_ratio=0.25)
+    m64 = copy.deepcopy(model).double()
+    m64.__class__ = type("RefFluxM64", (m64.__class__,), {})
+    fr.install_magcache(type(m64), table, steps, thresh=10.0, K=3, retention_ratio=0.25)
+    ours = copy.deepcopy(model).to(DEV)
+    ours.__class__ = type("OurFluxM", (ours.__class__,), {})
+    mc.init_magcache_flux(ours, steps, thresh=10.0, K=3, retention_ratio=0.25, mag_ratios=table)
+    kinds = []
+    with torch.no_grad():
+        for call in range(3):
+            ref = ref_m(hs, enc, pooled, t, img_ids, txt_ids, gd, return_dict=False)[0]
+            with fr.exact():
+                exact = m64(hs.double(), enc.double(), pooled.double(), t.double(), img_ids, txt_ids, gd.double(), return_dict=False)[0]
+            out = ours(hs.to(DEV), enc.to(DEV), pooled.to(DEV), t.to(DEV), img_ids.to(DEV), txt_ids.to(DEV), gd.to(DEV), return_dict=False)[0].cpu()
+            kinds.append(int(ref_m.last_skip))
+            e_ours, e_ref, e_vs = rel_l2(out, exact), rel_l2(ref, exact), rel_l2(out, ref)
+            print(f"[flux mid, call {call}, {'hit' if kinds[-1] else 'miss'}] ours vs fp64 {e_ours:.3e} | oracle(bf16) vs fp64 {e_ref:.3e} | ours vs oracle {e_vs:.3e}")
+            assert e_ours <= 1.5 * e_ref + 1e-3 and e_vs <= 2.0 * e_ref + 1e-3, (call, e_ours, e_ref, e_vs)
+            assert float(ours.cnt) == float(ref_m.cnt)
+    assert kinds == [0, 1, 1], kinds
