@@ -83,15 +83,15 @@ def _stage(self, x, t, context, seq_len, clip_fea, y, pad_ok=True, vace_context=
     assert n_tok <= seq_len  # reference: assert seq_lens.max() <= seq_len (:242)
     # seq_len > n_tok (upstream rounds seq_len up to a multiple of the sequence-parallel size): the reference appends zero rows
     # (:243-246) that never reach a real token — keys are masked by k_lens = seq_lens, every other op is per token, unpatchify
-    # reads the first n_tok rows — so they are simply not computed here. The only visible difference: residual_cache[i] has
-    # n_tok rows instead of seq_len. The calibration statistics DO average over the padded rows upstream, hence the check there.
-    if n_tok != seq_len and pad_ok is False:
-        raise NotImplementedError("magcache_b200: calibration with seq_len > token count (the reference averages the ratios over the "
-                                  "zero-padded rows too); pass seq_len == token count")
+    # reads the first n_tok rows — so the forwards simply do not compute them; the only visible difference: residual_cache[i] has
+    # n_tok rows instead of seq_len. The calibration statistics DO average over the padded rows upstream: there (pad_ok=False) ONE
+    # representative pad row is computed — the padded rows are all identical — and weighted by their count.
+    pad_row = 1 if (n_tok != seq_len and pad_ok is False) else 0
     if vace_context is not None and len(vace_context) != 1:
         raise NotImplementedError("magcache_b200: one sample per call")
     eng.stage_inputs(lat, t, context[0], clip_fea=clip_fea, y=None if y is None else y[0],
-                     vace_context=None if vace_context is None else vace_context[0], vace_scale=vace_scale)
+                     vace_context=None if vace_context is None else vace_context[0], vace_scale=vace_scale, pad_row=pad_row)
+    eng.pad_weight = (seq_len - n_tok) if pad_row else 0
     return eng
 
 
@@ -213,7 +213,17 @@ def _calibrate(self, eng):
         if eng.shard is not None:  # the statistics are sums over tokens: add the partial sums of every token shard
             from .shard import allreduce_stats
             reduce = lambda st: allreduce_stats(st, eng.shard.group)  # noqa: E731
-        residual_x, (norm_ratio, norm_std, cos_dis) = ops.residual_sub_stats(xs, x0, prev, reduce=reduce)
+        if eng.pad_row:
+            # seq_len > token count: rows [n_tok, seq_len) of the reference's tensors are identical copies of the one pad row computed
+            # here; its three per-row terms enter the means (seq_len - n_tok) times (:167-169 average over dim 1 of [1, seq_len, D])
+            n_tok, wgt = eng.n_keys, float(eng.pad_weight)
+            keep = {}
+            ops.residual_sub_stats(xs[n_tok:], x0[n_tok:], prev[n_tok:].contiguous(), reduce=lambda st: keep.setdefault("pad", st.clone()))
+            residual_tok, (norm_ratio, norm_std, cos_dis) = ops.residual_sub_stats(
+                xs[:n_tok], x0[:n_tok], prev[:n_tok].contiguous(), reduce=lambda st: st + keep["pad"] * st.new_tensor([wgt, wgt, wgt, wgt]))
+            residual_x = torch.cat([residual_tok, xs[n_tok:] - x0[n_tok:].float()])
+        else:
+            residual_x, (norm_ratio, norm_std, cos_dis) = ops.residual_sub_stats(xs, x0, prev, reduce=reduce)
         self.norm_ratio.append(round(norm_ratio, 5))
         self.norm_std.append(round(norm_std, 5))
         self.cos_dis.append(round(cos_dis, 5))

@@ -259,14 +259,19 @@ class WanEngine:
         self.hit_sum_bf16 = False  # TeaCache comparator: the hit sum is rounded to bf16 before the head (wan_teacache.py:569/577)
 
     # ------------------------------------------------------------------------------------------ workspace
-    def _workspace(self, n_total):
-        if self._n == n_total:
+    def _workspace(self, n_total, pad_row=0):
+        """`pad_row` = 1 (calibration with seq_len > token count): one extra row after the tokens stands for ALL the zero rows the
+        reference pads the sequence with (magcache_generate.py:243-246) — they are identical (zero input, no RoPE, same keys), so one
+        is computed and the caller weights it. It is a query only: keys / values stay the `n_total` tokens (`k_lens` upstream)."""
+        if self._n == (n_total, pad_row):
             return
         d, dev = self.dims, self.device
         D, F = d.dim, d.ffn_dim
-        self.npad = (n_total + 7) // 8 * 8
+        self.n_keys, self.pad_row = n_total, pad_row
         bf = dict(dtype=torch.bfloat16, device=dev)
         if self.world > 1:
+            if pad_row:
+                raise NotImplementedError("magcache_b200: calibration with seq_len > token count on a token-sharded engine")
             from .shard import TokenShard, make_exchange
             self.shard = TokenShard(self.rank, self.world, n_total, self.group)
             n = self.shard.n_local
@@ -278,7 +283,7 @@ class WanEngine:
             self.xch = make_exchange(self.shard, 2 * D, (d.out_dim, self.grid[0], 2 * self.grid[1], 2 * self.grid[2]), dev)
             self._xi = 0
         else:
-            n = n_total
+            n = n_total + pad_row
             self.qkv = torch.empty(n, 3 * D, **bf)
         self.x0 = torch.empty(n, D, **bf)
         self.xs = torch.empty(n, D, dtype=torch.float32, device=dev)
@@ -312,15 +317,20 @@ class WanEngine:
         self.s_t = torch.zeros(1, dtype=torch.float64, device=dev)
         self.s_lat = None
         self._graphs = {}
-        self._n = n_total
+        self._n = (n_total, pad_row)
 
     def _rope_for(self, grid):
-        if grid not in self._rope:
-            self._rope[grid] = rope_table(grid, self.dims.head_dim, self.device)
-        return self._rope[grid]
+        key = (grid, self.pad_row)
+        if key not in self._rope:
+            tab = rope_table(grid, self.dims.head_dim, self.device)
+            if self.pad_row:  # the padded rows are not rotated (`rope_apply` leaves the tail untouched): cos 1, sin 0
+                ident = torch.tensor([1.0, 0.0], device=self.device).repeat(self.dims.head_dim // 2)[None]
+                tab = torch.cat([tab, ident]).contiguous()
+            self._rope[key] = tab
+        return self._rope[key]
 
     # ------------------------------------------------------------------------------------------ prologue (:229-275)
-    def stage_inputs(self, latent, t, context, clip_fea=None, y=None, vace_context=None, vace_scale=1.0):
+    def stage_inputs(self, latent, t, context, clip_fea=None, y=None, vace_context=None, vace_scale=1.0, pad_row=0):
         """Copy one call's inputs into the engine's fixed buffers (outside any captured graph): latent fp32 [C, F, H, W],
         t tensor [1], context [L <= text_len, text_dim] (zero-padded to text_len, cast to bf16 as autocast would); i2v also
         y [C_y, F, H, W] (concatenated under the latent channels, magcache_generate.py:233-234) and clip_fea [1, 257, clip_dim]."""
@@ -332,7 +342,7 @@ class WanEngine:
         if C + c_y != d.in_dim:
             raise ValueError(f"magcache_b200: {C}+{c_y} input channels, the patch embedding takes {d.in_dim}")
         self.grid = (Fr, H // 2, W // 2)
-        self._workspace(self.grid[0] * self.grid[1] * self.grid[2])
+        self._workspace(self.grid[0] * self.grid[1] * self.grid[2], pad_row)
         shape = (C + c_y, Fr, H, W)
         if self.s_lat is None or tuple(self.s_lat.shape) != shape:
             self.s_lat = torch.empty(shape, dtype=torch.float32, device=self.device)
@@ -376,7 +386,9 @@ class WanEngine:
         tok = ops.patchify(self.s_lat)
         if self.shard is not None:
             tok = self.shard.rows(tok)  # this rank embeds only its own tokens
-        ops.gemm(tok, w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0)
+        ops.gemm(tok, w.patch_w, w.patch_b, E.MC_EPI_BIAS_BF16, out=self.x0[:tok.shape[0]])
+        if self.pad_row:
+            self.x0[tok.shape[0]:].zero_()  # `u.new_zeros(1, seq_len - u.size(1), u.size(2))` (:244-245)
         e, e0 = self.time_embedding()
         # the head's modulated weight depends on the time embedding only: prepared here, off the tail of the forward
         self._head_prep = ops.head_prepare(w.head_mod, e, w.head_wt, w.head_b)
@@ -488,7 +500,7 @@ class WanEngine:
             q, k, v = self.qkv[:, :D], self.qkv[:, D:2 * D], self.qkv[:, 2 * D:]
             ops.gemm(self.h, b["w_qkv"], b["b_qkv"], E.MC_EPI_BIAS_BF16, out=self.qkv, tag="gemm_qkv")
             ops.rmsnorm_rope_segs_(self.qkv, b["nqk"], 2, rope, d.head_dim, eps=d.eps)  # q and k column blocks, one launch
-            ops.attention(q, k, v, H, out=self.att, tag="attn_self")
+            ops.attention(q, k[:self.n_keys], v[:self.n_keys], H, out=self.att, tag="attn_self")  # keys = the tokens (`k_lens`), never the pad row
         else:
             # k | v first: their rows start travelling to the other ranks (copy engines, side stream) while this rank projects q;
             # the attention kernel then begins on the local keys and picks the peers' segments up as they land
@@ -528,6 +540,10 @@ class WanEngine:
         tag = "head_hit_fused" if residual is not None else "head"
         kw = dict(c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps, tag=tag, round_sum_to_bf16=round_sum_to_bf16, prep=self._head_prep)
         if self.shard is None:
+            if self.pad_row:  # unpatchify reads the token rows only (`u[:math.prod(v)]`)
+                x = x[:self.n_keys]
+                if residual is not None:
+                    kw["residual"] = residual[:self.n_keys]
             return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, **kw)
         self.xch.join()  # every push of this forward is ordered before its end (and inside a captured graph)
         out, peer_outs = self.xch.head_output(self._slot)

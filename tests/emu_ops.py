@@ -284,3 +284,22 @@ def residual_stats(r_cur, r_prev, denom_eps=0.0):
     from oracle.controller_ref import calibration_stats
     _count(2)
     return calibration_stats(r_cur.to(F32)[None], r_prev.to(F32)[None], denom_eps)
+
+
+def residual_sub_stats(x_out, x_in, r_prev, denom_eps=0.0, reduce=None):
+    """`mc_residual_sub_stats` as the kernel defines it: r = x_out - x_in (fp32) and the four raw sums (sum ratio, sum ratio^2,
+    sum (1 - cos), rows) over the rows, handed to `reduce` before they are finalised like ops._finish_stats does."""
+    import math
+
+    import torch.nn.functional as Fn
+    r = x_out.to(F32) - x_in.to(F32)
+    ratio = (r.norm(dim=-1) / (r_prev.to(F32).norm(dim=-1) + denom_eps)).double()
+    cosd = (1 - Fn.cosine_similarity(r, r_prev.to(F32), dim=-1, eps=1e-8)).double()
+    stats = torch.stack([ratio.sum(), (ratio * ratio).sum(), cosd.sum(), torch.tensor(float(r.shape[0]), dtype=torch.float64)])
+    _count(2)
+    if reduce is not None:
+        stats = reduce(stats)
+    s0, s1, s2, n = stats.tolist()
+    mean = s0 / n
+    var = (s1 - s0 * s0 / n) / (n - 1) if n > 1 else float("nan")
+    return r, (mean, math.sqrt(max(var, 0.0)), s2 / n)

@@ -78,14 +78,6 @@ def test_wan_engine_forward_sequence_matches_oracle(emulated, kind):
 
 def test_wan_engine_calibration_and_eval_variant(emulated, tmp_path):
     model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128, text_len=32).init_synthetic(2)
-    # statistics of `ops.residual_sub_stats` come from the real library; emulate that one op with the reference expressions
-    from oracle.controller_ref import calibration_stats
-
-    def residual_sub_stats(xs, x0, prev, reduce=None):
-        r = xs.float() - x0.float()
-        return r, calibration_stats(r[None], prev[None].float())
-
-    emu_ops.residual_sub_stats = residual_sub_stats
     ref = copy.deepcopy(model)
     ref.__class__ = type("RefC", (ref.__class__,), {})
     wan_ref.install_magcache(type(ref), None, 3, calibration=True)
@@ -105,3 +97,35 @@ def test_wan_engine_calibration_and_eval_variant(emulated, tmp_path):
     for a, b in zip(ours.norm_ratio, ref.norm_ratio):
         assert abs(a - b) <= 2e-2 * abs(b)
     assert (tmp_path / "wan2_1_mag_ratio.json").exists()
+
+
+def test_wan_engine_calibration_with_padded_seq_len(emulated, tmp_path):
+    """seq_len > token count (MagCache4Wan2.1/magcache_generate.py:243-246 pads the sequence with zero rows): the reference's three
+    statistics (:167-169) average over the padded rows too. The engine computes ONE representative pad row (they are identical:
+    zero input, no RoPE, same keys) as an extra query and weights it by the pad count — same means and std as the oracle, which
+    really carries all the padded rows."""
+    model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128, text_len=32).init_synthetic(4)
+    ref = copy.deepcopy(model)
+    ref.__class__ = type("RefCP", (ref.__class__,), {})
+    wan_ref.install_magcache(type(ref), None, 3, calibration=True)
+    ours = copy.deepcopy(model)
+    ours.__class__ = type("OursCP", (ours.__class__,), {})
+    mc.init_magcache_calibration(ours, 3)
+    type(ours).calibration_dir = str(tmp_path)
+    _attach_engine(ours)
+    g = torch.Generator().manual_seed(6)
+    lat, ctx = torch.randn(16, 2, 8, 8, generator=g), torch.randn(9, 128, generator=g)
+    n_tok, seq_len = 32, 41  # 9 padded rows = 22 % of the sequence: the statistics differ visibly from the unpadded ones
+    outs = []
+    with torch.no_grad():
+        for i in range(6):
+            x = lat * (1.0 - 0.1 * i)
+            a = ref([x], t=torch.tensor([900.0 - 50 * i]), context=[ctx], seq_len=seq_len)[0]
+            b = ours([x], t=torch.tensor([900.0 - 50 * i]), context=[ctx], seq_len=seq_len)[0]
+            outs.append(rel_l2(b, a))
+    assert max(outs) <= 1.5e-2, outs
+    assert len(ours.norm_ratio) == len(ref.norm_ratio) == 4
+    for name in ("norm_ratio", "norm_std", "cos_dis"):
+        for a, b in zip(getattr(ours, name), getattr(ref, name)):
+            assert abs(a - b) <= 3e-2 * abs(b) + 2e-4, (name, a, b)
+    assert ours._mc_engine.pad_row == 1 and ours.residual_cache[0].shape[1] == n_tok + 1
