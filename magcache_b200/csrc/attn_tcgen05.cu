@@ -33,8 +33,7 @@
 namespace mc {
 
 constexpr int kHD = 128;
-constexpr float kRescaleThreshold = 8.0f;  // log2 units: the running reference follows the maximum only when it is this far behind
-constexpr float kSpecLimit = 64.0f;        // log2 units: largest 2^x a speculative exponential may produce (bf16 / fp32 hold 2^127)
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kLongMinLk = 1024;
 
 struct AttnParams {
@@ -295,26 +294,6 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
     const uint32_t tmem_o = tmem_base + 256 + t * 128 + lane_sel;
     const uint64_t scale2 = ptx::pack_f32x2(p.scale_log2, p.scale_log2);
     float m = -INFINITY, l = 0.f;
-    float m_seen = -INFINITY;  // largest scaled score seen so far: m follows it lazily (only when it is more than 2^8 ahead)
-
-    // O_t *= 2^(m - m_to), l likewise, m = m_to for the rows that ask for it. All 32 lanes execute the TMEM loads / stores
-    // (.sync.aligned); O_t must be quiescent (no PV MMA of this query tile in flight).
-    auto rescale_to = [&](bool need, float m_to) {
-      const float factor = need ? ptx::ex2_approx(m - m_to) : 1.0f;
-      if (need) {
-        l *= factor;
-        m = m_to;
-      }
-#pragma unroll 1
-      for (int c = 0; c < kHD / 32; ++c) {
-        uint32_t o[32];
-        ptx::tmem_ld_32x32b_x32(tmem_o + c * 32, o);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-        ptx::tmem_st_32x32b_x32(tmem_o + c * 32, o);
-      }
-    };
 
     for (int j = 0; j < n_tiles; ++j) {
       // s_full(j) also certifies that PV_t(j-1) has completed (commit semantics): O_t is quiescent until p_half0(j) is signalled
@@ -322,22 +301,52 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
       ptx::tc_fence_after();
       const int valid = p.Lk - tile_of(j) * kBKV;  // columns >= valid are padding (only the globally last tile)
       if (valid < kBKV) mask_padding_columns(tmem_s, valid, kBKV);  // warp-uniform, at most once per CTA
-      // the running reference m catches up with the largest score of the EARLIER tiles here, where O_t is quiescent
-      if (j > 0) {
-        const bool need = m_seen > m + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) rescale_to(need, m_seen);
-      }
       uint32_t sreg[4][32];
-      ptx::tmem_ld_32x32b_x32(tmem_s, sreg[0]);
-      ptx::tmem_ld_wait();
 #pragma unroll
-      for (int h = 1; h < 4; ++h) ptx::tmem_ld_32x32b_x32(tmem_s + h * 32, sreg[h]);  // in flight under the first chunk's exponentials
-
-      // P = 2^(s*scale - m) for one 32-column chunk -> 16 packed bf16 words + its fp32 row-sum contribution (summed before the
-      // bf16 rounding, as flash-attention does). Packed fp32x2 FMA / ADD.
+      for (int h = 0; h < 4; ++h) ptx::tmem_ld_32x32b_x32(tmem_s + h * 32, sreg[h]);
+      ptx::tmem_ld_wait();
+      // 3-input max, 0.5 instruction per element, in EIGHT independent chains (two per 32-column chunk): the exponentials cannot
+      // start before the row max is known, so the chain depth (8 dependent ops) is what this costs, not the instruction count
+      float mxa[4], mxb[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        mxa[h] = -INFINITY, mxb[h] = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          mxa[h] = ptx::max3(mxa[h], __uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1]));
+          mxb[h] = ptx::max3(mxb[h], __uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3]));
+        }
+      }
+      const float mx = fmaxf(ptx::max3(mxa[0], mxa[1], mxa[2]), fmaxf(mxa[3], fmaxf(ptx::max3(mxb[0], mxb[1], mxb[2]), mxb[3])));
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      if (j == 0) {
+        m = m_new;
+      } else {
+        const bool need = m_new > m + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          const float factor = need ? ptx::ex2_approx(m - m_new) : 1.0f;
+          if (need) {
+            l *= factor;
+            m = m_new;
+          }
+#pragma unroll 1
+          for (int c = 0; c < kHD / 32; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld_32x32b_x32(tmem_o + c * 32, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            ptx::tmem_st_32x32b_x32(tmem_o + c * 32, o);
+          }
+        }
+      }
+      // P = 2^(s*scale - m), row sum in fp32 before the bf16 rounding (as flash-attention does). Packed fp32x2 FMA / ADD;
+      // 32 columns -> 16 packed words, stored over the consumed S columns right away.
+      const uint64_t negm2 = ptx::pack_f32x2(-m, -m);
       uint64_t sum2a = 0ull, sum2b = 0ull;
-      auto chunk = [&](int h, uint32_t (&pk)[16]) {
-        const uint64_t negm2 = ptx::pack_f32x2(-m, -m);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t pk[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           float a0, a1, b0, b1;
@@ -350,56 +359,13 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
           pk[c >> 1] = pack_bf16x2(a0, a1);
           pk[(c >> 1) + 1] = pack_bf16x2(b0, b1);
         }
-      };
-      // 3-input max over the whole tile, 0.5 instruction per element, EIGHT independent chains
-      auto tile_max = [&]() {
-        float mxa[4], mxb[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          mxa[h] = -INFINITY, mxb[h] = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            mxa[h] = ptx::max3(mxa[h], __uint_as_float(sreg[h][c]), __uint_as_float(sreg[h][c + 1]));
-            mxb[h] = ptx::max3(mxb[h], __uint_as_float(sreg[h][c + 2]), __uint_as_float(sreg[h][c + 3]));
-          }
-        }
-        return fmaxf(ptx::max3(mxa[0], mxa[1], mxa[2]), fmaxf(mxa[3], fmaxf(ptx::max3(mxb[0], mxb[1], mxb[2]), mxb[3]))) * p.scale_log2;
-      };
-
-      uint32_t pk0[16], pk1[16];
-      if (j == 0) {  // no reference yet: the first tile's own maximum (the only tile whose exponentials wait for the max)
-        ptx::tmem_ld_wait();
-        m = m_seen = tile_max();
-        chunk(0, pk0);
-        chunk(1, pk1);
-      } else {
-        // SPECULATIVE exponentials against the reference m of the earlier tiles: exact for any m as long as nothing overflows —
-        // 2^x with x <= kSpecLimit is safe in bf16 (P), in the fp32 row sum and in the fp32 accumulator — so the tile's own maximum
-        // is off the critical path; it is computed next to the exponentials (independent instructions) and only CHECKED before
-        // anything is signalled. A row whose scores jump by more than 2^kSpecLimit between tiles takes the exact slow path below.
-        chunk(0, pk0);
-        ptx::tmem_ld_wait();
-        chunk(1, pk1);
-        const float mt = tile_max();
-        m_seen = fmaxf(m_seen, mt);
-        const bool over = mt > m + kSpecLimit;
-        if (__any_sync(0xffffffffu, over)) {
-          // O_t is still quiescent (PV_t(j-1) complete, nothing of tile j signalled): move the reference, redo the two chunks
-          rescale_to(over, m_seen);
-          sum2a = 0ull, sum2b = 0ull;
-          chunk(0, pk0);
-          chunk(1, pk1);
+        ptx::tmem_st_32x32b_x16(tmem_s + h * 16, pk);
+        if (h == 1) {  // keys 0..63 of this tile are in place: let the first half of PV_t(j) go
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&p_half0[t]);
         }
       }
-      ptx::tmem_st_32x32b_x16(tmem_s, pk0);
-      ptx::tmem_st_32x32b_x16(tmem_s + 16, pk1);
-      ptx::tmem_st_wait();  // (also covers the O stores of a rescale)
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&p_half0[t]);  // keys 0..63 of this tile are in place: let the first half of PV_t(j) go
-      chunk(2, pk0);
-      ptx::tmem_st_32x32b_x16(tmem_s + 32, pk0);
-      chunk(3, pk1);
-      ptx::tmem_st_32x32b_x16(tmem_s + 48, pk1);
       float s0, s1, s2, s3;
       ptx::unpack_f32x2(sum2a, s0, s1);
       ptx::unpack_f32x2(sum2b, s2, s3);
