@@ -19,7 +19,7 @@
 //     KV tiles, two CTAs co-resident per SM so that one CTA's prologue / epilogue overlaps the other's main loop.
 // Both: thread = query row (TMEM lane) in the softmax warps, online softmax in the exp2 domain with lazy rescaling of O
 // (only when the running max grows by more than 2^8), P -> bf16 -> tcgen05.st over the consumed S columns, PV MMA with A
-// from TMEM. Small grids (token-sharded ranks) split the KV range over blockIdx.z and merge with attn_combine_kernel.
+// from TMEM. The units of a partially filled last wave are split over the KV range and merged by attn_combine_kernel.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -38,9 +38,12 @@ constexpr int kLongMinLk = 1024;
 
 struct AttnParams {
   int Lq, Lk, heads;
-  int splits;      // > 1: blockIdx.z owns a contiguous range of KV tiles and writes a partial result (split-KV)
-  float* part_o;   // [splits][Lq][heads*128] fp32, each split's output normalised by its own row sum
-  float2* part_ml; // [splits][Lq][heads]     (row max in the scaled log2 domain, row sum)
+  // Work decomposition (plan_attention): a unit = one query block of one head. CTAs [0, full_units) each own a whole unit;
+  // the remaining `tail_units` units (the part of the grid that would not fill a last wave) are split `tail_split` ways over
+  // the KV range, CTA full_units + u * tail_split + s owning split s of tail unit u and writing a partial result.
+  int q_blocks, full_units, tail_units, tail_split;
+  float* part_o;   // [tail_split][tail_units][rows per CTA][128] fp32, each split's output normalised by its own row sum
+  float2* part_ml; // [tail_split][tail_units][rows per CTA]      (row max in the scaled log2 domain, row sum)
   float scale_log2;  // softmax scale * log2(e)
   __nv_bfloat16* out;
   int64_t ldo;
@@ -52,6 +55,30 @@ struct AttnParams {
   const uint32_t* seg_epoch;  // device memory: the epoch the flags must have reached (read at run time, so graph replays work)
   int seg_rows;
 };
+
+struct WorkItem {
+  int q_block, head;
+  int split, nsplit;  // nsplit > 1: this CTA covers KV tiles [split * per, ...) of its unit and writes a partial
+  int tail_unit;
+};
+
+__device__ __forceinline__ WorkItem work_item(const AttnParams& p) {
+  WorkItem w;
+  int c = blockIdx.x, unit;
+  if (c < p.full_units) {
+    unit = c, w.split = 0, w.nsplit = 1, w.tail_unit = 0;
+  } else {
+    c -= p.full_units;
+    w.tail_unit = c / p.tail_split;
+    w.split = c - w.tail_unit * p.tail_split;
+    w.nsplit = p.tail_split;
+    unit = p.full_units + w.tail_unit;
+  }
+  // query blocks of one head are adjacent in launch order: the CTAs resident together stream the same K/V through L2
+  w.head = unit / p.q_blocks;
+  w.q_block = unit - w.head * p.q_blocks;
+  return w;
+}
 
 // P = 2^x for four consecutive elements (two packed pairs): MUFU for a pair unless its bit in EMU_MASK is set, in which case the
 // pair goes through the FMA-pipe polynomial. `pair` is the running pair index (mod 8 selects the mask bit).
@@ -139,17 +166,17 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
   uint64_t* v_full = bars + 5;    // [2]
   uint64_t* v_empty = bars + 7;   // [2]
   uint64_t* s_full = bars + 9;    // [2] per query tile
-  uint64_t* p_half0 = bars + 11;  // [2] per query tile, 128 arrivals: P columns of keys 0..63 of the tile are in TMEM
-  uint64_t* p_half1 = bars + 13;  // [2] per query tile, 128 arrivals: keys 64..127
-  uint64_t* pv_done = bars + 15;  // [2] per query tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* p_part = bars + 11;   // [2][4] per query tile and quarter, 128 arrivals: P of keys [32 q, 32 q + 32) of the tile is in TMEM
+  uint64_t* pv_done = bars + 19;  // [2] per query tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * kBQ);
-  const int head = blockIdx.y;
+  const WorkItem wi = work_item(p);
+  const int q0 = wi.q_block * (2 * kBQ);
+  const int head = wi.head;
   const int total_tiles = (p.Lk + kBKV - 1) / kBKV;
-  const int per_split = (total_tiles + p.splits - 1) / p.splits;
-  const int t0 = blockIdx.z * per_split;                 // first KV tile (in rotated order) of this CTA
+  const int per_split = (total_tiles + wi.nsplit - 1) / wi.nsplit;
+  const int t0 = wi.split * per_split;                   // first KV tile (in rotated order) of this CTA
   const int n_tiles = min(per_split, total_tiles - t0);  // >= 1, guaranteed by the host
   auto tile_of = [&](int j) {  // global KV tile index of this CTA's j-th tile
     int t = p.tile_rot + t0 + j;
@@ -171,8 +198,7 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
       ptx::mbar_init(&v_full[s], 1);
       ptx::mbar_init(&v_empty[s], 1);
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&p_half0[s], 128);
-      ptx::mbar_init(&p_half1[s], 128);
+      for (int q = 0; q < 4; ++q) ptx::mbar_init(&p_part[s * 4 + q], 128);
       ptx::mbar_init(&pv_done[s], 1);
     }
     ptx::fence_mbar_init();
@@ -251,19 +277,20 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
     for (int j = 0; j < n_tiles; ++j) {
       const uint64_t dv0 = ptx::umma_desc_sw128_mnmajor(v_base + (j & 1) * kVBytes, kBKV * 128);  // LBO = one [128 kv x 64 d] box
       for (int t = 0; t < 2; ++t) {
-        // O_t += P_t(j) V_j, A from TMEM (8 packed columns per K16 step), in two halves: the first 64 keys' probabilities are
-        // signalled as soon as they are written, so this half of the MMA runs while the softmax warps exponentiate the rest
+        // O_t += P_t(j) V_j, A from TMEM (8 packed columns per K16 step), in four quarters: every 32 keys' probabilities are
+        // signalled as soon as they are written, so most of the MMA runs while the softmax warps exponentiate the rest and only
+        // the last quarter (plus the next S MMA) is left on the softmax -> PV -> S -> softmax chain of this query tile
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          ptx::mbar_wait(half == 0 ? &p_half0[t] : &p_half1[t], j & 1);
-          if (t == 0 && half == 0) ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+        for (int part = 0; part < 4; ++part) {
+          ptx::mbar_wait(&p_part[t * 4 + part], j & 1);
+          if (t == 0 && part == 0) ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int kk = half * 4; kk < half * 4 + 4; ++kk)  // one K-step = 16 kv rows = 2048 B of the MN-major tile
+            for (int kk = part * 2; kk < part * 2 + 2; ++kk)  // one K-step = 16 kv rows = 2048 B of the MN-major tile
               ptx::umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, dv0 + static_cast<uint64_t>(kk * (2048 / 16)), idesc_o,
                            (j | kk) != 0 ? 1u : 0u);
-            if (half == 1) {
+            if (part == 3) {
               if (t == 1) ptx::umma_commit(&v_empty[j & 1]);
               ptx::umma_commit(&pv_done[t]);
             }
@@ -294,13 +321,19 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
     const uint32_t tmem_o = tmem_base + 256 + t * 128 + lane_sel;
     const uint64_t scale2 = ptx::pack_f32x2(p.scale_log2, p.scale_log2);
     float m = -INFINITY, l = 0.f;
+    // the globally last KV tile is the only one that can hold padding columns (keys >= Lk): its position in this CTA's order
+    int j_ragged = -1;
+    if (p.Lk % kBKV != 0) {
+      int jr = total_tiles - 1 - p.tile_rot - t0;
+      if (jr < 0) jr += total_tiles;
+      if (jr < n_tiles) j_ragged = jr;
+    }
 
     for (int j = 0; j < n_tiles; ++j) {
-      // s_full(j) also certifies that PV_t(j-1) has completed (commit semantics): O_t is quiescent until p_half0(j) is signalled
+      // s_full(j) also certifies that PV_t(j-1) has completed (commit semantics): O_t is quiescent until p_part[0](j) is signalled
       ptx::mbar_wait(&s_full[t], j & 1);
       ptx::tc_fence_after();
-      const int valid = p.Lk - tile_of(j) * kBKV;  // columns >= valid are padding (only the globally last tile)
-      if (valid < kBKV) mask_padding_columns(tmem_s, valid, kBKV);  // warp-uniform, at most once per CTA
+      if (j == j_ragged) mask_padding_columns(tmem_s, p.Lk - (total_tiles - 1) * kBKV, kBKV);  // warp-uniform, at most once per CTA
       uint32_t sreg[4][32];
 #pragma unroll
       for (int h = 0; h < 4; ++h) ptx::tmem_ld_32x32b_x32(tmem_s + h * 32, sreg[h]);
@@ -360,19 +393,14 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
           pk[(c >> 1) + 1] = pack_bf16x2(b0, b1);
         }
         ptx::tmem_st_32x32b_x16(tmem_s + h * 16, pk);
-        if (h == 1) {  // keys 0..63 of this tile are in place: let the first half of PV_t(j) go
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&p_half0[t]);
-        }
+        ptx::tmem_st_wait();  // keys [32 h, 32 h + 32) of this tile are in place: let that quarter of PV_t(j) go
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&p_part[t * 4 + h]);
       }
       float s0, s1, s2, s3;
       ptx::unpack_f32x2(sum2a, s0, s1);
       ptx::unpack_f32x2(sum2b, s2, s3);
       l += (s0 + s1) + (s2 + s3);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&p_half1[t]);
     }
 
     // ---- epilogue: O_t / l -> bf16 -> global (or the normalised fp32 partial of this split)
@@ -380,16 +408,17 @@ __global__ void __launch_bounds__(lk::kThreads, 1)
     ptx::tc_fence_after();
     const float inv_l = 1.0f / l;
     const int row = q0 + t * kBQ + r;
-    if (p.splits > 1 && row < p.Lq)
-      p.part_ml[(static_cast<int64_t>(blockIdx.z) * p.Lq + row) * p.heads + head] = make_float2(m, l);
+    const bool partial = wi.nsplit > 1;
+    const int64_t prow = (static_cast<int64_t>(wi.split) * p.tail_units + wi.tail_unit) * (2 * kBQ) + t * kBQ + r;
+    if (partial) p.part_ml[prow] = make_float2(m, l);
 #pragma unroll 1
     for (int c = 0; c < kHD / 32; ++c) {
       uint32_t o[32];
       ptx::tmem_ld_32x32b_x32(tmem_o + c * 32, o);
       ptx::tmem_ld_wait();
       if (row < p.Lq) {
-        if (p.splits > 1) {
-          float* dst = p.part_o + (static_cast<int64_t>(blockIdx.z) * p.Lq + row) * (static_cast<int64_t>(p.heads) * kHD) + head * kHD + c * 32;
+        if (partial) {
+          float* dst = p.part_o + prow * kHD + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
             *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
@@ -450,11 +479,12 @@ __global__ void __launch_bounds__(sk::kThreads, 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kBQ;
-  const int head = blockIdx.y;
+  const WorkItem wi = work_item(p);
+  const int q0 = wi.q_block * kBQ;
+  const int head = wi.head;
   const int total_tiles = (p.Lk + kBKV - 1) / kBKV;
-  const int per_split = (total_tiles + p.splits - 1) / p.splits;
-  const int t0 = blockIdx.z * per_split;                 // first (global) KV tile of this CTA
+  const int per_split = (total_tiles + wi.nsplit - 1) / wi.nsplit;
+  const int t0 = wi.split * per_split;                   // first (global) KV tile of this CTA
   const int n_tiles = min(per_split, total_tiles - t0);  // local tile count (>= 1, guaranteed by the host)
 
   if (threadIdx.x == 0) {
@@ -649,16 +679,17 @@ __global__ void __launch_bounds__(sk::kThreads, 2)
     ptx::tc_fence_after();
     const float inv_l = 1.0f / l;
     const int row = q0 + r;
-    if (p.splits > 1 && row < p.Lq)
-      p.part_ml[(static_cast<int64_t>(blockIdx.z) * p.Lq + row) * p.heads + head] = make_float2(m, l);
+    const bool partial = wi.nsplit > 1;
+    const int64_t prow = (static_cast<int64_t>(wi.split) * p.tail_units + wi.tail_unit) * kBQ + r;
+    if (partial) p.part_ml[prow] = make_float2(m, l);
 #pragma unroll 1
     for (int c = 0; c < kHD / 32; ++c) {
       uint32_t o[32];
       ptx::tmem_ld_32x32b_x32(tmem_o + lane_sel + c * 32, o);
       ptx::tmem_ld_wait();
       if (row < p.Lq) {
-        if (p.splits > 1) {
-          float* dst = p.part_o + (static_cast<int64_t>(blockIdx.z) * p.Lq + row) * (static_cast<int64_t>(p.heads) * kHD) + head * kHD + c * 32;
+        if (partial) {
+          float* dst = p.part_o + prow * kHD + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
             *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
@@ -684,40 +715,47 @@ __global__ void __launch_bounds__(sk::kThreads, 2)
   if (warp == 5) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// Merge of the split-KV partials: out = sum_s w_s O_s / sum_s w_s with w_s = l_s * 2^(m_s - max_s m_s).
-__global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, int splits,
-                                                           int Lq, int heads, __nv_bfloat16* __restrict__ out, int64_t ldo) {
-  const int groups_per_row = heads * (kHD / 8);
-  const int64_t total = static_cast<int64_t>(Lq) * groups_per_row;
-  const int64_t W = static_cast<int64_t>(heads) * kHD;
+// Merge of the split-KV partials of the tail units: out = sum_s w_s O_s / sum_s w_s with w_s = l_s * 2^(m_s - max_s m_s).
+__global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, int nsplit,
+                                                           int tail_units, int full_units, int q_blocks, int rows_per_cta, int Lq,
+                                                           __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  constexpr int kGroups = kHD / 8;
+  const int64_t total = static_cast<int64_t>(tail_units) * rows_per_cta * kGroups;
+  const int64_t split_stride = static_cast<int64_t>(tail_units) * rows_per_cta;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int row = static_cast<int>(i / groups_per_row), g = static_cast<int>(i % groups_per_row);
-    const int head = g / (kHD / 8);
+    const int64_t prow = i / kGroups;
+    const int g = static_cast<int>(i - prow * kGroups);
+    const int tu = static_cast<int>(prow / rows_per_cta), r = static_cast<int>(prow - static_cast<int64_t>(tu) * rows_per_cta);
+    const int unit = full_units + tu;
+    const int head = unit / q_blocks, row = (unit - head * q_blocks) * rows_per_cta + r;
+    if (row >= Lq) continue;
     float mmax = -INFINITY;
-    for (int s = 0; s < splits; ++s) mmax = fmaxf(mmax, part_ml[(static_cast<int64_t>(s) * Lq + row) * heads + head].x);
+    for (int s = 0; s < nsplit; ++s) mmax = fmaxf(mmax, part_ml[s * split_stride + prow].x);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float wsum = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float2 ml = part_ml[(static_cast<int64_t>(s) * Lq + row) * heads + head];
+    for (int s = 0; s < nsplit; ++s) {
+      const float2 ml = part_ml[s * split_stride + prow];
       const float w = ml.y * ptx::ex2_approx(ml.x - mmax);
       wsum += w;
       float v[8];
-      ptx::ld_nc_v8_f32(part_o + (static_cast<int64_t>(s) * Lq + row) * W + g * 8, v);
+      ptx::ld_nc_v8_f32(part_o + (s * split_stride + prow) * kHD + g * 8, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, v[j], acc[j]);
     }
     const float inv = 1.0f / wsum;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] *= inv;
-    *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo + g * 8) = pack_bf16x8(acc);
+    *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo + head * kHD + g * 8) = pack_bf16x8(acc);
   }
 }
 
 // ---- host side: work decomposition ----------------------------------------------------------------------------------
 struct AttnPlan {
   bool long_kernel;
-  int q_blocks, kv_tile, total_tiles, splits;
-  size_t ws_bytes;  // workspace for the split partials (0 when unsplit)
+  int q_blocks, kv_tile, total_tiles, rows_per_cta;
+  int full_units, tail_units, tail_split;  // see AttnParams
+  size_t ws_bytes;                         // workspace for the split partials (0 when nothing is split)
+  int grid() const { return full_units + tail_units * tail_split; }
 };
 
 static int env_int(const char* name, int lo, int hi, int dflt) {
@@ -727,39 +765,42 @@ static int env_int(const char* name, int lo, int hi, int dflt) {
   return (v < lo || v > hi) ? dflt : v;
 }
 
-// One CTA = 256 (long kernel, 1 CTA/SM) or 128 (short kernel, 2 CTAs/SM) query rows of one head. With fewer than four waves of
-// CTAs the last, partially filled wave dominates (token-sharded runs: 4095 rows x 12 heads = 192 CTAs on 148 SMs), so the KV
-// range is split across blockIdx.z until the last wave is >= 92 % full, and the partial softmaxes are merged by a second kernel.
+// One CTA = 256 (long kernel, 1 CTA/SM) or 128 (short kernel, 2 CTAs/SM) query rows of one head, every unit the same length, so
+// the grid runs in rounds of `slots` CTAs and a partially filled last round costs a whole one (32760 rows x 12 heads = 1536
+// units on 148 SMs: 10.4 rounds of work take 11; a token-sharded rank's 4095 rows: 192 units, 1.3 rounds take 2). The units
+// of that last round are therefore split over the KV range, floor(slots / units) ways, so that they fill the SMs once at a
+// fraction of the length; a second kernel merges their partial softmaxes. Units of the full rounds are never split.
 static AttnPlan plan_attention(int Lq, int Lk, int heads, bool need_long = false) {
   AttnPlan pl;
-  const int forced_splits = env_int("MC_ATTN_SPLITS", 1, 16, 0);  // MC_ATTN_SPLITS=n forces n splits (1 = never split)
+  const int forced_splits = env_int("MC_ATTN_SPLITS", 1, 16, 0);  // MC_ATTN_SPLITS=n: every unit split n ways (1 = never split)
   const int kernel_sel = env_int("MC_ATTN_KERNEL", 0, 2, 0);  // 0 = by Lk, 1 = short, 2 = long (tests / A-B timing)
   pl.long_kernel = need_long || kernel_sel == 2 || (kernel_sel == 0 && Lk >= kLongMinLk);  // rotated / flag-gated key order: long kernel only
-  const int rows_per_cta = pl.long_kernel ? 2 * lk::kBQ : sk::kBQ;
+  pl.rows_per_cta = pl.long_kernel ? 2 * lk::kBQ : sk::kBQ;
   pl.kv_tile = pl.long_kernel ? lk::kBKV : sk::kBKV;
-  pl.q_blocks = (Lq + rows_per_cta - 1) / rows_per_cta;
+  pl.q_blocks = (Lq + pl.rows_per_cta - 1) / pl.rows_per_cta;
   pl.total_tiles = (Lk + pl.kv_tile - 1) / pl.kv_tile;
-  const double slots = (pl.long_kernel ? 1.0 : 2.0) * num_sms();
-  const double waves = static_cast<double>(pl.q_blocks) * heads / slots;
+  const int64_t units = static_cast<int64_t>(pl.q_blocks) * heads;
+  const int slots = (pl.long_kernel ? 1 : 2) * num_sms();
   const int min_tiles_per_split = pl.long_kernel ? 4 : 8;
-  int splits = 1;
+  int full = static_cast<int>(units), tail = 0, split = 1;
   if (forced_splits > 0) {
-    splits = forced_splits;
-  } else if (waves < 4.0 && pl.total_tiles >= 2 * min_tiles_per_split) {
-    double best = 0.0;
-    for (int sp = 1; sp <= 8 && sp * min_tiles_per_split <= pl.total_tiles; ++sp) {
-      const double w = waves * sp, fill = w / static_cast<double>(static_cast<int64_t>(w + 0.999999));
-      if (fill > best + 1e-9) best = fill, splits = sp;
-      if (fill >= 0.92) break;
-    }
+    if (forced_splits > 1) full = 0, tail = static_cast<int>(units), split = forced_splits;
+  } else {
+    const int rem = static_cast<int>(units % slots);
+    const int by_tiles = pl.total_tiles / min_tiles_per_split;
+    int f = rem > 0 ? slots / rem : 1;
+    if (f > 8) f = 8;
+    if (f > by_tiles) f = by_tiles;
+    if (f >= 2) full = static_cast<int>(units) - rem, tail = rem, split = f;
   }
-  if (splits > pl.total_tiles) splits = pl.total_tiles;
-  if (splits > 1) {
-    const int per = (pl.total_tiles + splits - 1) / splits;
-    splits = (pl.total_tiles + per - 1) / per;  // no empty split
+  if (split > pl.total_tiles) split = pl.total_tiles;
+  if (split > 1) {
+    const int per = (pl.total_tiles + split - 1) / split;
+    split = (pl.total_tiles + per - 1) / per;  // no empty split
   }
-  pl.splits = splits;
-  pl.ws_bytes = splits > 1 ? static_cast<size_t>(splits) * Lq * heads * (kHD * sizeof(float) + sizeof(float2)) : 0;
+  if (split <= 1) full = static_cast<int>(units), tail = 0, split = 1;
+  pl.full_units = full, pl.tail_units = tail, pl.tail_split = split;
+  pl.ws_bytes = tail > 0 ? static_cast<size_t>(split) * tail * pl.rows_per_cta * (kHD * sizeof(float) + sizeof(float2)) : 0;
   return pl;
 }
 
@@ -786,7 +827,8 @@ extern "C" int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int
   MC_CHECK_ARG(first_key_row >= 0 && first_key_row < Lk, "mc_attn_fwd: first_key_row=%d outside [0, %d)", first_key_row, Lk);
   MC_CHECK_ARG(seg_flags == nullptr || (seg_rows >= 1 && seg_epoch != nullptr), "mc_attn_fwd: seg_rows=%d / null epoch", seg_rows);
   const mc::AttnPlan pl = mc::plan_attention(Lq, Lk, heads, first_key_row != 0 || seg_flags != nullptr);
-  if (pl.splits > 1) {
+  MC_CHECK_ARG(static_cast<int64_t>(pl.q_blocks) * heads * 8 < INT32_MAX, "mc_attn_fwd: grid too large");
+  if (pl.tail_units > 0) {
     MC_CHECK_ARG(workspace != nullptr && workspace_bytes >= static_cast<int64_t>(pl.ws_bytes) && (reinterpret_cast<uintptr_t>(workspace) & 31u) == 0,
                  "mc_attn_fwd: split-KV needs a 32-byte aligned workspace of %lld bytes (mc_attn_workspace_bytes), got %lld",
                  static_cast<long long>(pl.ws_bytes), static_cast<long long>(workspace_bytes));
@@ -801,10 +843,12 @@ extern "C" int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int
   if (rc) return rc;
 
   float* part_o = static_cast<float*>(workspace);
-  float2* part_ml = pl.splits > 1 ? reinterpret_cast<float2*>(part_o + static_cast<size_t>(pl.splits) * Lq * heads * mc::kHD) : nullptr;
+  const size_t part_rows = static_cast<size_t>(pl.tail_split) * pl.tail_units * pl.rows_per_cta;
+  float2* part_ml = pl.tail_units > 0 ? reinterpret_cast<float2*>(part_o + part_rows * mc::kHD) : nullptr;
   mc::AttnParams p{};
-  p.Lq = Lq, p.Lk = Lk, p.heads = heads, p.splits = pl.splits;
-  p.part_o = pl.splits > 1 ? part_o : nullptr, p.part_ml = part_ml;
+  p.Lq = Lq, p.Lk = Lk, p.heads = heads;
+  p.q_blocks = pl.q_blocks, p.full_units = pl.full_units, p.tail_units = pl.tail_units, p.tail_split = pl.tail_split;
+  p.part_o = pl.tail_units > 0 ? part_o : nullptr, p.part_ml = part_ml;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out), p.ldo = ldo;
   // start with the first tile that lies entirely inside the caller's own (already resident) rows; the tile straddling the segment
@@ -812,7 +856,7 @@ extern "C" int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int
   p.tile_rot = ((first_key_row + pl.kv_tile - 1) / pl.kv_tile) % pl.total_tiles;
   p.seg_flags = seg_flags, p.seg_epoch = seg_epoch, p.seg_rows = seg_rows > 0 ? seg_rows : Lk;
 
-  dim3 grid(pl.q_blocks, heads, pl.splits);
+  dim3 grid(pl.grid(), 1, 1);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.long_kernel) {
     static mc::PerDeviceOnce once[4];
@@ -839,11 +883,11 @@ extern "C" int32_t mc_attn_fwd_ex(const void* q, int64_t ldq, const void* k, int
     mc::attn_short_kernel<<<grid, mc::sk::kThreads, mc::sk::kSmem, st>>>(tq, tk, tv, p);
     MC_CHECK_LAUNCH("attn_short_kernel launch");
   }
-  if (pl.splits > 1) {
-    const int64_t total = static_cast<int64_t>(Lq) * heads * (mc::kHD / 8);
+  if (pl.tail_units > 0) {
+    const int64_t total = static_cast<int64_t>(pl.tail_units) * pl.rows_per_cta * (mc::kHD / 8);
     const int64_t want = (total + 255) / 256, cap = static_cast<int64_t>(mc::num_sms()) * 8;
-    mc::attn_combine_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, st>>>(p.part_o, p.part_ml, pl.splits, Lq, heads,
-                                                                                      static_cast<__nv_bfloat16*>(out), ldo);
+    mc::attn_combine_kernel<<<static_cast<int>(want < cap ? want : cap), 256, 0, st>>>(
+        p.part_o, p.part_ml, pl.tail_split, pl.tail_units, pl.full_units, pl.q_blocks, pl.rows_per_cta, Lq, static_cast<__nv_bfloat16*>(out), ldo);
     MC_CHECK_LAUNCH("attn_combine_kernel launch");
   }
   return MC_OK;
