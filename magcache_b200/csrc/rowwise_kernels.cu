@@ -316,6 +316,243 @@ __global__ void __launch_bounds__(256, 2) rmsnorm_rope_pipe_kernel(__nv_bfloat16
   }
 }
 
+// ---- TMA-staged forms of the same two kernels: the register-pipelined forms above keep one row per warp in flight (48-96 KB
+// per SM), which is short of the ~60 KB x latency a 6.5 TB/s stream needs once the warps also reduce, compute and store
+// (3.2-3.9 TB/s measured on 32760 x 1536). Here one producer thread keeps `stages` x 8 rows in flight with cp.async.bulk into a
+// shared-memory ring (144-192 KB per SM, independent of what the consumer warps are doing); NG groups of eight consumer warps
+// take the stages in turn (stage `it` belongs to group it % NG), one row of the stage per warp: copy it to registers, hand the
+// slot back at once, then run the same arithmetic as the forms above (bit-identical results). One CTA per SM, chunks of 8 rows
+// strided over the grid. The consumers, not the loads, bound these kernels: 8 warps 4.2 TB/s, 16 warps 4.7 TB/s on fp32 rows
+// (24 warps spill at 80 registers); the bf16 RMSNorm rows take 24 warps: 3.2 -> 5.1 TB/s.
+constexpr int kRingRows = 8;                                                   // rows (or (token, block) items) per stage
+constexpr int ring_threads(int groups) { return (groups * kRingRows + 1) * 32; }  // + the producer warp
+constexpr int kLnRingGroups = 2, kRmsRingGroups = 3;
+
+template <int G, int NG>
+__global__ void __launch_bounds__(ring_threads(NG), 1) ln_modulate_tma_kernel(const void* __restrict__ x, int x_bf16, int64_t rows, int cols, float eps,
+                                                                         int mode, const float* __restrict__ p0, const float* __restrict__ p1,
+                                                                         int scale_idx, int shift_idx, int round_ln, void* __restrict__ out,
+                                                                         int out_bf16, int stages) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  const int row_bytes = cols * (x_bf16 ? 2 : 4);
+  const int stage_bytes = kRingRows * row_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_dyn + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* empty = full + stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_chunks = (rows + kRingRows - 1) / kRingRows;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], kRingRows);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NG * kRingRows) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+        const int s = it % stages;
+        ptx::mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        const int64_t row0 = c * kRingRows;
+        const int64_t left = rows - row0;
+        const uint32_t bytes = static_cast<uint32_t>(left < kRingRows ? left : kRingRows) * row_bytes;  // rows are contiguous
+        ptx::mbar_expect_tx(&full[s], bytes);
+        ptx::bulk_load_1d(smem_dyn + static_cast<size_t>(s) * stage_bytes, static_cast<const uint8_t*>(x) + row0 * row_bytes, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  const int groups = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  const float* pa = (mode == 0) ? p0 + static_cast<int64_t>(scale_idx) * cols : p0;
+  const float* pb = (mode == 0) ? p0 + static_cast<int64_t>(shift_idx) * cols : p1;
+  const int grp = warp / kRingRows, wr = warp - grp * kRingRows;  // consumer group, row of the stage
+  uint32_t it = grp;
+  for (int64_t c = blockIdx.x + static_cast<int64_t>(grp) * gridDim.x; c < n_chunks; c += static_cast<int64_t>(NG) * gridDim.x, it += NG) {
+    const int s = it % stages;
+    ptx::mbar_wait(&full[s], (it / stages) & 1);
+    const int64_t row = c * kRingRows + wr;
+    const uint8_t* rp = smem_dyn + static_cast<size_t>(s) * stage_bytes + wr * row_bytes;
+    float v[G][8];
+    if (row < rows) {
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int g = lane + i * 32;
+        if (g < groups) {
+          if (x_bf16) {
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(rp + g * 16), v[i]);
+          } else {
+            const float4 a = *reinterpret_cast<const float4*>(rp + g * 32), b = *reinterpret_cast<const float4*>(rp + g * 32 + 16);
+            v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[s]);  // the row is in registers: the slot can be refilled while it is processed
+    if (row >= rows) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+      if (lane + i * 32 < groups) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[i][j];
+      }
+    const float mean = warp_sum(sum) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+      if (lane + i * 32 < groups) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int g = lane + i * 32;
+      if (g < groups) {
+        const int c0 = g * 8;
+        float a[8], b[8], o[8];
+        load_param8(pa + c0, a);
+        load_param8(pb + c0, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = (v[i][j] - mean) * rstd;
+          if (round_ln) y = round_bf16(y);
+          const float aa = (mode == 0) ? 1.0f + a[j] : a[j];
+          o[j] = __fadd_rn(__fmul_rn(y, aa), b[j]);  // torch eager: separate mul and add, no FMA contraction
+        }
+        if (out_bf16) {
+          ptx::st_na_v4(static_cast<__nv_bfloat16*>(out) + row * cols + c0, pack_bf16x8(o));
+        } else {
+          ptx::st_na_v8_f32(static_cast<float*>(out) + row * cols + c0, o);
+        }
+      }
+    }
+  }
+}
+
+// items = (token, block); the `segs` blocks of a token are adjacent in memory, so a stage of 8 items is 8 / segs pitched rows of
+// segs * cols elements (one bulk copy each) plus their RoPE rows (contiguous: one bulk copy).
+template <int G, int NG>
+__global__ void __launch_bounds__(ring_threads(NG), 1) rmsnorm_rope_tma_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int64_t rows, int segs, int cols,
+                                                                          const float* __restrict__ w, float eps,
+                                                                          const float* __restrict__ cos_sin, int head_dim, int stages) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  const int item_bytes = cols * 2;
+  const int rows_per_stage = kRingRows / segs;  // segs in {1, 2, 4}
+  const int cs_row_bytes = cos_sin != nullptr ? head_dim * 4 : 0;
+  const int stage_bytes = kRingRows * item_bytes + rows_per_stage * cs_row_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_dyn + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* empty = full + stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_chunks = (rows + rows_per_stage - 1) / rows_per_stage;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], kRingRows);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == NG * kRingRows) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+        const int s = it % stages;
+        ptx::mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        const int64_t row0 = c * rows_per_stage;
+        const int64_t left = rows - row0;
+        const int nr = left < rows_per_stage ? static_cast<int>(left) : rows_per_stage;
+        uint8_t* base = smem_dyn + static_cast<size_t>(s) * stage_bytes;
+        const uint32_t per_row = static_cast<uint32_t>(segs) * item_bytes;
+        ptx::mbar_expect_tx(&full[s], static_cast<uint32_t>(nr) * (per_row + cs_row_bytes));
+        for (int r = 0; r < nr; ++r) ptx::bulk_load_1d(base + r * per_row, x + (row0 + r) * ld, per_row, &full[s]);
+        if (cs_row_bytes) ptx::bulk_load_1d(base + kRingRows * item_bytes, cos_sin + row0 * head_dim, nr * cs_row_bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  const int groups = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  const int grp = warp / kRingRows, wr = warp - grp * kRingRows;  // consumer group, item of the stage
+  const int r_in_stage = wr / segs, seg = wr - r_in_stage * segs;
+  const float* ws = w + static_cast<int64_t>(seg) * cols;
+  uint32_t it = grp;
+  for (int64_t c = blockIdx.x + static_cast<int64_t>(grp) * gridDim.x; c < n_chunks; c += static_cast<int64_t>(NG) * gridDim.x, it += NG) {
+    const int s = it % stages;
+    ptx::mbar_wait(&full[s], (it / stages) & 1);
+    const int64_t row = c * rows_per_stage + r_in_stage;
+    const uint8_t* base = smem_dyn + static_cast<size_t>(s) * stage_bytes;
+    const uint8_t* rp = base + wr * item_bytes;  // item wr of the stage = (row r_in_stage, block seg)
+    uint4 raw[G];
+    float cs[8] = {1.f, 0.f, 1.f, 0.f, 1.f, 0.f, 1.f, 0.f};
+    if (row < rows) {
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int g = lane + i * 32;
+        if (g < groups) raw[i] = *reinterpret_cast<const uint4*>(rp + g * 16);
+      }
+      if (cs_row_bytes) {
+        // a lane's groups are 256 columns apart: with head_dim dividing 256 they all sit at the same position inside their head
+        const float4* cp = reinterpret_cast<const float4*>(base + kRingRows * item_bytes + r_in_stage * cs_row_bytes + ((lane * 8) % head_dim) * 4);
+        const float4 a = cp[0], b = cp[1];
+        cs[0] = a.x; cs[1] = a.y; cs[2] = a.z; cs[3] = a.w; cs[4] = b.x; cs[5] = b.y; cs[6] = b.z; cs[7] = b.w;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[s]);
+    if (row >= rows) continue;
+    __nv_bfloat16* px = x + row * ld + static_cast<int64_t>(seg) * cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+      if (lane + i * 32 < groups) {
+        float f[8];
+        unpack_bf16x8(raw[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q = fmaf(f[j], f[j], q);
+      }
+    const float r = rsqrtf(warp_sum(q) * inv_n + eps);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int g = lane + i * 32;
+      if (g < groups) {
+        const int c0 = g * 8;
+        float f[8], wv[8], o[8];
+        unpack_bf16x8(raw[i], f);
+        load_param8(ws + c0, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = round_bf16(f[j] * r) * wv[j];  // _norm(x.float()).type_as(x) * weight
+        if (cs_row_bytes) {
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const float re = o[2 * pp], im = o[2 * pp + 1], cc = cs[2 * pp], sn = cs[2 * pp + 1];
+            o[2 * pp] = __fsub_rn(__fmul_rn(re, cc), __fmul_rn(im, sn));
+            o[2 * pp + 1] = __fadd_rn(__fmul_rn(re, sn), __fmul_rn(im, cc));
+          }
+        }
+        *reinterpret_cast<uint4*>(px + c0) = pack_bf16x8(o);
+      }
+    }
+  }
+}
+
+// number of ring stages that fit (0: the staged form does not apply)
+static int ring_stages(int stage_bytes) {
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  return stages >= 2 ? stages : 0;
+}
+
 // ---- per-HEAD RMSNorm (head_dim 128, bf16 weight semantics) + RoPE, in place on bf16: the q / k normalisation of the MMDiT
 // attention (diffusers `RMSNorm(head_dim)` on [B, H, L, 128] followed by `apply_rotary_emb`, upstream of
 // MagCache4FLUX/magcache_flux.py:361-366). 16 threads per (token, head), 8 elements each.
@@ -535,6 +772,30 @@ int32_t mc_ln_modulate(const void* x, int32_t x_dtype, int64_t rows, int32_t col
 #define MC_LNP(G)                                                                                                              \
   mc::ln_modulate_pipe_kernel<G><<<mc::pipe_grid(rows, (G) >= 6 ? 1 : 2), 256, 0, s>>>(x, x_dtype == MC_BF16, rows, cols, eps, mode, p0, p1,      \
                                                                      scale_idx, shift_idx, round_ln_to_bf16, out, out_dtype == MC_BF16)
+  // long inputs: the TMA-staged form (needs >= 2 stages of 8 rows in shared memory and 16-byte aligned rows)
+  const int ring = rows >= 1024 && groups <= 32 * mc::kMaxG ? mc::ring_stages(mc::kRingRows * cols * (x_dtype == MC_BF16 ? 2 : 4)) : 0;
+  if (ring > 0) {
+    const int smem = ring * mc::kRingRows * cols * (x_dtype == MC_BF16 ? 2 : 4) + ring * 16 + 64;
+    const int64_t chunks = (rows + mc::kRingRows - 1) / mc::kRingRows;
+    const int grid = static_cast<int>(chunks < mc::num_sms() ? chunks : mc::num_sms());
+    int32_t rc = MC_OK;
+#define MC_LNT(G, IDX)                                                                                                                 \
+  do {                                                                                                                                 \
+    static mc::PerDeviceOnce once_##IDX;                                                                                               \
+    rc = mc::set_max_smem_once(mc::ln_modulate_tma_kernel<G, mc::kLnRingGroups>, 208 * 1024, once_##IDX, "cudaFuncSetAttribute(ln_modulate_tma smem)");   \
+    if (rc == MC_OK)                                                                                                                   \
+      mc::ln_modulate_tma_kernel<G, mc::kLnRingGroups><<<grid, mc::ring_threads(mc::kLnRingGroups), smem, s>>>(x, x_dtype == MC_BF16, rows, cols, eps, mode, p0, p1, scale_idx, \
+                                                                        shift_idx, round_ln_to_bf16, out, out_dtype == MC_BF16, ring); \
+  } while (0)
+    if (groups <= 32 * 2) MC_LNT(2, 2);
+    else if (groups <= 32 * 4) MC_LNT(4, 4);
+    else if (groups <= 32 * 6) MC_LNT(6, 6);
+    else MC_LNT(8, 8);
+#undef MC_LNT
+    if (rc) return rc;
+    MC_CHECK_LAUNCH("ln_modulate_tma_kernel launch");
+    return MC_OK;
+  }
   if (groups <= 32 * 2) MC_LNP(2);
   else if (groups <= 32 * 4) MC_LNP(4);
   else if (groups <= 32 * 6) MC_LNP(6);
@@ -567,6 +828,32 @@ int32_t mc_rmsnorm_rope_segs(void* x_bf16, int64_t ld, int64_t rows, int32_t seg
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = cols / 8;
   __nv_bfloat16* xp = static_cast<__nv_bfloat16*>(x_bf16);
+  const bool ring_ok = rows * segs >= 1024 && groups <= 32 * mc::kMaxG && (segs == 1 || segs == 2 || segs == 4) &&
+                       (cos_sin == nullptr || 256 % head_dim == 0);
+  const int rows_per_stage = mc::kRingRows / (segs == 3 ? 1 : segs);
+  const int ring_stage_bytes = mc::kRingRows * cols * 2 + (cos_sin != nullptr ? rows_per_stage * head_dim * 4 : 0);
+  const int ring = ring_ok ? mc::ring_stages(ring_stage_bytes) : 0;
+  if (ring > 0) {
+    const int smem = ring * ring_stage_bytes + ring * 16 + 64;
+    const int64_t chunks = (rows + rows_per_stage - 1) / rows_per_stage;
+    const int grid = static_cast<int>(chunks < mc::num_sms() ? chunks : mc::num_sms());
+    int32_t rc = MC_OK;
+#define MC_RMST(G, IDX)                                                                                                                 \
+  do {                                                                                                                                  \
+    static mc::PerDeviceOnce once_##IDX;                                                                                                \
+    rc = mc::set_max_smem_once(mc::rmsnorm_rope_tma_kernel<G, mc::kRmsRingGroups>, 208 * 1024, once_##IDX, "cudaFuncSetAttribute(rmsnorm_rope_tma smem)"); \
+    if (rc == MC_OK)                                                                                                                    \
+      mc::rmsnorm_rope_tma_kernel<G, mc::kRmsRingGroups><<<grid, mc::ring_threads(mc::kRmsRingGroups), smem, s>>>(xp, ld, rows, segs, cols, w, eps, cos_sin, head_dim, ring);   \
+  } while (0)
+    if (groups <= 32 * 2) MC_RMST(2, 2);
+    else if (groups <= 32 * 4) MC_RMST(4, 4);
+    else if (groups <= 32 * 6) MC_RMST(6, 6);
+    else MC_RMST(8, 8);
+#undef MC_RMST
+    if (rc) return rc;
+    MC_CHECK_LAUNCH("rmsnorm_rope_tma_kernel launch");
+    return MC_OK;
+  }
 #define MC_RMSP(G) mc::rmsnorm_rope_pipe_kernel<G><<<mc::pipe_grid(rows * segs), 256, 0, s>>>(xp, ld, rows, segs, cols, w, eps, cos_sin, head_dim)
   if (groups <= 32 * 2) MC_RMSP(2);
   else if (groups <= 32 * 4) MC_RMSP(4);

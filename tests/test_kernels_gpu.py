@@ -234,7 +234,10 @@ def test_patchify_matches_conv3d_im2col():
     assert torch.allclose(y, y2, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("rows,cols,xdt", [(37, 1536, torch.float32), (130, 5120, torch.float32), (64, 1536, torch.bfloat16), (5, 256, torch.float32)])
+@pytest.mark.parametrize("rows,cols,xdt", [(37, 1536, torch.float32), (130, 5120, torch.float32), (64, 1536, torch.bfloat16), (5, 256, torch.float32),
+                                           # >= 1024 rows: the TMA-staged form (ragged last group of 8 rows, 2-8 ring stages)
+                                           (1029, 1536, torch.float32), (4099, 1536, torch.bfloat16), (2050, 384, torch.float32),
+                                           (1500, 2048, torch.float32), (1025, 3072, torch.float32)])
 def test_ln_modulate(rows, cols, xdt):
     ops = _ops()
     x = (torch.randn(rows, cols, device=DEV) * 3 + 0.5).to(xdt)
@@ -260,9 +263,10 @@ def test_ln_modulate(rows, cols, xdt):
     assert torch.equal(out16, out32.bfloat16())
 
 
-def test_ln_affine():
+@pytest.mark.parametrize("rows", [77, 3003])
+def test_ln_affine(rows):
     ops = _ops()
-    x = torch.randn(77, 1536, device=DEV) * 2
+    x = torch.randn(rows, 1536, device=DEV) * 2
     w = torch.randn(1536, device=DEV)
     b = torch.randn(1536, device=DEV)
     out = ops.ln_affine(x, w, b, out_dtype=torch.float32)
@@ -279,7 +283,8 @@ def _rope_ref(x, cos_sin, heads):
     return torch.view_as_real(xc * fr).reshape(rows, cols).float()
 
 
-@pytest.mark.parametrize("rows,cols,heads,rope", [(100, 1536, 12, True), (512, 1536, 12, False), (33, 5120, 40, True)])
+@pytest.mark.parametrize("rows,cols,heads,rope", [(100, 1536, 12, True), (512, 1536, 12, False), (33, 5120, 40, True),
+                                                  (1027, 1536, 12, True), (4101, 1536, 12, False), (2049, 256, 2, True)])  # TMA-staged form
 def test_rmsnorm_rope(rows, cols, heads, rope):
     ops = _ops()
     x = torch.randn(rows, 2 * cols, device=DEV).bfloat16()
@@ -488,7 +493,7 @@ def test_gemm_strided_operands():
     assert torch.allclose(out, _gemm_ref(a, b).float(), rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.parametrize("rows,D", [(7, 256), (333, 384), (1000, 1536), (515, 2048)])
+@pytest.mark.parametrize("rows,D", [(7, 256), (333, 384), (1000, 1536), (515, 2048), (1031, 1536), (3001, 384)])
 def test_rmsnorm_rope_two_blocks_one_launch(rows, D):
     """q | k of the fused q|k|v buffer normalised (+ RoPE) by ONE launch over two column blocks == two single-block launches, bit
     for bit (same per-row arithmetic), on a row-strided view; the v block is untouched."""
@@ -504,6 +509,26 @@ def test_rmsnorm_rope_two_blocks_one_launch(rows, D):
     assert torch.equal(a, b)
     assert torch.equal(a[:, 2 * D:], qkv[:, 2 * D:])
     assert not torch.equal(a[:, :2 * D], qkv[:, :2 * D])
+
+
+def test_rmsnorm_rope_staged_form_matches_register_form_bitwise():
+    """The TMA-staged kernels (>= 1024 items) and the register-pipelined ones (fewer) run the same per-row arithmetic: the first
+    1000 rows of a long input, processed alone, must come out bit-identical; likewise LayerNorm + modulation."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    D = 1536
+    qkv = torch.randn(2500, 3 * D, device=DEV, generator=g).bfloat16()
+    w = 1 + 0.1 * torch.randn(2, D, device=DEV, generator=g)
+    cs = torch.randn(2500, 128, device=DEV, generator=g)
+    a, b = qkv.clone(), qkv[:500].clone()
+    ops.rmsnorm_rope_segs_(a, w, 2, cs, 128)         # 5000 items: staged
+    ops.rmsnorm_rope_segs_(b, w, 2, cs[:500], 128)   # 1000 items: register form
+    assert torch.equal(a[:500], b)
+    x = torch.randn(2500, D, device=DEV, generator=g) * 2 + 0.3
+    em = torch.randn(6, D, device=DEV, generator=g) * 0.2
+    ya = ops.ln_modulate(x, em, 4, 3)
+    yb = ops.ln_modulate(x[:1000], em, 4, 3)
+    assert torch.equal(ya[:1000], yb)
 
 
 # ------------------------------------------------------------------------------------------- tcgen05 attention
