@@ -267,10 +267,10 @@ def run_ours(args, rank, world):
 
     def step_resident(i, x):
         t = t_dev[i % SAMPLE_STEPS]
-        cond = fwd(x, t, ctx_d)
-        uncond = fwd(x, t, ctxn_d)
-        # caller-side code (wan_magcache.py:301-310): CFG combine + an Euler flow step standing in for FlowUniPC, one fused kernel
-        return ops.cfg_step(cond, uncond, guide, x, float(sig[(i % SAMPLE_STEPS) + 1] - sig[i % SAMPLE_STEPS]), out=x)
+        # caller-side code (wan_magcache.py:296-310): cond call, uncond call, CFG combine + an Euler flow step standing in for
+        # FlowUniPC. One GPU: the combine and the update ride in the epilogue of the unconditional call's head kernel
+        # (mc_head_unpatchify_step); token-sharded: one mc_cfg_step launch after the two calls.
+        return mc.cfg_denoise_step(model, x, t, ctx_d, ctxn_d, N_TOK, guide, float(sig[(i % SAMPLE_STEPS) + 1] - sig[i % SAMPLE_STEPS]), forward=fwd)
 
     def step_e2e(i, x_unused):
         t = t_dev[i % SAMPLE_STEPS]

@@ -316,6 +316,18 @@ int32_t mc_head_prepare(const float* head_mod, const float* e, const float* Wt, 
 int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
                               int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, float eps, float* const* outs, int32_t n_out,
                               const void* prepared, int64_t prepared_bytes, int32_t flags, void* stream);
+/* The caller loop's step folded into the head pass (eval/magcache/experiments/wan_magcache.py:301-310:
+ * `noise_pred = uncond + g * (cond - uncond)`, `scheduler.step`): this launch is the UNCONDITIONAL head of a denoising step, given
+ * the conditional prediction `cond` of the same step and the current latent `x_latent` (both fp32 in the output layout
+ * [C, F, 2Hp, 2Wp]). Instead of the unconditional prediction y it stores
+ *     out = coef_x * x_latent + coef_v * (y + guide_scale * (cond - y))
+ * (flow-matching Euler: coef_x = 1, coef_v = sigma_next - sigma), every product and sum rounded separately in that order: bit-equal
+ * to mc_head_unpatchify_ex followed by mc_cfg_step. x_latent may alias an output (in-place update of the latent). Positions of
+ * tokens outside [row_offset, row_offset + rows) are not touched. */
+int32_t mc_head_unpatchify_step(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
+                                int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, float eps, float* const* outs, int32_t n_out,
+                                const void* prepared, int64_t prepared_bytes, int32_t flags, const float* cond, const float* x_latent,
+                                float guide_scale, float coef_x, float coef_v, void* stream);
 
 /* bf16 transpose dst[c, r] = src[r, c]. */
 int32_t mc_transpose_bf16(const void* src, int64_t lds, int32_t rows, int32_t cols, void* dst, int64_t ldd, void* stream);

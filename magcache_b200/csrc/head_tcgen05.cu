@@ -57,6 +57,12 @@ struct HeadParams {
   float eps;
   float* out[hd::kMaxPeers];  // fp32 [16, F, 2Hp, 2Wp] — the caller's own and, token-sharded, every peer's (P2P stores)
   int n_out;
+  // Caller-loop step folded into the epilogue (eval/.../wan_magcache.py:301-310): this launch is the UNCONDITIONAL
+  // head of a step; instead of its prediction it writes  out = coef_x * x + coef_v * (y + g * (cond - y))  with `cond` the
+  // conditional prediction of the same step and `x` the current latent (both in the output layout; x may alias out).
+  const float* step_cond;  // nullptr: plain head
+  const float* step_x;
+  float step_g, step_cx, step_cv;
 };
 
 // ---- per-forward preparation: W' = (1 + e1) * W split into bf16 hi / lo, K-major [64, cols]; c1, c0 ----------------------------
@@ -347,29 +353,55 @@ __global__ void __launch_bounds__(hd::kThreads, 1) head_tc_kernel(const __grid_c
         // output feature j = (q*2 + rr)*16 + c -> out[c, f, 2*hp+q, 2*wp+rr]: columns [32q, 32q+32) hold rr = 0 | rr = 1 for the
         // same 16 channels, so every store is one float2 and a warp writes 256 contiguous bytes per channel row.
         const int qtr = warp & 3, qh = warp >> 2;
+        const int er = qtr * 32 + lane;
+        const int64_t erow = cta_row0 + static_cast<int64_t>(st) * kRows + er;
+        const bool elive = erow < cta_row1;
+        const int64_t tok = p.row_offset + erow;
+        const int wp = static_cast<int>(tok % p.Wp);
+        const int hp = static_cast<int>((tok / p.Wp) % p.Hp);
+        const int f = static_cast<int>(tok / (static_cast<int64_t>(p.Wp) * p.Hp));
+        const int H2 = p.Hp * 2, W2 = p.Wp * 2;
+        const int64_t plane = static_cast<int64_t>(p.F) * H2 * W2;
+        const int64_t off = (static_cast<int64_t>(f) * H2 + hp * 2 + qh) * W2 + wp * 2;
+        const bool step = p.step_cond != nullptr && elive;
+        // fused caller step: the conditional prediction and the latent at this thread's 16 output positions, fetched in two batches
+        // of 8 channels; the first batch is in flight while the last MMAs of the tile finish (x may alias out: every position is
+        // read by the thread that later writes it, before it writes it)
+        float2 cc[8], xl[8];
+        auto fetch = [&](int c0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            cc[c] = *reinterpret_cast<const float2*>(p.step_cond + (c0 + c) * plane + off);
+            xl[c] = *reinterpret_cast<const float2*>(p.step_x + (c0 + c) * plane + off);
+          }
+        };
+        if (step) fetch(0);
         ptx::mbar_wait(acc_full, st & 1);
         ptx::tc_fence_after();
         uint32_t acc[32];
         ptx::tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(qtr * 32) << 16) + qh * 32, acc);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        const int er = qtr * 32 + lane;
-        const int64_t erow = cta_row0 + static_cast<int64_t>(st) * kRows + er;
-        if (erow < cta_row1) {
+        if (elive) {
           const float2 ms = stats[er];
-          const int64_t tok = p.row_offset + erow;
-          const int wp = static_cast<int>(tok % p.Wp);
-          const int hp = static_cast<int>((tok / p.Wp) % p.Hp);
-          const int f = static_cast<int>(tok / (static_cast<int64_t>(p.Wp) * p.Hp));
-          const int H2 = p.Hp * 2, W2 = p.Wp * 2;
-          const int64_t plane = static_cast<int64_t>(p.F) * H2 * W2;
-          const int64_t off = (static_cast<int64_t>(f) * H2 + hp * 2 + qh) * W2 + wp * 2;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int j0 = qh * 32 + c, j1 = j0 + 16;
-            const float y0 = fmaf(ms.y, __uint_as_float(acc[c]) - ms.x * __ldg(p.c1 + j0), __ldg(p.c0 + j0));
-            const float y1 = fmaf(ms.y, __uint_as_float(acc[16 + c]) - ms.x * __ldg(p.c1 + j1), __ldg(p.c0 + j1));
-            for (int o = 0; o < p.n_out; ++o) *reinterpret_cast<float2*>(p.out[o] + c * plane + off) = make_float2(y0, y1);
+          for (int cb = 0; cb < 16; cb += 8) {
+            if (step && cb != 0) fetch(cb);
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+              const int c = cb + ci;
+              const int j0 = qh * 32 + c, j1 = j0 + 16;
+              float y0 = fmaf(ms.y, __uint_as_float(acc[c]) - ms.x * __ldg(p.c1 + j0), __ldg(p.c0 + j0));
+              float y1 = fmaf(ms.y, __uint_as_float(acc[16 + c]) - ms.x * __ldg(p.c1 + j1), __ldg(p.c0 + j1));
+              if (step) {
+                // same operations, same order, each rounded separately, as mc_cfg_step (cache_kernels.cu::cfg_step_one): bit-identical
+                const float v0 = __fadd_rn(y0, __fmul_rn(p.step_g, __fsub_rn(cc[ci].x, y0)));
+                const float v1 = __fadd_rn(y1, __fmul_rn(p.step_g, __fsub_rn(cc[ci].y, y1)));
+                y0 = __fadd_rn(__fmul_rn(p.step_cx, xl[ci].x), __fmul_rn(p.step_cv, v0));
+                y1 = __fadd_rn(__fmul_rn(p.step_cx, xl[ci].y), __fmul_rn(p.step_cv, v1));
+              }
+              for (int o = 0; o < p.n_out; ++o) *reinterpret_cast<float2*>(p.out[o] + c * plane + off) = make_float2(y0, y1);
+            }
           }
         }
       }
@@ -418,9 +450,10 @@ int32_t mc_head_prepare(const float* head_mod, const float* e, const float* Wt, 
   return MC_OK;
 }
 
-int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
-                              int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, float eps, float* const* outs, int32_t n_out,
-                              const void* prepared, int64_t prepared_bytes, int32_t flags, void* stream) {
+static int32_t head_launch(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols, int32_t F,
+                           int32_t Hp, int32_t Wp, int32_t C_out, float eps, float* const* outs, int32_t n_out, const void* prepared,
+                           int64_t prepared_bytes, int32_t flags, const float* step_cond, const float* step_x, float step_g, float step_cx,
+                           float step_cv, void* stream) {
   using namespace mc;
   MC_CHECK_ARG(x && outs && prepared, "mc_head_unpatchify: null pointer");
   MC_CHECK_ARG(n_out >= 1 && n_out <= hd::kMaxPeers, "mc_head_unpatchify: n_out=%d outside [1, %d]", n_out, hd::kMaxPeers);
@@ -453,6 +486,7 @@ int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_
     p.out[i] = outs[i];
   }
   p.n_out = n_out;
+  p.step_cond = step_cond, p.step_x = step_x, p.step_g = step_g, p.step_cx = step_cx, p.step_cv = step_cv;
 
   HeadMaps maps{};
   rc = make_tmap_bf16_2d(&maps.w_hi, w_hi, 64, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols), hd::kOut, hd::kKC);
@@ -484,6 +518,24 @@ int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_
   }
   MC_CHECK_LAUNCH("head_tc_kernel launch");
   return MC_OK;
+}
+
+int32_t mc_head_unpatchify_ex(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
+                              int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, float eps, float* const* outs, int32_t n_out,
+                              const void* prepared, int64_t prepared_bytes, int32_t flags, void* stream) {
+  return head_launch(x, x_dtype, r_or_null, rows, row_offset, cols, F, Hp, Wp, C_out, eps, outs, n_out, prepared, prepared_bytes, flags, nullptr,
+                     nullptr, 0.f, 0.f, 0.f, stream);
+}
+
+int32_t mc_head_unpatchify_step(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,
+                                int32_t F, int32_t Hp, int32_t Wp, int32_t C_out, float eps, float* const* outs, int32_t n_out,
+                                const void* prepared, int64_t prepared_bytes, int32_t flags, const float* cond, const float* x_latent,
+                                float guide_scale, float coef_x, float coef_v, void* stream) {
+  MC_CHECK_ARG(cond != nullptr && x_latent != nullptr, "mc_head_unpatchify_step: null cond / latent");
+  MC_CHECK_ARG((reinterpret_cast<uintptr_t>(cond) & 7u) == 0 && (reinterpret_cast<uintptr_t>(x_latent) & 7u) == 0,
+               "mc_head_unpatchify_step: cond / latent must be 8-byte aligned");
+  return head_launch(x, x_dtype, r_or_null, rows, row_offset, cols, F, Hp, Wp, C_out, eps, outs, n_out, prepared, prepared_bytes, flags, cond,
+                     x_latent, guide_scale, coef_x, coef_v, stream);
 }
 
 int32_t mc_head_unpatchify(const void* x, int32_t x_dtype, const float* r_or_null, int64_t rows, int64_t row_offset, int32_t cols,

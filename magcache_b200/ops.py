@@ -398,12 +398,15 @@ def head_prepare(head_mod, e, w_t, b, tag=None):
 
 
 def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None, row_offset=0, out=None, round_sum_to_bf16=False,
-                    peer_outs=None, prep=None):
+                    peer_outs=None, prep=None, step=None):
     """head(x, e) + unpatchify (MagCache4Wan2.1/magcache_generate.py:304-305) -> fp32 [c_out, F, 2*Hp, 2*Wp].
     x fp32 (the residual stream), or bf16 with `residual` (fp32): the cache-hit sum x + residual is formed on the fly (fused hit
     path, :295). `prep`: a `head_prepare` result for this forward's time embedding (else it is computed here). A token-sharded
     caller passes its contiguous token range (`row_offset`, x.shape[0] rows) and an `out` whose other positions the peers fill;
-    `peer_outs` (device pointers of the peers' outputs) makes the kernel store its rows there as well."""
+    `peer_outs` (device pointers of the peers' outputs) makes the kernel store its rows there as well.
+    `step` = (cond, x_latent, guide_scale, coef_x, coef_v): this is the unconditional head of a denoising step and the caller loop's
+    CFG combine + scheduler update are applied in the epilogue (`mc_head_unpatchify_step`): the result is
+    `coef_x * x_latent + coef_v * (y + guide_scale * (cond - y))` instead of y — bit-equal to this head followed by `cfg_step`."""
     import ctypes
     _dev(x)
     F, Hp, Wp = grid
@@ -421,9 +424,18 @@ def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1
         out = torch.empty(c_out, F, 2 * Hp, 2 * Wp, dtype=torch.float32, device=x.device)
     ptrs = [out.data_ptr()] + [int(p) for p in (peer_outs or [])]
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    rptr = residual.data_ptr() if residual is not None else None
     with _Timed(tag, "head"):
-        check(lib.mc_head_unpatchify_ex(x.data_ptr(), _dt(x), residual.data_ptr() if residual is not None else None, rows, row_offset, cols,
-                                        F, Hp, Wp, c_out, eps, arr, len(ptrs), prep.ptr, prep.nbytes, 1 if round_sum_to_bf16 else 0, _stream()))
+        if step is None:
+            check(lib.mc_head_unpatchify_ex(x.data_ptr(), _dt(x), rptr, rows, row_offset, cols, F, Hp, Wp, c_out, eps, arr, len(ptrs), prep.ptr,
+                                            prep.nbytes, 1 if round_sum_to_bf16 else 0, _stream()))
+        else:
+            cond, x_lat, g, cx, cv = step
+            for t_ in (cond, x_lat):
+                assert t_.dtype == torch.float32 and t_.is_contiguous() and t_.numel() == out.numel() and t_.device == x.device
+            check(lib.mc_head_unpatchify_step(x.data_ptr(), _dt(x), rptr, rows, row_offset, cols, F, Hp, Wp, c_out, eps, arr, len(ptrs), prep.ptr,
+                                              prep.nbytes, 1 if round_sum_to_bf16 else 0, cond.data_ptr(), x_lat.data_ptr(), float(g), float(cx),
+                                              float(cv), _stream()))
     _count()
     return out
 

@@ -27,6 +27,27 @@ def sampling_sigmas(steps, shift):
     return out
 
 
+def cfg_denoise_step(model, x, t, context, context_null, seq_len, guide_scale, coef_v, coef_x=1.0, forward=None, **kw):
+    """`x <- coef_x * x + coef_v * (uncond + g * (cond - uncond))` with both predictions from the patched forward of `model`
+    (SURVEY §8f rank 1 as written). On the unsharded Wan engine the combine and the update ride in the epilogue of the unconditional
+    call's head kernel (`mc_head_unpatchify_step`): the unconditional prediction is never written, no separate pass over the
+    latents runs — on a step where both calls hit the cache the whole step is two streaming head launches. Token-sharded engines
+    (whose head stores go to every peer) and multistep solvers that keep history terms use `ops.cfg_step` after the two calls.
+    Bit-equal either way. `forward(x, t, context) -> prediction` replaces the plain `model([x], t=..., context=[...])` call (a
+    caller that wraps its forwards, e.g. with timing events)."""
+    from .patch import _engine
+    if forward is None:
+        def forward(xx, tt, cc):
+            return model([xx], t=tt, context=[cc], seq_len=seq_len, **kw)[0]
+    cond = forward(x, t, context)
+    eng = _engine(model)
+    if getattr(eng, "shard", None) is None and hasattr(eng, "arm_step"):
+        eng.arm_step(cond, x, guide_scale, coef_x, coef_v, out=x)
+        return forward(x, t, context_null)
+    uncond = forward(x, t, context_null)
+    return ops.cfg_step(cond, uncond, guide_scale, x, coef_v, coef_x=coef_x, out=x)
+
+
 class FlowEulerSampler:
     """x <- x + (sigma_{i+1} - sigma_i) * v : one launch per step, in place."""
 
@@ -42,6 +63,13 @@ class FlowEulerSampler:
         d = self.sigmas[self.i + 1] - self.sigmas[self.i]
         self.i += 1
         return ops.cfg_step(cond, uncond, guide_scale, x, d, out=x)
+
+    def denoise(self, model, x, t, context, context_null, seq_len, guide_scale, **kw):
+        """One whole step of the caller loop (wan_magcache.py:296-310): cond call, uncond call, CFG combine, scheduler update; the
+        latent `x` [C, F, H, W] is updated in place and returned. `model` carries the patched forward (`init_magcache`)."""
+        d = self.sigmas[self.i + 1] - self.sigmas[self.i]
+        self.i += 1
+        return cfg_denoise_step(model, x, t, context, context_null, seq_len, guide_scale, coef_v=d, **kw)
 
 
 class FlowUniPCSampler:

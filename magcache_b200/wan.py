@@ -257,6 +257,7 @@ class WanEngine:
         self.xch = None  # K|V exchange of a token-sharded engine (shard.py)
         self._slot = 0   # CFG slot of the forward in flight (selects the output window of a sharded engine)
         self.hit_sum_bf16 = False  # TeaCache comparator: the hit sum is rounded to bf16 before the head (wan_teacache.py:569/577)
+        self._step = None          # (cond, x_latent, guide_scale, coef_x, coef_v, out) armed by `arm_step` for the next forward
 
     # ------------------------------------------------------------------------------------------ workspace
     def _workspace(self, n_total, pad_row=0):
@@ -417,12 +418,24 @@ class WanEngine:
         ops.residual_sub(xs, x0, out=self.res[slot])  # magcache_generate.py:299, written into the slot's fixed buffer
         return self.head(xs, e, self.grid)
 
+    def arm_step(self, cond, x_latent, guide_scale, coef_x, coef_v, out=None):
+        """Fold the caller loop's CFG combine + scheduler update (eval/.../wan_magcache.py:301-310) into the head pass of the NEXT
+        forward, which must be the unconditional call of the step whose conditional prediction is `cond`: that forward then returns
+        `coef_x * x_latent + coef_v * (uncond + guide_scale * (cond - uncond))` (written into `out`, which may be `x_latent` itself)
+        instead of the unconditional prediction. One-shot; bit-equal to the plain forward followed by `ops.cfg_step`."""
+        if self.shard is not None:
+            raise NotImplementedError("magcache_b200: the fused step is built for the unsharded engine (sharded runs use ops.cfg_step)")
+        self._step = (cond, x_latent, float(guide_scale), float(coef_x), float(coef_v), out)
+
     def forward(self, kind, slot):
         """Run (or replay) one forward of the given kind for CFG slot `slot`; returns a fresh fp32 [C, F, H, W] tensor."""
         if kind == "hit" and not self.res_valid[slot]:
             raise TypeError("magcache_b200: cache hit with an empty residual_cache slot (reference: Tensor + NoneType)")
-        if not self.use_graphs:
-            out = self._body(kind, slot)
+        if not self.use_graphs or self._step is not None:  # an armed step carries per-step scalars: never captured
+            try:
+                out = self._body(kind, slot)
+            finally:
+                self._step = None
         else:
             key = (kind, slot, self.hit_sum_bf16)
             st = self._graphs.get(key)
@@ -544,6 +557,8 @@ class WanEngine:
                 x = x[:self.n_keys]
                 if residual is not None:
                     kw["residual"] = residual[:self.n_keys]
+            if self._step is not None:
+                kw["step"], kw["out"] = self._step[:5], self._step[5]
             return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, **kw)
         self.xch.join()  # every push of this forward is ordered before its end (and inside a captured graph)
         out, peer_outs = self.xch.head_output(self._slot)

@@ -228,7 +228,7 @@ def head_prepare(head_mod, e, w_t, b, tag=None):
 
 
 def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1e-6, tag=None, row_offset=0, out=None, round_sum_to_bf16=False,
-                    peer_outs=None, prep=None):
+                    peer_outs=None, prep=None, step=None):
     assert (x.dtype == F32 and residual is None) or (x.dtype == BF and residual is not None), "fp32 stream, or bf16 + fp32 residual"
     assert x.shape[1] % 64 == 0, "mc_head_unpatchify: cols % 64"
     xs = x.to(F32) + (residual if residual is not None else 0.0)
@@ -244,6 +244,12 @@ def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1
         o = full
     u = o.view(f, h, w, 1, 2, 2, c_out)
     u = torch.einsum("fhwpqrc->cfphqwr", u).reshape(c_out, f, 2 * h, 2 * w).contiguous()
+    if step is not None:  # mc_head_unpatchify_step: the caller loop's CFG combine + scheduler update in the epilogue (full token range)
+        assert o.shape[0] == f * h * w
+        cond, x_lat, g, cx, cv = step
+        t32 = lambda a: torch.tensor(a, dtype=F32)  # noqa: E731
+        v = u + t32(g) * (cond - u)
+        u = t32(cx) * x_lat + t32(cv) * v
     _count()
     if out is not None:
         out.copy_(u)

@@ -71,6 +71,33 @@ def test_magcache_generation_loop(emulated, solver):
     assert bool(torch.isfinite(x).all())
 
 
+def test_fused_step_equals_two_calls_plus_cfg_step(emulated):
+    """`FlowEulerSampler.denoise` (SURVEY §8f-1 as written: CFG combine + scheduler update in the epilogue of the unconditional
+    call's head, `mc_head_unpatchify_step`) walks the same hit / miss sequence and produces the same latents, bit for bit, as the
+    two patched-forward calls followed by `cfg_step` — over a whole schedule with hits and misses, latent updated in place."""
+    steps, guide = 10, 5.0
+    table = mc.tables()["wan2.1_t2v_1.3b"]
+    inst = lambda m: mc.init_magcache(m, steps, thresh=0.12, K=2, retention_ratio=0.2, mag_ratios=table)  # noqa: E731
+    a_model, b_model = _models(lambda c: None, inst)[1], _models(lambda c: None, inst)[1]
+    g = torch.Generator().manual_seed(2)
+    lat = torch.randn(16, 2, 8, 8, generator=g)
+    ctx, ctx_null = torch.randn(9, 128, generator=g), torch.randn(7, 128, generator=g)
+    sig = mc.sampling_sigmas(steps, 5.0)
+    sa, sb = mc.FlowEulerSampler(sig), mc.FlowEulerSampler(sig)
+    xa, xb = lat.clone(), lat.clone()
+    with torch.no_grad():
+        for i in range(steps):
+            t = torch.tensor([sa.timestep], dtype=torch.float32)
+            cond = a_model([xa], t=t, context=[ctx], seq_len=32)[0]
+            uncond = a_model([xa], t=t, context=[ctx_null], seq_len=32)[0]
+            xa = sa.step(cond, uncond, guide, xa)
+            out = sb.denoise(b_model, xb, t, ctx, ctx_null, 32, guide)
+            assert out.data_ptr() == xb.data_ptr()  # in place
+            assert torch.equal(xa, xb), i
+            assert a_model.cnt == b_model.cnt and a_model.accumulated_err == b_model.accumulated_err
+    assert b_model._mc_engine._step is None
+
+
 def test_teacache_generation_loop(emulated):
     steps, coef = 8, [0.02, 0.04, 0.0]
     ref, ours = _models(lambda c: wan_ref.install_teacache(c, steps, 0.08, coef), lambda m: mc.init_teacache(m, steps, teacache_thresh=0.08, coefficients=coef))

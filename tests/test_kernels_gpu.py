@@ -310,6 +310,40 @@ def test_rmsnorm_rope(rows, cols, heads, rope):
     assert nbad <= 1e-4 * view.numel(), (nbad, maxerr)
 
 
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("grid", [(3, 5, 7), (5, 30, 52)])
+def test_head_step_epilogue_equals_head_then_cfg_step_bitwise(fused, grid):
+    """`mc_head_unpatchify_step` (CFG combine + scheduler update in the head's epilogue) == `mc_head_unpatchify_ex`
+    followed by `mc_cfg_step`, bit for bit, for the stream form and the cache-hit form, out of place and with the latent updated
+    in place."""
+    ops = _ops()
+    F, Hp, Wp = grid
+    D = 1536
+    rows = F * Hp * Wp
+    g = torch.Generator(device=DEV).manual_seed(rows + int(fused))
+    head_mod = torch.randn(1, 2, D, device=DEV, generator=g) / math.sqrt(D)
+    e = torch.randn(1, D, device=DEV, generator=g) * 0.3
+    wt = (torch.randn(D, 64, device=DEV, generator=g) * 0.05).contiguous()
+    b = torch.randn(64, device=DEV, generator=g) * 0.1
+    if fused:
+        x = torch.randn(rows, D, device=DEV, generator=g).bfloat16()
+        kw = dict(residual=torch.randn(rows, D, device=DEV, generator=g) * 0.3)
+    else:
+        x = torch.randn(rows, D, device=DEV, generator=g) * 2
+        kw = {}
+    cond = torch.randn(16, F, 2 * Hp, 2 * Wp, device=DEV, generator=g)
+    lat = torch.randn(16, F, 2 * Hp, 2 * Wp, device=DEV, generator=g)
+    gs, cx, cv = 5.0, 1.0, -0.0371
+    uncond = ops.head_unpatchify(x, head_mod, e, wt, b, grid, **kw)
+    want = ops.cfg_step(cond, uncond, gs, lat, cv, coef_x=cx)
+    got = ops.head_unpatchify(x, head_mod, e, wt, b, grid, step=(cond, lat, gs, cx, cv), **kw)
+    assert torch.equal(got, want)
+    lat2 = lat.clone()
+    got2 = ops.head_unpatchify(x, head_mod, e, wt, b, grid, step=(cond, lat2, gs, 0.9, cv), out=lat2, **kw)
+    assert got2.data_ptr() == lat2.data_ptr()
+    assert torch.equal(lat2, ops.cfg_step(cond, uncond, gs, lat, cv, coef_x=0.9))
+
+
 def test_linear_f32_small_and_time_path():
     ops = _ops()
     t = torch.tensor([999.0, 417.25], device=DEV)

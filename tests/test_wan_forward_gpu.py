@@ -270,6 +270,39 @@ def test_magcache_loop_mask_cache_and_outputs():
     assert ours_model.cnt == 0  # wrapped around after num_steps calls
 
 
+def test_fused_denoise_step_equals_two_calls_plus_cfg_step():
+    """SURVEY §8f-1 as written: `FlowEulerSampler.denoise` (cond call, then the unconditional call whose head epilogue applies the
+    CFG combine and the Euler update, `mc_head_unpatchify_step`) against the two patched-forward calls + `mc_cfg_step`, over a
+    schedule with hits and misses: same hit / miss sequence, latents bit-equal every step, latent updated in place."""
+    import magcache_b200 as mc
+    from magcache_b200 import ops
+    wan_ref, model = build("tiny")
+    steps, guide = 10, 5.0
+    kw = dict(thresh=0.12, K=2, retention_ratio=0.2)
+    a_model = install_ours(copy.deepcopy(model).to(DEV), steps, **kw)
+    b_model = install_ours(copy.deepcopy(model).to(DEV), steps, **kw)
+    lat, ctx, ctx_null = (v.to(DEV) for v in make_inputs(4))
+    n_tok = lat.shape[1] * (lat.shape[2] // 2) * (lat.shape[3] // 2)
+    sig = mc.sampling_sigmas(steps, 5.0)
+    sa, sb = mc.FlowEulerSampler(sig), mc.FlowEulerSampler(sig)
+    xa, xb = lat.clone(), lat.clone()
+    launches = []
+    with torch.no_grad():
+        for i in range(steps):
+            t = torch.tensor([sa.timestep], dtype=torch.float32, device=DEV)
+            cond = a_model([xa], t=t, context=[ctx], seq_len=n_tok)[0]
+            uncond = a_model([xa], t=t, context=[ctx_null], seq_len=n_tok)[0]
+            xa = sa.step(cond, uncond, guide, xa)
+            n0 = ops.LAUNCHES
+            out = sb.denoise(b_model, xb, t, ctx, ctx_null, n_tok, guide)
+            launches.append(ops.LAUNCHES - n0)
+            assert out.data_ptr() == xb.data_ptr()
+            assert torch.equal(xa, xb), i
+            for attr in ("cnt", "accumulated_ratio", "accumulated_err", "accumulated_steps"):
+                assert getattr(a_model, attr) == getattr(b_model, attr), attr
+    assert min(launches) < 40 < max(launches)  # steps where both calls hit the cache: two prologues + two head launches
+
+
 def test_eval_variant_loop_vs_oracle():
     """`magcache_eval_forward` (eval/magcache/experiments/Wan2.1_EVAL/wan_magcache.py:682-817, the code behind the paper's Wan2.1
     rows) for one whole 50-step video: identical hit/miss sequence (62 of 100 skipped at 0.12 / K4), float64 accumulators bit-equal,

@@ -30,3 +30,27 @@ for name, fn, nbytes in (("hit", lambda s: ops.head_unpatchify(s[0], hm, e, wt, 
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 12
     print(f"head {name}: {ms * 1e3:.1f} us per call (prep + main), {nbytes / ms / 1e6:.0f} GB/s", flush=True)
+
+# the caller step on a cache-hit step: two hit heads + mc_cfg_step  vs  hit head + hit head with the step in its epilogue
+F, Hp, Wp = grid
+lat = torch.randn(16, F, 2 * Hp, 2 * Wp, device="cuda", generator=g)
+prep = ops.head_prepare(hm, e, wt, b)
+def unfused():
+    c = ops.head_unpatchify(sets[0][0], hm, e, wt, b, grid, residual=sets[0][1], prep=prep)
+    u = ops.head_unpatchify(sets[1][0], hm, e, wt, b, grid, residual=sets[1][1], prep=prep)
+    ops.cfg_step(c, u, 5.0, lat, -0.02, out=lat)
+def fused():
+    c = ops.head_unpatchify(sets[0][0], hm, e, wt, b, grid, residual=sets[0][1], prep=prep)
+    ops.head_unpatchify(sets[1][0], hm, e, wt, b, grid, residual=sets[1][1], prep=prep, step=(c, lat, 5.0, 1.0, -0.02), out=lat)
+for rnd in range(2):
+    for name, fn in (("two heads + cfg_step", unfused), ("head + head-with-step", fused)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"hit step, {name}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us")
