@@ -388,8 +388,13 @@ def run_ours(args, rank, world):
     if "head_hit_fused" in kern:
         n_loc = N_TOK // world
         hb = n_loc * D * 6 + n_loc * 64 * 4
+        if world == 1:
+            # one GPU: every second hit launch (the unconditional call) also carries the caller step in its epilogue and reads the
+            # conditional prediction and the latent at its output positions (2 x n x 256 B): the mean over the launches
+            hb += n_loc * 64 * 4
         gbs = hb / (kern["head_hit_fused"]["ms_avg"] * 1e-3) / 1e9
-        hit_path = {"kernel": "head_prep_kernel + head_tc_kernel<hit> (cache-hit add + LN + modulate + Linear + unpatchify, one pass)", "bound": "hbm",
+        hit_path = {"kernel": "head_tc_kernel<hit> (cache-hit add + LN + modulate + Linear + unpatchify, one pass; one GPU: + CFG combine and "
+                              "scheduler update in the epilogue of the unconditional call)", "bound": "hbm",
                     "algorithmic_bytes": hb, "ms": kern["head_hit_fused"]["ms_avg"], "achieved": gbs, "unit": "GB/s", "peak": pk["hbm_gbs"],
                     "frac": gbs / pk["hbm_gbs"], "frac_of_8TBps": gbs / 8000.0, "peak_source": pk["src"], "measured": roofline_source}
     # the stand-alone `x + residual_x` kernel (FLUX / HunyuanVideo hit branch, VACE): a micro-benchmark, NOT on the Wan hit path above
