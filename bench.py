@@ -208,7 +208,7 @@ def run_reference_arm(args, rank):
     t_miss_small, t_hit = statistics.median(tm), statistics.median(th)
     value, sec_video, t_miss = cpu_extrapolate(t_miss_small, t_hit)
     sample = cpu_sample_text(len(tm), cores, t_miss_small, t_hit, t_miss, sec_video)
-    line = {"metric": "denoising_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": 0, "steps": len(tm), "warmup": min(args.warmup, 1),
+    line = {"metric": "denoising_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": len(tm), "warmup": min(args.warmup, 1),
             "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "impl": "reference", "sec_per_video": sec_video,
             "config": {"workload": "Wan2.1-T2V-1.3B 832x480x81f, 50 steps, MagCache E012K4R02 (BASELINE configs[1])", "tokens": N_TOK,
