@@ -12,6 +12,11 @@
 //                             the K = 1536 GEMMs were epilogue-bound: ~12 us of dependent load/store per tile against a
 //                             6.4 us main loop.)
 // Tiles are walked in waves of gridDim.x consecutive tiles with N fastest: the CTAs of one wave share A row-panels in L2.
+// A second instantiation with 128-wide N tiles serves grids whose last wave would otherwise be mostly empty (a token-sharded
+// rank's 4095 x 1536 output is 192 tiles of 128 x 256 on 148 SMs — two waves at 65 % — but 384 tiles of 128 x 128 — three half-cost
+// waves): launch_gemm picks it when the wave count says it is at least 8 % cheaper.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
@@ -27,18 +32,21 @@ std::mutex& tmap_cache_mutex() {
   return m;
 }
 
-constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 4;
+constexpr int kBM = 128, kBK = 64, kStages = 4;
 constexpr int kTileABytes = kBM * kBK * 2;  // 16 KB
-constexpr int kTileBBytes = kBN * kBK * 2;  // 32 KB
-constexpr int kStageBytes = kTileABytes + kTileBBytes;
 constexpr int kStagePad = 33;                                 // floats per staged row (conflict-free transpose)
 constexpr int kEpiWarps = 8;
 constexpr int kStagingBytes = kEpiWarps * 32 * kStagePad * 4;  // one 32x32 fp32 patch per epilogue warp
-constexpr int kOffStaging = kStages * kStageBytes;            // 196608
-constexpr int kOffBars = kOffStaging + kStagingBytes;         // + 33792
-constexpr int kGemmSmem = kOffBars + 128;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
-constexpr int kTmemCols = 512;  // 2 accumulators x 256 fp32 columns
+template <int BN>
+struct GemmTile {  // BN = 256 (default) or 128
+  static constexpr int kTileBBytes = BN * kBK * 2;                 // 32 / 16 KB
+  static constexpr int kStageBytes = kTileABytes + kTileBBytes;
+  static constexpr int kOffStaging = kStages * kStageBytes;        // 196608 / 131072
+  static constexpr int kOffBars = kOffStaging + kStagingBytes;     // + 33792
+  static constexpr int kSmem = kOffBars + 128;
+  static constexpr int kTmemCols = 2 * BN;                         // 2 accumulators x BN fp32 columns
+};
 
 struct GemmParams {
   int M, N, K;
@@ -179,9 +187,11 @@ __device__ __forceinline__ void epilogue_patch(const GemmParams& p, const float*
   }
 }
 
-template <int EPI>
+template <int EPI, int kBN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using T = GemmTile<kBN>;
+  constexpr int kStageBytes = T::kStageBytes, kOffStaging = T::kOffStaging, kOffBars = T::kOffBars, kTmemCols = T::kTmemCols;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* staging = reinterpret_cast<float*>(smem + kOffStaging);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -300,17 +310,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <int EPI>
-static int32_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+template <int EPI, int BN>
+static int32_t launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
   static PerDeviceOnce once;
-  const int32_t rc = set_max_smem_once(gemm_bf16_kernel<EPI>, kGemmSmem, once, "cudaFuncSetAttribute(gemm smem)");
+  const int32_t rc = set_max_smem_once(gemm_bf16_kernel<EPI, BN>, GemmTile<BN>::kSmem, once, "cudaFuncSetAttribute(gemm smem)");
   if (rc) return rc;
-  const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + kBN - 1) / kBN;
+  const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_bf16_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, p);
+  gemm_bf16_kernel<EPI, BN><<<grid, kGemmThreads, GemmTile<BN>::kSmem, s>>>(ta, tb, p);
   MC_CHECK_LAUNCH("gemm_bf16_kernel launch");
   return MC_OK;
+}
+
+// N-tile width for an M x N output: waves of 148 tiles; a wave of 128-wide tiles costs half a wave of 256-wide ones (and moves the
+// same A panel for half the math, hence the margin). MC_GEMM_BN = 128 | 256 forces one (tests, A/B timing).
+static int pick_bn(int M, int N) {
+  const char* e = getenv("MC_GEMM_BN");
+  if (e && *e) {
+    const int v = atoi(e);
+    if (v == 128 || v == 256) return v;
+  }
+  const int64_t sms = num_sms(), m_tiles = (M + kBM - 1) / kBM;
+  const int64_t t256 = m_tiles * ((N + 255) / 256), t128 = m_tiles * ((N + 127) / 128);
+  const int64_t cost256 = ((t256 + sms - 1) / sms) * 2, cost128 = (t128 + sms - 1) / sms;
+  return cost128 * 100 <= cost256 * 92 ? 128 : 256;
 }
 
 }  // namespace mc
@@ -325,19 +349,23 @@ extern "C" int32_t mc_gemm_bf16(const void* A, int64_t lda, const void* B, int64
   CUtensorMap ta, tb;
   int32_t rc = mc::make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), mc::kBM, mc::kBK);
   if (rc) return rc;
-  rc = mc::make_tmap_bf16_2d(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), mc::kBN, mc::kBK);
+  const int bn = mc::pick_bn(M, N);
+  rc = mc::make_tmap_bf16_2d(&tb, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), bn, mc::kBK);
   if (rc) return rc;
   mc::GemmParams p{M, N, K, bias, out, ldo, gate};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define MC_GEMM_CASE(E) \
+  case E: return bn == 128 ? mc::launch_gemm_bn<E, 128>(ta, tb, p, s) : mc::launch_gemm_bn<E, 256>(ta, tb, p, s)
   switch (epilogue) {
-    case MC_EPI_BIAS_BF16: return mc::launch_gemm<MC_EPI_BIAS_BF16>(ta, tb, p, s);
-    case MC_EPI_BIAS_GELU_BF16: return mc::launch_gemm<MC_EPI_BIAS_GELU_BF16>(ta, tb, p, s);
-    case MC_EPI_BIAS_GATE_RESID: return mc::launch_gemm<MC_EPI_BIAS_GATE_RESID>(ta, tb, p, s);
-    case MC_EPI_ROWBIAS_BF16: return mc::launch_gemm<MC_EPI_ROWBIAS_BF16>(ta, tb, p, s);
-    case MC_EPI_BIAS_F32: return mc::launch_gemm<MC_EPI_BIAS_F32>(ta, tb, p, s);
-    case MC_EPI_BIAS_GELU_ERF_BF16: return mc::launch_gemm<MC_EPI_BIAS_GELU_ERF_BF16>(ta, tb, p, s);
-    case MC_EPI_BIAS_GATE_RESID_BF16: return mc::launch_gemm<MC_EPI_BIAS_GATE_RESID_BF16>(ta, tb, p, s);
-    case MC_EPI_BIAS_SILU_BF16: return mc::launch_gemm<MC_EPI_BIAS_SILU_BF16>(ta, tb, p, s);
+    MC_GEMM_CASE(MC_EPI_BIAS_BF16);
+    MC_GEMM_CASE(MC_EPI_BIAS_GELU_BF16);
+    MC_GEMM_CASE(MC_EPI_BIAS_GATE_RESID);
+    MC_GEMM_CASE(MC_EPI_ROWBIAS_BF16);
+    MC_GEMM_CASE(MC_EPI_BIAS_F32);
+    MC_GEMM_CASE(MC_EPI_BIAS_GELU_ERF_BF16);
+    MC_GEMM_CASE(MC_EPI_BIAS_GATE_RESID_BF16);
+    MC_GEMM_CASE(MC_EPI_BIAS_SILU_BF16);
+#undef MC_GEMM_CASE
     default:
       mc::set_error("mc_gemm_bf16: unknown epilogue %d", epilogue);
       return MC_ERR_INVALID;

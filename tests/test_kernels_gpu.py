@@ -459,9 +459,13 @@ def _gemm_ref(a, b):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (256, 384, 1536), (300, 200, 512), (1000, 1536, 1536), (517, 8960, 1536),
-                                    (777, 1536, 8960), (64, 64, 64), (512, 1536, 4096), (333, 1536, 64)])
-def test_gemm_bias_bf16(M, N, K):
+                                    (777, 1536, 8960), (64, 64, 64), (512, 1536, 4096), (333, 1536, 64),
+                                    (4095, 1536, 1536)])  # a token-sharded rank's o-projection: 192 wide tiles / 384 narrow ones
+@pytest.mark.parametrize("bn", [0, 128, 256])  # 0: the launcher's choice by wave count; else the N-tile width forced (MC_GEMM_BN)
+def test_gemm_bias_bf16(M, N, K, bn, monkeypatch):
     ops, L = _ops(), _lib()
+    if bn:
+        monkeypatch.setenv("MC_GEMM_BN", str(bn))
     a = torch.randn(M, K, device=DEV).bfloat16()
     b = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device=DEV).bfloat16().float()
@@ -474,8 +478,10 @@ def test_gemm_bias_bf16(M, N, K):
     assert torch.allclose(out32, ref, rtol=1e-3, atol=1e-4), float((out32 - ref).abs().max())
 
 
-def test_gemm_epilogues():
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_epilogues(bn, monkeypatch):
     ops, L = _ops(), _lib()
+    monkeypatch.setenv("MC_GEMM_BN", str(bn))
     M, N, K = 391, 640, 1536
     a = torch.randn(M, K, device=DEV).bfloat16()
     b = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
