@@ -12,9 +12,11 @@
 //                             the K = 1536 GEMMs were epilogue-bound: ~12 us of dependent load/store per tile against a
 //                             6.4 us main loop.)
 // Tiles are walked in waves of gridDim.x consecutive tiles with N fastest: the CTAs of one wave share A row-panels in L2.
-// A second instantiation with 128-wide N tiles serves grids whose last wave would otherwise be mostly empty (a token-sharded
-// rank's 4095 x 1536 output is 192 tiles of 128 x 256 on 148 SMs — two waves at 65 % — but 384 tiles of 128 x 128 — three half-cost
-// waves): launch_gemm picks it when the wave count says it is at least 8 % cheaper.
+// A second instantiation with 128-wide N tiles serves small grids (the text K|V projection: 512 x 3072 is 48 wide tiles on 148
+// SMs, 96 narrow ones: 21 -> 18 us). A narrow tile is NOT half the cost of a wide one — the same A panel moves for half the math and
+// the operands sit at the 128 B/clk fetch limit: measured 0.62-0.65 — so for the ragged grids of a token-sharded rank (4095 x 1536:
+// two wide waves at 65 % against three narrow ones) it gains 6 % at K = 1536 and LOSES 18 % at K = 8960; pick_bn's cost model
+// therefore only takes it where the wave count makes it at least 8 % cheaper at 0.62 per wave.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -323,8 +325,8 @@ static int32_t launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, cons
   return MC_OK;
 }
 
-// N-tile width for an M x N output: waves of 148 tiles; a wave of 128-wide tiles costs half a wave of 256-wide ones (and moves the
-// same A panel for half the math, hence the margin). MC_GEMM_BN = 128 | 256 forces one (tests, A/B timing).
+// N-tile width for an M x N output: waves of 148 tiles, a wave of 128-wide tiles at 0.62 of a wave of 256-wide ones (measured, see
+// the header). MC_GEMM_BN = 128 | 256 forces one (tests, A/B timing).
 static int pick_bn(int M, int N) {
   const char* e = getenv("MC_GEMM_BN");
   if (e && *e) {
@@ -333,7 +335,7 @@ static int pick_bn(int M, int N) {
   }
   const int64_t sms = num_sms(), m_tiles = (M + kBM - 1) / kBM;
   const int64_t t256 = m_tiles * ((N + 255) / 256), t128 = m_tiles * ((N + 127) / 128);
-  const int64_t cost256 = ((t256 + sms - 1) / sms) * 2, cost128 = (t128 + sms - 1) / sms;
+  const int64_t cost256 = ((t256 + sms - 1) / sms) * 100, cost128 = ((t128 + sms - 1) / sms) * 62;
   return cost128 * 100 <= cost256 * 92 ? 128 : 256;
 }
 
