@@ -125,8 +125,11 @@ class MMDiTCore:
 
     def _alloc_core(self, n_img, n_txt):
         """Buffers for one (image tokens, text tokens) shape. Token-sharded (`self.world > 1`): the IMAGE rows are split over
-        the ranks, the (few) text rows are replicated — every rank carries all of them and computes the identical text stream — and per
-        attention the image K / V rows are all-gathered into the full-length K / V buffers (text rows copied in locally)."""
+        the ranks, the (few) text rows are replicated — every rank carries all of them and computes the identical text stream. Per
+        attention the K|V rows of a rank's image tokens travel through the same exchange as the Wan engine's (`shard.make_exchange`:
+        copy-engine pushes into every peer's gathered buffer, consumed segment by segment inside the attention kernel; or the
+        all-gather formulation), and the text K|V rows are written locally behind the image rows of the gathered buffer — the key
+        order [image | text] differs from the unsharded engine's, which a softmax over keys cannot see."""
         D, dev = self.w.dim, self.device
         bf = dict(dtype=torch.bfloat16, device=dev)
         self.n_img_total, self.n_txt = n_img, n_txt
@@ -152,8 +155,10 @@ class MMDiTCore:
             self.qk = torch.empty(S, 2 * D, **bf)
             self.v = torch.empty(S, D, **bf)   # row-major V: the attention kernel consumes it as is (MN-major B operand)
         else:
-            self.q_loc, self.k_loc, self.v_loc = torch.empty(S, D, **bf), torch.empty(S, D, **bf), torch.empty(S, D, **bf)
-            self.k_all, self.v_all = torch.empty(Sg, D, **bf), torch.empty(Sg, D, **bf)
+            from .shard import make_exchange
+            self.q_loc, self.k_loc = torch.empty(S, D, **bf), torch.empty(S, D, **bf)  # k_loc: the text refiner's own (local) keys
+            self.xch = make_exchange(self.shard, 2 * D, (1,), dev, extra_rows=n_txt)
+            self._xi, self._kv_cur = 0, None
         self.cat = torch.empty(S, 5 * D, **bf)
         self.ada = torch.empty(1, self.w.ada_rows, **bf)
         self.adaf = torch.empty(self.w.ada_rows, dtype=torch.float32, device=dev)
@@ -178,10 +183,20 @@ class MMDiTCore:
     def _project(self, rows, h_rows, qk_w, qk_b, v_w, v_b):
         """q | k and V projections of the token range `rows` from its LN+modulate output."""
         D = self.w.dim
-        if self.shard is not None:  # separate contiguous q / k / v buffers: k and v rows are sent to the other ranks
+        if self.shard is not None:
+            # K | V straight into the exchange's gathered buffer: image rows into this rank's segment (pushed to the peers by
+            # `_joint_attention`), text rows into the local tail; q stays local
+            own, tail = self._kv_views()
             ops.gemm(h_rows, qk_w[:D], qk_b[:D], E.MC_EPI_BIAS_BF16, out=self.q_loc[rows])
-            ops.gemm(h_rows, qk_w[D:], qk_b[D:], E.MC_EPI_BIAS_BF16, out=self.k_loc[rows])
-            ops.gemm(h_rows, v_w, v_b, E.MC_EPI_BIAS_BF16, out=self.v_loc[rows])
+            if rows == self.img:
+                parts = ((h_rows, own),)
+            elif rows == self.txt:
+                parts = ((h_rows, tail),)
+            else:  # the whole local sequence (single-stream blocks)
+                parts = ((h_rows[self.img], own), (h_rows[self.txt], tail))
+            for hp, dst in parts:
+                ops.gemm(hp, qk_w[D:], qk_b[D:], E.MC_EPI_BIAS_BF16, out=dst[:, :D])
+                ops.gemm(hp, v_w, v_b, E.MC_EPI_BIAS_BF16, out=dst[:, D:])
             return
         ops.gemm(h_rows, qk_w, qk_b, E.MC_EPI_BIAS_BF16, out=self.qk[rows])
         ops.gemm(h_rows, v_w, v_b, E.MC_EPI_BIAS_BF16, out=self.v[rows])
@@ -190,22 +205,28 @@ class MMDiTCore:
         """Per-head RMSNorm of q and k (+ RoPE where the family applies it), in place."""
         D, H = self.w.dim, self.w.heads
         rope = self._rope_for(rows)
-        q, k = (self.q_loc[rows], self.k_loc[rows]) if self.shard is not None else (self.qk[rows][:, :D], self.qk[rows][:, D:])
+        if self.shard is not None:
+            own, tail = self._kv_views()
+            q, k = self.q_loc[rows], (own if rows == self.img else tail)[:, :D]
+        else:
+            q, k = self.qk[rows][:, :D], self.qk[rows][:, D:]
         ops.rmsnorm_head_rope_(q, nq, H, rope)
         ops.rmsnorm_head_rope_(k, nk, H, rope)
+
+    def _kv_views(self):
+        """(this rank's image segment, the local text tail) of the gathered K|V buffer the NEXT joint attention reads, [rows, 2 D]."""
+        if self._kv_cur is None:
+            self._kv_cur = (self.xch.own_rows(self._xi), self.xch.tail_rows(self._xi))
+        return self._kv_cur
 
     def _joint_attention(self, out):
         D, H = self.w.dim, self.w.heads
         if self.shard is not None:
-            from .shard import gather_rows
-            # image K / V rows of every rank -> the image block of the full-length buffers; the replicated text rows are copied in
-            wk = gather_rows(self.k_loc[self.img], self.k_all[self.img_g], self.shard.group, async_op=True)
-            wv = gather_rows(self.v_loc[self.img], self.v_all[self.img_g], self.shard.group, async_op=True)
-            self.k_all[self.txt_g].copy_(self.k_loc[self.txt])
-            self.v_all[self.txt_g].copy_(self.v_loc[self.txt])
-            wk.wait()
-            wv.wait()
-            ops.attention(self.q_loc, self.k_all, self.v_all, H, out=out, tag="mmdit_attn")
+            xi = self._xi
+            self.xch.begin(xi)  # this rank's normalised image K|V rows start travelling to the peers
+            kv_all, kw = self.xch.keys_values(xi)
+            ops.attention(self.q_loc, kv_all[:, :D], kv_all[:, D:], H, out=out, tag="mmdit_attn", **kw)
+            self._xi, self._kv_cur = xi ^ 1, None
             return
         ops.attention(self.qk[:, :D], self.qk[:, D:], self.v, H, out=out, tag="mmdit_attn")
 
@@ -272,6 +293,8 @@ class MMDiTCore:
         else:
             self.hs[self.img].copy_(x0)                                           # `ori_hidden_states` / `ori_img` stays in x0
             x = self.run_blocks()
+            if self.shard is not None:
+                self.xch.join()  # every push of this forward is ordered before its end
             ops.residual_sub(x.contiguous(), x0, out=self.res)                    # :426 ; :140 (x is a contiguous row range of hs)
             self.res_valid = True
         return self.head(x)

@@ -99,23 +99,28 @@ class CollectiveExchange:
 
     p2p = False
 
-    def __init__(self, shard: TokenShard, width, out_shape, device):
-        self.sh, self.device, self.out_shape = shard, device, tuple(out_shape)
+    def __init__(self, shard: TokenShard, width, out_shape, device, extra_rows=0):
+        assert extra_rows == 0 or shard.pad == 0, "locally written tail rows follow the token rows directly: no pad slots in between"
+        self.sh, self.device, self.out_shape, self.extra = shard, device, tuple(out_shape), extra_rows
         bf = dict(dtype=torch.bfloat16, device=device)
         self.kv_loc = torch.zeros(shard.n_slots, width, **bf)          # pad slots stay zero
-        self.kv_all = torch.empty(shard.n_padded, width, **bf)
+        self.kv_all = torch.empty(shard.n_padded + extra_rows, width, **bf)
         self._work = None
 
     def own_rows(self, i):
         return self.kv_loc[:self.sh.n_local]
 
+    def tail_rows(self, i):
+        """The `extra_rows` key rows behind the token rows that every rank writes for itself (MMDiT: the replicated text tokens)."""
+        return self.kv_all[self.sh.n_padded:]
+
     def begin(self, i):
-        self._work = gather_rows(self.kv_loc, self.kv_all, self.sh.group, async_op=True)
+        self._work = gather_rows(self.kv_loc, self.kv_all[:self.sh.n_padded], self.sh.group, async_op=True)
 
     def keys_values(self, i):
-        """(gathered [N, width] view, extra keyword arguments for ops.attention). Blocks the stream until the rows are there."""
+        """(gathered [N (+ extra), width] view, extra keyword arguments for ops.attention). Blocks the stream until the rows are there."""
         self._work.wait()
-        return self.kv_all[:self.sh.n_tokens], {}
+        return self.kv_all[:self.sh.n_tokens + self.extra], {}
 
     def head_output(self, slot):
         return torch.zeros(self.out_shape, dtype=torch.float32, device=self.device), None
@@ -144,17 +149,18 @@ class P2PExchange:
     p2p = True
     FLAG_BYTES = 4096
 
-    def __init__(self, shard: TokenShard, width, out_shape, device):
+    def __init__(self, shard: TokenShard, width, out_shape, device, extra_rows=0):
         from . import _lib
         self._lib = _lib
         lib, check = _lib.lib, _lib.check
-        self.sh, self.device, self.out_shape, self.width = shard, device, tuple(out_shape), width
+        assert extra_rows == 0 or shard.pad == 0, "locally written tail rows follow the token rows directly: no pad slots in between"
+        self.sh, self.device, self.out_shape, self.width, self.extra = shard, device, tuple(out_shape), width, extra_rows
         P = shard.world
         out_numel = 1
         for v in out_shape:
             out_numel *= v
         self.out_bytes = (out_numel * 4 + 255) // 256 * 256
-        self.kv_bytes = (shard.n_padded * width * 2 + 255) // 256 * 256
+        self.kv_bytes = ((shard.n_padded + extra_rows) * width * 2 + 255) // 256 * 256
         self.seg_bytes = shard.n_slots * width * 2
         total = self.FLAG_BYTES + 2 * self.out_bytes + 2 * self.kv_bytes
         ptr = ctypes.c_void_p()
@@ -179,8 +185,15 @@ class P2PExchange:
         self.outs = [self.window[o0 + s * self.out_bytes:o0 + s * self.out_bytes + out_numel * 4].view(torch.float32).view(self.out_shape)
                      for s in range(2)]
         k0 = o0 + 2 * self.out_bytes
-        self.kv = [self.window[k0 + i * self.kv_bytes:k0 + i * self.kv_bytes + shard.n_padded * width * 2].view(torch.bfloat16)
-                   .view(shard.n_padded, width) for i in range(2)]
+        self.kv = [self.window[k0 + i * self.kv_bytes:k0 + i * self.kv_bytes + (shard.n_padded + extra_rows) * width * 2].view(torch.bfloat16)
+                   .view(shard.n_padded + extra_rows, width) for i in range(2)]
+        if extra_rows:
+            # the attention kernel waits on the flag of every segment a KV tile touches; the tail rows are local, their
+            # "segments" (indices P ...) are permanently published
+            n_tail = (extra_rows + shard.n_slots - 1) // shard.n_slots + 1
+            assert P + n_tail <= 64, "flag table: 64 entries per exchange parity"
+            flags[P:P + n_tail] = 0x7FFFFFFF
+            flags[64 + P:64 + P + n_tail] = 0x7FFFFFFF
         self._kv_off = [k0 + i * self.kv_bytes + shard.start * width * 2 for i in range(2)]
         self.epochs = torch.zeros(4, dtype=torch.int32, device=device)  # [0] K|V exchange rounds, [1] head-output rounds
         self.comm = torch.cuda.Stream(device=device)
@@ -197,6 +210,12 @@ class P2PExchange:
             torch.cuda.current_stream().wait_event(self._done[i])
         sh = self.sh
         return self.kv[i][sh.start:sh.start + sh.n_local]
+
+    def tail_rows(self, i):
+        """The `extra_rows` key rows behind the token rows of gathered buffer i, written by every rank for itself (MMDiT: the
+        replicated text tokens); call after `own_rows(i)` (which orders the stream behind the pushes that last read the buffer — they
+        never touch the tail, but the attention that last read it is ordered the same way)."""
+        return self.kv[i][self.sh.n_padded:]
 
     def begin(self, i):
         lib, check = self._lib.lib, self._lib.check
@@ -217,7 +236,7 @@ class P2PExchange:
 
     def keys_values(self, i):
         sh = self.sh
-        return self.kv[i][:sh.n_tokens], dict(first_key_row=sh.start, seg_flags=self.kv_flags[i], seg_epoch=self.epochs[0:1], seg_rows=sh.n_slots)
+        return self.kv[i][:sh.n_tokens + self.extra], dict(first_key_row=sh.start, seg_flags=self.kv_flags[i], seg_epoch=self.epochs[0:1], seg_rows=sh.n_slots)
 
     # -- head output ----------------------------------------------------------------------------------------------
     def head_output(self, slot):
@@ -260,6 +279,6 @@ class P2PExchange:
             self.base = 0
 
 
-def make_exchange(shard, width, out_shape, device):
+def make_exchange(shard, width, out_shape, device, extra_rows=0):
     use_p2p = torch.device(device).type == "cuda" and os.environ.get("MC_SHARD_P2P", "1") != "0"
-    return (P2PExchange if use_p2p else CollectiveExchange)(shard, width, out_shape, device)
+    return (P2PExchange if use_p2p else CollectiveExchange)(shard, width, out_shape, device, extra_rows=extra_rows)
