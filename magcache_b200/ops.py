@@ -381,15 +381,17 @@ class HeadPrep:
         self.ptr, self.nbytes, self.cols, self._keep = ptr, nbytes, cols, keep
 
 
-def head_prepare(head_mod, e, w_t, b, tag=None):
-    """Fold (modulation + e) into head.weight for one forward: head_mod [2, cols] fp32, e [cols] fp32, w_t [cols, 64] fp32, b [64]."""
+def head_prepare(head_mod, e, w_t, b, tag=None, slot=0):
+    """Fold (modulation + e) into head.weight for one forward: head_mod [2, cols] fp32, e [cols] fp32, w_t [cols, 64] fp32, b [64].
+    `slot`: which of this module's head workspaces receives it — a forward that needs several preparations alive at once (per-token
+    timesteps, more than 16 output channels) numbers them."""
     import ctypes
     _dev(w_t)
     cols = w_t.shape[0]
     assert head_mod.shape[-2:] == (2, cols) and e.numel() == cols and w_t.shape == (cols, 64) and w_t.is_contiguous() and b.numel() == 64
     need = ctypes.c_int64(0)
     check(lib.mc_head_workspace_bytes(cols, ctypes.byref(need)))
-    ws = _workspace("head", w_t.device, need.value + 1024)
+    ws = _workspace("head" if slot == 0 else f"head{slot}", w_t.device, need.value + 1024)
     ptr = (ws.data_ptr() + 1023) // 1024 * 1024
     with _Timed(tag, "head_prepare"):
         check(lib.mc_head_prepare(head_mod.data_ptr(), e.data_ptr(), w_t.data_ptr(), b.data_ptr(), cols, ptr, need.value, _stream()))

@@ -153,14 +153,16 @@ def magcache_wan22_forward(self, x, t, context, seq_len, clip_fea=None, y=None):
     r"""MagCache4Wan2.2/magcache_generate.py:209-336 for the A14B experts (T2V and I2V) on the Wan engine: the Wan2.1 forward with the
     two-expert skip windows (`split_step`, `mode`, :294-303) and a counter shared by the high-noise and the low-noise model — two
     instances of one class, one engine (weights) each, one controller state and one residual cache between them (:340-362).
-    Wan2.2 broadcasts `t` to every token (:263-264); only a uniform timestep is built, i.e. not TI2V-5B, whose first-frame tokens carry
-    t = 0 (per-token modulation)."""
+    Wan2.2 gives every token its own timestep (:263-272). A 1-D `t` (the A14B experts) is one value for all tokens; TI2V-5B passes
+    [1, seq_len] with t = 0 on the first-frame tokens of an image-conditioned run: the engine reduces it to its distinct values and the
+    contiguous token ranges carrying them (`WanEngine._stage_t`), so the arithmetic per token is the reference's. With `split_step` None
+    (TI2V, :301-303) the window is the plain `int(num_steps * retention_ratio)`."""
     if getattr(self, "model_type", "t2v") == "i2v":
         assert y is not None  # :239-240
     if t.dim() != 1:
-        if not bool((t == t.reshape(-1)[0]).all()):
-            raise NotImplementedError("magcache_b200: per-token timesteps (Wan2.2 TI2V-5B) are not built; A14B experts pass one t")
-        t = t.reshape(-1)[:1]
+        if t.size(0) != 1:
+            raise NotImplementedError("magcache_b200: one sample per call")
+        assert t.size(1) == seq_len  # what `.unflatten(0, (bt, seq_len))` (:270) requires
     eng = _stage(self, x, t, context, seq_len, None, y, require_clip=False)
     ctrls = self.__dict__.setdefault("_mc_ctrls", {})
     fam = "wan2.2-i2v" if getattr(self, "mode", "t2v") == "i2v" else "wan2.2-t2v"

@@ -41,7 +41,8 @@ def cfg_denoise_step(model, x, t, context, context_null, seq_len, guide_scale, c
             return model([xx], t=tt, context=[cc], seq_len=seq_len, **kw)[0]
     cond = forward(x, t, context)
     eng = _engine(model)
-    if getattr(eng, "shard", None) is None and hasattr(eng, "arm_step"):
+    # the fused form is built for one timestep per call and 16 output channels (not Wan2.2 TI2V-5B: per-token t, 48 channels)
+    if getattr(eng, "shard", None) is None and hasattr(eng, "arm_step") and t.numel() == 1 and len(getattr(eng, "head_groups", (0,))) == 1:
         eng.arm_step(cond, x, guide_scale, coef_x, coef_v, out=x)
         return forward(x, t, context_null)
     uncond = forward(x, t, context_null)

@@ -53,7 +53,12 @@ WAN_CONFIGS = {
     "i2v-14B": WanDims(5120, 13824, 40, 40, in_dim=36, model_type="i2v"),
     "vace-1.3B": WanDims(1536, 8960, 12, 30, model_type="vace", vace_layers=tuple(range(0, 30, 2))),
     "vace-14B": WanDims(5120, 13824, 40, 40, model_type="vace", vace_layers=tuple(range(0, 40, 5))),
+    # Wan2.2 TI2V-5B (MagCache4Wan2.2, table `wan2.2_ti2v_5b_*`): 48 latent channels in and out, per-token timesteps
+    "ti2v-5B": WanDims(3072, 14336, 24, 30, in_dim=48, out_dim=48),
 }
+
+MAX_T_VALUES = 8    # distinct timesteps in one call (the time MLP kernel takes <= 8 rows)
+MAX_T_RUNS = 64     # contiguous token ranges of equal timestep in one call
 
 
 def _bf16(t, device):
@@ -258,6 +263,20 @@ class WanEngine:
         self._slot = 0   # CFG slot of the forward in flight (selects the output window of a sharded engine)
         self.hit_sum_bf16 = False  # TeaCache comparator: the hit sum is rounded to bf16 before the head (wan_teacache.py:569/577)
         self._step = None          # (cond, x_latent, guide_scale, coef_x, coef_v, out) armed by `arm_step` for the next forward
+        # per-token timesteps (Wan2.2, MagCache4Wan2.2/magcache_generate.py:263-272): the distinct values of this call and the
+        # contiguous LOCAL row ranges that carry them, [(row0, row1, value index)]; None = one timestep for every token
+        self.t_values, self.runs, self._runs_key = 1, None, None
+        # the head kernel produces 64 output features (16 channels x the 2x2 patch) per launch: a model with more output channels
+        # (TI2V-5B: 48) runs it once per group of 16 channels, on the matching columns of head.weight (feature index = p * C + c)
+        C = self.dims.out_dim
+        if C % 16:
+            raise NotImplementedError(f"out_dim {C}: the head kernel writes 16 channels per launch")
+        if C == 16:
+            self.head_groups = [(weights.head_wt, weights.head_b)]
+        else:
+            wt, hb = weights.head_wt.view(self.dims.dim, 4, C), weights.head_b.view(4, C)
+            self.head_groups = [(wt[:, :, g:g + 16].reshape(self.dims.dim, 64).contiguous(), hb[:, g:g + 16].reshape(64).contiguous())
+                                for g in range(0, C, 16)]
 
     # ------------------------------------------------------------------------------------------ workspace
     def _workspace(self, n_total, pad_row=0):
@@ -296,7 +315,7 @@ class WanEngine:
         self.ctx_in = torch.zeros(d.text_len, d.text_dim, **bf)
         self.ctx_h = torch.empty(d.text_len, D, **bf)
         self.ctx = torch.empty(d.text_len, D, **bf)
-        self.em = torch.empty(6, D, dtype=torch.float32, device=dev)
+        self.em = torch.empty(MAX_T_VALUES, 6, D, dtype=torch.float32, device=dev)  # modulation + e0, one [6, D] per timestep value
         if d.model_type == "vace":
             self.cs = torch.empty(n, D, dtype=torch.float32, device=dev)             # control stream (fp32 like the main one)
             self.cbf = torch.empty(len(d.vace_layers), n, D, **bf)                   # bf16 copies = A operands of the after_proj GEMMs
@@ -315,7 +334,7 @@ class WanEngine:
         self.res_buf = torch.empty(2, n, D, dtype=torch.float32, device=dev)  # one buffer: the paper-eval forward exposes it whole
         self.res = [self.res_buf[0], self.res_buf[1]]
         self.res_valid = [False, False]
-        self.s_t = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.s_t = torch.zeros(MAX_T_VALUES, dtype=torch.float64, device=dev)
         self.s_lat = None
         self._graphs = {}
         self._n = (n_total, pad_row)
@@ -364,20 +383,62 @@ class WanEngine:
         if clip_fea is not None:
             assert tuple(clip_fea.shape[-2:]) == (d.clip_len, d.clip_dim) and clip_fea.numel() == d.clip_len * d.clip_dim, "one sample per call"
             self.clip_in.copy_(clip_fea.reshape(d.clip_len, d.clip_dim))
-        self.s_t.copy_(t.reshape(-1)[:1])
+        self._stage_t(t)
         L = context.shape[0]
         assert L <= d.text_len and context.shape[1] == d.text_dim
         self.ctx_in.zero_()
         self.ctx_in[:L].copy_(context)
 
+    def _stage_t(self, t):
+        """One timestep (`t` with one element: Wan2.1, the Wan2.2 A14B experts) is copied device to device. A per-token `t`
+        ([1, seq_len], MagCache4Wan2.2/magcache_generate.py:263-264 — TI2V-5B gives its first-frame tokens t = 0) is read back once
+        (the only host synchronisation of a forward) and reduced to its distinct values and the contiguous row ranges that carry
+        them: the time MLP then runs once per VALUE, and every op that consumes the modulation runs once per RANGE with that value's
+        vectors — the same arithmetic per token as the reference's per-token embedding. Rows past the tokens (`seq_len` padding) are
+        not computed, except the one representative pad row of a calibration call, which takes the first padded position's t."""
+        if t.numel() == 1:
+            self.s_t[:1].copy_(t.reshape(-1))
+            self.t_values, self.runs, key = 1, None, None
+        else:
+            n_rows = self.n_keys + self.pad_row
+            tv = t.detach().reshape(-1).to(torch.float64).cpu().numpy()
+            if tv.shape[0] < n_rows:
+                raise ValueError(f"magcache_b200: {tv.shape[0]} timesteps for {n_rows} token rows")
+            if self.pad_row and np.any(tv[self.n_keys:] != tv[self.n_keys]):
+                raise NotImplementedError("magcache_b200: the padded positions of a calibration call must share one timestep")
+            tv = tv[:n_rows]
+            cuts = np.flatnonzero(tv[1:] != tv[:-1]) + 1
+            bounds = np.concatenate([[0], cuts, [n_rows]])
+            values, runs = [], []
+            for r0, r1 in zip(bounds[:-1].tolist(), bounds[1:].tolist()):
+                v = float(tv[r0])
+                if v not in values:
+                    values.append(v)
+                runs.append((r0, r1, values.index(v)))
+            if len(values) == 1:
+                self.s_t[:1].copy_(t.reshape(-1)[:1])
+                self.t_values, self.runs, key = 1, None, None
+            else:
+                if len(values) > MAX_T_VALUES or len(runs) > MAX_T_RUNS:
+                    raise NotImplementedError(f"magcache_b200: {len(values)} distinct timesteps in {len(runs)} token ranges "
+                                              f"(built for <= {MAX_T_VALUES} values, <= {MAX_T_RUNS} ranges; TI2V-5B has 2 and 2)")
+                self.s_t[:len(values)].copy_(torch.tensor(values, dtype=torch.float64))
+                if self.shard is not None:  # this rank's rows of every range, in local coordinates
+                    a, b = self.shard.start, self.shard.start + self.shard.n_local
+                    runs = [(max(r0, a) - a, min(r1, b) - a, u) for r0, r1, u in runs if min(r1, b) > max(r0, a)]
+                self.t_values, self.runs, key = len(values), runs, tuple(runs)
+        if key != self._runs_key:
+            self._runs_key, self._graphs = key, {}  # a captured forward bakes the ranges in
+
     def time_embedding(self):
         """`e = time_embedding(sinusoid(t))`, `e0 = time_projection(e)` (fp32 region, magcache_generate.py:249-254) from the staged t:
-        e fp32 [1, D], e0 fp32 [6, D]. Also what the TeaCache comparator measures between steps (wan_teacache.py:534)."""
-        d, w = self.dims, self.w
-        sin = ops.time_sinusoid(self.s_t, d.freq_dim)
+        e fp32 [1, D], e0 fp32 [6, D] ([U, D] and [U, 6, D] for U > 1 distinct per-token timesteps). Also what the TeaCache comparator
+        measures between steps (wan_teacache.py:534)."""
+        d, w, U = self.dims, self.w, self.t_values
+        sin = ops.time_sinusoid(self.s_t[:U], d.freq_dim)
         e = ops.linear_f32_small(ops.linear_f32_small(sin, w.time_w1, w.time_b1, act=2), w.time_w2, w.time_b2, act=0)
-        e0 = ops.linear_f32_small(e, w.tproj_w, w.tproj_b, act=1).view(6, d.dim)
-        return e, e0
+        e0 = ops.linear_f32_small(e, w.tproj_w, w.tproj_b, act=1)
+        return e, (e0.view(6, d.dim) if U == 1 else e0.view(U, 6, d.dim))
 
     def prologue(self, need_ctx=True):
         """Embeddings from the staged inputs. Returns (x0 bf16 [N_local, D], e fp32 [1, D], e0 fp32 [6, D], ctx bf16 [text_len, D]).
@@ -392,7 +453,8 @@ class WanEngine:
             self.x0[tok.shape[0]:].zero_()  # `u.new_zeros(1, seq_len - u.size(1), u.size(2))` (:244-245)
         e, e0 = self.time_embedding()
         # the head's modulated weight depends on the time embedding only: prepared here, off the tail of the forward
-        self._head_prep = ops.head_prepare(w.head_mod, e, w.head_wt, w.head_b)
+        self._head_prep = {(u, g): ops.head_prepare(w.head_mod, e[u], wt, hb, slot=u * len(self.head_groups) + g)
+                           for u in range(self.t_values) for g, (wt, hb) in enumerate(self.head_groups)}
         if not need_ctx:
             return self.x0, e, e0, None
         ops.gemm(self.ctx_in, w.text_w1, w.text_b1, E.MC_EPI_BIAS_GELU_BF16, out=self.ctx_h)
@@ -425,6 +487,8 @@ class WanEngine:
         instead of the unconditional prediction. One-shot; bit-equal to the plain forward followed by `ops.cfg_step`."""
         if self.shard is not None:
             raise NotImplementedError("magcache_b200: the fused step is built for the unsharded engine (sharded runs use ops.cfg_step)")
+        if len(self.head_groups) != 1:
+            raise NotImplementedError("magcache_b200: the fused step is built for 16 output channels (use ops.cfg_step)")
         self._step = (cond, x_latent, float(guide_scale), float(coef_x), float(coef_v), out)
 
     def forward(self, kind, slot):
@@ -506,9 +570,9 @@ class WanEngine:
         D = d.dim
         n = xs.shape[0]
         sh = self.shard
-        ops.cache_hit_add(b["mod"], e0, out=self.em)  # e = modulation + e0 (fp32)
+        self._modulation(b["mod"], e0)  # e = modulation + e0 (fp32)
         # --- self attention
-        ops.ln_modulate(xs, self.em, 1, 0, eps=d.eps, round_ln_to_bf16=first, out=self.h)
+        self._ln_modulate(xs, 1, 0, first)
         if sh is None:
             q, k, v = self.qkv[:, :D], self.qkv[:, D:2 * D], self.qkv[:, 2 * D:]
             ops.gemm(self.h, b["w_qkv"], b["b_qkv"], E.MC_EPI_BIAS_BF16, out=self.qkv, tag="gemm_qkv")
@@ -527,7 +591,7 @@ class WanEngine:
             ops.rmsnorm_rope_(self.q_loc, b["nqk"][0], rope, d.head_dim, eps=d.eps)
             kv_all, kw = self.xch.keys_values(xi)
             ops.attention(self.q_loc, kv_all[:, :D], kv_all[:, D:], H, out=self.att, tag="attn_self", **kw)
-        ops.gemm(self.att, b["w_o"], b["b_o"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[2], tag="gemm_o")
+        self._gemm_gated(self.att, b["w_o"], b["b_o"], xs, 2, "gemm_o")
         # --- cross attention (text)
         ops.ln_affine(xs, b["n3_w"], b["n3_b"], eps=d.eps, out=self.h)
         ops.gemm(self.h, b["c_wq"], b["c_bq"], E.MC_EPI_BIAS_BF16, out=self.cq, tag="gemm_cq")
@@ -543,26 +607,76 @@ class WanEngine:
             att = ops.cache_hit_add(self.att, self.att_img, out=self.h)  # h (norm3 output) is dead once cq is projected
         ops.gemm(att, b["c_wo"], b["c_bo"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=None, tag="gemm_co")
         # --- FFN
-        ops.ln_modulate(xs, self.em, 4, 3, eps=d.eps, out=self.h)
+        self._ln_modulate(xs, 4, 3, False)
         ops.gemm(self.h, b["w_f1"], b["b_f1"], E.MC_EPI_BIAS_GELU_BF16, out=self.ffn, tag="gemm_ffn1")
-        ops.gemm(self.ffn, b["w_f2"], b["b_f2"], E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[5], tag="gemm_ffn2")
+        self._gemm_gated(self.ffn, b["w_f2"], b["b_f2"], xs, 5, "gemm_ffn2")
+
+    # The three places a block consumes the time modulation. With one timestep they are single launches over all rows; with per-token
+    # timesteps (`self.runs`) each runs once per contiguous row range, on row slices of the same buffers, with that range's vectors.
+    def _modulation(self, mod, e0):
+        if self.runs is None:
+            return ops.cache_hit_add(mod, e0, out=self.em[0])
+        for u in range(self.t_values):
+            ops.cache_hit_add(mod, e0[u], out=self.em[u])
+        return self.em
+
+    def _ln_modulate(self, xs, scale_idx, shift_idx, first):
+        eps = self.dims.eps
+        if self.runs is None:
+            ops.ln_modulate(xs, self.em[0], scale_idx, shift_idx, eps=eps, round_ln_to_bf16=first, out=self.h)
+            return
+        for r0, r1, u in self.runs:
+            ops.ln_modulate(xs[r0:r1], self.em[u], scale_idx, shift_idx, eps=eps, round_ln_to_bf16=first, out=self.h[r0:r1])
+
+    def _gemm_gated(self, a, w, bias, xs, gate_idx, tag):
+        """xs += (a @ w.T + bias) * gate (the gated residual adds of the block), gate = row `gate_idx` of modulation + e0."""
+        if self.runs is None:
+            ops.gemm(a, w, bias, E.MC_EPI_BIAS_GATE_RESID, out=xs, gate=self.em[0][gate_idx], tag=tag)
+            return
+        for r0, r1, u in self.runs:
+            ops.gemm(a[r0:r1], w, bias, E.MC_EPI_BIAS_GATE_RESID, out=xs[r0:r1], gate=self.em[u][gate_idx], tag=tag)
 
     # ------------------------------------------------------------------------------------------ epilogue (:304-305)
     def head(self, x, e, grid, residual=None, round_sum_to_bf16=False):
-        w = self.w
+        w, G = self.w, len(self.head_groups)
         tag = "head_hit_fused" if residual is not None else "head"
-        kw = dict(c_out=self.dims.out_dim, residual=residual, eps=self.dims.eps, tag=tag, round_sum_to_bf16=round_sum_to_bf16, prep=self._head_prep)
+        kw = dict(c_out=16, eps=self.dims.eps, tag=tag, round_sum_to_bf16=round_sum_to_bf16)
+        row_offset, out, peer_outs = 0, None, None
         if self.shard is None:
             if self.pad_row:  # unpatchify reads the token rows only (`u[:math.prod(v)]`)
                 x = x[:self.n_keys]
                 if residual is not None:
-                    kw["residual"] = residual[:self.n_keys]
+                    residual = residual[:self.n_keys]
+        else:
+            self.xch.join()  # every push of this forward is ordered before its end (and inside a captured graph)
+            out, peer_outs = self.xch.head_output(self._slot)
+            row_offset = self.shard.start
+        if self.runs is None and G == 1:  # one timestep, 16 output channels: a single launch
+            (wt, hb), = self.head_groups
+            if self.shard is None and self._step is not None:
+                kw["step"], out = self._step[:5], self._step[5]
+            out = ops.head_unpatchify(x, w.head_mod, e, wt, hb, grid, residual=residual, row_offset=row_offset, out=out, peer_outs=peer_outs,
+                                      prep=self._head_prep[(0, 0)], **kw)
+        else:
+            # per-token timesteps and / or more than 16 output channels: one launch per (row range, channel group), each writing
+            # its own rows x channels of the same output tensor
             if self._step is not None:
-                kw["step"], kw["out"] = self._step[:5], self._step[5]
-            return ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, **kw)
-        self.xch.join()  # every push of this forward is ordered before its end (and inside a captured graph)
-        out, peer_outs = self.xch.head_output(self._slot)
-        ops.head_unpatchify(x, w.head_mod, e, w.head_wt, w.head_b, grid, row_offset=self.shard.start, out=out, peer_outs=peer_outs, **kw)
+                raise NotImplementedError("magcache_b200: the fused step is built for one timestep and 16 output channels (use ops.cfg_step)")
+            n_rows = x.shape[0]
+            if out is None:
+                out = torch.empty(self.dims.out_dim, grid[0], 2 * grid[1], 2 * grid[2], dtype=torch.float32, device=x.device)
+            group_bytes = 16 * out[0].numel() * 4
+            for r0, r1, u in (self.runs if self.runs is not None else [(0, n_rows, 0)]):
+                r1 = min(r1, n_rows)  # a calibration call's pad row is not unpatchified
+                if r1 <= r0:
+                    continue
+                for g, (wt, hb) in enumerate(self.head_groups):
+                    ops.head_unpatchify(x[r0:r1], w.head_mod, e[u], wt, hb, grid, residual=None if residual is None else residual[r0:r1],
+                                        row_offset=row_offset + r0, out=out[16 * g:16 * g + 16],
+                                        peer_outs=None if peer_outs is None else [int(p) + g * group_bytes for p in peer_outs],
+                                        prep=self._head_prep[(u, g)], **kw)
+        if self.shard is None:
+            return out
         return self.xch.finish_head(out, self._slot)  # every rank ends up with the full noise prediction
 
 

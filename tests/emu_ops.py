@@ -222,7 +222,8 @@ def linear_f32_small(x, w, b=None, act=0):
     return F.silu(y) if act == 2 else y
 
 
-def head_prepare(head_mod, e, w_t, b, tag=None):
+def head_prepare(head_mod, e, w_t, b, tag=None, slot=0):
+    assert w_t.shape == (head_mod.shape[-1], 64) and w_t.is_contiguous() and b.numel() == 64 and e.numel() == head_mod.shape[-1]
     _count()
     return None
 
@@ -238,12 +239,16 @@ def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1
     y = F.layer_norm(xs, (xs.shape[-1],), None, None, eps) * (1 + em[1]) + em[0]
     o = y @ w_t + b  # [rows, 4*c_out]
     f, h, w = grid
-    if o.shape[0] != f * h * w:  # token-sharded caller: only the positions of rows [row_offset, row_offset + rows) are written
-        full = torch.zeros(f * h * w, o.shape[1])
+    assert c_out == 16 and o.shape[1] == 64, "the head kernel writes 16 channels (64 features) per launch"
+    unpatch = lambda rows: torch.einsum("fhwpqrc->cfphqwr", rows.view(f, h, w, 1, 2, 2, c_out)).reshape(c_out, f, 2 * h, 2 * w).contiguous()  # noqa: E731
+    written = None
+    if o.shape[0] != f * h * w:  # a row range [row_offset, row_offset + rows): only the positions of those rows are written
+        assert out is not None, "a partial token range needs a caller-provided output"
+        full, mark = torch.zeros(f * h * w, o.shape[1]), torch.zeros(f * h * w, o.shape[1])
         full[row_offset:row_offset + o.shape[0]] = o
-        o = full
-    u = o.view(f, h, w, 1, 2, 2, c_out)
-    u = torch.einsum("fhwpqrc->cfphqwr", u).reshape(c_out, f, 2 * h, 2 * w).contiguous()
+        mark[row_offset:row_offset + o.shape[0]] = 1.0
+        o, written = full, unpatch(mark) > 0
+    u = unpatch(o)
     if step is not None:  # mc_head_unpatchify_step: the caller loop's CFG combine + scheduler update in the epilogue (full token range)
         assert o.shape[0] == f * h * w
         cond, x_lat, g, cx, cv = step
@@ -252,7 +257,11 @@ def head_unpatchify(x, head_mod, e, w_t, b, grid, c_out=16, residual=None, eps=1
         u = t32(cx) * x_lat + t32(cv) * v
     _count()
     if out is not None:
-        out.copy_(u)
+        assert out.is_contiguous() and out.shape == u.shape
+        if written is None:
+            out.copy_(u)
+        else:
+            out[written] = u[written]
         return out
     return u
 

@@ -125,12 +125,17 @@ def _engine_worker(rank, world, initfile, results, kind="t2v", grid=GRID):
         patch_mod.ops = emu_ops
         torch.Tensor.is_cuda = property(lambda self: True)
         os.environ["MC_GRAPHS"] = "0"
-        extra_model = {"i2v": dict(in_dim=36, model_type="i2v", clip_dim=64), "vace": dict(model_type="vace", vace_in_dim=24)}.get(kind, {})
+        extra_model = {"i2v": dict(in_dim=36, model_type="i2v", clip_dim=64), "vace": dict(model_type="vace", vace_in_dim=24),
+                       "ti2v": dict(in_dim=48, out_dim=48)}.get(kind, {})
         model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=8, **extra_model).init_synthetic(3)
         g = torch.Generator().manual_seed(7)
         shape = [grid[0], 2 * grid[1], 2 * grid[2]]
         n_tok = grid[0] * grid[1] * grid[2]
-        lat, ctx = torch.randn(16, *shape, generator=g), torch.randn(5, 64, generator=g)
+        lat, ctx = torch.randn(48 if kind == "ti2v" else 16, *shape, generator=g), torch.randn(5, 64, generator=g)
+        t = torch.tensor([500.0])
+        if kind == "ti2v":  # per-token timesteps (Wan2.2 TI2V-5B): a clean range that ends inside rank 1's rows
+            t = torch.full((1, n_tok), 500.0)
+            t[0, :n_tok // 2 + 6] = 0.0
         extra = {}
         if kind == "i2v":
             extra = dict(clip_fea=torch.randn(1, 257, 64, generator=g), y=[torch.randn(20, *shape, generator=g)])
@@ -147,9 +152,9 @@ def _engine_worker(rank, world, initfile, results, kind="t2v", grid=GRID):
             with torch.no_grad():
                 for i in range(4):  # miss, miss, hit, hit
                     if kind == "vace":
-                        seq.append(m.forward([lat], torch.tensor([500.0]), extra["vace_context"], [ctx], n_tok)[0].clone())
+                        seq.append(m.forward([lat], t, extra["vace_context"], [ctx], n_tok)[0].clone())
                     else:
-                        seq.append(m.forward([lat], torch.tensor([500.0]), [ctx], n_tok, **extra)[0].clone())
+                        seq.append(m.forward([lat], t, [ctx], n_tok, **extra)[0].clone())
             outs[name] = (seq, m._mc_engine, m.residual_cache)
         eng = outs["sharded"][1]
         sh = eng.shard
@@ -157,12 +162,16 @@ def _engine_worker(rank, world, initfile, results, kind="t2v", grid=GRID):
         r_full = outs["single"][2][0][0]
         r_loc = outs["sharded"][2][0][0]
         cache_err = float((r_loc - r_full[sh.start:sh.stop]).abs().max() / r_full.abs().max())
+        if kind == "ti2v":
+            h = n_tok // 2
+            assert eng.t_values == 2 and eng.runs == ([(0, h, 0)] if rank == 0 else [(0, 6, 0), (6, h, 1)]), eng.runs
+            assert outs["single"][1].runs == [(0, h + 6, 0), (h + 6, n_tok, 1)] and seq[0].shape[0] == 48
         results[rank] = (errs, cache_err, tuple(r_loc.shape), (sh.start, sh.stop))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["t2v", "i2v", "vace"])
+@pytest.mark.parametrize("kind", ["t2v", "i2v", "vace", "ti2v"])
 def test_sharded_engine_equals_single_engine_world2(kind):
     with tempfile.TemporaryDirectory() as d:
         mgr = mp.get_context("spawn").Manager()

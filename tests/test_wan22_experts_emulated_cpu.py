@@ -70,14 +70,85 @@ def test_two_experts_share_controller_and_cache(emulated, mode):
     assert int(OurCls.cnt) == 0
 
 
-def test_per_token_timesteps_are_refused(emulated):
-    m = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=1, text_dim=128, text_len=32).init_synthetic(0)
-    m.__class__ = type("OurTI2V", (wan_ref.WanModel,), {})
-    object.__setattr__(m, "_mc_engine", mc.WanEngine(mc.WanWeights.from_module(m, torch.device("cpu"))))
-    mc.init_magcache_wan22(m, mc.tables()["wan2.2_ti2v_5b_a"][2:].tolist(), 50)
-    t = torch.full((1, 32), 500.0)
-    t[0, :8] = 0.0
-    with pytest.raises(NotImplementedError):
-        m([torch.randn(16, 2, 8, 8)], t=t, context=[torch.randn(5, 128)], seq_len=32)
-    out = m([torch.randn(16, 2, 8, 8)], t=torch.full((1, 32), 500.0), context=[torch.randn(5, 128)], seq_len=32)[0]  # uniform [B, L] is fine
-    assert out.shape == (16, 2, 8, 8)
+def _ti2v_pair(seed=0, **over):
+    """A TI2V-5B-shaped model at test size (48 latent channels in and out -> three 16-channel head groups) as oracle and as ours."""
+    kw = dict(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128, text_len=32, in_dim=48, out_dim=48)
+    kw.update(over)
+    proto = wan_ref.WanModel(**kw).init_synthetic(seed)
+    ref, our = copy.deepcopy(proto), copy.deepcopy(proto)
+    RefCls, OurCls = type("RefTI2V", (wan_ref.WanModel,), {}), type("OurTI2V", (wan_ref.WanModel,), {})
+    ref.__class__, our.__class__ = RefCls, OurCls
+    object.__setattr__(our, "_mc_engine", mc.WanEngine(mc.WanWeights.from_module(our, torch.device("cpu"))))
+    return ref, our, RefCls, OurCls
+
+
+def _ti2v_timesteps(step_t, grid, seq_len, first_frame_clean=True):
+    """`temp_ts = (mask2[0][0][:, ::2, ::2] * timestep).flatten()` padded to seq_len with `timestep` (upstream Wan2.2 `generate` for
+    ti2v image-to-video): the first latent frame is the clean image, its tokens carry t = 0."""
+    f, h, w = grid
+    t = torch.full((f, h, w), float(step_t))
+    if first_frame_clean:
+        t[0] = 0.0
+    return torch.cat([t.flatten(), torch.full((seq_len - f * h * w,), float(step_t))]).unsqueeze(0)
+
+
+def test_ti2v_per_token_timesteps_follow_the_oracle(emulated):
+    """MagCache4Wan2.2/magcache_generate.py:260-272 with `t` [1, seq_len]: first-frame tokens at t = 0, the rest at the step's timestep,
+    `split_step` None -> the plain retention window (:301-303). Same hit / miss sequence as the oracle, every output (48 channels) and
+    the cached residual to bf16-pipeline noise — and NOT what a uniform timestep would give."""
+    ref, our, RefCls, OurCls = _ti2v_pair()
+    steps = 10
+    ratios = mc.tables()["wan2.2_ti2v_5b_a"][2:].tolist()
+    wan_ref.install_magcache_wan22(RefCls, ratios, steps, thresh=0.12, K=2, retention_ratio=0.2)
+    mc.init_magcache_wan22(our, ratios, steps, thresh=0.12, K=2, retention_ratio=0.2)
+    assert OurCls.split_step is None and OurCls.mag_ratios.tolist() == RefCls.mag_ratios.tolist()
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(48, 3, 8, 8, generator=g)   # grid (3, 4, 4): 48 tokens, the first 16 are the image frame
+    ctxs = [torch.randn(9, 128, generator=g), torch.randn(7, 128, generator=g)]
+    kinds, seq_len = [], 56
+    with torch.no_grad():
+        for call in range(2 * steps):
+            t = _ti2v_timesteps(950.0 - 90.0 * (call // 2), (3, 4, 4), seq_len)
+            a = ref([lat], t=t, context=[ctxs[call % 2]], seq_len=seq_len)[0]
+            b = our([lat], t=t, context=[ctxs[call % 2]], seq_len=seq_len)[0]
+            assert a.shape == b.shape == (48, 3, 8, 8)
+            kinds.append(int(ref.last_skip))
+            rel = float((a - b).norm() / a.norm())
+            assert rel < 2e-2, (call, rel)
+            ra, rb = RefCls.residual_cache[call % 2][0, :48].float(), OurCls.residual_cache[call % 2][0].float()
+            assert float((ra - rb).norm() / ra.norm()) < 2e-2
+            assert OurCls.accumulated_err == RefCls.accumulated_err and OurCls.accumulated_steps == RefCls.accumulated_steps
+            if call == 0:
+                eng = our._mc_engine
+                assert eng.t_values == 2 and eng.runs == [(0, 16, 0), (16, 48, 1)]
+                uni = copy.deepcopy(ref)
+                uni.__class__ = type("UniTI2V", (wan_ref.WanModel,), {})
+                wan_ref.install_magcache_wan22(uni.__class__, ratios, steps, thresh=0.12, K=2, retention_ratio=0.2)
+                c = uni([lat], t=_ti2v_timesteps(950.0, (3, 4, 4), seq_len, first_frame_clean=False), context=[ctxs[0]], seq_len=seq_len)[0]
+                assert float((a - c).norm() / a.norm()) > 10 * rel, "the per-token timesteps must matter in this test"
+    want = mc.MagCacheConfig("wan2.2-ti2v", 0.12, 2, 0.2, steps, mag_ratios=OurCls.mag_ratios).schedule().tolist()
+    assert kinds == want and 0 < sum(want) < 2 * steps
+    assert int(OurCls.cnt) == 0
+
+
+def test_ti2v_uniform_and_scattered_timesteps(emulated):
+    """A [1, seq_len] `t` that is uniform (TI2V text-to-video) takes the one-timestep path (no row ranges); a `t` with several
+    non-adjacent ranges of the same value reuses that value's embedding; too many distinct values are refused, not approximated."""
+    ref, our, RefCls, OurCls = _ti2v_pair(seed=1, num_layers=1)
+    ratios = mc.tables()["wan2.2_ti2v_5b_a"][2:].tolist()
+    wan_ref.install_magcache_wan22(RefCls, ratios, 10)
+    mc.init_magcache_wan22(our, ratios, 10)
+    g = torch.Generator().manual_seed(4)
+    lat, ctx = torch.randn(48, 3, 8, 8, generator=g), torch.randn(6, 128, generator=g)
+    eng = our._mc_engine
+    with torch.no_grad():
+        t = torch.full((1, 48), 700.0)
+        a, b = ref([lat], t=t, context=[ctx], seq_len=48)[0], our([lat], t=t, context=[ctx], seq_len=48)[0]
+        assert eng.runs is None and eng.t_values == 1 and float((a - b).norm() / a.norm()) < 2e-2
+        t = torch.full((1, 48), 700.0)
+        t[0, 5:9], t[0, 20:31], t[0, 40:] = 0.0, 0.0, 350.0
+        a, b = ref([lat], t=t, context=[ctx], seq_len=48)[0], our([lat], t=t, context=[ctx], seq_len=48)[0]
+        assert eng.t_values == 3 and eng.runs == [(0, 5, 0), (5, 9, 1), (9, 20, 0), (20, 31, 1), (31, 40, 0), (40, 48, 2)]
+        assert float((a - b).norm() / a.norm()) < 2e-2
+        with pytest.raises(NotImplementedError):
+            our([lat], t=torch.arange(48.0).unsqueeze(0), context=[ctx], seq_len=48)

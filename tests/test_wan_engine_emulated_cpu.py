@@ -129,3 +129,41 @@ def test_wan_engine_calibration_with_padded_seq_len(emulated, tmp_path):
         for a, b in zip(getattr(ours, name), getattr(ref, name)):
             assert abs(a - b) <= 3e-2 * abs(b) + 2e-4, (name, a, b)
     assert ours._mc_engine.pad_row == 1 and ours.residual_cache[0].shape[1] == n_tok + 1
+
+
+def test_wan_engine_calibration_with_per_token_timesteps_and_padding(emulated, tmp_path):
+    """Calibration of a TI2V-5B-shaped model (MagCache4Wan2.2/magcache_generate.py:80-194 twin: 48 channels, `t` [1, seq_len] with the
+    first-frame tokens at t = 0, seq_len > token count): the representative pad row takes the padded positions' timestep, the row
+    ranges stop at the tokens in the head, and the statistics equal the oracle's (which carries every padded row)."""
+    model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128, text_len=32, in_dim=48, out_dim=48).init_synthetic(5)
+    ref = copy.deepcopy(model)
+    ref.__class__ = type("RefCT", (ref.__class__,), {})
+    wan_ref.install_magcache(type(ref), None, 3, calibration=True)
+    ours = copy.deepcopy(model)
+    ours.__class__ = type("OursCT", (ours.__class__,), {})
+    mc.init_magcache_calibration(ours, 3)
+    type(ours).calibration_dir = str(tmp_path)
+    _attach_engine(ours)
+    g = torch.Generator().manual_seed(8)
+    lat, ctx = torch.randn(48, 2, 8, 8, generator=g), torch.randn(9, 128, generator=g)
+    n_tok, seq_len = 32, 39
+    outs = []
+    with torch.no_grad():
+        for i in range(6):
+            t = torch.full((1, seq_len), 900.0 - 50 * i)
+            t[0, :16] = 0.0
+            x = lat * (1.0 - 0.1 * i)
+            a = ref([x], t=t, context=[ctx], seq_len=seq_len)[0]
+            b = ours([x], t=t, context=[ctx], seq_len=seq_len)[0]
+            assert b.shape == (48, 2, 8, 8)
+            outs.append(rel_l2(b, a))
+    assert max(outs) <= 1.5e-2, outs
+    for name in ("norm_ratio", "norm_std", "cos_dis"):
+        for a, b in zip(getattr(ours, name), getattr(ref, name)):
+            assert abs(a - b) <= 3e-2 * abs(b) + 2e-4, (name, a, b)
+    eng = ours._mc_engine
+    assert eng.pad_row == 1 and eng.runs == [(0, 16, 0), (16, 33, 1)] and ours.residual_cache[0].shape[1] == n_tok + 1
+    with pytest.raises(NotImplementedError):  # padded positions with different timesteps: no single representative row
+        t = torch.full((1, seq_len), 500.0)
+        t[0, -1] = 0.0
+        ours([lat], t=t, context=[ctx], seq_len=seq_len)

@@ -503,3 +503,55 @@ def test_wan14b_shaped_blocks_vs_oracle():
     e = rel_l2(out, ref)
     print("14B-shaped rel-L2 vs oracle", e)
     assert e <= 2e-2
+
+
+def test_ti2v_per_token_timesteps_vs_oracle_and_fp64():
+    """Wan2.2 TI2V-5B's forward (MagCache4Wan2.2/magcache_generate.py:209-336) at test size on the kernels: 48 latent channels in and out
+    (three 16-channel head launches per row range), `t` [1, seq_len] with the first-frame tokens at t = 0 (row ranges [0, 384) and
+    [384, 1152) — neither a multiple of the 128-row tiles' grid), seq_len > token count, `split_step` None. miss, miss, then hits on
+    both CFG slots against the oracle; the first call also against the fp64 evaluation of the same network."""
+    from oracle import wan_ref
+    import magcache_b200 as mc
+    model = wan_ref.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, in_dim=48, out_dim=48, text_dim=512, text_len=64).init_synthetic(6)
+    g = torch.Generator().manual_seed(9)
+    grid = (3, 16, 24)
+    lat = torch.randn(48, 3, 32, 48, generator=g)
+    ctx, ctx_null = torch.randn(37, 512, generator=g), torch.randn(30, 512, generator=g)
+    n_tok = grid[0] * grid[1] * grid[2]
+    seq_len = n_tok + 24
+    ratios = mc.tables()["wan2.2_ti2v_5b_a"][2:].tolist()
+
+    def timesteps(v):
+        t = torch.full((1, seq_len), float(v))
+        t[0, :grid[1] * grid[2]] = 0.0
+        return t
+
+    RefCls, Ref64, OurCls = (type(n, (wan_ref.WanModel,), {}) for n in ("RefTI2V", "Ref64TI2V", "OurTI2V"))
+    ref, m64, our = copy.deepcopy(model), copy.deepcopy(model).double(), copy.deepcopy(model).to(DEV)
+    ref.__class__, m64.__class__, our.__class__ = RefCls, Ref64, OurCls
+    kw = dict(thresh=10.0, K=3, retention_ratio=0.25)  # 4 steps = 8 calls: miss, miss, then hits
+    wan_ref.install_magcache_wan22(RefCls, ratios, 4, **kw)
+    wan_ref.install_magcache_wan22(Ref64, ratios, 4, **kw)
+    mc.init_magcache_wan22(our, ratios, 4, **kw)
+    kinds = []
+    with torch.no_grad():
+        for call in range(6):
+            t = timesteps(900.0 - 100.0 * (call // 2))
+            c = ctx if call % 2 == 0 else ctx_null
+            a = ref([lat], t=t, context=[c], seq_len=seq_len)[0]
+            b = our([lat.to(DEV)], t=t.to(DEV), context=[c.to(DEV)], seq_len=seq_len)[0].cpu()
+            kinds.append(int(ref.last_skip))
+            assert b.shape == a.shape == (48, 3, 32, 48) and b.dtype == torch.float32
+            e_vs = rel_l2(b, a)
+            print(f"[ti2v call {call} {'hit' if kinds[-1] else 'miss'}] rel-L2 ours vs oracle {e_vs:.3e}")
+            assert e_vs <= 2e-2
+            assert rel_l2(OurCls.residual_cache[call % 2].cpu()[0], RefCls.residual_cache[call % 2][0, :n_tok]) <= 3e-2
+            if call == 0:
+                with wan_ref.exact_fp64():
+                    exact = m64([lat.double()], t=t.double(), context=[c.double()], seq_len=seq_len)[0]
+                e_ours, e_ref = rel_l2(b, exact), rel_l2(a, exact)
+                print(f"[ti2v] rel-L2: ours vs fp64 {e_ours:.3e} | oracle(bf16) vs fp64 {e_ref:.3e}")
+                assert e_ours <= 1.5 * e_ref + 1e-4
+                eng = our._mc_engine
+                assert eng.t_values == 2 and eng.runs == [(0, 384, 0), (384, n_tok, 1)] and len(eng.head_groups) == 3
+    assert kinds == [0, 0, 1, 1, 1, 1]
