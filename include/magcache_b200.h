@@ -339,6 +339,71 @@ int32_t mc_time_sinusoid(const double* pos_dev, int32_t n_pos, int32_t dim, floa
 /* elementwise helpers */
 int32_t mc_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * The whole patched forward in one call (SURVEY §8b `mc_dit_forward`): prologue -> { cache hit | block stack + residual } -> head,
+ * MagCache4Wan2.1/magcache_generate.py:229-275 and :293-305 for a text-to-video WanModel; the skip decision (:277-292) is the
+ * caller's (mc_ctrl_step). Native host code that issues the launch sequence of the Python engine (magcache_b200/wan.py) through
+ * the entry points above, on buffers carved out of ONE caller-owned workspace: same kernels, operands and order, bit-identical
+ * results. Built for the plain case (one sample, one timestep, one GPU, head_dim 128, 16 output channels); i2v / VACE /
+ * token-sharded / per-token-timestep forwards are sequenced by the Python engine.
+ * All weight pointers are DEVICE pointers in the engine's packed layout, borrowed (they must outlive the handle), 16-byte aligned:
+ * bf16 `[out, in]` matrices (`const void*`), fp32 vectors / small fp32 matrices (`const float*`); biases are the bf16-rounded values
+ * kept as fp32 (nn.Linear under autocast).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct mc_dit_dims {
+  int32_t dim, ffn_dim, num_heads, num_layers; /* dim == num_heads * 128 */
+  int32_t in_dim, out_dim;                     /* latent channels in (patch (1,2,2): in_dim*4 columns) and out (16) */
+  int32_t freq_dim, text_dim, text_len;
+  float eps;
+} mc_dit_dims;
+
+typedef struct mc_dit_block {                 /* one WanAttentionBlock [EXT upstream wan/modules/model.py] */
+  const float* mod;                           /* modulation               fp32 [6, dim] */
+  const void* w_qkv;  const float* b_qkv;     /* self_attn q|k|v fused    bf16 [3 dim, dim], fp32 [3 dim] */
+  const void* w_o;    const float* b_o;       /* self_attn.o */
+  const float* nqk;                           /* norm_q | norm_k weights  fp32 [2, dim] */
+  const float* n3_w;  const float* n3_b;      /* norm3 (affine LayerNorm) */
+  const void* c_wq;   const float* c_bq;      /* cross_attn.q */
+  const void* c_wkv;  const float* c_bkv;     /* cross_attn k|v fused     bf16 [2 dim, dim] */
+  const void* c_wo;   const float* c_bo;      /* cross_attn.o */
+  const float* c_nq;  const float* c_nk;      /* cross_attn norm_q / norm_k */
+  const void* w_f1;   const float* b_f1;      /* ffn[0]                   bf16 [ffn_dim, dim] */
+  const void* w_f2;   const float* b_f2;      /* ffn[2]                   bf16 [dim, ffn_dim] */
+} mc_dit_block;
+
+typedef struct mc_dit_weights {
+  const void* patch_w;  const float* patch_b; /* patch_embedding          bf16 [dim, in_dim*4] in (c, kt, kh, kw) order */
+  const void* text_w1;  const float* text_b1; /* text_embedding[0]        bf16 [dim, text_dim] */
+  const void* text_w2;  const float* text_b2; /* text_embedding[2]        bf16 [dim, dim] */
+  const float* time_w1; const float* time_b1; /* time_embedding[0]        fp32 [dim, freq_dim] */
+  const float* time_w2; const float* time_b2; /* time_embedding[2]        fp32 [dim, dim] */
+  const float* tproj_w; const float* tproj_b; /* time_projection[1]       fp32 [6 dim, dim] */
+  const float* head_mod;                      /* head.modulation          fp32 [2, dim] */
+  const float* head_wt; const float* head_b;  /* head.head weight TRANSPOSED fp32 [dim, 64], bias fp32 [64] */
+  const mc_dit_block* blocks;                 /* [num_layers] (copied by mc_dit_create) */
+} mc_dit_weights;
+
+typedef struct mc_dit mc_dit;
+/* NULL (and mc_last_error) on unsupported dims or null / misaligned pointers. No device work. */
+mc_dit* mc_dit_create(const mc_dit_dims* dims, const mc_dit_weights* weights);
+void mc_dit_destroy(mc_dit* h);
+/* Device scratch one (F, Hp, Wp) token grid needs: every activation of a forward (patch tokens, x0, the fp32 stream, q|k|v, FFN
+ * hidden, text embeddings, time embeddings, the head's prepared weight, split-KV partials). Host arithmetic only. */
+int32_t mc_dit_workspace_bytes(const mc_dit* h, int32_t F, int32_t Hp, int32_t Wp, int64_t* bytes_out);
+/* Bind the handle to a token grid: `workspace` (1024-byte aligned, >= mc_dit_workspace_bytes, caller-owned, one per stream of
+ * concurrent use) and the RoPE table fp32 [F*Hp*Wp, 128] (interleaved cos, sin; mc_rmsnorm_rope's layout). No device work. */
+int32_t mc_dit_bind(mc_dit* h, int32_t F, int32_t Hp, int32_t Wp, void* workspace, int64_t workspace_bytes, const float* rope_cos_sin);
+/* One patched forward on `stream`. latent fp32 [in_dim, F, 2Hp, 2Wp]; t_dev: the timestep as ONE device double; context bf16
+ * [text_len, text_dim], zero-padded (may be NULL when skip != 0: a hit does not read it); residual fp32 [F*Hp*Wp, dim]: the slot
+ * `residual_cache[cnt % 2]` — READ when skip != 0 (`x + residual_x`, :295), WRITTEN when skip == 0 (`x - ori_x`, :299);
+ * out fp32 [16, F, 2Hp, 2Wp]. All device pointers, 16-byte aligned. Returns the first failing entry point's code. */
+int32_t mc_dit_forward(mc_dit* h, const float* latent, const double* t_dev, const void* context_bf16, int32_t skip, float* residual,
+                       float* out, void* stream);
+/* The launch plan of mc_dit_forward(skip) as text, one line per launch, operands printed as name+byte_offset; nothing is launched
+ * (inspection / test aid: the CPU suite compares it with the sequence the Python engine issues). *needed = bytes incl. the
+ * terminator; the text is written when buf_bytes >= *needed. */
+int32_t mc_dit_plan(mc_dit* h, int32_t skip, char* buf, int64_t buf_bytes, int64_t* needed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,5 +11,6 @@ from .patch import (enable_token_shard, invalidate_engine, init_magcache, init_m
                     teacache_forward)
 from .sampler import FlowEulerSampler, FlowUniPCSampler, cfg_denoise_step, sampling_sigmas  # noqa: F401
 from .wan import WAN_CONFIGS, WanDims, WanEngine, WanModelHandle, WanWeights  # noqa: F401
+from .native import NativeWanForward  # noqa: F401
 
 __version__ = "0.1.0"

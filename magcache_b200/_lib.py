@@ -16,7 +16,7 @@ MC_F32, MC_BF16 = 0, 1
 MC_CMP_LT, MC_CMP_LE = 0, 1
 MC_RETAIN_FLOOR, MC_RETAIN_HALF_UP, MC_RETAIN_CEIL, MC_RETAIN_WAN22_T2V, MC_RETAIN_WAN22_I2V, MC_RETAIN_EXPLICIT = 0, 1, 2, 3, 4, 5
 MC_CTRL_SIGNED_ERR, MC_CTRL_RESET_AT_ZERO, MC_CTRL_RATIO_VETO, MC_CTRL_WRAP_KEEPS_ACC = 1, 2, 4, 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 MC_EPI_BIAS_BF16, MC_EPI_BIAS_GELU_BF16, MC_EPI_BIAS_GATE_RESID, MC_EPI_ROWBIAS_BF16, MC_EPI_BIAS_F32, MC_EPI_BIAS_GELU_ERF_BF16 = 0, 1, 2, 3, 4, 5
 MC_EPI_BIAS_GATE_RESID_BF16, MC_EPI_BIAS_SILU_BF16 = 6, 7
 
@@ -41,6 +41,25 @@ class TeaConfig(Structure):
 
 class TeaState(Structure):
     _fields_ = [("cnt", c_int32), ("pad", c_int32), ("accumulated", c_double * 2)]
+
+
+class DitDims(Structure):
+    _fields_ = [("dim", c_int32), ("ffn_dim", c_int32), ("num_heads", c_int32), ("num_layers", c_int32), ("in_dim", c_int32),
+                ("out_dim", c_int32), ("freq_dim", c_int32), ("text_dim", c_int32), ("text_len", c_int32), ("eps", c_float)]
+
+
+DIT_BLOCK_FIELDS = ("mod", "w_qkv", "b_qkv", "w_o", "b_o", "nqk", "n3_w", "n3_b", "c_wq", "c_bq", "c_wkv", "c_bkv", "c_wo", "c_bo", "c_nq",
+                    "c_nk", "w_f1", "b_f1", "w_f2", "b_f2")
+DIT_TOP_FIELDS = ("patch_w", "patch_b", "text_w1", "text_b1", "text_w2", "text_b2", "time_w1", "time_b1", "time_w2", "time_b2", "tproj_w",
+                  "tproj_b", "head_mod", "head_wt", "head_b")
+
+
+class DitBlock(Structure):
+    _fields_ = [(n, c_void_p) for n in DIT_BLOCK_FIELDS]
+
+
+class DitWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in DIT_TOP_FIELDS] + [("blocks", POINTER(DitBlock))]
 
 
 class CtrlState(Structure):
@@ -106,6 +125,10 @@ SIGNATURES = {
     "mc_transpose_bf16": [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p],
     "mc_time_sinusoid": [c_void_p, c_int32, c_int32, c_void_p, c_void_p],
     "mc_cast": [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
+    "mc_dit_workspace_bytes": [c_void_p, c_int32, c_int32, c_int32, POINTER(c_int64)],
+    "mc_dit_bind": [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p],
+    "mc_dit_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p],
+    "mc_dit_plan": [c_void_p, c_int32, c_void_p, c_int64, POINTER(c_int64)],
 }
 
 if not os.path.exists(LIB_PATH):
@@ -126,7 +149,9 @@ for _name, _args in SIGNATURES.items():
 lib.mc_ctrl_create.restype, lib.mc_ctrl_create.argtypes = c_void_p, [POINTER(CtrlConfig), c_int32]
 lib.mc_ctrl_state_of.restype, lib.mc_ctrl_state_of.argtypes = POINTER(CtrlState), [c_void_p]
 lib.mc_ctrl_destroy.restype, lib.mc_ctrl_destroy.argtypes = None, [c_void_p]
-OTHER_EXPORTS = ("mc_last_error", "mc_ctrl_create", "mc_ctrl_state_of", "mc_ctrl_destroy")
+lib.mc_dit_create.restype, lib.mc_dit_create.argtypes = c_void_p, [POINTER(DitDims), POINTER(DitWeights)]
+lib.mc_dit_destroy.restype, lib.mc_dit_destroy.argtypes = None, [c_void_p]
+OTHER_EXPORTS = ("mc_last_error", "mc_ctrl_create", "mc_ctrl_state_of", "mc_ctrl_destroy", "mc_dit_create", "mc_dit_destroy")
 
 if lib.mc_abi_version() != ABI_VERSION:
     raise ImportError(f"{LIB_PATH} has ABI version {lib.mc_abi_version()}, this package needs {ABI_VERSION}: rebuild with "

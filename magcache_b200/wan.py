@@ -239,13 +239,13 @@ def rope_table(grid, head_dim, device):
                           np.broadcast_to(angs[1][None, :, None, :], (f, h, w, split[1])),
                           np.broadcast_to(angs[2][None, None, :, :], (f, h, w, split[2]))], axis=-1).reshape(f * h * w, c)
     cs = np.stack([np.cos(ang), np.sin(ang)], axis=-1).reshape(f * h * w, head_dim)
-    return torch.from_numpy(cs.astype(np.float32)).to(device)
+    return torch.from_numpy(cs.astype(np.float32)).clone().to(device)  # clone: torch-allocated (64-byte aligned) storage on CPU too
 
 
 class WanEngine:
     """Runs prologue / block stack / head of one Wan forward on the kernels. One engine per (weights, token count)."""
 
-    def __init__(self, weights: WanWeights, shard_world=1, shard_rank=0, shard_group=None):
+    def __init__(self, weights: WanWeights, shard_world=1, shard_rank=0, shard_group=None, native=None):
         self.w = weights
         self.dims = weights.dims
         self.device = weights.device
@@ -260,6 +260,12 @@ class WanEngine:
         self.use_graphs = (shard_world > 1) if env is None else (env == "1")
         self._graphs = {}
         self.xch = None  # K|V exchange of a token-sharded engine (shard.py)
+        # native=True / MC_NATIVE=1: plain forwards (one timestep, one GPU, t2v, 16 output channels) are ONE call into the library —
+        # `mc_dit_forward` (csrc/dit_forward.cu) issues the launch sequence below from native code, bit-identically. Off by default:
+        # per-kernel timing tags (`ops.PROFILE`, what bench.py's attribution reads) exist only on the Python-sequenced path.
+        env_n = os.environ.get("MC_NATIVE")
+        self.native = (env_n == "1") if native is None else bool(native)
+        self._nat, self._nat_grid = None, None
         self._slot = 0   # CFG slot of the forward in flight (selects the output window of a sharded engine)
         self.hit_sum_bf16 = False  # TeaCache comparator: the hit sum is rounded to bf16 before the head (wan_teacache.py:569/577)
         self._step = None          # (cond, x_latent, guide_scale, coef_x, coef_v, out) armed by `arm_step` for the next forward
@@ -472,6 +478,8 @@ class WanEngine:
     def _body(self, kind, slot):
         """prologue -> {hit: head(x0 + residual) | miss: block stack, residual = x - x0, head(x)} on the staged inputs."""
         self._slot = slot
+        if self._native_ok():
+            return self._native_body(kind, slot)
         x0, e, e0, ctx = self.prologue(need_ctx=(kind != "hit"))
         if kind == "hit":
             # `x + residual_x` (:295) is formed inside the head kernel; TeaCache's in-place bf16 `x += residual` rounds the sum first
@@ -479,6 +487,25 @@ class WanEngine:
         xs = self.run_blocks(x0, e0, ctx, self.grid)
         ops.residual_sub(xs, x0, out=self.res[slot])  # magcache_generate.py:299, written into the slot's fixed buffer
         return self.head(xs, e, self.grid)
+
+    def _native_ok(self):
+        if not self.native or self.shard is not None or self.runs is not None or self.pad_row or self._step is not None or self.hit_sum_bf16:
+            return False
+        from . import native
+        return native.supported(self.dims) and getattr(ops, "PROFILE", None) is None
+
+    def _native_body(self, kind, slot):
+        """The same forward through `mc_dit_forward`: staged latent / timestep / text in, the slot's residual read (hit) or written (miss)."""
+        from . import native
+        if self._nat is None:
+            self._nat = native.NativeWanForward(self.w)
+        if self._nat_grid != self.grid:
+            self._nat.bind(self.grid, self._rope_for(self.grid))
+            self._nat_grid = self.grid
+        skip = kind == "hit"
+        out = self._nat.forward(self.s_lat, self.s_t, self.ctx_in, skip, self.res[slot])
+        ops._count(self._nat.launches(skip))
+        return out
 
     def arm_step(self, cond, x_latent, guide_scale, coef_x, coef_v, out=None):
         """Fold the caller loop's CFG combine + scheduler update (eval/.../wan_magcache.py:301-310) into the head pass of the NEXT
