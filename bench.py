@@ -397,6 +397,13 @@ def run_ours(args, rank, world):
                               "scheduler update in the epilogue of the unconditional call)", "bound": "hbm",
                     "algorithmic_bytes": hb, "ms": kern["head_hit_fused"]["ms_avg"], "achieved": gbs, "unit": "GB/s", "peak": pk["hbm_gbs"],
                     "frac": gbs / pk["hbm_gbs"], "frac_of_8TBps": gbs / 8000.0, "peak_source": pk["src"], "measured": roofline_source}
+        if world == 1:
+            # a hit forward is host-bound (8 small launches, the GPU idles between them), so the events around its head launch also see
+            # the host's launch latency; the same launch on the engine's own buffers, queued back to back, gives the kernel's own rate
+            try:
+                hit_path["queued"] = bench_hit_head(eng, n_loc * D * 6 + n_loc * 64 * 4, pk)
+            except Exception as exc:  # noqa: BLE001 — supplementary figure: never takes the line down
+                hit_path["queued"] = {"error": repr(exc)[:200]}
     # the stand-alone `x + residual_x` kernel (FLUX / HunyuanVideo hit branch, VACE): a micro-benchmark, NOT on the Wan hit path above
     k1 = bench_k1(dev, pk) if MODEL_KEY == "t2v-1.3B" else None
 
@@ -493,15 +500,18 @@ def run_mmdit(args, rank, world):
     import magcache_b200 as mc
     from magcache_b200 import mmdit, ops
 
-    if world != 1:
-        raise SystemExit("--workload flux / hunyuan720p: single GPU (token-sharded MMDiT runs are covered by tests/test_shard_gpu.py)")
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
+    if world > 1:  # ONE sample, image tokens sharded over the ranks, text tokens replicated, K|V rows exchanged peer to peer per attention
+        dist.init_process_group("nccl", device_id=dev)
+    skw = dict(shard_world=world, shard_rank=rank) if world > 1 else {}
     g = torch.Generator(device=dev).manual_seed(0)
     flux = args.workload == "flux"
     if flux:
         total_steps, preset = 28, dict(thresh=0.24, K=5, retention_ratio=0.1)
-        model = mmdit.MMDiTHandle(mmdit.FluxEngine(mmdit.random_flux_weights(dev)))
+        model = mmdit.MMDiTHandle(mmdit.FluxEngine(mmdit.random_flux_weights(dev), **skw))
         mc.init_magcache_flux(model, total_steps, **preset)
         n_img, n_txt, heads, layers = 4096, 512, 24, 19 + 38
         hs_h = torch.randn(1, n_img, 64, generator=torch.Generator().manual_seed(0)).bfloat16().pin_memory()
@@ -519,7 +529,7 @@ def run_mmdit(args, rank, world):
         workload = "FLUX.1-dev 1024x1024, 28 steps, MagCache E024K5R01 (BASELINE configs[0])"
     else:
         total_steps, preset = 50, dict(thresh=0.24, K=6, retention_ratio=0.2)
-        model = mmdit.MMDiTHandle(mmdit.HunyuanEngine(mmdit.random_hunyuan_weights(dev)))
+        model = mmdit.MMDiTHandle(mmdit.HunyuanEngine(mmdit.random_hunyuan_weights(dev), **skw))
         mc.init_magcache_hunyuan(model, total_steps, **preset)
         grid = (33, 45, 80)  # 129 frames -> 33 latent frames; 720 x 1280 -> 90 x 160 latent -> 45 x 80 patches
         n_img, n_txt, heads, layers = grid[0] * grid[1] * grid[2], 256, 24, 20 + 40
@@ -551,8 +561,13 @@ def run_mmdit(args, rank, world):
         ops.PROFILE = {} if tags else None
         ops.PROFILE_TAGS = tags
         n0 = ops.LAUNCHES
-        sampler = ClockSampler(0)
-        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        barrier()
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -564,32 +579,42 @@ def run_mmdit(args, rank, world):
             else:
                 call(i, hs, enc)
         e1.record()
-        torch.cuda.synchronize()
+        barrier()
         clocks = sampler.stop()
         prof, ops.PROFILE, ops.PROFILE_TAGS = ops.PROFILE, None, None
-        return e0.elapsed_time(e1), ops.LAUNCHES - n0, clocks, prof
+        t_ms = e0.elapsed_time(e1)
+        if world > 1:  # the job's time is the slowest rank's
+            tms = torch.tensor([t_ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            t_ms = float(tms.item())
+        return t_ms, ops.LAUNCHES - n0, clocks, prof
 
     ms, launches, clocks, prof = timed(False, {"mmdit_attn"})
     ms_e2e, _, _, _ = timed(True, None)
     pk = peaks()
     S = n_img + n_txt
-    attn_flops = 4.0 * S * S * heads * 128
+    attn_flops = 4.0 * (n_img // world + n_txt) * S * heads * 128  # per GPU: its image rows + the replicated text rows x all keys
     kern = {t: {"launches": len(ev), "ms_avg": sum(a.elapsed_time(b) for a, b in ev) / len(ev), "ms_total": sum(a.elapsed_time(b) for a, b in ev)} for t, ev in (prof or {}).items()}
     roof = None
     if "mmdit_attn" in kern:
         ach = attn_flops / (kern["mmdit_attn"]["ms_avg"] * 1e-3) / 1e12
-        roof = {"kernel": f"attn_long_kernel (joint attention, {S}x{S}x{heads} heads)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+        roof = {"kernel": f"attn_long_kernel (joint attention, {n_img // world + n_txt}x{S}x{heads} heads per GPU)", "bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)", "share_of_step": kern["mmdit_attn"]["ms_total"] / ms,
                 "flops_per_launch": attn_flops, "measured": "CUDA events around every launch inside the timed region"}
-    line = {"metric": "denoising_steps_per_sec", "value": steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+    line = {"metric": "denoising_steps_per_sec", "value": steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "image_tokens": n_img, "text_tokens": n_txt, "layers": layers, "parallelism": "single GPU",
+            "config": {"workload": workload, "image_tokens": n_img, "text_tokens": n_txt, "layers": layers,
+                       "parallelism": "single GPU" if world == 1 else f"image tokens sharded over {world} GPUs ({n_img // world} each), text tokens replicated, "
+                                      f"K|V rows pushed peer to peer per attention ({type(getattr(model, '_mc_flux_engine', None) or model._mc_hunyuan_engine).__name__})",
                        "schedule": f"the first {steps} calls of the {total_steps}-step schedule from cnt = 0"},
             "sec_per_sample_if_linear": (ms * 1e-3) * total_steps / steps,
             "e2e": {"value": steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": hs_h.numel() * 2 + enc_h.numel() * 2,
                     "d2h_bytes_per_step": hs_h.numel() * 2, "ms_per_step": ms_e2e / steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kern}
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        shutdown_distributed(model)
 
 
 def shutdown_distributed(model):
@@ -642,6 +667,28 @@ def bench_k1(dev, pk):
     return {"kernel": "axpb_kernel<bf16,f32,f32> (x + residual as a stand-alone pass, 503.2 MB algorithmic; micro-benchmark)", "bound": "hbm", "ms": ms, "achieved": gbs, "unit": "GB/s",
             "peak": pk["hbm_gbs"], "frac": gbs / pk["hbm_gbs"], "frac_of_8TBps": gbs / 8000.0, "peak_source": pk["src"],
             "method": "30 back-to-back launches rotating over 3 buffer sets (1.5 GB), CUDA events"}
+
+
+def bench_hit_head(eng, algorithmic_bytes, pk):
+    """The hit branch's kernel exactly as the path launches it (bf16 patch embedding + the slot's fp32 residual -> fp32 prediction,
+    no step epilogue), 30 launches queued back to back on the engine's buffers of the last forward; every launch streams 302 MB
+    (> the 126 MB L2)."""
+    import torch
+    e, _ = eng.time_embedding()
+    for _ in range(3):
+        eng.head(eng.x0, e, eng.grid, residual=eng.res[0])
+    torch.cuda.synchronize()
+    iters = 30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        eng.head(eng.x0, e, eng.grid, residual=eng.res[0])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    gbs = algorithmic_bytes / (ms * 1e-3) / 1e9
+    return {"ms": ms, "achieved": gbs, "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "frac_of_8TBps": gbs / 8000.0, "algorithmic_bytes": algorithmic_bytes,
+            "method": "30 launches of head_tc_kernel<hit> on the engine's own x0 / residual buffers queued back to back, CUDA events around the batch"}
 
 
 def cpu_baseline_leg():
