@@ -286,6 +286,21 @@ int32_t mc_p2p_push(const void* src, void* const* dst_ptrs, void* const* flag_pt
                     void* stream);
 int32_t mc_p2p_wait(const uint32_t* flags, int32_t n, const uint32_t* epoch, void* stream);
 
+/* ---- the collective formulation of the same exchange (SURVEY §8b `mc_nccl_init` / `mc_allgather_kv`; csrc/nccl_gather.cu) ---------
+ * `dist.all_gather(tensor_list, input_)` + `torch.cat` of videosys/core/comm.py:272-292 as ONE ncclAllGather on the caller's
+ * stream. NCCL is looked up at run time (the copy the process already loaded, else libnccl.so.2): MC_ERR_STATE when it is absent.
+ * mc_nccl_unique_id: 128 bytes created by ONE rank and handed to the others by the host (any channel).
+ * mc_nccl_init:      collective over the `world` ranks, each on its own current device; NULL + mc_last_error() on failure.
+ * mc_allgather_kv:   k_full[r * n : (r+1) * n] = rank r's k_local[0 : n] (n = elems_per_rank bf16 elements, same on every rank), and
+ *                    the same for v when v_local / v_full are given (both NULL: one fused K|V buffer, the engines' layout);
+ *                    stream-ordered, capturable into a CUDA graph. */
+typedef struct mc_nccl mc_nccl;
+int32_t mc_nccl_unique_id(void* id_out_128);
+mc_nccl* mc_nccl_init(int32_t rank, int32_t world, const void* unique_id_128);
+int32_t mc_nccl_destroy(mc_nccl* h);
+int32_t mc_allgather_kv(mc_nccl* h, const void* k_local, const void* v_local, void* k_full, void* v_full, int64_t elems_per_rank,
+                        void* stream);
+
 /* Small fp32 linear for the time-embedding path (autocast-disabled region, magcache_generate.py:249-254):
  * y[m, n] = act(sum_k x[m,k] * W[n,k] + b[n]), M <= 8. act: 0 none, 1 SiLU applied to the INPUT x first (time_projection),
  * 2 SiLU applied to the output. */

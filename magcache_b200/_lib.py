@@ -125,6 +125,9 @@ SIGNATURES = {
     "mc_transpose_bf16": [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p],
     "mc_time_sinusoid": [c_void_p, c_int32, c_int32, c_void_p, c_void_p],
     "mc_cast": [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p],
+    "mc_nccl_unique_id": [c_void_p],
+    "mc_nccl_destroy": [c_void_p],
+    "mc_allgather_kv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     "mc_dit_workspace_bytes": [c_void_p, c_int32, c_int32, c_int32, POINTER(c_int64)],
     "mc_dit_bind": [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p],
     "mc_dit_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p],
@@ -151,7 +154,8 @@ lib.mc_ctrl_state_of.restype, lib.mc_ctrl_state_of.argtypes = POINTER(CtrlState)
 lib.mc_ctrl_destroy.restype, lib.mc_ctrl_destroy.argtypes = None, [c_void_p]
 lib.mc_dit_create.restype, lib.mc_dit_create.argtypes = c_void_p, [POINTER(DitDims), POINTER(DitWeights)]
 lib.mc_dit_destroy.restype, lib.mc_dit_destroy.argtypes = None, [c_void_p]
-OTHER_EXPORTS = ("mc_last_error", "mc_ctrl_create", "mc_ctrl_state_of", "mc_ctrl_destroy", "mc_dit_create", "mc_dit_destroy")
+lib.mc_nccl_init.restype, lib.mc_nccl_init.argtypes = c_void_p, [c_int32, c_int32, c_void_p]
+OTHER_EXPORTS = ("mc_last_error", "mc_ctrl_create", "mc_ctrl_state_of", "mc_ctrl_destroy", "mc_dit_create", "mc_dit_destroy", "mc_nccl_init")
 
 if lib.mc_abi_version() != ABI_VERSION:
     raise ImportError(f"{LIB_PATH} has ABI version {lib.mc_abi_version()}, this package needs {ABI_VERSION}: rebuild with "

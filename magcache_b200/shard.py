@@ -106,8 +106,26 @@ class CollectiveExchange:
         self.kv_loc = torch.zeros(shard.n_slots, width, **bf)          # pad slots stay zero
         self.kv_all = torch.empty(shard.n_padded + extra_rows, width, **bf)
         self._work = None
+        # MC_SHARD_NCCL=capi (CUDA): the gather is `mc_allgather_kv` — ncclAllGather behind the C ABI on a communicator of this
+        # exchange's own (csrc/nccl_gather.cu) — instead of torch.distributed's; same buffers, same ordering
+        self._nccl = None
+        if torch.device(device).type == "cuda" and os.environ.get("MC_SHARD_NCCL", "") == "capi":
+            from . import _lib
+            uid = ctypes.create_string_buffer(128)
+            if shard.rank == 0:
+                _lib.check(_lib.lib.mc_nccl_unique_id(uid))
+            box = [bytes(uid.raw)]
+            dist.broadcast_object_list(box, src=0 if shard.group is None else dist.get_global_rank(shard.group, 0), group=shard.group)
+            h = _lib.lib.mc_nccl_init(shard.rank, shard.world, ctypes.create_string_buffer(box[0], 128))
+            if not h:
+                raise _lib.MagCacheError(_lib.MC_ERR_STATE, _lib.lib.mc_last_error().decode("utf-8", "replace"))
+            self._lib, self._nccl = _lib, h
+            self.comm = torch.cuda.Stream(device=device)
+            self._done = None
 
     def own_rows(self, i):
+        if self._nccl is not None and self._done is not None:
+            torch.cuda.current_stream().wait_event(self._done)  # the gather that last read kv_loc has drained
         return self.kv_loc[:self.sh.n_local]
 
     def tail_rows(self, i):
@@ -115,11 +133,24 @@ class CollectiveExchange:
         return self.kv_all[self.sh.n_padded:]
 
     def begin(self, i):
+        if self._nccl is not None:  # on a side stream, so that the q projection overlaps it like the async c10d gather does
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.comm.wait_event(ev)
+            self._lib.check(self._lib.lib.mc_allgather_kv(self._nccl, self.kv_loc.data_ptr(), None, self.kv_all.data_ptr(), None,
+                                                          self.kv_loc.numel(), self.comm.cuda_stream))
+            self._done = torch.cuda.Event()
+            self._done.record(self.comm)
+            return
         self._work = gather_rows(self.kv_loc, self.kv_all[:self.sh.n_padded], self.sh.group, async_op=True)
 
     def keys_values(self, i):
         """(gathered [N (+ extra), width] view, extra keyword arguments for ops.attention). Blocks the stream until the rows are there."""
-        self._work.wait()
+        if self._nccl is not None:
+            torch.cuda.current_stream().wait_event(self._done)
+        else:
+            self._work.wait()
         return self.kv_all[:self.sh.n_tokens + self.extra], {}
 
     def head_output(self, slot):
@@ -129,10 +160,14 @@ class CollectiveExchange:
         return sum_partial_outputs(out, self.sh.group)
 
     def join(self):
-        pass
+        if self._nccl is not None and self._done is not None:
+            torch.cuda.current_stream().wait_event(self._done)
 
     def close(self):
-        pass
+        if self._nccl is not None:
+            torch.cuda.synchronize()
+            self._lib.lib.mc_nccl_destroy(self._nccl)
+            self._nccl = None
 
 
 class _RawCuda:

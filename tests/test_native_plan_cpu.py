@@ -209,3 +209,19 @@ def test_native_handle_argument_checks():
     assert not lib.mc_dit_create(ctypes.byref(bad), ctypes.byref(wts)) and b"unsupported dims" in lib.mc_last_error()
     ok = _lib.DitDims(256, 512, 2, 1, 16, 16, 256, 128, 32, 1e-6)
     assert not lib.mc_dit_create(ctypes.byref(ok), ctypes.byref(wts)) and b"null or not 16-byte aligned" in lib.mc_last_error()
+
+
+def test_nccl_gather_abi_argument_checks():
+    """`mc_nccl_*` / `mc_allgather_kv` without a GPU: the entry points exist, validate their arguments and report through
+    mc_last_error; a communicator is never created here (that is a collective over GPUs: tests/test_shard_gpu.py, 2 GPUs)."""
+    lib = _lib.lib
+    assert lib.mc_nccl_unique_id(None) == _lib.MC_ERR_INVALID
+    uid = ctypes.create_string_buffer(128)
+    rc = lib.mc_nccl_unique_id(uid)
+    assert rc in (_lib.MC_OK, _lib.MC_ERR_STATE, _lib.MC_ERR_CUDA)  # OK when a libnccl.so.2 is loadable on this host
+    if rc == _lib.MC_OK:
+        assert any(uid.raw)
+    assert not lib.mc_nccl_init(0, 2, None) and b"null id" in lib.mc_last_error()
+    assert not lib.mc_nccl_init(3, 2, uid) and b"rank 3 of 2" in lib.mc_last_error()
+    assert lib.mc_allgather_kv(None, 16, None, 16, None, 8, None) == _lib.MC_ERR_INVALID and b"null communicator" in lib.mc_last_error()
+    assert lib.mc_nccl_destroy(None) == _lib.MC_OK

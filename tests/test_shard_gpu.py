@@ -34,14 +34,15 @@ def _worker(rank, world, initfile, results, latent_shape):
         t = torch.tensor([640.0], device=dev)
         table = [1.0, 1.0] + [0.999] * 18
         outs = {}
-        for mode in ("single", "p2p", "p2p_graphs", "collective"):
-            os.environ["MC_SHARD_P2P"] = "0" if mode == "collective" else "1"
-            os.environ["MC_GRAPHS"] = "1" if mode == "p2p_graphs" else "0"
+        for mode in ("single", "p2p", "p2p_graphs", "collective", "collective_capi", "collective_capi_graphs"):
+            os.environ["MC_SHARD_P2P"] = "0" if mode.startswith("collective") else "1"
+            os.environ["MC_SHARD_NCCL"] = "capi" if "capi" in mode else ""  # mc_allgather_kv (ncclAllGather behind the C ABI) vs c10d
+            os.environ["MC_GRAPHS"] = "1" if mode.endswith("graphs") else "0"
             w = mc.WanWeights.random(dims, dev, seed=5)
             m = mc.WanModelHandle(w) if mode == "single" else mc.WanModelHandle(w, shard_world=world, shard_rank=rank)
             mc.init_magcache(m, 10, thresh=0.12, K=2, retention_ratio=0.1, mag_ratios=table)
             seq = []
-            for rep in range(3 if mode == "p2p_graphs" else 1):  # graphs: eager, capture, replay
+            for rep in range(3 if mode.endswith("graphs") else 1):  # graphs: eager, capture, replay
                 mc.reset_magcache(m)
                 seq = [m([lat], t=t, context=[ctx], seq_len=n_tok)[0].clone() for _ in range(4)]  # miss, miss, hit, hit
             outs[mode] = (seq, m.residual_cache[0].clone(), m._mc_engine)
@@ -49,13 +50,16 @@ def _worker(rank, world, initfile, results, latent_shape):
             dist.barrier()
         ref_seq, ref_cache, _ = outs["single"]
         res = {}
-        for mode in ("p2p", "p2p_graphs", "collective"):
+        for mode in ("p2p", "p2p_graphs", "collective", "collective_capi", "collective_capi_graphs"):
             seq, cache, eng = outs[mode]
             sh = eng.shard
             errs = [rel_l2(a, b) for a, b in zip(seq, ref_seq)]
             c_err = rel_l2(cache.view(sh.n_local, 256), ref_cache.view(n_tok, 256)[sh.start:sh.stop])
-            res[mode] = (max(errs), c_err, type(eng.xch).__name__)
+            res[mode] = (max(errs), c_err, type(eng.xch).__name__ + ("+capi" if getattr(eng.xch, "_nccl", None) else ""))
         results[rank] = (res, float(ref_seq[0].abs().mean()))
+        for mode in ("collective_capi", "collective_capi_graphs"):  # destroy the exchanges' own NCCL communicators before the group goes
+            outs[mode][2]._graphs.clear()
+            outs[mode][2].xch.close()
     finally:
         dist.destroy_process_group()
 
@@ -73,6 +77,7 @@ def test_sharded_forward_matches_single_gpu(latent_shape):
             res, mag = results[r]
             assert mag > 0
             assert res["p2p"][2] == "P2PExchange" and res["collective"][2] == "CollectiveExchange"
+            assert res["collective_capi"][2] == res["collective_capi_graphs"][2] == "CollectiveExchange+capi"
             for mode, (err, c_err, _) in res.items():
                 assert err < 3e-3, (mode, "outputs", err)
                 assert c_err < 3e-3, (mode, "residual cache slice", c_err)

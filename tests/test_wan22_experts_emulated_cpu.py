@@ -152,3 +152,39 @@ def test_ti2v_uniform_and_scattered_timesteps(emulated):
         assert float((a - b).norm() / a.norm()) < 2e-2
         with pytest.raises(NotImplementedError):
             our([lat], t=torch.arange(48.0).unsqueeze(0), context=[ctx], seq_len=48)
+
+
+def test_timestep_ranges_reconstruct_t_exactly():
+    """`WanEngine._stage_t` (the host reduction of a per-token `t`, MagCache4Wan2.2/magcache_generate.py:263-264): for random piecewise-
+    constant timestep vectors the (row range, value index) list must reproduce `t` row by row, cover every row exactly once, reuse one
+    index per distinct value — also clipped to a rank's rows of a token shard."""
+    import numpy as np
+    from magcache_b200.shard import TokenShard
+    rng = np.random.default_rng(0)
+    w = mc.WanWeights.random(mc.WanDims(256, 512, 2, 1, text_dim=64, text_len=8), torch.device("cpu"))
+    for trial in range(40):
+        n = int(rng.integers(5, 400))
+        vals = rng.choice([0.0, 17.5, 250.0, 499.0, 731.25, 999.0], size=int(rng.integers(1, 5)), replace=False)
+        cuts = np.sort(rng.choice(np.arange(1, n), size=min(n - 1, int(rng.integers(0, 7))), replace=False))
+        t = np.empty(n)
+        for seg, (a, b) in enumerate(zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [n]]))):
+            t[a:b] = vals[seg % len(vals)]
+        for world in (1, 3):
+            if world > 1 and n < world:
+                continue
+            for rank in range(world):
+                eng = mc.WanEngine(w)
+                eng.n_keys, eng.pad_row = n, 0
+                eng.s_t = torch.zeros(wan_mod.MAX_T_VALUES, dtype=torch.float64)
+                eng.shard = TokenShard(rank, world, n) if world > 1 else None
+                eng._stage_t(torch.from_numpy(t).unsqueeze(0))
+                lo, hi = (eng.shard.start, eng.shard.stop) if eng.shard is not None else (0, n)
+                if eng.runs is None:
+                    assert len(set(t.tolist())) == 1 and eng.t_values == 1 and float(eng.s_t[0]) == t[0]
+                    continue
+                got = np.full(hi - lo, np.nan)
+                for r0, r1, u in eng.runs:
+                    assert 0 <= r0 < r1 <= hi - lo and np.isnan(got[r0:r1]).all()
+                    got[r0:r1] = float(eng.s_t[u])
+                assert np.array_equal(got, t[lo:hi]), (trial, world, rank)
+                assert eng.t_values == len(set(t.tolist())) == len(set(eng.s_t[:eng.t_values].tolist()))
