@@ -162,6 +162,7 @@ class CollectiveExchange:
     def join(self):
         if self._nccl is not None and self._done is not None:
             torch.cuda.current_stream().wait_event(self._done)
+            self._done = None  # a later forward (possibly captured into a graph of its own) must not wait on this event again
 
     def close(self):
         if self._nccl is not None:
