@@ -85,3 +85,41 @@ def test_native_patched_forward_follows_the_oracle():
             assert rel_l2(b["nat"].cpu(), a) <= 2e-2, (call, rel_l2(b["nat"].cpu(), a))
             assert type(ours["nat"]).accumulated_err == type(ref).accumulated_err and type(ours["nat"]).cnt == type(ref).cnt
     assert 0 < sum(kinds) < 12 and ours["nat"]._mc_engine._nat is not None
+
+
+def test_nccl_gather_capi_single_rank_eager_and_captured():
+    """`mc_nccl_unique_id` / `mc_nccl_init` / `mc_allgather_kv` / `mc_nccl_destroy` on one GPU (a communicator of one rank: the gather is
+    the identity): run-time lookup of libnccl, communicator creation, the fused K|V form and the two-buffer form, eagerly and captured
+    into a CUDA graph and replayed. (Two ranks: tests/test_shard_gpu.py, modes collective_capi*.)"""
+    import ctypes
+    from magcache_b200 import _lib
+    lib = _lib.lib
+    uid = ctypes.create_string_buffer(128)
+    _lib.check(lib.mc_nccl_unique_id(uid))
+    h = lib.mc_nccl_init(0, 1, uid)
+    assert h, lib.mc_last_error()
+    try:
+        g = torch.Generator(device=DEV).manual_seed(0)
+        k, v = (torch.randn(1024, 512, device=DEV, generator=g).bfloat16() for _ in range(2))
+        kf, vf = torch.zeros_like(k), torch.zeros_like(v)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.mc_allgather_kv(h, k.data_ptr(), None, kf.data_ptr(), None, k.numel(), stream))
+        torch.cuda.synchronize()
+        assert torch.equal(kf, k)
+        kf.zero_()
+        _lib.check(lib.mc_allgather_kv(h, k.data_ptr(), v.data_ptr(), kf.data_ptr(), vf.data_ptr(), k.numel(), stream))
+        torch.cuda.synchronize()
+        assert torch.equal(kf, k) and torch.equal(vf, v)
+        assert lib.mc_allgather_kv(h, k.data_ptr(), v.data_ptr(), kf.data_ptr(), None, k.numel(), stream) == _lib.MC_ERR_INVALID
+        kf.zero_(), vf.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            _lib.check(lib.mc_allgather_kv(h, k.data_ptr(), v.data_ptr(), kf.data_ptr(), vf.data_ptr(), k.numel(), torch.cuda.current_stream().cuda_stream))
+        k.mul_(2.0)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(kf, k) and torch.equal(vf, v)
+        del graph
+    finally:
+        torch.cuda.synchronize()
+        assert lib.mc_nccl_destroy(h) == _lib.MC_OK
