@@ -225,3 +225,58 @@ def test_nccl_gather_abi_argument_checks():
     assert not lib.mc_nccl_init(3, 2, uid) and b"rank 3 of 2" in lib.mc_last_error()
     assert lib.mc_allgather_kv(None, 16, None, 16, None, 8, None) == _lib.MC_ERR_INVALID and b"null communicator" in lib.mc_last_error()
     assert lib.mc_nccl_destroy(None) == _lib.MC_OK
+
+
+def test_native_plan_at_the_benchmarked_shape():
+    """The plan of `mc_dit_forward` for BASELINE configs[1] itself (Wan2.1-T2V-1.3B, 832x480x81f: 32 760 tokens, dim 1536, ffn 8960,
+    12 heads, 30 layers) — no weights are needed to PLAN, so the weight pointers are stand-in addresses. Checks the launch count, that
+    every operand resolves to a known buffer inside its bounds, the GEMM shapes / leading dimensions / epilogues per layer, the
+    algorithmic FLOPs the plan adds up to (283.0 TF per forward) and the workspace size."""
+    lib = _lib.lib
+    D, Fd, H, L, N, TL, TD = 1536, 8960, 12, 30, 21 * 30 * 52, 512, 4096
+    dims = _lib.DitDims(D, Fd, H, L, 16, 16, 256, TD, TL, 1e-6)
+    addr = iter(range(1 << 44, 1 << 46, 1 << 32))  # distinct, 16-byte aligned, 4 GB apart: never dereferenced by mc_dit_plan
+    blocks = (_lib.DitBlock * L)()
+    for b in blocks:
+        for name in _lib.DIT_BLOCK_FIELDS:
+            setattr(b, name, next(addr))
+    w = _lib.DitWeights()
+    for name in _lib.DIT_TOP_FIELDS:
+        setattr(w, name, next(addr))
+    w.blocks = ctypes.cast(blocks, ctypes.POINTER(_lib.DitBlock))
+    h = lib.mc_dit_create(ctypes.byref(dims), ctypes.byref(w))
+    assert h, lib.mc_last_error()
+    need = ctypes.c_int64(0)
+    _lib.check(lib.mc_dit_workspace_bytes(h, 21, 30, 52, ctypes.byref(need)))
+    act = N * (64 * 2 + D * 2 * 4 + D * 4 + 3 * D * 2 + Fd * 2)  # tok, x0 / h / att / cq, xs, qkv, ffn
+    assert act < need.value < act + (64 << 20), (need.value, act)      # + text / time buffers, head workspace, split-KV partials
+    _lib.check(lib.mc_dit_bind(h, 21, 30, 52, 1 << 40, need.value, next(addr)))
+    plans = {}
+    for skip in (0, 1):
+        n = ctypes.c_int64(0)
+        _lib.check(lib.mc_dit_plan(h, skip, None, 0, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value)
+        _lib.check(lib.mc_dit_plan(h, skip, buf, n.value, ctypes.byref(n)))
+        plans[skip] = buf.value.decode().splitlines()
+    lib.mc_dit_destroy(h)
+    miss, hit = plans[0], plans[1]
+    assert len(miss) == 12 + 16 * L and len(hit) == 8 and hit[:7] == miss[:7] and "?" not in "".join(miss + hit)
+    assert hit[7] == f"head x=x0+0:1 r=residual+0 rows={N} cols={D} prep=head_prep+0 -> out+0" and miss[-1].startswith("head x=xs+0:0 r=null")
+    assert miss[-2] == f"residual_sub x_out=xs+0 x_in=x0+0 -> residual+0 n={N * D}"
+    flops, gemms = 0.0, []
+    for line in miss:
+        kv = dict(f.split("=", 1) for f in line.split()[1:] if "=" in f)
+        if line.startswith("gemm "):
+            M, Nn, K = int(kv["M"]), int(kv["N"]), int(kv["K"])
+            assert int(kv["lda"]) >= K and int(kv["ldb"]) >= K and int(kv["ldo"]) >= Nn
+            flops += 2.0 * M * Nn * K
+            gemms.append((M, Nn, K, int(kv["epi"]), kv["out"].split("+")[0], kv["gate"].split("+")[0]))
+        elif line.startswith("attention "):
+            flops += 4.0 * int(kv["Lq"]) * int(kv["Lk"]) * D
+            assert kv["q"].split("+")[0] in ("qkv", "cq") and int(kv["heads"]) == H
+    per_layer = gemms[3:3 + 7]
+    assert gemms[:3] == [(N, D, 64, 0, "x0", "null"), (TL, D, TD, 1, "ctx_h", "null"), (TL, D, D, 0, "ctx", "null")]
+    assert per_layer == [(N, 3 * D, D, 0, "qkv", "null"), (N, D, D, 2, "xs", "em"), (N, D, D, 0, "cq", "null"), (TL, 2 * D, D, 0, "ckv", "null"),
+                         (N, D, D, 2, "xs", "null"), (N, Fd, D, 1, "ffn", "null"), (N, D, Fd, 2, "xs", "em")]
+    assert all(gemms[3 + 7 * i:3 + 7 * (i + 1)] == per_layer for i in range(L))
+    assert abs(flops / 283.0e12 - 1.0) < 0.01, flops  # SURVEY §8d's figure for this forward
