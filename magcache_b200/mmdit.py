@@ -305,14 +305,17 @@ class MMDiTCore:
         stack; returns (head output, (norm_ratio, norm_std, cos_dis) against the previous residual or None on the first call). The
         statistics come from the fused fp32/fp64 reduction kernel — finer than the reference's bf16 tensor ops, which quantise them to
         multiples of 2^-8 (the shipped FLUX table is visibly bf16-quantised)."""
-        if self.shard is not None:
-            raise NotImplementedError("magcache_b200: token-sharded calibration of the MMDiT engines is not built (run it on one GPU)")
         x0 = self.prologue()
         self.hs[self.img].copy_(x0)
         x = self.run_blocks()
+        reduce = None
+        if self.shard is not None:  # the statistics are sums over the image tokens: add the partial sums of every token shard
+            from .shard import allreduce_stats
+            self.xch.join()
+            reduce = lambda st: allreduce_stats(st, self.shard.group)  # noqa: E731
         new = self.hit
         ops.residual_sub(x.contiguous(), x0, out=new)
-        stats = ops.residual_stats(new, self.res) if self.res_valid else None
+        stats = ops.residual_stats(new, self.res, reduce=reduce) if self.res_valid else None
         self.res, self.hit = new, self.res
         self.res_valid = True
         return self.head(x), stats

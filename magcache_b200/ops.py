@@ -143,8 +143,9 @@ def _finish_stats(stats_dev):
     return mean, math.sqrt(max(var, 0.0)), s2 / n
 
 
-def residual_stats(r_cur, r_prev, denom_eps=0.0):
-    """(norm_ratio, norm_std, cos_dis) of MagCache4Wan2.1/magcache_generate.py:167-169 in one pass + one sync."""
+def residual_stats(r_cur, r_prev, denom_eps=0.0, reduce=None):
+    """(norm_ratio, norm_std, cos_dis) of MagCache4Wan2.1/magcache_generate.py:167-169 in one pass + one sync. `reduce(stats_dev)` lets
+    a token-sharded caller add the four partial sums of every rank before they are finalised."""
     _dev(r_cur), _dev(r_prev)
     assert r_cur.shape == r_prev.shape and r_cur.is_contiguous() and r_prev.is_contiguous()
     cols = r_cur.shape[-1]
@@ -153,6 +154,8 @@ def residual_stats(r_cur, r_prev, denom_eps=0.0):
     check(lib.mc_residual_stats(r_cur.data_ptr(), _dt(r_cur), r_prev.data_ptr(), _dt(r_prev), rows, cols, float(denom_eps),
                                 stats.data_ptr(), _stream()))
     _count(2)
+    if reduce is not None:
+        stats = reduce(stats)
     return _finish_stats(stats)
 
 

@@ -295,10 +295,14 @@ def rel_l1(cur, prev):
     return ((cur - prev).abs().mean() / prev.abs().mean()).item()
 
 
-def residual_stats(r_cur, r_prev, denom_eps=0.0):
-    from oracle.controller_ref import calibration_stats
-    _count(2)
-    return calibration_stats(r_cur.to(F32)[None], r_prev.to(F32)[None], denom_eps)
+def residual_stats(r_cur, r_prev, denom_eps=0.0, reduce=None):
+    if reduce is None:
+        from oracle.controller_ref import calibration_stats
+        _count(2)
+        return calibration_stats(r_cur.to(F32)[None], r_prev.to(F32)[None], denom_eps)
+    # token-sharded caller: the kernel's four raw sums over this rank's rows, reduced, then finalised like ops._finish_stats
+    zero = torch.zeros_like(r_cur, dtype=BF)
+    return residual_sub_stats(r_cur.to(F32), zero, r_prev, denom_eps, reduce)[1]
 
 
 def residual_sub_stats(x_out, x_in, r_prev, denom_eps=0.0, reduce=None):

@@ -65,7 +65,21 @@ def _worker(rank, world, initfile, results, family):
         errs = [float((a.float() - b.float()).abs().max() / b.float().abs().max()) for a, b in zip(outs["sharded"][0], outs["single"][0])]
         full_res, loc_res = outs["single"][1].res, eng.res
         res_err = float((loc_res.float() - full_res[eng.shard.start:eng.shard.stop].float()).abs().max() / full_res.float().abs().max())
-        results[rank] = (errs, res_err, eng.n_img, eng.n_img_total, eng.S_keys)
+        # calibration twin (magcache_flux.py:21-231 / magcache_sample_video.py:163-290) on the sharded engine: the three statistics are
+        # sums over the image tokens, so the ranks' partial sums are added before they are finalised — same lists as one engine
+        cal = {}
+        for name in ("single", "sharded"):
+            m = copy.deepcopy(model)
+            m.__class__ = type("C_" + name, (m.__class__,), {})
+            (mc.init_magcache_flux_calibration if family == "flux" else mc.init_magcache_hunyuan_calibration)(m, 5)
+            type(m).calibration_dir = None
+            if name == "sharded":
+                mc.enable_token_shard(m, rank, world)
+            with torch.no_grad():
+                for i in range(4):
+                    call(m, i)
+            cal[name] = [list(getattr(m, k)) for k in ("norm_ratio", "norm_std", "cos_dis")]
+        results[rank] = (errs, res_err, eng.n_img, eng.n_img_total, eng.S_keys, cal)
     finally:
         dist.destroy_process_group()
 
@@ -78,7 +92,10 @@ def test_sharded_mmdit_engine_equals_single_world2(family):
         mp.spawn(_worker, args=(2, os.path.join(d, "init"), results, family), nprocs=2, join=True)
         assert set(results.keys()) == {0, 1}
         for r in (0, 1):
-            errs, res_err, n_loc, n_tot, s_keys = results[r]
+            errs, res_err, n_loc, n_tot, s_keys, cal = results[r]
+            assert all(len(v) == 3 for v in cal["single"]) and all(len(v) == 3 for v in cal["sharded"]), cal
+            for a, b in zip(sum(cal["sharded"], []), sum(cal["single"], [])):
+                assert abs(a - b) <= 2e-2 * abs(b) + 2e-3, cal
             assert n_loc * 2 == n_tot == 48 and s_keys == 48 + (19 if family == "flux" else 11)
             assert len(errs) == 6 and max(errs) < 1.2e-2, errs   # bf16 streams: a different GEMM row blocking flips roundings
             assert res_err < 3e-2
